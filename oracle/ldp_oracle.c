@@ -1,0 +1,441 @@
+/* TEST INFRASTRUCTURE ONLY -- see ldp_oracle.h for scope, provenance and parity status.
+ *
+ * Plain C, double precision, explicit fma() in a fixed summation order so that a
+ * sequential GPU implementation of the same rules can be compared bit for bit.
+ *
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -pthread -fPIC -shared (see Makefile).
+ */
+#include "ldp_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+typedef struct {
+  int k;          /* working-set size */
+  int sing;       /* last added row is dependent (D[k-1] == 0) */
+  int32_t *ws;    /* row index per position */
+  int8_t *side;   /* +1 upper, -1 lower */
+  double *lam, *lams, *L, *D, *z, *y, *u, *dup, *dlo;
+  uint8_t *inws;  /* m flags */
+} work_t;
+
+static work_t *work_new(const orc_problem *p) {
+  int n = p->n, m = p->m, cap = n + 1;
+  work_t *w = (work_t *)calloc(1, sizeof(work_t));
+  w->ws = (int32_t *)calloc(cap, sizeof(int32_t));
+  w->side = (int8_t *)calloc(cap, 1);
+  w->lam = (double *)calloc(cap, sizeof(double));
+  w->lams = (double *)calloc(cap, sizeof(double));
+  w->L = (double *)calloc((size_t)cap * (cap + 1) / 2, sizeof(double));
+  w->D = (double *)calloc(cap, sizeof(double));
+  w->z = (double *)calloc(cap, sizeof(double));
+  w->y = (double *)calloc(cap, sizeof(double));
+  w->u = (double *)calloc(n, sizeof(double));
+  w->dup = (double *)calloc(m, sizeof(double));
+  w->dlo = (double *)calloc(m, sizeof(double));
+  w->inws = (uint8_t *)calloc(m, 1);
+  return w;
+}
+static void work_free(work_t *w) {
+  free(w->ws); free(w->side); free(w->lam); free(w->lams); free(w->L); free(w->D);
+  free(w->z); free(w->y); free(w->u); free(w->dup); free(w->dlo); free(w->inws); free(w);
+}
+static void work_reset(const orc_problem *p, work_t *w) {
+  w->k = 0; w->sing = 0;
+  memset(w->inws, 0, (size_t)p->m);
+  memset(w->u, 0, sizeof(double) * (size_t)p->n);
+}
+
+/* packed unit-lower L: row i holds its i sub-diagonal entries at offset i(i-1)/2 */
+#define LROW(w, i) ((w)->L + ((size_t)(i) * ((i) - 1)) / 2)
+
+/* mpc_update_qp (codegen/mpc_update_qp.c:1-10): d = d0 + Dth theta */
+static void update_bounds(const orc_problem *p, const double *th, work_t *w, double *fl) {
+  for (int j = 0; j < p->m; ++j) {
+    double acc = 0.0;
+    const double *row = p->Dth + (size_t)j * p->nth;
+    for (int t = 0; t < p->nth; ++t) acc = fma(row[t], th[t], acc);
+    w->dup[j] = p->du[j] + acc;
+    w->dlo[j] = p->dl[j] + acc;
+  }
+  if (fl) *fl += 2.0 * p->m * p->nth;
+}
+
+/* append row `j` (side s) to the factorisation; SURVEY Appendix A "LDL-add" */
+static void ldl_add(const orc_problem *p, work_t *w, int j, int s, double *fl) {
+  int k = w->k;
+  double *lrow = LROW(w, k);
+  const double *g = p->Gram + (size_t)j * p->m;
+  double dnew = g[j];
+  if (p->sense[j] & ORC_SOFT) dnew += p->rho_soft;
+  for (int i = 0; i < k; ++i) {
+    double yi = g[w->ws[i]];
+    const double *li = LROW(w, i);
+    for (int c = 0; c < i; ++c) yi = fma(-li[c], w->y[c], yi);
+    w->y[i] = yi;
+  }
+  for (int i = 0; i < k; ++i) {
+    double l = w->y[i] / w->D[i];
+    lrow[i] = l;
+    dnew = fma(-w->y[i], l, dnew);
+  }
+  w->ws[k] = j; w->side[k] = (int8_t)s; w->lam[k] = 0.0; w->inws[j] = 1;
+  if (dnew < p->zero_tol) { w->sing = 1; dnew = 0.0; }
+  w->D[k] = dnew;
+  w->k = k + 1;
+  if (fl) *fl += (double)k * k + 3.0 * k;
+}
+
+/* delete position r; rank-one update of the trailing block (Gill et al. C1) */
+static void ldl_remove(const orc_problem *p, work_t *w, int r, double *fl) {
+  int k = w->k;
+  double alpha = w->D[r];
+  double *wv = w->y; /* scratch: column r below the diagonal */
+  for (int i = r + 1; i < k; ++i) wv[i] = LROW(w, i)[r];
+  /* shift rows up / columns left */
+  for (int i = r + 1; i < k; ++i) {
+    double *src = LROW(w, i), *dst = LROW(w, i - 1);
+    for (int c = 0; c < r; ++c) dst[c] = src[c];
+    for (int c = r + 1; c < i; ++c) dst[c - 1] = src[c];
+    w->D[i - 1] = w->D[i];
+    wv[i - 1] = wv[i];
+    w->ws[i - 1] = w->ws[i]; w->side[i - 1] = w->side[i]; w->lam[i - 1] = w->lam[i];
+  }
+  k -= 1;
+  for (int j = r; j < k; ++j) {
+    double pj = wv[j];
+    double t = alpha * pj;
+    double dbar = fma(t, pj, w->D[j]);
+    double beta = t / dbar;
+    alpha = (w->D[j] * alpha) / dbar;
+    w->D[j] = dbar;
+    for (int i = j + 1; i < k; ++i) {
+      double *li = LROW(w, i);
+      wv[i] = fma(-pj, li[j], wv[i]);
+      li[j] = fma(beta, wv[i], li[j]);
+    }
+  }
+  w->k = k;
+  w->sing = 0;
+  if (k > 0 && w->D[k - 1] < p->zero_tol) { w->sing = 1; w->D[k - 1] = 0.0; }
+  if (fl) *fl += 3.0 * (k - r) * (k - r) + 2.0 * k;
+}
+
+static void remove_pos(const orc_problem *p, work_t *w, int r, double *fl) {
+  w->inws[w->ws[r]] = 0;
+  ldl_remove(p, w, r, fl);
+}
+
+/* the dual active-set loop */
+static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *soft_slack_out,
+                    double *fl) {
+  const int n = p->n, m = p->m;
+  int flag = ORC_ITERLIMIT, iter, cycle = 0;
+  double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
+  for (iter = 1; iter < p->iter_limit; ++iter) {
+    int k = w->k, nblock = 0;
+    if (!w->sing) {
+      /* 1. CSP: L D L' lam* = -d_W */
+      for (int i = 0; i < k; ++i) {
+        int j = w->ws[i];
+        double zi = -(w->side[i] > 0 ? w->dup[j] : w->dlo[j]);
+        const double *li = LROW(w, i);
+        for (int c = 0; c < i; ++c) zi = fma(-li[c], w->z[c], zi);
+        w->z[i] = zi;
+      }
+      for (int i = 0; i < k; ++i) w->lams[i] = w->z[i] / w->D[i];
+      for (int jx = k - 1; jx > 0; --jx) {
+        const double *lj = LROW(w, jx);
+        double xj = w->lams[jx];
+        for (int i = 0; i < jx; ++i) w->lams[i] = fma(-lj[i], xj, w->lams[i]);
+      }
+      if (fl) *fl += 2.0 * k * k;
+      /* 2. blocking set */
+      for (int i = 0; i < k; ++i) {
+        if (p->sense[w->ws[i]] & ORC_IMMUTABLE) continue;
+        if (w->side[i] > 0 ? (w->lams[i] < -p->dual_tol) : (w->lams[i] > p->dual_tol)) nblock++;
+      }
+      if (nblock == 0) {
+        /* 3. primal iterate, objective, most violated row */
+        for (int c = 0; c < n; ++c) w->u[c] = 0.0;
+        for (int i = 0; i < k; ++i) {
+          const double *mr = p->Mbar + (size_t)w->ws[i] * n;
+          double li = w->lams[i];
+          for (int c = 0; c < n; ++c) w->u[c] = fma(-li, mr[c], w->u[c]);
+        }
+        fval = 0.0; soft_slack = 0.0;
+        for (int c = 0; c < n; ++c) fval = fma(w->u[c], w->u[c], fval);
+        for (int i = 0; i < k; ++i)
+          if (p->sense[w->ws[i]] & ORC_SOFT) {
+            fval = fma(p->rho_soft * w->lams[i], w->lams[i], fval);
+            double sl = p->rho_soft * fabs(w->lams[i]);
+            if (sl > soft_slack) soft_slack = sl;
+          }
+        if (fl) *fl += 2.0 * k * n + 2.0 * n;
+        if (fval > p->fval_bound) { flag = ORC_INFEASIBLE; break; }
+        double best = -p->primal_tol;
+        int add = -1, addside = 0;
+        for (int j = 0; j < m; ++j) {
+          if (w->inws[j] || (p->sense[j] & ORC_IMMUTABLE)) continue;
+          const double *mr = p->Mbar + (size_t)j * n;
+          double mu = 0.0;
+          for (int c = 0; c < n; ++c) mu = fma(mr[c], w->u[c], mu);
+          double su = w->dup[j] - mu;
+          if (su < best) { best = su; add = j; addside = 1; }
+          else {
+            double sl = mu - w->dlo[j];
+            if (sl < best) { best = sl; add = j; addside = -1; }
+          }
+        }
+        if (fl) *fl += 2.0 * n * (m - k);
+        if (add < 0) { flag = soft_slack > p->primal_tol ? ORC_SOFT_OPTIMAL : ORC_OPTIMAL; break; }
+        for (int i = 0; i < k; ++i) w->lam[i] = w->lams[i];
+        ldl_add(p, w, add, addside, fl);
+        continue;
+      }
+      /* 4. blocking: cycle guard, ratio test, remove */
+      if (fval - p->progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+      else if (cycle++ > p->cycle_tol) { flag = ORC_CYCLE; break; }
+      double alpha = INFINITY; int rm = -1;
+      for (int i = 0; i < k; ++i) {
+        if (p->sense[w->ws[i]] & ORC_IMMUTABLE) continue;
+        if (!(w->side[i] > 0 ? (w->lams[i] < -p->dual_tol) : (w->lams[i] > p->dual_tol))) continue;
+        double a = -w->lam[i] / (w->lams[i] - w->lam[i]);
+        if (a < alpha) { alpha = a; rm = i; }
+      }
+      for (int i = 0; i < k; ++i) w->lam[i] = fma(alpha, w->lams[i] - w->lam[i], w->lam[i]);
+      if (fl) *fl += 3.0 * k;
+      remove_pos(p, w, rm, fl);
+    } else {
+      /* 5. singular: direction p = s [-L^-T l ; 1] on the first k-1 rows */
+      int kk = k - 1;
+      const double *ll = LROW(w, kk);
+      for (int i = 0; i < kk; ++i) w->lams[i] = -ll[i];
+      for (int jx = kk - 1; jx > 0; --jx) {
+        const double *lj = LROW(w, jx);
+        double xj = w->lams[jx];
+        for (int i = 0; i < jx; ++i) w->lams[i] = fma(-lj[i], xj, w->lams[i]);
+      }
+      w->lams[kk] = 1.0;
+      if (w->side[kk] < 0) for (int i = 0; i <= kk; ++i) w->lams[i] = -w->lams[i];
+      if (fl) *fl += (double)kk * kk;
+      double alpha = INFINITY; int rm = -1;
+      for (int i = 0; i < k; ++i) {
+        if (p->sense[w->ws[i]] & ORC_IMMUTABLE) continue;
+        if (!(w->side[i] > 0 ? (w->lams[i] < -p->dual_tol) : (w->lams[i] > p->dual_tol))) continue;
+        double a = -w->lam[i] / w->lams[i];
+        if (a < alpha) { alpha = a; rm = i; }
+      }
+      if (rm < 0) { flag = ORC_INFEASIBLE; break; }
+      for (int i = 0; i < k; ++i) w->lam[i] = fma(alpha, w->lams[i], w->lam[i]);
+      if (fl) *fl += 3.0 * k;
+      remove_pos(p, w, rm, fl);
+    }
+  }
+  *iters = iter;
+  if (soft_slack_out) *soft_slack_out = soft_slack;
+  return flag;
+}
+
+/* cold start: working set = equality rows (ACTIVE bit), SURVEY Appendix A "Start state" */
+static int activate_equalities(const orc_problem *p, work_t *w) {
+  for (int j = 0; j < p->m; ++j)
+    if (p->sense[j] & ORC_ACTIVE) {
+      ldl_add(p, w, j, (p->sense[j] & ORC_LOWER) ? -1 : 1, NULL);
+      if (w->sing) return ORC_OVERDETERMINED;
+    }
+  return 0;
+}
+
+/* mpc_get_solution (codegen/mpc_update_qp.c:14-22) with x = R^-1 u (ldp2qp_solution) */
+static void get_solution(const orc_problem *p, const double *th, const work_t *w, double *ctl,
+                         double *fl) {
+  for (int i = 0; i < p->nu; ++i) {
+    const double *rr = p->Rinv + (size_t)i * p->n;
+    double x = 0.0;
+    for (int c = i; c < p->n; ++c) x = fma(rr[c], w->u[c], x);
+    double sh = p->uoff[i];
+    const double *ur = p->Uth + (size_t)i * p->nth;
+    for (int t = 0; t < p->nth; ++t) sh = fma(ur[t], th[t], sh);
+    ctl[i] = x + sh;
+  }
+  if (fl) *fl += (double)p->nu * (2 * p->n - p->nu + 1) + 2.0 * p->nu * p->nth;
+}
+
+static int solve_with(const orc_problem *p, work_t *w, const double *th, double *ctl,
+                      int32_t *iters, uint64_t *au, uint64_t *al, double *fl, int cold) {
+  int flag = 0, it = 0;
+  update_bounds(p, th, w, fl);
+  if (cold) {
+    work_reset(p, w);
+    flag = activate_equalities(p, w);
+  }
+  if (flag == 0) flag = ldp_loop(p, w, &it, NULL, fl);
+  get_solution(p, th, w, ctl, fl);
+  if (iters) *iters = it;
+  int words = (p->m + 63) / 64;
+  if (au) memset(au, 0, sizeof(uint64_t) * words);
+  if (al) memset(al, 0, sizeof(uint64_t) * words);
+  for (int i = 0; i < w->k; ++i) {
+    int j = w->ws[i];
+    if (w->side[i] > 0) { if (au) au[j >> 6] |= 1ull << (j & 63); }
+    else if (al) al[j >> 6] |= 1ull << (j & 63);
+  }
+  return flag;
+}
+
+int orc_solve(const orc_problem *p, const double *theta, double *u, int32_t *iters,
+              uint64_t *act_u, uint64_t *act_l, double *flops) {
+  work_t *w = work_new(p);
+  if (flops) *flops = 0.0;
+  int flag = solve_with(p, w, theta, u, iters, act_u, act_l, flops, 1);
+  work_free(w);
+  return flag;
+}
+
+int orc_num_threads(void) {
+  long c = sysconf(_SC_NPROCESSORS_ONLN);
+  return c > 0 ? (int)c : 1;
+}
+
+/* static contiguous chunks over pthreads (one workspace per thread) */
+typedef void (*chunk_fn)(void *ctx, int64_t lo, int64_t hi);
+typedef struct { chunk_fn fn; void *ctx; int64_t lo, hi; } chunk_t;
+static void *chunk_tramp(void *a) { chunk_t *c = (chunk_t *)a; c->fn(c->ctx, c->lo, c->hi); return NULL; }
+static void parallel_for(int64_t N, int nthreads, chunk_fn fn, void *ctx) {
+  if (nthreads <= 0) nthreads = orc_num_threads();
+  if (nthreads > N) nthreads = N > 0 ? (int)N : 1;
+  if (nthreads <= 1) { fn(ctx, 0, N); return; }
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  chunk_t *ch = (chunk_t *)malloc(sizeof(chunk_t) * nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    ch[t].fn = fn; ch[t].ctx = ctx;
+    ch[t].lo = N * t / nthreads; ch[t].hi = N * (t + 1) / nthreads;
+    pthread_create(&th[t], NULL, chunk_tramp, &ch[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  free(th); free(ch);
+}
+
+typedef struct {
+  const orc_problem *p; const double *Theta; double *U;
+  int32_t *flag, *iters; uint64_t *au, *al; double *flops;
+} batch_ctx;
+static void batch_chunk(void *vc, int64_t lo, int64_t hi) {
+  batch_ctx *c = (batch_ctx *)vc;
+  const orc_problem *p = c->p;
+  int words = (p->m + 63) / 64;
+  work_t *w = work_new(p);
+  for (int64_t q = lo; q < hi; ++q) {
+    double fl = 0.0;
+    int32_t it = 0;
+    int f = solve_with(p, w, c->Theta + q * p->nth, c->U + q * p->nu, &it,
+                       c->au ? c->au + q * words : NULL, c->al ? c->al + q * words : NULL,
+                       c->flops ? &fl : NULL, 1);
+    if (c->flag) c->flag[q] = f;
+    if (c->iters) c->iters[q] = it;
+    if (c->flops) c->flops[q] = fl;
+  }
+  work_free(w);
+}
+void orc_solve_batch(const orc_problem *p, const double *Theta, int64_t N, double *U,
+                     int32_t *flag, int32_t *iters, uint64_t *act_u, uint64_t *act_l,
+                     double *flops, int nthreads) {
+  batch_ctx c = {p, Theta, U, flag, iters, act_u, act_l, flops};
+  parallel_for(N, nthreads, batch_chunk, &c);
+}
+
+typedef struct {
+  const orc_problem *p; int nx, nr, nd, nuprev; const double *Fx, *Gx, *Gdx, *X0, *R, *D, *U0;
+  int T, warm; double *Xend, *Ulast, *Utraj; int32_t *flag, *iters;
+} sim_ctx;
+static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
+  sim_ctx *s = (sim_ctx *)vc;
+  const orc_problem *p = s->p;
+  const int nu = p->nu, nth = p->nth, nx = s->nx, nr = s->nr, nd = s->nd, nuprev = s->nuprev;
+  work_t *w = work_new(p);
+  double *th = (double *)calloc(nth, sizeof(double));
+  double *x = (double *)calloc(nx, sizeof(double));
+  double *xn = (double *)calloc(nx, sizeof(double));
+  double *u = (double *)calloc(nu, sizeof(double));
+  for (int64_t q = lo; q < hi; ++q) {
+    int worst = ORC_OPTIMAL, tot = 0;
+    for (int i = 0; i < nx; ++i) x[i] = s->X0[q * nx + i];
+    for (int i = 0; i < nu; ++i) u[i] = (s->U0 && i < nuprev) ? s->U0[q * nuprev + i] : 0.0;
+    for (int t = 0; t < s->T; ++t) {
+      /* theta = [x; r; d; uprev] (explicit.jl:54-63) */
+      int o = 0;
+      for (int i = 0; i < nx; ++i) th[o++] = x[i];
+      for (int i = 0; i < nr; ++i) th[o++] = s->R ? s->R[q * nr + i] : 0.0;
+      for (int i = 0; i < nd; ++i) th[o++] = s->D ? s->D[q * nd + i] : 0.0;
+      for (int i = 0; i < nuprev; ++i) th[o++] = u[i];
+      int32_t it = 0;
+      int f = solve_with(p, w, th, u, &it, NULL, NULL, NULL, !(s->warm && t > 0));
+      tot += it;
+      if (f < 0) { if (worst > 0 || f < worst) worst = f; }
+      else if (worst > 0 && f > worst) worst = f;
+      if (s->Utraj) for (int i = 0; i < nu; ++i) s->Utraj[(q * s->T + t) * nu + i] = u[i];
+      /* x+ = F x + G u + Gd d (model.jl:70) */
+      for (int i = 0; i < nx; ++i) {
+        double acc = 0.0;
+        for (int c = 0; c < nx; ++c) acc = fma(s->Fx[i * nx + c], x[c], acc);
+        for (int c = 0; c < nu; ++c) acc = fma(s->Gx[i * nu + c], u[c], acc);
+        for (int c = 0; c < nd; ++c) acc = fma(s->Gdx[i * nd + c], s->D ? s->D[q * nd + c] : 0.0, acc);
+        xn[i] = acc;
+      }
+      for (int i = 0; i < nx; ++i) x[i] = xn[i];
+    }
+    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = x[i];
+    for (int i = 0; i < nu; ++i) s->Ulast[q * nu + i] = u[i];
+    if (s->flag) s->flag[q] = worst;
+    if (s->iters) s->iters[q] = tot;
+  }
+  free(th); free(x); free(xn); free(u);
+  work_free(w);
+}
+void orc_simulate_batch(const orc_problem *p, int nx, int nr, int nd, int nuprev,
+                        const double *Fx, const double *Gx, const double *Gdx,
+                        const double *X0, const double *R, const double *D, const double *U0,
+                        int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
+                        int32_t *flag, int32_t *iters, int nthreads) {
+  sim_ctx s = {p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, T, warm, Xend, Ulast, Utraj, flag, iters};
+  parallel_for(N, nthreads, sim_chunk, &s);
+}
+
+typedef struct { const orc_bst *t; const double *Theta; double *U; int32_t *region; } bst_ctx;
+static void bst_chunk(void *vc, int64_t lo, int64_t hi) {
+  bst_ctx *b = (bst_ctx *)vc;
+  const orc_bst *t = b->t;
+  const int nth = t->nth, nu = t->nu, ld = nth + 1;
+  for (int64_t q = lo; q < hi; ++q) {
+    const double *th = b->Theta + q * nth;
+    int id = 0;
+    for (;;) {
+      int jmp = t->jump_list[id];
+      if (jmp == 0) break;
+      const double *hp = t->halfplanes + (size_t)t->hp_list[id] * ld;
+      double acc = 0.0;
+      for (int c = 0; c < nth; ++c) acc = fma(hp[c], th[c], acc);
+      id = id + jmp + (acc <= hp[nth] ? 0 : 1);
+    }
+    int reg = t->hp_list[id];
+    const double *fb = t->feedbacks + (size_t)reg * nu * ld;
+    for (int i = 0; i < nu; ++i) {
+      double acc = fb[i * ld + nth];
+      for (int c = 0; c < nth; ++c) acc = fma(fb[i * ld + c], th[c], acc);
+      if (t->clip) {
+        if (acc < t->clip[2 * i]) acc = t->clip[2 * i];
+        if (acc > t->clip[2 * i + 1]) acc = t->clip[2 * i + 1];
+      }
+      b->U[q * nu + i] = acc;
+    }
+    if (b->region) b->region[q] = reg;
+  }
+}
+void orc_bst_evaluate_batch(const orc_bst *t, const double *Theta, int64_t N, double *U,
+                            int32_t *region, int nthreads) {
+  bst_ctx b = {t, Theta, U, region};
+  parallel_for(N, nthreads, bst_chunk, &b);
+}
