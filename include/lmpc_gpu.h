@@ -1,0 +1,199 @@
+/* lmpc_gpu.h -- C ABI of liblmpcgpu.so: batched evaluation of a condensed linear-MPC law
+ * on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of LinearMPC.jl: theta -> (affine QP update)
+ * -> DAQP dual active-set solve -> u, and the ExplicitMPC point-location alternative.
+ * Each entry point names the reference interface it replaces.  All matrices cross the
+ * ABI COLUMN-MAJOR (Julia's native layout) unless stated; all pointers are plain
+ * double/int32/uint64 arrays owned by the caller.  Batched arrays hold one instance per
+ * COLUMN (Theta is nth x N, U is nu x N), so instance q is contiguous.
+ *
+ * Pointers passed to the *_batch calls may be host or device pointers (detected with
+ * cudaPointerGetAttributes).  Host buffers are staged through the handle's pinned/device
+ * scratch inside the call; device buffers are used in place on the handle's stream.
+ *
+ * Return value of every function: 0 on success, negative LMPC_E_* on API failure
+ * (never an exception).  Per-instance solver status uses DAQP's exit-flag integers
+ * (reference: src/setup.jl:15-20, src/utils.jl:46).
+ */
+#ifndef LMPC_GPU_H
+#define LMPC_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-instance exit flags (DAQP convention) */
+#define LMPC_EXIT_OPTIMAL          1
+#define LMPC_EXIT_SOFT_OPTIMAL     2
+#define LMPC_EXIT_INFEASIBLE     (-1)
+#define LMPC_EXIT_CYCLE          (-2)
+#define LMPC_EXIT_UNBOUNDED      (-3)
+#define LMPC_EXIT_ITERLIMIT      (-4)
+#define LMPC_EXIT_NONCONVEX      (-5)
+#define LMPC_EXIT_OVERDETERMINED (-6)
+#define LMPC_EXIT_CAPACITY       (-7)  /* working set outgrew the kernel's on-chip capacity */
+
+/* API-level errors */
+#define LMPC_E_INVALID    (-100)  /* bad argument / dimension */
+#define LMPC_E_UNSUPPORTED (-101) /* binaries, non-symmetric H (AVI), hierarchical break points */
+#define LMPC_E_SETUP      (-102)  /* Cholesky failed (setup flag -5) or zero row */
+#define LMPC_E_CUDA       (-103)  /* CUDA runtime error; see lmpc_gpu_last_error() */
+#define LMPC_E_NOGPU      (-104)  /* no usable sm_100 device: there is NO CPU fallback */
+
+/* constraint sense bits (DAQPBase constants, set at src/mpc2mpqp.jl:868-885) */
+#define LMPC_ACTIVE 1
+#define LMPC_LOWER 2
+#define LMPC_IMMUTABLE 4
+#define LMPC_SOFT 8
+#define LMPC_BINARY 16
+
+/* kernel selection (LMPC_KERNEL_AUTO picks by n: <=8 thread-per-QP, <=32 warp-per-QP, else CTA-per-QP) */
+#define LMPC_KERNEL_AUTO 0
+#define LMPC_KERNEL_THREAD 1
+#define LMPC_KERNEL_WARP 2
+#define LMPC_KERNEL_CTA 3
+
+typedef struct lmpc_handle lmpc_handle;   /* one implicit controller on one GPU */
+typedef struct lmpc_bst lmpc_bst;         /* one explicit controller (search tree) on one GPU */
+
+/* The dense mpQP exactly as LinearMPC.MPQP holds it (src/types.jl:75-98) plus the
+ * runtime fields of MPC the path reads (src/types.jl:108-160: K, settings.soft_weight). */
+typedef struct {
+  int32_t n;        /* decision variables                      size(H,1)            */
+  int32_t m;        /* two-sided rows                          length(bu)           */
+  int32_t ms;       /* leading simple bounds                   m - size(A,1)        */
+  int32_t nth;      /* parameter length                        size(f_theta,2)      */
+  int32_t nu;       /* controls returned (first nu variables)  mpc.model.nu         */
+  int32_t nx;       /* leading theta entries K multiplies      mpc.model.nx         */
+  const double *H;        /* n x n                                                  */
+  const double *f;        /* n                                                      */
+  const double *f_theta;  /* n x nth                                                */
+  const double *A;        /* (m-ms) x n                                             */
+  const double *bu;       /* m   (+-1e30 = infinite, src/mpc2mpqp.jl:887-888)       */
+  const double *bl;       /* m                                                      */
+  const double *W;        /* m x nth                                                */
+  const int32_t *senses;  /* m                                                      */
+  const double *K;        /* nu x nx prestabilising feedback, NULL = 0              */
+  double soft_weight;     /* mpc.settings.soft_weight; rho_soft = 1/soft_weight (src/setup.jl:26) */
+  int32_t has_binaries;   /* MPQP.has_binaries   -> refused                         */
+  int32_t is_symmetric;   /* MPQP.is_symmetric   -> 0 refused                       */
+  int32_t n_break_points; /* length(break_points) -> >0 refused                     */
+} lmpc_problem;
+
+/* DAQP settings used by the loop (docs/src/manual/solver.md:49-56); zero-initialise
+ * and call lmpc_gpu_default_settings() to get the defaults. */
+typedef struct {
+  double primal_tol;    /* 1e-6  on normalised slacks */
+  double dual_tol;      /* 1e-12 */
+  double zero_tol;      /* 1e-11 pivot below which an added row is treated as dependent */
+  double progress_tol;  /* 1e-6  */
+  double fval_bound;    /* 1e30  */
+  int32_t cycle_tol;    /* 10    */
+  int32_t iter_limit;   /* 10000 */
+  int32_t kernel;       /* LMPC_KERNEL_* */
+  int32_t reserved;
+} lmpc_settings;
+
+void lmpc_gpu_default_settings(lmpc_settings *s);
+const char *lmpc_gpu_last_error(void);
+int lmpc_gpu_device_count(void);
+
+/* Replaces setup!(mpc) -> DAQP.setup (src/setup.jl:7-29) and qp2ldp
+ * (src/codegen.jl:239-280): Cholesky, R^-1, M = A R^-1, row normalisation, the
+ * theta-absorbed bounds Dth/du/dl and the output map; uploads them once to `device`. */
+int lmpc_gpu_create(const lmpc_problem *p, const lmpc_settings *s, int device, lmpc_handle **out);
+int lmpc_gpu_destroy(lmpc_handle *h);
+
+/* Read back the LDP constants the handle computed (row-major, as generated C stores
+ * them, src/codegen.jl:275): Mbar m x n, Gram m x m (= Mbar Mbar'), Dth m x nth, du m, dl m,
+ * Rinv nu x n, Uth nu x nth, uoff nu.  Any pointer may be NULL.  Lets a caller (and the
+ * parity tests) check the setup step against qp2ldp. */
+int lmpc_gpu_get_ldp(const lmpc_handle *h, double *Mbar, double *Gram, double *Dth, double *du,
+                     double *dl, double *Rinv, double *Uth, double *uoff);
+/* The same constants straight from a problem description, host only (no GPU touched, no
+ * handle): the once-per-controller setup step in isolation.  senses m, cap 1 (nullable). */
+int lmpc_gpu_host_ldp(const lmpc_problem *p, double *Mbar, double *Gram, double *Dth, double *du,
+                      double *dl, double *Rinv, double *Uth, double *uoff, int32_t *senses,
+                      int32_t *cap);
+/* which kernel create() selected (LMPC_KERNEL_*), the working-set capacity it provisions,
+ * and the effective sense bits (m; zero rows are marked IMMUTABLE).  Pointers may be NULL. */
+int lmpc_gpu_get_info(const lmpc_handle *h, int32_t *kernel, int32_t *cap, int32_t *senses);
+
+/* Replaces solve(mpc, theta) + the compute_control epilogue (src/utils.jl:43-51,268-283)
+ * for N parameters at once.  Theta nth x N; U nu x N receives z[1:nu] - K theta[1:nx];
+ * exitflag N; iters N (nullable); active_upper/active_lower ceil(m/64) words per
+ * instance, bit j of word j/64 = row j active at its upper/lower bound (nullable).
+ * Cold start per instance (as the generated C without DAQP_WARMSTART,
+ * codegen/mpc_update_qp.c:44-47). */
+int lmpc_gpu_solve_batch(lmpc_handle *h, const double *Theta, int64_t N, double *U,
+                         int32_t *exitflag, int32_t *iters,
+                         uint64_t *active_upper, uint64_t *active_lower);
+
+/* Same, device pointers only, asynchronous on `stream` (a cudaStream_t, NULL = the
+ * handle's own stream); the caller synchronises. */
+int lmpc_gpu_solve_batch_async(lmpc_handle *h, const double *Theta, int64_t N, double *U,
+                               int32_t *exitflag, int32_t *iters,
+                               uint64_t *active_upper, uint64_t *active_lower, void *stream);
+
+/* Batched analogue of the generated mpc_compute_control(control, state, reference,
+ * disturbance) (codegen/mpc_update_qp.h:3-7, mpc_update_parameter.c:1-29): theta is
+ * assembled on the fly as [state; reference; disturbance; control] with
+ * nx + nr + nd + nuprev = nth; `control` (nu x N) is in/out: it holds u_prev on entry
+ * (first nuprev rows are read) and the new control on return.  reference/disturbance
+ * may be NULL when nr/nd is 0.  Returns per-instance exit flags in `exitflag`. */
+int lmpc_gpu_compute_control_batch(lmpc_handle *h, double *control, const double *state,
+                                   const double *reference, const double *disturbance,
+                                   int32_t nr, int32_t nd, int32_t nuprev, int64_t N,
+                                   int32_t *exitflag);
+
+/* Replaces N independent copies of the Simulation loop (src/simulation.jl:93-113) with the
+ * default linear dynamics x+ = F x + G u + Gd d (src/model.jl:70): T steps of
+ * compute_control + dynamics, entirely on the GPU.  F nx x nx, G nx x nu, Gd nx x nd
+ * column-major.  X0 nx x N; R nr x N and D nd x N are held constant over the horizon;
+ * U0 nuprev x N (NULL = 0).  warm_start != 0 carries the working set between steps (the
+ * Julia path's behaviour); 0 cold-starts every step (generated C default).
+ * Outputs: Xend nx x N, Ulast nu x N, Utraj nu x T x N (nullable), exitflag N = worst
+ * flag over the T steps, iters N = total iterations (nullable). */
+int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                            int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                            const double *X0, const double *R, const double *D, const double *U0,
+                            int64_t N, int32_t T, int32_t warm_start,
+                            double *Xend, double *Ulast, double *Utraj,
+                            int32_t *exitflag, int32_t *iters);
+
+/* Replaces ParametricDAQP.build_tree's result as used by compute_control(empc, ...)
+ * (src/utils.jl:53-60, src/explicit.jl:65-71).  halfplanes (nth+1) x n_hp column-major
+ * (column h = [a_h; b_h]); feedbacks n_fb blocks of (nth+1) x nu column-major (u = F'[theta;1]);
+ * hp_list / jump_list n_nodes (0-based here): at node i, jump_list[i] == 0 marks a leaf whose
+ * region is hp_list[i]; otherwise next = i + jump_list[i] and the walk goes to `next` if
+ * a'theta <= b for halfplane hp_list[i], else to next+1.  clipping nu x 2 column-major
+ * [min max] or NULL. */
+int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *feedbacks,
+                        int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
+                        int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
+                        int device, lmpc_bst **out);
+int lmpc_gpu_destroy_bst(lmpc_bst *t);
+/* Replaces ParametricDAQP.evaluate(bst, theta) (src/utils.jl:57) / {fname}_evaluate
+ * (src/codegen.jl:113-124) for N parameters.  region (nullable) receives the leaf's region id. */
+int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double *U,
+                            int32_t *region);
+int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, double *U,
+                                  int32_t *region, void *stream);
+
+/* Measurement helpers used by bench.py (not part of the reference's interface):
+ * sustained FP64 FMA throughput of the device in TFLOP/s, and the stream of a handle. */
+int lmpc_gpu_fp64_peak(int device, double *tflops);
+void *lmpc_gpu_stream(lmpc_handle *h);
+/* number of kernel launches this library has issued in this process (for bench's gpu_launches) */
+int64_t lmpc_gpu_launch_count(void);
+/* pinned host memory for callers that want DMA-speed staging of Theta / U (cudaHostAlloc) */
+void *lmpc_gpu_host_alloc(size_t bytes);
+void lmpc_gpu_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMPC_GPU_H */

@@ -1,0 +1,574 @@
+// C ABI of liblmpcgpu.so (declared in include/lmpc_gpu.h).  Host-side plumbing only:
+// handle lifetime, constant upload, host<->device staging with a 3-slot copy/compute
+// pipeline, kernel selection.  There is NO CPU fallback: without an sm_100 device every
+// entry point fails with LMPC_E_NOGPU.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "lmpc_common.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int set_err(int code, const char *fmt, const char *detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define CUDA_OK(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) return set_err(LMPC_E_CUDA, #call ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return set_err(LMPC_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+constexpr int kSlots = 3;
+constexpr int64_t kChunk = 1 << 20;   // instances per pipeline stage for host buffers
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf in[4], u, flag, iters, au, al, aux[3];
+};
+
+bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int check_device(int device, int *sm_count) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    return set_err(LMPC_E_NOGPU, "no CUDA device visible: liblmpcgpu has no CPU fallback%s");
+  }
+  if (device < 0 || device >= cnt) return set_err(LMPC_E_INVALID, "device index out of range%s");
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_err(LMPC_E_NOGPU, "device is not sm_100 (B200): kernels are built for sm_100a only%s");
+  *sm_count = prop.multiProcessorCount;
+  return 0;
+}
+
+}  // namespace
+
+struct lmpc_handle {
+  int device = 0, sm_count = 148, kernel = 0;
+  LdpLayout lay;
+  LdpSettings st;
+  double *h_blk = nullptr;
+  double *d_blk = nullptr;
+  cudaStream_t stream = nullptr;
+  Slot slots[kSlots];
+  DevBuf dyn;   // F, G, Gd for simulate
+};
+
+struct lmpc_bst {
+  int device = 0, sm_count = 148;
+  BstDev dev;
+  double *d_blk = nullptr;
+  cudaStream_t stream = nullptr;
+  Slot slots[kSlots];
+};
+
+extern "C" {
+
+void lmpc_gpu_default_settings(lmpc_settings *s) {
+  if (!s) return;
+  s->primal_tol = 1e-6; s->dual_tol = 1e-12; s->zero_tol = 1e-11; s->progress_tol = 1e-6;
+  s->fval_bound = 1e30; s->cycle_tol = 10; s->iter_limit = 10000; s->kernel = LMPC_KERNEL_AUTO;
+  s->reserved = 0;
+}
+
+const char *lmpc_gpu_last_error(void) { return g_err; }
+
+int lmpc_gpu_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+
+int64_t lmpc_gpu_launch_count(void) { return g_launches.load(); }
+
+int lmpc_gpu_create(const lmpc_problem *p, const lmpc_settings *s, int device, lmpc_handle **out) {
+  if (!p || !out) return set_err(LMPC_E_INVALID, "lmpc_gpu_create: null argument%s");
+  *out = nullptr;
+  LdpHost hs;
+  char msg[256] = "";
+  int rc = lmpc_host_setup(p, &hs, msg, sizeof(msg));
+  if (rc != 0) return set_err(rc, "%s", msg);
+  int sm = 0;
+  rc = check_device(device, &sm);
+  if (rc != 0) { free(hs.blk); return rc; }
+  lmpc_settings def;
+  lmpc_gpu_default_settings(&def);
+  if (s) def = *s;
+  lmpc_handle *h = new lmpc_handle();
+  h->device = device; h->sm_count = sm; h->lay = hs.lay; h->h_blk = hs.blk;
+  h->st.primal_tol = def.primal_tol; h->st.dual_tol = def.dual_tol; h->st.zero_tol = def.zero_tol;
+  h->st.progress_tol = def.progress_tol; h->st.fval_bound = def.fval_bound;
+  h->st.rho_soft = 1.0 / (p->soft_weight > 0 ? p->soft_weight : 1e6);
+  h->st.cycle_tol = def.cycle_tol; h->st.iter_limit = def.iter_limit;
+  int kern = def.kernel;
+  if (kern == LMPC_KERNEL_AUTO) {
+    if (ldp_thread_supports(h->lay)) kern = LMPC_KERNEL_THREAD;
+    else if (ldp_warp_supports(h->lay)) kern = LMPC_KERNEL_WARP;
+    else if (ldp_cta_supports(h->lay)) kern = LMPC_KERNEL_CTA;
+    else kern = -1;
+  } else {
+    const bool ok = (kern == LMPC_KERNEL_THREAD && ldp_thread_supports(h->lay)) ||
+                    (kern == LMPC_KERNEL_WARP && ldp_warp_supports(h->lay)) ||
+                    (kern == LMPC_KERNEL_CTA && ldp_cta_supports(h->lay));
+    if (!ok) kern = -1;
+  }
+  if (kern < 0) {
+    free(hs.blk); delete h;
+    return set_err(LMPC_E_UNSUPPORTED, "no kernel supports these dimensions (n, m, capacity)%s");
+  }
+  h->kernel = kern;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void **)&h->d_blk, (size_t)h->lay.total * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(h->d_blk, h->h_blk, (size_t)h->lay.total * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    const char *es = cudaGetErrorString(cudaGetLastError());
+    lmpc_gpu_destroy(h);
+    return set_err(LMPC_E_CUDA, "lmpc_gpu_create: %s", es);
+  }
+  for (int i = 0; i < kSlots; ++i)
+    if (cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) {
+      lmpc_gpu_destroy(h);
+      return set_err(LMPC_E_CUDA, "cudaStreamCreate failed%s");
+    }
+  *out = h;
+  return 0;
+}
+
+static void free_slots(Slot *slots) {
+  for (int i = 0; i < kSlots; ++i) {
+    Slot &s = slots[i];
+    for (auto &b : s.in) b.release();
+    for (auto &b : s.aux) b.release();
+    s.u.release(); s.flag.release(); s.iters.release(); s.au.release(); s.al.release();
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s.stream = nullptr;
+  }
+}
+
+int lmpc_gpu_destroy(lmpc_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  free_slots(h->slots);
+  h->dyn.release();
+  if (h->d_blk) cudaFree(h->d_blk);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  free(h->h_blk);
+  delete h;
+  return 0;
+}
+
+int lmpc_gpu_get_ldp(const lmpc_handle *h, double *Mbar, double *Gram, double *Dth, double *du,
+                     double *dl, double *Rinv, double *Uth, double *uoff) {
+  if (!h) return set_err(LMPC_E_INVALID, "null handle%s");
+  const LdpLayout &l = h->lay;
+  const double *b = h->h_blk;
+  if (Mbar) memcpy(Mbar, b + l.oM, sizeof(double) * l.m * l.n);
+  if (Gram) memcpy(Gram, b + l.oG, sizeof(double) * l.m * l.m);
+  if (Dth) memcpy(Dth, b + l.oDth, sizeof(double) * l.m * l.nth);
+  if (du) memcpy(du, b + l.odu, sizeof(double) * l.m);
+  if (dl) memcpy(dl, b + l.odl, sizeof(double) * l.m);
+  if (Rinv) memcpy(Rinv, b + l.oRinv, sizeof(double) * l.nu * l.n);
+  if (Uth) memcpy(Uth, b + l.oUth, sizeof(double) * l.nu * l.nth);
+  if (uoff) memcpy(uoff, b + l.ouoff, sizeof(double) * l.nu);
+  return 0;
+}
+
+int lmpc_gpu_host_ldp(const lmpc_problem *p, double *Mbar, double *Gram, double *Dth, double *du,
+                      double *dl, double *Rinv, double *Uth, double *uoff, int32_t *senses,
+                      int32_t *cap) {
+  if (!p) return set_err(LMPC_E_INVALID, "null problem%s");
+  LdpHost hs;
+  char msg[256] = "";
+  int rc = lmpc_host_setup(p, &hs, msg, sizeof(msg));
+  if (rc != 0) return set_err(rc, "%s", msg);
+  lmpc_handle tmp;
+  tmp.lay = hs.lay; tmp.h_blk = hs.blk;
+  lmpc_gpu_get_ldp(&tmp, Mbar, Gram, Dth, du, dl, Rinv, Uth, uoff);
+  if (senses) memcpy(senses, hs.blk + hs.lay.oSense, sizeof(int32_t) * hs.lay.m);
+  if (cap) *cap = hs.lay.cap;
+  free(hs.blk);
+  return 0;
+}
+
+int lmpc_gpu_get_info(const lmpc_handle *h, int32_t *kernel, int32_t *cap, int32_t *senses) {
+  if (!h) return set_err(LMPC_E_INVALID, "null handle%s");
+  if (kernel) *kernel = h->kernel;
+  if (cap) *cap = h->lay.cap;
+  if (senses) memcpy(senses, h->h_blk + h->lay.oSense, sizeof(int32_t) * h->lay.m);
+  return 0;
+}
+
+void *lmpc_gpu_stream(lmpc_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+static int run_kernel(lmpc_handle *h, const ThetaSegs &th, int64_t N, const SolveOut &o,
+                      const SimDesc *sim, cudaStream_t s) {
+  int e;
+  switch (h->kernel) {
+    case LMPC_KERNEL_THREAD: e = launch_ldp_thread(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s); break;
+    case LMPC_KERNEL_WARP: e = launch_ldp_warp(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s); break;
+    case LMPC_KERNEL_CTA: e = launch_ldp_cta(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s); break;
+    default: return set_err(LMPC_E_INVALID, "handle has no kernel%s");
+  }
+  if (e != 0) return set_err(LMPC_E_CUDA, "kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int lmpc_gpu_solve_batch_async(lmpc_handle *h, const double *Theta, int64_t N, double *U,
+                               int32_t *exitflag, int32_t *iters, uint64_t *au, uint64_t *al,
+                               void *stream) {
+  if (!h || !Theta || !U || !exitflag || N < 0 || ((au == nullptr) != (al == nullptr)))
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_solve_batch_async: bad argument%s");
+  CUDA_OK(cudaSetDevice(h->device));
+  ThetaSegs th;
+  memset(&th, 0, sizeof(th));
+  th.nseg = 1; th.ptr[0] = Theta; th.len[0] = h->lay.nth; th.stride[0] = h->lay.nth;
+  SolveOut o{U, exitflag, iters, au, al};
+  return run_kernel(h, th, N, o, nullptr, stream ? (cudaStream_t)stream : h->stream);
+}
+
+// host buffers: H2D -> kernel -> D2H in kChunk-sized stages round-robined over kSlots streams
+static int solve_segments_host(lmpc_handle *h, const double *const *seg, const int *len,
+                               const int *stride, int nseg, int64_t N, double *U, int ustride,
+                               int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al) {
+  const LdpLayout &l = h->lay;
+  const int words = (l.m + 63) / 64;
+  for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
+    const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;
+    Slot &s = h->slots[c % kSlots];
+    ThetaSegs th;
+    memset(&th, 0, sizeof(th));
+    th.nseg = nseg;
+    for (int g = 0; g < nseg; ++g) {
+      const size_t bytes = (size_t)cnt * stride[g] * sizeof(double);
+      if (s.in[g].reserve(bytes)) return LMPC_E_CUDA;
+      CUDA_OK(cudaMemcpyAsync(s.in[g].p, seg[g] + off * stride[g], bytes, cudaMemcpyHostToDevice, s.stream));
+      th.ptr[g] = (const double *)s.in[g].p; th.len[g] = len[g]; th.stride[g] = stride[g];
+    }
+    if (s.u.reserve((size_t)cnt * l.nu * sizeof(double)) || s.flag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+    if (iters && s.iters.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+    if (au && (s.au.reserve((size_t)cnt * words * 8) || s.al.reserve((size_t)cnt * words * 8))) return LMPC_E_CUDA;
+    SolveOut o{(double *)s.u.p, (int32_t *)s.flag.p, iters ? (int32_t *)s.iters.p : nullptr,
+               au ? (uint64_t *)s.au.p : nullptr, au ? (uint64_t *)s.al.p : nullptr};
+    int rc = run_kernel(h, th, cnt, o, nullptr, s.stream);
+    if (rc) return rc;
+    if (ustride == l.nu) {
+      CUDA_OK(cudaMemcpyAsync(U + off * l.nu, s.u.p, (size_t)cnt * l.nu * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      CUDA_OK(cudaMemcpy2DAsync(U + off * ustride, (size_t)ustride * 8, s.u.p, (size_t)l.nu * 8,
+                                (size_t)l.nu * 8, (size_t)cnt, cudaMemcpyDeviceToHost, s.stream));
+    }
+    CUDA_OK(cudaMemcpyAsync(flag + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (iters) CUDA_OK(cudaMemcpyAsync(iters + off, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (au) {
+      CUDA_OK(cudaMemcpyAsync(au + off * words, s.au.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
+      CUDA_OK(cudaMemcpyAsync(al + off * words, s.al.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+  }
+  for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(h->slots[i].stream));
+  return 0;
+}
+
+int lmpc_gpu_solve_batch(lmpc_handle *h, const double *Theta, int64_t N, double *U,
+                         int32_t *exitflag, int32_t *iters, uint64_t *au, uint64_t *al) {
+  if (!h || !Theta || !U || !exitflag || N < 0 || ((au == nullptr) != (al == nullptr)))
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_solve_batch: bad argument%s");
+  if (N == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (is_device_ptr(Theta)) {
+    int rc = lmpc_gpu_solve_batch_async(h, Theta, N, U, exitflag, iters, au, al, h->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  const double *seg[1] = {Theta};
+  int len[1] = {h->lay.nth}, stride[1] = {h->lay.nth};
+  return solve_segments_host(h, seg, len, stride, 1, N, U, h->lay.nu, exitflag, iters, au, al);
+}
+
+int lmpc_gpu_compute_control_batch(lmpc_handle *h, double *control, const double *state,
+                                   const double *reference, const double *disturbance,
+                                   int32_t nr, int32_t nd, int32_t nuprev, int64_t N,
+                                   int32_t *exitflag) {
+  if (!h || !control || !state || !exitflag || N < 0 || nr < 0 || nd < 0 || nuprev < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_compute_control_batch: bad argument%s");
+  const LdpLayout &l = h->lay;
+  const int nx = l.nth - nr - nd - nuprev;
+  if (nx <= 0 || nuprev > l.nu || (nr > 0 && !reference) )
+    return set_err(LMPC_E_INVALID, "compute_control_batch: nx + nr + nd + nuprev must equal nth%s");
+  if (N == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  const double *seg[4]; int len[4], stride[4], ns = 0;
+  seg[ns] = state; len[ns] = nx; stride[ns] = nx; ns++;
+  if (nr > 0) { seg[ns] = reference; len[ns] = nr; stride[ns] = nr; ns++; }
+  if (nd > 0) {
+    if (!disturbance) return set_err(LMPC_E_INVALID, "disturbance is NULL but nd > 0%s");
+    seg[ns] = disturbance; len[ns] = nd; stride[ns] = nd; ns++;
+  }
+  if (nuprev > 0) { seg[ns] = control; len[ns] = nuprev; stride[ns] = l.nu; ns++; }
+  if (is_device_ptr(state)) {
+    // in/out aliasing of `control`: each thread reads its own u_prev before it writes u
+    ThetaSegs th;
+    memset(&th, 0, sizeof(th));
+    th.nseg = ns;
+    for (int g = 0; g < ns; ++g) { th.ptr[g] = seg[g]; th.len[g] = len[g]; th.stride[g] = stride[g]; }
+    SolveOut o{control, exitflag, nullptr, nullptr, nullptr};
+    int rc = run_kernel(h, th, N, o, nullptr, h->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  return solve_segments_host(h, seg, len, stride, ns, N, control, l.nu, exitflag, nullptr, nullptr, nullptr);
+}
+
+int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                            int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                            const double *X0, const double *R, const double *D, const double *U0,
+                            int64_t N, int32_t T, int32_t warm_start,
+                            double *Xend, double *Ulast, double *Utraj,
+                            int32_t *exitflag, int32_t *iters) {
+  if (!h || !F || !G || !X0 || !Xend || !Ulast || !exitflag || N < 0 || T < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_simulate_batch: bad argument%s");
+  const LdpLayout &l = h->lay;
+  if (nx + nr + nd + nuprev != l.nth || nuprev > l.nu || (nd > 0 && !Gd))
+    return set_err(LMPC_E_INVALID, "simulate_batch: nx + nr + nd + nuprev must equal nth%s");
+  if (N == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  const int nu = l.nu;
+  // dynamics to row-major on the device
+  std::vector<double> dynh((size_t)nx * (nx + nu + nd));
+  double *Fr = dynh.data(), *Gr = Fr + (size_t)nx * nx, *Gdr = Gr + (size_t)nx * nu;
+  for (int i = 0; i < nx; ++i) {
+    for (int c = 0; c < nx; ++c) Fr[i * nx + c] = F[(size_t)c * nx + i];
+    for (int c = 0; c < nu; ++c) Gr[i * nu + c] = G[(size_t)c * nx + i];
+    for (int c = 0; c < nd; ++c) Gdr[i * nd + c] = Gd[(size_t)c * nx + i];
+  }
+  if (h->dyn.reserve(dynh.size() * sizeof(double))) return LMPC_E_CUDA;
+  CUDA_OK(cudaMemcpyAsync(h->dyn.p, dynh.data(), dynh.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  SimDesc sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.F = (double *)h->dyn.p; sd.G = sd.F + (size_t)nx * nx; sd.Gd = sd.G + (size_t)nx * nu;
+  sd.nx = nx; sd.nr = nr; sd.nd = nd; sd.nuprev = nuprev; sd.T = T; sd.warm = warm_start;
+  ThetaSegs th;
+  memset(&th, 0, sizeof(th));
+  if (is_device_ptr(X0)) {
+    sd.X0 = X0; sd.R = R; sd.D = D; sd.U0 = U0; sd.Xend = Xend; sd.Ulast = Ulast; sd.Utraj = Utraj;
+    SolveOut o{nullptr, exitflag, iters, nullptr, nullptr};
+    int rc = run_kernel(h, th, N, o, &sd, h->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
+    const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;
+    Slot &s = h->slots[c % kSlots];
+    const double *src[4] = {X0, R, D, U0};
+    const int ln[4] = {nx, nr, nd, nuprev};
+    const double *dv[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int g = 0; g < 4; ++g) {
+      if (!src[g] || ln[g] == 0) continue;
+      const size_t bytes = (size_t)cnt * ln[g] * sizeof(double);
+      if (s.in[g].reserve(bytes)) return LMPC_E_CUDA;
+      CUDA_OK(cudaMemcpyAsync(s.in[g].p, src[g] + off * ln[g], bytes, cudaMemcpyHostToDevice, s.stream));
+      dv[g] = (const double *)s.in[g].p;
+    }
+    if (s.aux[0].reserve((size_t)cnt * nx * 8) || s.u.reserve((size_t)cnt * nu * 8) ||
+        s.flag.reserve((size_t)cnt * 4) || s.iters.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+    if (Utraj && s.aux[1].reserve((size_t)cnt * nu * T * 8)) return LMPC_E_CUDA;
+    SimDesc d = sd;
+    d.X0 = dv[0]; d.R = dv[1]; d.D = dv[2]; d.U0 = dv[3];
+    d.Xend = (double *)s.aux[0].p; d.Ulast = (double *)s.u.p; d.Utraj = Utraj ? (double *)s.aux[1].p : nullptr;
+    SolveOut o{nullptr, (int32_t *)s.flag.p, (int32_t *)s.iters.p, nullptr, nullptr};
+    int rc = run_kernel(h, th, cnt, o, &d, s.stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(Xend + off * nx, d.Xend, (size_t)cnt * nx * 8, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaMemcpyAsync(Ulast + off * nu, d.Ulast, (size_t)cnt * nu * 8, cudaMemcpyDeviceToHost, s.stream));
+    if (Utraj) CUDA_OK(cudaMemcpyAsync(Utraj + off * nu * T, d.Utraj, (size_t)cnt * nu * T * 8, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaMemcpyAsync(exitflag + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (iters) CUDA_OK(cudaMemcpyAsync(iters + off, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(h->slots[i].stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// explicit MPC
+// ---------------------------------------------------------------------------------------
+int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *feedbacks,
+                        int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
+                        int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
+                        int device, lmpc_bst **out) {
+  if (!halfplanes || !feedbacks || !hp_list || !jump_list || !out || n_hp < 0 || n_fb <= 0 ||
+      n_nodes <= 0 || nth <= 0 || nu <= 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_create_bst: bad argument%s");
+  *out = nullptr;
+  // validate the walk: every internal node must jump forward inside the array and name a
+  // valid half-plane; every leaf must name a valid feedback
+  for (int i = 0; i < n_nodes; ++i) {
+    const int j = jump_list[i];
+    if (j == 0) { if (hp_list[i] < 0 || hp_list[i] >= n_fb) return set_err(LMPC_E_INVALID, "bst: leaf names a missing feedback%s"); }
+    else if (j < 0 || i + j + 1 >= n_nodes || hp_list[i] < 0 || hp_list[i] >= n_hp)
+      return set_err(LMPC_E_INVALID, "bst: internal node out of range%s");
+  }
+  int sm = 0;
+  int rc = check_device(device, &sm);
+  if (rc) return rc;
+  const int ld = nth + 1;
+  auto al2 = [](size_t x) { return (x + 1) & ~(size_t)1; };
+  const size_t ohp = 0, ofb = al2((size_t)n_hp * ld), oclip = ofb + al2((size_t)n_fb * nu * ld);
+  const size_t olist = oclip + al2((size_t)2 * nu), total = olist + al2((size_t)(2 * n_nodes + 1) / 2);
+  std::vector<double> blk(total, 0.0);
+  for (int hI = 0; hI < n_hp; ++hI)      // column-major (nth+1) x n_hp == row-major n_hp x (nth+1)
+    for (int c = 0; c < ld; ++c) blk[ohp + (size_t)hI * ld + c] = halfplanes[(size_t)hI * ld + c];
+  for (int r = 0; r < n_fb; ++r)          // block r: (nth+1) x nu column-major -> nu x (nth+1) row-major
+    for (int i = 0; i < nu; ++i)
+      for (int c = 0; c < ld; ++c)
+        blk[ofb + ((size_t)r * nu + i) * ld + c] = feedbacks[(size_t)r * ld * nu + (size_t)i * ld + c];
+  if (clipping)
+    for (int i = 0; i < nu; ++i) { blk[oclip + 2 * i] = clipping[i]; blk[oclip + 2 * i + 1] = clipping[nu + i]; }
+  int32_t *lists = reinterpret_cast<int32_t *>(blk.data() + olist);
+  memcpy(lists, hp_list, sizeof(int32_t) * n_nodes);
+  memcpy(lists + n_nodes, jump_list, sizeof(int32_t) * n_nodes);
+  lmpc_bst *t = new lmpc_bst();
+  t->device = device; t->sm_count = sm;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void **)&t->d_blk, total * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(t->d_blk, blk.data(), total * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    const char *es = cudaGetErrorString(cudaGetLastError());
+    lmpc_gpu_destroy_bst(t);
+    return set_err(LMPC_E_CUDA, "lmpc_gpu_create_bst: %s", es);
+  }
+  for (int i = 0; i < kSlots; ++i)
+    if (cudaStreamCreateWithFlags(&t->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) {
+      lmpc_gpu_destroy_bst(t);
+      return set_err(LMPC_E_CUDA, "cudaStreamCreate failed%s");
+    }
+  t->dev.hp = t->d_blk + ohp; t->dev.fb = t->d_blk + ofb;
+  t->dev.clip = clipping ? t->d_blk + oclip : nullptr;
+  t->dev.hp_list = reinterpret_cast<const int32_t *>(t->d_blk + olist);
+  t->dev.jump_list = t->dev.hp_list + n_nodes;
+  t->dev.nth = nth; t->dev.nu = nu; t->dev.n_hp = n_hp; t->dev.n_fb = n_fb; t->dev.n_nodes = n_nodes;
+  *out = t;
+  return 0;
+}
+
+int lmpc_gpu_destroy_bst(lmpc_bst *t) {
+  if (!t) return 0;
+  cudaSetDevice(t->device);
+  free_slots(t->slots);
+  if (t->d_blk) cudaFree(t->d_blk);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+  return 0;
+}
+
+int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, double *U,
+                                  int32_t *region, void *stream) {
+  if (!t || !Theta || !U || N < 0) return set_err(LMPC_E_INVALID, "lmpc_gpu_evaluate_batch_async: bad argument%s");
+  CUDA_OK(cudaSetDevice(t->device));
+  int e = launch_bst_eval(t->dev, Theta, N, U, region, t->sm_count, stream ? stream : (void *)t->stream);
+  if (e) return set_err(LMPC_E_CUDA, "bst kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double *U, int32_t *region) {
+  if (!t || !Theta || !U || N < 0) return set_err(LMPC_E_INVALID, "lmpc_gpu_evaluate_batch: bad argument%s");
+  if (N == 0) return 0;
+  CUDA_OK(cudaSetDevice(t->device));
+  if (is_device_ptr(Theta)) {
+    int rc = lmpc_gpu_evaluate_batch_async(t, Theta, N, U, region, t->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(t->stream));
+    return 0;
+  }
+  const int nth = t->dev.nth, nu = t->dev.nu;
+  for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
+    const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;
+    Slot &s = t->slots[c % kSlots];
+    if (s.in[0].reserve((size_t)cnt * nth * 8) || s.u.reserve((size_t)cnt * nu * 8)) return LMPC_E_CUDA;
+    if (region && s.flag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+    CUDA_OK(cudaMemcpyAsync(s.in[0].p, Theta + off * nth, (size_t)cnt * nth * 8, cudaMemcpyHostToDevice, s.stream));
+    int rc = lmpc_gpu_evaluate_batch_async(t, (const double *)s.in[0].p, cnt, (double *)s.u.p,
+                                           region ? (int32_t *)s.flag.p : nullptr, s.stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(U + off * nu, s.u.p, (size_t)cnt * nu * 8, cudaMemcpyDeviceToHost, s.stream));
+    if (region) CUDA_OK(cudaMemcpyAsync(region + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(t->slots[i].stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------------------
+int lmpc_gpu_fp64_peak(int device, double *tflops) {
+  if (!tflops) return set_err(LMPC_E_INVALID, "null output%s");
+  int sm = 0;
+  int rc = check_device(device, &sm);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  double *d = nullptr;
+  CUDA_OK(cudaMalloc((void **)&d, 8));
+  cudaEvent_t a, b;
+  CUDA_OK(cudaEventCreate(&a));
+  CUDA_OK(cudaEventCreate(&b));
+  const int iters = 1 << 16;
+  launch_fp64_peak(1 << 10, d, sm, nullptr);   // warm-up
+  CUDA_OK(cudaDeviceSynchronize());
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_OK(cudaEventRecord(a, nullptr));
+    int e = launch_fp64_peak(iters, d, sm, nullptr);
+    CUDA_OK(cudaEventRecord(b, nullptr));
+    CUDA_OK(cudaEventSynchronize(b));
+    if (e) return set_err(LMPC_E_CUDA, "fp64 peak kernel: %s", cudaGetErrorString((cudaError_t)e));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * 8.0 * sm;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  g_launches.fetch_add(4);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *tflops = best;
+  return 0;
+}
+
+void *lmpc_gpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void lmpc_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

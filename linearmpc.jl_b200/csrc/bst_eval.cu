@@ -1,0 +1,139 @@
+// K4: batched explicit-MPC evaluation: binary-search-tree point location + affine law.
+//
+// Replaces ParametricDAQP.evaluate(bst, theta) (call site /root/reference/src/utils.jl:57) and
+// the generated {fname}_evaluate (/root/reference/src/codegen.jl:113-124) for N parameters.
+// One thread per theta; theta lives in registers (NTH is a template parameter), the tree
+// (half-planes, leaf laws, node lists) is staged once per CTA into shared memory with a TMA
+// bulk copy.  The kernel is HBM-bound by design: 8(nth+nu) bytes per theta, everything else on chip.
+#include "ldp_device.cuh"
+
+namespace {
+
+constexpr int K4_BLOCK = 256;
+
+// tree block layout in doubles: [hp n_hp x (nth+1)] [fb n_fb x nu x (nth+1)] [clip nu x 2]
+// then int32 [hp_list n_nodes] [jump_list n_nodes]
+struct BstLayout {
+  int ohp, ofb, oclip, olist, total;  // offsets in doubles
+};
+
+template <int NTH>
+__global__ void __launch_bounds__(K4_BLOCK)
+bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int n_nodes,
+                int has_clip, int in_smem, const double *__restrict__ Theta, int64_t N,
+                double *__restrict__ U, int32_t *__restrict__ region) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  const double *base = blk;
+  if (in_smem) {
+    stage_constants_tma(smem, blk, bl.total, &mbar);
+    base = smem;
+  }
+  const int nth = NTH > 0 ? NTH : nth_rt;
+  const int ld = nth + 1;
+  const double *hp = base + bl.ohp, *fb = base + bl.ofb, *clip = base + bl.oclip;
+  const int32_t *hp_list = reinterpret_cast<const int32_t *>(base + bl.olist);
+  const int32_t *jump_list = hp_list + n_nodes;
+  constexpr int TH = NTH > 0 ? NTH : 1;
+  for (int64_t q = (int64_t)blockIdx.x * K4_BLOCK + threadIdx.x; q < N;
+       q += (int64_t)gridDim.x * K4_BLOCK) {
+    const double *src = Theta + q * nth;
+    double th[TH];
+    if (NTH > 0) {
+#pragma unroll
+      for (int c = 0; c < TH; ++c) th[c] = ld_stream(src + c);
+    }
+    int id = 0;
+    for (;;) {
+      const int jmp = jump_list[id];
+      if (jmp == 0) break;
+      const double *h = hp + hp_list[id] * ld;
+      double acc = 0.0;
+      if (NTH > 0) {
+#pragma unroll
+        for (int c = 0; c < TH; ++c) acc = fma(h[c], th[c], acc);
+      } else {
+        for (int c = 0; c < nth; ++c) acc = fma(h[c], src[c], acc);
+      }
+      id = id + jmp + (acc <= h[nth] ? 0 : 1);
+    }
+    const int reg = hp_list[id];
+    const double *f = fb + (size_t)reg * nu * ld;
+    for (int i = 0; i < nu; ++i) {
+      double acc = f[i * ld + nth];
+      if (NTH > 0) {
+#pragma unroll
+        for (int c = 0; c < TH; ++c) acc = fma(f[i * ld + c], th[c], acc);
+      } else {
+        for (int c = 0; c < nth; ++c) acc = fma(f[i * ld + c], src[c], acc);
+      }
+      if (has_clip) {
+        if (acc < clip[2 * i]) acc = clip[2 * i];
+        if (acc > clip[2 * i + 1]) acc = clip[2 * i + 1];
+      }
+      U[q * nu + i] = acc;
+    }
+    if (region) region[q] = reg;
+  }
+}
+
+template <int NTH>
+int launch_k4(const BstDev &t, const BstLayout &bl, const double *blk, const double *Theta, int64_t N,
+              double *U, int32_t *region, int sm_count, cudaStream_t s) {
+  auto kern = bst_eval_kernel<NTH>;
+  size_t smem = (size_t)bl.total * sizeof(double);
+  int in_smem = smem <= 200 * 1024;
+  if (!in_smem) smem = 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K4_BLOCK, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (N + K4_BLOCK - 1) / K4_BLOCK;
+  const int64_t cap = (int64_t)sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, K4_BLOCK, smem, s>>>(blk, bl, t.nth, t.nu, t.n_nodes, t.clip != nullptr,
+                                                in_smem, Theta, N, U, region);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// BstDev.hp points at the start of the packed tree block (see api.cu: pack_bst); the other
+// pointers are offsets into the same allocation.
+int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
+                    int sm_count, void *stream) {
+  if (N <= 0) return 0;
+  BstLayout bl;
+  bl.ohp = 0;
+  bl.ofb = (int)(t.fb - t.hp);
+  bl.oclip = (int)((t.clip ? t.clip : t.fb) - t.hp);
+  bl.olist = (int)(reinterpret_cast<const double *>(t.hp_list) - t.hp);
+  bl.total = bl.olist + (2 * t.n_nodes + 1) / 2;
+  bl.total = (bl.total + 1) & ~1;
+  cudaStream_t s = (cudaStream_t)stream;
+#define K4_CASE(NN) case NN: return launch_k4<NN>(t, bl, t.hp, Theta, N, U, region, sm_count, s);
+  switch (t.nth) {
+    K4_CASE(1) K4_CASE(2) K4_CASE(3) K4_CASE(4) K4_CASE(5) K4_CASE(6) K4_CASE(7) K4_CASE(8)
+    K4_CASE(9) K4_CASE(10) K4_CASE(11) K4_CASE(12) K4_CASE(13) K4_CASE(14) K4_CASE(15) K4_CASE(16)
+    default: return launch_k4<0>(t, bl, t.hp, Theta, N, U, region, sm_count, s);
+  }
+}
+
+// ---- FP64 FMA peak microbenchmark (roofline denominator measured in the same run) -------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *out) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 123.456) out[0] = r;  // keep the chain alive
+}
+
+int launch_fp64_peak(int iters, double *d_out, int sm_count, void *stream) {
+  fp64_peak_kernel<<<sm_count * 8, 256, 0, (cudaStream_t)stream>>>(iters, d_out);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,102 @@
+// Shared host/device definitions for liblmpcgpu.so.
+//
+// Data layout in HBM (one "constant block" per controller, uploaded once by
+// lmpc_gpu_create, staged into shared memory by every CTA with one TMA bulk copy):
+//
+//   doubles:  Mbar   m  x n    row-major, unit rows (first ms rows: normalised rows of R^-1)
+//             MbarT  n  x mp   row-major transpose, mp = m rounded up to 4 (lane-per-row scans)
+//             Gram   m  x m    Mbar Mbar'
+//             Dth    m  x nth  row-major (generated-C layout, /root/reference/src/codegen.jl:275)
+//             du, dl m
+//             Rinv   nu x n    first nu rows of the un-normalised R^-1
+//             Uth    nu x nth  -(H^-1 f_theta)[1:nu,:] - [K 0]
+//             uoff   nu
+//   int32:    sense  m         DAQP sense bits
+//
+// Every section starts 16-byte aligned so the whole block can move with cp.async.bulk.
+#pragma once
+#include <cstdint>
+#include "lmpc_gpu.h"
+
+struct LdpLayout {
+  int n, m, ms, nth, nu, mp;
+  int cap;        // working-set capacity (rows) the kernels provision on chip
+  int nsoft;
+  int has_general; // m > ms or any soft row: singular branch reachable
+  // offsets in doubles into the constant block
+  int oM, oMT, oG, oDth, odu, odl, oRinv, oUth, ouoff, oSense;
+  int total;      // block size in doubles (multiple of 2 -> 16 bytes)
+};
+
+struct LdpSettings {
+  double primal_tol, dual_tol, zero_tol, progress_tol, fval_bound, rho_soft;
+  int cycle_tol, iter_limit;
+};
+
+// theta may arrive as up to four row-segments (state / reference / disturbance / control),
+// each a (len x N) column-major array: the batched mpc_update_parameter
+// (/root/reference/codegen/mpc_update_parameter.c:1-29) is fused into the kernel's load.
+struct ThetaSegs {
+  const double *ptr[4];
+  int len[4];
+  int stride[4];   // doubles between consecutive instances (>= len)
+  int nseg;
+};
+
+struct SolveOut {
+  double *U;        // nu x N
+  int32_t *flag;    // N
+  int32_t *iters;   // N or null
+  uint64_t *act_u;  // words x N or null
+  uint64_t *act_l;
+};
+
+// closed-loop description for the simulate kernels (x+ = F x + G u + Gd d), row-major
+struct SimDesc {
+  const double *F, *G, *Gd;     // device, row-major nx x nx, nx x nu, nx x nd
+  const double *X0, *R, *D, *U0;
+  double *Xend, *Ulast, *Utraj;
+  int nx, nr, nd, nuprev, T, warm;
+};
+
+enum {
+  EXIT_OPTIMAL = 1, EXIT_SOFT_OPTIMAL = 2, EXIT_INFEASIBLE = -1, EXIT_CYCLE = -2,
+  EXIT_UNBOUNDED = -3, EXIT_ITERLIMIT = -4, EXIT_NONCONVEX = -5, EXIT_OVERDETERMINED = -6,
+  EXIT_CAPACITY = -7
+};
+enum { S_ACTIVE = 1, S_LOWER = 2, S_IMMUTABLE = 4, S_SOFT = 8, S_BINARY = 16 };
+
+// host-side setup result
+struct LdpHost {
+  LdpLayout lay;
+  double *blk;   // lay.total doubles (malloc)
+};
+
+// setup.cpp
+int lmpc_host_setup(const lmpc_problem *p, LdpHost *out, char *err, int errlen);
+
+// kernel launchers (each .cu exports one); all return cudaError_t as int
+struct cudaDeviceProp;
+int launch_ldp_thread(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                      const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                      int sm_count, void *stream);
+int launch_ldp_warp(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                    const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                    int sm_count, void *stream);
+int launch_ldp_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                   const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                   int sm_count, void *stream);
+bool ldp_thread_supports(const LdpLayout &lay);
+bool ldp_warp_supports(const LdpLayout &lay);
+bool ldp_cta_supports(const LdpLayout &lay);
+
+struct BstDev {
+  const double *hp;      // n_hp x (nth+1) row-major
+  const double *fb;      // n_fb x nu x (nth+1) row-major
+  const double *clip;    // nu x 2 row-major or null
+  const int32_t *hp_list, *jump_list;
+  int nth, nu, n_hp, n_fb, n_nodes;
+};
+int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
+                    int sm_count, void *stream);
+int launch_fp64_peak(int iters, double *d_out, int sm_count, void *stream);

@@ -1,0 +1,446 @@
+"""ctypes binding of liblmpcgpu.so and the host-side mirror of the reference interface.
+
+Reference interface mirrored (argument meaning and error behaviour kept):
+  * ``compute_control(mpc, x; r, d, uprev, check)``   /root/reference/src/utils.jl:43-51
+  * ``solve(mpc, theta)``                              /root/reference/src/utils.jl:268-283
+  * ``form_parameter``                                 /root/reference/src/explicit.jl:54-63
+  * ``Simulation(mpc; x0, r, d, N)``                   /root/reference/src/simulation.jl:37-116
+  * ``compute_control(empc, x; ...)``                  /root/reference/src/utils.jl:53-60
+Batch semantics: where the reference takes a vector ``x`` (nx), these take a matrix
+(nx x N, one instance per column) and return nu x N.
+
+numpy arrays are accepted as host buffers; objects exposing ``data_ptr()`` (torch CUDA
+tensors) or ``__cuda_array_interface__`` are passed through as device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP, KERNEL_CTA = 0, 1, 2, 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LmpcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblmpcgpu error {code}: {msg}")
+        self.code = code
+
+
+class _Problem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("ms", C.c_int32), ("nth", C.c_int32),
+                ("nu", C.c_int32), ("nx", C.c_int32),
+                ("H", C.c_void_p), ("f", C.c_void_p), ("f_theta", C.c_void_p), ("A", C.c_void_p),
+                ("bu", C.c_void_p), ("bl", C.c_void_p), ("W", C.c_void_p), ("senses", C.c_void_p),
+                ("K", C.c_void_p), ("soft_weight", C.c_double),
+                ("has_binaries", C.c_int32), ("is_symmetric", C.c_int32),
+                ("n_break_points", C.c_int32)]
+
+
+class _Settings(C.Structure):
+    _fields_ = [("primal_tol", C.c_double), ("dual_tol", C.c_double), ("zero_tol", C.c_double),
+                ("progress_tol", C.c_double), ("fval_bound", C.c_double),
+                ("cycle_tol", C.c_int32), ("iter_limit", C.c_int32), ("kernel", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "liblmpcgpu.so")
+
+
+def load_library():
+    """Load liblmpcgpu.so.  Fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LmpcError(-1, f"{path} not found: build it with `python __graft_entry__.py` "
+                            f"or `make -C linearmpc.jl_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(path)
+    L.lmpc_gpu_last_error.restype = C.c_char_p
+    L.lmpc_gpu_launch_count.restype = C.c_int64
+    L.lmpc_gpu_stream.restype = C.c_void_p
+    L.lmpc_gpu_stream.argtypes = [C.c_void_p]
+    L.lmpc_gpu_host_alloc.restype = C.c_void_p
+    L.lmpc_gpu_host_alloc.argtypes = [C.c_size_t]
+    L.lmpc_gpu_host_free.argtypes = [C.c_void_p]
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.lmpc_gpu_create.argtypes = [C.POINTER(_Problem), C.POINTER(_Settings), C.c_int, C.POINTER(vp)]
+    L.lmpc_gpu_destroy.argtypes = [vp]
+    L.lmpc_gpu_get_ldp.argtypes = [vp] * 9
+    L.lmpc_gpu_get_info.argtypes = [vp, vp, vp, vp]
+    L.lmpc_gpu_solve_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_solve_batch_async.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_compute_control_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
+    L.lmpc_gpu_simulate_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i64,
+                                          i32, i32, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_create_bst.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, C.c_int,
+                                      C.POINTER(vp)]
+    L.lmpc_gpu_destroy_bst.argtypes = [vp]
+    L.lmpc_gpu_evaluate_batch.argtypes = [vp, vp, i64, vp, vp]
+    L.lmpc_gpu_evaluate_batch_async.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.lmpc_gpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.lmpc_gpu_default_settings.argtypes = [C.POINTER(_Settings)]
+    _LIB = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def _check(rc):
+    if rc != 0:
+        raise LmpcError(rc, lib().lmpc_gpu_last_error().decode())
+
+
+def device_count():
+    return lib().lmpc_gpu_device_count()
+
+
+def launch_count():
+    return int(lib().lmpc_gpu_launch_count())
+
+
+def fp64_peak_tflops(device=0):
+    out = C.c_double(0.0)
+    _check(lib().lmpc_gpu_fp64_peak(device, C.byref(out)))
+    return out.value
+
+
+def default_settings(**over):
+    s = _Settings()
+    lib().lmpc_gpu_default_settings(C.byref(s))
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+def _ptr(a):
+    """host numpy array / device tensor -> raw pointer (None -> NULL)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    if hasattr(a, "__cuda_array_interface__"):
+        return a.__cuda_array_interface__["data"][0]
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _is_device(a):
+    return a is not None and not isinstance(a, np.ndarray)
+
+
+def _colmajor(a, rows):
+    """Batch argument -> (rows x N) column-major float64 host array (instance per column).
+    A vector of length `rows` is one instance; with rows == 1 a vector is 1 x N."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(rows, 1) if a.size == rows else (a.reshape(1, -1) if rows == 1 else a)
+    if a.ndim != 2 or a.shape[0] != rows:
+        raise ValueError(f"expected {rows} rows, got shape {a.shape}")
+    return np.asfortranarray(a)
+
+
+def host_ldp(H, f, f_theta, A, bu, bl, W, senses, nu, nx=0, K=None, soft_weight=1e6):
+    """Run ONLY the host-side setup (Cholesky, R^-1, normalisation, theta-absorbed bounds) and
+    return its constants; needs no GPU.  Used to check the setup step against qp2ldp."""
+    H = np.asfortranarray(np.asarray(H, np.float64)); n = H.shape[0]
+    bu = np.ascontiguousarray(bu, np.float64); bl = np.ascontiguousarray(bl, np.float64); m = bu.shape[0]
+    f_theta = np.asfortranarray(np.asarray(f_theta, np.float64)); nth = f_theta.shape[1]
+    A = np.asfortranarray(np.asarray(A, np.float64).reshape(-1, n)); ms = m - A.shape[0]
+    W = np.asfortranarray(np.asarray(W, np.float64).reshape(m, nth))
+    f = np.ascontiguousarray(f, np.float64) if f is not None and np.size(f) else np.zeros(n)
+    senses = np.ascontiguousarray(senses, np.int32)
+    Kc = None if K is None else np.asfortranarray(np.asarray(K, np.float64).reshape(nu, nx))
+    p = _Problem(n, m, ms, nth, nu, nx, _ptr(H), _ptr(f), _ptr(f_theta), _ptr(A) if A.size else None,
+                 _ptr(bu), _ptr(bl), _ptr(W) if W.size else None, _ptr(senses), _ptr(Kc),
+                 float(soft_weight), 0, 1, 0)
+    out = dict(Mbar=np.zeros((m, n)), Gram=np.zeros((m, m)), Dth=np.zeros((m, nth)), du=np.zeros(m),
+               dl=np.zeros(m), Rinv=np.zeros((nu, n)), Uth=np.zeros((nu, nth)), uoff=np.zeros(nu),
+               senses=np.zeros(m, np.int32))
+    cap = C.c_int32()
+    L = lib()
+    L.lmpc_gpu_host_ldp.argtypes = [C.POINTER(_Problem)] + [C.c_void_p] * 10
+    _check(L.lmpc_gpu_host_ldp(C.byref(p), *[_ptr(out[k]) for k in
+                               ("Mbar", "Gram", "Dth", "du", "dl", "Rinv", "Uth", "uoff", "senses")],
+                               C.cast(C.byref(cap), C.c_void_p)))
+    out["cap"] = cap.value
+    return out
+
+
+class GpuMPC:
+    """Device-resident implicit controller: the GPU backend `setup_gpu!` would attach to an MPC.
+
+    Built from the dense mpQP that `mpc2mpqp` produces (types.jl:75-98) plus K and
+    soft_weight.  numpy inputs are ordinary (row-major) arrays; they are handed to the C ABI
+    column-major, as Julia would.
+    """
+
+    def __init__(self, H, f, f_theta, A, bu, bl, W, senses, nu, nx=None, K=None,
+                 soft_weight=1e6, has_binaries=False, is_symmetric=True, n_break_points=0,
+                 device=0, settings=None, dims=None):
+        L = lib()
+        F = lambda x, shape=None: np.asfortranarray(np.asarray(x, np.float64).reshape(shape) if shape else np.asarray(x, np.float64))
+        H = F(H)
+        n = H.shape[0]
+        bu, bl = F(bu).ravel(), F(bl).ravel()
+        m = bu.shape[0]
+        f_theta = F(f_theta)
+        nth = f_theta.shape[1] if f_theta.ndim == 2 else 0
+        A = F(A).reshape(-1, n) if np.size(A) else np.zeros((0, n), order="F")
+        A = np.asfortranarray(A)
+        ms = m - A.shape[0]
+        W = np.asfortranarray(F(W).reshape(m, nth))
+        f = F(f).ravel() if f is not None and np.size(f) else np.zeros(n)
+        senses = np.ascontiguousarray(senses, np.int32)
+        self.n, self.m, self.ms, self.nth, self.nu = n, m, ms, nth, int(nu)
+        self.nx = int(nx) if nx is not None else 0
+        self.dims = dims  # optional (nx, nr, nd, nuprev) for form_parameter / compute_control
+        Kc = None
+        if K is not None and np.any(np.asarray(K) != 0):
+            Kc = np.asfortranarray(np.asarray(K, np.float64).reshape(self.nu, self.nx))
+        self._keep = (H, f, f_theta, A, bu, bl, W, senses, Kc)
+        p = _Problem(n, m, ms, nth, self.nu, self.nx, _ptr(H), _ptr(f), _ptr(f_theta),
+                     _ptr(A) if A.size else None, _ptr(bu), _ptr(bl), _ptr(W) if W.size else None,
+                     _ptr(senses), _ptr(Kc), float(soft_weight), int(has_binaries),
+                     int(is_symmetric), int(n_break_points))
+        st = settings if settings is not None else default_settings()
+        self._h = C.c_void_p()
+        _check(L.lmpc_gpu_create(C.byref(p), C.byref(st), device, C.byref(self._h)))
+        self.device = device
+        self.uprev = np.zeros(self.nu)   # mirrors mpc.uprev (utils.jl:48)
+        k, cap = C.c_int32(), C.c_int32()
+        se = np.zeros(m, np.int32)
+        _check(L.lmpc_gpu_get_info(self._h, C.byref(k), C.byref(cap), _ptr(se)))
+        self.kernel, self.cap, self.senses = k.value, cap.value, se
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().lmpc_gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup constants (for parity checks against qp2ldp) ------------------------------
+    def ldp_constants(self):
+        n, m, nth, nu = self.n, self.m, self.nth, self.nu
+        out = dict(Mbar=np.zeros((m, n)), Gram=np.zeros((m, m)), Dth=np.zeros((m, nth)),
+                   du=np.zeros(m), dl=np.zeros(m), Rinv=np.zeros((nu, n)),
+                   Uth=np.zeros((nu, nth)), uoff=np.zeros(nu))
+        _check(lib().lmpc_gpu_get_ldp(self._h, *[_ptr(out[k]) for k in
+                                                 ("Mbar", "Gram", "Dth", "du", "dl", "Rinv", "Uth", "uoff")]))
+        return out
+
+    # -- solve(mpc, theta), batched ---------------------------------------------------------
+    def solve(self, Theta, want_iters=True, want_active=True, out=None):
+        """Theta: nth x N host array (or device tensor of N x nth contiguous = nth x N column-major).
+
+        Returns dict(U nu x N, exitflag N, iters N, active_upper, active_lower (N x words))."""
+        words = (self.m + 63) // 64
+        if _is_device(Theta):
+            import torch
+            N = Theta.numel() // self.nth
+            dev = Theta.device
+            U = torch.empty((N, self.nu), dtype=torch.float64, device=dev)
+            flag = torch.empty(N, dtype=torch.int32, device=dev)
+            iters = torch.empty(N, dtype=torch.int32, device=dev) if want_iters else None
+            au = torch.empty((N, words), dtype=torch.int64, device=dev) if want_active else None
+            al = torch.empty((N, words), dtype=torch.int64, device=dev) if want_active else None
+            _check(lib().lmpc_gpu_solve_batch(self._h, _ptr(Theta), N, _ptr(U), _ptr(flag),
+                                              _ptr(iters), _ptr(au), _ptr(al)))
+            return dict(U=U.T, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
+        Th = _colmajor(Theta, self.nth)
+        N = Th.shape[1]
+        U = np.zeros((self.nu, N), order="F")
+        flag = np.zeros(N, np.int32)
+        iters = np.zeros(N, np.int32) if want_iters else None
+        au = np.zeros((N, words), np.uint64) if want_active else None
+        al = np.zeros((N, words), np.uint64) if want_active else None
+        _check(lib().lmpc_gpu_solve_batch(self._h, _ptr(Th), N, _ptr(U), _ptr(flag), _ptr(iters),
+                                          _ptr(au), _ptr(al)))
+        return dict(U=U, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
+
+    def solve_async(self, Theta_dev, U_dev, flag_dev, iters_dev=None, au_dev=None, al_dev=None,
+                    N=None, stream=None):
+        """Device pointers only, no synchronisation (bench's device-resident leg)."""
+        N = Theta_dev.numel() // self.nth if N is None else N
+        _check(lib().lmpc_gpu_solve_batch_async(self._h, _ptr(Theta_dev), N, _ptr(U_dev),
+                                                _ptr(flag_dev), _ptr(iters_dev), _ptr(au_dev),
+                                                _ptr(al_dev), stream))
+
+    def stream(self):
+        return lib().lmpc_gpu_stream(self._h)
+
+    # -- form_parameter / compute_control -----------------------------------------------------
+    def form_parameter(self, x, r=None, d=None, uprev=None):
+        """theta = [x; r; d; uprev] per column (explicit.jl:54-63); missing r/d default to 0 and
+        missing uprev to the controller's stored previous control (utils.jl:48, explicit.jl:60)."""
+        if self.dims is None:
+            raise ValueError("GpuMPC was built without dims=(nx, nr, nd, nuprev)")
+        nx, nr, nd, nup = self.dims
+        X = _colmajor(x, nx)
+        N = X.shape[1]
+        def blk(v, rows, default=None):
+            if rows == 0:
+                return np.zeros((0, N))
+            if v is None:
+                base = np.zeros(rows) if default is None else np.asarray(default, float)[:rows]
+                return np.repeat(base.reshape(rows, 1), N, axis=1)
+            v = np.asarray(v, float)
+            if v.ndim == 1:
+                if v.size != rows and v.size < rows:
+                    raise ValueError(f"vector length ({v.size}) must match ({rows})")
+                return np.repeat(v[:rows].reshape(rows, 1), N, axis=1)
+            if v.shape[0] < rows:
+                raise ValueError(f"matrix must have {rows} rows")
+            if v.shape[1] == 1 and N > 1:
+                return np.repeat(v[:rows], N, axis=1)
+            return v[:rows]
+        Rm, Dm, Um = blk(r, nr), blk(d, nd), blk(uprev, nup, self.uprev)
+        if nd > 0 and Dm.shape[0] != nd:
+            raise ValueError(f"Disturbance vector must have length {nd}")
+        return np.asfortranarray(np.vstack([X, Rm, Dm, Um]))
+
+    def compute_control(self, x, r=None, d=None, uprev=None, check=True):
+        """Batched compute_control (utils.jl:43-51): returns nu x N (a vector for a single x)."""
+        single = np.ndim(x) == 1
+        Th = self.form_parameter(x, r, d, uprev)
+        out = self.solve(Th, want_iters=False, want_active=False)
+        if check:
+            assert np.all(out["exitflag"] >= 1), "exitflag < 1 (utils.jl:46)"
+        U = out["U"]
+        self.uprev = U[:, -1].copy()
+        return U[:, 0].copy() if single else U
+
+    def compute_control_c(self, control, state, reference=None, disturbance=None):
+        """Batched twin of the generated mpc_compute_control(control, state, reference,
+        disturbance) (codegen/mpc_update_qp.h:3-7): `control` (nu x N) is in/out."""
+        nx, nr, nd, nup = self.dims
+        ctl = _colmajor(control, self.nu)
+        st = _colmajor(state, nx)
+        N = st.shape[1]
+        ref = _colmajor(reference, nr) if nr > 0 else None
+        dis = _colmajor(disturbance, nd) if (nd > 0 and disturbance is not None) else None
+        flag = np.zeros(N, np.int32)
+        _check(lib().lmpc_gpu_compute_control_batch(self._h, _ptr(ctl), _ptr(st), _ptr(ref), _ptr(dis),
+                                                    nr, nd, nup, N, _ptr(flag)))
+        return ctl, flag
+
+    # -- Simulation, batched ----------------------------------------------------------------
+    def simulate(self, F, G, x0, r=None, d=None, u0=None, N=None, T=None, Gd=None, warm_start=True,
+                 want_traj=False):
+        """N independent closed loops of `steps` steps (simulation.jl:93-113) with the default
+        linear dynamics (model.jl:70).  `N` = number of steps, as in the reference's keyword."""
+        nx, nr, nd, nup = self.dims
+        steps = int(N if N is not None else T)
+        X0 = _colmajor(x0, nx)
+        n = X0.shape[1]
+        Fm, Gm = np.asfortranarray(np.asarray(F, float)), np.asfortranarray(np.asarray(G, float).reshape(nx, -1))
+        Gdm = np.asfortranarray(np.asarray(Gd, float).reshape(nx, -1)) if (nd > 0 and Gd is not None) else None
+        def bc(v, rows):
+            if rows == 0:
+                return None
+            if v is None:
+                return np.zeros((rows, n), order="F")
+            v = np.asarray(v, float)
+            if v.ndim == 1:
+                v = np.repeat(v.reshape(rows, 1), n, axis=1)
+            return np.asfortranarray(v)
+        Rm, Dm, Um = bc(r, nr), bc(d, nd), bc(u0, nup) if u0 is not None else None
+        Xend = np.zeros((nx, n), order="F")
+        Ulast = np.zeros((self.nu, n), order="F")
+        Utraj = np.zeros((n, steps, self.nu)) if want_traj else None
+        flag = np.zeros(n, np.int32)
+        iters = np.zeros(n, np.int32)
+        _check(lib().lmpc_gpu_simulate_batch(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
+                                             _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), n, steps,
+                                             int(bool(warm_start)), _ptr(Xend), _ptr(Ulast), _ptr(Utraj),
+                                             _ptr(flag), _ptr(iters)))
+        return dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj, exitflag=flag, iters=iters)
+
+
+def setup_gpu(mpqp, nu, dims=None, K=None, soft_weight=1e6, device=0, settings=None, **kw):
+    """`setup_gpu!(mpc)`: build the device-resident backend from an MPQP-like object with
+    fields H, f, f_theta, A, bu, bl, W, senses (types.jl:75-98)."""
+    g = lambda k, default=None: getattr(mpqp, k, default) if not isinstance(mpqp, dict) else mpqp.get(k, default)
+    nx = dims[0] if dims is not None else kw.pop("nx", None)
+    return GpuMPC(g("H"), g("f"), g("f_theta"), g("A"), g("bu"), g("bl"), g("W"), g("senses"),
+                  nu=nu, nx=nx, K=K, soft_weight=soft_weight,
+                  has_binaries=bool(g("has_binaries", False)),
+                  is_symmetric=bool(g("is_symmetric", True)),
+                  n_break_points=len(g("break_points", ()) or ()),
+                  device=device, settings=settings, dims=dims)
+
+
+class GpuExplicitMPC:
+    """Device-resident explicit controller: what `compute_control(empc, ...)` evaluates.
+
+    halfplanes: n_hp x (nth+1) rows [a, b]; feedbacks: n_fb x nu x (nth+1) rows [F, g];
+    hp_list / jump_list: node arrays (0-based; jump 0 = leaf); clipping: nu x 2 or None.
+    """
+
+    def __init__(self, halfplanes, feedbacks, hp_list, jump_list, clipping=None, dims=None, device=0):
+        hp = np.ascontiguousarray(halfplanes, np.float64)          # row-major n_hp x ld == col-major ld x n_hp
+        fb = np.ascontiguousarray(feedbacks, np.float64)           # n_fb x nu x ld: block r col-major ld x nu
+        self.nth = hp.shape[1] - 1 if hp.size else fb.shape[2] - 1
+        self.nu = fb.shape[1]
+        hl = np.ascontiguousarray(hp_list, np.int32)
+        jl = np.ascontiguousarray(jump_list, np.int32)
+        clip = None if clipping is None else np.asfortranarray(np.asarray(clipping, np.float64).reshape(self.nu, 2))
+        self._keep = (hp, fb, hl, jl, clip)
+        self.dims = dims
+        self.uprev = np.zeros(self.nu)
+        self._t = C.c_void_p()
+        _check(lib().lmpc_gpu_create_bst(_ptr(hp), hp.shape[0], _ptr(fb), fb.shape[0], _ptr(hl), _ptr(jl),
+                                         len(hl), _ptr(clip), self.nth, self.nu, device, C.byref(self._t)))
+
+    def close(self):
+        if getattr(self, "_t", None) is not None and self._t:
+            lib().lmpc_gpu_destroy_bst(self._t)
+            self._t = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def evaluate(self, Theta, want_region=True):
+        if _is_device(Theta):
+            import torch
+            N = Theta.numel() // self.nth
+            U = torch.empty((N, self.nu), dtype=torch.float64, device=Theta.device)
+            reg = torch.empty(N, dtype=torch.int32, device=Theta.device) if want_region else None
+            _check(lib().lmpc_gpu_evaluate_batch(self._t, _ptr(Theta), N, _ptr(U), _ptr(reg)))
+            return U.T, reg
+        Th = _colmajor(Theta, self.nth)
+        N = Th.shape[1]
+        U = np.zeros((self.nu, N), order="F")
+        reg = np.zeros(N, np.int32) if want_region else None
+        _check(lib().lmpc_gpu_evaluate_batch(self._t, _ptr(Th), N, _ptr(U), _ptr(reg)))
+        return U, reg
+
+    def evaluate_async(self, Theta_dev, U_dev, region_dev=None, N=None, stream=None):
+        N = Theta_dev.numel() // self.nth if N is None else N
+        _check(lib().lmpc_gpu_evaluate_batch_async(self._t, _ptr(Theta_dev), N, _ptr(U_dev),
+                                                   _ptr(region_dev), stream))
+
+    form_parameter = GpuMPC.form_parameter
+
+    def compute_control(self, x, r=None, d=None, uprev=None, check=True):
+        single = np.ndim(x) == 1
+        U, _ = self.evaluate(self.form_parameter(x, r, d, uprev), want_region=False)
+        self.uprev = U[:, -1].copy()
+        return U[:, 0].copy() if single else U

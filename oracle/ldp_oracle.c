@@ -17,12 +17,12 @@ typedef struct {
   int sing;       /* last added row is dependent (D[k-1] == 0) */
   int32_t *ws;    /* row index per position */
   int8_t *side;   /* +1 upper, -1 lower */
-  double *lam, *lams, *L, *D, *z, *y, *u, *dup, *dlo;
+  double *lam, *lams, *L, *D, *Dinv, *z, *y, *u, *dup, *dlo;
   uint8_t *inws;  /* m flags */
 } work_t;
 
 static work_t *work_new(const orc_problem *p) {
-  int n = p->n, m = p->m, cap = n + 1;
+  int n = p->n, m = p->m, cap = (m > n ? m : n) + 1;
   work_t *w = (work_t *)calloc(1, sizeof(work_t));
   w->ws = (int32_t *)calloc(cap, sizeof(int32_t));
   w->side = (int8_t *)calloc(cap, 1);
@@ -30,6 +30,7 @@ static work_t *work_new(const orc_problem *p) {
   w->lams = (double *)calloc(cap, sizeof(double));
   w->L = (double *)calloc((size_t)cap * (cap + 1) / 2, sizeof(double));
   w->D = (double *)calloc(cap, sizeof(double));
+  w->Dinv = (double *)calloc(cap, sizeof(double));
   w->z = (double *)calloc(cap, sizeof(double));
   w->y = (double *)calloc(cap, sizeof(double));
   w->u = (double *)calloc(n, sizeof(double));
@@ -39,7 +40,7 @@ static work_t *work_new(const orc_problem *p) {
   return w;
 }
 static void work_free(work_t *w) {
-  free(w->ws); free(w->side); free(w->lam); free(w->lams); free(w->L); free(w->D);
+  free(w->ws); free(w->side); free(w->lam); free(w->lams); free(w->L); free(w->D); free(w->Dinv);
   free(w->z); free(w->y); free(w->u); free(w->dup); free(w->dlo); free(w->inws); free(w);
 }
 static void work_reset(const orc_problem *p, work_t *w) {
@@ -77,13 +78,14 @@ static void ldl_add(const orc_problem *p, work_t *w, int j, int s, double *fl) {
     w->y[i] = yi;
   }
   for (int i = 0; i < k; ++i) {
-    double l = w->y[i] / w->D[i];
+    double l = w->y[i] * w->Dinv[i];
     lrow[i] = l;
     dnew = fma(-w->y[i], l, dnew);
   }
   w->ws[k] = j; w->side[k] = (int8_t)s; w->lam[k] = 0.0; w->inws[j] = 1;
   if (dnew < p->zero_tol) { w->sing = 1; dnew = 0.0; }
   w->D[k] = dnew;
+  w->Dinv[k] = w->sing ? 0.0 : 1.0 / dnew;  /* pivots are inverted once, when they change */
   w->k = k + 1;
   if (fl) *fl += (double)k * k + 3.0 * k;
 }
@@ -99,7 +101,7 @@ static void ldl_remove(const orc_problem *p, work_t *w, int r, double *fl) {
     double *src = LROW(w, i), *dst = LROW(w, i - 1);
     for (int c = 0; c < r; ++c) dst[c] = src[c];
     for (int c = r + 1; c < i; ++c) dst[c - 1] = src[c];
-    w->D[i - 1] = w->D[i];
+    w->D[i - 1] = w->D[i]; w->Dinv[i - 1] = w->Dinv[i];
     wv[i - 1] = wv[i];
     w->ws[i - 1] = w->ws[i]; w->side[i - 1] = w->side[i]; w->lam[i - 1] = w->lam[i];
   }
@@ -108,9 +110,10 @@ static void ldl_remove(const orc_problem *p, work_t *w, int r, double *fl) {
     double pj = wv[j];
     double t = alpha * pj;
     double dbar = fma(t, pj, w->D[j]);
-    double beta = t / dbar;
-    alpha = (w->D[j] * alpha) / dbar;
-    w->D[j] = dbar;
+    double rinv = 1.0 / dbar;
+    double beta = t * rinv;
+    alpha = (w->D[j] * alpha) * rinv;
+    w->D[j] = dbar; w->Dinv[j] = rinv;
     for (int i = j + 1; i < k; ++i) {
       double *li = LROW(w, i);
       wv[i] = fma(-pj, li[j], wv[i]);
@@ -119,7 +122,7 @@ static void ldl_remove(const orc_problem *p, work_t *w, int r, double *fl) {
   }
   w->k = k;
   w->sing = 0;
-  if (k > 0 && w->D[k - 1] < p->zero_tol) { w->sing = 1; w->D[k - 1] = 0.0; }
+  if (k > 0 && !(w->D[k - 1] >= p->zero_tol)) { w->sing = 1; w->D[k - 1] = 0.0; w->Dinv[k - 1] = 0.0; }
   if (fl) *fl += 3.0 * (k - r) * (k - r) + 2.0 * k;
 }
 
@@ -145,7 +148,7 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
         for (int c = 0; c < i; ++c) zi = fma(-li[c], w->z[c], zi);
         w->z[i] = zi;
       }
-      for (int i = 0; i < k; ++i) w->lams[i] = w->z[i] / w->D[i];
+      for (int i = 0; i < k; ++i) w->lams[i] = w->z[i] * w->Dinv[i];
       for (int jx = k - 1; jx > 0; --jx) {
         const double *lj = LROW(w, jx);
         double xj = w->lams[jx];
