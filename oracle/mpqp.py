@@ -617,6 +617,17 @@ def simple_md(q1=1.0) -> MPC:
     return mpc
 
 
+def double_integrator_hard(Np=4, Nc=4) -> MPC:
+    """Small controller with HARD general rows (velocity limits) for the thread-per-QP kernel's
+    general / singular branch; same plant as runtests.jl:1067-1074."""
+    F, G = np.array([[1, 0.1], [0, 1.0]]), np.array([[0.005], [0.1]])
+    mpc = MPC(F, G, C=np.array([[1.0, 0]]), Ts=0.1, Np=Np, Nc=Nc)
+    mpc.set_objective(Q=[1.0], R=[0.1], Rr=[0.0])
+    mpc.set_input_bounds(umin=[-1.0], umax=[1.0])
+    mpc.add_constraint(Ax=np.array([[0.0, 1.0]]), lb=[-0.5], ub=[0.5], ks=range(2, Np + 2))
+    return mpc
+
+
 def sample_theta(lo, hi, N, seed=1234):
     """theta ~ U(lo, hi), seed 1234 (runtests.jl:8); returns nth x N column-major."""
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -1,0 +1,117 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every declared symbol, refuses
+to run without a GPU, validates arguments, and its host-side setup step matches qp2ldp."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util
+from oracle import mpqp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "lmpc_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lmpc_gpu_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lmpc):
+    L = lmpc.lib()
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/lmpc_gpu.h but not exported"
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "linearmpc.jl_b200")
+    for dp, _, fns in os.walk(pkg):
+        if os.path.basename(dp) == "build":
+            continue
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, fn
+
+
+def has_gpu(lmpc):
+    return lmpc.device_count() > 0
+
+
+def test_no_gpu_fails_loudly(lmpc):
+    if has_gpu(lmpc):
+        pytest.skip("GPU present")
+    mpc = util.controller("invpend")
+    qp = mpqp.mpc2mpqp(mpc)
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.setup_gpu(qp, nu=1, dims=mpc.parameter_dims())
+    assert e.value.code == -104 and "no CPU fallback" in str(e.value)
+    with pytest.raises(lmpc.LmpcError):
+        lmpc.fp64_peak_tflops(0)
+    with pytest.raises(lmpc.LmpcError):
+        lmpc.GpuExplicitMPC(np.zeros((1, 3)), np.zeros((2, 1, 3)), [0, 0, 1], [1, 0, 0])
+
+
+@pytest.mark.parametrize("name", ["invpend", "aircraft", "aircraft_ksall", "simple", "chain_small", "chain"])
+def test_host_setup_matches_qp2ldp(lmpc, name):
+    """lmpc_gpu_create's setup step == qp2ldp (codegen.jl:239-280) to rounding (scaled by cond)."""
+    mpc = util.controller(name)
+    qp = mpqp.mpc2mpqp(mpc)
+    L = mpqp.qp2ldp(qp, mpc.nu, soft_weight=mpc.soft_weight)
+    c = lmpc.host_ldp(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, qp.senses, mpc.nu)
+    tol = 1e-13 * max(1.0, np.linalg.cond(qp.H))
+    finite = np.abs(L.du) < 1e20
+    for k, ref in [("Mbar", L.Mbar), ("Dth", L.Dth), ("Rinv", L.Rinv[:mpc.nu]), ("Uth", L.Uth_offset),
+                   ("uoff", L.u_offset)]:
+        assert np.max(np.abs(c[k] - ref)) <= tol * max(1.0, np.abs(ref).max()), k
+    assert np.allclose(c["du"][finite], L.du[finite], rtol=tol, atol=tol)
+    assert np.allclose(np.diag(c["Gram"]), 1.0, atol=1e-12)
+    assert np.allclose(c["Gram"], c["Mbar"] @ c["Mbar"].T, atol=1e-13)
+    nsoft = int(np.count_nonzero(qp.senses & mpqp.SOFT))
+    general = qp.m > qp.ms or nsoft > 0
+    assert c["cap"] == min(qp.m, qp.n + (1 if general else 0) + nsoft)
+
+
+def test_host_setup_rejects_bad_problems(lmpc):
+    mpc = util.controller("invpend")
+    qp = mpqp.mpc2mpqp(mpc)
+    Hbad = qp.H.copy()
+    Hbad[0, 0] = -1.0
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.host_ldp(Hbad, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, qp.senses, 1)
+    assert e.value.code == -102
+    s = qp.senses.copy()
+    s[0] |= mpqp.BINARY
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.host_ldp(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, s, 1)
+    assert e.value.code == -101
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.host_ldp(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, qp.senses, 9)
+    assert e.value.code == -100
+
+
+def test_default_settings_follow_the_doc_table(lmpc):
+    """docs/src/manual/solver.md:49-56."""
+    s = lmpc.default_settings()
+    assert (s.primal_tol, s.dual_tol, s.progress_tol, s.cycle_tol, s.iter_limit) == (1e-6, 1e-12, 1e-6, 10, 10000)
+
+
+def test_form_parameter_layout(lmpc):
+    """theta = [x; r; d; uprev] (explicit.jl:54-63), same as the oracle's restatement."""
+    mpc = util.controller("aircraft")
+    cls = lmpc.GpuMPC.__new__(lmpc.GpuMPC)
+    cls.dims, cls.uprev, cls.nu = mpc.parameter_dims(), np.array([0.1, -0.2]), 2
+    x = np.arange(4.0)
+    th = cls.form_parameter(x, r=[1.0, 2.0], d=[3.0, 4.0])
+    assert np.array_equal(th[:, 0], np.concatenate([x, [1, 2], [3, 4], [0.1, -0.2]]))
+    th = cls.form_parameter(x, uprev=[9.0, 8.0])
+    assert np.array_equal(th[:, 0], mpc.form_parameter(x, uprev=[9.0, 8.0]))
+    X = np.arange(12.0).reshape(4, 3)
+    th = cls.form_parameter(X, r=[1.0, 2.0])
+    assert th.shape == (10, 3) and np.array_equal(th[4:6, 2], [1, 2]) and th.flags.f_contiguous
+    with pytest.raises(ValueError):
+        cls.form_parameter(np.zeros(3))

@@ -1,0 +1,202 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): exit flag and final active set identical, u within 1e-9
+relative.  Because kernels and oracle share the summation order, we additionally assert
+bit-identical u wherever both succeed.  Run on the GPU box with `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import mpqp, ldp
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+_cache = {}
+
+
+def gpu_controller(lmpc, name, kernel=0):
+    key = (name, kernel)
+    if key not in _cache:
+        mpc = util.controller(name)
+        qp = mpqp.mpc2mpqp(mpc)
+        st = lmpc.default_settings(kernel=kernel)
+        g = lmpc.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight, settings=st)
+        cst = g.ldp_constants()
+        cst["senses"] = g.senses
+        P = util.oracle_from_constants(qp, mpc.nu, cst, soft_weight=mpc.soft_weight)
+        _cache[key] = (mpc, qp, g, P)
+    return _cache[key]
+
+
+def assert_parity(out, ref, rel=1e-9, bitexact=True):
+    assert np.array_equal(out["exitflag"], ref["flag"])
+    assert np.array_equal(out["iters"], ref["iters"])
+    assert np.array_equal(out["active_upper"], ref["act_u"])
+    assert np.array_equal(out["active_lower"], ref["act_l"])
+    ok = ref["flag"] >= 1
+    U, V = np.asarray(out["U"])[:, ok], ref["U"][:, ok]
+    err = np.max(np.abs(U - V) / np.maximum(1.0, np.abs(V))) if ok.any() else 0.0
+    assert err <= rel, err
+    if bitexact:
+        assert np.array_equal(U, V)
+
+
+@pytest.mark.parametrize("name", ["invpend", "simple", "simple_q1000"])
+def test_known_answers_on_gpu(lmpc, name):
+    """runtests.jl:62-66, simple.md:107, simple.md:203-205 through compute_control on the GPU."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    k = util.KNOWN[name]
+    u = g.compute_control(np.array(k["x"]), r=k["r"])
+    assert abs(u[0] - k["u"]) < k["tol"]
+
+
+CASES = [("invpend", 1.0, 10000), ("invpend", 0.25, 10000), ("invpend", 0.05, 10000),
+         ("dint_hard", 1.0, 10000), ("dint_hard", 0.3, 4000),
+         ("aircraft", 1.0, 4000), ("aircraft", 0.25, 4000), ("aircraft_ksall", 0.25, 2000),
+         ("simple", 1.0, 4000), ("simple_q1000", 0.5, 2000),
+         ("chain_small", 1.0, 2000), ("chain", 1.0, 300), ("chain", 0.25, 300)]
+
+
+@pytest.mark.parametrize("name,scale,N", CASES)
+def test_batch_matches_oracle(lmpc, name, scale, N):
+    """BASELINE config 1 (10^4 sampled states) and the other controllers at oracle-sized N."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    lo, hi = util.theta_range(name, scale)
+    Th = mpqp.sample_theta(lo, hi, N)
+    assert_parity(g.solve(Th), P.solve_batch(Th))
+
+
+@pytest.mark.parametrize("fn", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")))
+def test_batch_matches_golden_fixture(lmpc, fn):
+    z = np.load(os.path.join(GOLD, fn))
+    name = fn.rsplit("_s", 1)[0]
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    out = g.solve(z["Theta"])
+    assert np.array_equal(out["exitflag"], z["flag"])
+    assert np.array_equal(out["active_upper"], z["act_u"]) and np.array_equal(out["active_lower"], z["act_l"])
+    ok = z["flag"] >= 1
+    rel = 1e-9 if name in ("invpend", "chain_small") else 1e-5   # setup-step rounding x cond(H)
+    assert np.max(np.abs(out["U"][:, ok] - z["U"][:, ok]) / np.maximum(1, np.abs(z["U"][:, ok]))) < rel
+
+
+@pytest.mark.parametrize("name,kernel", [("invpend", 2), ("dint_hard", 2), ("invpend", 3), ("aircraft", 3)])
+def test_every_kernel_gives_the_same_answer(lmpc, name, kernel):
+    """thread- / warp- / CTA-per-QP kernels are interchangeable on problems they all support."""
+    mpc, qp, g, P = gpu_controller(lmpc, name, kernel)
+    assert g.kernel == kernel
+    lo, hi = util.theta_range(name, 1.0)
+    Th = mpqp.sample_theta(lo, hi, 3000, seed=99)
+    assert_parity(g.solve(Th), P.solve_batch(Th))
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 127, 128, 129, 4097])
+def test_ragged_batch_sizes(lmpc, N):
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    lo, hi = mpqp.invpend_range(1.0)
+    Th = mpqp.sample_theta(lo, hi, max(N, 1))[:, :N]
+    out = g.solve(Th)
+    assert out["U"].shape == (1, N)
+    if N:
+        assert_parity(out, P.solve_batch(Th))
+
+
+def test_full_size_properties(lmpc):
+    """BASELINE config 2 size (10^7 theta): size-independent properties instead of the oracle:
+    every instance optimal, bounds respected, idempotent, device path == chunked host path,
+    and a 1e5 random subsample equals the oracle bit for bit."""
+    import torch
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    lo, hi = mpqp.invpend_range(1.0)
+    N = 10_000_000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234)
+    Th = torch.rand((N, 7), dtype=torch.float64, device="cuda", generator=gen)
+    Th = Th * torch.tensor(hi - lo, device="cuda") + torch.tensor(lo, device="cuda")
+    a = g.solve(Th)
+    b = g.solve(Th)
+    assert bool((a["exitflag"] == 1).all())
+    assert bool((a["U"].abs() <= 2.0 + 1e-5).all())          # |u| <= 2 (README.md:47)
+    assert bool((a["U"] == b["U"]).all()) and bool((a["active_upper"] == b["active_upper"]).all())
+    host = g.solve(np.asfortranarray(Th.cpu().numpy().T), want_active=False)   # 10 pipeline chunks
+    assert np.array_equal(host["U"], a["U"].cpu().numpy())
+    idx = torch.randperm(N, device="cuda")[:100_000]
+    sub = Th[idx].cpu().numpy().T
+    ref = P.solve_batch(sub)
+    assert np.array_equal(a["U"][:, idx].cpu().numpy(), ref["U"])
+    assert np.array_equal(a["exitflag"][idx].cpu().numpy(), ref["flag"])
+    # active-set size histogram sanity (at s=1 most instances saturate all 5 bounds)
+    k = util.bits(ref["act_u"], 5).sum(1) + util.bits(ref["act_l"], 5).sum(1)
+    assert (k == 5).mean() > 0.5
+
+
+def test_compute_control_c_twin(lmpc):
+    """Batched mpc_compute_control(control, state, reference, disturbance): in/out control."""
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    rng = np.random.default_rng(3)
+    N = 5000
+    X = rng.uniform(-5, 5, (4, N)); R = rng.uniform(-2, 2, (2, N)); Up = rng.uniform(-2, 2, (1, N))
+    ctl, flag = g.compute_control_c(Up.copy(), X, R, None)
+    Th = np.vstack([X, R, Up])
+    ref = P.solve_batch(Th)
+    assert np.array_equal(ctl, ref["U"]) and np.array_equal(flag, ref["flag"])
+    U2 = g.compute_control(X, r=R, uprev=Up)
+    assert np.array_equal(U2, ref["U"])
+
+
+@pytest.mark.parametrize("name,T", [("invpend", 100), ("aircraft", 40)])
+@pytest.mark.parametrize("warm", [False, True])
+def test_closed_loop_matches_oracle(lmpc, name, T, warm):
+    """BASELINE config 3 shape: N independent Simulation loops (simulation.jl:93-113)."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    rng = np.random.default_rng(11)
+    N = 512
+    lo, hi = util.theta_range(name, 0.25)
+    X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
+    r = np.array([0.1, 0.0]) if name == "aircraft" else np.zeros(nr)
+    Rm = np.repeat(r.reshape(-1, 1), N, axis=1)
+    Dm = np.zeros((nd, N)) if nd else None
+    out = g.simulate(mpc.F, mpc.G, X0, r=Rm, d=Dm, N=T, Gd=mpc.Gd if nd else None, warm_start=warm,
+                     want_traj=True)
+    ref = P.simulate_batch(mpc.F, mpc.G, mpc.Gd if nd else None, X0, Rm, Dm, None, T, nr, nd, nup,
+                           warm=warm, want_traj=True)
+    assert np.array_equal(out["exitflag"], ref["flag"])
+    assert np.array_equal(out["iters"], ref["iters"])
+    assert np.array_equal(out["Utraj"], ref["Utraj"])
+    assert np.array_equal(out["Xend"], ref["Xend"])
+
+
+def test_warm_equals_cold_on_gpu(lmpc):
+    """runtests.jl:85-117 on the GPU: 100 closed-loop steps, |u_warm - u_cold| < 1e-9."""
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    X0 = np.array([[5.0, 5, 0, 0], [1.0, -2, 0.1, 0], [0, 0, 0.15, 0], [10.0, -8, 0.2, 1]]).T
+    a = g.simulate(mpc.F, mpc.G, X0, N=100, warm_start=False, want_traj=True)
+    b = g.simulate(mpc.F, mpc.G, X0, N=100, warm_start=True, want_traj=True)
+    assert np.all(a["exitflag"] >= 1) and np.all(b["exitflag"] >= 1)
+    assert np.max(np.abs(a["Utraj"] - b["Utraj"])) < 1e-9
+    assert abs(a["Utraj"][0, 0, 0] - 1.7612519326) < 1e-6
+
+
+def test_unsupported_problems_are_refused(lmpc):
+    mpc = util.controller("invpend")
+    qp = mpqp.mpc2mpqp(mpc)
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.GpuMPC(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, qp.senses, nu=1, has_binaries=True)
+    assert e.value.code == -101
+    with pytest.raises(lmpc.LmpcError):
+        lmpc.GpuMPC(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, qp.senses, nu=1, is_symmetric=False)
+    with pytest.raises(lmpc.LmpcError):
+        lmpc.GpuMPC(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, qp.bl, qp.W, qp.senses, nu=1, n_break_points=2)
+
+
+def test_native_library_is_what_ran(lmpc):
+    """Guard against a silent fallback: the in-tree .so is loaded and counted launches."""
+    before = lmpc.launch_count()
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    g.solve(mpqp.sample_theta(*mpqp.invpend_range(1.0), 256))
+    assert lmpc.launch_count() > before
+    with open("/proc/self/maps") as f:
+        assert "liblmpcgpu.so" in f.read()

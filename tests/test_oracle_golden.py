@@ -1,0 +1,162 @@
+"""CPU tests that pin the oracle (oracle/) before anything is compared against it.
+
+Anchors: the reference's own known answers, brute-force KKT enumeration,
+and a KKT certificate check of every oracle solution.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import linprog
+
+import util
+from oracle import mpqp, ldp, kkt_enum
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def make(name):
+    mpc = util.controller(name)
+    qp = mpqp.mpc2mpqp(mpc)
+    L = mpqp.qp2ldp(qp, mpc.nu, soft_weight=mpc.soft_weight)
+    return mpc, qp, L, ldp.OracleProblem(L, mpc.nu)
+
+
+@pytest.mark.parametrize("name", ["invpend", "simple", "simple_q1000"])
+def test_known_answers(name):
+    """runtests.jl:62-66 (1.7612519326), simple.md:107 (-1), simple.md:203-205 (1.0)."""
+    mpc, qp, L, P = make(name)
+    k = util.KNOWN[name]
+    u, flag, _ = P.solve(mpc.form_parameter(k["x"], r=k["r"]))
+    assert flag >= 1
+    assert abs(u[0] - k["u"]) < k["tol"]
+
+
+def test_problem_dimensions():
+    """n, m, ms, nth of the BASELINE controllers."""
+    _, qp, _, _ = make("invpend")
+    assert (qp.n, qp.m, qp.ms, qp.nth) == (5, 5, 5, 7)
+    assert 1.4e3 < np.linalg.cond(qp.H) < 1.8e3
+    _, qp, _, _ = make("aircraft")
+    assert (qp.n, qp.m, qp.ms, qp.nth) == (20, 22, 20, 10)
+    assert np.count_nonzero(qp.senses & mpqp.SOFT) == 2
+    _, qp, _, _ = make("aircraft_ksall")
+    assert (qp.n, qp.m, qp.ms, qp.nth) == (20, 38, 20, 10)
+    _, qp, _, _ = make("chain")
+    assert (qp.n, qp.m, qp.ms, qp.nth) == (180, 180, 180, 20)
+
+
+def test_preprocessing_matches_reference():
+    """runtests.jl:1306-1318: general rows on u alone fold into the simple bounds."""
+    F, G = mpqp.zoh(np.array([[0, 1.0], [10, 0]]), np.array([[0], [1.0]]), 0.1)
+    mpc = mpqp.MPC(F, G, Np=10)
+    mpc.set_bounds(umin=[-1], umax=[1])
+    mpc.add_constraint(Au=np.array([[-1.0]]), lb=[-0.9], ub=[1.5], ks=range(1, 11))
+    mpc.add_constraint(Au=np.array([[1.0]]), lb=[-0.5], ub=[2.0], ks=range(1, 11))
+    qp = mpqp.mpc2mpqp(mpc)
+    assert qp.A.shape[0] == 0
+    assert np.all(qp.bu == 0.9 * np.ones(10))
+    assert np.all(qp.bl == -0.5 * np.ones(10))
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.25, 0.05])
+def test_invpend_matches_kkt_enumeration(scale):
+    """3^5 = 243 candidate working sets per theta; unique optimum and active set."""
+    mpc, qp, L, P = make("invpend")
+    lo, hi = mpqp.invpend_range(scale)
+    Th = mpqp.sample_theta(lo, hi, 120, seed=1234 + int(scale * 100))
+    out = P.solve_batch(Th)
+    au, al = util.bits(out["act_u"], 5), util.bits(out["act_l"], 5)
+    for q in range(Th.shape[1]):
+        sh = L.Dth @ Th[:, q]
+        v, eu, el, margin = kkt_enum.enumerate_ldp(L.Mbar, L.du + sh, L.dl + sh)
+        x = L.Rinv[:1] @ v + L.u_offset + L.Uth_offset @ Th[:, q]
+        assert abs(x[0] - out["U"][0, q]) <= 1e-9 * max(1.0, abs(x[0]))
+        assert out["flag"][q] == 1
+        if margin > 1e-5:  # non-degenerate: the active set is unique
+            assert set(np.where(au[q])[0]) == eu and set(np.where(al[q])[0]) == el
+
+
+def kkt_certificate(L, P, theta, act_u, act_l, rho, tol=1e-6):
+    """Independent optimality check of one oracle answer from its final active set."""
+    sh = L.Dth @ theta
+    du, dl = L.du + sh, L.dl + sh
+    idx = np.where(act_u | act_l)[0]
+    soft = (L.senses & mpqp.SOFT) != 0
+    if len(idx):
+        Mw = L.Mbar[idx]
+        dw = np.where(act_u[idx], du[idx], dl[idx])
+        G = Mw @ Mw.T + np.diag(np.where(soft[idx], rho, 0.0))
+        lam = np.linalg.solve(G, -dw)
+        v = -Mw.T @ lam
+        sgn = np.where(act_u[idx], 1.0, -1.0)
+        assert np.all(lam * sgn >= -1e-9 * (1 + np.abs(lam).max())), "dual infeasible"
+    else:
+        v = np.zeros(L.Mbar.shape[1])
+    mv = L.Mbar @ v
+    inact = ~(act_u | act_l) & ((L.senses & mpqp.IMMUTABLE) == 0)
+    assert np.all(du[inact] - mv[inact] >= -tol * 1.001) and np.all(mv[inact] - dl[inact] >= -tol * 1.001)
+    return v
+
+
+# tolerance of the independent re-solve: the aircraft Hessian has cond 3.5e8 and its active
+# Gram matrices reach cond ~1e10, so two correct fp64 factorisations differ by ~1e-6 in u (an
+# 80-bit re-solve differs from BOTH by the same amount); the others are well conditioned.
+@pytest.mark.parametrize("name,scale,rtol", [("aircraft", 0.25, 2e-5), ("simple", 1.0, 2e-6),
+                                             ("chain_small", 1.0, 1e-8), ("invpend", 1.0, 1e-9)])
+def test_oracle_solutions_satisfy_kkt(name, scale, rtol):
+    mpc, qp, L, P = make(name)
+    lo, hi = util.theta_range(name, scale)
+    Th = mpqp.sample_theta(lo, hi, 200, seed=7)
+    out = P.solve_batch(Th)
+    au, al = util.bits(out["act_u"], P.m), util.bits(out["act_l"], P.m)
+    hard = ((L.senses & mpqp.SOFT) == 0) & ((L.senses & mpqp.IMMUTABLE) == 0)
+    for q in range(Th.shape[1]):
+        if out["flag"][q] >= 1:
+            v = kkt_certificate(L, P, Th[:, q], au[q], al[q], L.rho_soft)
+            x = L.Rinv[:mpc.nu] @ v + L.u_offset + L.Uth_offset @ Th[:, q]
+            assert np.allclose(x, out["U"][:, q], rtol=rtol, atol=rtol)
+        else:
+            assert out["flag"][q] == -1
+            sh = L.Dth @ Th[:, q]
+            A = np.vstack([L.Mbar[hard], -L.Mbar[hard]])
+            b = np.concatenate([(L.du + sh)[hard], -(L.dl + sh)[hard]])
+            res = linprog(np.zeros(A.shape[1]), A_ub=A, b_ub=b, bounds=[(None, None)] * A.shape[1])
+            assert res.status == 2, "oracle said infeasible but the hard rows admit a point"
+
+
+@pytest.mark.parametrize("fn", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")))
+def test_oracle_reproduces_golden(fn):
+    """Frozen oracle outputs (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(GOLD, fn))
+    name = fn.rsplit("_s", 1)[0]
+    mpc, qp, L, P = make(name)
+    assert np.allclose(qp.H, z["H"], rtol=1e-12, atol=1e-12) and np.allclose(qp.W, z["W"], rtol=1e-12, atol=1e-12)
+    out = P.solve_batch(z["Theta"])
+    assert np.array_equal(out["flag"], z["flag"])
+    assert np.array_equal(out["act_u"], z["act_u"]) and np.array_equal(out["act_l"], z["act_l"])
+    ok = z["flag"] >= 1
+    assert np.allclose(out["U"][:, ok], z["U"][:, ok], rtol=1e-10, atol=1e-12)
+
+
+def test_warm_equals_cold_closed_loop():
+    """runtests.jl:85-117: 100 closed-loop steps, |u_warm - u_cold| < 1e-9."""
+    mpc, qp, L, P = make("invpend")
+    nx, nr, nd, nup = mpc.parameter_dims()
+    X0 = np.array([[5.0, 5, 0, 0], [1.0, -2, 0.1, 0], [0, 0, 0.15, 0]]).T
+    kw = dict(Fx=mpc.F, Gx=mpc.G, Gdx=None, X0=X0, R=np.zeros((nr, 3)), D=None, U0=None, T=100,
+              nr=nr, nd=nd, nuprev=nup, want_traj=True)
+    cold = P.simulate_batch(warm=False, **kw)
+    warm = P.simulate_batch(warm=True, **kw)
+    assert np.all(cold["flag"] >= 1) and np.all(warm["flag"] >= 1)
+    assert np.max(np.abs(cold["Utraj"] - warm["Utraj"])) < 1e-9
+    # the pendulum angle is being regulated (cart position takes longer than 1 s)
+    assert np.all(np.abs(cold["Xend"][2]) < 0.5)
+
+
+def test_thread_count_does_not_change_results():
+    mpc, qp, L, P = make("invpend")
+    lo, hi = mpqp.invpend_range(1.0)
+    Th = mpqp.sample_theta(lo, hi, 1001)
+    a = P.solve_batch(Th, nthreads=1)
+    b = P.solve_batch(Th, nthreads=5)
+    assert np.array_equal(a["U"], b["U"]) and np.array_equal(a["act_u"], b["act_u"])
