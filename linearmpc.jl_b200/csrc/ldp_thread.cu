@@ -45,6 +45,18 @@ LMPC_DEVINL void sfor_down(F &&f) {
 #define SFOR_DOWN(var, B, E) sfor_down<B, E>([&](auto var##_c) { constexpr int var = decltype(var##_c)::value;
 #define SEND });
 
+// Canonical cross-element sum (see oracle/ldp_oracle.c: lanesum): element i lives on lane
+// i mod 32 and the lanes are combined by an xor-butterfly, i.e. the value on lane 0 is
+// S(base, step) = S(base, 2 step) + S(base + step, 2 step), S(base, 32) = p[base].  With
+// LEN <= 32 every lane holds at most one product, so a thread can evaluate the same tree
+// statically (sub-trees that only contain padding zeros are skipped: x + 0 == x).
+template <int LEN, int BASE, int STEP>
+LMPC_DEVINL double tree_sum(const double (&p)[LEN]) {
+  if constexpr (STEP >= 32) return p[BASE];
+  else if constexpr (BASE + STEP >= LEN) return tree_sum<LEN, BASE, 2 * STEP>(p);
+  else return tree_sum<LEN, BASE, 2 * STEP>(p) + tree_sum<LEN, BASE + STEP, 2 * STEP>(p);
+}
+
 template <int N, int CAP>
 struct QpState {
   double L[CAP * (CAP - 1) / 2 > 0 ? CAP * (CAP - 1) / 2 : 1];
@@ -85,13 +97,12 @@ LMPC_DEVINL void qp_add(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
       y[i] = yi;
     }
   SEND
+  double pr[CAP];
   SFOR(i, 0, CAP)
-    l[i] = 0.0;
-    if (i < k) {
-      l[i] = y[i] * s.Dinv[i];
-      dnew = fma(-y[i], l[i], dnew);
-    }
+    l[i] = (i < k) ? y[i] * s.Dinv[i] : 0.0;
+    pr[i] = y[i] * l[i];
   SEND
+  dnew = dnew - tree_sum<CAP, 0, 1>(pr);
   const bool sing = dnew < st.zero_tol;
   if (sing) dnew = 0.0;
   const double dinv = sing ? 0.0 : 1.0 / dnew;
@@ -229,16 +240,21 @@ LMPC_DEVINL int qp_loop(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
             SFOR(c, 0, N) u[c] = fma(-li, mr[c], u[c]); SEND
           }
         SEND
-        fval = 0.0; soft_slack = 0.0;
-        SFOR(c, 0, N) fval = fma(u[c], u[c], fval); SEND
+        soft_slack = 0.0;
+        {
+          double pu[N];
+          SFOR(c, 0, N) pu[c] = u[c] * u[c]; SEND
+          fval = tree_sum<N, 0, 1>(pu);
+        }
         if (GENERAL) {
+          double ps[CAP];
           SFOR(i, 0, CAP)
-            if (i < k && ((s.softmask >> i) & 1u)) {
-              fval = fma(st.rho_soft * s.lams[i], s.lams[i], fval);
-              const double sl = st.rho_soft * fabs(s.lams[i]);
-              if (sl > soft_slack) soft_slack = sl;
-            }
+            const bool sf = (i < k) && ((s.softmask >> i) & 1u);
+            ps[i] = sf ? s.lams[i] * s.lams[i] : 0.0;
+            const double sl = st.rho_soft * fabs(s.lams[i]);
+            if (sf && sl > soft_slack) soft_slack = sl;
           SEND
+          fval = fma(st.rho_soft, tree_sum<CAP, 0, 1>(ps), fval);
         }
         if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
         double best = -st.primal_tol, addd = 0.0;
@@ -270,6 +286,7 @@ LMPC_DEVINL int qp_loop(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
       // 4. blocking: cycle guard, step, remove
       if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
       else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+      if (!(alpha < CUDART_INF)) { flag = EXIT_CYCLE; break; }   // blocked but no finite ratio
       SFOR(i, 0, CAP)
         s.lam[i] = (i < k) ? fma(alpha, s.lams[i] - s.lam[i], s.lam[i]) : s.lam[i];
       SEND
@@ -324,7 +341,7 @@ LMPC_DEVINL int qp_solve(QpState<N, CAP> &s, const ConstView &cv, const LdpLayou
   if (cold) {
     qp_reset<N, CAP>(s);
     SFOR(c, 0, N) u[c] = 0.0; SEND
-    for (int j = 0; j < m; ++j) {
+    for (int j = 0; lay.neq > 0 && j < m; ++j) {
       const int sj = cv.sense[j];
       if (sj & S_ACTIVE) {
         if (s.k >= CAP) { flag = EXIT_OVERDETERMINED; break; }
@@ -353,8 +370,9 @@ template <int N>
 LMPC_DEVINL double control_out(const ConstView &cv, int nth, int i, const double (&u)[N],
                                const double *thv) {
   const double *rr = cv.Rinv + i * N;
-  double x = 0.0;
-  SFOR(c, 0, N) x = fma(rr[c], u[c], x); SEND
+  double pr[N];
+  SFOR(c, 0, N) pr[c] = rr[c] * u[c]; SEND
+  const double x = tree_sum<N, 0, 1>(pr);
   double sh = cv.uoff[i];
   const double *ur = cv.Uth + i * nth;
   for (int t = 0; t < nth; ++t) sh = fma(ur[t], thv[t * K1_BLOCK], sh);

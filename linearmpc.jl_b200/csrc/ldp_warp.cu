@@ -1,5 +1,510 @@
-// K2 placeholder (filled in next): warp-per-QP kernel for 8 < n <= 32.
+// K2: warp-per-QP dual active-set LDP kernel for 8 < n <= 32 (working-set capacity <= 32,
+// m <= 64).  The configuration north_star names for the AFTI-16 controller (n = 20, m = 22).
+//
+// Mapping.  One warp owns one QP at a time and loops over its share of the batch.
+//   * working-set position i  -> lane i : D_i, 1/D_i, lambda_i, lambda*_i, d_W,i, row id, L slot
+//   * decision variable c     -> lane c : u_c
+//   * constraint row j        -> lane j mod 32 (two rows per lane when m > 32): shift sh_j
+// The unit-lower factor L lives in the warp's shared-memory tile as a square array indexed by
+// PHYSICAL SLOT (odd leading dimension: column reads and row reads are both conflict free).
+// A position -> slot indirection held in registers means removing a row never moves data:
+// lanes above the removed position shift their registers down by one (__shfl_down) and the
+// slot is returned to a free mask.  Triangular solves are column sweeps: one shuffle
+// broadcast + one fma per step.  Slack argmin, ratio-test argmin and the three cross-lane
+// sums (pivot, dual objective, output map) are warp reductions; the sums use the canonical
+// butterfly order shared with the oracle, so results stay bit-identical to
+// oracle/ldp_oracle.c and to the thread-per-QP kernel.
+//
+// The constant block (Mbar, Mbar', Gram, Dth, du, dl, R^-1 rows, Uth, uoff, senses) is staged
+// into shared memory once per CTA by a TMA bulk copy and shared by its warps.
+//
+// Reference path replaced: solve(mpc, theta) -> DAQP.update/solve (src/utils.jl:268-283),
+// Simulation loop (src/simulation.jl:93-113).
 #include "ldp_device.cuh"
-bool ldp_warp_supports(const LdpLayout &) { return false; }
-int launch_ldp_warp(const LdpLayout &, const LdpSettings &, const double *, const ThetaSegs &, int64_t,
-                    const SolveOut &, const SimDesc *, int, void *) { return (int)cudaErrorNotSupported; }
+#include <math_constants.h>
+
+namespace {
+
+constexpr int K2_WARPS = 8;
+constexpr int K2_BLOCK = K2_WARPS * 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+LMPC_DEVINL double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+LMPC_DEVINL double shfl_down_d(double v, int d) { return __shfl_down_sync(FULL, v, d); }
+
+// canonical lane sum for len <= 32: one element per lane, xor-butterfly 16,8,4,2,1
+LMPC_DEVINL double bfly_sum(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+  return v;
+}
+LMPC_DEVINL double bfly_min(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double o = __shfl_xor_sync(FULL, v, off);
+    v = (o < v) ? o : v;
+  }
+  return v;
+}
+LMPC_DEVINL double bfly_max(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double o = __shfl_xor_sync(FULL, v, off);
+    v = (o > v) ? o : v;
+  }
+  return v;
+}
+
+struct WarpQp {
+  // per lane (position = lane)
+  double D, Dinv, lam, lams, dW;
+  int row, slot;
+  bool low, imm, soft;
+  // warp-uniform
+  int k;
+  bool sing;
+  unsigned used;              // physical L slots in use
+  unsigned long long inws;    // rows in the working set
+};
+
+struct WarpCtx {
+  ConstView cv;
+  const LdpLayout *lay;
+  const LdpSettings *st;
+  double *Lw;      // cap x LS tile, indexed [slot_row * LS + slot_col]
+  double *uw;      // n: primal iterate, broadcast source for the slack scan
+  double *thw;     // nth: theta
+  int LS;
+  int lane;
+};
+
+LMPC_DEVINL void wq_reset(WarpQp &s) {
+  s.D = 1.0; s.Dinv = 1.0; s.lam = 0.0; s.lams = 0.0; s.dW = 0.0; s.row = 0; s.slot = 0;
+  s.low = false; s.imm = false; s.soft = false;
+  s.k = 0; s.sing = false; s.used = 0u; s.inws = 0ull;
+}
+
+// column sweep: z <- L^-1 z on positions [0, kk)
+LMPC_DEVINL double sweep_fwd(const WarpCtx &c, const WarpQp &s, double z, int kk) {
+  const double *lrow = c.Lw + s.slot * c.LS;
+  for (int j = 0; j + 1 < kk; ++j) {
+    const int sj = __shfl_sync(FULL, s.slot, j);
+    const double lij = lrow[sj];
+    const double zj = shfl_d(z, j);
+    if (c.lane > j && c.lane < kk) z = fma(-lij, zj, z);
+  }
+  return z;
+}
+// column sweep: x <- L^-T x on positions [0, kk), descending (the oracle's axpy order)
+LMPC_DEVINL double sweep_bwd(const WarpCtx &c, const WarpQp &s, double x, int kk) {
+  for (int j = kk - 1; j > 0; --j) {
+    const int sj = __shfl_sync(FULL, s.slot, j);
+    const double lji = c.Lw[sj * c.LS + s.slot];
+    const double xj = shfl_d(x, j);
+    if (c.lane < j) x = fma(-lji, xj, x);
+  }
+  return x;
+}
+
+// append row j (oracle: ldl_add)
+LMPC_DEVINL void wq_add(const WarpCtx &c, WarpQp &s, int j, bool lower, double dval) {
+  const int m = c.lay->m, k = s.k, lane = c.lane;
+  const double *g = c.cv.G + j * m;
+  const int sj = c.cv.sense[j];
+  double dnew = g[j];
+  if (sj & S_SOFT) dnew += c.st->rho_soft;
+  double y = (lane < k) ? g[s.row] : 0.0;
+  y = sweep_fwd(c, s, y, k);
+  const double l = (lane < k) ? y * s.Dinv : 0.0;
+  dnew = dnew - bfly_sum(y * l);
+  const bool sing = dnew < c.st->zero_tol;
+  if (sing) dnew = 0.0;
+  const double dinv = sing ? 0.0 : 1.0 / dnew;
+  const int ns = __ffs(~s.used) - 1;         // free physical slot
+  if (lane < k) c.Lw[ns * c.LS + s.slot] = l;
+  if (lane == k) {
+    s.D = dnew; s.Dinv = dinv; s.lam = 0.0; s.dW = dval; s.row = j; s.slot = ns;
+    s.low = lower; s.imm = (sj & S_IMMUTABLE) != 0; s.soft = (sj & S_SOFT) != 0;
+  }
+  s.used |= 1u << ns;
+  s.inws |= 1ull << j;
+  s.sing = sing;
+  s.k = k + 1;
+  __syncwarp();
+}
+
+// delete position r (oracle: ldl_remove); no data moves, positions above r shift down a lane
+LMPC_DEVINL void wq_remove(const WarpCtx &c, WarpQp &s, int r) {
+  const int lane = c.lane;
+  int k = s.k;
+  double alpha = shfl_d(s.D, r);
+  const int rslot = __shfl_sync(FULL, s.slot, r);
+  const int rrow = __shfl_sync(FULL, s.row, r);
+  // column r below the diagonal, still at old positions
+  double wv = (lane > r && lane < k) ? c.Lw[s.slot * c.LS + rslot] : 0.0;
+  s.inws &= ~(1ull << rrow);
+  s.used &= ~(1u << rslot);
+  // positions p >= r take position p+1
+  {
+    const double D = shfl_down_d(s.D, 1), Dinv = shfl_down_d(s.Dinv, 1), lam = shfl_down_d(s.lam, 1);
+    const double dW = shfl_down_d(s.dW, 1), w2 = shfl_down_d(wv, 1);
+    const int row = __shfl_down_sync(FULL, s.row, 1), slot = __shfl_down_sync(FULL, s.slot, 1);
+    const unsigned fl = __shfl_down_sync(FULL, (unsigned)s.low | ((unsigned)s.imm << 1) | ((unsigned)s.soft << 2), 1);
+    if (lane >= r && lane + 1 < k) {
+      s.D = D; s.Dinv = Dinv; s.lam = lam; s.dW = dW; s.row = row; s.slot = slot; wv = w2;
+      s.low = fl & 1u; s.imm = (fl >> 1) & 1u; s.soft = (fl >> 2) & 1u;
+    }
+  }
+  k -= 1;
+  bool sing = false;
+  for (int j = r; j < k; ++j) {
+    const double pj = shfl_d(wv, j);
+    const double Dj = shfl_d(s.D, j);
+    const int sj = __shfl_sync(FULL, s.slot, j);
+    const double t = alpha * pj;
+    double dbar = fma(t, pj, Dj);
+    double rinv = 1.0 / dbar;
+    const double beta = t * rinv;
+    alpha = (Dj * alpha) * rinv;
+    if (j == k - 1 && !(dbar >= c.st->zero_tol)) { sing = true; dbar = 0.0; rinv = 0.0; }
+    if (lane == j) { s.D = dbar; s.Dinv = rinv; }
+    if (lane > j && lane < k) {
+      double *lp = c.Lw + s.slot * c.LS + sj;
+      const double lij = *lp;
+      wv = fma(-pj, lij, wv);
+      *lp = fma(beta, wv, lij);
+    }
+  }
+  s.k = k;
+  s.sing = sing;
+  __syncwarp();
+}
+
+// lowest lane holding the minimum of a (NaN-free), or -1 when every lane is +inf
+LMPC_DEVINL int argmin_first(double a, double &amin) {
+  amin = bfly_min(a);
+  const unsigned hit = __ballot_sync(FULL, a == amin && a < CUDART_INF);
+  return hit ? (__ffs(hit) - 1) : -1;
+}
+
+// The dual active-set loop for one QP (oracle: ldp_loop).  sh0/sh1: shifts of rows lane, lane+32.
+LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, double &u, int &iters) {
+  const LdpLayout &lay = *c.lay;
+  const LdpSettings &st = *c.st;
+  const int lane = c.lane, n = lay.n, m = lay.m, mp = lay.mp;
+  int flag = EXIT_ITERLIMIT, iter, cycle = 0;
+  double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
+  for (iter = 1; iter < st.iter_limit; ++iter) {
+    const int k = s.k;
+    double a = CUDART_INF;
+    if (!s.sing) {
+      // 1. CSP: L D L' lam* = -d_W
+      double z = (lane < k) ? -s.dW : 0.0;
+      z = sweep_fwd(c, s, z, k);
+      s.lams = (lane < k) ? z * s.Dinv : 0.0;
+      s.lams = sweep_bwd(c, s, s.lams, k);
+      // 2. blocking set + ratio test
+      const bool blk = lane < k && !s.imm && (s.low ? (s.lams > st.dual_tol) : (s.lams < -st.dual_tol));
+      if (!__any_sync(FULL, blk)) {
+        // 3. primal iterate u = -M_W' lam*
+        double uc = 0.0;
+        for (int i = 0; i < k; ++i) {
+          const double li = shfl_d(s.lams, i);
+          const int ri = __shfl_sync(FULL, s.row, i);
+          if (lane < n) uc = fma(-li, c.cv.M[ri * n + lane], uc);
+        }
+        u = uc;
+        if (lane < n) c.uw[lane] = uc;
+        __syncwarp();
+        fval = bfly_sum(lane < n ? uc * uc : 0.0);
+        soft_slack = 0.0;
+        if (lay.nsoft > 0) {
+          const bool sf = lane < k && s.soft;
+          fval = fma(st.rho_soft, bfly_sum(sf ? s.lams * s.lams : 0.0), fval);
+          soft_slack = bfly_max(sf ? st.rho_soft * fabs(s.lams) : 0.0);
+        }
+        if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
+        // most violated row: candidate per row, then first-index argmin over the warp
+        double best = CUDART_INF, bestd = 0.0;
+        int bestj = -1;
+        bool bestlow = false;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int j = lane + 32 * half;
+          if (j < m) {
+            double mu = 0.0;
+            for (int cc = 0; cc < n; ++cc) mu = fma(c.cv.MT[cc * mp + j], c.uw[cc], mu);
+            const bool skip = ((s.inws >> j) & 1ull) || (c.cv.sense[j] & S_IMMUTABLE);
+            const double shj = half ? sh1 : sh0;
+            const double dU = c.cv.du[j] + shj, dLo = c.cv.dl[j] + shj;
+            const double su = dU - mu, sl = mu - dLo;
+            if (!skip) {
+              // the sequential rule (upper tested first against the running best) picks, for
+              // consistent bounds, the negative one of su / sl; strict '<' keeps the lower row
+              if (su < -st.primal_tol && su < best) { best = su; bestd = dU; bestj = j; bestlow = false; }
+              else if (!(su < -st.primal_tol) && sl < -st.primal_tol && sl < best) { best = sl; bestd = dLo; bestj = j; bestlow = true; }
+            }
+          }
+        }
+        const double vmin = bfly_min(best);
+        // ties: lowest row index wins; rows lane (half 0) come before lane+32 (half 1)
+        const bool hit = (best == vmin) && bestj >= 0;
+        const unsigned hit0 = __ballot_sync(FULL, hit && bestj < 32);
+        const unsigned hit1 = __ballot_sync(FULL, hit && bestj >= 32);
+        if (!(hit0 | hit1)) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
+        if (k >= lay.cap || k >= 32) { flag = EXIT_CAPACITY; break; }
+        const int src = hit0 ? (__ffs(hit0) - 1) : (__ffs(hit1) - 1);
+        const int add = __shfl_sync(FULL, bestj, src);
+        const bool addlow = __shfl_sync(FULL, (int)bestlow, src);
+        const double addd = shfl_d(bestd, src);
+        if (lane < k) s.lam = s.lams;
+        wq_add(c, s, add, addlow, addd);
+        continue;
+      }
+      // 4. blocking: cycle guard, ratio test, step, remove
+      if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+      else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+      if (blk) {
+        a = -s.lam / (s.lams - s.lam);
+        if (!(a == a)) a = CUDART_INF;
+      }
+      double alpha;
+      const int rm = argmin_first(a, alpha);
+      if (rm < 0) { flag = EXIT_CYCLE; break; }   // blocked but no finite ratio (NaN guard)
+      if (lane < k) s.lam = fma(alpha, s.lams - s.lam, s.lam);
+      wq_remove(c, s, rm);
+    } else {
+      // 5. singular: p = side * [-L^-T l ; 1] on the first k-1 positions
+      const int kk = k - 1;
+      const int kslot = __shfl_sync(FULL, s.slot, kk);
+      const bool lastlow = __shfl_sync(FULL, (int)s.low, kk);
+      double p = (lane < kk) ? -c.Lw[kslot * c.LS + s.slot] : 0.0;
+      p = sweep_bwd(c, s, p, kk);
+      if (lane == kk) p = 1.0;
+      if (lastlow && lane <= kk) p = -p;
+      s.lams = (lane < k) ? p : 0.0;
+      const bool blk = lane < k && !s.imm && (s.low ? (p > st.dual_tol) : (p < -st.dual_tol));
+      if (blk) {
+        a = -s.lam / p;
+        if (!(a == a)) a = CUDART_INF;
+      }
+      double alpha;
+      const int rm = argmin_first(a, alpha);
+      if (rm < 0) { flag = EXIT_INFEASIBLE; break; }
+      if (lane < k) s.lam = fma(alpha, p, s.lam);
+      wq_remove(c, s, rm);
+    }
+  }
+  iters = iter;
+  return flag;
+}
+
+// one solve for theta in c.thw; returns the flag; u (lane c holds u_c) and iters by reference
+LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters) {
+  const LdpLayout &lay = *c.lay;
+  const int lane = c.lane, m = lay.m, nth = lay.nth;
+  // mpc_update_qp: sh_j = Dth[j,:] theta for rows lane and lane + 32
+  double sh0 = 0.0, sh1 = 0.0;
+  if (lane < m) {
+    const double *dr = c.cv.Dth + lane * nth;
+    for (int t = 0; t < nth; ++t) sh0 = fma(dr[t], c.thw[t], sh0);
+  }
+  if (lane + 32 < m) {
+    const double *dr = c.cv.Dth + (lane + 32) * nth;
+    for (int t = 0; t < nth; ++t) sh1 = fma(dr[t], c.thw[t], sh1);
+  }
+  int flag = 0;
+  if (cold) {
+    wq_reset(s);
+    u = 0.0;
+    for (int j = 0; lay.neq > 0 && j < m; ++j) {
+      const int sj = c.cv.sense[j];
+      if (sj & S_ACTIVE) {
+        if (s.k >= lay.cap || s.k >= 32) { flag = EXIT_OVERDETERMINED; break; }
+        const bool low = sj & S_LOWER;
+        const double shj = shfl_d(j < 32 ? sh0 : sh1, j & 31);
+        wq_add(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
+        if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
+      }
+    }
+  } else {
+    // warm start: same working set, new right-hand sides
+    const int j = s.row;
+    const double shj_lo = shfl_d(sh0, j & 31), shj_hi = shfl_d(sh1, j & 31);
+    if (lane < s.k) s.dW = (s.low ? c.cv.dl[j] : c.cv.du[j]) + (j < 32 ? shj_lo : shj_hi);
+  }
+  iters = 0;
+  if (flag == 0) flag = wq_loop(c, s, sh0, sh1, u, iters);
+  return flag;
+}
+
+// mpc_get_solution: control_i = (R^-1 u)_i + uoff_i + Uth[i,:] theta, canonical lane sum over c
+LMPC_DEVINL double control_out_w(const WarpCtx &c, int i, double u) {
+  const LdpLayout &lay = *c.lay;
+  const double x = bfly_sum(c.lane < lay.n ? c.cv.Rinv[i * lay.n + c.lane] * u : 0.0);
+  double sh = c.cv.uoff[i];
+  const double *ur = c.cv.Uth + i * lay.nth;
+  for (int t = 0; t < lay.nth; ++t) sh = fma(ur[t], c.thw[t], sh);
+  return x + sh;
+}
+
+LMPC_DEVINL WarpCtx make_ctx(double *smem, const LdpLayout &lay, const LdpSettings &st, int extra) {
+  WarpCtx c;
+  c.cv = make_view(smem, lay);
+  c.lay = &lay; c.st = &st;
+  c.LS = lay.cap | 1;
+  const int warp = threadIdx.x >> 5;
+  const int per_warp = ((lay.cap * c.LS + lay.n + lay.nth + extra) + 1) & ~1;
+  double *w = smem + lay.total + (size_t)warp * per_warp;
+  c.Lw = w; c.uw = w + lay.cap * c.LS; c.thw = c.uw + lay.n;
+  c.lane = threadIdx.x & 31;
+  return c;
+}
+
+__global__ void __launch_bounds__(K2_BLOCK)
+ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
+                const double *__restrict__ cblk, ThetaSegs th,
+                int64_t Ninst, SolveOut out) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  stage_constants_tma(smem, cblk, lay.total, &mbar);
+  const WarpCtx c = make_ctx(smem, lay, st, 0);
+  const int lane = c.lane, words = (lay.m + 63) >> 6;
+  const int64_t wid = (int64_t)blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+  const int64_t wstride = (int64_t)gridDim.x * K2_WARPS;
+  WarpQp s;
+  double u = 0.0;
+  for (int64_t q = wid; q < Ninst; q += wstride) {
+    // batched mpc_update_parameter: gather theta from its row segments (coalesced per segment)
+    int o = 0;
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg) {
+      if (sg < th.nseg) {
+        const int len = th.len[sg];
+        for (int t = lane; t < len; t += 32) c.thw[o + t] = ld_stream(th.ptr[sg] + q * th.stride[sg] + t);
+        o += len;
+      }
+    }
+    __syncwarp();
+    int iters;
+    const int flag = wq_solve(c, s, true, u, iters);
+    for (int i = 0; i < lay.nu; ++i) {
+      const double ctl = control_out_w(c, i, u);
+      if (lane == 0) out.U[q * lay.nu + i] = ctl;
+    }
+    // active set as bit masks (m <= 64: one word each)
+    unsigned long long au = 0ull, al = 0ull;
+    if (lane < s.k) { if (s.low) al = 1ull << s.row; else au = 1ull << s.row; }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      au |= __shfl_xor_sync(FULL, au, off);
+      al |= __shfl_xor_sync(FULL, al, off);
+    }
+    if (lane == 0) {
+      out.flag[q] = flag;
+      if (out.iters) out.iters[q] = iters;
+      if (out.act_u) { out.act_u[q * words] = au; out.act_l[q * words] = al; }
+    }
+    __syncwarp();
+  }
+}
+
+// closed loop: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
+__global__ void __launch_bounds__(K2_BLOCK)
+ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
+                    const double *__restrict__ cblk,
+                    int64_t Ninst, SimDesc sd, int32_t *flagout, int32_t *itersout) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  stage_constants_tma(smem, cblk, lay.total, &mbar);
+  const int nx = sd.nx, nr = sd.nr, nd = sd.nd, nup = sd.nuprev, nu = lay.nu;
+  const WarpCtx c = make_ctx(smem, lay, st, nx + nu);
+  double *xnw = c.thw + lay.nth;      // [nx] next state
+  double *ucw = xnw + nx;             // [nu] control
+  const int lane = c.lane;
+  const int64_t wid = (int64_t)blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
+  const int64_t wstride = (int64_t)gridDim.x * K2_WARPS;
+  WarpQp s;
+  double u = 0.0;
+  for (int64_t q = wid; q < Ninst; q += wstride) {
+    for (int i = lane; i < nx; i += 32) c.thw[i] = ld_stream(sd.X0 + q * nx + i);
+    for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.R ? ld_stream(sd.R + q * nr + i) : 0.0;
+    for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.D ? ld_stream(sd.D + q * nd + i) : 0.0;
+    for (int i = lane; i < nu; i += 32) ucw[i] = (sd.U0 && i < nup) ? ld_stream(sd.U0 + q * nup + i) : 0.0;
+    __syncwarp();
+    int worst = EXIT_OPTIMAL, tot = 0;
+    for (int t = 0; t < sd.T; ++t) {
+      for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
+      __syncwarp();
+      int iters;
+      const int f = wq_solve(c, s, !(sd.warm && t > 0), u, iters);
+      tot += iters;
+      if (f < 0) { if (worst > 0 || f < worst) worst = f; }
+      else if (worst > 0 && f > worst) worst = f;
+      for (int i = 0; i < nu; ++i) {
+        const double ctl = control_out_w(c, i, u);
+        if (lane == 0) {
+          ucw[i] = ctl;
+          if (sd.Utraj) sd.Utraj[(q * sd.T + t) * nu + i] = ctl;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < nx; i += 32) {
+        double acc = 0.0;
+        for (int cc = 0; cc < nx; ++cc) acc = fma(sd.F[i * nx + cc], c.thw[cc], acc);
+        for (int cc = 0; cc < nu; ++cc) acc = fma(sd.G[i * nu + cc], ucw[cc], acc);
+        for (int cc = 0; cc < nd; ++cc) acc = fma(sd.Gd[i * nd + cc], c.thw[nx + nr + cc], acc);
+        xnw[i] = acc;
+      }
+      __syncwarp();
+      for (int i = lane; i < nx; i += 32) c.thw[i] = xnw[i];
+      __syncwarp();
+    }
+    for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = c.thw[i];
+    for (int i = lane; i < nu; i += 32) sd.Ulast[q * nu + i] = ucw[i];
+    if (lane == 0) {
+      flagout[q] = worst;
+      if (itersout) itersout[q] = tot;
+    }
+    __syncwarp();
+  }
+}
+
+size_t k2_smem(const LdpLayout &lay, int extra) {
+  const int LS = lay.cap | 1;
+  const size_t per_warp = (((size_t)lay.cap * LS + lay.n + lay.nth + extra) + 1) & ~(size_t)1;
+  return ((size_t)lay.total + per_warp * K2_WARPS) * sizeof(double);
+}
+
+}  // namespace
+
+bool ldp_warp_supports(const LdpLayout &lay) {
+  return lay.n >= 1 && lay.n <= 32 && lay.cap <= 32 && lay.m <= 64 && k2_smem(lay, 64) <= 200 * 1024;
+}
+
+int launch_ldp_warp(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                    const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                    int sm_count, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N <= 0) return 0;
+  const size_t smem = k2_smem(lay, sim ? sim->nx + lay.nu : 0);
+  int per_sm = 0;
+  int64_t blocks = (N + K2_WARPS - 1) / K2_WARPS;
+  cudaError_t e;
+  if (sim) {
+    e = cudaFuncSetAttribute(ldp_warp_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ldp_warp_sim_kernel, K2_BLOCK, smem);
+    if (per_sm < 1) per_sm = 1;
+    if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+    ldp_warp_sim_kernel<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, N, *sim, out.flag, out.iters);
+  } else {
+    e = cudaFuncSetAttribute(ldp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ldp_warp_kernel, K2_BLOCK, smem);
+    if (per_sm < 1) per_sm = 1;
+    if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+    ldp_warp_kernel<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, th, N, out);
+  }
+  return (int)cudaGetLastError();
+}

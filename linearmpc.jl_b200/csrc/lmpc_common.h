@@ -23,6 +23,7 @@ struct LdpLayout {
   int cap;        // working-set capacity (rows) the kernels provision on chip
   int nsoft;
   int has_general; // m > ms or any soft row: singular branch reachable
+  int neq;         // rows with the ACTIVE sense bit (equalities): activated at cold start
   // offsets in doubles into the constant block
   int oM, oMT, oG, oDth, odu, odl, oRinv, oUth, ouoff, oSense;
   int total;      // block size in doubles (multiple of 2 -> 16 bytes)

@@ -130,6 +130,9 @@ int lmpc_host_setup(const lmpc_problem *p, LdpHost *out, char *err, int errlen) 
       sense[i] &= ~S_ACTIVE;
     }
   }
+  int neq = 0;
+  for (int i = 0; i < m; ++i) if (sense[i] & S_ACTIVE) neq++;
+  lay.neq = neq;
   for (int i = 0; i < m; ++i)
     for (int c = 0; c < n; ++c) MT[(size_t)c * lay.mp + i] = M[(size_t)i * n + c];
   for (int i = 0; i < m; ++i)

@@ -49,6 +49,29 @@ static void work_reset(const orc_problem *p, work_t *w) {
   memset(w->u, 0, sizeof(double) * (size_t)p->n);
 }
 
+/* Canonical cross-element sum, shared by the oracle and every kernel so that results can be
+ * compared bit for bit whatever the degree of parallelism: element i is accumulated (fma
+ * chain, increasing i) on "lane" i mod 32, then the 32 lane sums are combined with an
+ * xor-butterfly (16, 8, 4, 2, 1).  stride lets a/b be gathered. */
+static double lane_tree(const double *acc, int base, int step, int nl) {
+  if (step >= 32) return acc[base];
+  if (base + step >= nl) return lane_tree(acc, base, 2 * step, nl);  /* right half: padding zeros */
+  return lane_tree(acc, base, 2 * step, nl) + lane_tree(acc, base + step, 2 * step, nl);
+}
+static double lanesum(const double *a, const double *b, int len) {
+  double acc[32];
+  int nl = len < 32 ? len : 32;
+  if (nl <= 0) return 0.0;
+  for (int l = 0; l < nl; ++l) {
+    double s = a[l] * b[l];
+    for (int i = l + 32; i < len; i += 32) s = fma(a[i], b[i], s);
+    acc[l] = s;
+  }
+  /* value on lane 0 after the butterfly: S(base, step) = S(base, 2 step) + S(base + step, 2 step);
+   * sub-trees holding only padding zeros are skipped (x + 0 == x) */
+  return lane_tree(acc, 0, 1, nl);
+}
+
 /* packed unit-lower L: row i holds its i sub-diagonal entries at offset i(i-1)/2 */
 #define LROW(w, i) ((w)->L + ((size_t)(i) * ((i) - 1)) / 2)
 
@@ -77,11 +100,8 @@ static void ldl_add(const orc_problem *p, work_t *w, int j, int s, double *fl) {
     for (int c = 0; c < i; ++c) yi = fma(-li[c], w->y[c], yi);
     w->y[i] = yi;
   }
-  for (int i = 0; i < k; ++i) {
-    double l = w->y[i] * w->Dinv[i];
-    lrow[i] = l;
-    dnew = fma(-w->y[i], l, dnew);
-  }
+  for (int i = 0; i < k; ++i) lrow[i] = w->y[i] * w->Dinv[i];
+  dnew = dnew - lanesum(w->y, lrow, k);
   w->ws[k] = j; w->side[k] = (int8_t)s; w->lam[k] = 0.0; w->inws[j] = 1;
   if (dnew < p->zero_tol) { w->sing = 1; dnew = 0.0; }
   w->D[k] = dnew;
@@ -168,14 +188,16 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
           double li = w->lams[i];
           for (int c = 0; c < n; ++c) w->u[c] = fma(-li, mr[c], w->u[c]);
         }
-        fval = 0.0; soft_slack = 0.0;
-        for (int c = 0; c < n; ++c) fval = fma(w->u[c], w->u[c], fval);
-        for (int i = 0; i < k; ++i)
-          if (p->sense[w->ws[i]] & ORC_SOFT) {
-            fval = fma(p->rho_soft * w->lams[i], w->lams[i], fval);
+        fval = lanesum(w->u, w->u, n); soft_slack = 0.0;
+        for (int i = 0; i < k; ++i) {
+          int sf = (p->sense[w->ws[i]] & ORC_SOFT) != 0;
+          w->z[i] = sf ? w->lams[i] : 0.0;   /* z is free here: soft multipliers, 0 elsewhere */
+          if (sf) {
             double sl = p->rho_soft * fabs(w->lams[i]);
             if (sl > soft_slack) soft_slack = sl;
           }
+        }
+        fval = fma(p->rho_soft, lanesum(w->z, w->lams, k), fval);
         if (fl) *fl += 2.0 * k * n + 2.0 * n;
         if (fval > p->fval_bound) { flag = ORC_INFEASIBLE; break; }
         double best = -p->primal_tol;
@@ -208,6 +230,7 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
         double a = -w->lam[i] / (w->lams[i] - w->lam[i]);
         if (a < alpha) { alpha = a; rm = i; }
       }
+      if (!(alpha < INFINITY)) { flag = ORC_CYCLE; break; }  /* blocked but no finite ratio */
       for (int i = 0; i < k; ++i) w->lam[i] = fma(alpha, w->lams[i] - w->lam[i], w->lam[i]);
       if (fl) *fl += 3.0 * k;
       remove_pos(p, w, rm, fl);
@@ -257,8 +280,7 @@ static void get_solution(const orc_problem *p, const double *th, const work_t *w
                          double *fl) {
   for (int i = 0; i < p->nu; ++i) {
     const double *rr = p->Rinv + (size_t)i * p->n;
-    double x = 0.0;
-    for (int c = i; c < p->n; ++c) x = fma(rr[c], w->u[c], x);
+    double x = lanesum(rr, w->u, p->n);
     double sh = p->uoff[i];
     const double *ur = p->Uth + (size_t)i * p->nth;
     for (int t = 0; t < p->nth; ++t) sh = fma(ur[t], th[t], sh);
