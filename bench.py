@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- batched condensed-MPC QP solves/s on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path (theta -> affine update -> dual active-set solve -> u)
+over one batch of synthetic theta.  Workload at every N: BASELINE.json configs[1], the
+inverted-pendulum controller (README.md:36-53) on 10^7 uniformly sampled theta = (x, r, u_prev)
+PER GPU (weak scaling: contiguous theta ranges, one process per GPU, no data-path collective;
+only a final result gather).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...   # the CPU oracle port on the host cores
+
+Prints ONE JSON line on rank 0.  `value` is device-resident throughput (CUDA events on the
+launching stream, max over ranks); `e2e` goes through the public C-ABI call with pinned HOST
+buffers, H2D and D2H inside the timed region (wall clock around the synchronous call).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (controller, theta-range scale, instances per GPU)
+    "invpend_1e7": ("invpend", 1.0, 10_000_000),
+}
+SEED = 1234  # /root/reference/test/runtests.jl:8
+
+
+def build_problem(name):
+    """Controller constants via the test-side restatement of mpc2mpqp (oracle/ is the fixture
+    generator; the product consumes only the resulting arrays, as it would from Julia)."""
+    from oracle import mpqp
+    if name == "invpend":
+        mpc = mpqp.invpend()
+    else:
+        raise KeyError(name)
+    return mpc, mpqp.mpc2mpqp(mpc)
+
+
+def theta_range(name, scale):
+    from oracle import mpqp
+    return {"invpend": mpqp.invpend_range}[name](scale)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_problem(mpc, qp, cst=None):
+    from oracle import mpqp, ldp
+    L = mpqp.qp2ldp(qp, mpc.nu, soft_weight=mpc.soft_weight)
+    if cst is not None:
+        L.Mbar, L.Dth, L.du, L.dl = cst["Mbar"], cst["Dth"], cst["du"], cst["dl"]
+        Rf = np.zeros_like(L.Rinv); Rf[:mpc.nu] = cst["Rinv"]; L.Rinv = Rf
+        L.Uth_offset, L.u_offset = cst["Uth"], cst["uoff"]
+    P = ldp.OracleProblem(L, mpc.nu)
+    if cst is not None:
+        P.Gram[:] = cst["Gram"]
+    return P
+
+
+def cpu_leg(P, Theta_host, seconds_hint=None):
+    """The oracle port on all host cores over a bounded sample; returns (solves/s, cores, n, flops/solve)."""
+    from oracle import ldp
+    cores = ldp.num_threads()
+    P.solve_batch(Theta_host[:, :20000], nthreads=cores)          # warm the threads / caches
+    t0 = time.perf_counter()
+    out = P.solve_batch(Theta_host, nthreads=cores, want_flops=True)
+    dt = time.perf_counter() - t0
+    return Theta_host.shape[1] / dt, cores, Theta_host.shape[1], float(out["flops"].mean()), out
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path.  The real one (Julia compute_control -> DAQPBase
+    -> libdaqp) cannot run here (no Julia, libdaqp not under /root/reference), so this times the
+    oracle port of it on all host cores; each step is a bounded 2e6-theta sample of the workload."""
+    if rank != 0:
+        return
+    ctrl, scale, n_per = WORKLOADS[args.workload]
+    from oracle import mpqp
+    mpc, qp = build_problem(ctrl)
+    P = oracle_problem(mpc, qp)
+    lo, hi = theta_range(ctrl, scale)
+    n = min(n_per, 2_000_000)
+    Th = mpqp.sample_theta(lo, hi, n, seed=SEED)
+    from oracle import ldp
+    cores = ldp.num_threads()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        P.solve_batch(Th, nthreads=cores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    val = n * len(times) / total
+    line = {"impl": "reference", "metric": "batched MPC QP solves/sec", "value": val, "unit": "solves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "controller": ctrl, "theta_scale": scale,
+                       "instances_per_step": n, "note": "bounded sample of the 1e7-theta workload"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} theta per step, oracle/ldp_oracle.c cold start, {cores} pthreads"},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="invpend_1e7", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import lmpc_b200
+    from oracle import mpqp  # fixture generator + checker only
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    ctrl, scale, n_per = WORKLOADS[args.workload]
+    mpc, qp = build_problem(ctrl)
+    g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), device=local_rank)
+    nth, nu = g.nth, g.nu
+    lo, hi = theta_range(ctrl, scale)
+
+    # this rank's contiguous theta range, generated on the device (Philox, seed 1234 + rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + rank)
+    Th = torch.rand((n_per, nth), dtype=torch.float64, device=dev, generator=gen)
+    Th = Th * torch.tensor(hi - lo, device=dev) + torch.tensor(lo, device=dev)   # N x nth == nth x N col-major
+    U = torch.empty((n_per, nu), dtype=torch.float64, device=dev)
+    flag = torch.empty(n_per, dtype=torch.int32, device=dev)
+
+    # ---- parity gate on the cfg-1 set (10^4 theta) and CPU baseline, rank 0 only -----------
+    parity, cpu_baseline, flops_per_solve = None, None, None
+    if rank == 0:
+        sub = Th[:10000].cpu().numpy().T
+        cst = g.ldp_constants()
+        P = oracle_problem(mpc, qp, cst)
+        got = g.solve(np.asfortranarray(sub))
+        ref = P.solve_batch(sub, want_flops=True)
+        same = (got["exitflag"] == ref["flag"]) & np.all(got["active_upper"] == ref["act_u"], axis=1) & \
+               np.all(got["active_lower"] == ref["act_l"], axis=1)
+        rel = float(np.max(np.abs(got["U"] - ref["U"]) / np.maximum(1.0, np.abs(ref["U"]))))
+        parity = {"n": 10000, "identical_flag_and_active_set": int(same.sum()), "max_rel_err_u": rel,
+                  "bit_identical_u": bool(np.array_equal(got["U"], ref["U"]))}
+        flops_per_solve = float(ref["flops"].mean())
+        if not args.no_cpu_baseline and world == 1:
+            host = Th[:4_000_000].cpu().numpy().T
+            val, cores, ns, fl, _ = cpu_leg(P, host)
+            flops_per_solve = fl
+            cpu_baseline = {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                            "sample": f"first {ns} theta of rank 0's batch, oracle/ldp_oracle.c cold start, "
+                                      f"{cores} pthreads (the real reference, Julia+libdaqp, cannot run here)"}
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    stream = torch.cuda.current_stream()
+    def step():
+        g.solve_async(Th, U, flag, N=n_per, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lmpc_b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record(stream)
+    for a, b in per_step:
+        a.record(stream); step(); b.record(stream)
+    ev1.record(stream)
+    barrier()
+    launches = lmpc_b200.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_step]))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ok_all = bool((flag >= 1).all().item())
+
+    # ---- end-to-end through the C ABI with pinned host buffers ----------------------------------
+    Th_h = torch.empty((n_per, nth), dtype=torch.float64).pin_memory()
+    Th_h.copy_(Th)
+    U_h = torch.empty((n_per, nu), dtype=torch.float64).pin_memory()
+    fl_h = torch.empty(n_per, dtype=torch.int32).pin_memory()
+    def e2e_step():
+        rc = lmpc_b200.lib().lmpc_gpu_solve_batch(g._h, Th_h.data_ptr(), n_per, U_h.data_ptr(), fl_h.data_ptr(),
+                                                  None, None, None)
+        assert rc == 0, lmpc_b200.lib().lmpc_gpu_last_error()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_ok = bool(torch.equal(U_h, U.cpu()))
+
+    # ---- final result gather (the only inter-GPU traffic of the path), untimed but checked ------
+    gather_ms = None
+    if world > 1:
+        outs = [torch.empty_like(U) for _ in range(world)] if rank == 0 else None
+        torch.cuda.synchronize(); dist.barrier()
+        tg = time.perf_counter()
+        dist.gather(U, outs, dst=0)
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - tg)
+        if rank == 0:
+            assert torch.equal(outs[0], U)
+
+    if rank == 0:
+        total_solves = float(n_per) * world * args.steps
+        value = total_solves / (ms_total * 1e-3)
+        hbm_peak, peak_src = peaks()
+        fp64_peak = lmpc_b200.fp64_peak_tflops(local_rank)
+        bytes_per_solve = 8 * nth + 8 * nu + 4
+        ach_tf = flops_per_solve * n_per / (kernel_ms * 1e-3) / 1e12
+        ach_gbs = bytes_per_solve * n_per / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        line = {
+            "metric": "batched MPC QP solves/sec", "value": value, "unit": "solves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "controller": ctrl, "n": g.n, "m": g.m, "nth": nth,
+                       "theta_scale": scale, "instances_per_gpu_per_step": n_per, "seed": SEED,
+                       "kernel": {1: "thread-per-QP", 2: "warp-per-QP", 3: "CTA-per-QP"}[g.kernel],
+                       "l2": "inputs larger than L2 (560 MB theta per step vs 126 MB L2)",
+                       "settings": {"primal_tol": 1e-6, "dual_tol": 1e-12, "zero_tol": 1e-11,
+                                    "progress_tol": 1e-6, "cycle_tol": 10, "iter_limit": 10000},
+                       "all_exitflags_optimal": ok_all},
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach_tf / fp64_peak, "traffic": traffic,
+                         "kernel": "ldp_thread_kernel<5,5>", "kernel_ms": kernel_ms,
+                         "flops_per_solve": flops_per_solve,
+                         "peak_source": "FP64 FMA microbenchmark in this run (lmpc_gpu_fp64_peak)",
+                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                                 "bytes_per_solve": bytes_per_solve, "peak_source": peak_src}},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": float(n_per) * world * e2e_steps / e2e_s, "unit": "solves/s",
+                    "h2d_bytes_per_step": 8 * nth * n_per, "d2h_bytes_per_step": (8 * nu + 4) * n_per,
+                    "steps": e2e_steps, "timer": "wall clock around lmpc_gpu_solve_batch (host pointers)",
+                    "matches_device_path": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity": parity,
+        }
+        if gather_ms is not None:
+            line["gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

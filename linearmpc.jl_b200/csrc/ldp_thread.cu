@@ -54,7 +54,7 @@ template <int LEN, int BASE, int STEP>
 LMPC_DEVINL double tree_sum(const double (&p)[LEN]) {
   if constexpr (STEP >= 32) return p[BASE];
   else if constexpr (BASE + STEP >= LEN) return tree_sum<LEN, BASE, 2 * STEP>(p);
-  else return tree_sum<LEN, BASE, 2 * STEP>(p) + tree_sum<LEN, BASE + STEP, 2 * STEP>(p);
+  else return __dadd_rn(tree_sum<LEN, BASE, 2 * STEP>(p), tree_sum<LEN, BASE + STEP, 2 * STEP>(p));
 }
 
 template <int N, int CAP>
@@ -100,9 +100,9 @@ LMPC_DEVINL void qp_add(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
   double pr[CAP];
   SFOR(i, 0, CAP)
     l[i] = (i < k) ? y[i] * s.Dinv[i] : 0.0;
-    pr[i] = y[i] * l[i];
+    pr[i] = __dmul_rn(y[i], l[i]);   // never contracted into the tree's adds
   SEND
-  dnew = dnew - tree_sum<CAP, 0, 1>(pr);
+  dnew = __dsub_rn(dnew, tree_sum<CAP, 0, 1>(pr));
   const bool sing = dnew < st.zero_tol;
   if (sing) dnew = 0.0;
   const double dinv = sing ? 0.0 : 1.0 / dnew;
@@ -243,14 +243,14 @@ LMPC_DEVINL int qp_loop(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
         soft_slack = 0.0;
         {
           double pu[N];
-          SFOR(c, 0, N) pu[c] = u[c] * u[c]; SEND
+          SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
           fval = tree_sum<N, 0, 1>(pu);
         }
         if (GENERAL) {
           double ps[CAP];
           SFOR(i, 0, CAP)
             const bool sf = (i < k) && ((s.softmask >> i) & 1u);
-            ps[i] = sf ? s.lams[i] * s.lams[i] : 0.0;
+            ps[i] = sf ? __dmul_rn(s.lams[i], s.lams[i]) : 0.0;
             const double sl = st.rho_soft * fabs(s.lams[i]);
             if (sf && sl > soft_slack) soft_slack = sl;
           SEND
@@ -371,12 +371,12 @@ LMPC_DEVINL double control_out(const ConstView &cv, int nth, int i, const double
                                const double *thv) {
   const double *rr = cv.Rinv + i * N;
   double pr[N];
-  SFOR(c, 0, N) pr[c] = rr[c] * u[c]; SEND
+  SFOR(c, 0, N) pr[c] = __dmul_rn(rr[c], u[c]); SEND
   const double x = tree_sum<N, 0, 1>(pr);
   double sh = cv.uoff[i];
   const double *ur = cv.Uth + i * nth;
   for (int t = 0; t < nth; ++t) sh = fma(ur[t], thv[t * K1_BLOCK], sh);
-  return x + sh;
+  return __dadd_rn(x, sh);
 }
 
 template <int N, int CAP, bool GENERAL>

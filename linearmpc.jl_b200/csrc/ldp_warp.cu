@@ -35,7 +35,7 @@ LMPC_DEVINL double shfl_down_d(double v, int d) { return __shfl_down_sync(FULL, 
 // canonical lane sum for len <= 32: one element per lane, xor-butterfly 16,8,4,2,1
 LMPC_DEVINL double bfly_sum(double v) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+  for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, off));
   return v;
 }
 LMPC_DEVINL double bfly_min(double v) {
@@ -116,7 +116,7 @@ LMPC_DEVINL void wq_add(const WarpCtx &c, WarpQp &s, int j, bool lower, double d
   double y = (lane < k) ? g[s.row] : 0.0;
   y = sweep_fwd(c, s, y, k);
   const double l = (lane < k) ? y * s.Dinv : 0.0;
-  dnew = dnew - bfly_sum(y * l);
+  dnew = __dsub_rn(dnew, bfly_sum(__dmul_rn(y, l)));
   const bool sing = dnew < c.st->zero_tol;
   if (sing) dnew = 0.0;
   const double dinv = sing ? 0.0 : 1.0 / dnew;
@@ -216,11 +216,11 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         u = uc;
         if (lane < n) c.uw[lane] = uc;
         __syncwarp();
-        fval = bfly_sum(lane < n ? uc * uc : 0.0);
+        fval = bfly_sum(lane < n ? __dmul_rn(uc, uc) : 0.0);
         soft_slack = 0.0;
         if (lay.nsoft > 0) {
           const bool sf = lane < k && s.soft;
-          fval = fma(st.rho_soft, bfly_sum(sf ? s.lams * s.lams : 0.0), fval);
+          fval = fma(st.rho_soft, bfly_sum(sf ? __dmul_rn(s.lams, s.lams) : 0.0), fval);
           soft_slack = bfly_max(sf ? st.rho_soft * fabs(s.lams) : 0.0);
         }
         if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
@@ -341,11 +341,11 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
 // mpc_get_solution: control_i = (R^-1 u)_i + uoff_i + Uth[i,:] theta, canonical lane sum over c
 LMPC_DEVINL double control_out_w(const WarpCtx &c, int i, double u) {
   const LdpLayout &lay = *c.lay;
-  const double x = bfly_sum(c.lane < lay.n ? c.cv.Rinv[i * lay.n + c.lane] * u : 0.0);
+  const double x = bfly_sum(c.lane < lay.n ? __dmul_rn(c.cv.Rinv[i * lay.n + c.lane], u) : 0.0);
   double sh = c.cv.uoff[i];
   const double *ur = c.cv.Uth + i * lay.nth;
   for (int t = 0; t < lay.nth; ++t) sh = fma(ur[t], c.thw[t], sh);
-  return x + sh;
+  return __dadd_rn(x, sh);
 }
 
 LMPC_DEVINL WarpCtx make_ctx(double *smem, const LdpLayout &lay, const LdpSettings &st, int extra) {

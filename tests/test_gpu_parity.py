@@ -81,8 +81,9 @@ def test_batch_matches_golden_fixture(lmpc, fn):
     mpc, qp, g, P = gpu_controller(lmpc, name)
     out = g.solve(z["Theta"])
     assert np.array_equal(out["exitflag"], z["flag"])
-    assert np.array_equal(out["active_upper"], z["act_u"]) and np.array_equal(out["active_lower"], z["act_l"])
-    ok = z["flag"] >= 1
+    ok = z["flag"] >= 1   # the working set left behind by an infeasible exit is not a result
+    assert np.array_equal(out["active_upper"][ok], z["act_u"][ok])
+    assert np.array_equal(out["active_lower"][ok], z["act_l"][ok])
     rel = 1e-9 if name in ("invpend", "chain_small") else 1e-5   # setup-step rounding x cond(H)
     assert np.max(np.abs(out["U"][:, ok] - z["U"][:, ok]) / np.maximum(1, np.abs(z["U"][:, ok]))) < rel
 
