@@ -163,8 +163,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="invpend_1e7", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,7 +226,10 @@ def main():
                                       f"{cores} pthreads (the real reference, Julia+libdaqp, cannot run here)"}
 
     # ---- device-resident timing ---------------------------------------------------------------
-    stream = torch.cuda.current_stream()
+    # an explicit (non-null) stream: the C ABI reads a NULL stream as "the handle's own stream",
+    # which torch events on the legacy default stream would not see
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     def step():
         g.solve_async(Th, U, flag, N=n_per, stream=stream.cuda_stream)
 
@@ -235,12 +238,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()      # runs through warm-up, the timed region and the e2e leg
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = lmpc_b200.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_step = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -253,7 +256,6 @@ def main():
     launches = lmpc_b200.launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_step]))
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -283,6 +285,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e_ok = bool(torch.equal(U_h, U.cpu()))
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- final result gather (the only inter-GPU traffic of the path), untimed but checked ------
     gather_ms = None

@@ -1,0 +1,158 @@
+# LinearMPCGPU.jl -- the thin glue a LinearMPC.jl maintainer would add as src/gpu/.
+# It binds liblmpcgpu.so (include/lmpc_gpu.h) with ccall and keeps the reference's API shape:
+#   setup_gpu!(mpc)                          after setup!(mpc)          (src/setup.jl:7-29)
+#   compute_control(gmpc, X; r=R, d=D, uprev=U)  X::AbstractMatrix => batch (src/utils.jl:43-51)
+#   solve(gmpc, Θ)                                                        (src/utils.jl:268-283)
+#   Simulation-style closed loops: simulate(gmpc, X0; r, d, N, warm_start) (src/simulation.jl:93-113)
+#   compute_control(gempc, X; ...)            explicit controllers          (src/utils.jl:53-60)
+# NOT executed in the build container (no Julia there); every call below is a 1:1 ccall of a
+# function that the Python mirror (linearmpc.jl_b200/host.py) exercises in the tests.
+module LinearMPCGPU
+
+using LinearMPC, LinearAlgebra
+
+const liblmpcgpu = get(ENV, "LMPC_GPU_LIB", "liblmpcgpu.so")
+
+struct LmpcProblem            # mirrors lmpc_problem in include/lmpc_gpu.h
+    n::Int32; m::Int32; ms::Int32; nth::Int32; nu::Int32; nx::Int32
+    H::Ptr{Float64}; f::Ptr{Float64}; f_theta::Ptr{Float64}; A::Ptr{Float64}
+    bu::Ptr{Float64}; bl::Ptr{Float64}; W::Ptr{Float64}; senses::Ptr{Cint}
+    K::Ptr{Float64}; soft_weight::Float64
+    has_binaries::Int32; is_symmetric::Int32; n_break_points::Int32
+end
+
+mutable struct GpuMPC
+    handle::Ptr{Cvoid}
+    mpc::LinearMPC.MPC
+    nth::Int; nu::Int; m::Int
+end
+
+lasterror() = unsafe_string(ccall((:lmpc_gpu_last_error, liblmpcgpu), Cstring, ()))
+check(rc) = rc == 0 || error("liblmpcgpu error $rc: $(lasterror())")
+
+"""
+    setup_gpu!(mpc; device=0) -> GpuMPC
+
+Uploads the condensed problem once (what `DAQP.setup` + `qp2ldp` do on the host,
+src/setup.jl:11-13, src/codegen.jl:239-280).  Refuses hybrid / AVI / hierarchical problems.
+"""
+function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0)
+    mpc.mpqp_issetup || LinearMPC.setup!(mpc)
+    q = mpc.mpQP
+    n, m = size(q.H, 1), length(q.bu)
+    nth = size(q.f_theta, 2)
+    K = iszero(mpc.K) ? C_NULL : pointer(mpc.K)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve q mpc begin
+        p = LmpcProblem(n, m, m - size(q.A, 1), nth, mpc.model.nu, mpc.model.nx,
+                        pointer(q.H), pointer(q.f), pointer(q.f_theta),
+                        isempty(q.A) ? C_NULL : pointer(q.A), pointer(q.bu), pointer(q.bl),
+                        pointer(q.W), pointer(q.senses), K, mpc.settings.soft_weight,
+                        q.has_binaries, q.is_symmetric, length(q.break_points))
+        check(ccall((:lmpc_gpu_create, liblmpcgpu), Cint,
+                    (Ref{LmpcProblem}, Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), p, C_NULL, device, h))
+    end
+    g = GpuMPC(h[], mpc, nth, mpc.model.nu, m)
+    finalizer(x -> ccall((:lmpc_gpu_destroy, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle), g)
+    return g
+end
+
+"""
+    solve(g, Θ) -> (U, exitflag, iters)     Θ is nth × N (one parameter per column)
+"""
+function solve(g::GpuMPC, Θ::Matrix{Float64})
+    N = size(Θ, 2)
+    U = Matrix{Float64}(undef, g.nu, N); flag = Vector{Int32}(undef, N); it = Vector{Int32}(undef, N)
+    check(ccall((:lmpc_gpu_solve_batch, liblmpcgpu), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt64}, Ptr{UInt64}),
+                g.handle, Θ, N, U, flag, it, C_NULL, C_NULL))
+    return U, flag, it
+end
+
+"""
+    compute_control(g, X; r, d, uprev, check=true) -> nu × N
+
+Batched `compute_control` (src/utils.jl:43-51): X is nx × N; r, d, uprev are vectors (broadcast)
+or matrices with N columns.  θ = [x; r; d; uprev] exactly as `form_parameter` (src/explicit.jl:54-63).
+"""
+function LinearMPC.compute_control(g::GpuMPC, X::AbstractMatrix; r=nothing, d=nothing, uprev=nothing, check=true)
+    nx, nr, nd, nup, np = LinearMPC.get_parameter_dims(g.mpc)
+    np == 0 || error("generalized parameters are not supported by the GPU backend")
+    N = size(X, 2)
+    col(v, k) = v isa AbstractMatrix ? v[1:k, :] : repeat(isnothing(v) ? zeros(k) : v[1:k], 1, N)
+    Θ = Matrix{Float64}([X; col(r, nr); col(d, nd); col(isnothing(uprev) ? g.mpc.uprev : uprev, nup)])
+    U, flag, _ = solve(g, Θ)
+    check && @assert all(flag .>= 1)
+    g.mpc.uprev .= U[:, end]
+    return U
+end
+
+"""
+    simulate(g, X0; r, d, N, warm_start=true) -> (Xend, Ulast, exitflag)
+
+N_traj independent copies of the `Simulation` loop (src/simulation.jl:93-113) with the model's
+linear dynamics (src/model.jl:70), N steps each, entirely on the GPU.
+"""
+function simulate(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integer=100, warm_start::Bool=true)
+    mdl = g.mpc.model
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
+    M = size(X0, 2)
+    R = nr == 0 ? C_NULL : Matrix{Float64}(r isa AbstractMatrix ? r : repeat(isnothing(r) ? zeros(nr) : r, 1, M))
+    D = nd == 0 ? C_NULL : Matrix{Float64}(d isa AbstractMatrix ? d : repeat(isnothing(d) ? zeros(nd) : d, 1, M))
+    Xend = similar(X0); Ulast = Matrix{Float64}(undef, g.nu, M); flag = Vector{Int32}(undef, M)
+    check(ccall((:lmpc_gpu_simulate_batch, liblmpcgpu), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int32,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                g.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
+                X0, R, D, C_NULL, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
+    return Xend, Ulast, flag
+end
+
+# ---- explicit controllers ---------------------------------------------------------------------
+mutable struct GpuExplicitMPC
+    handle::Ptr{Cvoid}
+    empc::LinearMPC.ExplicitMPC
+    nth::Int; nu::Int
+end
+
+"""
+    setup_gpu!(empc) -> GpuExplicitMPC     (needs `build_tree!(empc)` first, src/explicit.jl:65-71)
+
+Uploads bst.halfplanes / feedbacks / hp_list / jump_list / clipping.  The library's node
+convention is 0-based with jump 0 marking a leaf; ParametricDAQP's arrays are 1-based with
+`next == id` marking a leaf, so the lists are shifted here.
+"""
+function setup_gpu!(empc::LinearMPC.ExplicitMPC; device::Integer=0)
+    bst = empc.bst
+    isnothing(bst) && error("Need to build a binary search tree to evaluate control law")  # src/utils.jl:54-55
+    nth = size(bst.halfplanes, 1) - 1
+    nu = size(bst.feedbacks[1], 2)
+    fb = reduce(hcat, [vec(F) for F in bst.feedbacks])            # (nth+1)*nu × n_fb
+    jump = Int32.(bst.jump_list)                                   # 0 stays 0 (leaf)
+    hp = Int32.(bst.hp_list) .- Int32(1)
+    clip = isnothing(bst.clipping) ? C_NULL : Matrix{Float64}(bst.clipping[:, 1:2])
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lmpc_gpu_create_bst, liblmpcgpu), Cint,
+                (Ptr{Float64}, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64},
+                 Int32, Int32, Cint, Ref{Ptr{Cvoid}}),
+                bst.halfplanes, size(bst.halfplanes, 2), fb, size(fb, 2), hp, jump, length(jump), clip,
+                nth, nu, device, h))
+    g = GpuExplicitMPC(h[], empc, nth, nu)
+    finalizer(x -> ccall((:lmpc_gpu_destroy_bst, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle), g)
+    return g
+end
+
+function LinearMPC.compute_control(g::GpuExplicitMPC, X::AbstractMatrix; r=nothing, d=nothing, uprev=nothing)
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.empc)
+    N = size(X, 2)
+    col(v, k) = v isa AbstractMatrix ? v[1:k, :] : repeat(isnothing(v) ? zeros(k) : v[1:k], 1, N)
+    Θ = Matrix{Float64}([X; col(r, nr); col(d, nd); col(isnothing(uprev) ? g.empc.uprev : uprev, nup)])
+    U = Matrix{Float64}(undef, g.nu, N)
+    check(ccall((:lmpc_gpu_evaluate_batch, liblmpcgpu), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}), g.handle, Θ, N, U, C_NULL))
+    g.empc.uprev .= U[:, end]
+    return U
+end
+
+end # module
