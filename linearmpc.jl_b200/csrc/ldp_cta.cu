@@ -1,5 +1,585 @@
-// K3 placeholder (filled in next): CTA-per-QP kernel for n > 32.
+// K3: the large-problem dual active-set LDP kernel (32 < n <= 256, capacity <= 256, m <= 512),
+// e.g. the chain-of-masses controller (n = m = 180) and AFTI-16 with output bounds on the
+// whole horizon (m = 38, capacity 38).
+//
+// Mapping.  One warp drives one QP; a lane owns T working-set positions (i = lane + 32 t),
+// T decision variables and 2T constraint rows, all in statically indexed register tiles.
+// The unit-lower factor L is PACKED (row i holds i entries at i(i-1)/2) in the warp's
+// shared-memory region -- 129 KB at capacity 180, which is why a CTA holds as many QPs as
+// shared memory allows (1 at n = 180, 8 at capacity 38) -- and Mbar / Mbar' / Gram stay in
+// global memory (L2-resident, read coalesced).  Triangular solves are column sweeps over the
+// register tiles (one shuffle broadcast per step), blocked by 32 so that every register index
+// is a compile-time constant.  Cross-element sums follow the canonical lane order of the
+// oracle (element i on lane i mod 32, then xor-butterfly), so results are bit-identical to
+// oracle/ldp_oracle.c and to K1/K2.
+//
+// Reference path replaced: solve(mpc, theta) -> DAQP.update/solve (src/utils.jl:268-283).
 #include "ldp_device.cuh"
-bool ldp_cta_supports(const LdpLayout &) { return false; }
-int launch_ldp_cta(const LdpLayout &, const LdpSettings &, const double *, const ThetaSegs &, int64_t,
-                   const SolveOut &, const SimDesc *, int, void *) { return (int)cudaErrorNotSupported; }
+#include <math_constants.h>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+LMPC_DEVINL double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+LMPC_DEVINL double bfly_sum(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, off));
+  return v;
+}
+LMPC_DEVINL double bfly_min(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double o = __shfl_xor_sync(FULL, v, off);
+    v = (o < v) ? o : v;
+  }
+  return v;
+}
+LMPC_DEVINL double bfly_max(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double o = __shfl_xor_sync(FULL, v, off);
+    v = (o > v) ? o : v;
+  }
+  return v;
+}
+LMPC_DEVINL int bfly_min_i(int v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const int o = __shfl_xor_sync(FULL, v, off);
+    v = (o < v) ? o : v;
+  }
+  return v;
+}
+
+template <int T>
+struct BigQp {
+  double D[T], Dinv[T], lam[T], lams[T], dW[T];
+  int row[T];
+  unsigned low, imm, soft;   // bit t: flag of position lane + 32 t
+  unsigned inws;             // bit t2: row lane + 32 t2 is in the working set (t2 < 2T)
+  int k;
+  bool sing;
+};
+
+struct BigCtx {
+  const double *M, *MT, *G;          // global (L2) copies
+  ConstView cv;                      // shared-memory copies of the small sections
+  const LdpLayout *lay;
+  const LdpSettings *st;
+  double *Lw;      // packed L
+  double *uw;      // n
+  double *thw;     // nth
+  double *lamw;    // cap: lam* broadcast copy
+  int *roww;       // cap: row ids broadcast copy
+  int lane;
+};
+
+#define PIDX(i, c) ((size_t)(i) * ((i)-1) / 2 + (c))
+#define TFOR(t) _Pragma("unroll") for (int t = 0; t < T; ++t)
+
+template <int T>
+LMPC_DEVINL void bq_reset(BigQp<T> &s) {
+  TFOR(t) { s.D[t] = 1.0; s.Dinv[t] = 1.0; s.lam[t] = 0.0; s.lams[t] = 0.0; s.dW[t] = 0.0; s.row[t] = 0; }
+  s.low = s.imm = s.soft = 0u; s.inws = 0u; s.k = 0; s.sing = false;
+}
+
+// value held at position j (tile j>>5, lane j&31), broadcast to the warp; j is warp-uniform
+template <int T>
+LMPC_DEVINL double bcast_pos(const double (&v)[T], int j) {
+  double r = 0.0;
+  TFOR(t) { const double x = shfl_d(v[t], j & 31); r = ((j >> 5) == t) ? x : r; }
+  return r;
+}
+template <int T>
+LMPC_DEVINL int bcast_pos_i(const int (&v)[T], int j) {
+  int r = 0;
+  TFOR(t) { const int x = __shfl_sync(FULL, v[t], j & 31); r = ((j >> 5) == t) ? x : r; }
+  return r;
+}
+
+// z <- L^-1 z on positions [0, kk): column sweep, blocked by tile so register indices are static
+template <int T>
+LMPC_DEVINL void sweep_fwd(const BigCtx &c, double (&z)[T], int kk) {
+#pragma unroll
+  for (int tt = 0; tt < T; ++tt) {
+    const int jend = min(32, kk - 1 - 32 * tt);
+    for (int jj = 0; jj < jend; ++jj) {
+      const int j = 32 * tt + jj;
+      const double zj = shfl_d(z[tt], jj);
+#pragma unroll
+      for (int t = tt; t < T; ++t) {
+        const int i = c.lane + 32 * t;
+        if (i > j && i < kk) z[t] = fma(-c.Lw[PIDX(i, j)], zj, z[t]);
+      }
+    }
+  }
+}
+// x <- L^-T x on positions [0, kk), descending
+template <int T>
+LMPC_DEVINL void sweep_bwd(const BigCtx &c, double (&x)[T], int kk) {
+#pragma unroll
+  for (int tt = T - 1; tt >= 0; --tt) {
+    const int jhi = min(31, kk - 1 - 32 * tt);
+    for (int jj = jhi; jj >= 0; --jj) {
+      const int j = 32 * tt + jj;
+      if (j == 0) break;
+      const double xj = shfl_d(x[tt], jj);
+#pragma unroll
+      for (int t = 0; t <= tt; ++t) {
+        const int i = c.lane + 32 * t;
+        if (i < j) x[t] = fma(-c.Lw[PIDX(j, i)], xj, x[t]);
+      }
+    }
+  }
+}
+
+// canonical lane sum of a[i] * b[i] over positions i < len (element i on lane i mod 32)
+template <int T>
+LMPC_DEVINL double lanesum_pos(const BigCtx &c, const double (&a)[T], const double (&b)[T], int len) {
+  double s = (c.lane < len) ? __dmul_rn(a[0], b[0]) : 0.0;
+#pragma unroll
+  for (int t = 1; t < T; ++t)
+    if (c.lane + 32 * t < len) s = fma(a[t], b[t], s);
+  return bfly_sum(s);
+}
+
+// append row j (oracle: ldl_add)
+template <int T>
+LMPC_DEVINL void bq_add(const BigCtx &c, BigQp<T> &s, int j, bool lower, double dval) {
+  const int m = c.lay->m, k = s.k, lane = c.lane;
+  const double *g = c.G + (size_t)j * m;
+  const int sj = c.cv.sense[j];
+  double dnew = g[j];
+  if (sj & S_SOFT) dnew += c.st->rho_soft;
+  double y[T], l[T];
+  TFOR(t) y[t] = (lane + 32 * t < k) ? g[s.row[t]] : 0.0;
+  sweep_fwd<T>(c, y, k);
+  TFOR(t) l[t] = (lane + 32 * t < k) ? y[t] * s.Dinv[t] : 0.0;
+  dnew = __dsub_rn(dnew, lanesum_pos<T>(c, y, l, k));
+  const bool sing = dnew < c.st->zero_tol;
+  if (sing) dnew = 0.0;
+  const double dinv = sing ? 0.0 : 1.0 / dnew;
+  TFOR(t) {
+    const int i = lane + 32 * t;
+    if (i < k) c.Lw[PIDX(k, i)] = l[t];
+    if (i == k) {
+      s.D[t] = dnew; s.Dinv[t] = dinv; s.lam[t] = 0.0; s.dW[t] = dval; s.row[t] = j;
+      const unsigned bit = 1u << t;
+      s.low = lower ? (s.low | bit) : (s.low & ~bit);
+      s.imm = (sj & S_IMMUTABLE) ? (s.imm | bit) : (s.imm & ~bit);
+      s.soft = (sj & S_SOFT) ? (s.soft | bit) : (s.soft & ~bit);
+      c.roww[k] = j;
+    }
+  }
+  if ((j & 31) == lane) s.inws |= 1u << (j >> 5);
+  s.sing = sing;
+  s.k = k + 1;
+  __syncwarp();
+}
+
+// position i takes the value of position i + 1 (for r <= i < k - 1)
+template <int T>
+LMPC_DEVINL void shift_down(double (&v)[T], int lane, int r, int k) {
+  double nxt[T];
+  TFOR(t) {
+    const double same = __shfl_down_sync(FULL, v[t], 1);
+    const double wrap = (t + 1 < T) ? shfl_d(v[(t + 1 < T) ? t + 1 : t], 0) : 0.0;
+    nxt[t] = (lane < 31) ? same : wrap;
+  }
+  TFOR(t) { const int i = lane + 32 * t; if (i >= r && i + 1 < k) v[t] = nxt[t]; }
+}
+template <int T>
+LMPC_DEVINL void shift_down_i(int (&v)[T], int lane, int r, int k) {
+  int nxt[T];
+  TFOR(t) {
+    const int same = __shfl_down_sync(FULL, v[t], 1);
+    const int wrap = (t + 1 < T) ? __shfl_sync(FULL, v[(t + 1 < T) ? t + 1 : t], 0) : 0;
+    nxt[t] = (lane < 31) ? same : wrap;
+  }
+  TFOR(t) { const int i = lane + 32 * t; if (i >= r && i + 1 < k) v[t] = nxt[t]; }
+}
+template <int T>
+LMPC_DEVINL unsigned shift_down_bits(unsigned bits, int lane, int r, int k) {
+  int v[T];
+  TFOR(t) v[t] = (bits >> t) & 1u;
+  shift_down_i<T>(v, lane, r, k);
+  unsigned o = 0u;
+  TFOR(t) o |= (unsigned)v[t] << t;
+  return o;
+}
+
+// delete position r (oracle: ldl_remove): packed rows are physically shifted, as in the oracle
+template <int T>
+LMPC_DEVINL void bq_remove(const BigCtx &c, BigQp<T> &s, int r) {
+  const int lane = c.lane;
+  int k = s.k;
+  double alpha = bcast_pos<T>(s.D, r);
+  const int rrow = bcast_pos_i<T>(s.row, r);
+  double wv[T];
+  TFOR(t) { const int i = lane + 32 * t; wv[t] = (i > r && i < k) ? c.Lw[PIDX(i, r)] : 0.0; }
+  if ((rrow & 31) == lane) s.inws &= ~(1u << (rrow >> 5));
+  // rows r+1 .. k-1 move up one row and lose column r
+  for (int p = r; p + 1 < k; ++p) {
+    double tmp[T];
+    TFOR(t) { const int cc = lane + 32 * t; tmp[t] = (cc < p) ? c.Lw[PIDX(p + 1, cc < r ? cc : cc + 1)] : 0.0; }
+    __syncwarp();
+    TFOR(t) { const int cc = lane + 32 * t; if (cc < p) c.Lw[PIDX(p, cc)] = tmp[t]; }
+    __syncwarp();
+  }
+  shift_down<T>(s.D, lane, r, k); shift_down<T>(s.Dinv, lane, r, k); shift_down<T>(s.lam, lane, r, k);
+  shift_down<T>(s.dW, lane, r, k); shift_down<T>(wv, lane, r, k); shift_down_i<T>(s.row, lane, r, k);
+  s.low = shift_down_bits<T>(s.low, lane, r, k);
+  s.imm = shift_down_bits<T>(s.imm, lane, r, k);
+  s.soft = shift_down_bits<T>(s.soft, lane, r, k);
+  k -= 1;
+  TFOR(t) { const int i = lane + 32 * t; if (i >= r && i < k) c.roww[i] = s.row[t]; }
+  bool sing = false;
+#pragma unroll
+  for (int tt = 0; tt < T; ++tt) {
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = 32 * tt + jj;
+      if (j < r) continue;
+      if (j >= k) break;
+      const double pj = shfl_d(wv[tt], jj);
+      const double Dj = shfl_d(s.D[tt], jj);
+      const double tq = alpha * pj;
+      double dbar = fma(tq, pj, Dj);
+      double rinv = 1.0 / dbar;
+      const double beta = tq * rinv;
+      alpha = (Dj * alpha) * rinv;
+      if (j == k - 1 && !(dbar >= c.st->zero_tol)) { sing = true; dbar = 0.0; rinv = 0.0; }
+      if (lane == jj) { s.D[tt] = dbar; s.Dinv[tt] = rinv; }
+#pragma unroll
+      for (int t = tt; t < T; ++t) {
+        const int i = lane + 32 * t;
+        if (i > j && i < k) {
+          double *lp = c.Lw + PIDX(i, j);
+          const double lij = *lp;
+          wv[t] = fma(-pj, lij, wv[t]);
+          *lp = fma(beta, wv[t], lij);
+        }
+      }
+    }
+  }
+  s.k = k;
+  s.sing = sing;
+  __syncwarp();
+}
+
+// lowest position holding the minimum of a[] (NaN-free), or -1 when all +inf
+template <int T>
+LMPC_DEVINL int argmin_first(const BigCtx &c, const double (&a)[T], double &amin) {
+  double mine = CUDART_INF;
+  TFOR(t) mine = (a[t] < mine) ? a[t] : mine;
+  amin = bfly_min(mine);
+  int pos = 1 << 30;
+#pragma unroll
+  for (int t = T - 1; t >= 0; --t)
+    if (a[t] == amin && a[t] < CUDART_INF) pos = c.lane + 32 * t;
+  pos = bfly_min_i(pos);
+  return pos == (1 << 30) ? -1 : pos;
+}
+
+template <int T>
+LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T], double (&u)[T], int &iters) {
+  const LdpLayout &lay = *c.lay;
+  const LdpSettings &st = *c.st;
+  const int lane = c.lane, n = lay.n, m = lay.m, mp = lay.mp;
+  int flag = EXIT_ITERLIMIT, iter, cycle = 0;
+  double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
+  for (iter = 1; iter < st.iter_limit; ++iter) {
+    const int k = s.k;
+    double a[T];
+    TFOR(t) a[t] = CUDART_INF;
+    if (!s.sing) {
+      // 1. CSP
+      double z[T];
+      TFOR(t) z[t] = (lane + 32 * t < k) ? -s.dW[t] : 0.0;
+      sweep_fwd<T>(c, z, k);
+      TFOR(t) s.lams[t] = (lane + 32 * t < k) ? z[t] * s.Dinv[t] : 0.0;
+      sweep_bwd<T>(c, s.lams, k);
+      // 2. blocking
+      bool anyblk = false;
+      bool blk[T];
+      TFOR(t) {
+        const bool low = (s.low >> t) & 1u, imm = (s.imm >> t) & 1u;
+        blk[t] = (lane + 32 * t < k) && !imm && (low ? (s.lams[t] > st.dual_tol) : (s.lams[t] < -st.dual_tol));
+        anyblk |= blk[t];
+      }
+      if (!__any_sync(FULL, anyblk)) {
+        // 3. u = -M_W' lam*
+        TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = s.lams[t]; }
+        __syncwarp();
+        TFOR(t) u[t] = 0.0;
+        for (int i = 0; i < k; ++i) {
+          const double li = c.lamw[i];
+          const double *mr = c.M + (size_t)c.roww[i] * n;
+          TFOR(t) { const int cc = lane + 32 * t; if (cc < n) u[t] = fma(-li, mr[cc], u[t]); }
+        }
+        TFOR(t) { const int cc = lane + 32 * t; if (cc < n) c.uw[cc] = u[t]; }
+        __syncwarp();
+        fval = lanesum_pos<T>(c, u, u, n);
+        soft_slack = 0.0;
+        if (lay.nsoft > 0) {
+          double sl[T];
+          double smax = 0.0;
+          TFOR(t) {
+            const bool sf = (lane + 32 * t < k) && ((s.soft >> t) & 1u);
+            sl[t] = sf ? s.lams[t] : 0.0;
+            const double v = st.rho_soft * fabs(s.lams[t]);
+            if (sf && v > smax) smax = v;
+          }
+          fval = fma(st.rho_soft, lanesum_pos<T>(c, sl, s.lams, k), fval);
+          soft_slack = bfly_max(smax);
+        }
+        if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
+        // slack scan: rows lane + 32 t2; the loop over columns is outermost for ILP across rows
+        double mu[2 * T];
+#pragma unroll
+        for (int t2 = 0; t2 < 2 * T; ++t2) mu[t2] = 0.0;
+        for (int cc = 0; cc < n; ++cc) {
+          const double uc = c.uw[cc];
+          const double *mt = c.MT + (size_t)cc * mp + lane;
+#pragma unroll
+          for (int t2 = 0; t2 < 2 * T; ++t2)
+            if (lane + 32 * t2 < m) mu[t2] = fma(mt[32 * t2], uc, mu[t2]);
+        }
+        double best = CUDART_INF, bestd = 0.0;
+        int bestj = 1 << 30;
+        bool bestlow = false;
+#pragma unroll
+        for (int t2 = 0; t2 < 2 * T; ++t2) {
+          const int j = lane + 32 * t2;
+          if (j < m && !((s.inws >> t2) & 1u) && !(c.cv.sense[j] & S_IMMUTABLE)) {
+            const double dU = c.cv.du[j] + sh[t2], dLo = c.cv.dl[j] + sh[t2];
+            const double su = dU - mu[t2], sl = mu[t2] - dLo;
+            if (su < -st.primal_tol && su < best) { best = su; bestd = dU; bestj = j; bestlow = false; }
+            else if (!(su < -st.primal_tol) && sl < -st.primal_tol && sl < best) { best = sl; bestd = dLo; bestj = j; bestlow = true; }
+          }
+        }
+        const double vmin = bfly_min(best);
+        const int add = bfly_min_i((best == vmin && bestj < (1 << 30)) ? bestj : (1 << 30));
+        if (add == (1 << 30)) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
+        if (k >= lay.cap || k >= 32 * T) { flag = EXIT_CAPACITY; break; }
+        const int src = add & 31;
+        const bool addlow = __shfl_sync(FULL, (int)(bestj == add && bestlow), src);
+        const double addd = shfl_d(bestd, src);
+        TFOR(t) if (lane + 32 * t < k) s.lam[t] = s.lams[t];
+        bq_add<T>(c, s, add, addlow, addd);
+        continue;
+      }
+      // 4. blocking
+      if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+      else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+      TFOR(t) if (blk[t]) { a[t] = -s.lam[t] / (s.lams[t] - s.lam[t]); if (!(a[t] == a[t])) a[t] = CUDART_INF; }
+      double alpha;
+      const int rm = argmin_first<T>(c, a, alpha);
+      if (rm < 0) { flag = EXIT_CYCLE; break; }
+      TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, s.lams[t] - s.lam[t], s.lam[t]);
+      bq_remove<T>(c, s, rm);
+    } else {
+      // 5. singular direction
+      const int kk = k - 1;
+      bool lastlow = false;
+      {
+        int lowv[T];
+        TFOR(t) lowv[t] = (s.low >> t) & 1u;
+        lastlow = bcast_pos_i<T>(lowv, kk) != 0;
+      }
+      double p[T];
+      TFOR(t) { const int i = lane + 32 * t; p[t] = (i < kk) ? -c.Lw[PIDX(kk, i)] : 0.0; }
+      sweep_bwd<T>(c, p, kk);
+      TFOR(t) {
+        const int i = lane + 32 * t;
+        if (i == kk) p[t] = 1.0;
+        if (lastlow && i <= kk) p[t] = -p[t];
+        s.lams[t] = (i < k) ? p[t] : 0.0;
+        const bool low = (s.low >> t) & 1u, imm = (s.imm >> t) & 1u;
+        const bool b = (i < k) && !imm && (low ? (p[t] > st.dual_tol) : (p[t] < -st.dual_tol));
+        if (b) { a[t] = -s.lam[t] / p[t]; if (!(a[t] == a[t])) a[t] = CUDART_INF; }
+      }
+      double alpha;
+      const int rm = argmin_first<T>(c, a, alpha);
+      if (rm < 0) { flag = EXIT_INFEASIBLE; break; }
+      TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, p[t], s.lam[t]);
+      bq_remove<T>(c, s, rm);
+    }
+  }
+  iters = iter;
+  return flag;
+}
+
+template <int T>
+LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iters) {
+  const LdpLayout &lay = *c.lay;
+  const int lane = c.lane, m = lay.m, nth = lay.nth;
+  double sh[2 * T];
+#pragma unroll
+  for (int t2 = 0; t2 < 2 * T; ++t2) {
+    sh[t2] = 0.0;
+    const int j = lane + 32 * t2;
+    if (j < m) {
+      const double *dr = c.cv.Dth + (size_t)j * nth;
+      double acc = 0.0;
+      for (int t = 0; t < nth; ++t) acc = fma(dr[t], c.thw[t], acc);
+      sh[t2] = acc;
+    }
+  }
+  int flag = 0;
+  bq_reset<T>(s);
+  TFOR(t) u[t] = 0.0;
+  for (int j = 0; lay.neq > 0 && j < m; ++j) {
+    const int sj = c.cv.sense[j];
+    if (sj & S_ACTIVE) {
+      if (s.k >= lay.cap || s.k >= 32 * T) { flag = EXIT_OVERDETERMINED; break; }
+      const bool low = sj & S_LOWER;
+      double shj = 0.0;
+#pragma unroll
+      for (int t2 = 0; t2 < 2 * T; ++t2) { const double x = shfl_d(sh[t2], j & 31); shj = ((j >> 5) == t2) ? x : shj; }
+      bq_add<T>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
+      if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
+    }
+  }
+  iters = 0;
+  if (flag == 0) flag = bq_loop<T>(c, s, sh, u, iters);
+  return flag;
+}
+
+struct K3Geom { int warps; size_t per_warp; size_t small_total; size_t smem; };
+
+// shared memory holds only the small constant sections (Dth, du, dl, Rinv, Uth, uoff, sense):
+// they are contiguous at the tail of the block starting at oDth
+LMPC_DEVINL int small_off(const LdpLayout &lay) { return lay.oDth; }
+
+template <int T>
+__global__ void __launch_bounds__(256)
+ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
+               const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out,
+               int warps, int per_warp_doubles) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int soff = small_off(lay);
+  stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
+  BigCtx c;
+  c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
+  const double *sb = smem - soff;    // so that section offsets stay valid
+  c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
+  c.cv.Dth = sb + lay.oDth; c.cv.du = sb + lay.odu; c.cv.dl = sb + lay.odl; c.cv.Rinv = sb + lay.oRinv;
+  c.cv.Uth = sb + lay.oUth; c.cv.uoff = sb + lay.ouoff;
+  c.cv.sense = reinterpret_cast<const int32_t *>(sb + lay.oSense);
+  c.lay = &lay; c.st = &st;
+  const int warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  double *w = smem + (lay.total - soff) + (size_t)warp * per_warp_doubles;
+  const int cap = lay.cap;
+  c.Lw = w; w += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+  c.uw = w; w += (lay.n + 1) & ~1;
+  c.thw = w; w += (lay.nth + 1) & ~1;
+  c.lamw = w; w += (cap + 1) & ~1;
+  c.roww = reinterpret_cast<int *>(w);
+  const int lane = c.lane, words = (lay.m + 63) >> 6;
+  const int64_t wid = (int64_t)blockIdx.x * warps + warp;
+  const int64_t wstride = (int64_t)gridDim.x * warps;
+  BigQp<T> s;
+  double u[T];
+  for (int64_t q = wid; q < Ninst; q += wstride) {
+    int o = 0;
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg) {
+      if (sg < th.nseg) {
+        const int len = th.len[sg];
+        for (int t = lane; t < len; t += 32) c.thw[o + t] = ld_stream(th.ptr[sg] + q * th.stride[sg] + t);
+        o += len;
+      }
+    }
+    __syncwarp();
+    int iters;
+    const int flag = bq_solve<T>(c, s, u, iters);
+    // output map: canonical lane sum over the n variables, one control at a time
+    for (int i = 0; i < lay.nu; ++i) {
+      double rr[T];
+      TFOR(t) { const int cc = lane + 32 * t; rr[t] = (cc < lay.n) ? c.cv.Rinv[(size_t)i * lay.n + cc] : 0.0; }
+      const double x = lanesum_pos<T>(c, rr, u, lay.n);
+      double shv = c.cv.uoff[i];
+      const double *ur = c.cv.Uth + (size_t)i * lay.nth;
+      for (int t = 0; t < lay.nth; ++t) shv = fma(ur[t], c.thw[t], shv);
+      if (lane == 0) out.U[q * lay.nu + i] = __dadd_rn(x, shv);
+    }
+    if (out.act_u) {
+      for (int wd = lane; wd < words; wd += 32) { out.act_u[q * words + wd] = 0ull; out.act_l[q * words + wd] = 0ull; }
+      __syncwarp();
+      TFOR(t) {
+        const int i = lane + 32 * t;
+        if (i < s.k) {
+          const int j = s.row[t];
+          unsigned long long *dst = reinterpret_cast<unsigned long long *>(((s.low >> t) & 1u) ? out.act_l : out.act_u) + q * words + (j >> 6);
+          atomicOr(dst, 1ull << (j & 63));
+        }
+      }
+    }
+    if (lane == 0) {
+      out.flag[q] = flag;
+      if (out.iters) out.iters[q] = iters;
+    }
+    __syncwarp();
+  }
+}
+
+K3Geom k3_geom(const LdpLayout &lay) {
+  K3Geom g;
+  const size_t cap = lay.cap;
+  size_t pw = ((cap * (cap - 1) / 2 + 1) & ~(size_t)1) + ((lay.n + 1) & ~1) + ((lay.nth + 1) & ~1) +
+              ((cap + 1) & ~1) + ((cap + 1) / 2 + 1);
+  pw = (pw + 1) & ~(size_t)1;
+  g.per_warp = pw;
+  g.small_total = (size_t)(lay.total - lay.oDth);
+  const size_t budget = 200 * 1024 / sizeof(double);
+  int w = (int)((budget - g.small_total) / pw);
+  if (g.small_total + pw > budget) w = 0;
+  if (w > 8) w = 8;
+  g.warps = w;
+  g.smem = (g.small_total + pw * (w > 0 ? w : 1)) * sizeof(double);
+  return g;
+}
+
+template <int T>
+int launch_big(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
+               int64_t N, const SolveOut &out, int sm_count, cudaStream_t s) {
+  const K3Geom g = k3_geom(lay);
+  auto kern = ldp_big_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.warps * 32, g.smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (N + g.warps - 1) / g.warps;
+  if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+  kern<<<(unsigned)blocks, g.warps * 32, g.smem, s>>>(lay, st, cblk, th, N, out, g.warps, (int)g.per_warp);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+bool ldp_cta_supports(const LdpLayout &lay) {
+  if (lay.n < 1 || lay.n > 256 || lay.cap > 256 || lay.m > 512) return false;
+  return k3_geom(lay).warps >= 1;
+}
+
+int launch_ldp_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                   const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                   int sm_count, void *stream) {
+  if (sim) return (int)cudaErrorNotSupported;   // closed loop runs on K1/K2 (round 1)
+  if (N <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int need = lay.cap > lay.n ? lay.cap : lay.n;
+  if ((lay.m + 1) / 2 > need) need = (lay.m + 1) / 2;
+  const int T = (need + 31) / 32;
+  switch (T) {
+    case 1: case 2: return launch_big<2>(lay, st, cblk, th, N, out, sm_count, s);
+    case 3: case 4: return launch_big<4>(lay, st, cblk, th, N, out, sm_count, s);
+    case 5: case 6: return launch_big<6>(lay, st, cblk, th, N, out, sm_count, s);
+    case 7: case 8: return launch_big<8>(lay, st, cblk, th, N, out, sm_count, s);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
