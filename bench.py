@@ -256,10 +256,8 @@ def main():
     launches = lmpc_b200.launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_step]))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+        ms_total = lmpc_b200.max_over_ranks(ms_total, device=dev)
     ok_all = bool((flag >= 1).all().item())
 
     # ---- end-to-end through the C ABI with pinned host buffers ----------------------------------
@@ -280,24 +278,21 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+        e2e_s = lmpc_b200.max_over_ranks(e2e_s, device=dev)
     e2e_ok = bool(torch.equal(U_h, U.cpu()))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- final result gather (the only inter-GPU traffic of the path), untimed but checked ------
     gather_ms = None
     if world > 1:
-        outs = [torch.empty_like(U) for _ in range(world)] if rank == 0 else None
         torch.cuda.synchronize(); dist.barrier()
         tg = time.perf_counter()
-        dist.gather(U, outs, dst=0)
+        allU = lmpc_b200.gather_columns(U.T, n_per * world)      # nu x (N * world) on rank 0
         torch.cuda.synchronize()
         gather_ms = 1e3 * (time.perf_counter() - tg)
         if rank == 0:
-            assert torch.equal(outs[0], U)
+            assert torch.equal(allU[:, :n_per], U.T)
 
     if rank == 0:
         total_solves = float(n_per) * world * args.steps
