@@ -361,6 +361,9 @@ LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T],
         const double vmin = bfly_min(best);
         const int add = bfly_min_i((best == vmin && bestj < (1 << 30)) ? bestj : (1 << 30));
         if (add == (1 << 30)) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
+        // cycle guard where the dual objective is fresh (see oracle/ldp_oracle.c)
+        if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+        else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
         if (k >= lay.cap || k >= 32 * T) { flag = EXIT_CAPACITY; break; }
         const int src = add & 31;
         const bool addlow = __shfl_sync(FULL, (int)(bestj == add && bestlow), src);
@@ -370,8 +373,6 @@ LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T],
         continue;
       }
       // 4. blocking
-      if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-      else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
       TFOR(t) if (blk[t]) { a[t] = -s.lam[t] / (s.lams[t] - s.lam[t]); if (!(a[t] == a[t])) a[t] = CUDART_INF; }
       double alpha;
       const int rm = argmin_first<T>(c, a, alpha);

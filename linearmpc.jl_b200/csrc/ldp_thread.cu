@@ -278,14 +278,15 @@ LMPC_DEVINL int qp_loop(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
           }
         }
         if (add < 0) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
+        // cycle guard where the dual objective is fresh (see oracle/ldp_oracle.c)
+        if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+        else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
         if (k >= CAP) { flag = EXIT_CAPACITY; break; }
         SFOR(i, 0, CAP) s.lam[i] = (i < k) ? s.lams[i] : s.lam[i]; SEND
         qp_add<N, CAP>(s, cv, m, st, add, addlow, addd);
         continue;
       }
-      // 4. blocking: cycle guard, step, remove
-      if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-      else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+      // 4. blocking: step, remove
       if (!(alpha < CUDART_INF)) { flag = EXIT_CYCLE; break; }   // blocked but no finite ratio
       SFOR(i, 0, CAP)
         s.lam[i] = (i < k) ? fma(alpha, s.lams[i] - s.lam[i], s.lam[i]) : s.lam[i];

@@ -252,6 +252,9 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         const unsigned hit0 = __ballot_sync(FULL, hit && bestj < 32);
         const unsigned hit1 = __ballot_sync(FULL, hit && bestj >= 32);
         if (!(hit0 | hit1)) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
+        // cycle guard where the dual objective is fresh (see oracle/ldp_oracle.c)
+        if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+        else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
         if (k >= lay.cap || k >= 32) { flag = EXIT_CAPACITY; break; }
         const int src = hit0 ? (__ffs(hit0) - 1) : (__ffs(hit1) - 1);
         const int add = __shfl_sync(FULL, bestj, src);
@@ -261,9 +264,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         wq_add(c, s, add, addlow, addd);
         continue;
       }
-      // 4. blocking: cycle guard, ratio test, step, remove
-      if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-      else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+      // 4. blocking: ratio test, step, remove
       if (blk) {
         a = -s.lam / (s.lams - s.lam);
         if (!(a == a)) a = CUDART_INF;

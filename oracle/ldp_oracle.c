@@ -216,13 +216,15 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
         }
         if (fl) *fl += 2.0 * n * (m - k);
         if (add < 0) { flag = soft_slack > p->primal_tol ? ORC_SOFT_OPTIMAL : ORC_OPTIMAL; break; }
+        /* cycle guard, evaluated where the dual objective is fresh: a new dual-feasible iterate
+         * that still violates a row must have raised fval by progress_tol, or the counter runs */
+        if (fval - p->progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+        else if (cycle++ > p->cycle_tol) { flag = ORC_CYCLE; break; }
         for (int i = 0; i < k; ++i) w->lam[i] = w->lams[i];
         ldl_add(p, w, add, addside, fl);
         continue;
       }
-      /* 4. blocking: cycle guard, ratio test, remove */
-      if (fval - p->progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-      else if (cycle++ > p->cycle_tol) { flag = ORC_CYCLE; break; }
+      /* 4. blocking: ratio test, step, remove */
       double alpha = INFINITY; int rm = -1;
       for (int i = 0; i < k; ++i) {
         if (p->sense[w->ws[i]] & ORC_IMMUTABLE) continue;
