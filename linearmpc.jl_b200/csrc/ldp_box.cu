@@ -1,0 +1,288 @@
+// K1b: thread-per-QP fast path for BOX-ONLY problems (m == n simple bounds, no soft /
+// equality / general rows, n <= 8, nu <= 2) -- the shape of the headline workload
+// (inverted pendulum: n = m = 5, nth = 7, nu = 1).
+//
+// Same algorithm and the same arithmetic as ldp_thread.cu (bit-identical results), restructured
+// to cut the instruction count, which is what bounds this kernel (ncu r01: issue slots 54 %
+// busy with 12 warps/SM, FP64 pipe 18 %, 7350 thread-instructions per solve for 578
+// algorithmic flops):
+//   * "unused slots are zero rows": positions >= k always hold L row 0, D = 1/D = 1,
+//     d_W = lam = 0, so the CSP solve, the step and the primal update run unpredicated over
+//     the full capacity and produce exact zeros there (no per-slot selects / predicates);
+//   * the slack scan is unrolled over the m == N rows, uses the triangular structure of the
+//     normalised R^-1 rows (row j starts at column j) and keeps sh_j in registers;
+//   * theta is consumed as it is loaded: one pass accumulates every sh_j and the output
+//     shift, so theta never sits in shared memory;
+//   * no immutable / soft / singular handling at all (cannot occur for this class).
+#include "ldp_device.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int KB_BLOCK = 128;
+
+template <int N>
+struct BoxState {
+  double L[N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1];
+  double D[N], Dinv[N], lam[N], lams[N], dW[N];
+  int row[N];
+  unsigned lowmask;  // bit i: position i active at its LOWER bound
+  unsigned inws;     // bit j: row j in the working set
+  int k;
+};
+
+template <int N>
+LMPC_DEVINL void box_reset(BoxState<N> &s) {
+  s.k = 0; s.lowmask = 0u; s.inws = 0u;
+  SFOR(i, 0, N) s.D[i] = 1.0; s.Dinv[i] = 1.0; s.lam[i] = 0.0; s.lams[i] = 0.0; s.dW[i] = 0.0; s.row[i] = 0; SEND
+  SFOR(i, 0, N * (N - 1) / 2) s.L[i] = 0.0; SEND
+}
+
+// append row j (oracle: ldl_add).  Rows are independent for a box problem: never singular.
+template <int N>
+LMPC_DEVINL void box_add(BoxState<N> &s, const double *G, int j, bool lower, double dval) {
+  const double *g = G + j * N;
+  const int k = s.k;
+  double y[N], l[N], pr[N];
+  SFOR(i, 0, N)
+    double yi = (i < k) ? g[s.row[i]] : 0.0;
+    SFOR(c, 0, i) yi = fma(-s.L[LIDX(i, c)], y[c], yi); SEND
+    y[i] = yi;
+  SEND
+  SFOR(i, 0, N) l[i] = y[i] * s.Dinv[i]; pr[i] = __dmul_rn(y[i], l[i]); SEND
+  const double dnew = __dsub_rn(g[j], tree_sum<N, 0, 1>(pr));
+  const double dinv = 1.0 / dnew;
+  SFOR(kk, 0, N)
+    const bool here = (kk == k);
+    SFOR(i, 0, kk) s.L[LIDX(kk, i)] = here ? l[i] : s.L[LIDX(kk, i)]; SEND
+    s.D[kk] = here ? dnew : s.D[kk];
+    s.Dinv[kk] = here ? dinv : s.Dinv[kk];
+    s.dW[kk] = here ? dval : s.dW[kk];
+    s.row[kk] = here ? j : s.row[kk];
+  SEND
+  const unsigned bit = 1u << k;
+  s.lowmask = lower ? (s.lowmask | bit) : (s.lowmask & ~bit);
+  s.inws |= 1u << j;
+  s.k = k + 1;
+}
+
+// delete position r (oracle: ldl_remove); vacated slots become zero rows again
+template <int N>
+LMPC_DEVINL void box_remove(BoxState<N> &s, int r) {
+  const int k = s.k - 1;   // size after removal
+  double alpha = 0.0, wv[N];
+  int rrow = 0;
+  SFOR(i, 0, N)
+    wv[i] = 0.0;
+    alpha = (i == r) ? s.D[i] : alpha;
+    rrow = (i == r) ? s.row[i] : rrow;
+    SFOR(c, 0, i) wv[i] = (c == r) ? s.L[LIDX(i, c)] : wv[i]; SEND
+  SEND
+  s.inws &= ~(1u << rrow);
+  // position p takes old position p + 1 for every p >= r; the last slot becomes a zero row
+  SFOR(p, 0, N)
+    const bool mv = (p >= r);
+    if constexpr (p + 1 < N) {
+      SFOR(c, 0, p)
+        const double src = (c < r) ? s.L[LIDX(p + 1, c)] : s.L[LIDX(p + 1, c + 1)];
+        s.L[LIDX(p, c)] = mv ? src : s.L[LIDX(p, c)];
+      SEND
+      s.D[p] = mv ? s.D[p + 1] : s.D[p];
+      s.Dinv[p] = mv ? s.Dinv[p + 1] : s.Dinv[p];
+      s.lam[p] = mv ? s.lam[p + 1] : s.lam[p];
+      s.dW[p] = mv ? s.dW[p + 1] : s.dW[p];
+      s.row[p] = mv ? s.row[p + 1] : s.row[p];
+      wv[p] = mv ? wv[p + 1] : wv[p];
+    } else {
+      SFOR(c, 0, p) s.L[LIDX(p, c)] = 0.0; SEND
+      s.D[p] = 1.0; s.Dinv[p] = 1.0; s.lam[p] = 0.0; s.dW[p] = 0.0; wv[p] = 0.0;
+    }
+  SEND
+  const unsigned lo = s.lowmask & ((1u << r) - 1u);
+  s.lowmask = lo | ((s.lowmask >> (r + 1)) << r);
+  SFOR(j, 0, N - 1)
+    if (j >= r && j < k) {
+      const double pj = wv[j];
+      const double t = alpha * pj;
+      const double dbar = fma(t, pj, s.D[j]);
+      const double rinv = 1.0 / dbar;
+      const double beta = t * rinv;
+      alpha = (s.D[j] * alpha) * rinv;
+      s.D[j] = dbar; s.Dinv[j] = rinv;
+      SFOR(i, j + 1, N - 1)
+        // rows >= k are zero rows with wv == 0: the update is an exact no-op there
+        wv[i] = fma(-pj, s.L[LIDX(i, j)], wv[i]);
+        s.L[LIDX(i, j)] = fma(beta, wv[i], s.L[LIDX(i, j)]);
+      SEND
+    }
+  SEND
+  s.k = k;
+}
+
+template <int N, int NU>
+__global__ void __launch_bounds__(KB_BLOCK, 4)
+ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, ThetaSegs th,
+               int64_t Ninst, SolveOut out) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  stage_constants_tma(smem, cblk, lay.total, &mbar);
+  const ConstView cv = make_view(smem, lay);
+  const int nth = lay.nth;
+  BoxState<N> s;
+  for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst;
+       q += (int64_t)gridDim.x * KB_BLOCK) {
+    // ---- mpc_update_parameter + mpc_update_qp + output shift in one pass over theta ----------
+    double sh[N], sho[NU];
+    SFOR(j, 0, N) sh[j] = 0.0; SEND
+    SFOR(i, 0, NU) sho[i] = cv.uoff[i]; SEND
+    int o = 0;
+    SFOR(sg, 0, 4)
+      if (sg < th.nseg) {
+        const int len = th.len[sg];
+        const double *src = th.ptr[sg] + q * th.stride[sg];
+        for (int t = 0; t < len; ++t) {
+          const double tv = ld_stream(src + t);
+          const int tt = o + t;
+          SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
+          SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
+        }
+        o += len;
+      }
+    SEND
+    // ---- dual active-set loop, cold start --------------------------------------------------
+    box_reset<N>(s);
+    double u[N];
+    SFOR(c, 0, N) u[c] = 0.0; SEND
+    int flag = EXIT_ITERLIMIT, iter, cycle = 0;
+    double best_fval = -1.0, fval = 0.0;
+    for (iter = 1; iter < st.iter_limit; ++iter) {
+      // 1. CSP over the full capacity (slots >= k are zero rows -> exact zeros)
+      double z[N];
+      SFOR(i, 0, N)
+        double zi = -s.dW[i];
+        SFOR(c, 0, i) zi = fma(-s.L[LIDX(i, c)], z[c], zi); SEND
+        z[i] = zi;
+      SEND
+      SFOR(i, 0, N) s.lams[i] = z[i] * s.Dinv[i]; SEND
+      SFOR_DOWN(j, N, 1)
+        const double xj = s.lams[j];
+        SFOR(i, 0, j) s.lams[i] = fma(-s.L[LIDX(j, i)], xj, s.lams[i]); SEND
+      SEND
+      // 2. blocking set (an unused slot has lam* == 0 and can never block)
+      unsigned blkmask = 0u;
+      SFOR(i, 0, N)
+        const bool low = (s.lowmask >> i) & 1u;
+        const bool blk = low ? (s.lams[i] > st.dual_tol) : (s.lams[i] < -st.dual_tol);
+        blkmask |= blk ? (1u << i) : 0u;
+      SEND
+      if (blkmask == 0u) {
+        // 3. primal iterate, dual objective, most violated row
+        SFOR(c, 0, N) u[c] = 0.0; SEND
+        SFOR(i, 0, N)
+          const double *mr = cv.M + s.row[i] * N;
+          const double li = s.lams[i];
+          SFOR(c, 0, N) u[c] = fma(-li, mr[c], u[c]); SEND
+        SEND
+        double pu[N];
+        SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
+        fval = tree_sum<N, 0, 1>(pu);
+        if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
+        double best = -st.primal_tol, addd = 0.0;
+        int add = -1;
+        bool addlow = false;
+        SFOR(j, 0, N)
+          // row j of the normalised R^-1 is zero before column j
+          double mu = 0.0;
+          SFOR(c, j, N) mu = fma(cv.M[j * N + c], u[c], mu); SEND
+          const bool free_row = !((s.inws >> j) & 1u);
+          const double dU = cv.du[j] + sh[j];
+          const double dLo = cv.dl[j] + sh[j];
+          const double su = dU - mu, sl = mu - dLo;
+          const bool tu = free_row && (su < best);
+          const bool tl = free_row && !tu && (sl < best);
+          best = tu ? su : (tl ? sl : best);
+          addd = tu ? dU : (tl ? dLo : addd);
+          add = (tu || tl) ? j : add;
+          addlow = tu ? false : (tl ? true : addlow);
+        SEND
+        if (add < 0) { flag = EXIT_OPTIMAL; break; }
+        if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+        else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+        if (s.k >= N) { flag = EXIT_CAPACITY; break; }
+        SFOR(i, 0, N) s.lam[i] = s.lams[i]; SEND
+        box_add<N>(s, cv.G, add, addlow, addd);
+      } else {
+        // 4. ratio test (first minimum wins), step, remove
+        double alpha = CUDART_INF;
+        int rm = -1;
+        SFOR(i, 0, N)
+          if ((blkmask >> i) & 1u) {
+            const double a = -s.lam[i] / (s.lams[i] - s.lam[i]);
+            if (a < alpha) { alpha = a; rm = i; }
+          }
+        SEND
+        if (!(alpha < CUDART_INF)) { flag = EXIT_CYCLE; break; }
+        SFOR(i, 0, N) s.lam[i] = fma(alpha, s.lams[i] - s.lam[i], s.lam[i]); SEND
+        box_remove<N>(s, rm);
+      }
+    }
+    // ---- mpc_get_solution -------------------------------------------------------------------
+    SFOR(i, 0, NU)
+      double pr[N];
+      SFOR(c, 0, N) pr[c] = __dmul_rn(cv.Rinv[i * N + c], u[c]); SEND
+      out.U[q * NU + i] = __dadd_rn(tree_sum<N, 0, 1>(pr), sho[i]);
+    SEND
+    out.flag[q] = flag;
+    if (out.iters) out.iters[q] = iter;
+    if (out.act_u) {
+      unsigned long long au = 0ull, al = 0ull;
+      SFOR(i, 0, N)
+        if (i < s.k) {
+          if ((s.lowmask >> i) & 1u) al |= 1ull << s.row[i]; else au |= 1ull << s.row[i];
+        }
+      SEND
+      out.act_u[q] = au;
+      out.act_l[q] = al;
+    }
+  }
+}
+
+template <int N, int NU>
+int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
+               int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
+  auto kern = ldp_box_kernel<N, NU>;
+  const size_t smem = (size_t)lay.total * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KB_BLOCK, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
+  const int64_t cap = (int64_t)sm_count * per_sm;   // persistent: whole resident waves over the SMs
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, cblk, th, Ninst, out);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+bool ldp_box_supports(const LdpLayout &lay) {
+  return lay.plain && lay.m == lay.n && lay.n >= 1 && lay.n <= 8 && lay.nu >= 1 && lay.nu <= 2 &&
+         lay.nu <= lay.n && lay.cap <= lay.n;
+}
+
+#define KB_CASE(NN)                                                                              \
+  case NN:                                                                                       \
+    if (lay.nu == 1) return launch_box<NN, 1>(lay, st, cblk, th, N, out, sm_count, s);           \
+    if constexpr (NN >= 2) return launch_box<NN, 2>(lay, st, cblk, th, N, out, sm_count, s);     \
+    return (int)cudaErrorInvalidValue;
+
+int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                   const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N <= 0) return 0;
+  switch (lay.n) {
+    KB_CASE(1) KB_CASE(2) KB_CASE(3) KB_CASE(4) KB_CASE(5) KB_CASE(6) KB_CASE(7) KB_CASE(8)
+    default: return (int)cudaErrorInvalidValue;
+  }
+}

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 #include "lmpc_common.h"
 
 #define LMPC_DEVINL __device__ __forceinline__
@@ -78,3 +79,40 @@ LMPC_DEVINL double ld_stream(const double *p) {
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+
+// ---- compile-time loops and the canonical tree sum (shared by the thread-per-QP kernels) ----
+#define LIDX(i, c) ((i) * ((i)-1) / 2 + (c))
+
+// Compile-time loops.  Every index into per-thread state is a constant at the front end, so
+// the state is scalarised into registers before any optimisation pass can rewrite a chain of
+// "slot == run-time position" selects into one dynamically indexed (local-memory) access.
+template <int B, int E, class F>
+LMPC_DEVINL void sfor(F &&f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    sfor<B + 1, E>(f);
+  }
+}
+template <int B, int E, class F>   // B-1, B-2, ..., E
+LMPC_DEVINL void sfor_down(F &&f) {
+  if constexpr (B > E) {
+    f(std::integral_constant<int, B - 1>{});
+    sfor_down<B - 1, E>(f);
+  }
+}
+#define SFOR(var, B, E) sfor<B, E>([&](auto var##_c) { constexpr int var = decltype(var##_c)::value;
+#define SFOR_DOWN(var, B, E) sfor_down<B, E>([&](auto var##_c) { constexpr int var = decltype(var##_c)::value;
+#define SEND });
+
+// Canonical cross-element sum (see oracle/ldp_oracle.c: lanesum): element i lives on lane
+// i mod 32 and the lanes are combined by an xor-butterfly, i.e. the value on lane 0 is
+// S(base, step) = S(base, 2 step) + S(base + step, 2 step), S(base, 32) = p[base].  With
+// LEN <= 32 every lane holds at most one product, so a thread can evaluate the same tree
+// statically (sub-trees that only contain padding zeros are skipped: x + 0 == x).
+template <int LEN, int BASE, int STEP>
+LMPC_DEVINL double tree_sum(const double (&p)[LEN]) {
+  if constexpr (STEP >= 32) return p[BASE];
+  else if constexpr (BASE + STEP >= LEN) return tree_sum<LEN, BASE, 2 * STEP>(p);
+  else return __dadd_rn(tree_sum<LEN, BASE, 2 * STEP>(p), tree_sum<LEN, BASE + STEP, 2 * STEP>(p));
+}
+

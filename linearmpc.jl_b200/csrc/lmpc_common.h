@@ -24,6 +24,7 @@ struct LdpLayout {
   int nsoft;
   int has_general; // m > ms or any soft row: singular branch reachable
   int neq;         // rows with the ACTIVE sense bit (equalities): activated at cold start
+  int plain;       // box-only problem: m == ms, every sense word is 0 (no soft/equality/immutable)
   // offsets in doubles into the constant block
   int oM, oMT, oG, oDth, odu, odl, oRinv, oUth, ouoff, oSense;
   int total;      // block size in doubles (multiple of 2 -> 16 bytes)
@@ -88,6 +89,9 @@ int launch_ldp_cta(const LdpLayout &lay, const LdpSettings &st, const double *cb
                    const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
                    int sm_count, void *stream);
 bool ldp_thread_supports(const LdpLayout &lay);
+bool ldp_box_supports(const LdpLayout &lay);
+int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                   const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream);
 bool ldp_warp_supports(const LdpLayout &lay);
 bool ldp_cta_supports(const LdpLayout &lay);
 

@@ -133,6 +133,8 @@ int lmpc_host_setup(const lmpc_problem *p, LdpHost *out, char *err, int errlen) 
   int neq = 0;
   for (int i = 0; i < m; ++i) if (sense[i] & S_ACTIVE) neq++;
   lay.neq = neq;
+  lay.plain = (m == ms) ? 1 : 0;
+  for (int i = 0; i < m; ++i) if (sense[i] != 0) lay.plain = 0;
   for (int i = 0; i < m; ++i)
     for (int c = 0; c < n; ++c) MT[(size_t)c * lay.mp + i] = M[(size_t)i * n + c];
   for (int i = 0; i < m; ++i)
