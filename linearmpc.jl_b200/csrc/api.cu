@@ -443,21 +443,23 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
   int rc = check_device(device, &sm);
   if (rc) return rc;
   const int ld = nth + 1;
+  // rows are read as 16-byte pairs: an odd number of pairs per row spreads divergent row
+  // gathers over all eight 16-byte bank groups
+  const int ldh = 2 * (((ld + 1) / 2) | 1);
   auto al2 = [](size_t x) { return (x + 1) & ~(size_t)1; };
-  const size_t ohp = 0, ofb = al2((size_t)n_hp * ld), oclip = ofb + al2((size_t)n_fb * nu * ld);
-  const size_t olist = oclip + al2((size_t)2 * nu), total = olist + al2((size_t)(2 * n_nodes + 1) / 2);
+  const size_t onodes = 0, ohp = al2((size_t)n_nodes), ofb = ohp + al2((size_t)n_hp * ldh);
+  const size_t oclip = ofb + al2((size_t)n_fb * nu * ldh), total = oclip + al2((size_t)2 * nu);
   std::vector<double> blk(total, 0.0);
+  int32_t *nodes = reinterpret_cast<int32_t *>(blk.data() + onodes);
+  for (int i = 0; i < n_nodes; ++i) { nodes[2 * i] = jump_list[i]; nodes[2 * i + 1] = hp_list[i]; }
   for (int hI = 0; hI < n_hp; ++hI)      // column-major (nth+1) x n_hp == row-major n_hp x (nth+1)
-    for (int c = 0; c < ld; ++c) blk[ohp + (size_t)hI * ld + c] = halfplanes[(size_t)hI * ld + c];
-  for (int r = 0; r < n_fb; ++r)          // block r: (nth+1) x nu column-major -> nu x (nth+1) row-major
+    for (int c = 0; c < ld; ++c) blk[ohp + (size_t)hI * ldh + c] = halfplanes[(size_t)hI * ld + c];
+  for (int r = 0; r < n_fb; ++r)          // block r: (nth+1) x nu column-major -> nu x ldh row-major
     for (int i = 0; i < nu; ++i)
       for (int c = 0; c < ld; ++c)
-        blk[ofb + ((size_t)r * nu + i) * ld + c] = feedbacks[(size_t)r * ld * nu + (size_t)i * ld + c];
+        blk[ofb + ((size_t)r * nu + i) * ldh + c] = feedbacks[(size_t)r * ld * nu + (size_t)i * ld + c];
   if (clipping)
     for (int i = 0; i < nu; ++i) { blk[oclip + 2 * i] = clipping[i]; blk[oclip + 2 * i + 1] = clipping[nu + i]; }
-  int32_t *lists = reinterpret_cast<int32_t *>(blk.data() + olist);
-  memcpy(lists, hp_list, sizeof(int32_t) * n_nodes);
-  memcpy(lists + n_nodes, jump_list, sizeof(int32_t) * n_nodes);
   lmpc_bst *t = new lmpc_bst();
   t->device = device; t->sm_count = sm;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -472,10 +474,9 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
       lmpc_gpu_destroy_bst(t);
       return set_err(LMPC_E_CUDA, "cudaStreamCreate failed%s");
     }
-  t->dev.hp = t->d_blk + ohp; t->dev.fb = t->d_blk + ofb;
-  t->dev.clip = clipping ? t->d_blk + oclip : nullptr;
-  t->dev.hp_list = reinterpret_cast<const int32_t *>(t->d_blk + olist);
-  t->dev.jump_list = t->dev.hp_list + n_nodes;
+  t->dev.blk = t->d_blk;
+  t->dev.onodes = (int)onodes; t->dev.ohp = (int)ohp; t->dev.ofb = (int)ofb; t->dev.oclip = (int)oclip;
+  t->dev.ldh = ldh; t->dev.total = (int)total; t->dev.has_clip = clipping ? 1 : 0;
   t->dev.nth = nth; t->dev.nu = nu; t->dev.n_hp = n_hp; t->dev.n_fb = n_fb; t->dev.n_nodes = n_nodes;
   *out = t;
   return 0;

@@ -9,31 +9,33 @@
 
 namespace {
 
-constexpr int K4_BLOCK = 256;
+constexpr int K4_BLOCK = 512;
 
-// tree block layout in doubles: [hp n_hp x (nth+1)] [fb n_fb x nu x (nth+1)] [clip nu x 2]
-// then int32 [hp_list n_nodes] [jump_list n_nodes]
+// Tree block as packed by lmpc_gpu_create_bst (api.cu: pack_bst), all offsets in doubles:
+//   nodes  n_nodes x int2 {jump, index}      (one 8-byte load per visited node)
+//   hp     n_hp x ldh   rows [a(nth) | b | pad]   read as 16-byte pairs, odd number of pairs per row
+//   fb     n_fb x nu x ldh rows [F(nth) | g | pad]
+//   clip   nu x 2
 struct BstLayout {
-  int ohp, ofb, oclip, olist, total;  // offsets in doubles
+  int onodes, ohp, ofb, oclip, ldh, total;
 };
 
-template <int NTH>
+template <int NTH, bool SMEM>
 __global__ void __launch_bounds__(K4_BLOCK)
-bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int n_nodes,
-                int has_clip, int in_smem, const double *__restrict__ Theta, int64_t N,
-                double *__restrict__ U, int32_t *__restrict__ region) {
+bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int has_clip,
+                const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
+                int32_t *__restrict__ region) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   const double *base = blk;
-  if (in_smem) {
+  if (SMEM) {
     stage_constants_tma(smem, blk, bl.total, &mbar);
     base = smem;
   }
   const int nth = NTH > 0 ? NTH : nth_rt;
-  const int ld = nth + 1;
+  const int ldh = bl.ldh;
   const double *hp = base + bl.ohp, *fb = base + bl.ofb, *clip = base + bl.oclip;
-  const int32_t *hp_list = reinterpret_cast<const int32_t *>(base + bl.olist);
-  const int32_t *jump_list = hp_list + n_nodes;
+  const int2 *nodes = reinterpret_cast<const int2 *>(base + bl.onodes);
   constexpr int TH = NTH > 0 ? NTH : 1;
   for (int64_t q = (int64_t)blockIdx.x * K4_BLOCK + threadIdx.x; q < N;
        q += (int64_t)gridDim.x * K4_BLOCK) {
@@ -44,28 +46,41 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
       for (int c = 0; c < TH; ++c) th[c] = ld_stream(src + c);
     }
     int id = 0;
-    for (;;) {
-      const int jmp = jump_list[id];
-      if (jmp == 0) break;
-      const double *h = hp + hp_list[id] * ld;
-      double acc = 0.0;
+    int2 nd = nodes[0];
+    constexpr int P2 = (TH + 2) / 2;     // 16-byte pairs covering [a(nth) | b]
+    while (nd.x != 0) {
+      const double *h = hp + nd.y * ldh;
+      double acc = 0.0, rhs;
       if (NTH > 0) {
+        double v[2 * P2];
+        const double2 *h2 = reinterpret_cast<const double2 *>(h);
 #pragma unroll
-        for (int c = 0; c < TH; ++c) acc = fma(h[c], th[c], acc);
+        for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+#pragma unroll
+        for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
+        rhs = v[TH];
       } else {
         for (int c = 0; c < nth; ++c) acc = fma(h[c], src[c], acc);
+        rhs = h[nth];
       }
-      id = id + jmp + (acc <= h[nth] ? 0 : 1);
+      id = id + nd.x + (acc <= rhs ? 0 : 1);
+      nd = nodes[id];
     }
-    const int reg = hp_list[id];
-    const double *f = fb + (size_t)reg * nu * ld;
+    const int reg = nd.y;
+    const double *f = fb + (size_t)reg * nu * ldh;
     for (int i = 0; i < nu; ++i) {
-      double acc = f[i * ld + nth];
+      double acc;
       if (NTH > 0) {
+        double v[2 * P2];
+        const double2 *f2 = reinterpret_cast<const double2 *>(f + i * ldh);
 #pragma unroll
-        for (int c = 0; c < TH; ++c) acc = fma(f[i * ld + c], th[c], acc);
+        for (int c = 0; c < P2; ++c) { const double2 t2 = f2[c]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+        acc = v[TH];
+#pragma unroll
+        for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
       } else {
-        for (int c = 0; c < nth; ++c) acc = fma(f[i * ld + c], src[c], acc);
+        acc = f[i * ldh + nth];
+        for (int c = 0; c < nth; ++c) acc = fma(f[i * ldh + c], src[c], acc);
       }
       if (has_clip) {
         if (acc < clip[2 * i]) acc = clip[2 * i];
@@ -77,13 +92,11 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   }
 }
 
-template <int NTH>
-int launch_k4(const BstDev &t, const BstLayout &bl, const double *blk, const double *Theta, int64_t N,
-              double *U, int32_t *region, int sm_count, cudaStream_t s) {
-  auto kern = bst_eval_kernel<NTH>;
-  size_t smem = (size_t)bl.total * sizeof(double);
-  int in_smem = smem <= 200 * 1024;
-  if (!in_smem) smem = 0;
+template <int NTH, bool SMEM>
+int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
+               int32_t *region, int sm_count, cudaStream_t s) {
+  auto kern = bst_eval_kernel<NTH, SMEM>;
+  const size_t smem = SMEM ? (size_t)bl.total * sizeof(double) : 0;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 0;
@@ -92,31 +105,31 @@ int launch_k4(const BstDev &t, const BstLayout &bl, const double *blk, const dou
   int64_t blocks = (N + K4_BLOCK - 1) / K4_BLOCK;
   const int64_t cap = (int64_t)sm_count * per_sm;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, K4_BLOCK, smem, s>>>(blk, bl, t.nth, t.nu, t.n_nodes, t.clip != nullptr,
-                                                in_smem, Theta, N, U, region);
+  kern<<<(unsigned)blocks, K4_BLOCK, smem, s>>>(t.blk, bl, t.nth, t.nu, t.has_clip, Theta, N, U, region);
   return (int)cudaGetLastError();
+}
+
+template <int NTH>
+int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
+              int32_t *region, int sm_count, cudaStream_t s) {
+  if ((size_t)bl.total * sizeof(double) <= 100 * 1024)
+    return launch_k4s<NTH, true>(t, bl, Theta, N, U, region, sm_count, s);
+  return launch_k4s<NTH, false>(t, bl, Theta, N, U, region, sm_count, s);
 }
 
 }  // namespace
 
-// BstDev.hp points at the start of the packed tree block (see api.cu: pack_bst); the other
-// pointers are offsets into the same allocation.
 int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
                     int sm_count, void *stream) {
   if (N <= 0) return 0;
   BstLayout bl;
-  bl.ohp = 0;
-  bl.ofb = (int)(t.fb - t.hp);
-  bl.oclip = (int)((t.clip ? t.clip : t.fb) - t.hp);
-  bl.olist = (int)(reinterpret_cast<const double *>(t.hp_list) - t.hp);
-  bl.total = bl.olist + (2 * t.n_nodes + 1) / 2;
-  bl.total = (bl.total + 1) & ~1;
+  bl.onodes = t.onodes; bl.ohp = t.ohp; bl.ofb = t.ofb; bl.oclip = t.oclip; bl.ldh = t.ldh; bl.total = t.total;
   cudaStream_t s = (cudaStream_t)stream;
-#define K4_CASE(NN) case NN: return launch_k4<NN>(t, bl, t.hp, Theta, N, U, region, sm_count, s);
+#define K4_CASE(NN) case NN: return launch_k4<NN>(t, bl, Theta, N, U, region, sm_count, s);
   switch (t.nth) {
     K4_CASE(1) K4_CASE(2) K4_CASE(3) K4_CASE(4) K4_CASE(5) K4_CASE(6) K4_CASE(7) K4_CASE(8)
     K4_CASE(9) K4_CASE(10) K4_CASE(11) K4_CASE(12) K4_CASE(13) K4_CASE(14) K4_CASE(15) K4_CASE(16)
-    default: return launch_k4<0>(t, bl, t.hp, Theta, N, U, region, sm_count, s);
+    default: return launch_k4<0>(t, bl, Theta, N, U, region, sm_count, s);
   }
 }
 

@@ -16,6 +16,7 @@
 //   * no immutable / soft / singular handling at all (cannot occur for this class).
 #include "ldp_device.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace {
 
@@ -119,8 +120,8 @@ LMPC_DEVINL void box_remove(BoxState<N> &s, int r) {
   s.k = k;
 }
 
-template <int N, int NU>
-__global__ void __launch_bounds__(KB_BLOCK, 4)
+template <int N, int NU, int MINB>
+__global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, ThetaSegs th,
                int64_t Ninst, SolveOut out) {
   extern __shared__ __align__(16) double smem[];
@@ -247,10 +248,10 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
   }
 }
 
-template <int N, int NU>
+template <int N, int NU, int MINB = 4>
 int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
-  auto kern = ldp_box_kernel<N, NU>;
+  auto kern = ldp_box_kernel<N, NU, MINB>;
   const size_t smem = (size_t)lay.total * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -281,6 +282,13 @@ int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cb
                    const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 0) return 0;
+  if (lay.n == 5 && lay.nu == 1) {   // tuning hook (development): resident CTAs per SM
+    const char *e = getenv("LMPC_BOX_MINB");
+    const int mb = e ? atoi(e) : 4;
+    if (mb == 3) return launch_box<5, 1, 3>(lay, st, cblk, th, N, out, sm_count, s);
+    if (mb == 5) return launch_box<5, 1, 5>(lay, st, cblk, th, N, out, sm_count, s);
+    if (mb == 6) return launch_box<5, 1, 6>(lay, st, cblk, th, N, out, sm_count, s);
+  }
   switch (lay.n) {
     KB_CASE(1) KB_CASE(2) KB_CASE(3) KB_CASE(4) KB_CASE(5) KB_CASE(6) KB_CASE(7) KB_CASE(8)
     default: return (int)cudaErrorInvalidValue;

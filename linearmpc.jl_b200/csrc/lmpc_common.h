@@ -96,11 +96,9 @@ bool ldp_warp_supports(const LdpLayout &lay);
 bool ldp_cta_supports(const LdpLayout &lay);
 
 struct BstDev {
-  const double *hp;      // n_hp x (nth+1) row-major
-  const double *fb;      // n_fb x nu x (nth+1) row-major
-  const double *clip;    // nu x 2 row-major or null
-  const int32_t *hp_list, *jump_list;
-  int nth, nu, n_hp, n_fb, n_nodes;
+  const double *blk;     // packed tree block on the device (layout: see bst_eval.cu)
+  int onodes, ohp, ofb, oclip, ldh, total;   // offsets / sizes in doubles
+  int nth, nu, n_hp, n_fb, n_nodes, has_clip;
 };
 int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
                     int sm_count, void *stream);

@@ -1,0 +1,27 @@
+"""Launches one kernel family a few times so ncu can capture it:  python tools/prof_driver.py box|warp|cta|bst"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+import lmpc_b200, util
+from oracle import mpqp
+dev = torch.device("cuda", 0)
+which = sys.argv[1]
+def rand_theta(lo, hi, N):
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    T = torch.rand((N, len(lo)), dtype=torch.float64, device=dev, generator=gen)
+    return T * torch.tensor(hi - lo, device=dev) + torch.tensor(lo, device=dev)
+if which == "bst":
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "invpend_explicit.npz"))
+    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    N = 20_000_000
+    Th = rand_theta(z["lo"], z["hi"], N); U = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    for _ in range(4): ge.evaluate_async(Th, U, N=N)
+else:
+    name, scale, N = {"box": ("invpend", 1.0, 10_000_000), "warp": ("aircraft", 0.25, 300_000), "cta": ("chain", 0.25, 3000)}[which]
+    mpc = util.controller(name); qp = mpqp.mpc2mpqp(mpc)
+    g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
+    Th = rand_theta(*util.theta_range(name, scale), N)
+    U = torch.empty((N, g.nu), dtype=torch.float64, device=dev); fl = torch.empty(N, dtype=torch.int32, device=dev)
+    for _ in range(4): g.solve_async(Th, U, fl, N=N)
+torch.cuda.synchronize()
