@@ -72,6 +72,7 @@ struct BigCtx {
   double *thw;     // nth
   double *lamw;    // cap: lam* broadcast copy
   int *roww;       // cap: row ids broadcast copy
+  unsigned char *inwsb;   // CTA mode: m flags "row is in the working set" (else null)
   int lane;
 };
 
@@ -173,6 +174,7 @@ LMPC_DEVINL void bq_add(const BigCtx &c, BigQp<T> &s, int j, bool lower, double 
     }
   }
   if ((j & 31) == lane) s.inws |= 1u << (j >> 5);
+  if (c.inwsb && lane == 0) c.inwsb[j] = 1;
   s.sing = sing;
   s.k = k + 1;
   __syncwarp();
@@ -219,6 +221,7 @@ LMPC_DEVINL void bq_remove(const BigCtx &c, BigQp<T> &s, int r) {
   double wv[T];
   TFOR(t) { const int i = lane + 32 * t; wv[t] = (i > r && i < k) ? c.Lw[PIDX(i, r)] : 0.0; }
   if ((rrow & 31) == lane) s.inws &= ~(1u << (rrow >> 5));
+  if (c.inwsb && lane == 0) c.inwsb[rrow] = 0;
   // rows r+1 .. k-1 move up one row and lose column r
   for (int p = r; p + 1 < k; ++p) {
     double tmp[T];
@@ -479,6 +482,7 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   c.thw = w; w += (lay.nth + 1) & ~1;
   c.lamw = w; w += (cap + 1) & ~1;
   c.roww = reinterpret_cast<int *>(w);
+  c.inwsb = nullptr;
   const int lane = c.lane, words = (lay.m + 63) >> 6;
   const int64_t wid = (int64_t)blockIdx.x * warps + warp;
   const int64_t wstride = (int64_t)gridDim.x * warps;
@@ -525,6 +529,320 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     }
     __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-per-QP mode (problems whose packed L fills most of an SM's shared memory, e.g. n = 180).
+// Warp 0 is the factorisation warp: it owns the working-set state in its register tiles and runs
+// the triangular sweeps, LDL' add/remove and the ratio test exactly as in warp mode.  The two
+// O(k n) / O(n m) phases of an iteration -- the primal iterate u = -M_W' lam* and the slack scan --
+// are spread over all 256 threads (thread c owns u_c, thread j owns row j and its shift sh_j),
+// each thread keeping the oracle's sequential accumulation order, with the Mbar / Mbar' reads
+// coalesced and unrolled so eight loads are in flight per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int CTA_THREADS = 256;
+
+struct CoopShared {
+  double *shw;        // m: shifts sh_j (for equality activation / warm rows)
+  double *red_v;      // 8: per-warp scan minima
+  double *red_d;      // 8: bound value of the candidate
+  int *red_j;         // 8: row of the candidate (1<<30: none)
+  int *red_low;       // 8
+  int *ctl;           // [0] branch (0 add / 1 remove / 2 singular), [1] exit flag or 0, [2] k, [3] iters
+};
+
+template <int T>
+__global__ void __launch_bounds__(CTA_THREADS)
+ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
+               const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int soff = small_off(lay);
+  stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
+  BigCtx c;
+  c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
+  const double *sb = smem - soff;
+  c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
+  c.cv.Dth = sb + lay.oDth; c.cv.du = sb + lay.odu; c.cv.dl = sb + lay.odl; c.cv.Rinv = sb + lay.oRinv;
+  c.cv.Uth = sb + lay.oUth; c.cv.uoff = sb + lay.ouoff;
+  c.cv.sense = reinterpret_cast<const int32_t *>(sb + lay.oSense);
+  c.lay = &lay; c.st = &st;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  c.lane = tid & 31;
+  const int cap = lay.cap, n = lay.n, m = lay.m, mp = lay.mp, nth = lay.nth;
+  double *w = smem + (lay.total - soff);
+  c.Lw = w; w += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+  c.uw = w; w += (n + 1) & ~1;
+  c.thw = w; w += (nth + 1) & ~1;
+  c.lamw = w; w += (cap + 1) & ~1;
+  CoopShared cs;
+  cs.shw = w; w += (m + 1) & ~1;
+  cs.red_v = w; w += 8;
+  cs.red_d = w; w += 8;
+  cs.red_j = reinterpret_cast<int *>(w); w += 4;
+  cs.red_low = reinterpret_cast<int *>(w); w += 4;
+  cs.ctl = reinterpret_cast<int *>(w); w += 2;
+  c.roww = reinterpret_cast<int *>(w); w += (cap + 1) / 2 + 1;
+  c.inwsb = reinterpret_cast<unsigned char *>(w);
+  const int lane = c.lane, words = (m + 63) >> 6;
+  BigQp<T> s;          // meaningful in warp 0 only
+  double u[T];
+  for (int64_t q = blockIdx.x; q < Ninst; q += gridDim.x) {
+    // theta, shifts (thread j <-> rows j, j + 256), reset
+    int o = 0;
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg) {
+      if (sg < th.nseg) {
+        const int len = th.len[sg];
+        for (int t = tid; t < len; t += CTA_THREADS) c.thw[o + t] = ld_stream(th.ptr[sg] + q * th.stride[sg] + t);
+        o += len;
+      }
+    }
+    for (int j = tid; j < m; j += CTA_THREADS) c.inwsb[j] = 0;
+    __syncthreads();
+    double shr[2] = {0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = tid + CTA_THREADS * h;
+      if (j < m) {
+        const double *dr = c.cv.Dth + (size_t)j * nth;
+        double acc = 0.0;
+        for (int t = 0; t < nth; ++t) acc = fma(dr[t], c.thw[t], acc);
+        shr[h] = acc;
+        cs.shw[j] = acc;
+      }
+    }
+    if (tid == 0) { cs.ctl[1] = 0; cs.ctl[3] = 0; }
+    __syncthreads();
+    int flag = EXIT_ITERLIMIT, iter = 0, cycle = 0;
+    double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
+    if (warp == 0) {
+      bq_reset<T>(s);
+      TFOR(t) u[t] = 0.0;
+      for (int j = 0; lay.neq > 0 && j < m; ++j) {
+        const int sj = c.cv.sense[j];
+        if (sj & S_ACTIVE) {
+          if (s.k >= cap || s.k >= 32 * T) { flag = EXIT_OVERDETERMINED; break; }
+          const bool low = sj & S_LOWER;
+          bq_add<T>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + cs.shw[j]);
+          if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
+        }
+      }
+      if (flag == EXIT_OVERDETERMINED && lane == 0) cs.ctl[1] = flag;
+    }
+    __syncthreads();
+    const bool dead = cs.ctl[1] != 0;
+    for (iter = 1; !dead && iter < st.iter_limit; ++iter) {
+      // ---- phase A (warp 0): CSP, blocking test / singular step -------------------------------
+      double a[T];
+      bool blk[T];
+      if (warp == 0) {
+        const int k = s.k;
+        TFOR(t) { a[t] = CUDART_INF; blk[t] = false; }
+        int branch;
+        if (!s.sing) {
+          double z[T];
+          TFOR(t) z[t] = (lane + 32 * t < k) ? -s.dW[t] : 0.0;
+          sweep_fwd<T>(c, z, k);
+          TFOR(t) s.lams[t] = (lane + 32 * t < k) ? z[t] * s.Dinv[t] : 0.0;
+          sweep_bwd<T>(c, s.lams, k);
+          bool anyblk = false;
+          TFOR(t) {
+            const bool low = (s.low >> t) & 1u, imm = (s.imm >> t) & 1u;
+            blk[t] = (lane + 32 * t < k) && !imm && (low ? (s.lams[t] > st.dual_tol) : (s.lams[t] < -st.dual_tol));
+            anyblk |= blk[t];
+          }
+          branch = __any_sync(FULL, anyblk) ? 1 : 0;
+          if (branch == 0) { TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = s.lams[t]; } }
+        } else {
+          branch = 2;
+        }
+        if (lane == 0) { cs.ctl[0] = branch; cs.ctl[2] = k; }
+      }
+      __syncthreads();
+      const int branch = cs.ctl[0], k = cs.ctl[2];
+      if (branch == 0) {
+        // ---- phase B (all threads): u_c = -sum_i lam*_i Mbar[row_i][c], sequential in i ----------
+        if (tid < n) {
+          double uc = 0.0;
+#pragma unroll 8
+          for (int i = 0; i < k; ++i) uc = fma(-c.lamw[i], c.M[(size_t)c.roww[i] * n + tid], uc);
+          c.uw[tid] = uc;
+        }
+        __syncthreads();
+        // ---- phase C (all threads): slack of rows tid, tid + 256, sequential in c ---------------
+        double best = CUDART_INF, bestd = 0.0;
+        int bestj = 1 << 30, bestlow = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = tid + CTA_THREADS * h;
+          if (j < m) {
+            double mu = 0.0;
+            const double *mt = c.MT + j;
+#pragma unroll 8
+            for (int cc = 0; cc < n; ++cc) mu = fma(mt[(size_t)cc * mp], c.uw[cc], mu);
+            if (!c.inwsb[j] && !(c.cv.sense[j] & S_IMMUTABLE)) {
+              const double dU = c.cv.du[j] + shr[h], dLo = c.cv.dl[j] + shr[h];
+              const double su = dU - mu, sl = mu - dLo;
+              if (su < -st.primal_tol && su < best) { best = su; bestd = dU; bestj = j; bestlow = 0; }
+              else if (!(su < -st.primal_tol) && sl < -st.primal_tol && sl < best) { best = sl; bestd = dLo; bestj = j; bestlow = 1; }
+            }
+          }
+        }
+        {
+          const double vmin = bfly_min(best);
+          const int jw = bfly_min_i((best == vmin && bestj < (1 << 30)) ? bestj : (1 << 30));
+          // the owner of row jw (if any) publishes the warp's candidate
+          if (jw < (1 << 30) && bestj == jw && best == vmin) {
+            cs.red_v[warp] = vmin; cs.red_d[warp] = bestd; cs.red_j[warp] = jw; cs.red_low[warp] = bestlow;
+          } else if (jw == (1 << 30) && lane == 0) {
+            cs.red_v[warp] = CUDART_INF; cs.red_j[warp] = 1 << 30;
+          }
+        }
+        __syncthreads();
+        // ---- phase D (warp 0): objective, decision, add ----------------------------------------
+        if (warp == 0) {
+          TFOR(t) { const int cc = lane + 32 * t; u[t] = (cc < n) ? c.uw[cc] : 0.0; }
+          fval = lanesum_pos<T>(c, u, u, n);
+          soft_slack = 0.0;
+          if (lay.nsoft > 0) {
+            double sl[T];
+            double smax = 0.0;
+            TFOR(t) {
+              const bool sf = (lane + 32 * t < k) && ((s.soft >> t) & 1u);
+              sl[t] = sf ? s.lams[t] : 0.0;
+              const double v = st.rho_soft * fabs(s.lams[t]);
+              if (sf && v > smax) smax = v;
+            }
+            fval = fma(st.rho_soft, lanesum_pos<T>(c, sl, s.lams, k), fval);
+            soft_slack = bfly_max(smax);
+          }
+          int done = 0;
+          if (fval > st.fval_bound) done = EXIT_INFEASIBLE;
+          else {
+            const double v = (lane < 8) ? cs.red_v[lane] : CUDART_INF;
+            const int jl = (lane < 8) ? cs.red_j[lane] : (1 << 30);
+            const double vmin = bfly_min(v);
+            const int add = bfly_min_i((v == vmin && jl < (1 << 30)) ? jl : (1 << 30));
+            if (add == (1 << 30)) done = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL;
+            else {
+              if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+              else if (cycle++ > st.cycle_tol) done = EXIT_CYCLE;
+              if (!done && (k >= cap || k >= 32 * T)) done = EXIT_CAPACITY;
+              if (!done) {
+                const unsigned own = __ballot_sync(FULL, lane < 8 && jl == add && v == vmin);
+                const int src = __ffs(own) - 1;
+                const bool addlow = __shfl_sync(FULL, (lane < 8) ? cs.red_low[lane] : 0, src) != 0;
+                const double addd = shfl_d((lane < 8) ? cs.red_d[lane] : 0.0, src);
+                TFOR(t) if (lane + 32 * t < k) s.lam[t] = s.lams[t];
+                bq_add<T>(c, s, add, addlow, addd);
+              }
+            }
+          }
+          if (lane == 0) cs.ctl[1] = done;
+        }
+      } else if (warp == 0) {
+        // ---- removal branches (warp 0 only) -----------------------------------------------------
+        int done = 0;
+        if (branch == 1) {
+          TFOR(t) if (blk[t]) { a[t] = -s.lam[t] / (s.lams[t] - s.lam[t]); if (!(a[t] == a[t])) a[t] = CUDART_INF; }
+          double alpha;
+          const int rm = argmin_first<T>(c, a, alpha);
+          if (rm < 0) done = EXIT_CYCLE;
+          else {
+            TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, s.lams[t] - s.lam[t], s.lam[t]);
+            bq_remove<T>(c, s, rm);
+          }
+        } else {
+          const int kk = k - 1;
+          bool lastlow = false;
+          {
+            int lowv[T];
+            TFOR(t) lowv[t] = (s.low >> t) & 1u;
+            lastlow = bcast_pos_i<T>(lowv, kk) != 0;
+          }
+          double p[T];
+          TFOR(t) { const int i = lane + 32 * t; p[t] = (i < kk) ? -c.Lw[PIDX(kk, i)] : 0.0; }
+          sweep_bwd<T>(c, p, kk);
+          TFOR(t) {
+            const int i = lane + 32 * t;
+            if (i == kk) p[t] = 1.0;
+            if (lastlow && i <= kk) p[t] = -p[t];
+            s.lams[t] = (i < k) ? p[t] : 0.0;
+            const bool low = (s.low >> t) & 1u, imm = (s.imm >> t) & 1u;
+            const bool b = (i < k) && !imm && (low ? (p[t] > st.dual_tol) : (p[t] < -st.dual_tol));
+            if (b) { a[t] = -s.lam[t] / p[t]; if (!(a[t] == a[t])) a[t] = CUDART_INF; }
+          }
+          double alpha;
+          const int rm = argmin_first<T>(c, a, alpha);
+          if (rm < 0) done = EXIT_INFEASIBLE;
+          else {
+            TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, p[t], s.lam[t]);
+            bq_remove<T>(c, s, rm);
+          }
+        }
+        if (lane == 0) cs.ctl[1] = done;
+      }
+      __syncthreads();
+      if (cs.ctl[1] != 0) break;
+    }
+    flag = cs.ctl[1] != 0 ? cs.ctl[1] : EXIT_ITERLIMIT;
+    // ---- output (warp 0) ------------------------------------------------------------------------
+    if (warp == 0) {
+      for (int i = 0; i < lay.nu; ++i) {
+        double rr[T];
+        TFOR(t) { const int cc = lane + 32 * t; rr[t] = (cc < n) ? c.cv.Rinv[(size_t)i * n + cc] : 0.0; }
+        const double x = lanesum_pos<T>(c, rr, u, n);
+        double shv = c.cv.uoff[i];
+        const double *ur = c.cv.Uth + (size_t)i * nth;
+        for (int t = 0; t < nth; ++t) shv = fma(ur[t], c.thw[t], shv);
+        if (lane == 0) out.U[q * lay.nu + i] = __dadd_rn(x, shv);
+      }
+      if (out.act_u) {
+        for (int wd = lane; wd < words; wd += 32) { out.act_u[q * words + wd] = 0ull; out.act_l[q * words + wd] = 0ull; }
+        __syncwarp();
+        TFOR(t) {
+          const int i = lane + 32 * t;
+          if (i < s.k) {
+            const int j = s.row[t];
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(((s.low >> t) & 1u) ? out.act_l : out.act_u) + q * words + (j >> 6);
+            atomicOr(dst, 1ull << (j & 63));
+          }
+        }
+      }
+      if (lane == 0) {
+        out.flag[q] = flag;
+        if (out.iters) out.iters[q] = iter;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+size_t cta_smem(const LdpLayout &lay) {
+  const size_t cap = lay.cap;
+  size_t d = (size_t)(lay.total - lay.oDth);
+  d += (cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+  d += (lay.n + 1) & ~1; d += (lay.nth + 1) & ~1; d += (cap + 1) & ~1; d += (lay.m + 1) & ~1;
+  d += 8 + 8 + 4 + 4 + 2 + (cap + 1) / 2 + 1;
+  d += (lay.m + 7) / 8 + 1;
+  return d * sizeof(double);
+}
+
+template <int T>
+int launch_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
+               int64_t N, const SolveOut &out, int sm_count, cudaStream_t s) {
+  auto kern = ldp_cta_kernel<T>;
+  const size_t smem = cta_smem(lay);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_THREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = N;
+  if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+  kern<<<(unsigned)blocks, CTA_THREADS, smem, s>>>(lay, st, cblk, th, N, out);
+  return (int)cudaGetLastError();
 }
 
 K3Geom k3_geom(const LdpLayout &lay) {
@@ -576,6 +894,17 @@ int launch_ldp_cta(const LdpLayout &lay, const LdpSettings &st, const double *cb
   int need = lay.cap > lay.n ? lay.cap : lay.n;
   if ((lay.m + 1) / 2 > need) need = (lay.m + 1) / 2;
   const int T = (need + 31) / 32;
+  // few QPs fit in an SM's shared memory -> give each QP a whole CTA (cooperative u / scan)
+  const bool coop = k3_geom(lay).warps <= 2 && cta_smem(lay) <= 220 * 1024;
+  if (coop) {
+    switch (T) {
+      case 1: case 2: return launch_cta<2>(lay, st, cblk, th, N, out, sm_count, s);
+      case 3: case 4: return launch_cta<4>(lay, st, cblk, th, N, out, sm_count, s);
+      case 5: case 6: return launch_cta<6>(lay, st, cblk, th, N, out, sm_count, s);
+      case 7: case 8: return launch_cta<8>(lay, st, cblk, th, N, out, sm_count, s);
+      default: return (int)cudaErrorInvalidValue;
+    }
+  }
   switch (T) {
     case 1: case 2: return launch_big<2>(lay, st, cblk, th, N, out, sm_count, s);
     case 3: case 4: return launch_big<4>(lay, st, cblk, th, N, out, sm_count, s);
