@@ -320,7 +320,7 @@ def main():
                        "all_exitflags_optimal": ok_all},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach_tf / fp64_peak, "traffic": traffic,
-                         "kernel": "ldp_thread_kernel<5,5>", "kernel_ms": kernel_ms,
+                         "kernel": "ldp_box_kernel<5,1> (thread-per-QP, box-only fast path)", "kernel_ms": kernel_ms,
                          "flops_per_solve": flops_per_solve,
                          "peak_source": "FP64 FMA microbenchmark in this run (lmpc_gpu_fp64_peak)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,

@@ -150,6 +150,9 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
         o += len;
       }
     SEND
+    // theta-dependent bounds, once per solve (mpc_update_qp): d_u = du + sh, d_l = dl + sh
+    double dU[N], dLo[N];
+    SFOR(j, 0, N) dU[j] = cv.du[j] + sh[j]; dLo[j] = cv.dl[j] + sh[j]; SEND
     // ---- dual active-set loop, cold start --------------------------------------------------
     box_reset<N>(s);
     double u[N];
@@ -188,24 +191,23 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
         SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
         fval = tree_sum<N, 0, 1>(pu);
         if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
-        double best = -st.primal_tol, addd = 0.0;
-        int add = -1;
-        bool addlow = false;
+        double best = -st.primal_tol;
+        int code = -1;                       // 2 * row + (1 if lower)
         SFOR(j, 0, N)
           // row j of the normalised R^-1 is zero before column j
           double mu = 0.0;
           SFOR(c, j, N) mu = fma(cv.M[j * N + c], u[c], mu); SEND
           const bool free_row = !((s.inws >> j) & 1u);
-          const double dU = cv.du[j] + sh[j];
-          const double dLo = cv.dl[j] + sh[j];
-          const double su = dU - mu, sl = mu - dLo;
+          const double su = dU[j] - mu, sl = mu - dLo[j];
           const bool tu = free_row && (su < best);
           const bool tl = free_row && !tu && (sl < best);
           best = tu ? su : (tl ? sl : best);
-          addd = tu ? dU : (tl ? dLo : addd);
-          add = (tu || tl) ? j : add;
-          addlow = tu ? false : (tl ? true : addlow);
+          code = tu ? 2 * j : (tl ? 2 * j + 1 : code);
         SEND
+        const int add = code >> 1;
+        const bool addlow = code & 1;
+        double addd = 0.0;
+        SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
         if (add < 0) { flag = EXIT_OPTIMAL; break; }
         if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
         else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
@@ -248,7 +250,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
   }
 }
 
-template <int N, int NU, int MINB = 4>
+template <int N, int NU, int MINB = 3>
 int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
   auto kern = ldp_box_kernel<N, NU, MINB>;
@@ -284,8 +286,8 @@ int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cb
   if (N <= 0) return 0;
   if (lay.n == 5 && lay.nu == 1) {   // tuning hook (development): resident CTAs per SM
     const char *e = getenv("LMPC_BOX_MINB");
-    const int mb = e ? atoi(e) : 4;
-    if (mb == 3) return launch_box<5, 1, 3>(lay, st, cblk, th, N, out, sm_count, s);
+    const int mb = e ? atoi(e) : 3;
+    if (mb == 4) return launch_box<5, 1, 4>(lay, st, cblk, th, N, out, sm_count, s);
     if (mb == 5) return launch_box<5, 1, 5>(lay, st, cblk, th, N, out, sm_count, s);
     if (mb == 6) return launch_box<5, 1, 6>(lay, st, cblk, th, N, out, sm_count, s);
   }

@@ -27,6 +27,9 @@ namespace {
 
 constexpr int K2_WARPS = 8;
 constexpr int K2_BLOCK = K2_WARPS * 32;
+#ifndef K2_MINB
+#define K2_MINB 3
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 LMPC_DEVINL double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -87,6 +90,7 @@ LMPC_DEVINL void wq_reset(WarpQp &s) {
 // column sweep: z <- L^-1 z on positions [0, kk)
 LMPC_DEVINL double sweep_fwd(const WarpCtx &c, const WarpQp &s, double z, int kk) {
   const double *lrow = c.Lw + s.slot * c.LS;
+#pragma unroll 4
   for (int j = 0; j + 1 < kk; ++j) {
     const int sj = __shfl_sync(FULL, s.slot, j);
     const double lij = lrow[sj];
@@ -97,6 +101,7 @@ LMPC_DEVINL double sweep_fwd(const WarpCtx &c, const WarpQp &s, double z, int kk
 }
 // column sweep: x <- L^-T x on positions [0, kk), descending (the oracle's axpy order)
 LMPC_DEVINL double sweep_bwd(const WarpCtx &c, const WarpQp &s, double x, int kk) {
+#pragma unroll 4
   for (int j = kk - 1; j > 0; --j) {
     const int sj = __shfl_sync(FULL, s.slot, j);
     const double lji = c.Lw[sj * c.LS + s.slot];
@@ -208,6 +213,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
       if (!__any_sync(FULL, blk)) {
         // 3. primal iterate u = -M_W' lam*
         double uc = 0.0;
+#pragma unroll 4
         for (int i = 0; i < k; ++i) {
           const double li = shfl_d(s.lams, i);
           const int ri = __shfl_sync(FULL, s.row, i);
@@ -233,6 +239,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
           const int j = lane + 32 * half;
           if (j < m) {
             double mu = 0.0;
+#pragma unroll 4
             for (int cc = 0; cc < n; ++cc) mu = fma(c.cv.MT[cc * mp + j], c.uw[cc], mu);
             const bool skip = ((s.inws >> j) & 1ull) || (c.cv.sense[j] & S_IMMUTABLE);
             const double shj = half ? sh1 : sh0;
@@ -362,7 +369,7 @@ LMPC_DEVINL WarpCtx make_ctx(double *smem, const LdpLayout &lay, const LdpSettin
   return c;
 }
 
-__global__ void __launch_bounds__(K2_BLOCK)
+__global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                 const double *__restrict__ cblk, ThetaSegs th,
                 int64_t Ninst, SolveOut out) {
@@ -411,7 +418,7 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
 }
 
 // closed loop: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
-__global__ void __launch_bounds__(K2_BLOCK)
+__global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                     const double *__restrict__ cblk,
                     int64_t Ninst, SimDesc sd, int32_t *flagout, int32_t *itersout) {

@@ -152,6 +152,25 @@ def test_compute_control_c_twin(lmpc):
     assert np.array_equal(U2, ref["U"])
 
 
+@pytest.mark.parametrize("name", ["aircraft", "dint_hard", "aircraft_ksall"])
+def test_compute_control_c_twin_other_kernels(lmpc, name):
+    """theta assembled inside the kernel from state / reference / disturbance / control for the
+    general thread kernel, the warp kernel and the large-problem kernel."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    lo, hi = util.theta_range(name, 0.25)
+    Th = mpqp.sample_theta(lo, hi, 3000, seed=17)
+    X, R = Th[:nx], Th[nx:nx + nr]
+    D = Th[nx + nr:nx + nr + nd] if nd else None
+    ctl0 = np.zeros((g.nu, Th.shape[1]))
+    if nup:
+        ctl0[:nup] = Th[nx + nr + nd:]
+    ctl, flag = g.compute_control_c(ctl0.copy(), X, R, D)
+    ref = P.solve_batch(Th)
+    ok = ref["flag"] >= 1
+    assert np.array_equal(flag, ref["flag"]) and np.array_equal(ctl[:, ok], ref["U"][:, ok])
+
+
 @pytest.mark.parametrize("name,T", [("invpend", 100), ("aircraft", 40)])
 @pytest.mark.parametrize("warm", [False, True])
 def test_closed_loop_matches_oracle(lmpc, name, T, warm):
