@@ -443,21 +443,37 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
   int rc = check_device(device, &sm);
   if (rc) return rc;
   const int ld = nth + 1;
-  // rows are read as 16-byte pairs: an odd number of pairs per row spreads divergent row
-  // gathers over all eight 16-byte bank groups
-  const int ldh = 2 * (((ld + 1) / 2) | 1);
+  const int pairs = (ld + 1) / 2;          // 16-byte pairs per row [a | b | pad] / [F | g | pad]
   auto al2 = [](size_t x) { return (x + 1) & ~(size_t)1; };
-  const size_t onodes = 0, ohp = al2((size_t)n_nodes), ofb = ohp + al2((size_t)n_hp * ldh);
-  const size_t oclip = ofb + al2((size_t)n_fb * nu * ldh), total = oclip + al2((size_t)2 * nu);
+  // node records fit one 32-bit word when every jump and index is below 65536
+  bool packed = n_hp < 65536 && n_fb < 65536;
+  for (int i = 0; i < n_nodes && packed; ++i) packed = jump_list[i] < 65536;
+  const size_t node_d = packed ? al2(((size_t)n_nodes + 1) / 2) : al2((size_t)n_nodes);
+  // replicate the half-plane and leaf-law tables so that lane l reads replica l mod rep
+  // (conflict-free at 8); as many replicas (power of two <= 8) as fit in ~200 KB of shared memory
+  const size_t rows = (size_t)n_hp + (size_t)n_fb * nu;
+  int rep = 8;
+  while (rep > 1 && (node_d + rows * pairs * 2 * rep + 2 * nu) * sizeof(double) > 200 * 1024) rep >>= 1;
+  const size_t onodes = 0, ohp = node_d, ofb = ohp + (size_t)n_hp * pairs * 2 * rep;
+  const size_t oclip = ofb + (size_t)n_fb * nu * pairs * 2 * rep, total = oclip + al2((size_t)2 * nu);
   std::vector<double> blk(total, 0.0);
-  int32_t *nodes = reinterpret_cast<int32_t *>(blk.data() + onodes);
-  for (int i = 0; i < n_nodes; ++i) { nodes[2 * i] = jump_list[i]; nodes[2 * i + 1] = hp_list[i]; }
-  for (int hI = 0; hI < n_hp; ++hI)      // column-major (nth+1) x n_hp == row-major n_hp x (nth+1)
-    for (int c = 0; c < ld; ++c) blk[ohp + (size_t)hI * ldh + c] = halfplanes[(size_t)hI * ld + c];
-  for (int r = 0; r < n_fb; ++r)          // block r: (nth+1) x nu column-major -> nu x ldh row-major
+  if (packed) {
+    uint32_t *nodes = reinterpret_cast<uint32_t *>(blk.data() + onodes);
+    for (int i = 0; i < n_nodes; ++i) nodes[i] = ((uint32_t)jump_list[i] << 16) | (uint32_t)hp_list[i];
+  } else {
+    int32_t *nodes = reinterpret_cast<int32_t *>(blk.data() + onodes);
+    for (int i = 0; i < n_nodes; ++i) { nodes[2 * i] = jump_list[i]; nodes[2 * i + 1] = hp_list[i]; }
+  }
+  for (int hI = 0; hI < n_hp; ++hI)      // column-major (nth+1) x n_hp: column hI = [a; b]
+    for (int c = 0; c < ld; ++c)
+      for (int p2 = 0; p2 < rep; ++p2)
+        blk[ohp + (((size_t)hI * pairs + c / 2) * rep + p2) * 2 + (c & 1)] = halfplanes[(size_t)hI * ld + c];
+  for (int r = 0; r < n_fb; ++r)          // block r: (nth+1) x nu column-major; row (r, i) = [F_i | g_i]
     for (int i = 0; i < nu; ++i)
       for (int c = 0; c < ld; ++c)
-        blk[ofb + ((size_t)r * nu + i) * ldh + c] = feedbacks[(size_t)r * ld * nu + (size_t)i * ld + c];
+        for (int p2 = 0; p2 < rep; ++p2)
+          blk[ofb + ((((size_t)r * nu + i) * pairs + c / 2) * rep + p2) * 2 + (c & 1)] =
+              feedbacks[(size_t)r * ld * nu + (size_t)i * ld + c];
   if (clipping)
     for (int i = 0; i < nu; ++i) { blk[oclip + 2 * i] = clipping[i]; blk[oclip + 2 * i + 1] = clipping[nu + i]; }
   lmpc_bst *t = new lmpc_bst();
@@ -476,7 +492,8 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
     }
   t->dev.blk = t->d_blk;
   t->dev.onodes = (int)onodes; t->dev.ohp = (int)ohp; t->dev.ofb = (int)ofb; t->dev.oclip = (int)oclip;
-  t->dev.ldh = ldh; t->dev.total = (int)total; t->dev.has_clip = clipping ? 1 : 0;
+  t->dev.pairs = pairs; t->dev.rep = rep; t->dev.packed = packed ? 1 : 0;
+  t->dev.total = (int)total; t->dev.has_clip = clipping ? 1 : 0;
   t->dev.nth = nth; t->dev.nu = nu; t->dev.n_hp = n_hp; t->dev.n_fb = n_fb; t->dev.n_nodes = n_nodes;
   *out = t;
   return 0;

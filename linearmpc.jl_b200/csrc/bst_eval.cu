@@ -9,19 +9,23 @@
 
 namespace {
 
-constexpr int K4_BLOCK = 512;
+constexpr int K4_BLOCK = 1024;
 
-// Tree block as packed by lmpc_gpu_create_bst (api.cu: pack_bst), all offsets in doubles:
-//   nodes  n_nodes x int2 {jump, index}      (one 8-byte load per visited node)
-//   hp     n_hp x ldh   rows [a(nth) | b | pad]   read as 16-byte pairs, odd number of pairs per row
-//   fb     n_fb x nu x ldh rows [F(nth) | g | pad]
+// Tree block as packed by lmpc_gpu_create_bst (api.cu), all offsets in doubles:
+//   nodes  n_nodes x {jump, index}: packed into ONE 32-bit word (16 + 16 bits) when every jump and
+//          index fits (a warp's divergent node loads then cover 128 B instead of 256 B), else int2
+//   hp     half-planes [a(nth) | b | pad] cut into 16-byte pairs and REPLICATED `rep` times:
+//          pair c of row r, replica p sits at 16-byte slot (r * pairs + c) * rep + p, so that a lane
+//          reading replica (lane mod rep) always hits bank group (lane mod rep) when rep == 8: the
+//          divergent per-lane row gathers of a warp become conflict-free
+//   fb     leaf laws [F(nth) | g | pad], same pair-replicated layout (row = law * nu + output)
 //   clip   nu x 2
 struct BstLayout {
-  int onodes, ohp, ofb, oclip, ldh, total;
+  int onodes, ohp, ofb, oclip, pairs, rep, packed, total;
 };
 
-template <int NTH, bool SMEM>
-__global__ void __launch_bounds__(K4_BLOCK)
+template <int NTH, bool SMEM, bool PACKED>
+__global__ void __launch_bounds__(K4_BLOCK, 1)
 bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int has_clip,
                 const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
                 int32_t *__restrict__ region) {
@@ -33,10 +37,18 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
     base = smem;
   }
   const int nth = NTH > 0 ? NTH : nth_rt;
-  const int ldh = bl.ldh;
-  const double *hp = base + bl.ohp, *fb = base + bl.ofb, *clip = base + bl.oclip;
-  const int2 *nodes = reinterpret_cast<const int2 *>(base + bl.onodes);
+  const int rep = bl.rep, pairs = bl.pairs;
+  const double2 *hp2 = reinterpret_cast<const double2 *>(base + bl.ohp) + (threadIdx.x & (rep - 1));
+  const double2 *fb2 = reinterpret_cast<const double2 *>(base + bl.ofb) + (threadIdx.x & (rep - 1));
+  const double *clip = base + bl.oclip;
+  const int2 *nodes2 = reinterpret_cast<const int2 *>(base + bl.onodes);
+  const uint32_t *nodes1 = reinterpret_cast<const uint32_t *>(base + bl.onodes);
+  auto load_node = [&](int i) -> int2 {
+    if (PACKED) { const uint32_t w = nodes1[i]; return make_int2((int)(w >> 16), (int)(w & 0xffffu)); }
+    return nodes2[i];
+  };
   constexpr int TH = NTH > 0 ? NTH : 1;
+  constexpr int P2 = (TH + 2) / 2;     // 16-byte pairs covering [a(nth) | b]
   for (int64_t q = (int64_t)blockIdx.x * K4_BLOCK + threadIdx.x; q < N;
        q += (int64_t)gridDim.x * K4_BLOCK) {
     const double *src = Theta + q * nth;
@@ -46,41 +58,46 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
       for (int c = 0; c < TH; ++c) th[c] = ld_stream(src + c);
     }
     int id = 0;
-    int2 nd = nodes[0];
-    constexpr int P2 = (TH + 2) / 2;     // 16-byte pairs covering [a(nth) | b]
+    int2 nd = load_node(0);
     while (nd.x != 0) {
-      const double *h = hp + nd.y * ldh;
+      const double2 *h2 = hp2 + (size_t)nd.y * pairs * rep;
       double acc = 0.0, rhs;
       if (NTH > 0) {
         double v[2 * P2];
-        const double2 *h2 = reinterpret_cast<const double2 *>(h);
 #pragma unroll
-        for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+        for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c * rep]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
 #pragma unroll
         for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
         rhs = v[TH];
       } else {
-        for (int c = 0; c < nth; ++c) acc = fma(h[c], src[c], acc);
-        rhs = h[nth];
+        rhs = 0.0;
+        for (int c = 0; c <= nth; ++c) {
+          const double2 t2 = h2[(c >> 1) * rep];
+          const double hv = (c & 1) ? t2.y : t2.x;
+          if (c < nth) acc = fma(hv, src[c], acc); else rhs = hv;
+        }
       }
       id = id + nd.x + (acc <= rhs ? 0 : 1);
-      nd = nodes[id];
+      nd = load_node(id);
     }
     const int reg = nd.y;
-    const double *f = fb + (size_t)reg * nu * ldh;
     for (int i = 0; i < nu; ++i) {
+      const double2 *f2 = fb2 + ((size_t)reg * nu + i) * pairs * rep;
       double acc;
       if (NTH > 0) {
         double v[2 * P2];
-        const double2 *f2 = reinterpret_cast<const double2 *>(f + i * ldh);
 #pragma unroll
-        for (int c = 0; c < P2; ++c) { const double2 t2 = f2[c]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+        for (int c = 0; c < P2; ++c) { const double2 t2 = f2[c * rep]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
         acc = v[TH];
 #pragma unroll
         for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
       } else {
-        acc = f[i * ldh + nth];
-        for (int c = 0; c < nth; ++c) acc = fma(f[i * ldh + c], src[c], acc);
+        const double2 g2 = f2[(nth >> 1) * rep];
+        acc = (nth & 1) ? g2.y : g2.x;
+        for (int c = 0; c < nth; ++c) {
+          const double2 t2 = f2[(c >> 1) * rep];
+          acc = fma((c & 1) ? t2.y : t2.x, src[c], acc);
+        }
       }
       if (has_clip) {
         if (acc < clip[2 * i]) acc = clip[2 * i];
@@ -92,10 +109,10 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   }
 }
 
-template <int NTH, bool SMEM>
+template <int NTH, bool SMEM, bool PACKED>
 int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
                int32_t *region, int sm_count, cudaStream_t s) {
-  auto kern = bst_eval_kernel<NTH, SMEM>;
+  auto kern = bst_eval_kernel<NTH, SMEM, PACKED>;
   const size_t smem = SMEM ? (size_t)bl.total * sizeof(double) : 0;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -112,9 +129,11 @@ int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_
 template <int NTH>
 int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
               int32_t *region, int sm_count, cudaStream_t s) {
-  if ((size_t)bl.total * sizeof(double) <= 100 * 1024)
-    return launch_k4s<NTH, true>(t, bl, Theta, N, U, region, sm_count, s);
-  return launch_k4s<NTH, false>(t, bl, Theta, N, U, region, sm_count, s);
+  const bool in_smem = (size_t)bl.total * sizeof(double) <= 220 * 1024;
+  if (in_smem && bl.packed) return launch_k4s<NTH, true, true>(t, bl, Theta, N, U, region, sm_count, s);
+  if (in_smem) return launch_k4s<NTH, true, false>(t, bl, Theta, N, U, region, sm_count, s);
+  if (bl.packed) return launch_k4s<NTH, false, true>(t, bl, Theta, N, U, region, sm_count, s);
+  return launch_k4s<NTH, false, false>(t, bl, Theta, N, U, region, sm_count, s);
 }
 
 }  // namespace
@@ -123,7 +142,8 @@ int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, 
                     int sm_count, void *stream) {
   if (N <= 0) return 0;
   BstLayout bl;
-  bl.onodes = t.onodes; bl.ohp = t.ohp; bl.ofb = t.ofb; bl.oclip = t.oclip; bl.ldh = t.ldh; bl.total = t.total;
+  bl.onodes = t.onodes; bl.ohp = t.ohp; bl.ofb = t.ofb; bl.oclip = t.oclip;
+  bl.pairs = t.pairs; bl.rep = t.rep; bl.packed = t.packed; bl.total = t.total;
   cudaStream_t s = (cudaStream_t)stream;
 #define K4_CASE(NN) case NN: return launch_k4<NN>(t, bl, Theta, N, U, region, sm_count, s);
   switch (t.nth) {

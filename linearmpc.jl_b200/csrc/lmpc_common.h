@@ -97,7 +97,8 @@ bool ldp_cta_supports(const LdpLayout &lay);
 
 struct BstDev {
   const double *blk;     // packed tree block on the device (layout: see bst_eval.cu)
-  int onodes, ohp, ofb, oclip, ldh, total;   // offsets / sizes in doubles
+  int onodes, ohp, ofb, oclip, total;        // offsets / sizes in doubles
+  int pairs, rep, packed;                    // 16-byte pairs per row, table replicas, 32-bit node records
   int nth, nu, n_hp, n_fb, n_nodes, has_clip;
 };
 int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
