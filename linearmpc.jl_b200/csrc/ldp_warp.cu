@@ -126,6 +126,7 @@ LMPC_DEVINL void wq_add(const WarpCtx &c, WarpQp &s, int j, bool lower, double d
   if (sing) dnew = 0.0;
   const double dinv = sing ? 0.0 : 1.0 / dnew;
   const int ns = __ffs(~s.used) - 1;         // free physical slot
+  __syncwarp();                              // idle lanes may still be reading stale slots in the sweep
   if (lane < k) c.Lw[ns * c.LS + s.slot] = l;
   if (lane == k) {
     s.D = dnew; s.Dinv = dinv; s.lam = 0.0; s.dW = dval; s.row = j; s.slot = ns;
