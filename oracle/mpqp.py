@@ -67,6 +67,7 @@ class Constraint:
     Ar: np.ndarray
     Ad: np.ndarray
     Aup: np.ndarray
+    Ap: np.ndarray
     ub: np.ndarray
     lb: np.ndarray
     ks: Sequence[int]  # 1-based, k=1 <-> x0 (as in the reference)
@@ -125,6 +126,11 @@ class MPC:
     reference_tracking: bool = True
     preprocess_mpqp: bool = True
     soft_weight: float = 1e6
+    # generalized-parameter (affine) objective terms (Ex p + ex)'x + (Eu p + eu)'u, setup.jl:118-132
+    Ex: Optional[np.ndarray] = None
+    ex: Optional[np.ndarray] = None
+    Eu: Optional[np.ndarray] = None
+    eu: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.F = np.atleast_2d(np.asarray(self.F, float))
@@ -151,8 +157,16 @@ class MPC:
         self.K = np.zeros((nu, nx))
 
     # -- builder API mirroring setup.jl ------------------------------------
-    def set_objective(self, Q=None, R=None, Rr=None, Qf=None):
+    def set_objective(self, Q=None, R=None, Rr=None, Qf=None, Ex=None, ex=None, Eu=None, eu=None):
         """setup.jl:118-132 (subset)."""
+        if Ex is not None:
+            self.Ex = np.atleast_2d(np.asarray(Ex, float))
+        if ex is not None:
+            self.ex = np.atleast_1d(np.asarray(ex, float))
+        if Eu is not None:
+            self.Eu = np.atleast_2d(np.asarray(Eu, float))
+        if eu is not None:
+            self.eu = np.atleast_1d(np.asarray(eu, float))
         if Q is not None:
             self.Q = _diagify(Q, self.ny)
         if R is not None:
@@ -173,7 +187,7 @@ class MPC:
         self.umin = np.concatenate([umin, -BIG * np.ones(nb - len(umin))])
         self.umax = np.concatenate([umax, BIG * np.ones(nb - len(umax))])
 
-    def add_constraint(self, Ax=None, Au=None, Ar=None, Ad=None, Aup=None,
+    def add_constraint(self, Ax=None, Au=None, Ar=None, Ad=None, Aup=None, Ap=None,
                        ub=(), lb=(), ks=None, soft=False, prio=0):
         """setup.jl:61-84."""
         if Ax is None and Au is None:
@@ -191,8 +205,9 @@ class MPC:
         Ar = e if Ar is None else np.atleast_2d(np.asarray(Ar, float))
         Ad = e if Ad is None else np.atleast_2d(np.asarray(Ad, float))
         Aup = e if Aup is None else np.atleast_2d(np.asarray(Aup, float))
+        Ap = e if Ap is None else np.atleast_2d(np.asarray(Ap, float))
         ks = list(range(2, self.Np + 1)) if ks is None else list(ks)
-        self.constraints.append(Constraint(Au, Ax, Ar, Ad, Aup, ub, lb, ks, soft, prio))
+        self.constraints.append(Constraint(Au, Ax, Ar, Ad, Aup, Ap, ub, lb, ks, soft, prio))
 
     def set_output_bounds(self, ymin=(), ymax=(), ks=None, soft=True, prio=0):
         """setup.jl:94-98 (soft by default)."""
@@ -207,22 +222,33 @@ class MPC:
             self.set_output_bounds(ymin, ymax)
 
     # -- parameter layout ---------------------------------------------------
+    def affine_parameter_dim(self):
+        """np: widest generalized-parameter block in use (utils.jl:207-217)."""
+        dims = [0]
+        for E in (self.Ex, self.Eu):
+            if E is not None:
+                dims.append(E.shape[1])
+        dims += [c.Ap.shape[1] for c in self.constraints if c.Ap.size]
+        return max(dims)
+
     def parameter_dims(self):
-        """(nx, nr, nd, nuprev) -- mpc2mpqp.jl:147-164 without previews / p."""
+        """(nx, nr, nd, nuprev) -- mpc2mpqp.jl:147-164 without previews; np via affine_parameter_dim."""
         nr = self.ny if self.reference_tracking else 0
         nd = self.nd_model
         aup = any(c.Aup.size and np.any(c.Aup != 0) for c in self.constraints)
         nuprev = self.nu if (np.any(self.Rr != 0) or aup) else 0
         return self.nx, nr, nd, nuprev
 
-    def form_parameter(self, x, r=None, d=None, uprev=None):
-        """theta = [x; r; d; uprev] (explicit.jl:54-63)."""
+    def form_parameter(self, x, r=None, d=None, uprev=None, p=None):
+        """theta = [x; r; d; uprev; p] (explicit.jl:54-63)."""
         nx, nr, nd, nup = self.parameter_dims()
         x = np.asarray(x, float).reshape(nx)
         r = np.zeros(nr) if r is None else np.asarray(r, float).reshape(-1)[:nr]
         d = np.zeros(nd) if d is None else np.asarray(d, float).reshape(-1)[:nd]
         up = np.zeros(nup) if uprev is None else np.asarray(uprev, float).reshape(-1)[:nup]
-        return np.concatenate([x, r, d, up])
+        npar = self.affine_parameter_dim()
+        pv = np.zeros(npar) if p is None else np.asarray(p, float).reshape(-1)[:npar]
+        return np.concatenate([x, r, d, up, pv])
 
 
 # ---------------------------------------------------------------------------
@@ -313,6 +339,21 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
         f_theta = f_theta + Stot.T @ Phi
     H = (H + H.T) / 2
     f = np.zeros(H.shape[0])
+    # generalized-parameter terms (mpc2mpqp.jl:478-508), constant parameter across the horizon
+    npar = mpc.affine_parameter_dim()
+    nxm = mpc.nx
+    Ex = np.zeros((nxm, npar)) if mpc.Ex is None else mpc.Ex
+    ex = np.zeros(nxm) if mpc.ex is None else mpc.ex
+    Eu = np.zeros((nu, npar)) if mpc.Eu is None else mpc.Eu
+    eu = np.zeros(nu) if mpc.eu is None else mpc.eu
+    Umap = np.kron(np.vstack([np.eye(Nc), np.zeros((N - Nc, Nc))]), np.eye(nu))
+    f = f + Umap.T @ np.tile(eu, N)
+    xsel = np.hstack([np.eye(nxm), np.zeros((nxm, nxe - nxm))])
+    Gx = np.kron(np.eye(N), xsel) @ Gam[nxe:, :]
+    f = f + Gx.T @ np.tile(ex, N)
+    if npar > 0:
+        Fp = Umap.T @ np.tile(Eu, (N, 1)) + Gx.T @ np.tile(Ex, (N, 1))
+        f_theta = np.hstack([f_theta, Fp])
     return H, f, f_theta
 
 
@@ -352,6 +393,16 @@ def general_constraints(mpc: MPC, Phi, Gam):
         prio += [c.prio] * (mi * Ni)
     A = Axt @ Gam + Aut
     W = -Axt @ Phi
+    npar = mpc.affine_parameter_dim()
+    if npar > 0:   # parameter_preview_direct without preview (mpc2mpqp.jl:125-143): W_p = -Ap per row
+        Wp = []
+        for c in mpc.constraints:
+            mi = c.Au.shape[0]
+            kmax = Np + 1 if not np.any(c.Au != 0) else Np
+            Ni = len([k for k in c.ks if k <= kmax])
+            Apm = c.Ap if c.Ap.size else np.zeros((mi, npar))
+            Wp.append(np.tile(-Apm, (Ni, 1)))
+        W = np.hstack([W, np.vstack(Wp)])
     return (A, np.concatenate(ub), np.concatenate(lb), W,
             np.array(soft, bool), np.array(prio, int))
 
@@ -421,7 +472,7 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
     Phi, Gam = state_predictor(F, G, mpc.Np, mpc.Nc)
     H, f, f_theta = dense_objective(mpc, F, G, C, Phi, Gam)
     n = H.shape[0]
-    nth = sum(mpc.parameter_dims())
+    nth = sum(mpc.parameter_dims()) + mpc.affine_parameter_dim()
     if len(mpc.umax):
         bu, bl, W = control_bounds(mpc, nth)
         soft = np.zeros(n, bool)
@@ -625,6 +676,16 @@ def double_integrator_hard(Np=4, Nc=4) -> MPC:
     mpc.set_objective(Q=[1.0], R=[0.1], Rr=[0.0])
     mpc.set_input_bounds(umin=[-1.0], umax=[1.0])
     mpc.add_constraint(Ax=np.array([[0.0, 1.0]]), lb=[-0.5], ub=[0.5], ks=range(2, Np + 2))
+    return mpc
+
+
+def generalized_parameter_example() -> MPC:
+    """runtests.jl:1250-1256: scalar integrator, linear cost (Eu p + eu)'u, parametric constraint
+    u + p <= 1; known answers u = 1.0 (p = 0) and 0.25 (p = 0.75) at runtests.jl:1264-1268."""
+    mpc = MPC(np.array([[1.0]]), np.array([[1.0]]), C=np.array([[1.0]]), Np=4, Nc=4)
+    mpc.set_bounds(umin=[0.0], umax=[2.0])
+    mpc.set_objective(Q=[0.0], R=[1e-6], Eu=np.array([[-1.0]]), eu=[-0.1])
+    mpc.add_constraint(Au=np.array([[1.0]]), Ap=np.array([[1.0]]), ub=[1.0], ks=range(1, 5))
     return mpc
 
 

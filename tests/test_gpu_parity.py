@@ -58,8 +58,16 @@ def test_known_answers_on_gpu(lmpc, name):
     assert abs(u[0] - k["u"]) < k["tol"]
 
 
+@pytest.mark.parametrize("p,expect", [(0.0, 1.0), (0.75, 0.25)])
+def test_known_answer_generalized_parameter_on_gpu(lmpc, p, expect):
+    """runtests.jl:1250-1268 through the GPU (f != 0: nonzero v, u_offset)."""
+    mpc, qp, g, P = gpu_controller(lmpc, "genparam")
+    out = g.solve(mpc.form_parameter([0.0], r=[0.0], p=[p]).reshape(-1, 1))
+    assert out["exitflag"][0] >= 1 and abs(out["U"][0, 0] - expect) < 1e-6
+
+
 CASES = [("invpend", 1.0, 10000), ("invpend", 0.25, 10000), ("invpend", 0.05, 10000),
-         ("dint_hard", 1.0, 10000), ("dint_hard", 0.3, 4000),
+         ("dint_hard", 1.0, 10000), ("dint_hard", 0.3, 4000), ("genparam", 1.0, 5000),
          ("aircraft", 1.0, 4000), ("aircraft", 0.25, 4000), ("aircraft_ksall", 0.25, 2000),
          ("simple", 1.0, 4000), ("simple_q1000", 0.5, 2000),
          ("chain_small", 1.0, 2000), ("chain", 1.0, 300), ("chain", 0.25, 300)]

@@ -31,6 +31,17 @@ def test_known_answers(name):
     assert abs(u[0] - k["u"]) < k["tol"]
 
 
+@pytest.mark.parametrize("p,expect", [(0.0, 1.0), (0.75, 0.25)])
+def test_known_answer_generalized_parameter(p, expect):
+    """runtests.jl:1250-1268: u = 1.0 (p = 0) and 0.25 (p = 0.75), tol 1e-6.  The only known
+    answer with f != 0: exercises v = R^-T f, du/dl += Mext v and the output offset u_offset."""
+    mpc, qp, L, P = make("genparam")
+    assert (mpc.parameter_dims(), mpc.affine_parameter_dim()) == ((1, 1, 0, 0), 1)
+    assert np.any(qp.f != 0) and np.any(L.u_offset != 0)
+    u, flag, _ = P.solve(mpc.form_parameter([0.0], r=[0.0], p=[p]))
+    assert flag >= 1 and abs(u[0] - expect) < 1e-6
+
+
 def test_problem_dimensions():
     """n, m, ms, nth of the BASELINE controllers."""
     _, qp, _, _ = make("invpend")
@@ -102,7 +113,8 @@ def kkt_certificate(L, P, theta, act_u, act_l, rho, tol=1e-6):
 # Gram matrices reach cond ~1e10, so two correct fp64 factorisations differ by ~1e-6 in u (an
 # 80-bit re-solve differs from BOTH by the same amount); the others are well conditioned.
 @pytest.mark.parametrize("name,scale,rtol", [("aircraft", 0.25, 2e-5), ("simple", 1.0, 2e-6),
-                                             ("chain_small", 1.0, 1e-8), ("invpend", 1.0, 1e-9)])
+                                             ("chain_small", 1.0, 1e-8), ("invpend", 1.0, 1e-9),
+                                             ("genparam", 1.0, 1e-8)])
 def test_oracle_solutions_satisfy_kkt(name, scale, rtol):
     mpc, qp, L, P = make(name)
     lo, hi = util.theta_range(name, scale)

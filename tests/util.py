@@ -27,6 +27,8 @@ def controller(name):
         return mpqp.chain_of_masses(nm=4, Np=10, Nc=10)
     if name == "dint_hard":
         return mpqp.double_integrator_hard()
+    if name == "genparam":
+        return mpqp.generalized_parameter_example()
     if name == "simple":
         return mpqp.simple_md(1.0)
     if name == "simple_q1000":
@@ -43,6 +45,8 @@ def theta_range(name, scale=1.0):
         return mpqp.chain_range(10, scale)
     if name == "chain_small":
         return mpqp.chain_range(4, scale)
+    if name == "genparam":      # theta = [x; r; p]
+        return np.array([-1.0, -1.0, -0.5]) * scale, np.array([1.0, 1.0, 1.5]) * scale
     if name == "dint_hard":
         hi = np.array([2.0, 1.0, 2.0]) * scale
         return -hi, hi
