@@ -415,7 +415,7 @@ LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T],
 }
 
 template <int T>
-LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iters) {
+LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iters, bool cold = true) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
   double sh[2 * T];
@@ -431,18 +431,29 @@ LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iter
     }
   }
   int flag = 0;
-  bq_reset<T>(s);
-  TFOR(t) u[t] = 0.0;
-  for (int j = 0; lay.neq > 0 && j < m; ++j) {
-    const int sj = c.cv.sense[j];
-    if (sj & S_ACTIVE) {
-      if (s.k >= lay.cap || s.k >= 32 * T) { flag = EXIT_OVERDETERMINED; break; }
-      const bool low = sj & S_LOWER;
+  if (cold) {
+    bq_reset<T>(s);
+    TFOR(t) u[t] = 0.0;
+    for (int j = 0; lay.neq > 0 && j < m; ++j) {
+      const int sj = c.cv.sense[j];
+      if (sj & S_ACTIVE) {
+        if (s.k >= lay.cap || s.k >= 32 * T) { flag = EXIT_OVERDETERMINED; break; }
+        const bool low = sj & S_LOWER;
+        double shj = 0.0;
+#pragma unroll
+        for (int t2 = 0; t2 < 2 * T; ++t2) { const double x = shfl_d(sh[t2], j & 31); shj = ((j >> 5) == t2) ? x : shj; }
+        bq_add<T>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
+        if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
+      }
+    }
+  } else {
+    // warm start: same working set, new right-hand sides (row j's shift lives on lane j & 31, tile j >> 5)
+    TFOR(t) {
+      const int j = s.row[t];
       double shj = 0.0;
 #pragma unroll
       for (int t2 = 0; t2 < 2 * T; ++t2) { const double x = shfl_d(sh[t2], j & 31); shj = ((j >> 5) == t2) ? x : shj; }
-      bq_add<T>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
-      if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
+      if (lane + 32 * t < s.k) s.dW[t] = (((s.low >> t) & 1u) ? c.cv.dl[j] : c.cv.du[j]) + shj;
     }
   }
   iters = 0;
@@ -526,6 +537,92 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     if (lane == 0) {
       out.flag[q] = flag;
       if (out.iters) out.iters[q] = iters;
+    }
+    __syncwarp();
+  }
+}
+
+// closed loop in warp mode: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
+template <int T>
+__global__ void __launch_bounds__(256)
+ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
+                   const double *__restrict__ cblk, int64_t Ninst, SimDesc sd, int32_t *flagout,
+                   int32_t *itersout, int warps, int per_warp_doubles) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int soff = small_off(lay);
+  stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
+  BigCtx c;
+  c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
+  const double *sb = smem - soff;
+  c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
+  c.cv.Dth = sb + lay.oDth; c.cv.du = sb + lay.odu; c.cv.dl = sb + lay.odl; c.cv.Rinv = sb + lay.oRinv;
+  c.cv.Uth = sb + lay.oUth; c.cv.uoff = sb + lay.ouoff;
+  c.cv.sense = reinterpret_cast<const int32_t *>(sb + lay.oSense);
+  c.lay = &lay; c.st = &st;
+  const int warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  double *w = smem + (lay.total - soff) + (size_t)warp * per_warp_doubles;
+  const int cap = lay.cap;
+  c.Lw = w; w += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+  c.uw = w; w += (lay.n + 1) & ~1;
+  c.thw = w; w += (lay.nth + 1) & ~1;
+  c.lamw = w; w += (cap + 1) & ~1;
+  c.roww = reinterpret_cast<int *>(w); w += (cap + 1) / 2 + 1;
+  c.inwsb = nullptr;
+  const int nx = sd.nx, nr = sd.nr, nd = sd.nd, nup = sd.nuprev, nu = lay.nu;
+  double *xnw = w; w += (nx + 1) & ~1;
+  double *ucw = w;
+  const int lane = c.lane;
+  const int64_t wid = (int64_t)blockIdx.x * warps + warp;
+  const int64_t wstride = (int64_t)gridDim.x * warps;
+  BigQp<T> s;
+  double u[T];
+  for (int64_t q = wid; q < Ninst; q += wstride) {
+    for (int i = lane; i < nx; i += 32) c.thw[i] = ld_stream(sd.X0 + q * nx + i);
+    for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.R ? ld_stream(sd.R + q * nr + i) : 0.0;
+    for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.D ? ld_stream(sd.D + q * nd + i) : 0.0;
+    for (int i = lane; i < nu; i += 32) ucw[i] = (sd.U0 && i < nup) ? ld_stream(sd.U0 + q * nup + i) : 0.0;
+    __syncwarp();
+    int worst = EXIT_OPTIMAL, tot = 0;
+    for (int t = 0; t < sd.T; ++t) {
+      for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
+      __syncwarp();
+      int iters;
+      const int f = bq_solve<T>(c, s, u, iters, !(sd.warm && t > 0));
+      tot += iters;
+      if (f < 0) { if (worst > 0 || f < worst) worst = f; }
+      else if (worst > 0 && f > worst) worst = f;
+      for (int i = 0; i < nu; ++i) {
+        double rr[T];
+        TFOR(tt) { const int cc = lane + 32 * tt; rr[tt] = (cc < lay.n) ? c.cv.Rinv[(size_t)i * lay.n + cc] : 0.0; }
+        const double x = lanesum_pos<T>(c, rr, u, lay.n);
+        double shv = c.cv.uoff[i];
+        const double *ur = c.cv.Uth + (size_t)i * lay.nth;
+        for (int tt = 0; tt < lay.nth; ++tt) shv = fma(ur[tt], c.thw[tt], shv);
+        const double ctl = __dadd_rn(x, shv);
+        if (lane == 0) {
+          ucw[i] = ctl;
+          if (sd.Utraj) sd.Utraj[(q * sd.T + t) * nu + i] = ctl;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < nx; i += 32) {
+        double acc = 0.0;
+        for (int cc = 0; cc < nx; ++cc) acc = fma(sd.F[i * nx + cc], c.thw[cc], acc);
+        for (int cc = 0; cc < nu; ++cc) acc = fma(sd.G[i * nu + cc], ucw[cc], acc);
+        for (int cc = 0; cc < nd; ++cc) acc = fma(sd.Gd[i * nd + cc], c.thw[nx + nr + cc], acc);
+        xnw[i] = acc;
+      }
+      __syncwarp();
+      for (int i = lane; i < nx; i += 32) c.thw[i] = xnw[i];
+      __syncwarp();
+    }
+    for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = c.thw[i];
+    for (int i = lane; i < nu; i += 32) sd.Ulast[q * nu + i] = ucw[i];
+    if (lane == 0) {
+      flagout[q] = worst;
+      if (itersout) itersout[q] = tot;
     }
     __syncwarp();
   }
@@ -665,8 +762,9 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
         // ---- phase B (all threads): u_c = -sum_i lam*_i Mbar[row_i][c], sequential in i ----------
         if (tid < n) {
           double uc = 0.0;
+          const double *mcol = c.M + tid;
 #pragma unroll 8
-          for (int i = 0; i < k; ++i) uc = fma(-c.lamw[i], c.M[(size_t)c.roww[i] * n + tid], uc);
+          for (int i = 0; i < k; ++i) uc = fma(-c.lamw[i], mcol[c.roww[i] * n], uc);
           c.uw[tid] = uc;
         }
         __syncthreads();
@@ -678,9 +776,12 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           const int j = tid + CTA_THREADS * h;
           if (j < m) {
             double mu = 0.0;
-            const double *mt = c.MT + j;
+            // a simple row j is a normalised row of the upper-triangular R^-1: exact zeros before
+            // column j, so the sum may start there (fma(0, u, mu) == mu)
+            const int c0 = (j < lay.ms) ? j : 0;
+            const double *mt = c.MT + j + c0 * mp;
 #pragma unroll 8
-            for (int cc = 0; cc < n; ++cc) mu = fma(mt[(size_t)cc * mp], c.uw[cc], mu);
+            for (int cc = c0; cc < n; ++cc) { mu = fma(*mt, c.uw[cc], mu); mt += mp; }
             if (!c.inwsb[j] && !(c.cv.sense[j] & S_IMMUTABLE)) {
               const double dU = c.cv.du[j] + shr[h], dLo = c.cv.dl[j] + shr[h];
               const double su = dU - mu, sl = mu - dLo;
@@ -845,11 +946,11 @@ int launch_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   return (int)cudaGetLastError();
 }
 
-K3Geom k3_geom(const LdpLayout &lay) {
+K3Geom k3_geom(const LdpLayout &lay, int extra = 0) {
   K3Geom g;
   const size_t cap = lay.cap;
   size_t pw = ((cap * (cap - 1) / 2 + 1) & ~(size_t)1) + ((lay.n + 1) & ~1) + ((lay.nth + 1) & ~1) +
-              ((cap + 1) & ~1) + ((cap + 1) / 2 + 1);
+              ((cap + 1) & ~1) + ((cap + 1) / 2 + 1) + extra;
   pw = (pw + 1) & ~(size_t)1;
   g.per_warp = pw;
   g.small_total = (size_t)(lay.total - lay.oDth);
@@ -878,6 +979,24 @@ int launch_big(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   return (int)cudaGetLastError();
 }
 
+template <int T>
+int launch_big_sim(const LdpLayout &lay, const LdpSettings &st, const double *cblk, int64_t N,
+                   const SolveOut &out, const SimDesc &sim, int sm_count, cudaStream_t s) {
+  const K3Geom g = k3_geom(lay, ((sim.nx + 1) & ~1) + ((lay.nu + 1) & ~1));
+  if (g.warps < 1) return (int)cudaErrorNotSupported;
+  auto kern = ldp_big_sim_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.warps * 32, g.smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (N + g.warps - 1) / g.warps;
+  if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+  kern<<<(unsigned)blocks, g.warps * 32, g.smem, s>>>(lay, st, cblk, N, sim, out.flag, out.iters, g.warps,
+                                                      (int)g.per_warp);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 bool ldp_cta_supports(const LdpLayout &lay) {
@@ -888,12 +1007,20 @@ bool ldp_cta_supports(const LdpLayout &lay) {
 int launch_ldp_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
                    const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
                    int sm_count, void *stream) {
-  if (sim) return (int)cudaErrorNotSupported;   // closed loop runs on K1/K2 (round 1)
   if (N <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   int need = lay.cap > lay.n ? lay.cap : lay.n;
   if ((lay.m + 1) / 2 > need) need = (lay.m + 1) / 2;
   const int T = (need + 31) / 32;
+  if (sim) {   // closed loop: warp mode (one trajectory per warp)
+    switch (T) {
+      case 1: case 2: return launch_big_sim<2>(lay, st, cblk, N, out, *sim, sm_count, s);
+      case 3: case 4: return launch_big_sim<4>(lay, st, cblk, N, out, *sim, sm_count, s);
+      case 5: case 6: return launch_big_sim<6>(lay, st, cblk, N, out, *sim, sm_count, s);
+      case 7: case 8: return launch_big_sim<8>(lay, st, cblk, N, out, *sim, sm_count, s);
+      default: return (int)cudaErrorInvalidValue;
+    }
+  }
   // few QPs fit in an SM's shared memory -> give each QP a whole CTA (cooperative u / scan)
   const bool coop = k3_geom(lay).warps <= 2 && cta_smem(lay) <= 220 * 1024;
   if (coop) {

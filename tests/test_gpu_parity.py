@@ -179,7 +179,7 @@ def test_compute_control_c_twin_other_kernels(lmpc, name):
     assert np.array_equal(flag, ref["flag"]) and np.array_equal(ctl[:, ok], ref["U"][:, ok])
 
 
-@pytest.mark.parametrize("name,T", [("invpend", 100), ("aircraft", 40)])
+@pytest.mark.parametrize("name,T", [("invpend", 100), ("aircraft", 40), ("aircraft_ksall", 40), ("chain_small", 15)])
 @pytest.mark.parametrize("warm", [False, True])
 def test_closed_loop_matches_oracle(lmpc, name, T, warm):
     """BASELINE config 3 shape: N independent Simulation loops (simulation.jl:93-113)."""
@@ -189,7 +189,7 @@ def test_closed_loop_matches_oracle(lmpc, name, T, warm):
     N = 512
     lo, hi = util.theta_range(name, 0.25)
     X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
-    r = np.array([0.1, 0.0]) if name == "aircraft" else np.zeros(nr)
+    r = np.array([0.1, 0.0]) if name.startswith("aircraft") else np.zeros(nr)
     Rm = np.repeat(r.reshape(-1, 1), N, axis=1)
     Dm = np.zeros((nd, N)) if nd else None
     out = g.simulate(mpc.F, mpc.G, X0, r=Rm, d=Dm, N=T, Gd=mpc.Gd if nd else None, warm_start=warm,
