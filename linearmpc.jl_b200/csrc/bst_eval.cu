@@ -24,13 +24,37 @@ struct BstLayout {
   int onodes, ohp, ofb, oclip, pairs, rep, packed, total;
 };
 
+// theta tiles: each warp streams its 32 parameters (one contiguous 32*nth*8-byte block of the
+// column-major Theta) into its own shared-memory slot with ONE TMA bulk copy, issued a whole tree
+// walk ahead; lanes then read their rows conflict-free.  This takes the theta traffic off the
+// L1TEX path that the table gathers saturate.
+LMPC_DEVINL void tile_issue(uint64_t *bar, double *dst, const double *src, uint32_t bytes) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+LMPC_DEVINL void tile_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t b = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(b), "r"(parity) : "memory");
+  }
+}
+
 template <int NTH, bool SMEM, bool PACKED>
 __global__ void __launch_bounds__(K4_BLOCK, 1)
 bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int has_clip,
                 const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
-                int32_t *__restrict__ region) {
+                int32_t *__restrict__ region, int use_tiles) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t tbar[K4_BLOCK / 32];
   const double *base = blk;
   if (SMEM) {
     stage_constants_tma(smem, blk, bl.total, &mbar);
@@ -49,14 +73,42 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   };
   constexpr int TH = NTH > 0 ? NTH : 1;
   constexpr int P2 = (TH + 2) / 2;     // 16-byte pairs covering [a(nth) | b]
-  for (int64_t q = (int64_t)blockIdx.x * K4_BLOCK + threadIdx.x; q < N;
-       q += (int64_t)gridDim.x * K4_BLOCK) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool tiles = SMEM && NTH > 0 && use_tiles;
+  double *tile = smem + bl.total + (size_t)warp * 32 * TH;      // this warp's theta slot
+  uint32_t tphase = 0;
+  const int64_t stride = (int64_t)gridDim.x * K4_BLOCK;
+  const int64_t q0 = (int64_t)blockIdx.x * K4_BLOCK + warp * 32;   // first theta of the warp's tile
+  if (tiles) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar[warp])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // full tiles only (byte count a multiple of 16); a ragged last tile is loaded directly
+    if (lane == 0 && q0 + 32 <= N) tile_issue(&tbar[warp], tile, Theta + q0 * TH, 32u * TH * 8u);
+  }
+  for (int64_t q = (int64_t)blockIdx.x * K4_BLOCK + threadIdx.x; q - lane < N; q += stride) {
+    const int64_t qt = q - lane;              // tile base (warp-uniform)
+    const bool live = q < N;
     const double *src = Theta + q * nth;
     double th[TH];
     if (NTH > 0) {
+      if (tiles && qt + 32 <= N) {
+        tile_wait(&tbar[warp], tphase);
+        tphase ^= 1u;
 #pragma unroll
-      for (int c = 0; c < TH; ++c) th[c] = ld_stream(src + c);
+        for (int c = 0; c < TH; ++c) th[c] = tile[lane * TH + c];
+        __syncwarp();
+        // prefetch the warp's next tile while this one is walked
+        if (lane == 0 && qt + stride + 32 <= N)
+          tile_issue(&tbar[warp], tile, Theta + (qt + stride) * TH, 32u * TH * 8u);
+      } else {
+#pragma unroll
+        for (int c = 0; c < TH; ++c) th[c] = live ? ld_stream(src + c) : 0.0;
+      }
     }
+    if (!live) continue;
     int id = 0;
     int2 nd = load_node(0);
     while (nd.x != 0) {
@@ -113,7 +165,12 @@ template <int NTH, bool SMEM, bool PACKED>
 int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
                int32_t *region, int sm_count, cudaStream_t s) {
   auto kern = bst_eval_kernel<NTH, SMEM, PACKED>;
-  const size_t smem = SMEM ? (size_t)bl.total * sizeof(double) : 0;
+  size_t smem = SMEM ? (size_t)bl.total * sizeof(double) : 0;
+  // room for one 32-theta tile per warp next to the tables?
+  const size_t tile_bytes = (size_t)K4_BLOCK * (NTH > 0 ? NTH : 0) * sizeof(double);
+  const int use_tiles = SMEM && NTH > 0 && smem + tile_bytes <= 225 * 1024 &&
+                        (reinterpret_cast<uintptr_t>(Theta) & 15u) == 0;   // TMA needs 16-byte alignment
+  if (use_tiles) smem += tile_bytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 0;
@@ -122,7 +179,8 @@ int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_
   int64_t blocks = (N + K4_BLOCK - 1) / K4_BLOCK;
   const int64_t cap = (int64_t)sm_count * per_sm;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, K4_BLOCK, smem, s>>>(t.blk, bl, t.nth, t.nu, t.has_clip, Theta, N, U, region);
+  kern<<<(unsigned)blocks, K4_BLOCK, smem, s>>>(t.blk, bl, t.nth, t.nu, t.has_clip, Theta, N, U, region,
+                                                use_tiles);
   return (int)cudaGetLastError();
 }
 
