@@ -36,9 +36,25 @@ WORKLOADS = {
 SEED = 1234  # /root/reference/test/runtests.jl:8
 
 
+def product_controller(name, device):
+    """The controller built with the PRODUCT's own builder (host-side C++ condensing behind the C ABI
+    + GPU upload): README.md:36-53 inverted pendulum, Ts = 0.01 zoh, Np = 50, Nc = 5."""
+    import lmpc_b200
+    from scipy.linalg import expm
+    if name != "invpend":
+        raise KeyError(name)
+    A = np.array([[0, 1, 0, 0], [0, -10, 9.81, 0], [0, 0, 0, 1], [0, -20, 39.24, 0.0]])
+    B = 100 * np.array([[0], [1.0], [0], [2.0]])
+    E = expm(np.block([[A * 0.01, B * 0.01], [np.zeros((1, 5))]]))      # zoh, utils.jl:291-295
+    mpc = lmpc_b200.MPC(E[:4, :4], E[:4, 4:], C=[[1.0, 0, 0, 0], [0, 0, 1.0, 0]], Np=50, Nc=5)
+    mpc.set_objective(Q=[1.2 ** 2, 1], R=[0.0], Rr=[1.0])
+    mpc.set_bounds(umin=[-2.0], umax=[2.0])
+    return mpc.setup(device=device)
+
+
 def build_problem(name):
-    """Controller constants via the test-side restatement of mpc2mpqp (oracle/ is the fixture
-    generator; the product consumes only the resulting arrays, as it would from Julia)."""
+    """CHECKER side only: the same controller through the test-side restatement of mpc2mpqp
+    (oracle/), used for the parity gate and the CPU baseline."""
     from oracle import mpqp
     if name == "invpend":
         mpc = mpqp.invpend()
@@ -190,8 +206,8 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     ctrl, scale, n_per = WORKLOADS[args.workload]
-    mpc, qp = build_problem(ctrl)
-    g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), device=local_rank)
+    g = product_controller(ctrl, local_rank)          # product path: no oracle involved
+    mpc, qp = build_problem(ctrl)                      # checker path
     nth, nu = g.nth, g.nu
     lo, hi = theta_range(ctrl, scale)
 

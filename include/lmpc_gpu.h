@@ -183,6 +183,50 @@ int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double 
 int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, double *U,
                                   int32_t *region, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host-side condensing: build the dense mpQP from a discrete-time model without
+ * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
+ * path supports: no prestabilising feedback, previews, move blocking, offsets, binaries or
+ * generalized parameters.  Pure host code; needs no GPU.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
+  int32_t rows;
+  const double *Au;         /* rows x nu, NULL = 0 (all matrices column-major) */
+  const double *Ax;         /* rows x nx, NULL = 0 */
+  const double *Ar;         /* rows x ny, NULL = 0 */
+  const double *Ad;         /* rows x nd, NULL = 0 */
+  const double *Aup;        /* rows x nu, NULL = 0 */
+  const double *ub, *lb;    /* rows, NULL = +-1e30 */
+  const int32_t *ks;        /* 1-based steps as in the reference: k = 1 is x0 (default there: 2:Np) */
+  int32_t nks;
+  int32_t soft;             /* src/setup.jl:94: output bounds are soft by default */
+  int32_t prio;
+} lmpc_constraint;
+
+typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.jl:17-41) */
+  int32_t nx, nu, ny, nd, Np, Nc;     /* Nc <= 0 means Nc = Np */
+  const double *F, *G;
+  const double *C;          /* ny x nx, NULL = identity (ny = nx) */
+  const double *Gd, *Dd;    /* nx x nd, ny x nd, NULL = 0 */
+  const double *Q, *R, *Rr, *Qf;      /* ny x ny, nu x nu, nu x nu, ny x ny; NULL = I, I, 0, 0 (src/types.jl:35-38) */
+  const double *umin, *umax;          /* nu each or NULL (src/setup.jl:36-46) */
+  const lmpc_constraint *constraints;
+  int32_t n_constraints;
+  int32_t reference_tracking;         /* MPCSettings.reference_tracking (default true) */
+  int32_t preprocess;                 /* MPCSettings.preprocess_mpqp (default true) */
+} lmpc_model;
+
+typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */
+
+int lmpc_gpu_condense(const lmpc_model *model, lmpc_mpqp **out);
+/* dims9 = {n, m, ms, nth, nu, nx, nr, nd, nuprev}: theta = [x(nx); r(nr); d(nd); uprev(nuprev)] */
+int lmpc_gpu_mpqp_dims(const lmpc_mpqp *q, int32_t *dims9);
+/* copy out, column-major: H n x n, f n, f_theta n x nth, A (m-ms) x n, bu m, bl m, W m x nth, senses m */
+int lmpc_gpu_mpqp_get(const lmpc_mpqp *q, double *H, double *f, double *f_theta, double *A,
+                      double *bu, double *bl, double *W, int32_t *senses);
+int lmpc_gpu_mpqp_free(lmpc_mpqp *q);
+const char *lmpc_gpu_condense_error(void);
+
 /* Measurement helpers used by bench.py (not part of the reference's interface):
  * sustained FP64 FMA throughput of the device in TFLOP/s, and the stream of a handle. */
 int lmpc_gpu_fp64_peak(int device, double *tflops);

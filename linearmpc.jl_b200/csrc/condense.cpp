@@ -1,0 +1,364 @@
+// Host-side mpQP condensing behind the C ABI: from a discrete-time model, weights,
+// bounds and constraints to the dense mpQP {H, f, f_theta, A, bu, bl, W, senses} that
+// lmpc_gpu_create consumes, so that non-Julia callers can build a controller.
+//
+// What it follows in the reference (subset: no prestabilising feedback, previews, move blocking,
+// offsets, binaries or generalized parameters -- those requests are refused):
+//   extended system / weights    /root/reference/src/mpc2mpqp.jl:649-731
+//   state predictor              /root/reference/src/mpc2mpqp.jl:20-46
+//   dense objective              /root/reference/src/mpc2mpqp.jl:407-533
+//   control bounds, general rows /root/reference/src/mpc2mpqp.jl:206-245, 249-354
+//   sort / preprocessing         /root/reference/src/mpc2mpqp.jl:733-866
+//   senses, clamping             /root/reference/src/mpc2mpqp.jl:868-899
+// Runs once per controller; plain dense loops.  Checked against the numpy restatement in
+// oracle/mpqp.py by tests/test_condense_cpu.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+#include "lmpc_common.h"
+
+namespace {
+
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> a;   // row-major
+  Mat() {}
+  Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
+  double &operator()(int i, int j) { return a[(size_t)i * c + j]; }
+  double operator()(int i, int j) const { return a[(size_t)i * c + j]; }
+};
+
+Mat from_colmajor(const double *p, int r, int c) {
+  Mat m(r, c);
+  if (p) for (int j = 0; j < c; ++j) for (int i = 0; i < r; ++i) m(i, j) = p[(size_t)j * r + i];
+  return m;
+}
+Mat eye(int n) { Mat m(n, n); for (int i = 0; i < n; ++i) m(i, i) = 1.0; return m; }
+Mat mul(const Mat &A, const Mat &B) {
+  Mat C(A.r, B.c);
+  for (int i = 0; i < A.r; ++i)
+    for (int k = 0; k < A.c; ++k) {
+      const double aik = A(i, k);
+      if (aik == 0.0) continue;
+      for (int j = 0; j < B.c; ++j) C(i, j) += aik * B(k, j);
+    }
+  return C;
+}
+Mat tr(const Mat &A) { Mat T(A.c, A.r); for (int i = 0; i < A.r; ++i) for (int j = 0; j < A.c; ++j) T(j, i) = A(i, j); return T; }
+bool any_nonzero(const Mat &A) { for (double v : A.a) if (v != 0.0) return true; return false; }
+void set_block(Mat &D, int r0, int c0, const Mat &S, double scale = 1.0) {
+  for (int i = 0; i < S.r; ++i) for (int j = 0; j < S.c; ++j) D(r0 + i, c0 + j) = scale * S(i, j);
+}
+void add_block(Mat &D, int r0, int c0, const Mat &S, double scale = 1.0) {
+  for (int i = 0; i < S.r; ++i) for (int j = 0; j < S.c; ++j) D(r0 + i, c0 + j) += scale * S(i, j);
+}
+Mat block_diag(const Mat &A, const Mat &B) {
+  Mat D(A.r + B.r, A.c + B.c);
+  set_block(D, 0, 0, A); set_block(D, A.r, A.c, B);
+  return D;
+}
+Mat rows_of(const Mat &A, const std::vector<int> &idx) {
+  Mat S((int)idx.size(), A.c);
+  for (size_t i = 0; i < idx.size(); ++i) for (int j = 0; j < A.c; ++j) S((int)i, j) = A(idx[i], j);
+  return S;
+}
+Mat sub(const Mat &A, const std::vector<int> &ri, const std::vector<int> &ci) {
+  Mat S((int)ri.size(), (int)ci.size());
+  for (size_t i = 0; i < ri.size(); ++i) for (size_t j = 0; j < ci.size(); ++j) S((int)i, (int)j) = A(ri[i], ci[j]);
+  return S;
+}
+
+}  // namespace
+
+struct lmpc_mpqp {
+  int n = 0, m = 0, ms = 0, nth = 0, nx = 0, nr = 0, nd = 0, nuprev = 0, nu = 0;
+  Mat H, f_theta, A, W;
+  std::vector<double> f, bu, bl;
+  std::vector<int32_t> senses;
+};
+
+static thread_local char c_err[256] = "";
+extern "C" const char *lmpc_gpu_condense_error(void) { return c_err; }
+static int cfail(int code, const char *msg) { snprintf(c_err, sizeof(c_err), "%s", msg); return code; }
+
+extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
+  if (!md || !out) return cfail(LMPC_E_INVALID, "lmpc_gpu_condense: null argument");
+  *out = nullptr;
+  const int nx = md->nx, nu = md->nu, Np = md->Np, Nc = md->Nc > 0 ? md->Nc : md->Np;
+  if (nx <= 0 || nu <= 0 || Np <= 0 || Nc > Np || !md->F || !md->G)
+    return cfail(LMPC_E_INVALID, "lmpc_gpu_condense: bad dimensions");
+  const int ny = md->C ? md->ny : nx;
+  const int ndm = md->nd;
+  if (ndm > 0 && !md->Gd && !md->Dd) return cfail(LMPC_E_INVALID, "nd > 0 needs Gd or Dd");
+  const Mat F0 = from_colmajor(md->F, nx, nx), G0 = from_colmajor(md->G, nx, nu);
+  const Mat C0 = md->C ? from_colmajor(md->C, ny, nx) : eye(nx);
+  const Mat Gd = from_colmajor(md->Gd, nx, ndm), Dd = from_colmajor(md->Dd, ny, ndm);
+  Mat Q = md->Q ? from_colmajor(md->Q, ny, ny) : eye(ny);               // MPCWeights(nu,nx,nr) defaults
+  Mat R = md->R ? from_colmajor(md->R, nu, nu) : eye(nu);
+  Mat Rr = md->Rr ? from_colmajor(md->Rr, nu, nu) : Mat(nu, nu);
+  Mat Qf = md->Qf ? from_colmajor(md->Qf, ny, ny) : Mat(ny, ny);
+  // parameter layout (mpc2mpqp.jl:147-164)
+  const int nr = md->reference_tracking ? ny : 0;
+  const int nd = ndm;
+  bool aup = false;
+  for (int ci = 0; ci < md->n_constraints; ++ci) {
+    const lmpc_constraint &c = md->constraints[ci];
+    if (c.Aup) for (int i = 0; i < c.rows * nu; ++i) if (c.Aup[i] != 0.0) aup = true;
+  }
+  const int nup = (any_nonzero(Rr) || aup) ? nu : 0;
+  const int nxe = nx + nr + nd + nup, nth = nxe;
+
+  // ---- extended system x~ = [x; r; d; u^-] (mpc2mpqp.jl:649-690, K = 0) -------------------------
+  Mat F(nxe, nxe), G(nxe, nu);
+  set_block(F, 0, 0, F0); set_block(G, 0, 0, G0);
+  int off = nx;
+  Mat C = C0;   // grows column-wise
+  auto hcat = [](const Mat &A, const Mat &B) { Mat M(A.r, A.c + B.c); set_block(M, 0, 0, A); set_block(M, 0, A.c, B); return M; };
+  if (nr > 0) {
+    for (int i = 0; i < ny; ++i) F(off + i, off + i) = 1.0;
+    Mat mI = eye(ny); for (double &v : mI.a) v = -v;
+    C = hcat(C, mI);
+    off += ny;
+  }
+  if (nd > 0) {
+    for (int i = 0; i < nd; ++i) F(off + i, off + i) = 1.0;
+    set_block(F, 0, off, Gd);
+    C = hcat(C, Dd);
+    off += nd;
+  }
+  if (nup > 0) {
+    for (int i = 0; i < nu; ++i) G(off + i, i) = 1.0;      // F block stays 0
+    Mat C2(C.r + nu, C.c + nu);
+    set_block(C2, 0, 0, C);
+    for (int i = 0; i < nu; ++i) C2(C.r + i, C.c + i) = 1.0;
+    C = C2;
+  }
+  // ---- extended weights (mpc2mpqp.jl:692-731, K = 0) ----------------------------------------------
+  if (!any_nonzero(Qf)) Qf = Q;
+  Mat S(nxe, nu);
+  if (nup > 0) {
+    Q = block_diag(Q, Rr);
+    Qf = block_diag(Qf, Mat(nu, nu));
+    for (int i = 0; i < nu; ++i) for (int j = 0; j < nu; ++j) { S(nx + nr + nd + i, j) = -Rr(i, j); R(i, j) += Rr(i, j); }
+  }
+  // ---- predictor X = Phi x0 + Gamma U (mpc2mpqp.jl:20-46) -----------------------------------------
+  Mat Phi((Np + 1) * nxe, nxe), Gam((Np + 1) * nxe, Nc * nu);
+  set_block(Phi, 0, 0, eye(nxe));
+  {
+    Mat Pk = eye(nxe), Gk(nxe, Nc * nu);
+    for (int k = 0; k < Np; ++k) {
+      Pk = mul(F, Pk);
+      Gk = mul(F, Gk);
+      const int j = std::min(k, Nc - 1);
+      add_block(Gk, 0, j * nu, G);
+      set_block(Phi, (k + 1) * nxe, 0, Pk);
+      set_block(Gam, (k + 1) * nxe, 0, Gk);
+    }
+  }
+  // ---- objective (mpc2mpqp.jl:407-533) -------------------------------------------------------------
+  std::vector<int> posQ, posF, allc(nxe);
+  for (int i = 0; i < nxe; ++i) allc[i] = i;
+  for (int i = 0; i < Q.r; ++i) if (Q(i, i) > 0) posQ.push_back(i);
+  for (int i = 0; i < Qf.r; ++i) if (Qf(i, i) > 0) posF.push_back(i);
+  const Mat Cp = rows_of(C, posQ), Qp = sub(Q, posQ, posQ), Cf = rows_of(C, posF), Qfp = sub(Qf, posF, posF);
+  const Mat CQC = mul(tr(Cp), mul(Qp, Cp)), CQCf = mul(tr(Cf), mul(Qfp, Cf));
+  const int n = Nc * nu;
+  Mat H(n, n);
+  for (int b = 0; b < Nc; ++b) add_block(H, b * nu, b * nu, R);
+  add_block(H, n - nu, n - nu, R, (double)(Np - Nc));
+  // Gamma' CQCtot Gamma and Gamma' CQCtot Phi, block row by block row (CQCtot is block diagonal)
+  Mat fth(n, nth);
+  for (int k = 0; k <= Np; ++k) {
+    const Mat &W = (k == Np) ? CQCf : CQC;
+    Mat Gk(nxe, n), Pk(nxe, nxe);
+    for (int i = 0; i < nxe; ++i) {
+      for (int j = 0; j < n; ++j) Gk(i, j) = Gam(k * nxe + i, j);
+      for (int j = 0; j < nxe; ++j) Pk(i, j) = Phi(k * nxe + i, j);
+    }
+    const Mat GtW = mul(tr(Gk), W);
+    add_block(H, 0, 0, mul(GtW, Gk));
+    add_block(fth, 0, 0, mul(GtW, Pk));
+  }
+  if (any_nonzero(S)) {
+    // Stot: S on blocks k < Nc (column block k), and on Nc <= k < Np into the last column block
+    Mat GS(n, n), StP(n, nth);
+    for (int k = 0; k < Np; ++k) {
+      const int cb = std::min(k, Nc - 1);
+      Mat Gk(nxe, n), Pk(nxe, nxe);
+      for (int i = 0; i < nxe; ++i) {
+        for (int j = 0; j < n; ++j) Gk(i, j) = Gam(k * nxe + i, j);
+        for (int j = 0; j < nxe; ++j) Pk(i, j) = Phi(k * nxe + i, j);
+      }
+      add_block(GS, 0, cb * nu, mul(tr(Gk), S));
+      add_block(StP, cb * nu, 0, mul(tr(S), Pk));
+    }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) H(i, j) += GS(i, j) + GS(j, i);
+    add_block(fth, 0, 0, StP);
+  }
+  { Mat Hs(n, n); for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Hs(i, j) = 0.5 * (H(i, j) + H(j, i)); H = Hs; }
+
+  // ---- constraints ------------------------------------------------------------------------------------
+  std::vector<double> bu, bl;
+  std::vector<int> soft, prio;
+  Mat W(0, nth);
+  int ms = 0;
+  if (md->umax || md->umin) {
+    ms = n;
+    for (int b = 0; b < Nc; ++b)
+      for (int i = 0; i < nu; ++i) {
+        bu.push_back(md->umax ? md->umax[i] : 1e30);
+        bl.push_back(md->umin ? md->umin[i] : -1e30);
+        soft.push_back(0); prio.push_back(0);
+      }
+    W = Mat(ms, nth);
+  }
+  // general rows (mpc2mpqp.jl:249-354): lb <= [Ax Ar Ad Aup] x~_{k-1} + Au u_{k-1} <= ub, k in ks
+  std::vector<std::vector<double>> Arows, Wrows;
+  std::vector<double> gbu, gbl;
+  std::vector<int> gsoft, gprio;
+  for (int ci = 0; ci < md->n_constraints; ++ci) {
+    const lmpc_constraint &c = md->constraints[ci];
+    const int mi = c.rows;
+    if (mi <= 0) continue;
+    const Mat Au = from_colmajor(c.Au, mi, nu), Ax = from_colmajor(c.Ax, mi, nx);
+    const Mat Ar = from_colmajor(c.Ar, mi, nr), Ad = from_colmajor(c.Ad, mi, nd), Aupm = from_colmajor(c.Aup, mi, nup);
+    Mat row(mi, nxe);
+    set_block(row, 0, 0, Ax); set_block(row, 0, nx, Ar); set_block(row, 0, nx + nr, Ad); set_block(row, 0, nx + nr + nd, Aupm);
+    const int kmax = any_nonzero(Au) ? Np : Np + 1;
+    for (int q = 0; q < c.nks; ++q) {
+      const int k = c.ks[q];
+      if (k < 1 || k > kmax) continue;
+      // x~_{k-1} = Phi_{k-1} x0 + Gam_{k-1} U ; u_{k-1} only for k <= Nc (eyeU has zero rows beyond)
+      Mat Gk(nxe, n), Pk(nxe, nxe);
+      for (int i = 0; i < nxe; ++i) {
+        for (int j = 0; j < n; ++j) Gk(i, j) = Gam((k - 1) * nxe + i, j);
+        for (int j = 0; j < nxe; ++j) Pk(i, j) = Phi((k - 1) * nxe + i, j);
+      }
+      Mat Ak = mul(row, Gk);
+      if (k <= Nc) add_block(Ak, 0, (k - 1) * nu, Au);
+      const Mat Wk = mul(row, Pk);
+      for (int i = 0; i < mi; ++i) {
+        std::vector<double> ar(n), wr(nth);
+        for (int j = 0; j < n; ++j) ar[j] = Ak(i, j);
+        for (int j = 0; j < nth; ++j) wr[j] = -Wk(i, j);
+        Arows.push_back(ar); Wrows.push_back(wr);
+        gbu.push_back(c.ub ? c.ub[i] : 1e30); gbl.push_back(c.lb ? c.lb[i] : -1e30);
+        gsoft.push_back(c.soft ? 1 : 0); gprio.push_back(c.prio);
+      }
+    }
+  }
+  // stable sort of the general rows by priority (mpc2mpqp.jl:859-866)
+  std::vector<int> order(Arows.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return gprio[a] < gprio[b]; });
+  {
+    std::vector<std::vector<double>> A2, W2; std::vector<double> u2, l2; std::vector<int> s2, p2;
+    for (int i : order) { A2.push_back(Arows[i]); W2.push_back(Wrows[i]); u2.push_back(gbu[i]); l2.push_back(gbl[i]); s2.push_back(gsoft[i]); p2.push_back(gprio[i]); }
+    Arows.swap(A2); Wrows.swap(W2); gbu.swap(u2); gbl.swap(l2); gsoft.swap(s2); gprio.swap(p2);
+  }
+  if (md->preprocess) {
+    // remove_redundant (mpc2mpqp.jl:733-773)
+    std::vector<int> keep; std::vector<double> scale;
+    for (size_t i = 0; i < Arows.size(); ++i) {
+      std::vector<double> &a = Arows[i];
+      double nf = 0.0; for (double v : a) nf += v * v; nf = std::sqrt(nf);
+      if (!(nf > 1e-10)) continue;
+      int nz = 0; while (nz < n && !(std::fabs(a[nz]) > 1e-12)) ++nz;
+      if (a[nz] < 0) {
+        for (double &v : a) v = -v + 0.0;
+        const double t = gbu[i]; gbu[i] = -gbl[i]; gbl[i] = -t;
+        for (double &v : Wrows[i]) v = -v + 0.0;
+      }
+      int cnt = 0; for (double v : a) if (std::fabs(v) > 1e-12) ++cnt;
+      if (cnt == 1 && nz < ms && prio[nz] == gprio[i] && soft[nz] == gsoft[i]) {
+        bool same = true;
+        for (int j = 0; j < nth; ++j) if (Wrows[i][j] - W(nz, j) != 0.0) same = false;
+        if (same) { bu[nz] = std::min(bu[nz], gbu[i] / nf); bl[nz] = std::max(bl[nz], gbl[i] / nf); continue; }
+      }
+      keep.push_back((int)i); scale.push_back(1.0 / nf);
+    }
+    if (keep.size() < Arows.size()) {   // rows are normalised only when something was removed (reference behaviour)
+      std::vector<std::vector<double>> A2, W2; std::vector<double> u2, l2; std::vector<int> s2, p2;
+      for (size_t q = 0; q < keep.size(); ++q) {
+        const int i = keep[q]; const double sc = scale[q];
+        std::vector<double> a = Arows[i], w = Wrows[i];
+        for (double &v : a) v *= sc; for (double &v : w) v *= sc;
+        A2.push_back(a); W2.push_back(w); u2.push_back(gbu[i] * sc); l2.push_back(gbl[i] * sc); s2.push_back(gsoft[i]); p2.push_back(gprio[i]);
+      }
+      Arows.swap(A2); Wrows.swap(W2); gbu.swap(u2); gbl.swap(l2); gsoft.swap(s2); gprio.swap(p2);
+    }
+    // remove_duplicate (mpc2mpqp.jl:775-828): rows equal to 6 digits in [A W soft prio]
+    std::map<std::vector<long long>, std::vector<int>> groups;
+    std::vector<std::vector<long long>> first_seen;
+    for (size_t i = 0; i < Arows.size(); ++i) {
+      std::vector<long long> key;
+      for (double v : Arows[i]) key.push_back(std::llround(v * 1e6));
+      for (double v : Wrows[i]) key.push_back(std::llround(v * 1e6));
+      key.push_back(gsoft[i]); key.push_back(gprio[i]);
+      if (!groups.count(key)) first_seen.push_back(key);
+      groups[key].push_back((int)i);
+    }
+    if (first_seen.size() < Arows.size()) {
+      std::vector<std::vector<double>> A2, W2; std::vector<double> u2, l2; std::vector<int> s2, p2;
+      for (auto &key : first_seen) {
+        const std::vector<int> &g = groups[key];
+        const int i0 = g[0];
+        double mu = gbu[i0], ml = gbl[i0];
+        for (int i : g) { mu = std::min(mu, gbu[i]); ml = std::max(ml, gbl[i]); }
+        A2.push_back(Arows[i0]); W2.push_back(Wrows[i0]); u2.push_back(mu); l2.push_back(ml); s2.push_back(gsoft[i0]); p2.push_back(gprio[i0]);
+      }
+      Arows.swap(A2); Wrows.swap(W2); gbu.swap(u2); gbl.swap(l2); gsoft.swap(s2); gprio.swap(p2);
+    }
+  }
+  lmpc_mpqp *q = new lmpc_mpqp();
+  const int mg = (int)Arows.size(), m = ms + mg;
+  q->n = n; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nr; q->nd = nd; q->nuprev = nup; q->nu = nu;
+  q->H = H; q->f_theta = fth; q->f.assign(n, 0.0);
+  q->A = Mat(mg, n); q->W = Mat(m, nth);
+  for (int i = 0; i < ms; ++i) for (int j = 0; j < nth; ++j) q->W(i, j) = W(i, j);
+  q->bu = bu; q->bl = bl;
+  for (int i = 0; i < mg; ++i) {
+    for (int j = 0; j < n; ++j) q->A(i, j) = Arows[i][j];
+    for (int j = 0; j < nth; ++j) q->W(ms + i, j) = Wrows[i][j];
+    q->bu.push_back(gbu[i]); q->bl.push_back(gbl[i]);
+    soft.push_back(gsoft[i]);
+  }
+  // senses + clamping (mpc2mpqp.jl:868-888)
+  q->senses.assign(m, 0);
+  for (int i = 0; i < m; ++i) {
+    if (q->bu[i] > 1e20 && q->bl[i] < -1e20) q->senses[i] = LMPC_IMMUTABLE;
+    else if (std::fabs(q->bu[i] - q->bl[i]) < 1e-12) q->senses[i] = LMPC_ACTIVE + LMPC_IMMUTABLE;
+    if (soft[i]) q->senses[i] += LMPC_SOFT;
+    q->bu[i] = std::min(std::max(q->bu[i], -1e30), 1e30);
+    q->bl[i] = std::min(std::max(q->bl[i], -1e30), 1e30);
+  }
+  *out = q;
+  return 0;
+}
+
+extern "C" int lmpc_gpu_mpqp_dims(const lmpc_mpqp *q, int32_t *dims9) {
+  if (!q || !dims9) return cfail(LMPC_E_INVALID, "null argument");
+  const int32_t d[9] = {q->n, q->m, q->ms, q->nth, q->nu, q->nx, q->nr, q->nd, q->nuprev};
+  memcpy(dims9, d, sizeof(d));
+  return 0;
+}
+
+extern "C" int lmpc_gpu_mpqp_get(const lmpc_mpqp *q, double *H, double *f, double *f_theta, double *A,
+                                 double *bu, double *bl, double *W, int32_t *senses) {
+  if (!q) return cfail(LMPC_E_INVALID, "null argument");
+  const int n = q->n, m = q->m, mg = q->m - q->ms, nth = q->nth;
+  if (H) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) H[(size_t)j * n + i] = q->H(i, j);
+  if (f) memcpy(f, q->f.data(), sizeof(double) * n);
+  if (f_theta) for (int j = 0; j < nth; ++j) for (int i = 0; i < n; ++i) f_theta[(size_t)j * n + i] = q->f_theta(i, j);
+  if (A) for (int j = 0; j < n; ++j) for (int i = 0; i < mg; ++i) A[(size_t)j * mg + i] = q->A(i, j);
+  if (bu) memcpy(bu, q->bu.data(), sizeof(double) * m);
+  if (bl) memcpy(bl, q->bl.data(), sizeof(double) * m);
+  if (W) for (int j = 0; j < nth; ++j) for (int i = 0; i < m; ++i) W[(size_t)j * m + i] = q->W(i, j);
+  if (senses) memcpy(senses, q->senses.data(), sizeof(int32_t) * m);
+  return 0;
+}
+
+extern "C" int lmpc_gpu_mpqp_free(lmpc_mpqp *q) { delete q; return 0; }

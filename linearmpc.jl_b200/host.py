@@ -444,3 +444,164 @@ class GpuExplicitMPC:
         U, _ = self.evaluate(self.form_parameter(x, r, d, uprev), want_region=False)
         self.uprev = U[:, -1].copy()
         return U[:, 0].copy() if single else U
+
+
+# ---------------------------------------------------------------------------------------------
+# Builder mirror: MPC(F, G; ...) / set_objective! / set_bounds! / add_constraint! / setup!
+# (src/types.jl:162-172, src/setup.jl:36-132) on top of lmpc_gpu_condense.  No oracle involved.
+# ---------------------------------------------------------------------------------------------
+class _Constraint(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("Au", C.c_void_p), ("Ax", C.c_void_p), ("Ar", C.c_void_p),
+                ("Ad", C.c_void_p), ("Aup", C.c_void_p), ("ub", C.c_void_p), ("lb", C.c_void_p),
+                ("ks", C.c_void_p), ("nks", C.c_int32), ("soft", C.c_int32), ("prio", C.c_int32)]
+
+
+class _Model(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("ny", C.c_int32), ("nd", C.c_int32),
+                ("Np", C.c_int32), ("Nc", C.c_int32),
+                ("F", C.c_void_p), ("G", C.c_void_p), ("C", C.c_void_p), ("Gd", C.c_void_p), ("Dd", C.c_void_p),
+                ("Q", C.c_void_p), ("R", C.c_void_p), ("Rr", C.c_void_p), ("Qf", C.c_void_p),
+                ("umin", C.c_void_p), ("umax", C.c_void_p),
+                ("constraints", C.c_void_p), ("n_constraints", C.c_int32),
+                ("reference_tracking", C.c_int32), ("preprocess", C.c_int32)]
+
+
+def _diag(v, n):
+    v = np.asarray(v, np.float64)
+    if v.ndim == 0:
+        return np.eye(n) * float(v)
+    return np.diag(v) if v.ndim == 1 else v
+
+
+class MPC:
+    """`MPC(F, G; C, Gd, Dd, Np, Nc)` with the reference's builder calls; `setup()` condenses on the
+    host (C++) and uploads to the GPU, after which `compute_control` / `solve` / `simulate` work as
+    on GpuMPC.  Discrete-time models only (use your own zoh for continuous ones, utils.jl:291-295)."""
+
+    def __init__(self, F, G, C=None, Gd=None, Dd=None, Np=10, Nc=None, Ts=-1.0):
+        f64 = lambda a: np.asarray(a, np.float64)
+        self.F = np.atleast_2d(f64(F)); self.nx = self.F.shape[0]
+        self.G = f64(G).reshape(self.nx, -1); self.nu = self.G.shape[1]
+        self.C = None if C is None else np.atleast_2d(f64(C))
+        self.ny = self.nx if self.C is None else self.C.shape[0]
+        gd = None if Gd is None else f64(Gd).reshape(self.nx, -1)
+        dd = None if Dd is None else f64(Dd).reshape(self.ny, -1)
+        self.nd = max(0 if gd is None else gd.shape[1], 0 if dd is None else dd.shape[1])
+        pad = lambda a, r: None if self.nd == 0 else (np.zeros((r, self.nd)) if a is None else np.hstack([a, np.zeros((r, self.nd - a.shape[1]))]))
+        self.Gd, self.Dd = pad(gd, self.nx), pad(dd, self.ny)
+        self.Np, self.Nc, self.Ts = int(Np), int(Nc if Nc is not None else Np), Ts
+        self.Q = self.R = self.Rr = self.Qf = None
+        self.umin = self.umax = None
+        self.constraints = []
+        self.reference_tracking, self.preprocess_mpqp, self.soft_weight = True, True, 1e6
+        self.gpu = None
+        self.mpqp = None
+
+    # setup.jl:118-132
+    def set_objective(self, Q=None, R=None, Rr=None, Qf=None):
+        if Q is not None: self.Q = _diag(Q, self.ny)
+        if R is not None: self.R = _diag(R, self.nu)
+        if Rr is not None: self.Rr = _diag(Rr, self.nu)
+        if Qf is not None: self.Qf = _diag(Qf, self.ny)
+        self.gpu = None
+
+    # setup.jl:36-46
+    def set_input_bounds(self, umin=None, umax=None):
+        big = 1e30
+        lo = np.atleast_1d(np.asarray([] if umin is None else umin, np.float64))
+        hi = np.atleast_1d(np.asarray([] if umax is None else umax, np.float64))
+        if max(len(lo), len(hi)) == 0:
+            return
+        self.umin = np.concatenate([lo, -big * np.ones(self.nu - len(lo))])
+        self.umax = np.concatenate([hi, big * np.ones(self.nu - len(hi))])
+        self.gpu = None
+
+    # setup.jl:61-84
+    def add_constraint(self, Ax=None, Au=None, Ar=None, Ad=None, Aup=None, ub=(), lb=(), ks=None,
+                       soft=False, prio=0):
+        if Ax is None and Au is None:
+            return
+        ub = np.atleast_1d(np.asarray(ub, np.float64)); lb = np.atleast_1d(np.asarray(lb, np.float64))
+        m = max(len(ub), len(lb))
+        if m == 0:
+            return
+        ub = np.concatenate([ub, 1e30 * np.ones(m - len(ub))]); lb = np.concatenate([lb, -1e30 * np.ones(m - len(lb))])
+        mat = lambda a, c: None if a is None else np.asfortranarray(np.asarray(a, np.float64).reshape(m, c))
+        ks = np.ascontiguousarray(list(range(2, self.Np + 1)) if ks is None else list(ks), np.int32)
+        self.constraints.append(dict(rows=m, Au=mat(Au, self.nu), Ax=mat(Ax, self.nx), Ar=mat(Ar, self.ny),
+                                     Ad=mat(Ad, self.nd), Aup=mat(Aup, self.nu), ub=ub, lb=lb, ks=ks,
+                                     soft=int(bool(soft)), prio=int(prio)))
+        self.gpu = None
+
+    # setup.jl:94-98 (soft by default)
+    def set_output_bounds(self, ymin=(), ymax=(), ks=None, soft=True, prio=0):
+        Cm = np.eye(self.nx) if self.C is None else self.C
+        self.add_constraint(Ax=Cm, Ad=self.Dd, lb=ymin, ub=ymax, ks=ks, soft=soft, prio=prio)
+
+    # setup.jl:105-108
+    def set_bounds(self, umin=None, umax=None, ymin=(), ymax=()):
+        if umin is not None or umax is not None:
+            self.set_input_bounds(umin, umax)
+        if len(np.atleast_1d(ymin)) or len(np.atleast_1d(ymax)):
+            self.set_output_bounds(ymin, ymax)
+
+    def condense(self):
+        """mpc2mpqp on the host (C++): returns the dense mpQP as numpy arrays (row-major views)."""
+        L = lib()
+        L.lmpc_gpu_condense.argtypes = [C.POINTER(_Model), C.POINTER(C.c_void_p)]
+        L.lmpc_gpu_mpqp_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.lmpc_gpu_mpqp_get.argtypes = [C.c_void_p] * 9
+        L.lmpc_gpu_mpqp_free.argtypes = [C.c_void_p]
+        L.lmpc_gpu_condense_error.restype = C.c_char_p
+        keep = []
+        def cm(a):
+            if a is None:
+                return None
+            a = np.asfortranarray(np.asarray(a, np.float64)); keep.append(a)
+            return a.ctypes.data
+        cons = (_Constraint * max(len(self.constraints), 1))()
+        for i, c in enumerate(self.constraints):
+            cons[i] = _Constraint(c["rows"], cm(c["Au"]), cm(c["Ax"]), cm(c["Ar"]), cm(c["Ad"]), cm(c["Aup"]),
+                                  cm(c["ub"]), cm(c["lb"]), c["ks"].ctypes.data, len(c["ks"]), c["soft"], c["prio"])
+        md = _Model(self.nx, self.nu, self.ny, self.nd, self.Np, self.Nc, cm(self.F), cm(self.G), cm(self.C),
+                    cm(self.Gd), cm(self.Dd), cm(self.Q), cm(self.R), cm(self.Rr), cm(self.Qf),
+                    cm(self.umin), cm(self.umax), C.cast(cons, C.c_void_p), len(self.constraints),
+                    int(self.reference_tracking), int(self.preprocess_mpqp))
+        q = C.c_void_p()
+        rc = L.lmpc_gpu_condense(C.byref(md), C.byref(q))
+        if rc != 0:
+            raise LmpcError(rc, L.lmpc_gpu_condense_error().decode())
+        try:
+            d = np.zeros(9, np.int32)
+            L.lmpc_gpu_mpqp_dims(q, d.ctypes.data)
+            n, m, ms, nth, nu, nx, nr, nd, nup = [int(v) for v in d]
+            out = dict(H=np.zeros((n, n), order="F"), f=np.zeros(n), f_theta=np.zeros((n, nth), order="F"),
+                       A=np.zeros((m - ms, n), order="F"), bu=np.zeros(m), bl=np.zeros(m),
+                       W=np.zeros((m, nth), order="F"), senses=np.zeros(m, np.int32))
+            L.lmpc_gpu_mpqp_get(q, *[out[k].ctypes.data for k in ("H", "f", "f_theta", "A", "bu", "bl", "W", "senses")])
+            out["dims"] = (nx, nr, nd, nup)
+        finally:
+            L.lmpc_gpu_mpqp_free(q)
+        self.mpqp = out
+        return out
+
+    def setup(self, device=0, settings=None):
+        """setup!(mpc) + setup_gpu!(mpc): condense, then Cholesky / normalisation / upload."""
+        q = self.condense()
+        self.gpu = GpuMPC(q["H"], q["f"], q["f_theta"], q["A"], q["bu"], q["bl"], q["W"], q["senses"],
+                          nu=self.nu, nx=self.nx, soft_weight=self.soft_weight, device=device,
+                          settings=settings, dims=q["dims"])
+        return self.gpu
+
+    def _g(self):
+        return self.gpu if self.gpu is not None else self.setup()
+
+    def compute_control(self, x, r=None, d=None, uprev=None, check=True):
+        return self._g().compute_control(x, r=r, d=d, uprev=uprev, check=check)
+
+    def solve(self, Theta, **kw):
+        return self._g().solve(Theta, **kw)
+
+    def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False):
+        return self._g().simulate(self.F, self.G, x0, r=r, d=d, N=N, Gd=self.Gd, warm_start=warm_start,
+                                  want_traj=want_traj)

@@ -1,0 +1,73 @@
+"""Host-side condensing behind the C ABI against the numpy restatement of
+mpc2mpqp in oracle/mpqp.py, through the Python builder mirror (no GPU needed)."""
+import numpy as np
+import pytest
+
+import util
+from oracle import mpqp
+
+
+def mirror_of(lmpc, o):
+    """Rebuild an oracle-side controller description with the product's builder API."""
+    m = lmpc.MPC(o.F, o.G, C=o.C, Gd=o.Gd if o.nd_model else None, Dd=o.Dd if o.nd_model else None,
+                 Np=o.Np, Nc=o.Nc)
+    m.set_objective(Q=o.Q, R=o.R, Rr=o.Rr, Qf=o.Qf)
+    if len(o.umax):
+        m.set_input_bounds(o.umin, o.umax)
+    for c in o.constraints:
+        m.add_constraint(Ax=c.Ax, Au=c.Au, Ar=c.Ar if c.Ar.size else None, Ad=c.Ad if c.Ad.size else None,
+                         Aup=c.Aup if c.Aup.size else None, ub=c.ub, lb=c.lb, ks=c.ks, soft=c.soft, prio=c.prio)
+    m.reference_tracking = o.reference_tracking
+    m.soft_weight = o.soft_weight
+    return m
+
+
+@pytest.mark.parametrize("name", ["invpend", "aircraft", "aircraft_ksall", "simple", "simple_q1000",
+                                  "dint_hard", "chain_small", "chain"])
+def test_condense_matches_numpy_restatement(lmpc, name):
+    o = util.controller(name)
+    ref = mpqp.mpc2mpqp(o)
+    q = mirror_of(lmpc, o).condense()
+    assert q["dims"] == o.parameter_dims()
+    assert q["H"].shape == ref.H.shape and q["A"].shape == ref.A.shape and q["W"].shape == ref.W.shape
+    sc = max(1.0, np.abs(ref.H).max())
+    assert np.max(np.abs(q["H"] - ref.H)) <= 1e-12 * sc
+    assert np.max(np.abs(q["f_theta"] - ref.f_theta)) <= 1e-12 * max(1.0, np.abs(ref.f_theta).max())
+    assert np.allclose(q["A"], ref.A, rtol=1e-12, atol=1e-13) and np.allclose(q["W"], ref.W, rtol=1e-12, atol=1e-13)
+    assert np.allclose(q["bu"], ref.bu, rtol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-13)
+    assert np.array_equal(q["senses"], ref.senses) and np.all(q["f"] == 0)
+
+
+def test_condense_preprocessing_known_answer(lmpc):
+    """runtests.jl:1306-1318 through the product's own builder."""
+    F, G = mpqp.zoh(np.array([[0, 1.0], [10, 0]]), np.array([[0], [1.0]]), 0.1)
+    m = lmpc.MPC(F, G, Np=10)
+    m.set_bounds(umin=[-1], umax=[1])
+    m.add_constraint(Au=[[-1.0]], lb=[-0.9], ub=[1.5], ks=range(1, 11))
+    m.add_constraint(Au=[[1.0]], lb=[-0.5], ub=[2.0], ks=range(1, 11))
+    q = m.condense()
+    assert q["A"].shape[0] == 0
+    assert np.all(q["bu"] == 0.9) and np.all(q["bl"] == -0.5)
+
+
+def test_condense_rejects_bad_model(lmpc):
+    m = lmpc.MPC(np.eye(2), np.ones((2, 1)), Np=3, Nc=5)
+    with pytest.raises(lmpc.LmpcError):
+        m.condense()
+
+
+@pytest.mark.gpu
+def test_builder_end_to_end_known_answers(lmpc):
+    """model -> C++ condensing -> GPU, no oracle in the loop: runtests.jl:62-66 and simple.md:107,203."""
+    o = util.controller("invpend")
+    m = mirror_of(lmpc, o)
+    assert abs(m.compute_control(np.array([5.0, 5, 0, 0]))[0] - 1.7612519326) < 1e-6
+    s = lmpc.MPC([[1, 0.5], [0, 1.0]], [[0], [1.0]], C=[[1.0, 0], [1, 1]], Np=10)
+    s.set_objective(Q=[1, 1], R=0, Rr=[1])
+    s.set_bounds(umin=[-3], umax=[3], ymin=[0, 0], ymax=[1, 2])
+    s.add_constraint(Ax=[[2.0, -1]], lb=[-1], ub=[2])
+    assert abs(s.compute_control(np.array([0.5, 1.0]), r=[0.0, 0.0])[0] + 1.0) < 1e-6
+    s.set_objective(Q=[1000, 1], Rr=[1])
+    assert abs(s.compute_control(np.array([0.0, 0.0]), r=[1.0, 0.0], uprev=[0.0])[0] - 1.0) < 1e-6
+    sim = m.simulate(np.array([[0.0, 0, 0.15, 0]]).T, N=200)
+    assert sim["exitflag"][0] >= 1 and abs(sim["Xend"][2, 0]) < 0.05
