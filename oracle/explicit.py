@@ -116,7 +116,7 @@ def _side(region, cell_G, cell_g, a, b, eps=1e-9):
     return (left is not None and left > eps), (right is not None and right > eps)
 
 
-def build_bst(regions, laws, nth, rng=None, samples=None):
+def build_bst(regions, laws, nth, rng=None, samples=None, exact_top=6):
     """Binary search tree over region facets.  Returns (halfplanes n_hp x (nth+1), hp_list, jump_list)."""
     rng = np.random.default_rng(0) if rng is None else rng
     # candidate half-planes: unique normalised facets of all regions (box facets excluded)
@@ -173,7 +173,7 @@ def build_bst(regions, laws, nth, rng=None, samples=None):
                 sc = (max(len(L), len(R)), len(L) + len(R))
                 if choice is None or sc < choice[0]:
                     choice = (sc, ci, L, R)
-            if choice is not None and pos >= 5:
+            if choice is not None and pos >= exact_top - 1:
                 break
         if choice is None:
             raise RuntimeError("no separating facet found")
@@ -203,7 +203,7 @@ def build_bst(regions, laws, nth, rng=None, samples=None):
             np.array(jump_list, np.int32))
 
 
-def explicit_solution(mpc, qp, lo, hi, n_samples=20000, seed=0):
+def explicit_solution(mpc, qp, lo, hi, n_samples=20000, seed=0, exact_top=6):
     """Full fixture: regions, laws, tree and the feedback tensor (n_fb x nu x (nth+1))."""
     from . import mpqp as mq
     ss = mq.make_singlesided(qp, soft_weight=mpc.soft_weight)
@@ -211,7 +211,7 @@ def explicit_solution(mpc, qp, lo, hi, n_samples=20000, seed=0):
     nth = qp.nth
     rng = np.random.default_rng(seed)
     pts = lo + (hi - lo) * rng.random((n_samples, nth))
-    hp, hp_list, jump_list = build_bst(regions, laws, nth, rng, pts)
+    hp, hp_list, jump_list = build_bst(regions, laws, nth, rng, pts, exact_top)
     fb = np.zeros((len(laws), mpc.nu, nth + 1))
     for i, (F, g0) in enumerate(laws):
         fb[i, :, :nth] = F
