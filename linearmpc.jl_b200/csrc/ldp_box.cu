@@ -3,9 +3,10 @@
 // (inverted pendulum: n = m = 5, nth = 7, nu = 1).
 //
 // Same algorithm and the same arithmetic as ldp_thread.cu (bit-identical results), restructured
-// to cut the instruction count, which is what bounds this kernel (ncu r01: issue slots 54 %
-// busy with 12 warps/SM, FP64 pipe 18 %, 7350 thread-instructions per solve for 578
-// algorithmic flops):
+// to cut the instruction count, which is what bounds this kernel (ncu r01 of the general kernel:
+// issue slots 54 % busy with 12 warps/SM, FP64 pipe 18 %, 7350 thread-instructions per solve for
+// 578 algorithmic flops; this kernel: 3200, FP64 pipe 39 %).  Resident CTAs per SM were swept
+// (3 / 4 / 5 / 6 -> 7.0 / 7.0 / 5.1 / 4.1e9 solves/s): registers beat occupancy, hence MINB = 3.
 //   * "unused slots are zero rows": positions >= k always hold L row 0, D = 1/D = 1,
 //     d_W = lam = 0, so the CSP solve, the step and the primal update run unpredicated over
 //     the full capacity and produce exact zeros there (no per-slot selects / predicates);
@@ -16,7 +17,6 @@
 //   * no immutable / soft / singular handling at all (cannot occur for this class).
 #include "ldp_device.cuh"
 #include <math_constants.h>
-#include <cstdlib>
 
 namespace {
 
@@ -284,13 +284,6 @@ int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cb
                    const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 0) return 0;
-  if (lay.n == 5 && lay.nu == 1) {   // tuning hook (development): resident CTAs per SM
-    const char *e = getenv("LMPC_BOX_MINB");
-    const int mb = e ? atoi(e) : 3;
-    if (mb == 4) return launch_box<5, 1, 4>(lay, st, cblk, th, N, out, sm_count, s);
-    if (mb == 5) return launch_box<5, 1, 5>(lay, st, cblk, th, N, out, sm_count, s);
-    if (mb == 6) return launch_box<5, 1, 6>(lay, st, cblk, th, N, out, sm_count, s);
-  }
   switch (lay.n) {
     KB_CASE(1) KB_CASE(2) KB_CASE(3) KB_CASE(4) KB_CASE(5) KB_CASE(6) KB_CASE(7) KB_CASE(8)
     default: return (int)cudaErrorInvalidValue;

@@ -244,7 +244,7 @@ class GpuMPC:
         return out
 
     # -- solve(mpc, theta), batched ---------------------------------------------------------
-    def solve(self, Theta, want_iters=True, want_active=True, out=None):
+    def solve(self, Theta, want_iters=True, want_active=True):
         """Theta: nth x N host array (or device tensor of N x nth contiguous = nth x N column-major).
 
         Returns dict(U nu x N, exitflag N, iters N, active_upper, active_lower (N x words))."""

@@ -79,16 +79,3 @@ def bits(words, m):
     for j in range(m):
         out[:, j] = (w[:, j // 64] >> np.uint64(j % 64)) & np.uint64(1)
     return out
-
-
-def nondegenerate(P, Theta, out, tol=1e-6):
-    """Operational non-degeneracy: min |slack| of inactive rows and min |lambda|
-    proxy: distance of every inactive row from its bounds > 10*tol at the oracle optimum."""
-    Th = np.asarray(Theta)
-    sh = P.Dth @ Th
-    act = bits(out["act_u"], P.m) | bits(out["act_l"], P.m)
-    # reconstruct v from the active set by least squares on the oracle's own result is
-    # unnecessary: use the slack of inactive rows at u (primal) via Mbar v = ... not available;
-    # the caller only needs a conservative mask, so flag instances whose iteration count hit a
-    # tie-sensitive path: none detected in practice.
-    return np.ones(Th.shape[1], bool), act, sh
