@@ -157,9 +157,39 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
     box_reset<N>(s);
     double u[N];
     SFOR(c, 0, N) u[c] = 0.0; SEND
-    int flag = EXIT_ITERLIMIT, iter, cycle = 0;
+    int flag = EXIT_ITERLIMIT, iter = 1, cycle = 0;
     double best_fval = -1.0, fval = 0.0;
-    for (iter = 1; iter < st.iter_limit; ++iter) {
+    bool done = false;
+    // Iteration 1 is the same for every thread: empty working set, u = 0, so every slack is
+    // just a bound (d_u - 0, 0 - d_l), the dual objective is 0, and the first row is appended at
+    // the static position 0.  Same values as the generic iteration, none of its padding.
+    if (st.iter_limit > 2) {
+      double best = -st.primal_tol;
+      int code = -1;
+      SFOR(j, 0, N)
+        const double su = dU[j] - 0.0, sl = 0.0 - dLo[j];
+        const bool tu = su < best;
+        const bool tl = !tu && (sl < best);
+        best = tu ? su : (tl ? sl : best);
+        code = tu ? 2 * j : (tl ? 2 * j + 1 : code);
+      SEND
+      const int add = code >> 1;
+      const bool addlow = code & 1;
+      if (add < 0) { flag = EXIT_OPTIMAL; done = true; }
+      else {
+        if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+        else cycle++;
+        double addd = 0.0;
+        SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
+        const double g = cv.G[add * N + add];
+        s.D[0] = g; s.Dinv[0] = 1.0 / g; s.dW[0] = addd; s.row[0] = add;
+        s.lowmask = addlow ? 1u : 0u;
+        s.inws = 1u << add;
+        s.k = 1;
+        iter = 2;
+      }
+    }
+    for (; !done && iter < st.iter_limit; ++iter) {
       // 1. CSP over the full capacity (slots >= k are zero rows -> exact zeros)
       double z[N];
       SFOR(i, 0, N)
