@@ -189,6 +189,64 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
         iter = 2;
       }
     }
+    // Iteration 2: every thread still running holds exactly one row, at position 0, so the CSP is
+    // one multiply, u one row of Mbar, and the second row is appended at the static position 1.
+    // (A blocked multiplier cannot occur with a single violated row, but if rounding ever
+    // produced one, the generic loop below redoes this iteration from the same state.)
+    if (!done && st.iter_limit > 3) {
+      const double l0 = -s.dW[0] * s.Dinv[0];
+      const bool low0 = s.lowmask & 1u;
+      const bool blocked = low0 ? (l0 > st.dual_tol) : (l0 < -st.dual_tol);
+      if (!blocked) {
+        s.lams[0] = l0;
+        const double *mr = cv.M + s.row[0] * N;
+        SFOR(c, 0, N) u[c] = fma(-l0, mr[c], 0.0); SEND
+        double pu[N];
+        SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
+        fval = tree_sum<N, 0, 1>(pu);
+        if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; done = true; }
+        else {
+          double best = -st.primal_tol;
+          int code = -1;
+          SFOR(j, 0, N)
+            double mu = 0.0;
+            SFOR(c, j, N) mu = fma(cv.M[j * N + c], u[c], mu); SEND
+            const bool free_row = !((s.inws >> j) & 1u);
+            const double su = dU[j] - mu, sl = mu - dLo[j];
+            const bool tu = free_row && (su < best);
+            const bool tl = free_row && !tu && (sl < best);
+            best = tu ? su : (tl ? sl : best);
+            code = tu ? 2 * j : (tl ? 2 * j + 1 : code);
+          SEND
+          const int add = code >> 1;
+          const bool addlow = code & 1;
+          if (add < 0) { flag = EXIT_OPTIMAL; done = true; }
+          else {
+            bool cyc = false;
+            if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+            else if (cycle++ > st.cycle_tol) cyc = true;
+            if (cyc) { flag = EXIT_CYCLE; done = true; }
+            else if constexpr (N >= 2) {
+              double addd = 0.0;
+              SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
+              const double *g = cv.G + add * N;
+              const double y0 = g[s.row[0]];
+              const double ll = y0 * s.Dinv[0];
+              const double dnew = __dsub_rn(g[add], __dmul_rn(y0, ll));
+              s.lam[0] = l0;
+              s.L[LIDX(1, 0)] = ll;
+              s.D[1] = dnew; s.Dinv[1] = 1.0 / dnew; s.dW[1] = addd; s.row[1] = add;
+              if (addlow) s.lowmask |= 2u;
+              s.inws |= 1u << add;
+              s.k = 2;
+              iter = 3;
+            } else {
+              flag = EXIT_CAPACITY; done = true;
+            }
+          }
+        }
+      }
+    }
     for (; !done && iter < st.iter_limit; ++iter) {
       // 1. CSP over the full capacity (slots >= k are zero rows -> exact zeros)
       double z[N];
