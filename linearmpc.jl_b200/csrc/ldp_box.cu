@@ -313,6 +313,8 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
         SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
         fval = tree_sum<N, 0, 1>(pu);
         if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
+        // every row already in the working set: the scan cannot find a violated free row
+        if (s.inws == (1u << N) - 1u) { flag = EXIT_OPTIMAL; break; }
         double best = -st.primal_tol;
         int code = -1;                       // 2 * row + (1 if lower)
         SFOR(j, 0, N)
