@@ -129,6 +129,34 @@ def oracle_problem(mpc, qp, cst=None):
     return P
 
 
+def count_degenerate(P, Theta, ref, tol=1e-6):
+    """Operational non-degeneracy: instances whose optimum has an inactive row within
+    10*tol of a bound or an active multiplier below 10*tol -- where two correct solvers may
+    legitimately report different active sets.  Re-solved in numpy from the oracle's active set."""
+    m = P.m
+    n_deg = 0
+    au = (ref["act_u"][:, 0][:, None] >> np.arange(m, dtype=np.uint64)) & np.uint64(1)
+    al = (ref["act_l"][:, 0][:, None] >> np.arange(m, dtype=np.uint64)) & np.uint64(1)
+    sh = P.Dth @ Theta
+    for q in range(Theta.shape[1]):
+        act = np.where((au[q] | al[q]) != 0)[0]
+        du, dl = P.du + sh[:, q], P.dl + sh[:, q]
+        if len(act):
+            Mw = P.Mbar[act]
+            dw = np.where(au[q][act] != 0, du[act], dl[act])
+            lam = np.linalg.solve(Mw @ Mw.T, -dw)
+            v = -Mw.T @ lam
+            margin = np.min(np.abs(lam))
+        else:
+            v = np.zeros(P.n); margin = np.inf
+        inact = np.setdiff1d(np.arange(m), act)
+        if len(inact):
+            mv = P.Mbar[inact] @ v
+            margin = min(margin, np.min(du[inact] - mv), np.min(mv - dl[inact]))
+        n_deg += int(margin < 10 * tol)
+    return n_deg
+
+
 def cpu_leg(P, Theta_host, passes=2):
     """The oracle port on all host cores over a bounded sample (about 10-30 core-seconds):
     returns (solves/s, cores, n, flops/solve, last result)."""
@@ -234,7 +262,8 @@ def main():
                np.all(got["active_lower"] == ref["act_l"], axis=1)
         rel = float(np.max(np.abs(got["U"] - ref["U"]) / np.maximum(1.0, np.abs(ref["U"]))))
         parity = {"n": 10000, "identical_flag_and_active_set": int(same.sum()), "max_rel_err_u": rel,
-                  "bit_identical_u": bool(np.array_equal(got["U"], ref["U"]))}
+                  "bit_identical_u": bool(np.array_equal(got["U"], ref["U"])),
+                  "degenerate": count_degenerate(P, sub, ref)}
         flops_per_solve = float(ref["flops"].mean())
         if not args.no_cpu_baseline and world == 1:
             host = Th.cpu().numpy().T                      # the whole 1e7-theta batch of rank 0
