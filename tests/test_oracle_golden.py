@@ -172,3 +172,34 @@ def test_thread_count_does_not_change_results():
     a = P.solve_batch(Th, nthreads=1)
     b = P.solve_batch(Th, nthreads=5)
     assert np.array_equal(a["U"], b["U"]) and np.array_equal(a["act_u"], b["act_u"])
+
+
+def test_soft_rows_equal_the_reference_explicit_slack_form():
+    """The oracle handles soft rows as rho = 1/soft_weight on the NORMALISED rows' LDL diagonal.
+    The reference states the same problem with explicit slack variables weighted by soft_weight
+    (make_singlesided, src/utils.jl:341-364; rho_soft at src/setup.jl:26).  Solve that explicit
+    form with an unrelated method (SLSQP) and compare: 50 theta, 13 with active soft rows."""
+    from scipy.optimize import minimize
+    mpc, qp, L, P = make("simple")
+    ss = mpqp.make_singlesided(qp, soft_weight=mpc.soft_weight, single_soft=False)
+    H, f, fth, A, b, W = ss["H"], ss["f"], ss["f_theta"], ss["A"], ss["b"], ss["W"]
+    lo, hi = util.theta_range("simple", 0.6)
+    Th = mpqp.sample_theta(lo, hi, 60, seed=3)
+    out = P.solve_batch(Th)
+    n = qp.n
+    sc = np.ones(H.shape[0])
+    sc[n:] = 1 / np.sqrt(mpc.soft_weight)          # rescale the slack variables for conditioning
+    Hs, As = H * sc[:, None] * sc[None, :], A * sc[None, :]
+    checked = soft_active = 0
+    for q in range(Th.shape[1]):
+        if out["flag"][q] < 1:
+            continue
+        g, rhs = (f + fth @ Th[:, q]) * sc, b + W @ Th[:, q]
+        res = minimize(lambda z: 0.5 * z @ Hs @ z + g @ z, np.zeros(len(sc)), jac=lambda z: Hs @ z + g,
+                       method="SLSQP", constraints=[{"type": "ineq", "fun": lambda z: rhs - As @ z,
+                                                     "jac": lambda z: -As}],
+                       options={"ftol": 1e-15, "maxiter": 500})
+        assert abs(res.x[0] - out["U"][0, q]) < 1e-6
+        checked += 1
+        soft_active += int(out["flag"][q] == 2)
+    assert checked >= 40 and soft_active >= 5
