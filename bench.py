@@ -36,7 +36,7 @@ WORKLOADS = {
 SEED = 1234  # /root/reference/test/runtests.jl:8
 
 
-def product_controller(name, device):
+def product_model(name):
     """The controller built with the PRODUCT's own builder (host-side C++ condensing behind the C ABI
     + GPU upload): README.md:36-53 inverted pendulum, Ts = 0.01 zoh, Np = 50, Nc = 5."""
     import lmpc_b200
@@ -49,7 +49,11 @@ def product_controller(name, device):
     mpc = lmpc_b200.MPC(E[:4, :4], E[:4, 4:], C=[[1.0, 0, 0, 0], [0, 0, 1.0, 0]], Np=50, Nc=5)
     mpc.set_objective(Q=[1.2 ** 2, 1], R=[0.0], Rr=[1.0])
     mpc.set_bounds(umin=[-2.0], umax=[2.0])
-    return mpc.setup(device=device)
+    return mpc
+
+
+def product_controller(name, device):
+    return product_model(name).setup(device=device)
 
 
 def build_problem(name):

@@ -164,6 +164,20 @@ int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, co
                             double *Xend, double *Ulast, double *Utraj,
                             int32_t *exitflag, int32_t *iters);
 
+/* One process, several GPUs (BASELINE north_star: "the batch is sharded by contiguous theta ranges
+ * across the 8 B200s of one box with no inter-GPU traffic beyond a final result gather").
+ * create_multi builds one replica of the controller per listed device (devices NULL = 0..n-1);
+ * solve_batch_multi takes HOST buffers, gives device g the contiguous range
+ * [g N / G, (g+1) N / G), runs the per-device host pipelines concurrently (one worker thread per
+ * GPU) and returns when every slice of U / exitflag has landed in the caller's arrays. */
+typedef struct lmpc_multi lmpc_multi;
+int lmpc_gpu_create_multi(const lmpc_problem *p, const lmpc_settings *s, const int32_t *devices,
+                          int32_t n_devices, lmpc_multi **out);
+int lmpc_gpu_destroy_multi(lmpc_multi *m);
+int lmpc_gpu_solve_batch_multi(lmpc_multi *m, const double *Theta, int64_t N, double *U,
+                               int32_t *exitflag, int32_t *iters,
+                               uint64_t *active_upper, uint64_t *active_lower);
+
 /* Replaces ParametricDAQP.build_tree's result as used by compute_control(empc, ...)
  * (src/utils.jl:53-60, src/explicit.jl:65-71).  halfplanes (nth+1) x n_hp column-major
  * (column h = [a_h; b_h]); feedbacks n_fb blocks of (nth+1) x nu column-major (u = F'[theta;1]);

@@ -7,6 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
+#include <functional>
+#include <string>
+#include <thread>
 #include <vector>
 #include "lmpc_common.h"
 
@@ -43,10 +48,54 @@ struct DevBuf {
 constexpr int kSlots = 3;
 constexpr int64_t kChunk = 1 << 20;   // instances per pipeline stage for host buffers
 
+// pinned staging for callers that hand us pageable arrays (a Julia Matrix, a numpy array)
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_err(LMPC_E_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e));
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct Slot {
   cudaStream_t stream = nullptr;
   DevBuf in[4], u, flag, iters, au, al, aux[3];
+  PinBuf hin[4], hu, hflag, hiters, hau, hal;
+  int64_t pend_off = 0, pend_cnt = 0;   // results sitting in the pinned buffers, not yet handed out
 };
+
+bool is_pageable(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// The driver's own pageable path stages through one thread (about 8 GB/s measured); several
+// host threads copying into / out of our pinned ring keep the PCIe link busy instead.
+int copy_threads(int share) {
+  static const int n = [] {
+    if (const char *e = getenv("LMPC_GPU_COPY_THREADS")) return std::max(1, atoi(e));
+    const int hc = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(8, hc / 2));
+  }();
+  return std::max(1, n / std::max(1, share));
+}
+
+void parallel_rows(int64_t rows, int nthreads, const std::function<void(int64_t, int64_t)> &f) {
+  if (nthreads <= 1 || rows < 4096) { f(0, rows); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(f, rows * t / nthreads, rows * (t + 1) / nthreads);
+  f(0, rows / nthreads);
+  for (auto &x : th) x.join();
+}
 
 bool is_device_ptr(const void *p) {
   if (!p) return false;
@@ -74,6 +123,7 @@ int check_device(int device, int *sm_count) {
 
 struct lmpc_handle {
   int device = 0, sm_count = 148, kernel = 0;
+  int copy_share = 1;   // how many handles split the host's copy threads (multi-device handle)
   LdpLayout lay;
   LdpSettings st;
   double *h_blk = nullptr;
@@ -168,6 +218,8 @@ static void free_slots(Slot *slots) {
     for (auto &b : s.in) b.release();
     for (auto &b : s.aux) b.release();
     s.u.release(); s.flag.release(); s.iters.release(); s.au.release(); s.al.release();
+    for (auto &b : s.hin) b.release();
+    s.hu.release(); s.hflag.release(); s.hiters.release(); s.hau.release(); s.hal.release();
     if (s.stream) cudaStreamDestroy(s.stream);
     s.stream = nullptr;
   }
@@ -255,22 +307,62 @@ int lmpc_gpu_solve_batch_async(lmpc_handle *h, const double *Theta, int64_t N, d
   return run_kernel(h, th, N, o, nullptr, stream ? (cudaStream_t)stream : h->stream);
 }
 
-// host buffers: H2D -> kernel -> D2H in kChunk-sized stages round-robined over kSlots streams
+// hand a finished stage's results from the pinned ring to the caller's pageable arrays
+static int drain_slot(lmpc_handle *h, Slot &s, double *U, int ustride, int32_t *flag, int32_t *iters,
+                      uint64_t *au, uint64_t *al) {
+  CUDA_OK(cudaStreamSynchronize(s.stream));
+  if (s.pend_cnt == 0) return 0;
+  const LdpLayout &l = h->lay;
+  const int words = (l.m + 63) / 64;
+  const int64_t off = s.pend_off;
+  parallel_rows(s.pend_cnt, copy_threads(h->copy_share), [&](int64_t a, int64_t b) {
+    const double *su = (const double *)s.hu.p;
+    if (ustride == l.nu) memcpy(U + (off + a) * l.nu, su + a * l.nu, (size_t)(b - a) * l.nu * 8);
+    else for (int64_t i = a; i < b; ++i) memcpy(U + (off + i) * ustride, su + i * l.nu, (size_t)l.nu * 8);
+    memcpy(flag + off + a, (const int32_t *)s.hflag.p + a, (size_t)(b - a) * 4);
+    if (iters) memcpy(iters + off + a, (const int32_t *)s.hiters.p + a, (size_t)(b - a) * 4);
+    if (au) {
+      memcpy(au + (off + a) * words, (const uint64_t *)s.hau.p + a * words, (size_t)(b - a) * words * 8);
+      memcpy(al + (off + a) * words, (const uint64_t *)s.hal.p + a * words, (size_t)(b - a) * words * 8);
+    }
+  });
+  s.pend_cnt = 0;
+  return 0;
+}
+
+// host buffers: H2D -> kernel -> D2H in kChunk-sized stages round-robined over kSlots streams.
+// Pinned caller memory is DMA'd in place; pageable memory goes through a pinned ring filled and
+// emptied by several host threads while the other stages' DMA and kernels run.
 static int solve_segments_host(lmpc_handle *h, const double *const *seg, const int *len,
                                const int *stride, int nseg, int64_t N, double *U, int ustride,
                                int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al) {
   const LdpLayout &l = h->lay;
   const int words = (l.m + 63) / 64;
-  for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
-    const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;
+  bool stage = is_pageable(U) || is_pageable(flag);
+  for (int g = 0; g < nseg; ++g) stage = stage || is_pageable(seg[g]);
+  const int64_t chunk = stage ? kChunk / 4 : kChunk;   // smaller stages: the ring fills sooner
+  for (int i = 0; i < kSlots; ++i) h->slots[i].pend_cnt = 0;
+  for (int64_t off = 0, c = 0; off < N; off += chunk, ++c) {
+    const int64_t cnt = (N - off < chunk) ? (N - off) : chunk;
     Slot &s = h->slots[c % kSlots];
+    if (stage) { int rc = drain_slot(h, s, U, ustride, flag, iters, au, al); if (rc) return rc; }
     ThetaSegs th;
     memset(&th, 0, sizeof(th));
     th.nseg = nseg;
     for (int g = 0; g < nseg; ++g) {
       const size_t bytes = (size_t)cnt * stride[g] * sizeof(double);
       if (s.in[g].reserve(bytes)) return LMPC_E_CUDA;
-      CUDA_OK(cudaMemcpyAsync(s.in[g].p, seg[g] + off * stride[g], bytes, cudaMemcpyHostToDevice, s.stream));
+      const double *src = seg[g] + off * stride[g];
+      if (stage) {
+        if (s.hin[g].reserve(bytes)) return LMPC_E_CUDA;
+        char *dst = (char *)s.hin[g].p;
+        const size_t row = (size_t)stride[g] * 8;
+        parallel_rows(cnt, copy_threads(h->copy_share), [&](int64_t a, int64_t b) {
+          memcpy(dst + a * row, (const char *)src + a * row, (size_t)(b - a) * row);
+        });
+        src = (const double *)s.hin[g].p;
+      }
+      CUDA_OK(cudaMemcpyAsync(s.in[g].p, src, bytes, cudaMemcpyHostToDevice, s.stream));
       th.ptr[g] = (const double *)s.in[g].p; th.len[g] = len[g]; th.stride[g] = stride[g];
     }
     if (s.u.reserve((size_t)cnt * l.nu * sizeof(double)) || s.flag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
@@ -280,6 +372,20 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
                au ? (uint64_t *)s.au.p : nullptr, au ? (uint64_t *)s.al.p : nullptr};
     int rc = run_kernel(h, th, cnt, o, nullptr, s.stream);
     if (rc) return rc;
+    if (stage) {
+      if (s.hu.reserve((size_t)cnt * l.nu * 8) || s.hflag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+      if (iters && s.hiters.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+      if (au && (s.hau.reserve((size_t)cnt * words * 8) || s.hal.reserve((size_t)cnt * words * 8))) return LMPC_E_CUDA;
+      CUDA_OK(cudaMemcpyAsync(s.hu.p, s.u.p, (size_t)cnt * l.nu * 8, cudaMemcpyDeviceToHost, s.stream));
+      CUDA_OK(cudaMemcpyAsync(s.hflag.p, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+      if (iters) CUDA_OK(cudaMemcpyAsync(s.hiters.p, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+      if (au) {
+        CUDA_OK(cudaMemcpyAsync(s.hau.p, s.au.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_OK(cudaMemcpyAsync(s.hal.p, s.al.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
+      }
+      s.pend_off = off; s.pend_cnt = cnt;
+      continue;
+    }
     if (ustride == l.nu) {
       CUDA_OK(cudaMemcpyAsync(U + off * l.nu, s.u.p, (size_t)cnt * l.nu * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     } else {
@@ -293,7 +399,10 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
       CUDA_OK(cudaMemcpyAsync(al + off * words, s.al.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
     }
   }
-  for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(h->slots[i].stream));
+  for (int i = 0; i < kSlots; ++i) {
+    int rc = drain_slot(h, h->slots[i], U, ustride, flag, iters, au, al);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -543,6 +652,66 @@ int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double 
     if (region) CUDA_OK(cudaMemcpyAsync(region + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
   }
   for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(t->slots[i].stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// one process, several GPUs: contiguous theta ranges, one worker thread per device
+// ---------------------------------------------------------------------------------------
+struct lmpc_multi {
+  std::vector<lmpc_handle *> h;
+};
+
+int lmpc_gpu_create_multi(const lmpc_problem *p, const lmpc_settings *s, const int32_t *devices,
+                          int32_t n_devices, lmpc_multi **out) {
+  if (!p || !out || n_devices <= 0) return set_err(LMPC_E_INVALID, "lmpc_gpu_create_multi: bad argument%s");
+  *out = nullptr;
+  lmpc_multi *m = new lmpc_multi();
+  for (int i = 0; i < n_devices; ++i) {
+    lmpc_handle *h = nullptr;
+    const int rc = lmpc_gpu_create(p, s, devices ? devices[i] : i, &h);
+    if (rc != 0) {
+      for (auto *x : m->h) lmpc_gpu_destroy(x);
+      delete m;
+      return rc;
+    }
+    m->h.push_back(h);
+  }
+  for (auto *x : m->h) x->copy_share = n_devices;
+  *out = m;
+  return 0;
+}
+
+int lmpc_gpu_destroy_multi(lmpc_multi *m) {
+  if (!m) return 0;
+  for (auto *x : m->h) lmpc_gpu_destroy(x);
+  delete m;
+  return 0;
+}
+
+int lmpc_gpu_solve_batch_multi(lmpc_multi *m, const double *Theta, int64_t N, double *U,
+                               int32_t *exitflag, int32_t *iters, uint64_t *au, uint64_t *al) {
+  if (!m || m->h.empty() || !Theta || !U || !exitflag || N < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_solve_batch_multi: bad argument%s");
+  const int G = (int)m->h.size();
+  const LdpLayout &l = m->h[0]->lay;
+  const int words = (l.m + 63) / 64;
+  std::vector<int> rc(G, 0);
+  std::vector<std::string> msg(G);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g) {
+    const int64_t lo = N * g / G, hi = N * (g + 1) / G;     // contiguous range [g N / G, (g+1) N / G)
+    th.emplace_back([=, &rc, &msg]() {
+      if (hi <= lo) return;
+      rc[g] = lmpc_gpu_solve_batch(m->h[g], Theta + lo * l.nth, hi - lo, U + lo * l.nu, exitflag + lo,
+                                   iters ? iters + lo : nullptr, au ? au + lo * words : nullptr,
+                                   al ? al + lo * words : nullptr);
+      if (rc[g]) msg[g] = g_err;      // thread-local error text of the worker
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rc[g]) return set_err(rc[g], "device worker: %s", msg[g].c_str());
   return 0;
 }
 

@@ -75,6 +75,9 @@ def load_library():
     L.lmpc_gpu_get_ldp.argtypes = [vp] * 9
     L.lmpc_gpu_get_info.argtypes = [vp, vp, vp, vp]
     L.lmpc_gpu_solve_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_create_multi.argtypes = [C.POINTER(_Problem), C.POINTER(_Settings), vp, i32, C.POINTER(vp)]
+    L.lmpc_gpu_destroy_multi.argtypes = [vp]
+    L.lmpc_gpu_solve_batch_multi.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     L.lmpc_gpu_solve_batch_async.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.lmpc_gpu_compute_control_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.lmpc_gpu_simulate_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i64,
@@ -97,6 +100,35 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise LmpcError(rc, lib().lmpc_gpu_last_error().decode())
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.p = lib().lmpc_gpu_host_alloc(max(nbytes, 8))
+        if not self.p:
+            raise LmpcError(-102, lib().lmpc_gpu_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            lib().lmpc_gpu_host_free(self.p)
+            self.p = None
+
+
+def pinned_empty(shape, dtype=np.float64, order="C"):
+    """numpy array in page-locked host memory (lmpc_gpu_host_alloc): the library DMAs such arrays
+    in place; ordinary (pageable) arrays are staged through an internal pinned ring."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    own = _Pinned(n * dtype.itemsize)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(own.p)
+    a = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order=order)
+    _PIN_OWNERS[id(buf)] = own
+    import weakref
+    weakref.finalize(buf, _PIN_OWNERS.pop, id(buf), None)
+    return a
+
+
+_PIN_OWNERS = {}
 
 
 def device_count():
@@ -184,10 +216,9 @@ class GpuMPC:
     column-major, as Julia would.
     """
 
-    def __init__(self, H, f, f_theta, A, bu, bl, W, senses, nu, nx=None, K=None,
-                 soft_weight=1e6, has_binaries=False, is_symmetric=True, n_break_points=0,
-                 device=0, settings=None, dims=None):
-        L = lib()
+    def _pack(self, H, f, f_theta, A, bu, bl, W, senses, nu, nx, K, soft_weight, has_binaries,
+              is_symmetric, n_break_points, dims):
+        """numpy mpQP -> lmpc_problem (column-major views kept alive on self)."""
         F = lambda x, shape=None: np.asfortranarray(np.asarray(x, np.float64).reshape(shape) if shape else np.asarray(x, np.float64))
         H = F(H)
         n = H.shape[0]
@@ -212,6 +243,15 @@ class GpuMPC:
                      _ptr(A) if A.size else None, _ptr(bu), _ptr(bl), _ptr(W) if W.size else None,
                      _ptr(senses), _ptr(Kc), float(soft_weight), int(has_binaries),
                      int(is_symmetric), int(n_break_points))
+        return p
+
+    def __init__(self, H, f, f_theta, A, bu, bl, W, senses, nu, nx=None, K=None,
+                 soft_weight=1e6, has_binaries=False, is_symmetric=True, n_break_points=0,
+                 device=0, settings=None, dims=None):
+        L = lib()
+        p = self._pack(H, f, f_theta, A, bu, bl, W, senses, nu, nx, K, soft_weight, has_binaries,
+                       is_symmetric, n_break_points, dims)
+        m = self.m
         st = settings if settings is not None else default_settings()
         self._h = C.c_void_p()
         _check(L.lmpc_gpu_create(C.byref(p), C.byref(st), device, C.byref(self._h)))
@@ -371,17 +411,63 @@ class GpuMPC:
         return dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj, exitflag=flag, iters=iters)
 
 
-def setup_gpu(mpqp, nu, dims=None, K=None, soft_weight=1e6, device=0, settings=None, **kw):
+def setup_gpu(mpqp, nu, dims=None, K=None, soft_weight=1e6, device=0, settings=None, devices=None,
+              **kw):
     """`setup_gpu!(mpc)`: build the device-resident backend from an MPQP-like object with
-    fields H, f, f_theta, A, bu, bl, W, senses (types.jl:75-98)."""
+    fields H, f, f_theta, A, bu, bl, W, senses (types.jl:75-98).  `devices=[...]` builds the
+    single-process multi-GPU variant (host batches only)."""
     g = lambda k, default=None: getattr(mpqp, k, default) if not isinstance(mpqp, dict) else mpqp.get(k, default)
     nx = dims[0] if dims is not None else kw.pop("nx", None)
-    return GpuMPC(g("H"), g("f"), g("f_theta"), g("A"), g("bu"), g("bl"), g("W"), g("senses"),
-                  nu=nu, nx=nx, K=K, soft_weight=soft_weight,
+    common = dict(nu=nu, nx=nx, K=K, soft_weight=soft_weight,
                   has_binaries=bool(g("has_binaries", False)),
                   is_symmetric=bool(g("is_symmetric", True)),
-                  n_break_points=len(g("break_points", ()) or ()),
-                  device=device, settings=settings, dims=dims)
+                  n_break_points=len(g("break_points", ()) or ()), settings=settings, dims=dims)
+    args = (g("H"), g("f"), g("f_theta"), g("A"), g("bu"), g("bl"), g("W"), g("senses"))
+    if devices is not None:
+        return MultiGpuMPC(*args, devices=devices, **common)
+    return GpuMPC(*args, device=device, **common)
+
+
+class MultiGpuMPC(GpuMPC):
+    """One process, several GPUs: a replica of the controller on every listed device; `solve`
+    splits a HOST batch into contiguous theta ranges, one per GPU, with no inter-GPU traffic
+    (include/lmpc_gpu.h: lmpc_gpu_create_multi / lmpc_gpu_solve_batch_multi)."""
+
+    def __init__(self, H, f, f_theta, A, bu, bl, W, senses, nu, nx=None, K=None,
+                 soft_weight=1e6, has_binaries=False, is_symmetric=True, n_break_points=0,
+                 devices=None, settings=None, dims=None):
+        L = lib()
+        p = self._pack(H, f, f_theta, A, bu, bl, W, senses, nu, nx, K, soft_weight, has_binaries,
+                       is_symmetric, n_break_points, dims)
+        st = settings if settings is not None else default_settings()
+        devices = list(range(device_count())) if devices is None else list(devices)
+        dv = np.ascontiguousarray(devices, np.int32)
+        self._h = None
+        self._mh = C.c_void_p()
+        _check(L.lmpc_gpu_create_multi(C.byref(p), C.byref(st), _ptr(dv), len(devices),
+                                       C.byref(self._mh)))
+        self.devices = devices
+        self.uprev = np.zeros(self.nu)
+
+    def solve(self, Theta, want_iters=True, want_active=True):
+        words = (self.m + 63) // 64
+        Th = _colmajor(Theta, self.nth)
+        N = Th.shape[1]
+        U = np.zeros((self.nu, N), order="F")
+        flag = np.zeros(N, np.int32)
+        iters = np.zeros(N, np.int32) if want_iters else None
+        au = np.zeros((N, words), np.uint64) if want_active else None
+        al = np.zeros((N, words), np.uint64) if want_active else None
+        _check(lib().lmpc_gpu_solve_batch_multi(self._mh, _ptr(Th), N, _ptr(U), _ptr(flag),
+                                                _ptr(iters), _ptr(au), _ptr(al)))
+        return dict(U=U, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
+
+    def close(self):
+        if getattr(self, "_mh", None):
+            lib().lmpc_gpu_destroy_multi(self._mh)
+            self._mh = None
+
+    __del__ = close
 
 
 class GpuExplicitMPC:
@@ -585,12 +671,14 @@ class MPC:
         self.mpqp = out
         return out
 
-    def setup(self, device=0, settings=None):
-        """setup!(mpc) + setup_gpu!(mpc): condense, then Cholesky / normalisation / upload."""
+    def setup(self, device=0, settings=None, devices=None):
+        """setup!(mpc) + setup_gpu!(mpc): condense, then Cholesky / normalisation / upload
+        (`devices=[...]`: one replica per listed GPU, host batches split by contiguous ranges)."""
         q = self.condense()
-        self.gpu = GpuMPC(q["H"], q["f"], q["f_theta"], q["A"], q["bu"], q["bl"], q["W"], q["senses"],
-                          nu=self.nu, nx=self.nx, soft_weight=self.soft_weight, device=device,
-                          settings=settings, dims=q["dims"])
+        args = (q["H"], q["f"], q["f_theta"], q["A"], q["bu"], q["bl"], q["W"], q["senses"])
+        kw = dict(nu=self.nu, nx=self.nx, soft_weight=self.soft_weight, settings=settings, dims=q["dims"])
+        self.gpu = (MultiGpuMPC(*args, devices=devices, **kw) if devices is not None
+                    else GpuMPC(*args, device=device, **kw))
         return self.gpu
 
     def _g(self):

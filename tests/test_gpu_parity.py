@@ -233,3 +233,40 @@ def test_native_library_is_what_ran(lmpc):
     assert lmpc.launch_count() > before
     with open("/proc/self/maps") as f:
         assert "liblmpcgpu.so" in f.read()
+
+
+@pytest.mark.parametrize("name,N", [("invpend", 100003), ("aircraft", 2001), ("invpend", 1)])
+def test_single_process_multi_device_handle(lmpc, name, N):
+    """lmpc_gpu_solve_batch_multi: contiguous theta ranges over every visible GPU (one GPU on the
+    round-end box: the range logic still runs, with the same device listed twice)."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    nd = lmpc.device_count()
+    devices = list(range(nd)) if nd > 1 else [0, 0]
+    mg = lmpc.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight, devices=devices)
+    lo, hi = util.theta_range(name, 1.0)
+    Th = mpqp.sample_theta(lo, hi, N, seed=5)
+    assert_parity(mg.solve(Th), P.solve_batch(Th))
+    mg.close()
+
+
+@pytest.mark.parametrize("N", [5, 300000, 1200007])
+def test_pinned_and_pageable_host_buffers_agree(lmpc, N):
+    """Pinned caller arrays are DMA'd in place, pageable ones go through the pinned ring
+    (several stages at the larger sizes): same bits either way."""
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    lo, hi = mpqp.invpend_range(1.0)
+    Th = np.asfortranarray(mpqp.sample_theta(lo, hi, N, seed=21))
+    a = g.solve(Th)
+    Tp = lmpc.pinned_empty(Th.shape, order="F")
+    Tp[...] = Th
+    words = (g.m + 63) // 64
+    U = lmpc.pinned_empty((g.nu, N), order="F"); fl = lmpc.pinned_empty(N, np.int32)
+    it = lmpc.pinned_empty(N, np.int32)
+    au = lmpc.pinned_empty((N, words), np.uint64); al = lmpc.pinned_empty((N, words), np.uint64)
+    rc = lmpc.lib().lmpc_gpu_solve_batch(g._h, Tp.ctypes.data, N, U.ctypes.data, fl.ctypes.data,
+                                         it.ctypes.data, au.ctypes.data, al.ctypes.data)
+    assert rc == 0, lmpc.lib().lmpc_gpu_last_error()
+    assert np.array_equal(a["U"], U) and np.array_equal(a["exitflag"], fl) and np.array_equal(a["iters"], it)
+    assert np.array_equal(a["active_upper"], au) and np.array_equal(a["active_lower"], al)
+    if N <= 300000:
+        assert_parity(a, P.solve_batch(Th))
