@@ -25,6 +25,7 @@ mutable struct GpuMPC
     handle::Ptr{Cvoid}
     mpc::LinearMPC.MPC
     nth::Int; nu::Int; m::Int
+    multi::Bool            # handle is an lmpc_multi (one replica per device, host batches only)
 end
 
 lasterror() = unsafe_string(ccall((:lmpc_gpu_last_error, liblmpcgpu), Cstring, ()))
@@ -36,7 +37,7 @@ check(rc) = rc == 0 || error("liblmpcgpu error $rc: $(lasterror())")
 Uploads the condensed problem once (what `DAQP.setup` + `qp2ldp` do on the host,
 src/setup.jl:11-13, src/codegen.jl:239-280).  Refuses hybrid / AVI / hierarchical problems.
 """
-function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0)
+function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0, devices=nothing)
     mpc.mpqp_issetup || LinearMPC.setup!(mpc)
     q = mpc.mpQP
     n, m = size(q.H, 1), length(q.bu)
@@ -49,11 +50,21 @@ function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0)
                         isempty(q.A) ? C_NULL : pointer(q.A), pointer(q.bu), pointer(q.bl),
                         pointer(q.W), pointer(q.senses), K, mpc.settings.soft_weight,
                         q.has_binaries, q.is_symmetric, length(q.break_points))
-        check(ccall((:lmpc_gpu_create, liblmpcgpu), Cint,
-                    (Ref{LmpcProblem}, Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), p, C_NULL, device, h))
+        if isnothing(devices)
+            check(ccall((:lmpc_gpu_create, liblmpcgpu), Cint,
+                        (Ref{LmpcProblem}, Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), p, C_NULL, device, h))
+        else    # one process, several GPUs: contiguous theta ranges, no inter-GPU traffic
+            dv = Int32.(collect(devices))
+            check(ccall((:lmpc_gpu_create_multi, liblmpcgpu), Cint,
+                        (Ref{LmpcProblem}, Ptr{Cvoid}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                        p, C_NULL, dv, length(dv), h))
+        end
     end
-    g = GpuMPC(h[], mpc, nth, mpc.model.nu, m)
-    finalizer(x -> ccall((:lmpc_gpu_destroy, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle), g)
+    g = GpuMPC(h[], mpc, nth, mpc.model.nu, m, !isnothing(devices))
+    finalizer(g) do x
+        x.multi ? ccall((:lmpc_gpu_destroy_multi, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle) :
+                  ccall((:lmpc_gpu_destroy, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle)
+    end
     return g
 end
 
@@ -63,9 +74,15 @@ end
 function solve(g::GpuMPC, Θ::Matrix{Float64})
     N = size(Θ, 2)
     U = Matrix{Float64}(undef, g.nu, N); flag = Vector{Int32}(undef, N); it = Vector{Int32}(undef, N)
-    check(ccall((:lmpc_gpu_solve_batch, liblmpcgpu), Cint,
-                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt64}, Ptr{UInt64}),
-                g.handle, Θ, N, U, flag, it, C_NULL, C_NULL))
+    if g.multi
+        check(ccall((:lmpc_gpu_solve_batch_multi, liblmpcgpu), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt64}, Ptr{UInt64}),
+                    g.handle, Θ, N, U, flag, it, C_NULL, C_NULL))
+    else
+        check(ccall((:lmpc_gpu_solve_batch, liblmpcgpu), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt64}, Ptr{UInt64}),
+                    g.handle, Θ, N, U, flag, it, C_NULL, C_NULL))
+    end
     return U, flag, it
 end
 
@@ -94,6 +111,7 @@ N_traj independent copies of the `Simulation` loop (src/simulation.jl:93-113) wi
 linear dynamics (src/model.jl:70), N steps each, entirely on the GPU.
 """
 function simulate(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integer=100, warm_start::Bool=true)
+    g.multi && error("simulate: build the backend with a single `device` (closed loops are per-GPU)")
     mdl = g.mpc.model
     nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
     M = size(X0, 2)
