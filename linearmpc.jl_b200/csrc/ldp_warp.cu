@@ -2,15 +2,17 @@
 // m <= 64).  The configuration north_star names for the AFTI-16 controller (n = 20, m = 22).
 //
 // Mapping.  One warp owns one QP at a time and loops over its share of the batch.
-//   * working-set position i  -> lane i : D_i, 1/D_i, lambda_i, lambda*_i, d_W,i, row id, L slot
+//   * working-set position i  -> lane i : D_i, 1/D_i, lambda_i, lambda*_i, d_W,i, row id
 //   * decision variable c     -> lane c : u_c
 //   * constraint row j        -> lane j mod 32 (two rows per lane when m > 32): shift sh_j
 // The unit-lower factor L lives in the warp's shared-memory tile as a square array indexed by
-// PHYSICAL SLOT (odd leading dimension: column reads and row reads are both conflict free).
-// A position -> slot indirection held in registers means removing a row never moves data:
-// lanes above the removed position shift their registers down by one (__shfl_down) and the
-// slot is returned to a free mask.  Triangular solves are column sweeps: one shuffle
-// broadcast + one fma per step.  Slack argmin, ratio-test argmin and the three cross-lane
+// POSITION (odd leading dimension: column reads and row reads are both conflict free), so a
+// sweep step addresses it with the loop counter alone.  Removing a row shifts the lanes above
+// it down by one (__shfl_down); the trailing block of L is rewritten by the rank-1 update
+// anyway, which stores it one row / column up, and only the r columns left of the removed
+// position are moved explicitly.  (r01 used a position -> physical-slot indirection instead:
+// no data moved on removal, but every sweep step paid a shuffle and an address multiply for it.)
+// Triangular solves are column sweeps: one shuffle broadcast + one fma per step.  Slack argmin, ratio-test argmin and the three cross-lane
 // sums (pivot, dual objective, output map) are warp reductions; the sums use the canonical
 // butterfly order shared with the oracle, so results stay bit-identical to
 // oracle/ldp_oracle.c and to the thread-per-QP kernel.
@@ -30,6 +32,12 @@ constexpr int K2_BLOCK = K2_WARPS * 32;
 #ifndef K2_MINB
 #define K2_MINB 3
 #endif
+// Unroll factor of the sweep / gather loops, per kernel (measured on AFTI-16, r01): single solves
+// run ~40 iterations per QP and like 4 (1.36e7 vs 1.31e7 / 1.19e7 solves/s at 2 / 1); the closed
+// loop runs ~2 iterations per warm-started solve, is instruction-fetch bound, and likes 2
+// (3.35e8 vs 2.95e8 solves/s at 4).
+constexpr int K2_UF_SOLVE = 4;
+constexpr int K2_UF_SIM = 2;
 constexpr unsigned FULL = 0xffffffffu;
 
 LMPC_DEVINL double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -61,12 +69,11 @@ LMPC_DEVINL double bfly_max(double v) {
 struct WarpQp {
   // per lane (position = lane)
   double D, Dinv, lam, lams, dW;
-  int row, slot;
+  int row;
   bool low, imm, soft;
   // warp-uniform
   int k;
   bool sing;
-  unsigned used;              // physical L slots in use
   unsigned long long inws;    // rows in the working set
 };
 
@@ -74,7 +81,7 @@ struct WarpCtx {
   ConstView cv;
   const LdpLayout *lay;
   const LdpSettings *st;
-  double *Lw;      // cap x LS tile, indexed [slot_row * LS + slot_col]
+  double *Lw;      // cap x LS tile, indexed [position_row * LS + position_col]
   double *uw;      // n: primal iterate, broadcast source for the slack scan
   double *thw;     // nth: theta
   int LS;
@@ -82,29 +89,31 @@ struct WarpCtx {
 };
 
 LMPC_DEVINL void wq_reset(WarpQp &s) {
-  s.D = 1.0; s.Dinv = 1.0; s.lam = 0.0; s.lams = 0.0; s.dW = 0.0; s.row = 0; s.slot = 0;
+  s.D = 1.0; s.Dinv = 1.0; s.lam = 0.0; s.lams = 0.0; s.dW = 0.0; s.row = 0;
   s.low = false; s.imm = false; s.soft = false;
-  s.k = 0; s.sing = false; s.used = 0u; s.inws = 0ull;
+  s.k = 0; s.sing = false; s.inws = 0ull;
 }
 
 // column sweep: z <- L^-1 z on positions [0, kk)
+template <int UF>
 LMPC_DEVINL double sweep_fwd(const WarpCtx &c, const WarpQp &s, double z, int kk) {
-  const double *lrow = c.Lw + s.slot * c.LS;
-#pragma unroll 4
+  const bool mine = c.lane < kk;
+  const double *lrow = c.Lw + (mine ? c.lane : 0) * c.LS;   // idle lanes re-read row 0 (in bounds)
+#pragma unroll UF
   for (int j = 0; j + 1 < kk; ++j) {
-    const int sj = __shfl_sync(FULL, s.slot, j);
-    const double lij = lrow[sj];
+    const double lij = lrow[j];
     const double zj = shfl_d(z, j);
-    if (c.lane > j && c.lane < kk) z = fma(-lij, zj, z);
+    if (mine && c.lane > j) z = fma(-lij, zj, z);
   }
   return z;
 }
 // column sweep: x <- L^-T x on positions [0, kk), descending (the oracle's axpy order)
+template <int UF>
 LMPC_DEVINL double sweep_bwd(const WarpCtx &c, const WarpQp &s, double x, int kk) {
-#pragma unroll 4
+  const double *lcol = c.Lw + (c.lane < kk ? c.lane : 0);
+#pragma unroll UF
   for (int j = kk - 1; j > 0; --j) {
-    const int sj = __shfl_sync(FULL, s.slot, j);
-    const double lji = c.Lw[sj * c.LS + s.slot];
+    const double lji = lcol[j * c.LS];
     const double xj = shfl_d(x, j);
     if (c.lane < j) x = fma(-lji, xj, x);
   }
@@ -112,6 +121,7 @@ LMPC_DEVINL double sweep_bwd(const WarpCtx &c, const WarpQp &s, double x, int kk
 }
 
 // append row j (oracle: ldl_add)
+template <int UF>
 LMPC_DEVINL void wq_add(const WarpCtx &c, WarpQp &s, int j, bool lower, double dval) {
   const int m = c.lay->m, k = s.k, lane = c.lane;
   const double *g = c.cv.G + j * m;
@@ -119,54 +129,57 @@ LMPC_DEVINL void wq_add(const WarpCtx &c, WarpQp &s, int j, bool lower, double d
   double dnew = g[j];
   if (sj & S_SOFT) dnew += c.st->rho_soft;
   double y = (lane < k) ? g[s.row] : 0.0;
-  y = sweep_fwd(c, s, y, k);
+  y = sweep_fwd<UF>(c, s, y, k);
   const double l = (lane < k) ? y * s.Dinv : 0.0;
   dnew = __dsub_rn(dnew, bfly_sum(__dmul_rn(y, l)));
   const bool sing = dnew < c.st->zero_tol;
   if (sing) dnew = 0.0;
   const double dinv = sing ? 0.0 : 1.0 / dnew;
-  const int ns = __ffs(~s.used) - 1;         // free physical slot
-  __syncwarp();                              // idle lanes may still be reading stale slots in the sweep
-  if (lane < k) c.Lw[ns * c.LS + s.slot] = l;
+  __syncwarp();                              // idle lanes may still be reading row k in the sweep
+  if (lane < k) c.Lw[k * c.LS + lane] = l;
   if (lane == k) {
-    s.D = dnew; s.Dinv = dinv; s.lam = 0.0; s.dW = dval; s.row = j; s.slot = ns;
+    s.D = dnew; s.Dinv = dinv; s.lam = 0.0; s.dW = dval; s.row = j;
     s.low = lower; s.imm = (sj & S_IMMUTABLE) != 0; s.soft = (sj & S_SOFT) != 0;
   }
-  s.used |= 1u << ns;
   s.inws |= 1ull << j;
   s.sing = sing;
   s.k = k + 1;
   __syncwarp();
 }
 
-// delete position r (oracle: ldl_remove); no data moves, positions above r shift down a lane
+// delete position r (oracle: ldl_remove): positions above r move down a lane, L moves up a row
+// and (right of r) a column while the rank-1 update rewrites it
 LMPC_DEVINL void wq_remove(const WarpCtx &c, WarpQp &s, int r) {
-  const int lane = c.lane;
+  const int lane = c.lane, LS = c.LS;
   int k = s.k;
   double alpha = shfl_d(s.D, r);
-  const int rslot = __shfl_sync(FULL, s.slot, r);
   const int rrow = __shfl_sync(FULL, s.row, r);
   // column r below the diagonal, still at old positions
-  double wv = (lane > r && lane < k) ? c.Lw[s.slot * c.LS + rslot] : 0.0;
+  double wv = (lane > r && lane < k) ? c.Lw[lane * LS + r] : 0.0;
   s.inws &= ~(1ull << rrow);
-  s.used &= ~(1u << rslot);
   // positions p >= r take position p+1
   {
     const double D = shfl_down_d(s.D, 1), Dinv = shfl_down_d(s.Dinv, 1), lam = shfl_down_d(s.lam, 1);
     const double dW = shfl_down_d(s.dW, 1), w2 = shfl_down_d(wv, 1);
-    const int row = __shfl_down_sync(FULL, s.row, 1), slot = __shfl_down_sync(FULL, s.slot, 1);
+    const int row = __shfl_down_sync(FULL, s.row, 1);
     const unsigned fl = __shfl_down_sync(FULL, (unsigned)s.low | ((unsigned)s.imm << 1) | ((unsigned)s.soft << 2), 1);
     if (lane >= r && lane + 1 < k) {
-      s.D = D; s.Dinv = Dinv; s.lam = lam; s.dW = dW; s.row = row; s.slot = slot; wv = w2;
+      s.D = D; s.Dinv = Dinv; s.lam = lam; s.dW = dW; s.row = row; wv = w2;
       s.low = fl & 1u; s.imm = (fl >> 1) & 1u; s.soft = (fl >> 2) & 1u;
     }
   }
   k -= 1;
+  const bool below = lane >= r && lane < k;    // new positions whose row came from old row lane + 1
+  // columns left of r: same values, one row up (all lanes read, then all lanes write)
+  for (int cc = 0; cc < r; ++cc) {
+    const double v = below ? c.Lw[(lane + 1) * LS + cc] : 0.0;
+    __syncwarp();
+    if (below) c.Lw[lane * LS + cc] = v;
+  }
   bool sing = false;
   for (int j = r; j < k; ++j) {
     const double pj = shfl_d(wv, j);
     const double Dj = shfl_d(s.D, j);
-    const int sj = __shfl_sync(FULL, s.slot, j);
     const double t = alpha * pj;
     double dbar = fma(t, pj, Dj);
     double rinv = 1.0 / dbar;
@@ -174,11 +187,13 @@ LMPC_DEVINL void wq_remove(const WarpCtx &c, WarpQp &s, int r) {
     alpha = (Dj * alpha) * rinv;
     if (j == k - 1 && !(dbar >= c.st->zero_tol)) { sing = true; dbar = 0.0; rinv = 0.0; }
     if (lane == j) { s.D = dbar; s.Dinv = rinv; }
-    if (lane > j && lane < k) {
-      double *lp = c.Lw + s.slot * c.LS + sj;
-      const double lij = *lp;
+    // new L[i][j] from old L[i+1][j+1]; old column j was consumed one step ago
+    const bool upd = lane > j && lane < k;
+    const double lij = upd ? c.Lw[(lane + 1) * LS + j + 1] : 0.0;
+    __syncwarp();
+    if (upd) {
       wv = fma(-pj, lij, wv);
-      *lp = fma(beta, wv, lij);
+      c.Lw[lane * LS + j] = fma(beta, wv, lij);
     }
   }
   s.k = k;
@@ -194,6 +209,7 @@ LMPC_DEVINL int argmin_first(double a, double &amin) {
 }
 
 // The dual active-set loop for one QP (oracle: ldp_loop).  sh0/sh1: shifts of rows lane, lane+32.
+template <int UF>
 LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, double &u, int &iters) {
   const LdpLayout &lay = *c.lay;
   const LdpSettings &st = *c.st;
@@ -202,19 +218,20 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
   double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
   for (iter = 1; iter < st.iter_limit; ++iter) {
     const int k = s.k;
-    double a = CUDART_INF;
+    double a = CUDART_INF, dir = 0.0;
+    int noblock = EXIT_CYCLE;
     if (!s.sing) {
       // 1. CSP: L D L' lam* = -d_W
       double z = (lane < k) ? -s.dW : 0.0;
-      z = sweep_fwd(c, s, z, k);
+      z = sweep_fwd<UF>(c, s, z, k);
       s.lams = (lane < k) ? z * s.Dinv : 0.0;
-      s.lams = sweep_bwd(c, s, s.lams, k);
+      s.lams = sweep_bwd<UF>(c, s, s.lams, k);
       // 2. blocking set + ratio test
       const bool blk = lane < k && !s.imm && (s.low ? (s.lams > st.dual_tol) : (s.lams < -st.dual_tol));
       if (!__any_sync(FULL, blk)) {
         // 3. primal iterate u = -M_W' lam*
         double uc = 0.0;
-#pragma unroll 4
+#pragma unroll UF
         for (int i = 0; i < k; ++i) {
           const double li = shfl_d(s.lams, i);
           const int ri = __shfl_sync(FULL, s.row, i);
@@ -235,12 +252,12 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         double best = CUDART_INF, bestd = 0.0;
         int bestj = -1;
         bool bestlow = false;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < (m > 32 ? 2 : 1); ++half) {
           const int j = lane + 32 * half;
           if (j < m) {
             double mu = 0.0;
-#pragma unroll 4
+#pragma unroll UF
             for (int cc = 0; cc < n; ++cc) mu = fma(c.cv.MT[cc * mp + j], c.uw[cc], mu);
             const bool skip = ((s.inws >> j) & 1ull) || (c.cv.sense[j] & S_IMMUTABLE);
             const double shj = half ? sh1 : sh0;
@@ -269,26 +286,21 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         const bool addlow = __shfl_sync(FULL, (int)bestlow, src);
         const double addd = shfl_d(bestd, src);
         if (lane < k) s.lam = s.lams;
-        wq_add(c, s, add, addlow, addd);
+        wq_add<UF>(c, s, add, addlow, addd);
         continue;
       }
-      // 4. blocking: ratio test, step, remove
+      // 4. blocking: ratio test against lam* - lam
       if (blk) {
         a = -s.lam / (s.lams - s.lam);
         if (!(a == a)) a = CUDART_INF;
       }
-      double alpha;
-      const int rm = argmin_first(a, alpha);
-      if (rm < 0) { flag = EXIT_CYCLE; break; }   // blocked but no finite ratio (NaN guard)
-      if (lane < k) s.lam = fma(alpha, s.lams - s.lam, s.lam);
-      wq_remove(c, s, rm);
+      dir = s.lams - s.lam;
     } else {
       // 5. singular: p = side * [-L^-T l ; 1] on the first k-1 positions
       const int kk = k - 1;
-      const int kslot = __shfl_sync(FULL, s.slot, kk);
       const bool lastlow = __shfl_sync(FULL, (int)s.low, kk);
-      double p = (lane < kk) ? -c.Lw[kslot * c.LS + s.slot] : 0.0;
-      p = sweep_bwd(c, s, p, kk);
+      double p = (lane < kk) ? -c.Lw[kk * c.LS + lane] : 0.0;
+      p = sweep_bwd<UF>(c, s, p, kk);
       if (lane == kk) p = 1.0;
       if (lastlow && lane <= kk) p = -p;
       s.lams = (lane < k) ? p : 0.0;
@@ -297,18 +309,22 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         a = -s.lam / p;
         if (!(a == a)) a = CUDART_INF;
       }
-      double alpha;
-      const int rm = argmin_first(a, alpha);
-      if (rm < 0) { flag = EXIT_INFEASIBLE; break; }
-      if (lane < k) s.lam = fma(alpha, p, s.lam);
-      wq_remove(c, s, rm);
+      dir = p;
+      noblock = EXIT_INFEASIBLE;
     }
+    // step to the first blocking multiplier and drop its row (one site for both branches)
+    double alpha;
+    const int rm = argmin_first(a, alpha);
+    if (rm < 0) { flag = noblock; break; }   // regular: blocked but no finite ratio (NaN guard)
+    if (lane < k) s.lam = fma(alpha, dir, s.lam);
+    wq_remove(c, s, rm);
   }
   iters = iter;
   return flag;
 }
 
 // one solve for theta in c.thw; returns the flag; u (lane c holds u_c) and iters by reference
+template <int UF>
 LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
@@ -332,7 +348,7 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
         if (s.k >= lay.cap || s.k >= 32) { flag = EXIT_OVERDETERMINED; break; }
         const bool low = sj & S_LOWER;
         const double shj = shfl_d(j < 32 ? sh0 : sh1, j & 31);
-        wq_add(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
+        wq_add<UF>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
         if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
       }
     }
@@ -343,7 +359,7 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
     if (lane < s.k) s.dW = (s.low ? c.cv.dl[j] : c.cv.du[j]) + (j < 32 ? shj_lo : shj_hi);
   }
   iters = 0;
-  if (flag == 0) flag = wq_loop(c, s, sh0, sh1, u, iters);
+  if (flag == 0) flag = wq_loop<UF>(c, s, sh0, sh1, u, iters);
   return flag;
 }
 
@@ -390,13 +406,14 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
     for (int sg = 0; sg < 4; ++sg) {
       if (sg < th.nseg) {
         const int len = th.len[sg];
+#pragma unroll 1
         for (int t = lane; t < len; t += 32) c.thw[o + t] = ld_stream(th.ptr[sg] + q * th.stride[sg] + t);
         o += len;
       }
     }
     __syncwarp();
     int iters;
-    const int flag = wq_solve(c, s, true, u, iters);
+    const int flag = wq_solve<K2_UF_SOLVE>(c, s, true, u, iters);
     for (int i = 0; i < lay.nu; ++i) {
       const double ctl = control_out_w(c, i, u);
       if (lane == 0) out.U[q * lay.nu + i] = ctl;
@@ -446,7 +463,7 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
       for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
       __syncwarp();
       int iters;
-      const int f = wq_solve(c, s, !(sd.warm && t > 0), u, iters);
+      const int f = wq_solve<K2_UF_SIM>(c, s, !(sd.warm && t > 0), u, iters);
       tot += iters;
       if (f < 0) { if (worst > 0 || f < worst) worst = f; }
       else if (worst > 0 && f > worst) worst = f;

@@ -49,7 +49,8 @@ class _Settings(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "liblmpcgpu.so")
+    """In-tree library; LMPC_GPU_LIB names another build of the same sources (A/B measurements)."""
+    return os.environ.get("LMPC_GPU_LIB") or os.path.join(_HERE, "liblmpcgpu.so")
 
 
 def load_library():
