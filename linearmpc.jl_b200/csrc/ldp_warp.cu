@@ -171,12 +171,14 @@ LMPC_DEVINL void wq_remove(const WarpCtx &c, WarpQp &s, int r) {
   k -= 1;
   const bool below = lane >= r && lane < k;    // new positions whose row came from old row lane + 1
   // columns left of r: same values, one row up (all lanes read, then all lanes write)
+#pragma unroll 1
   for (int cc = 0; cc < r; ++cc) {
     const double v = below ? c.Lw[(lane + 1) * LS + cc] : 0.0;
     __syncwarp();
     if (below) c.Lw[lane * LS + cc] = v;
   }
   bool sing = false;
+#pragma unroll 1
   for (int j = r; j < k; ++j) {
     const double pj = shfl_d(wv, j);
     const double Dj = shfl_d(s.D, j);
@@ -324,7 +326,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
 }
 
 // one solve for theta in c.thw; returns the flag; u (lane c holds u_c) and iters by reference
-template <int UF>
+template <int UF, bool EQ>
 LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
@@ -332,17 +334,21 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
   double sh0 = 0.0, sh1 = 0.0;
   if (lane < m) {
     const double *dr = c.cv.Dth + lane * nth;
+#pragma unroll 2
     for (int t = 0; t < nth; ++t) sh0 = fma(dr[t], c.thw[t], sh0);
   }
   if (lane + 32 < m) {
     const double *dr = c.cv.Dth + (lane + 32) * nth;
+#pragma unroll 2
     for (int t = 0; t < nth; ++t) sh1 = fma(dr[t], c.thw[t], sh1);
   }
   int flag = 0;
   if (cold) {
     wq_reset(s);
     u = 0.0;
-    for (int j = 0; lay.neq > 0 && j < m; ++j) {
+    // equality rows enter the working set before the first iteration; controllers without any
+    // (EQ == false) are compiled without this second copy of the add
+    for (int j = 0; EQ && j < m; ++j) {
       const int sj = c.cv.sense[j];
       if (sj & S_ACTIVE) {
         if (s.k >= lay.cap || s.k >= 32) { flag = EXIT_OVERDETERMINED; break; }
@@ -369,6 +375,7 @@ LMPC_DEVINL double control_out_w(const WarpCtx &c, int i, double u) {
   const double x = bfly_sum(c.lane < lay.n ? __dmul_rn(c.cv.Rinv[i * lay.n + c.lane], u) : 0.0);
   double sh = c.cv.uoff[i];
   const double *ur = c.cv.Uth + i * lay.nth;
+#pragma unroll 2
   for (int t = 0; t < lay.nth; ++t) sh = fma(ur[t], c.thw[t], sh);
   return __dadd_rn(x, sh);
 }
@@ -386,6 +393,7 @@ LMPC_DEVINL WarpCtx make_ctx(double *smem, const LdpLayout &lay, const LdpSettin
   return c;
 }
 
+template <bool EQ>
 __global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                 const double *__restrict__ cblk, ThetaSegs th,
@@ -413,7 +421,7 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
     }
     __syncwarp();
     int iters;
-    const int flag = wq_solve<K2_UF_SOLVE>(c, s, true, u, iters);
+    const int flag = wq_solve<K2_UF_SOLVE, EQ>(c, s, true, u, iters);
     for (int i = 0; i < lay.nu; ++i) {
       const double ctl = control_out_w(c, i, u);
       if (lane == 0) out.U[q * lay.nu + i] = ctl;
@@ -436,6 +444,7 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
 }
 
 // closed loop: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
+template <bool EQ>
 __global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                     const double *__restrict__ cblk,
@@ -453,17 +462,22 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
   WarpQp s;
   double u = 0.0;
   for (int64_t q = wid; q < Ninst; q += wstride) {
+    _Pragma("unroll 1")
     for (int i = lane; i < nx; i += 32) c.thw[i] = ld_stream(sd.X0 + q * nx + i);
+    _Pragma("unroll 1")
     for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.R ? ld_stream(sd.R + q * nr + i) : 0.0;
+    _Pragma("unroll 1")
     for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.D ? ld_stream(sd.D + q * nd + i) : 0.0;
+    _Pragma("unroll 1")
     for (int i = lane; i < nu; i += 32) ucw[i] = (sd.U0 && i < nup) ? ld_stream(sd.U0 + q * nup + i) : 0.0;
     __syncwarp();
     int worst = EXIT_OPTIMAL, tot = 0;
     for (int t = 0; t < sd.T; ++t) {
+      _Pragma("unroll 1")
       for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
       __syncwarp();
       int iters;
-      const int f = wq_solve<K2_UF_SIM>(c, s, !(sd.warm && t > 0), u, iters);
+      const int f = wq_solve<K2_UF_SIM, EQ>(c, s, !(sd.warm && t > 0), u, iters);
       tot += iters;
       if (f < 0) { if (worst > 0 || f < worst) worst = f; }
       else if (worst > 0 && f > worst) worst = f;
@@ -475,18 +489,25 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
         }
       }
       __syncwarp();
+      _Pragma("unroll 1")
       for (int i = lane; i < nx; i += 32) {
         double acc = 0.0;
+        _Pragma("unroll 2")
         for (int cc = 0; cc < nx; ++cc) acc = fma(sd.F[i * nx + cc], c.thw[cc], acc);
+        _Pragma("unroll 2")
         for (int cc = 0; cc < nu; ++cc) acc = fma(sd.G[i * nu + cc], ucw[cc], acc);
+        _Pragma("unroll 2")
         for (int cc = 0; cc < nd; ++cc) acc = fma(sd.Gd[i * nd + cc], c.thw[nx + nr + cc], acc);
         xnw[i] = acc;
       }
       __syncwarp();
+      _Pragma("unroll 1")
       for (int i = lane; i < nx; i += 32) c.thw[i] = xnw[i];
       __syncwarp();
     }
+    _Pragma("unroll 1")
     for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = c.thw[i];
+    _Pragma("unroll 1")
     for (int i = lane; i < nu; i += 32) sd.Ulast[q * nu + i] = ucw[i];
     if (lane == 0) {
       flagout[q] = worst;
@@ -508,29 +529,38 @@ bool ldp_warp_supports(const LdpLayout &lay) {
   return lay.n >= 1 && lay.n <= 32 && lay.cap <= 32 && lay.m <= 64 && k2_smem(lay, 64) <= 200 * 1024;
 }
 
-int launch_ldp_warp(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
-                    const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
-                    int sm_count, void *stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (N <= 0) return 0;
+template <bool EQ>
+static int launch_warp_t(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                         const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                         int sm_count, cudaStream_t s) {
   const size_t smem = k2_smem(lay, sim ? sim->nx + lay.nu : 0);
   int per_sm = 0;
   int64_t blocks = (N + K2_WARPS - 1) / K2_WARPS;
   cudaError_t e;
   if (sim) {
-    e = cudaFuncSetAttribute(ldp_warp_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = ldp_warp_sim_kernel<EQ>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ldp_warp_sim_kernel, K2_BLOCK, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_BLOCK, smem);
     if (per_sm < 1) per_sm = 1;
     if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
-    ldp_warp_sim_kernel<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, N, *sim, out.flag, out.iters);
+    kern<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, N, *sim, out.flag, out.iters);
   } else {
-    e = cudaFuncSetAttribute(ldp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = ldp_warp_kernel<EQ>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ldp_warp_kernel, K2_BLOCK, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_BLOCK, smem);
     if (per_sm < 1) per_sm = 1;
     if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
-    ldp_warp_kernel<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, th, N, out);
+    kern<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, th, N, out);
   }
   return (int)cudaGetLastError();
+}
+
+int launch_ldp_warp(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                    const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                    int sm_count, void *stream) {
+  if (N <= 0) return 0;
+  return lay.neq > 0 ? launch_warp_t<true>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream)
+                     : launch_warp_t<false>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream);
 }

@@ -679,6 +679,18 @@ def double_integrator_hard(Np=4, Nc=4) -> MPC:
     return mpc
 
 
+def double_integrator_terminal_eq(Np=10, Nc=10) -> MPC:
+    """Terminal EQUALITY constraint (position at the end of the horizon pinned to 0.2: lb == ub,
+    hard) on the double integrator: the rows get sense EQUALITY = ACTIVE + IMMUTABLE
+    (mpc2mpqp.jl:868-885) and enter the working set before the first iteration."""
+    F, G = np.array([[1, 0.1], [0, 1.0]]), np.array([[0.005], [0.1]])
+    mpc = MPC(F, G, C=np.array([[1.0, 0]]), Ts=0.1, Np=Np, Nc=Nc)
+    mpc.set_objective(Q=[1.0], R=[0.1], Rr=[0.0])
+    mpc.set_input_bounds(umin=[-1.0], umax=[1.0])
+    mpc.add_constraint(Ax=np.array([[1.0, 0.0]]), lb=[0.2], ub=[0.2], ks=[Np + 1], soft=False)
+    return mpc
+
+
 def generalized_parameter_example() -> MPC:
     """runtests.jl:1250-1256: scalar integrator, linear cost (Eu p + eu)'u, parametric constraint
     u + p <= 1; known answers u = 1.0 (p = 0) and 0.25 (p = 0.75) at runtests.jl:1264-1268."""

@@ -70,7 +70,8 @@ CASES = [("invpend", 1.0, 10000), ("invpend", 0.25, 10000), ("invpend", 0.05, 10
          ("dint_hard", 1.0, 10000), ("dint_hard", 0.3, 4000), ("genparam", 1.0, 5000),
          ("aircraft", 1.0, 4000), ("aircraft", 0.25, 4000), ("aircraft_ksall", 0.25, 2000),
          ("simple", 1.0, 4000), ("simple_q1000", 0.5, 2000),
-         ("chain_small", 1.0, 2000), ("chain", 1.0, 300), ("chain", 0.25, 300)]
+         ("chain_small", 1.0, 2000), ("chain", 1.0, 300), ("chain", 0.25, 300),
+         ("dint_eq", 1.0, 4000), ("dint_eq_small", 1.0, 4000)]   # terminal equality rows
 
 
 @pytest.mark.parametrize("name,scale,N", CASES)
@@ -96,7 +97,8 @@ def test_batch_matches_golden_fixture(lmpc, fn):
     assert np.max(np.abs(out["U"][:, ok] - z["U"][:, ok]) / np.maximum(1, np.abs(z["U"][:, ok]))) < rel
 
 
-@pytest.mark.parametrize("name,kernel", [("invpend", 2), ("dint_hard", 2), ("invpend", 3), ("aircraft", 3)])
+@pytest.mark.parametrize("name,kernel", [("invpend", 2), ("dint_hard", 2), ("invpend", 3), ("aircraft", 3),
+                                         ("dint_eq_small", 2), ("dint_eq_small", 3), ("dint_eq", 3)])
 def test_every_kernel_gives_the_same_answer(lmpc, name, kernel):
     """thread- / warp- / CTA-per-QP kernels are interchangeable on problems they all support."""
     mpc, qp, g, P = gpu_controller(lmpc, name, kernel)

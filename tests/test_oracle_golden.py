@@ -100,7 +100,8 @@ def kkt_certificate(L, P, theta, act_u, act_l, rho, tol=1e-6):
         lam = np.linalg.solve(G, -dw)
         v = -Mw.T @ lam
         sgn = np.where(act_u[idx], 1.0, -1.0)
-        assert np.all(lam * sgn >= -1e-9 * (1 + np.abs(lam).max())), "dual infeasible"
+        free = (L.senses[idx] & mpqp.ACTIVE) != 0      # equality rows: multiplier of either sign
+        assert np.all((lam * sgn >= -1e-9 * (1 + np.abs(lam).max())) | free), "dual infeasible"
     else:
         v = np.zeros(L.Mbar.shape[1])
     mv = L.Mbar @ v
@@ -114,16 +115,19 @@ def kkt_certificate(L, P, theta, act_u, act_l, rho, tol=1e-6):
 # 80-bit re-solve differs from BOTH by the same amount); the others are well conditioned.
 @pytest.mark.parametrize("name,scale,rtol", [("aircraft", 0.25, 2e-5), ("simple", 1.0, 2e-6),
                                              ("chain_small", 1.0, 1e-8), ("invpend", 1.0, 1e-9),
-                                             ("genparam", 1.0, 1e-8)])
+                                             ("genparam", 1.0, 1e-8), ("dint_eq", 1.0, 1e-8),
+                                             ("dint_eq_small", 1.0, 1e-8)])
 def test_oracle_solutions_satisfy_kkt(name, scale, rtol):
     mpc, qp, L, P = make(name)
     lo, hi = util.theta_range(name, scale)
     Th = mpqp.sample_theta(lo, hi, 200, seed=7)
     out = P.solve_batch(Th)
     au, al = util.bits(out["act_u"], P.m), util.bits(out["act_l"], P.m)
-    hard = ((L.senses & mpqp.SOFT) == 0) & ((L.senses & mpqp.IMMUTABLE) == 0)
+    eq = (L.senses & mpqp.ACTIVE) != 0
+    hard = ((L.senses & mpqp.SOFT) == 0) & (((L.senses & mpqp.IMMUTABLE) == 0) | eq)
     for q in range(Th.shape[1]):
         if out["flag"][q] >= 1:
+            assert np.all((au[q] | al[q])[eq]), "an equality row left the working set"
             v = kkt_certificate(L, P, Th[:, q], au[q], al[q], L.rho_soft)
             x = L.Rinv[:mpc.nu] @ v + L.u_offset + L.Uth_offset @ Th[:, q]
             assert np.allclose(x, out["U"][:, q], rtol=rtol, atol=rtol)

@@ -27,6 +27,10 @@ def controller(name):
         return mpqp.chain_of_masses(nm=4, Np=10, Nc=10)
     if name == "dint_hard":
         return mpqp.double_integrator_hard()
+    if name == "dint_eq":
+        return mpqp.double_integrator_terminal_eq()
+    if name == "dint_eq_small":
+        return mpqp.double_integrator_terminal_eq(Np=6, Nc=6)
     if name == "genparam":
         return mpqp.generalized_parameter_example()
     if name == "simple":
@@ -49,6 +53,9 @@ def theta_range(name, scale=1.0):
         return np.array([-1.0, -1.0, -0.5]) * scale, np.array([1.0, 1.0, 1.5]) * scale
     if name == "dint_hard":
         hi = np.array([2.0, 1.0, 2.0]) * scale
+        return -hi, hi
+    if name.startswith("dint_eq"):
+        hi = np.array([0.5, 0.5, 1.0]) * scale
         return -hi, hi
     if name.startswith("simple"):
         hi = np.array([1.0, 2.0, 1.0, 1.0, 3.0]) * scale
