@@ -21,6 +21,10 @@
 namespace {
 
 constexpr int KB_BLOCK = 128;
+#ifndef KB_TH_UNROLL
+#define KB_TH_UNROLL 4
+#endif
+constexpr int KB_THU = KB_TH_UNROLL;   // unroll factor of the loop over theta
 
 template <int N>
 struct BoxState {
@@ -220,6 +224,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
       if (sg < th.nseg) {
         const int len = th.len[sg];
         const double *src = th.ptr[sg] + q * th.stride[sg];
+#pragma unroll KB_THU
         for (int t = 0; t < len; ++t) {
           const double tv = ld_stream(src + t);
           const int tt = o + t;
