@@ -284,7 +284,12 @@ static int run_kernel(lmpc_handle *h, const ThetaSegs &th, int64_t N, const Solv
                       const SimDesc *sim, cudaStream_t s) {
   int e;
   switch (h->kernel) {
-    case LMPC_KERNEL_THREAD: e = launch_ldp_thread(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s); break;
+    case LMPC_KERNEL_THREAD:
+      // box-only problems take the specialised fast path (same arithmetic, fewer instructions)
+      e = (!sim && ldp_box_supports(h->lay))
+              ? launch_ldp_box(h->lay, h->st, h->d_blk, h->h_blk, th, N, o, h->sm_count, s)
+              : launch_ldp_thread(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s);
+      break;
     case LMPC_KERNEL_WARP: e = launch_ldp_warp(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s); break;
     case LMPC_KERNEL_CTA: e = launch_ldp_cta(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s); break;
     default: return set_err(LMPC_E_INVALID, "handle has no kernel%s");

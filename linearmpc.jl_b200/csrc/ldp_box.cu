@@ -26,6 +26,29 @@ constexpr int KB_BLOCK = 128;
 #endif
 constexpr int KB_THU = KB_TH_UNROLL;   // unroll factor of the loop over theta
 
+// Constants whose index is known at compile time travel as a kernel parameter: the compiler
+// reads them straight from the constant bank as an FMA operand (no load instruction).  Rows of
+// M-bar picked by a run-time row id stay in shared memory, padded to an even stride so that a
+// row is fetched with 128-bit loads.
+template <int N, int NU>
+struct BoxConst {
+  double M[N * N];
+  double du[N], dl[N];
+  double Rinv[NU * N];
+};
+template <int N>
+struct BoxPad { static constexpr int NP = (N + 1) & ~1; };
+
+// u <- u - li * M[row, :]  (row stride NP doubles, 16-byte aligned)
+template <int N>
+LMPC_DEVINL void box_axpy_row(const double *Mp, int row, double li, double (&u)[N]) {
+  constexpr int NP = BoxPad<N>::NP;
+  const double2 *r2 = reinterpret_cast<const double2 *>(Mp + row * NP);
+  double mr[NP];
+  SFOR(h, 0, NP / 2) const double2 v = r2[h]; mr[2 * h] = v.x; mr[2 * h + 1] = v.y; SEND
+  SFOR(c, 0, N) u[c] = fma(-li, mr[c], u[c]); SEND
+}
+
 template <int N>
 struct BoxState {
   double L[N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1];
@@ -134,8 +157,9 @@ struct IterCtx {
 // rows so far).  Same operations in the same order as the generic iteration, with exact loop
 // bounds and the new row written to the static slot K.  Does nothing for threads that are done,
 // behind (iter != K + 1) or whose multipliers block.
-template <int N, int K>
-LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const LdpSettings &st,
+template <int N, int K, class BC>
+LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const BC &bc, const double *Mp,
+                                 const LdpSettings &st,
                                  const double (&dU)[N], const double (&dLo)[N], double (&u)[N], IterCtx &cx) {
   static_assert(K >= 1 && K < N, "static iterations append at slot K");
   if (cx.done || cx.iter != K + 1 || s.k != K) return;
@@ -158,10 +182,7 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const LdpS
   if (blocked) return;                     // the generic loop redoes this iteration
   SFOR(i, 0, K) s.lams[i] = lams[i]; SEND
   SFOR(c, 0, N) u[c] = 0.0; SEND
-  SFOR(i, 0, K)
-    const double *mr = cv.M + s.row[i] * N;
-    SFOR(c, 0, N) u[c] = fma(-lams[i], mr[c], u[c]); SEND
-  SEND
+  SFOR(i, 0, K) box_axpy_row<N>(Mp, s.row[i], lams[i], u); SEND
   double pu[N];
   SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
   cx.fval = tree_sum<N, 0, 1>(pu);
@@ -170,7 +191,7 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const LdpS
   int code = -1;
   SFOR(j, 0, N)
     double mu = 0.0;
-    SFOR(c, j, N) mu = fma(cv.M[j * N + c], u[c], mu); SEND
+    SFOR(c, j, N) mu = fma(bc.M[j * N + c], u[c], mu); SEND
     const bool free_row = !((s.inws >> j) & 1u);
     const double su = dU[j] - mu, sl = mu - dLo[j];
     const bool tu = free_row && (su < best);
@@ -205,12 +226,17 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const LdpS
 
 template <int N, int NU, int MINB>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
-ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, ThetaSegs th,
-               int64_t Ninst, SolveOut out) {
+ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
+               const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
   const ConstView cv = make_view(smem, lay);
+  // padded copy of M-bar for the 128-bit row gathers
+  constexpr int NP = BoxPad<N>::NP;
+  double *Mp = smem + ((lay.total + 1) & ~1);
+  for (int i = threadIdx.x; i < N * NP; i += KB_BLOCK) Mp[i] = (i % NP < N) ? cv.M[(i / NP) * N + i % NP] : 0.0;
+  __syncthreads();
   const int nth = lay.nth;
   BoxState<N> s;
   for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst;
@@ -236,7 +262,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
     SEND
     // theta-dependent bounds, once per solve (mpc_update_qp): d_u = du + sh, d_l = dl + sh
     double dU[N], dLo[N];
-    SFOR(j, 0, N) dU[j] = cv.du[j] + sh[j]; dLo[j] = cv.dl[j] + sh[j]; SEND
+    SFOR(j, 0, N) dU[j] = bc.du[j] + sh[j]; dLo[j] = bc.dl[j] + sh[j]; SEND
     // ---- dual active-set loop, cold start --------------------------------------------------
     box_reset<N>(s);
     double u[N];
@@ -281,9 +307,9 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
     // generic iterations; blocking happens late, at |W| >= 3.)
     if (!done && st.iter_limit > N + 2) {
       IterCtx cx{best_fval, fval, cycle, flag, iter, done};
-      if constexpr (N >= 2) box_iter_static<N, 1>(s, cv, st, dU, dLo, u, cx);
-      if constexpr (N >= 3) box_iter_static<N, 2>(s, cv, st, dU, dLo, u, cx);
-      if constexpr (N >= 4) box_iter_static<N, 3>(s, cv, st, dU, dLo, u, cx);
+      if constexpr (N >= 2) box_iter_static<N, 1>(s, cv, bc, Mp, st, dU, dLo, u, cx);
+      if constexpr (N >= 3) box_iter_static<N, 2>(s, cv, bc, Mp, st, dU, dLo, u, cx);
+      if constexpr (N >= 4) box_iter_static<N, 3>(s, cv, bc, Mp, st, dU, dLo, u, cx);
       best_fval = cx.best_fval; fval = cx.fval; cycle = cx.cycle; flag = cx.flag; iter = cx.iter; done = cx.done;
     }
     for (; !done && iter < st.iter_limit; ++iter) {
@@ -309,11 +335,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
       if (blkmask == 0u) {
         // 3. primal iterate, dual objective, most violated row
         SFOR(c, 0, N) u[c] = 0.0; SEND
-        SFOR(i, 0, N)
-          const double *mr = cv.M + s.row[i] * N;
-          const double li = s.lams[i];
-          SFOR(c, 0, N) u[c] = fma(-li, mr[c], u[c]); SEND
-        SEND
+        SFOR(i, 0, N) box_axpy_row<N>(Mp, s.row[i], s.lams[i], u); SEND
         double pu[N];
         SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
         fval = tree_sum<N, 0, 1>(pu);
@@ -325,7 +347,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
         SFOR(j, 0, N)
           // row j of the normalised R^-1 is zero before column j
           double mu = 0.0;
-          SFOR(c, j, N) mu = fma(cv.M[j * N + c], u[c], mu); SEND
+          SFOR(c, j, N) mu = fma(bc.M[j * N + c], u[c], mu); SEND
           const bool free_row = !((s.inws >> j) & 1u);
           const double su = dU[j] - mu, sl = mu - dLo[j];
           const bool tu = free_row && (su < best);
@@ -361,7 +383,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
     // ---- mpc_get_solution -------------------------------------------------------------------
     SFOR(i, 0, NU)
       double pr[N];
-      SFOR(c, 0, N) pr[c] = __dmul_rn(cv.Rinv[i * N + c], u[c]); SEND
+      SFOR(c, 0, N) pr[c] = __dmul_rn(bc.Rinv[i * N + c], u[c]); SEND
       out.U[q * NU + i] = __dadd_rn(tree_sum<N, 0, 1>(pr), sho[i]);
     SEND
     out.flag[q] = flag;
@@ -380,10 +402,15 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, T
 }
 
 template <int N, int NU, int MINB = 3>
-int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
+int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
+               const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
   auto kern = ldp_box_kernel<N, NU, MINB>;
-  const size_t smem = (size_t)lay.total * sizeof(double);
+  const size_t smem = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
+  BoxConst<N, NU> bc;
+  for (int i = 0; i < N * N; ++i) bc.M[i] = hblk[lay.oM + i];
+  for (int i = 0; i < N; ++i) { bc.du[i] = hblk[lay.odu + i]; bc.dl[i] = hblk[lay.odl + i]; }
+  for (int i = 0; i < NU * N; ++i) bc.Rinv[i] = hblk[lay.oRinv + i];
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 0;
@@ -392,7 +419,7 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   int64_t blocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   const int64_t cap = (int64_t)sm_count * per_sm;   // persistent: whole resident waves over the SMs
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, cblk, th, Ninst, out);
+  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out);
   return (int)cudaGetLastError();
 }
 
@@ -405,11 +432,11 @@ bool ldp_box_supports(const LdpLayout &lay) {
 
 #define KB_CASE(NN)                                                                              \
   case NN:                                                                                       \
-    if (lay.nu == 1) return launch_box<NN, 1>(lay, st, cblk, th, N, out, sm_count, s);           \
-    if constexpr (NN >= 2) return launch_box<NN, 2>(lay, st, cblk, th, N, out, sm_count, s);     \
+    if (lay.nu == 1) return launch_box<NN, 1>(lay, st, cblk, hblk, th, N, out, sm_count, s);           \
+    if constexpr (NN >= 2) return launch_box<NN, 2>(lay, st, cblk, hblk, th, N, out, sm_count, s);     \
     return (int)cudaErrorInvalidValue;
 
-int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
                    const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 0) return 0;

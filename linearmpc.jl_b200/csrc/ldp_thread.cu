@@ -489,8 +489,6 @@ int launch_ldp_thread(const LdpLayout &lay, const LdpSettings &st, const double 
                       int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 0) return 0;
-  // box-only problems take the specialised fast path (same arithmetic, fewer instructions)
-  if (!sim && ldp_box_supports(lay)) return launch_ldp_box(lay, st, cblk, th, N, out, sm_count, stream);
   switch (lay.n) {
     K1_CASE(1) K1_CASE(2) K1_CASE(3) K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7) K1_CASE(8)
     default: return (int)cudaErrorInvalidValue;

@@ -90,7 +90,8 @@ int launch_ldp_cta(const LdpLayout &lay, const LdpSettings &st, const double *cb
                    int sm_count, void *stream);
 bool ldp_thread_supports(const LdpLayout &lay);
 bool ldp_box_supports(const LdpLayout &lay);
-int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+// hblk: host copy of the constant block (compile-time-indexed constants ride in the launch parameters)
+int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
                    const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream);
 bool ldp_warp_supports(const LdpLayout &lay);
 bool ldp_cta_supports(const LdpLayout &lay);
