@@ -227,7 +227,8 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const BC &
 template <int N, int NU, int MINB>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
-               const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out) {
+               const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
+               SolveOut out) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
@@ -246,20 +247,19 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
     SFOR(j, 0, N) sh[j] = 0.0; SEND
     SFOR(i, 0, NU) sho[i] = cv.uoff[i]; SEND
     int o = 0;
-    SFOR(sg, 0, 4)
-      if (sg < th.nseg) {
-        const int len = th.len[sg];
-        const double *src = th.ptr[sg] + q * th.stride[sg];
+#pragma unroll 1
+    for (int sg = 0; sg < th.nseg; ++sg) {      // one copy of the loop body for all segments
+      const int len = th.len[sg];
+      const double *src = th.ptr[sg] + q * th.stride[sg];
 #pragma unroll KB_THU
-        for (int t = 0; t < len; ++t) {
-          const double tv = ld_stream(src + t);
-          const int tt = o + t;
-          SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
-          SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
-        }
-        o += len;
+      for (int t = 0; t < len; ++t) {
+        const double tv = ld_stream(src + t);
+        const int tt = o + t;
+        SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
+        SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
       }
-    SEND
+      o += len;
+    }
     // theta-dependent bounds, once per solve (mpc_update_qp): d_u = du + sh, d_l = dl + sh
     double dU[N], dLo[N];
     SFOR(j, 0, N) dU[j] = bc.du[j] + sh[j]; dLo[j] = bc.dl[j] + sh[j]; SEND

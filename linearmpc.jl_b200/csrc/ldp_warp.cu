@@ -94,29 +94,25 @@ LMPC_DEVINL void wq_reset(WarpQp &s) {
   s.k = 0; s.sing = false; s.inws = 0ull;
 }
 
+// Invariant of the tile: row i < k holds L[i][j] for j < i and exact ZEROS for i <= j < LS (the
+// add writes the whole row, the remove only ever rewrites strictly-lower entries).  A sweep step
+// is then an unpredicated fma on every lane: lanes at or above the diagonal multiply by zero and
+// keep their value bit for bit; lanes >= kk compute garbage nobody reads (callers mask).
+//
 // column sweep: z <- L^-1 z on positions [0, kk)
 template <int UF>
 LMPC_DEVINL double sweep_fwd(const WarpCtx &c, const WarpQp &s, double z, int kk) {
-  const bool mine = c.lane < kk;
-  const double *lrow = c.Lw + (mine ? c.lane : 0) * c.LS;   // idle lanes re-read row 0 (in bounds)
+  const double *lrow = c.Lw + (c.lane < kk ? c.lane : 0) * c.LS;   // idle lanes re-read row 0 (in bounds)
 #pragma unroll UF
-  for (int j = 0; j + 1 < kk; ++j) {
-    const double lij = lrow[j];
-    const double zj = shfl_d(z, j);
-    if (mine && c.lane > j) z = fma(-lij, zj, z);
-  }
+  for (int j = 0; j + 1 < kk; ++j) z = fma(-lrow[j], shfl_d(z, j), z);
   return z;
 }
 // column sweep: x <- L^-T x on positions [0, kk), descending (the oracle's axpy order)
 template <int UF>
 LMPC_DEVINL double sweep_bwd(const WarpCtx &c, const WarpQp &s, double x, int kk) {
-  const double *lcol = c.Lw + (c.lane < kk ? c.lane : 0);
+  const double *lcol = c.Lw + (c.lane < c.LS ? c.lane : c.LS - 1);
 #pragma unroll UF
-  for (int j = kk - 1; j > 0; --j) {
-    const double lji = lcol[j * c.LS];
-    const double xj = shfl_d(x, j);
-    if (c.lane < j) x = fma(-lji, xj, x);
-  }
+  for (int j = kk - 1; j > 0; --j) x = fma(-lcol[j * c.LS], shfl_d(x, j), x);
   return x;
 }
 
@@ -130,13 +126,14 @@ LMPC_DEVINL void wq_add(const WarpCtx &c, WarpQp &s, int j, bool lower, double d
   if (sj & S_SOFT) dnew += c.st->rho_soft;
   double y = (lane < k) ? g[s.row] : 0.0;
   y = sweep_fwd<UF>(c, s, y, k);
-  const double l = (lane < k) ? y * s.Dinv : 0.0;
+  y = (lane < k) ? y : 0.0;                  // lanes >= k carried garbage through the sweep
+  const double l = y * s.Dinv;
   dnew = __dsub_rn(dnew, bfly_sum(__dmul_rn(y, l)));
   const bool sing = dnew < c.st->zero_tol;
   if (sing) dnew = 0.0;
   const double dinv = sing ? 0.0 : 1.0 / dnew;
   __syncwarp();                              // idle lanes may still be reading row k in the sweep
-  if (lane < k) c.Lw[k * c.LS + lane] = l;
+  if (lane < c.LS) c.Lw[k * c.LS + lane] = l;   // the whole row: l on [0, k), zeros from the diagonal on
   if (lane == k) {
     s.D = dnew; s.Dinv = dinv; s.lam = 0.0; s.dW = dval; s.row = j;
     s.low = lower; s.imm = (sj & S_IMMUTABLE) != 0; s.soft = (sj & S_SOFT) != 0;
@@ -233,12 +230,10 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
       if (!__any_sync(FULL, blk)) {
         // 3. primal iterate u = -M_W' lam*
         double uc = 0.0;
+        const double *mcol = c.cv.M + (lane < n ? lane : 0);   // lanes >= n shadow lane 0 (masked below)
+        const int rown = s.row * n;
 #pragma unroll UF
-        for (int i = 0; i < k; ++i) {
-          const double li = shfl_d(s.lams, i);
-          const int ri = __shfl_sync(FULL, s.row, i);
-          if (lane < n) uc = fma(-li, c.cv.M[ri * n + lane], uc);
-        }
+        for (int i = 0; i < k; ++i) uc = fma(-shfl_d(s.lams, i), mcol[__shfl_sync(FULL, rown, i)], uc);
         u = uc;
         if (lane < n) c.uw[lane] = uc;
         __syncwarp();
