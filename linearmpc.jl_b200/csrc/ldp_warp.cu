@@ -49,14 +49,6 @@ LMPC_DEVINL double bfly_sum(double v) {
   for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, off));
   return v;
 }
-LMPC_DEVINL double bfly_min(double v) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double o = __shfl_xor_sync(FULL, v, off);
-    v = (o < v) ? o : v;
-  }
-  return v;
-}
 LMPC_DEVINL double bfly_max(double v) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -64,6 +56,18 @@ LMPC_DEVINL double bfly_max(double v) {
     v = (o > v) ? o : v;
   }
   return v;
+}
+// Lanes holding the warp-wide minimum of v (NaN-free), as a ballot mask.  The minimum of a set
+// does not depend on how it is found, so this uses two 32-bit REDUX operations on an
+// order-preserving integer image of the double instead of a 5-step shuffle butterfly
+// (-0.0 is folded onto +0.0 first so that equal values share one key).
+LMPC_DEVINL unsigned min_lanes(double v) {
+  const long long b = __double_as_longlong(__dadd_rn(v, 0.0));
+  const unsigned long long key = (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned hmin = __reduce_min_sync(FULL, hi);
+  const unsigned lmin = __reduce_min_sync(FULL, hi == hmin ? lo : 0xffffffffu);
+  return __ballot_sync(FULL, hi == hmin && lo == lmin);
 }
 
 struct WarpQp {
@@ -202,9 +206,9 @@ LMPC_DEVINL void wq_remove(const WarpCtx &c, WarpQp &s, int r) {
 
 // lowest lane holding the minimum of a (NaN-free), or -1 when every lane is +inf
 LMPC_DEVINL int argmin_first(double a, double &amin) {
-  amin = bfly_min(a);
-  const unsigned hit = __ballot_sync(FULL, a == amin && a < CUDART_INF);
-  return hit ? (__ffs(hit) - 1) : -1;
+  const int lane = __ffs(min_lanes(a)) - 1;
+  amin = shfl_d(a, lane);                    // the first minimiser's own value, as the oracle keeps it
+  return (amin < CUDART_INF) ? lane : -1;
 }
 
 // The dual active-set loop for one QP (oracle: ldp_loop).  sh0/sh1: shifts of rows lane, lane+32.
@@ -238,12 +242,8 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         if (lane < n) c.uw[lane] = uc;
         __syncwarp();
         fval = bfly_sum(lane < n ? __dmul_rn(uc, uc) : 0.0);
-        soft_slack = 0.0;
-        if (lay.nsoft > 0) {
-          const bool sf = lane < k && s.soft;
-          fval = fma(st.rho_soft, bfly_sum(sf ? __dmul_rn(s.lams, s.lams) : 0.0), fval);
-          soft_slack = bfly_max(sf ? st.rho_soft * fabs(s.lams) : 0.0);
-        }
+        const bool sf = lay.nsoft > 0 && lane < k && s.soft;
+        if (lay.nsoft > 0) fval = fma(st.rho_soft, bfly_sum(sf ? __dmul_rn(s.lams, s.lams) : 0.0), fval);
         if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
         // most violated row: candidate per row, then first-index argmin over the warp
         double best = CUDART_INF, bestd = 0.0;
@@ -268,12 +268,16 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
             }
           }
         }
-        const double vmin = bfly_min(best);
         // ties: lowest row index wins; rows lane (half 0) come before lane+32 (half 1)
-        const bool hit = (best == vmin) && bestj >= 0;
+        const bool hit = ((min_lanes(best) >> lane) & 1u) && bestj >= 0;
         const unsigned hit0 = __ballot_sync(FULL, hit && bestj < 32);
         const unsigned hit1 = __ballot_sync(FULL, hit && bestj >= 32);
-        if (!(hit0 | hit1)) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
+        if (!(hit0 | hit1)) {
+          // largest soft slack rho |lam*|, only needed to tell OPTIMAL from SOFT_OPTIMAL
+          if (lay.nsoft > 0) soft_slack = bfly_max(sf ? st.rho_soft * fabs(s.lams) : 0.0);
+          flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL;
+          break;
+        }
         // cycle guard where the dual objective is fresh (see oracle/ldp_oracle.c)
         if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
         else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
