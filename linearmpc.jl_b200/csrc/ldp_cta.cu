@@ -27,13 +27,18 @@ LMPC_DEVINL double bfly_sum(double v) {
   for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, off));
   return v;
 }
+// warp-wide minimum of v (NaN-free): two 32-bit REDUX operations on an order-preserving integer
+// image of the double (-0.0 folded onto +0.0) instead of a 5-step shuffle butterfly; the minimum
+// of a set does not depend on how it is found
 LMPC_DEVINL double bfly_min(double v) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double o = __shfl_xor_sync(FULL, v, off);
-    v = (o < v) ? o : v;
-  }
-  return v;
+  const long long b = __double_as_longlong(__dadd_rn(v, 0.0));
+  const unsigned long long key = (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned hmin = __reduce_min_sync(FULL, hi);
+  const unsigned lmin = __reduce_min_sync(FULL, hi == hmin ? lo : 0xffffffffu);
+  const unsigned long long kmin = ((unsigned long long)hmin << 32) | lmin;
+  const long long bm = (long long)kmin;
+  return __longlong_as_double(bm < 0 ? (bm ^ (long long)0x8000000000000000ull) : ~bm);
 }
 LMPC_DEVINL double bfly_max(double v) {
 #pragma unroll
@@ -43,14 +48,7 @@ LMPC_DEVINL double bfly_max(double v) {
   }
   return v;
 }
-LMPC_DEVINL int bfly_min_i(int v) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const int o = __shfl_xor_sync(FULL, v, off);
-    v = (o < v) ? o : v;
-  }
-  return v;
-}
+LMPC_DEVINL int bfly_min_i(int v) { return __reduce_min_sync(FULL, v); }
 
 template <int T>
 struct BigQp {
