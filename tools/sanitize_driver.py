@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np
 import lmpc_b200, util
 from oracle import mpqp
-for name, N in (("invpend", 3000), ("dint_hard", 3000), ("aircraft", 600), ("aircraft_ksall", 200), ("chain", 8), ("simple", 600)):
+for name, N in (("invpend", 3000), ("dint_hard", 3000), ("aircraft", 600), ("aircraft_ksall", 200), ("chain", 8), ("simple", 600), ("dint_eq", 600), ("dint_eq_small", 600)):
     mpc = util.controller(name); qp = mpqp.mpc2mpqp(mpc)
     g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
     Th = mpqp.sample_theta(*util.theta_range(name, 1.0), N)
