@@ -164,6 +164,19 @@ int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, co
                             double *Xend, double *Ulast, double *Utraj,
                             int32_t *exitflag, int32_t *iters);
 
+/* Same, with a reference and / or measured-disturbance TRAJECTORY shared by all N closed loops:
+ * Rtraj nr x T, Dtraj nd x T, column-major HOST arrays (column t = rs[:, t+1], ds[:, t+1] of
+ * src/simulation.jl:70-80, i.e. already extended by "hold the last value"); either may be NULL, and
+ * where given it replaces the per-trajectory constant R / D.  The disturbance of step t enters both
+ * theta and the dynamics, as in src/simulation.jl:93-110. */
+int lmpc_gpu_simulate_batch_traj(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                                 int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                                 const double *X0, const double *R, const double *D, const double *U0,
+                                 const double *Rtraj, const double *Dtraj,
+                                 int64_t N, int32_t T, int32_t warm_start,
+                                 double *Xend, double *Ulast, double *Utraj,
+                                 int32_t *exitflag, int32_t *iters);
+
 /* One process, several GPUs (BASELINE north_star: "the batch is sharded by contiguous theta ranges
  * across the 8 B200s of one box with no inter-GPU traffic beyond a final result gather").
  * create_multi builds one replica of the controller per listed device (devices NULL = 0..n-1);

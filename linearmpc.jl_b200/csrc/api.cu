@@ -469,6 +469,17 @@ int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, co
                             int64_t N, int32_t T, int32_t warm_start,
                             double *Xend, double *Ulast, double *Utraj,
                             int32_t *exitflag, int32_t *iters) {
+  return lmpc_gpu_simulate_batch_traj(h, F, G, Gd, nx, nr, nd, nuprev, X0, R, D, U0, nullptr, nullptr,
+                                      N, T, warm_start, Xend, Ulast, Utraj, exitflag, iters);
+}
+
+int lmpc_gpu_simulate_batch_traj(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                                 int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                                 const double *X0, const double *R, const double *D, const double *U0,
+                                 const double *Rtraj, const double *Dtraj,
+                                 int64_t N, int32_t T, int32_t warm_start,
+                                 double *Xend, double *Ulast, double *Utraj,
+                                 int32_t *exitflag, int32_t *iters) {
   if (!h || !F || !G || !X0 || !Xend || !Ulast || !exitflag || N < 0 || T < 0)
     return set_err(LMPC_E_INVALID, "lmpc_gpu_simulate_batch: bad argument%s");
   const LdpLayout &l = h->lay;
@@ -478,8 +489,12 @@ int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, co
   CUDA_OK(cudaSetDevice(h->device));
   const int nu = l.nu;
   // dynamics to row-major on the device
-  std::vector<double> dynh((size_t)nx * (nx + nu + nd));
+  const size_t ndyn = (size_t)nx * (nx + nu + nd);
+  const size_t nrt = (Rtraj && nr > 0) ? (size_t)nr * T : 0, ndt = (Dtraj && nd > 0) ? (size_t)nd * T : 0;
+  std::vector<double> dynh(ndyn + nrt + ndt);
   double *Fr = dynh.data(), *Gr = Fr + (size_t)nx * nx, *Gdr = Gr + (size_t)nx * nu;
+  if (nrt) memcpy(dynh.data() + ndyn, Rtraj, nrt * sizeof(double));
+  if (ndt) memcpy(dynh.data() + ndyn + nrt, Dtraj, ndt * sizeof(double));
   for (int i = 0; i < nx; ++i) {
     for (int c = 0; c < nx; ++c) Fr[i * nx + c] = F[(size_t)c * nx + i];
     for (int c = 0; c < nu; ++c) Gr[i * nu + c] = G[(size_t)c * nx + i];
@@ -492,6 +507,8 @@ int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, co
   memset(&sd, 0, sizeof(sd));
   sd.F = (double *)h->dyn.p; sd.G = sd.F + (size_t)nx * nx; sd.Gd = sd.G + (size_t)nx * nu;
   sd.nx = nx; sd.nr = nr; sd.nd = nd; sd.nuprev = nuprev; sd.T = T; sd.warm = warm_start;
+  sd.Rtraj = nrt ? sd.F + ndyn : nullptr;
+  sd.Dtraj = ndt ? sd.F + ndyn + nrt : nullptr;
   ThetaSegs th;
   memset(&th, 0, sizeof(th));
   if (is_device_ptr(X0)) {

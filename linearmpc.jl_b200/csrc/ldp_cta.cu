@@ -585,6 +585,9 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
     int worst = EXIT_OPTIMAL, tot = 0;
     for (int t = 0; t < sd.T; ++t) {
       for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
+      // reference / disturbance of step t (rs[:, k], ds[:, k] of src/simulation.jl:93-104)
+      if (sd.Rtraj) for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.Rtraj[(size_t)t * nr + i];
+      if (sd.Dtraj) for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.Dtraj[(size_t)t * nd + i];
       __syncwarp();
       int iters;
       const int f = bq_solve<T>(c, s, u, iters, !(sd.warm && t > 0));

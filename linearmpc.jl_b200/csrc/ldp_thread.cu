@@ -412,6 +412,9 @@ ldp_thread_sim_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ 
     int worst = EXIT_OPTIMAL, tot = 0;
     for (int t = 0; t < sd.T; ++t) {
       for (int i = 0; i < nup; ++i) thv[(nx + nr + nd + i) * K1_BLOCK] = ucv[i * K1_BLOCK];
+      // reference / disturbance of step t (rs[:, k], ds[:, k] of src/simulation.jl:93-104)
+      if (sd.Rtraj) for (int i = 0; i < nr; ++i) thv[(nx + i) * K1_BLOCK] = sd.Rtraj[(size_t)t * nr + i];
+      if (sd.Dtraj) for (int i = 0; i < nd; ++i) thv[(nx + nr + i) * K1_BLOCK] = sd.Dtraj[(size_t)t * nd + i];
       int iters;
       const int f = qp_solve<N, CAP, GENERAL>(s, cv, lay, st, thv, shv, !(sd.warm && t > 0), u, iters);
       tot += iters;

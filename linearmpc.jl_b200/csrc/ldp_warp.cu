@@ -474,6 +474,9 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
     for (int t = 0; t < sd.T; ++t) {
       _Pragma("unroll 1")
       for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
+      // reference / disturbance of step t (rs[:, k], ds[:, k] of src/simulation.jl:93-104)
+      if (sd.Rtraj) { _Pragma("unroll 1") for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.Rtraj[(size_t)t * nr + i]; }
+      if (sd.Dtraj) { _Pragma("unroll 1") for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.Dtraj[(size_t)t * nd + i]; }
       __syncwarp();
       int iters;
       const int f = wq_solve<K2_UF_SIM, EQ>(c, s, !(sd.warm && t > 0), u, iters);

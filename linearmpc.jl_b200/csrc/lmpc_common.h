@@ -57,6 +57,7 @@ struct SolveOut {
 struct SimDesc {
   const double *F, *G, *Gd;     // device, row-major nx x nx, nx x nu, nx x nd
   const double *X0, *R, *D, *U0;
+  const double *Rtraj, *Dtraj;  // device, nr x T / nd x T (step t at + t * nr): shared by all trajectories, override R / D
   double *Xend, *Ulast, *Utraj;
   int nx, nr, nd, nuprev, T, warm;
 };

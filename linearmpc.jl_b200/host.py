@@ -83,6 +83,8 @@ def load_library():
     L.lmpc_gpu_compute_control_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.lmpc_gpu_simulate_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i64,
                                           i32, i32, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_simulate_batch_traj.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                                               i64, i32, i32, vp, vp, vp, vp, vp]
     L.lmpc_gpu_create_bst.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, C.c_int,
                                       C.POINTER(vp)]
     L.lmpc_gpu_destroy_bst.argtypes = [vp]
@@ -381,9 +383,13 @@ class GpuMPC:
 
     # -- Simulation, batched ----------------------------------------------------------------
     def simulate(self, F, G, x0, r=None, d=None, u0=None, N=None, T=None, Gd=None, warm_start=True,
-                 want_traj=False):
+                 want_traj=False, r_traj=None, d_traj=None):
         """N independent closed loops of `steps` steps (simulation.jl:93-113) with the default
-        linear dynamics (model.jl:70).  `N` = number of steps, as in the reference's keyword."""
+        linear dynamics (model.jl:70).  `N` = number of steps, as in the reference's keyword.
+
+        r, d: constant per closed loop (vector = the same for all, matrix = one column each).
+        r_traj (nr x Tr), d_traj (nd x Td): the scenario's trajectories, shared by all closed loops;
+        shorter than the horizon -> the last column is held (simulation.jl:70-80)."""
         nx, nr, nd, nup = self.dims
         steps = int(N if N is not None else T)
         X0 = _colmajor(x0, nx)
@@ -400,15 +406,23 @@ class GpuMPC:
                 v = np.repeat(v.reshape(rows, 1), n, axis=1)
             return np.asfortranarray(v)
         Rm, Dm, Um = bc(r, nr), bc(d, nd), bc(u0, nup) if u0 is not None else None
+        def hold(v, rows):
+            if v is None or rows == 0:
+                return None
+            v = np.asarray(v, float).reshape(rows, -1)
+            if v.shape[1] < steps:
+                v = np.hstack([v, np.repeat(v[:, -1:], steps - v.shape[1], axis=1)])
+            return np.asfortranarray(v[:, :steps])
+        Rt, Dt = hold(r_traj, nr), hold(d_traj, nd)
         Xend = np.zeros((nx, n), order="F")
         Ulast = np.zeros((self.nu, n), order="F")
         Utraj = np.zeros((n, steps, self.nu)) if want_traj else None
         flag = np.zeros(n, np.int32)
         iters = np.zeros(n, np.int32)
-        _check(lib().lmpc_gpu_simulate_batch(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
-                                             _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), n, steps,
-                                             int(bool(warm_start)), _ptr(Xend), _ptr(Ulast), _ptr(Utraj),
-                                             _ptr(flag), _ptr(iters)))
+        _check(lib().lmpc_gpu_simulate_batch_traj(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
+                                                  _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), _ptr(Rt), _ptr(Dt),
+                                                  n, steps, int(bool(warm_start)), _ptr(Xend), _ptr(Ulast),
+                                                  _ptr(Utraj), _ptr(flag), _ptr(iters)))
         return dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj, exitflag=flag, iters=iters)
 
 
@@ -691,6 +705,6 @@ class MPC:
     def solve(self, Theta, **kw):
         return self._g().solve(Theta, **kw)
 
-    def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False):
+    def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None):
         return self._g().simulate(self.F, self.G, x0, r=r, d=d, N=N, Gd=self.Gd, warm_start=warm_start,
-                                  want_traj=want_traj)
+                                  want_traj=want_traj, r_traj=r_traj, d_traj=d_traj)

@@ -108,22 +108,29 @@ end
     simulate(g, X0; r, d, N, warm_start=true) -> (Xend, Ulast, exitflag)
 
 N_traj independent copies of the `Simulation` loop (src/simulation.jl:93-113) with the model's
-linear dynamics (src/model.jl:70), N steps each, entirely on the GPU.
+linear dynamics (src/model.jl:70), N steps each, entirely on the GPU.  `r` / `d` follow the
+Scenario convention (src/simulation.jl:70-80): a vector is held constant, a matrix is a trajectory
+with one column per step, its last column held when it is shorter than the horizon; the same
+scenario drives every closed loop.
 """
 function simulate(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integer=100, warm_start::Bool=true)
     g.multi && error("simulate: build the backend with a single `device` (closed loops are per-GPU)")
     mdl = g.mpc.model
     nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
     M = size(X0, 2)
-    R = nr == 0 ? C_NULL : Matrix{Float64}(r isa AbstractMatrix ? r : repeat(isnothing(r) ? zeros(nr) : r, 1, M))
-    D = nd == 0 ? C_NULL : Matrix{Float64}(d isa AbstractMatrix ? d : repeat(isnothing(d) ? zeros(nd) : d, 1, M))
+    function traj(v, k)              # k x N, last column held
+        (k == 0 || isnothing(v)) && return C_NULL
+        V = v isa AbstractMatrix ? Matrix{Float64}(v) : reshape(Vector{Float64}(v), k, 1)
+        return hcat(V[:, 1:min(N, size(V, 2))], repeat(V[:, end], 1, max(0, N - size(V, 2))))
+    end
+    Rt, Dt = traj(r, nr), traj(d, nd)
     Xend = similar(X0); Ulast = Matrix{Float64}(undef, g.nu, M); flag = Vector{Int32}(undef, M)
-    check(ccall((:lmpc_gpu_simulate_batch, liblmpcgpu), Cint,
+    check(ccall((:lmpc_gpu_simulate_batch_traj, liblmpcgpu), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
-                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int32,
-                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
                 g.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
-                X0, R, D, C_NULL, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
+                X0, C_NULL, C_NULL, C_NULL, Rt, Dt, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
     return Xend, Ulast, flag
 end
 

@@ -125,7 +125,8 @@ class OracleProblem:
         return r["U"][:, 0], int(r["flag"][0]), r
 
     def simulate_batch(self, Fx, Gx, Gdx, X0, R, D, U0, T, nr, nd, nuprev, warm=False,
-                       nthreads=0, want_traj=False):
+                       nthreads=0, want_traj=False, Rtraj=None, Dtraj=None):
+        """Rtraj (nr x T) / Dtraj (nd x T): trajectories shared by all closed loops (override R / D)."""
         nx = Fx.shape[0]
         c = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, float).T)
         X0c, Rc, Dc, U0c = c(X0), c(R), c(D), c(U0)
@@ -137,10 +138,12 @@ class OracleProblem:
         Utraj = np.zeros((N, T, self.nu)) if want_traj else None
         flag = np.zeros(N, np.int32)
         iters = np.zeros(N, np.int32)
-        lib().orc_simulate_batch(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
-                                 _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), C.c_int64(N), T, int(warm),
-                                 _dp(Xend), _dp(Ulast), _dp(Utraj), _ip(flag), _ip(iters),
-                                 C.c_int(nthreads))
+        Rt, Dt = c(Rtraj), c(Dtraj)      # T x nr, T x nd row-major == column-major nr x T
+        lib().orc_simulate_batch_traj(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
+                                      _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), _dp(Rt), _dp(Dt),
+                                      C.c_int64(N), T, int(warm),
+                                      _dp(Xend), _dp(Ulast), _dp(Utraj), _ip(flag), _ip(iters),
+                                      C.c_int(nthreads))
         return dict(Xend=Xend.T, Ulast=Ulast.T, Utraj=Utraj, flag=flag, iters=iters)
 
 

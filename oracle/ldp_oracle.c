@@ -376,6 +376,7 @@ void orc_solve_batch(const orc_problem *p, const double *Theta, int64_t N, doubl
 
 typedef struct {
   const orc_problem *p; int nx, nr, nd, nuprev; const double *Fx, *Gx, *Gdx, *X0, *R, *D, *U0;
+  const double *Rtraj, *Dtraj;   /* nr x T, nd x T shared trajectories (simulation.jl:70-80), or NULL */
   int T, warm; double *Xend, *Ulast, *Utraj; int32_t *flag, *iters;
 } sim_ctx;
 static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
@@ -395,8 +396,8 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
       /* theta = [x; r; d; uprev] (explicit.jl:54-63) */
       int o = 0;
       for (int i = 0; i < nx; ++i) th[o++] = x[i];
-      for (int i = 0; i < nr; ++i) th[o++] = s->R ? s->R[q * nr + i] : 0.0;
-      for (int i = 0; i < nd; ++i) th[o++] = s->D ? s->D[q * nd + i] : 0.0;
+      for (int i = 0; i < nr; ++i) th[o++] = s->Rtraj ? s->Rtraj[(size_t)t * nr + i] : (s->R ? s->R[q * nr + i] : 0.0);
+      for (int i = 0; i < nd; ++i) th[o++] = s->Dtraj ? s->Dtraj[(size_t)t * nd + i] : (s->D ? s->D[q * nd + i] : 0.0);
       for (int i = 0; i < nuprev; ++i) th[o++] = u[i];
       int32_t it = 0;
       int f = solve_with(p, w, th, u, &it, NULL, NULL, NULL, !(s->warm && t > 0));
@@ -409,7 +410,7 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
         double acc = 0.0;
         for (int c = 0; c < nx; ++c) acc = fma(s->Fx[i * nx + c], x[c], acc);
         for (int c = 0; c < nu; ++c) acc = fma(s->Gx[i * nu + c], u[c], acc);
-        for (int c = 0; c < nd; ++c) acc = fma(s->Gdx[i * nd + c], s->D ? s->D[q * nd + c] : 0.0, acc);
+        for (int c = 0; c < nd; ++c) acc = fma(s->Gdx[i * nd + c], th[nx + nr + c], acc);
         xn[i] = acc;
       }
       for (int i = 0; i < nx; ++i) x[i] = xn[i];
@@ -427,7 +428,16 @@ void orc_simulate_batch(const orc_problem *p, int nx, int nr, int nd, int nuprev
                         const double *X0, const double *R, const double *D, const double *U0,
                         int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
                         int32_t *flag, int32_t *iters, int nthreads) {
-  sim_ctx s = {p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, T, warm, Xend, Ulast, Utraj, flag, iters};
+  orc_simulate_batch_traj(p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, NULL, NULL, N, T, warm, Xend, Ulast,
+                          Utraj, flag, iters, nthreads);
+}
+void orc_simulate_batch_traj(const orc_problem *p, int nx, int nr, int nd, int nuprev,
+                             const double *Fx, const double *Gx, const double *Gdx,
+                             const double *X0, const double *R, const double *D, const double *U0,
+                             const double *Rtraj, const double *Dtraj,
+                             int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
+                             int32_t *flag, int32_t *iters, int nthreads) {
+  sim_ctx s = {p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, Rtraj, Dtraj, T, warm, Xend, Ulast, Utraj, flag, iters};
   parallel_for(N, nthreads, sim_chunk, &s);
 }
 

@@ -67,6 +67,13 @@ void orc_simulate_batch(const orc_problem *p, int nx, int nr, int nd, int nuprev
                         const double *X0, const double *R, const double *D, const double *U0,
                         int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
                         int32_t *flag, int32_t *iters, int nthreads);
+/* same with reference / disturbance trajectories shared by all closed loops (nr x T, nd x T; NULL = use R / D) */
+void orc_simulate_batch_traj(const orc_problem *p, int nx, int nr, int nd, int nuprev,
+                             const double *Fx, const double *Gx, const double *Gdx,
+                             const double *X0, const double *R, const double *D, const double *U0,
+                             const double *Rtraj, const double *Dtraj,
+                             int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
+                             int32_t *flag, int32_t *iters, int nthreads);
 
 /* explicit MPC: binary search tree walk + affine law.
  * halfplanes: n_hp x (nth+1) row-major [a; b]; feedbacks: n_fb x nu x (nth+1)

@@ -204,6 +204,42 @@ def test_closed_loop_matches_oracle(lmpc, name, T, warm):
     assert np.array_equal(out["Xend"], ref["Xend"])
 
 
+@pytest.mark.parametrize("name,T", [("invpend", 60), ("aircraft", 40), ("aircraft_ksall", 30), ("chain_small", 12)])
+def test_closed_loop_with_reference_and_disturbance_trajectories(lmpc, name, T):
+    """Scenario trajectories rs[:, k], ds[:, k] shared by every closed loop (simulation.jl:70-110):
+    a reference step half way, a disturbance pulse, both shorter than the horizon (last value held)."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    rng = np.random.default_rng(5)
+    N = 300
+    lo, hi = util.theta_range(name, 0.25)
+    X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
+    Tr = T - 5
+    Rt = None
+    if nr:
+        Rt = np.zeros((nr, Tr))
+        Rt[0, Tr // 2:] = 0.1
+        Rt += 0.01 * rng.standard_normal((nr, Tr))
+    Dt = None
+    if nd:
+        Dt = np.zeros((nd, T // 2))
+        Dt[:, 3:8] = 0.05
+    for warm in (False, True):
+        out = g.simulate(mpc.F, mpc.G, X0, N=T, Gd=mpc.Gd if nd else None, warm_start=warm, want_traj=True,
+                         r_traj=Rt, d_traj=Dt)
+        hold = lambda v: None if v is None else np.hstack([v, np.repeat(v[:, -1:], T - v.shape[1], axis=1)])
+        ref = P.simulate_batch(mpc.F, mpc.G, mpc.Gd if nd else None, X0, None, None, None, T, nr, nd, nup,
+                               warm=warm, want_traj=True, Rtraj=hold(Rt), Dtraj=hold(Dt))
+        assert np.array_equal(out["exitflag"], ref["flag"])
+        assert np.array_equal(out["iters"], ref["iters"])
+        assert np.array_equal(out["Utraj"], ref["Utraj"])
+        assert np.array_equal(out["Xend"], ref["Xend"])
+    if nr:   # the trajectory matters: a constant-reference run differs
+        const = g.simulate(mpc.F, mpc.G, X0, r=np.zeros(nr), d=np.zeros(nd) if nd else None, N=T,
+                           Gd=mpc.Gd if nd else None, want_traj=True)
+        assert not np.array_equal(const["Utraj"], out["Utraj"])
+
+
 def test_warm_equals_cold_on_gpu(lmpc):
     """runtests.jl:85-117 on the GPU: 100 closed-loop steps, |u_warm - u_cold| < 1e-9."""
     mpc, qp, g, P = gpu_controller(lmpc, "invpend")

@@ -207,3 +207,30 @@ def test_soft_rows_equal_the_reference_explicit_slack_form():
         checked += 1
         soft_active += int(out["flag"][q] == 2)
     assert checked >= 40 and soft_active >= 5
+
+
+def test_closed_loop_with_trajectories_equals_the_stepwise_loop():
+    """orc_simulate_batch_traj against the Simulation loop written out in numpy
+    (simulation.jl:93-110: theta_k = [x_k; rs[:, k]; ds[:, k]; u_{k-1}], x+ = F x + G u + Gd ds[:, k]),
+    one cold solve per step.  Tolerance: the stepwise loop rounds the dynamics differently (BLAS
+    vs the oracle's fma chains) and the AFTI-16 problem amplifies 1 ulp of x to ~1e-7 of u (cond(H)
+    3.5e8, see test_oracle_solutions_satisfy_kkt); a wrong trajectory column would show at 1e-2."""
+    mpc, qp, L, P = make("aircraft")
+    nx, nr, nd, nup = mpc.parameter_dims()
+    T, N = 25, 6
+    rng = np.random.default_rng(3)
+    lo, hi = util.theta_range("aircraft", 0.25)
+    X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
+    Rt = np.zeros((nr, T)); Rt[0, 10:] = 0.1
+    Dt = np.zeros((nd, T)); Dt[:, 4:9] = 0.05
+    out = P.simulate_batch(mpc.F, mpc.G, mpc.Gd, X0, None, None, None, T, nr, nd, nup, warm=False,
+                           want_traj=True, Rtraj=Rt, Dtraj=Dt)
+    for q in range(N):
+        x, u = X0[:, q].copy(), np.zeros(mpc.nu)
+        for k in range(T):
+            th = np.concatenate([x, Rt[:, k], Dt[:, k], u[:nup]])
+            u, flag, _ = P.solve(th)
+            assert flag >= 1
+            assert np.allclose(u, out["Utraj"][q, k], rtol=0, atol=2e-5)
+            x = mpc.F @ x + mpc.G @ u + mpc.Gd @ Dt[:, k]
+        assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=2e-5)
