@@ -138,6 +138,18 @@ int lmpc_gpu_solve_batch_async(lmpc_handle *h, const double *Theta, int64_t N, d
                                int32_t *exitflag, int32_t *iters,
                                uint64_t *active_upper, uint64_t *active_lower, void *stream);
 
+/* Warm-started solve: the batch form of DAQP's warm start (the Julia path keeps the workspace
+ * between solve() calls, src/utils.jl:278-282; generated C: DAQP_WARMSTART,
+ * codegen/mpc_update_qp.c:44-47).  active_upper / active_lower are IN/OUT (required): on entry the
+ * working set to start from (normally what the previous call returned for the same closed
+ * loop), on return the final one.  Equality rows enter first as in a cold start, then the named
+ * rows in ascending order with zero multipliers; a named row that would make the factorisation
+ * singular is left out.  Results equal the cold solve's up to rounding (a different
+ * factorisation order); the iteration count is what changes.  Host or device pointers. */
+int lmpc_gpu_solve_batch_warm(lmpc_handle *h, const double *Theta, int64_t N, double *U,
+                              int32_t *exitflag, int32_t *iters,
+                              uint64_t *active_upper, uint64_t *active_lower);
+
 /* Batched analogue of the generated mpc_compute_control(control, state, reference,
  * disturbance) (codegen/mpc_update_qp.h:3-7, mpc_update_parameter.c:1-29): theta is
  * assembled on the fly as [state; reference; disturbance; control] with

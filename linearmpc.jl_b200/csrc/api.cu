@@ -286,7 +286,7 @@ static int run_kernel(lmpc_handle *h, const ThetaSegs &th, int64_t N, const Solv
   switch (h->kernel) {
     case LMPC_KERNEL_THREAD:
       // box-only problems take the specialised fast path (same arithmetic, fewer instructions)
-      e = (!sim && ldp_box_supports(h->lay))
+      e = (!sim && !o.ws_u && ldp_box_supports(h->lay))
               ? launch_ldp_box(h->lay, h->st, h->d_blk, h->h_blk, th, N, o, h->sm_count, s)
               : launch_ldp_thread(h->lay, h->st, h->d_blk, th, N, o, sim, h->sm_count, s);
       break;
@@ -340,7 +340,8 @@ static int drain_slot(lmpc_handle *h, Slot &s, double *U, int ustride, int32_t *
 // emptied by several host threads while the other stages' DMA and kernels run.
 static int solve_segments_host(lmpc_handle *h, const double *const *seg, const int *len,
                                const int *stride, int nseg, int64_t N, double *U, int ustride,
-                               int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al) {
+                               int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al,
+                               bool warm = false) {
   const LdpLayout &l = h->lay;
   const int words = (l.m + 63) / 64;
   bool stage = is_pageable(U) || is_pageable(flag);
@@ -375,6 +376,11 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
     if (au && (s.au.reserve((size_t)cnt * words * 8) || s.al.reserve((size_t)cnt * words * 8))) return LMPC_E_CUDA;
     SolveOut o{(double *)s.u.p, (int32_t *)s.flag.p, iters ? (int32_t *)s.iters.p : nullptr,
                au ? (uint64_t *)s.au.p : nullptr, au ? (uint64_t *)s.al.p : nullptr};
+    if (warm) {   // the caller's working sets go in through the same device buffers the final ones come out of
+      CUDA_OK(cudaMemcpyAsync(s.au.p, au + off * words, (size_t)cnt * words * 8, cudaMemcpyHostToDevice, s.stream));
+      CUDA_OK(cudaMemcpyAsync(s.al.p, al + off * words, (size_t)cnt * words * 8, cudaMemcpyHostToDevice, s.stream));
+      o.ws_u = o.act_u; o.ws_l = o.act_l;
+    }
     int rc = run_kernel(h, th, cnt, o, nullptr, s.stream);
     if (rc) return rc;
     if (stage) {
@@ -426,6 +432,27 @@ int lmpc_gpu_solve_batch(lmpc_handle *h, const double *Theta, int64_t N, double 
   const double *seg[1] = {Theta};
   int len[1] = {h->lay.nth}, stride[1] = {h->lay.nth};
   return solve_segments_host(h, seg, len, stride, 1, N, U, h->lay.nu, exitflag, iters, au, al);
+}
+
+int lmpc_gpu_solve_batch_warm(lmpc_handle *h, const double *Theta, int64_t N, double *U,
+                              int32_t *exitflag, int32_t *iters, uint64_t *au, uint64_t *al) {
+  if (!h || !Theta || !U || !exitflag || !au || !al || N < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_solve_batch_warm: bad argument%s");
+  if (N == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (is_device_ptr(Theta)) {
+    ThetaSegs th;
+    memset(&th, 0, sizeof(th));
+    th.nseg = 1; th.ptr[0] = Theta; th.len[0] = h->lay.nth; th.stride[0] = h->lay.nth;
+    SolveOut o{U, exitflag, iters, au, al, au, al};
+    int rc = run_kernel(h, th, N, o, nullptr, h->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  const double *seg[1] = {Theta};
+  int len[1] = {h->lay.nth}, stride[1] = {h->lay.nth};
+  return solve_segments_host(h, seg, len, stride, 1, N, U, h->lay.nu, exitflag, iters, au, al, true);
 }
 
 int lmpc_gpu_compute_control_batch(lmpc_handle *h, double *control, const double *state,

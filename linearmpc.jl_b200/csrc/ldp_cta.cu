@@ -178,6 +178,16 @@ LMPC_DEVINL void bq_add(const BigCtx &c, BigQp<T> &s, int j, bool lower, double 
   __syncwarp();
 }
 
+// take back a trial add of row j (warm start from masks: the row would have been singular)
+template <int T>
+LMPC_DEVINL void bq_undo_add(const BigCtx &c, BigQp<T> &s, int j) {
+  s.k -= 1;
+  if ((j & 31) == c.lane) s.inws &= ~(1u << (j >> 5));
+  if (c.inwsb && c.lane == 0) c.inwsb[j] = 0;
+  s.sing = false;
+  __syncwarp();
+}
+
 // position i takes the value of position i + 1 (for r <= i < k - 1)
 template <int T>
 LMPC_DEVINL void shift_down(double (&v)[T], int lane, int r, int k) {
@@ -413,7 +423,8 @@ LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T],
 }
 
 template <int T>
-LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iters, bool cold = true) {
+LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iters, bool cold = true,
+                         const uint64_t *wsu = nullptr, const uint64_t *wsl = nullptr) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
   double sh[2 * T];
@@ -443,6 +454,18 @@ LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iter
         bq_add<T>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
         if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
       }
+    }
+    // warm start from a caller-supplied working set (oracle: activate_rows)
+    for (int j = 0; wsu && flag == 0 && j < m; ++j) {
+      const int sj = c.cv.sense[j];
+      const bool up = (wsu[j >> 6] >> (j & 63)) & 1ull, lo = (wsl[j >> 6] >> (j & 63)) & 1ull;
+      if ((sj & (S_ACTIVE | S_IMMUTABLE)) || !(up || lo)) continue;
+      if (s.k >= lay.cap || s.k >= 32 * T) continue;
+      double shj = 0.0;
+#pragma unroll
+      for (int t2 = 0; t2 < 2 * T; ++t2) { const double x = shfl_d(sh[t2], j & 31); shj = ((j >> 5) == t2) ? x : shj; }
+      bq_add<T>(c, s, j, !up, (up ? c.cv.du[j] : c.cv.dl[j]) + shj);
+      if (s.sing) bq_undo_add<T>(c, s, j);
     }
   } else {
     // warm start: same working set, new right-hand sides (row j's shift lives on lane j & 31, tile j >> 5)
@@ -509,7 +532,8 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     }
     __syncwarp();
     int iters;
-    const int flag = bq_solve<T>(c, s, u, iters);
+    const int flag = bq_solve<T>(c, s, u, iters, true, out.ws_u ? out.ws_u + q * words : nullptr,
+                                 out.ws_u ? out.ws_l + q * words : nullptr);
     // output map: canonical lane sum over the n variables, one control at a time
     for (int i = 0; i < lay.nu; ++i) {
       double rr[T];
@@ -725,6 +749,16 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           bq_add<T>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + cs.shw[j]);
           if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
         }
+      }
+      // warm start from a caller-supplied working set (oracle: activate_rows)
+      for (int j = 0; out.ws_u && flag != EXIT_OVERDETERMINED && j < m; ++j) {
+        const int sj = c.cv.sense[j];
+        const uint64_t *wsu = out.ws_u + q * words, *wsl = out.ws_l + q * words;
+        const bool up = (wsu[j >> 6] >> (j & 63)) & 1ull, lo = (wsl[j >> 6] >> (j & 63)) & 1ull;
+        if ((sj & (S_ACTIVE | S_IMMUTABLE)) || !(up || lo)) continue;
+        if (s.k >= cap || s.k >= 32 * T) continue;
+        bq_add<T>(c, s, j, !up, (up ? c.cv.du[j] : c.cv.dl[j]) + cs.shw[j]);
+        if (s.sing) bq_undo_add<T>(c, s, j);
       }
       if (flag == EXIT_OVERDETERMINED && lane == 0) cs.ctl[1] = flag;
     }

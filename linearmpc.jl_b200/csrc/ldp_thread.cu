@@ -293,7 +293,8 @@ LMPC_DEVINL int qp_loop(QpState<N, CAP> &s, const ConstView &cv, int m, const Ld
 template <int N, int CAP, bool GENERAL>
 LMPC_DEVINL int qp_solve(QpState<N, CAP> &s, const ConstView &cv, const LdpLayout &lay,
                          const LdpSettings &st, const double *thv, double *shv, bool cold,
-                         double (&u)[N], int &iters) {
+                         double (&u)[N], int &iters, bool warm = false,
+                         unsigned long long wsu = 0ull, unsigned long long wsl = 0ull) {
   const int m = lay.m, nth = lay.nth;
   // mpc_update_qp: sh_j = Dth[j,:] theta
   for (int j = 0; j < m; ++j) {
@@ -315,6 +316,14 @@ LMPC_DEVINL int qp_solve(QpState<N, CAP> &s, const ConstView &cv, const LdpLayou
         qp_add<N, CAP>(s, cv, m, st, j, low, dv);
         if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
       }
+    }
+    // warm start from a caller-supplied working set (oracle: activate_rows)
+    for (int j = 0; warm && flag == 0 && j < m; ++j) {
+      const int sj = cv.sense[j];
+      const bool up = (wsu >> j) & 1ull, lo = (wsl >> j) & 1ull;
+      if ((sj & (S_ACTIVE | S_IMMUTABLE)) || !(up || lo) || s.k >= CAP) continue;
+      qp_add<N, CAP>(s, cv, m, st, j, !up, (up ? cv.du[j] : cv.dl[j]) + shv[j * K1_BLOCK]);
+      if (s.sing) { s.k -= 1; s.inws &= ~(1ull << j); s.sing = false; }   // undo the trial add
     }
   } else {
     // warm start: same working set, new right-hand sides
@@ -370,7 +379,9 @@ ldp_thread_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk
       }
     SEND
     int iters;
-    const int flag = qp_solve<N, CAP, GENERAL>(s, cv, lay, st, thv, shv, true, u, iters);
+    const bool warm = out.ws_u != nullptr;
+    const int flag = qp_solve<N, CAP, GENERAL>(s, cv, lay, st, thv, shv, true, u, iters, warm,
+                                               warm ? out.ws_u[q * words] : 0ull, warm ? out.ws_l[q * words] : 0ull);
     for (int i = 0; i < lay.nu; ++i) out.U[q * lay.nu + i] = control_out<N>(cv, lay.nth, i, u, thv);
     out.flag[q] = flag;
     if (out.iters) out.iters[q] = iters;

@@ -326,7 +326,8 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
 
 // one solve for theta in c.thw; returns the flag; u (lane c holds u_c) and iters by reference
 template <int UF, bool EQ>
-LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters) {
+LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters,
+                         bool warm = false, unsigned long long wsu = 0ull, unsigned long long wsl = 0ull) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
   // mpc_update_qp: sh_j = Dth[j,:] theta for rows lane and lane + 32
@@ -347,7 +348,7 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
     u = 0.0;
     // equality rows enter the working set before the first iteration; controllers without any
     // (EQ == false) are compiled without this second copy of the add
-    for (int j = 0; EQ && j < m; ++j) {
+    for (int j = 0; EQ && lay.neq > 0 && j < m; ++j) {
       const int sj = c.cv.sense[j];
       if (sj & S_ACTIVE) {
         if (s.k >= lay.cap || s.k >= 32) { flag = EXIT_OVERDETERMINED; break; }
@@ -356,6 +357,17 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
         wq_add<UF>(c, s, j, low, (low ? c.cv.dl[j] : c.cv.du[j]) + shj);
         if (s.sing) { flag = EXIT_OVERDETERMINED; break; }
       }
+    }
+    // warm start from a caller-supplied working set (oracle: activate_rows): named rows in
+    // ascending order, lam = 0, upper wins; a row that would be singular is left out
+    for (int j = 0; EQ && warm && flag == 0 && j < m; ++j) {
+      const int sj = c.cv.sense[j];
+      const bool up = (wsu >> j) & 1ull, lo = (wsl >> j) & 1ull;
+      if ((sj & (S_ACTIVE | S_IMMUTABLE)) || !(up || lo)) continue;
+      if (s.k >= lay.cap || s.k >= 32) continue;
+      const double shj = shfl_d(j < 32 ? sh0 : sh1, j & 31);
+      wq_add<UF>(c, s, j, !up, (up ? c.cv.du[j] : c.cv.dl[j]) + shj);
+      if (s.sing) { s.k -= 1; s.inws &= ~(1ull << j); s.sing = false; }   // undo the trial add
     }
   } else {
     // warm start: same working set, new right-hand sides
@@ -420,7 +432,9 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
     }
     __syncwarp();
     int iters;
-    const int flag = wq_solve<K2_UF_SOLVE, EQ>(c, s, true, u, iters);
+    const bool warm = EQ && out.ws_u != nullptr;
+    const int flag = wq_solve<K2_UF_SOLVE, EQ>(c, s, true, u, iters, warm, warm ? out.ws_u[q * words] : 0ull,
+                                               warm ? out.ws_l[q * words] : 0ull);
     for (int i = 0; i < lay.nu; ++i) {
       const double ctl = control_out_w(c, i, u);
       if (lane == 0) out.U[q * lay.nu + i] = ctl;
@@ -563,6 +577,6 @@ int launch_ldp_warp(const LdpLayout &lay, const LdpSettings &st, const double *c
                     const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
                     int sm_count, void *stream) {
   if (N <= 0) return 0;
-  return lay.neq > 0 ? launch_warp_t<true>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream)
+  return (lay.neq > 0 || out.ws_u) ? launch_warp_t<true>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream)
                      : launch_warp_t<false>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream);
 }

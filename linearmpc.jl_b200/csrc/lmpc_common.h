@@ -51,6 +51,10 @@ struct SolveOut {
   int32_t *iters;   // N or null
   uint64_t *act_u;  // words x N or null
   uint64_t *act_l;
+  // warm start (lmpc_gpu_solve_batch_warm): working sets to start from, words x N, or null = cold.
+  // May alias act_u / act_l (every instance reads its words before it writes them).
+  const uint64_t *ws_u;
+  const uint64_t *ws_l;
 };
 
 // closed-loop description for the simulate kernels (x+ = F x + G u + Gd d), row-major

@@ -79,6 +79,7 @@ def load_library():
     L.lmpc_gpu_create_multi.argtypes = [C.POINTER(_Problem), C.POINTER(_Settings), vp, i32, C.POINTER(vp)]
     L.lmpc_gpu_destroy_multi.argtypes = [vp]
     L.lmpc_gpu_solve_batch_multi.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_solve_batch_warm.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     L.lmpc_gpu_solve_batch_async.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.lmpc_gpu_compute_control_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.lmpc_gpu_simulate_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i64,
@@ -313,6 +314,32 @@ class GpuMPC:
         al = np.zeros((N, words), np.uint64) if want_active else None
         _check(lib().lmpc_gpu_solve_batch(self._h, _ptr(Th), N, _ptr(U), _ptr(flag), _ptr(iters),
                                           _ptr(au), _ptr(al)))
+        return dict(U=U, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
+
+    def solve_warm(self, Theta, active_upper, active_lower, want_iters=True):
+        """Warm-started solve (lmpc_gpu_solve_batch_warm): start every instance from the working set
+        in active_upper / active_lower (N x words uint64, e.g. the previous solve's result).
+        Host arrays (not modified) or device tensors (updated in place)."""
+        words = (self.m + 63) // 64
+        if _is_device(Theta):
+            import torch
+            N = Theta.numel() // self.nth
+            dev = Theta.device
+            U = torch.empty((N, self.nu), dtype=torch.float64, device=dev)
+            flag = torch.empty(N, dtype=torch.int32, device=dev)
+            iters = torch.empty(N, dtype=torch.int32, device=dev) if want_iters else None
+            _check(lib().lmpc_gpu_solve_batch_warm(self._h, _ptr(Theta), N, _ptr(U), _ptr(flag), _ptr(iters),
+                                                   _ptr(active_upper), _ptr(active_lower)))
+            return dict(U=U.T, exitflag=flag, iters=iters, active_upper=active_upper, active_lower=active_lower)
+        Th = _colmajor(Theta, self.nth)
+        N = Th.shape[1]
+        U = np.zeros((self.nu, N), order="F")
+        flag = np.zeros(N, np.int32)
+        iters = np.zeros(N, np.int32) if want_iters else None
+        au = np.ascontiguousarray(active_upper, np.uint64).reshape(N, words).copy()
+        al = np.ascontiguousarray(active_lower, np.uint64).reshape(N, words).copy()
+        _check(lib().lmpc_gpu_solve_batch_warm(self._h, _ptr(Th), N, _ptr(U), _ptr(flag), _ptr(iters),
+                                               _ptr(au), _ptr(al)))
         return dict(U=U, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
 
     def solve_async(self, Theta_dev, U_dev, flag_dev, iters_dev=None, au_dev=None, al_dev=None,

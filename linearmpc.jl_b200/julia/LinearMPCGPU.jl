@@ -87,6 +87,23 @@ function solve(g::GpuMPC, Θ::Matrix{Float64})
 end
 
 """
+    solve_warm!(g, Θ, active_upper, active_lower) -> (U, exitflag, iters)
+
+Warm-started batch (DAQP keeps its workspace between `solve` calls, src/utils.jl:278-282): every
+column starts from the working set in `active_upper` / `active_lower` (`cld(m, 64)` words per
+column, e.g. what the previous call left there) and the two arrays are overwritten with the final sets.
+"""
+function solve_warm!(g::GpuMPC, Θ::Matrix{Float64}, active_upper::Matrix{UInt64}, active_lower::Matrix{UInt64})
+    g.multi && error("solve_warm!: single-device backends only")
+    N = size(Θ, 2)
+    U = Matrix{Float64}(undef, g.nu, N); flag = Vector{Int32}(undef, N); it = Vector{Int32}(undef, N)
+    check(ccall((:lmpc_gpu_solve_batch_warm, liblmpcgpu), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt64}, Ptr{UInt64}),
+                g.handle, Θ, N, U, flag, it, active_upper, active_lower))
+    return U, flag, it
+end
+
+"""
     compute_control(g, X; r, d, uprev, check=true) -> nu × N
 
 Batched `compute_control` (src/utils.jl:43-51): X is nx × N; r, d, uprev are vectors (broadcast)

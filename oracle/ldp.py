@@ -120,6 +120,19 @@ class OracleProblem:
             out["flops"] = fl
         return out
 
+    def solve_batch_warm(self, Theta, act_u, act_l, nthreads=0):
+        """Warm start from the working sets act_u / act_l (N x words uint64; not modified)."""
+        Th = np.ascontiguousarray(np.asarray(Theta, float).T)
+        N = Th.shape[0]
+        U = np.zeros((N, self.nu))
+        flag = np.zeros(N, np.int32)
+        iters = np.zeros(N, np.int32)
+        au = np.ascontiguousarray(act_u, np.uint64).copy()
+        al = np.ascontiguousarray(act_l, np.uint64).copy()
+        lib().orc_solve_batch_warm(C.byref(self.c), _dp(Th), C.c_int64(N), _dp(U), _ip(flag), _ip(iters),
+                                   _up(au), _up(al), C.c_int(nthreads))
+        return dict(U=U.T, flag=flag, iters=iters, act_u=au, act_l=al)
+
     def solve(self, theta):
         r = self.solve_batch(np.asarray(theta, float).reshape(-1, 1), nthreads=1)
         return r["U"][:, 0], int(r["flag"][0]), r

@@ -291,11 +291,32 @@ static void get_solution(const orc_problem *p, const double *th, const work_t *w
   if (fl) *fl += (double)p->nu * (2 * p->n - p->nu + 1) + 2.0 * p->nu * p->nth;
 }
 
+/* Warm start from a caller-supplied working set (the batch form of DAQP_WARMSTART,
+ * codegen/mpc_update_qp.c:44-47): first the equality rows, exactly as in a cold start, then the
+ * rows named in wu / wl in ascending row order with lam = 0 (an upper bit wins over a lower
+ * bit); a named row that would make the factorisation singular is left out, IMMUTABLE rows are
+ * never named. */
+static int activate_rows(const orc_problem *p, work_t *w, const uint64_t *wu, const uint64_t *wl) {
+  int flag = activate_equalities(p, w);
+  if (flag) return flag;
+  for (int j = 0; j < p->m; ++j) {
+    if (p->sense[j] & (ORC_ACTIVE | ORC_IMMUTABLE)) continue;
+    const int up = wu && ((wu[j >> 6] >> (j & 63)) & 1ull), lo = wl && ((wl[j >> 6] >> (j & 63)) & 1ull);
+    if (!up && !lo) continue;
+    ldl_add(p, w, j, up ? 1 : -1, NULL);
+    if (w->sing) { w->k -= 1; w->inws[j] = 0; w->sing = 0; }   /* undo the trial add */
+  }
+  return 0;
+}
+
 static int solve_with(const orc_problem *p, work_t *w, const double *th, double *ctl,
                       int32_t *iters, uint64_t *au, uint64_t *al, double *fl, int cold) {
   int flag = 0, it = 0;
   update_bounds(p, th, w, fl);
-  if (cold) {
+  if (cold == 2) {            /* warm start from the masks in au / al (in/out) */
+    work_reset(p, w);
+    flag = activate_rows(p, w, au, al);
+  } else if (cold) {
     work_reset(p, w);
     flag = activate_equalities(p, w);
   }
@@ -348,7 +369,7 @@ static void parallel_for(int64_t N, int nthreads, chunk_fn fn, void *ctx) {
 
 typedef struct {
   const orc_problem *p; const double *Theta; double *U;
-  int32_t *flag, *iters; uint64_t *au, *al; double *flops;
+  int32_t *flag, *iters; uint64_t *au, *al; double *flops; int mode;   /* 1 cold, 2 warm from masks */
 } batch_ctx;
 static void batch_chunk(void *vc, int64_t lo, int64_t hi) {
   batch_ctx *c = (batch_ctx *)vc;
@@ -360,7 +381,7 @@ static void batch_chunk(void *vc, int64_t lo, int64_t hi) {
     int32_t it = 0;
     int f = solve_with(p, w, c->Theta + q * p->nth, c->U + q * p->nu, &it,
                        c->au ? c->au + q * words : NULL, c->al ? c->al + q * words : NULL,
-                       c->flops ? &fl : NULL, 1);
+                       c->flops ? &fl : NULL, c->mode);
     if (c->flag) c->flag[q] = f;
     if (c->iters) c->iters[q] = it;
     if (c->flops) c->flops[q] = fl;
@@ -370,7 +391,13 @@ static void batch_chunk(void *vc, int64_t lo, int64_t hi) {
 void orc_solve_batch(const orc_problem *p, const double *Theta, int64_t N, double *U,
                      int32_t *flag, int32_t *iters, uint64_t *act_u, uint64_t *act_l,
                      double *flops, int nthreads) {
-  batch_ctx c = {p, Theta, U, flag, iters, act_u, act_l, flops};
+  batch_ctx c = {p, Theta, U, flag, iters, act_u, act_l, flops, 1};
+  parallel_for(N, nthreads, batch_chunk, &c);
+}
+void orc_solve_batch_warm(const orc_problem *p, const double *Theta, int64_t N, double *U,
+                          int32_t *flag, int32_t *iters, uint64_t *act_u, uint64_t *act_l,
+                          int nthreads) {
+  batch_ctx c = {p, Theta, U, flag, iters, act_u, act_l, NULL, 2};
   parallel_for(N, nthreads, batch_chunk, &c);
 }
 

@@ -57,6 +57,10 @@ int orc_solve(const orc_problem *p, const double *theta, double *u, int32_t *ite
 void orc_solve_batch(const orc_problem *p, const double *Theta, int64_t N, double *U,
                      int32_t *flag, int32_t *iters, uint64_t *act_u, uint64_t *act_l,
                      double *flops, int nthreads);
+/* warm start from the working sets in act_u / act_l (in/out, required): see activate_rows */
+void orc_solve_batch_warm(const orc_problem *p, const double *Theta, int64_t N, double *U,
+                          int32_t *flag, int32_t *iters, uint64_t *act_u, uint64_t *act_l,
+                          int nthreads);
 
 /* closed loop: x+ = Fx x + Gx u + Gdx d (simulation.jl:93-113, model.jl:70).
  * X0 nx x N, R nr x N, D nd x N (held constant), U0 nuprev x N (nullable -> 0).

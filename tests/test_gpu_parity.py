@@ -308,3 +308,62 @@ def test_pinned_and_pageable_host_buffers_agree(lmpc, N):
     assert np.array_equal(a["active_upper"], au) and np.array_equal(a["active_lower"], al)
     if N <= 300000:
         assert_parity(a, P.solve_batch(Th))
+
+
+WARM_CASES = [("invpend", 0), ("invpend", 2), ("invpend", 3), ("dint_hard", 0), ("dint_eq_small", 0), ("dint_eq", 0),
+              ("aircraft", 0), ("aircraft", 3), ("aircraft_ksall", 0), ("simple", 0), ("chain_small", 0), ("chain", 0)]
+
+
+@pytest.mark.parametrize("name,kernel", WARM_CASES)
+def test_warm_started_batch_matches_oracle(lmpc, name, kernel):
+    """lmpc_gpu_solve_batch_warm against the oracle's activate_rows + loop: start every instance from
+    the optimal working set of a nearby theta (what a caller-managed closed loop does), bit for bit.
+    Also from an empty set (== cold start) and from the instance's own optimum (one iteration)."""
+    mpc, qp, g, P = gpu_controller(lmpc, name, kernel)
+    N = 200 if name == "chain" else 2000
+    lo, hi = util.theta_range(name, 0.5)
+    Th0 = mpqp.sample_theta(lo, hi, N, seed=3)
+    prev = P.solve_batch(Th0)
+    Th = Th0 + 0.02 * (hi - lo)[:, None] * np.random.default_rng(1).standard_normal(Th0.shape)
+    ref = P.solve_batch_warm(Th, prev["act_u"], prev["act_l"])
+    out = g.solve_warm(Th, prev["act_u"], prev["act_l"])
+    assert_parity(out, ref)
+    cold = P.solve_batch(Th)
+    assert ref["iters"].mean() < cold["iters"].mean() or cold["iters"].mean() < 1.5
+    # empty working sets: exactly the cold start
+    zero = np.zeros_like(prev["act_u"])
+    assert_parity(g.solve_warm(Th, zero, zero), cold)
+    # the instance's own optimal set: the first iteration confirms it
+    own = g.solve_warm(Th, cold["act_u"], cold["act_l"])
+    okc = cold["flag"] == 1
+    assert np.all(own["iters"][okc] == 1)
+    assert np.array_equal(own["active_upper"][okc], cold["act_u"][okc])
+
+
+def test_warm_start_on_device_buffers(lmpc):
+    """Device-resident in/out working sets: a caller-managed closed loop, 30 steps, the masks of
+    step t feed step t + 1; same controls as cold solves to 1e-9 (runtests.jl:85-117's bound)."""
+    import torch
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    nx, nr, nd, nup = mpc.parameter_dims()
+    N = 4096
+    lo, hi = util.theta_range("invpend", 0.25)
+    rng = np.random.default_rng(2)
+    X = rng.uniform(lo[:nx], hi[:nx], (N, nx))
+    dev = torch.device("cuda", 0)
+    au = torch.zeros((N, 1), dtype=torch.int64, device=dev)
+    al = torch.zeros((N, 1), dtype=torch.int64, device=dev)
+    uprev = np.zeros((N, nup))
+    it_w = it_c = 0
+    for t in range(30):
+        Th = np.hstack([X, np.zeros((N, nr)), uprev])
+        Td = torch.tensor(Th, dtype=torch.float64, device=dev)
+        w = g.solve_warm(Td, au, al)
+        c = g.solve(Td)
+        assert torch.all(w["exitflag"] >= 1)
+        assert torch.max(torch.abs(w["U"] - c["U"])).item() < 1e-9
+        it_w += int(w["iters"].sum()); it_c += int(c["iters"].sum())
+        u = w["U"].T.cpu().numpy()
+        X = X @ mpc.F.T + u @ mpc.G.T
+        uprev = u[:, :nup]
+    assert it_w < it_c

@@ -64,6 +64,39 @@ if "aircraft" in which:
     solve_cfg("aircraft", 1.0, 1_000_000, 100_000)
     solve_cfg("aircraft", 0.25, 1_000_000, 100_000)
     solve_cfg("aircraft_ksall", 0.25, 200_000, 50_000)
+if "warm" in which:
+    # warm-started batch (lmpc_gpu_solve_batch_warm): every instance starts from the optimal working
+    # set of a theta 2 % of the range away (a caller-managed closed loop between two samples)
+    for name, scale, N in (("aircraft", 0.25, 1_000_000), ("invpend", 1.0, 10_000_000)):
+        mpc = util.controller(name); qp = mpqp.mpc2mpqp(mpc)
+        g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
+        lo, hi = util.theta_range(name, scale)
+        Th0 = rand_theta(lo, hi, N)
+        gen = torch.Generator(device=dev); gen.manual_seed(7)
+        Th = Th0 + 0.02 * torch.tensor(hi - lo, device=dev) * torch.randn(Th0.shape, dtype=torch.float64, device=dev, generator=gen)
+        prev = g.solve(Th0)
+        au0, al0 = prev["active_upper"].clone(), prev["active_lower"].clone()
+        cold = g.solve(Th)
+        U = torch.empty((N, g.nu), dtype=torch.float64, device=dev); fl = torch.empty(N, dtype=torch.int32, device=dev)
+        it = torch.empty(N, dtype=torch.int32, device=dev)
+        au, al = au0.clone(), al0.clone()
+        def run(s):
+            au.copy_(au0); al.copy_(al0)
+            lmpc_b200.host._check(lmpc_b200.lib().lmpc_gpu_solve_batch_warm(g._h, Th.data_ptr(), N, U.data_ptr(), fl.data_ptr(),
+                                                                       it.data_ptr(), au.data_ptr(), al.data_ptr()))
+        t0 = time.perf_counter(); run(None); torch.cuda.synchronize()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps): run(None)
+        torch.cuda.synchronize(); ms_w = (time.perf_counter() - t0) / reps * 1e3
+        ms_c = timed(lambda s: g.solve_async(Th, U, fl, it, N=N, stream=s.cuda_stream))
+        ok = (cold["exitflag"] >= 1)
+        print(json.dumps({"config": name + "_warm_batch", "theta_scale": scale, "N": N,
+                          "warm_solves_per_s": N / ms_w * 1e3, "cold_solves_per_s": N / ms_c * 1e3,
+                          "mean_iters_warm": float(g.solve_warm(Th, au0.clone(), al0.clone())["iters"].float().mean()),
+                          "mean_iters_cold": float(cold["iters"].float().mean()),
+                          "max_abs_du_vs_cold": float((g.solve_warm(Th, au0.clone(), al0.clone())["U"] - cold["U"])[:, ok].abs().max()),
+                          "timer": "wall clock incl. the mask reset copies (warm), CUDA events (cold)"}), flush=True)
 if "chain" in which:
     solve_cfg("chain", 1.0, 20_000, 1_000)
     solve_cfg("chain", 0.25, 100_000, 4_000)
