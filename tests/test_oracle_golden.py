@@ -234,3 +234,27 @@ def test_closed_loop_with_trajectories_equals_the_stepwise_loop():
             assert np.allclose(u, out["Utraj"][q, k], rtol=0, atol=2e-5)
             x = mpc.F @ x + mpc.G @ u + mpc.Gd @ Dt[:, k]
         assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name,tol", [("invpend", 1e-9), ("dint_hard", 1e-9), ("dint_eq", 1e-9), ("chain_small", 1e-9),
+                                      ("simple", 1e-5)])
+def test_warm_start_from_masks_reaches_the_cold_solution(name, tol):
+    """activate_rows: starting from the optimal working set of a nearby theta changes the iteration
+    count, not the answer (runtests.jl:85-117 asserts warm == cold to 1e-9); from an empty set it IS
+    the cold start; from the instance's own optimal set the first iteration confirms it."""
+    mpc, qp, L, P = make(name)
+    lo, hi = util.theta_range(name, 0.5)
+    Th0 = mpqp.sample_theta(lo, hi, 1500, seed=3)
+    prev = P.solve_batch(Th0)
+    Th = Th0 + 0.02 * (hi - lo)[:, None] * np.random.default_rng(1).standard_normal(Th0.shape)
+    cold = P.solve_batch(Th)
+    warm = P.solve_batch_warm(Th, prev["act_u"], prev["act_l"])
+    assert np.array_equal(cold["flag"], warm["flag"])
+    ok = cold["flag"] >= 1
+    assert np.max(np.abs(cold["U"][:, ok] - warm["U"][:, ok])) <= tol
+    assert warm["iters"].sum() < cold["iters"].sum()
+    zero = np.zeros_like(prev["act_u"])
+    z = P.solve_batch_warm(Th, zero, zero)
+    assert np.array_equal(z["U"], cold["U"]) and np.array_equal(z["iters"], cold["iters"])
+    own = P.solve_batch_warm(Th, cold["act_u"], cold["act_l"])
+    assert np.all(own["iters"][cold["flag"] == 1] == 1)
