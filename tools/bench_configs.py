@@ -100,24 +100,25 @@ if "warm" in which:
 if "chain" in which:
     solve_cfg("chain", 1.0, 20_000, 1_000)
     solve_cfg("chain", 0.25, 100_000, 4_000)
-if "aircraft_sim" in which:
-    # BASELINE config 3: Monte-Carlo closed loop, r = [0.1, 0], d = 0, T = 40 (mpc_examples.jl:206)
-    mpc = util.controller("aircraft"); qp = mpqp.mpc2mpqp(mpc)
+
+
+def sim_cfg(name, scale, N, T, rvec, label):
+    mpc = util.controller(name); qp = mpqp.mpc2mpqp(mpc)
     g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
     nx, nr, nd, nup = mpc.parameter_dims()
-    N, T = 1_000_000, 40
-    lo, hi = util.theta_range("aircraft", 0.25)
+    lo, hi = util.theta_range(name, scale)
     X0 = rand_theta(lo[:nx], hi[:nx], N)
-    R = torch.tensor([0.1, 0.0], dtype=torch.float64, device=dev).repeat(N, 1).contiguous()
+    R = torch.tensor(rvec, dtype=torch.float64, device=dev).repeat(N, 1).contiguous()
     D = torch.zeros((N, nd), dtype=torch.float64, device=dev)
-    Xe = torch.empty((N, nx), dtype=torch.float64, device=dev); Ul = torch.empty((N, 2), dtype=torch.float64, device=dev)
+    Xe = torch.empty((N, nx), dtype=torch.float64, device=dev); Ul = torch.empty((N, mpc.nu), dtype=torch.float64, device=dev)
     fl = torch.empty(N, dtype=torch.int32, device=dev); it = torch.empty(N, dtype=torch.int32, device=dev)
     L = lmpc_b200.lib()
-    Fm, Gm, Gdm = [np.asfortranarray(a) for a in (mpc.F, mpc.G, mpc.Gd)]
+    Fm, Gm = np.asfortranarray(mpc.F), np.asfortranarray(mpc.G)
+    Gdm = np.asfortranarray(mpc.Gd) if nd else None
     for warm in (1, 0):
         def run(s=None):
-            rc = L.lmpc_gpu_simulate_batch(g._h, Fm.ctypes.data, Gm.ctypes.data, Gdm.ctypes.data, nx, nr, nd, nup,
-                                           X0.data_ptr(), R.data_ptr(), D.data_ptr(), None, N, T, warm,
+            rc = L.lmpc_gpu_simulate_batch(g._h, Fm.ctypes.data, Gm.ctypes.data, (Gdm.ctypes.data if nd else None), nx, nr, nd, nup,
+                                           X0.data_ptr(), R.data_ptr(), (D.data_ptr() if nd else None), None, N, T, warm,
                                            Xe.data_ptr(), Ul.data_ptr(), None, fl.data_ptr(), it.data_ptr())
             assert rc == 0
         run(); torch.cuda.synchronize()
@@ -126,16 +127,23 @@ if "aircraft_sim" in which:
         P = util.oracle_from_constants(qp, mpc.nu, cst, soft_weight=mpc.soft_weight)
         ncpu = 20000
         t1 = time.perf_counter()
-        ref = P.simulate_batch(mpc.F, mpc.G, mpc.Gd, X0[:ncpu].cpu().numpy().T, R[:ncpu].cpu().numpy().T,
-                               D[:ncpu].cpu().numpy().T, None, T, nr, nd, nup, warm=bool(warm))
+        ref = P.simulate_batch(mpc.F, mpc.G, mpc.Gd if nd else None, X0[:ncpu].cpu().numpy().T, R[:ncpu].cpu().numpy().T,
+                               (D[:ncpu].cpu().numpy().T if nd else None), None, T, nr, nd, nup, warm=bool(warm))
         dc = time.perf_counter() - t1
         same = bool(np.array_equal(Xe[:ncpu].cpu().numpy().T, ref["Xend"]) and np.array_equal(fl[:ncpu].cpu().numpy(), ref["flag"]))
         flags = {int(k): int(v) for k, v in zip(*np.unique(fl.cpu().numpy(), return_counts=True))}
-        print(json.dumps({"config": "aircraft_closed_loop", "warm_start": warm, "trajectories": N, "steps": T, "s": dt,
+        print(json.dumps({"config": label, "warm_start": warm, "trajectories": N, "steps": T, "s": dt,
                           "trajectories_per_s": N / dt, "solves_per_s": N * T / dt,
                           "mean_iters_per_solve": float(it.float().mean()) / T, "worst_flags": flags,
                           "cpu_port_solves_per_s": ncpu * T / dc, "cpu_cores": ldp.num_threads(), "cpu_sample": ncpu,
                           "bit_identical_to_oracle_on_sample": same}), flush=True)
+
+if "aircraft_sim" in which:
+    # BASELINE config 3: Monte-Carlo closed loop, r = [0.1, 0], d = 0, T = 40 (mpc_examples.jl:206)
+    sim_cfg("aircraft", 0.25, 1_000_000, 40, [0.1, 0.0], "aircraft_closed_loop")
+if "invpend_sim" in which:
+    # the README's own closed loop (README.md:55-60) as a Monte-Carlo batch: 100 steps = 1 s
+    sim_cfg("invpend", 0.25, 2_000_000, 100, [0.0, 0.0], "invpend_closed_loop")
 if "explicit" in which:
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "invpend_explicit.npz"))
     ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
