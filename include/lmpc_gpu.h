@@ -56,6 +56,12 @@ extern "C" {
 #define LMPC_KERNEL_WARP 2
 #define LMPC_KERNEL_CTA 3
 
+/* Threading.  A handle's problem data never changes after create, so any number of host threads
+ * may use one handle: the *_async entry points (device pointers, caller's stream) run concurrently;
+ * calls that take HOST buffers share the handle's staging buffers and are serialised by a mutex
+ * inside the handle (use one handle per thread, or lmpc_gpu_create_multi, to overlap them).
+ * lmpc_gpu_last_error() is thread-local.  (The reference's workspace and mpc.uprev are mutated
+ * in place and not re-entrant at all: SURVEY 8b "Threading".) */
 typedef struct lmpc_handle lmpc_handle;   /* one implicit controller on one GPU */
 typedef struct lmpc_bst lmpc_bst;         /* one explicit controller (search tree) on one GPU */
 

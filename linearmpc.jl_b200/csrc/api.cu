@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -131,6 +132,7 @@ struct lmpc_handle {
   cudaStream_t stream = nullptr;
   Slot slots[kSlots];
   DevBuf dyn;   // F, G, Gd for simulate
+  std::mutex mu;   // host-buffer calls share the staging slots / dyn: one at a time per handle
 };
 
 struct lmpc_bst {
@@ -139,6 +141,7 @@ struct lmpc_bst {
   double *d_blk = nullptr;
   cudaStream_t stream = nullptr;
   Slot slots[kSlots];
+  std::mutex mu;
 };
 
 extern "C" {
@@ -342,6 +345,7 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
                                const int *stride, int nseg, int64_t N, double *U, int ustride,
                                int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al,
                                bool warm = false) {
+  std::lock_guard<std::mutex> lock(h->mu);
   const LdpLayout &l = h->lay;
   const int words = (l.m + 63) / 64;
   bool stage = is_pageable(U) || is_pageable(flag);
@@ -513,6 +517,7 @@ int lmpc_gpu_simulate_batch_traj(lmpc_handle *h, const double *F, const double *
   if (nx + nr + nd + nuprev != l.nth || nuprev > l.nu || (nd > 0 && !Gd))
     return set_err(LMPC_E_INVALID, "simulate_batch: nx + nr + nd + nuprev must equal nth%s");
   if (N == 0) return 0;
+  std::lock_guard<std::mutex> lock(h->mu);
   CUDA_OK(cudaSetDevice(h->device));
   const int nu = l.nu;
   // dynamics to row-major on the device
@@ -687,6 +692,7 @@ int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double 
     CUDA_OK(cudaStreamSynchronize(t->stream));
     return 0;
   }
+  std::lock_guard<std::mutex> lock(t->mu);
   const int nth = t->dev.nth, nu = t->dev.nu;
   for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
     const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;

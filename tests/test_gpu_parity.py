@@ -367,3 +367,24 @@ def test_warm_start_on_device_buffers(lmpc):
         X = X @ mpc.F.T + u @ mpc.G.T
         uprev = u[:, :nup]
     assert it_w < it_c
+
+
+def test_one_handle_many_host_threads(lmpc):
+    """Host-buffer calls on one handle from several threads (serialised inside the handle) and
+    device-pointer calls on separate streams: every caller gets its own, correct answer."""
+    import threading
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    lo, hi = mpqp.invpend_range(1.0)
+    Ths = [mpqp.sample_theta(lo, hi, 300000 + 1000 * i, seed=40 + i) for i in range(6)]
+    outs = [None] * len(Ths)
+
+    def work(i):
+        outs[i] = g.solve(Ths[i])
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(Ths))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i, Th in enumerate(Ths):
+        ref = P.solve_batch(Th[:, :20000])
+        sub = {k: (v[:, :20000] if k == "U" else v[:20000]) for k, v in outs[i].items()}
+        assert_parity(sub, ref)
+        assert np.all(outs[i]["exitflag"] >= 1)
