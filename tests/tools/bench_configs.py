@@ -2,8 +2,8 @@
 masses, 5: explicit evaluate) plus AFTI-16 single solves.  One JSON line per config on stdout.
 Device-resident inputs, CUDA events on the launching stream, CPU oracle port beside each."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np, torch
 import lmpc_b200, util
 from oracle import mpqp, ldp
@@ -145,7 +145,7 @@ if "invpend_sim" in which:
     # the README's own closed loop (README.md:55-60) as a Monte-Carlo batch: 100 steps = 1 s
     sim_cfg("invpend", 0.25, 2_000_000, 100, [0.0, 0.0], "invpend_closed_loop")
 if "explicit" in which:
-    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "invpend_explicit.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
     ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
     B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
     N = 100_000_000

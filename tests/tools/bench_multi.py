@@ -1,6 +1,6 @@
 """Single-process multi-GPU host-buffer throughput (lmpc_gpu_solve_batch_multi).
 
-python tools/bench_multi.py [N_per_gpu]     -> one JSON line per device count 1..visible."""
+python tests/tools/bench_multi.py [N_per_gpu]     -> one JSON line per device count 1..visible."""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import lmpc_b200 as lmpc  # noqa: E402
 from bench import product_model, theta_range, SEED  # noqa: E402
 from oracle import mpqp  # noqa: E402  (theta sampler only)

@@ -1,6 +1,6 @@
 """Scratch GPU probe: smoke + kernel-only throughput of the invpend batch."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import lmpc_b200
 from oracle import mpqp

@@ -1,7 +1,7 @@
-"""Launches one kernel family a few times so ncu can capture it:  python tools/prof_driver.py box|warp|cta|bst"""
+"""Launches one kernel family a few times so ncu can capture it:  python tests/tools/prof_driver.py box|warp|cta|bst"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np, torch
 import lmpc_b200, util
 from oracle import mpqp
@@ -12,7 +12,7 @@ def rand_theta(lo, hi, N):
     T = torch.rand((N, len(lo)), dtype=torch.float64, device=dev, generator=gen)
     return T * torch.tensor(hi - lo, device=dev) + torch.tensor(lo, device=dev)
 if which == "bst":
-    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "invpend_explicit.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
     ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
     N = 20_000_000
     Th = rand_theta(z["lo"], z["hi"], N); U = torch.empty((N, 1), dtype=torch.float64, device=dev)

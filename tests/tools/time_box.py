@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, lmpc_b200
 from oracle import mpqp
 mpc = mpqp.invpend(); qp = mpqp.mpc2mpqp(mpc)
