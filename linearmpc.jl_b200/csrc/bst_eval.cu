@@ -28,25 +28,6 @@ struct BstLayout {
 // column-major Theta) into its own shared-memory slot with ONE TMA bulk copy, issued a whole tree
 // walk ahead; lanes then read their rows conflict-free.  This takes the theta traffic off the
 // L1TEX path that the table gathers saturate.
-LMPC_DEVINL void tile_issue(uint64_t *bar, double *dst, const double *src, uint32_t bytes) {
-  const uint32_t b = smem_u32(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
-}
-LMPC_DEVINL void tile_wait(uint64_t *bar, uint32_t parity) {
-  const uint32_t b = smem_u32(bar);
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(b), "r"(parity) : "memory");
-  }
-}
-
 template <int NTH, bool SMEM, bool PACKED>
 __global__ void __launch_bounds__(K4_BLOCK, 1)
 bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int has_clip,

@@ -228,7 +228,7 @@ template <int N, int NU, int MINB>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
                const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-               SolveOut out) {
+               SolveOut out, int use_tiles) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
@@ -237,28 +237,61 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
   constexpr int NP = BoxPad<N>::NP;
   double *Mp = smem + ((lay.total + 1) & ~1);
   for (int i = threadIdx.x; i < N * NP; i += KB_BLOCK) Mp[i] = (i % NP < N) ? cv.M[(i / NP) * N + i % NP] : 0.0;
+  // theta tiles: when Theta is one contiguous nth x N block, each warp streams its next 32
+  // parameters into its own slot with one TMA bulk copy while it is still iterating on the
+  // current ones (the direct loads at the top of a solve were 15 % of the stall samples)
+  __shared__ __align__(8) uint64_t tbar[KB_BLOCK / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *tile = Mp + N * NP + (size_t)warp * 32 * lay.nth;
+  const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
+  uint32_t tphase = 0;
+  if (use_tiles) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar[warp])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t q0 = (int64_t)blockIdx.x * KB_BLOCK + warp * 32;
+    if (lane == 0 && q0 + 32 <= Ninst) tile_issue(&tbar[warp], tile, th.ptr[0] + q0 * lay.nth, 32u * lay.nth * 8u);
+  }
   __syncthreads();
   const int nth = lay.nth;
   BoxState<N> s;
   for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst;
-       q += (int64_t)gridDim.x * KB_BLOCK) {
+       q += qstride) {
     // ---- mpc_update_parameter + mpc_update_qp + output shift in one pass over theta ----------
     double sh[N], sho[NU];
     SFOR(j, 0, N) sh[j] = 0.0; SEND
     SFOR(i, 0, NU) sho[i] = cv.uoff[i]; SEND
-    int o = 0;
-#pragma unroll 1
-    for (int sg = 0; sg < th.nseg; ++sg) {      // one copy of the loop body for all segments
-      const int len = th.len[sg];
-      const double *src = th.ptr[sg] + q * th.stride[sg];
+    const int64_t qt = q - lane;                 // first instance of this warp's tile (warp-uniform)
+    if (use_tiles && qt + 32 <= Ninst) {
+      tile_wait(&tbar[warp], tphase);
+      tphase ^= 1u;
+      const double *src = tile + lane * nth;     // stride nth doubles: conflict-free for odd and even nth alike
 #pragma unroll KB_THU
-      for (int t = 0; t < len; ++t) {
-        const double tv = ld_stream(src + t);
-        const int tt = o + t;
+      for (int tt = 0; tt < nth; ++tt) {
+        const double tv = src[tt];
         SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
         SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
       }
-      o += len;
+      __syncwarp();                              // everybody has read the slot: refill it
+      if (lane == 0 && qt + qstride + 32 <= Ninst)
+        tile_issue(&tbar[warp], tile, th.ptr[0] + (qt + qstride) * nth, 32u * nth * 8u);
+    } else {
+      int o = 0;
+#pragma unroll 1
+      for (int sg = 0; sg < th.nseg; ++sg) {      // one copy of the loop body for all segments
+        const int len = th.len[sg];
+        const double *src = th.ptr[sg] + q * th.stride[sg];
+#pragma unroll KB_THU
+        for (int t = 0; t < len; ++t) {
+          const double tv = ld_stream(src + t);
+          const int tt = o + t;
+          SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
+          SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
+        }
+        o += len;
+      }
     }
     // theta-dependent bounds, once per solve (mpc_update_qp): d_u = du + sh, d_l = dl + sh
     double dU[N], dLo[N];
@@ -406,7 +439,11 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
                const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
   auto kern = ldp_box_kernel<N, NU, MINB>;
-  const size_t smem = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
+  size_t smem = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
+  // one 32-theta slot per warp when Theta is a single contiguous, 16-byte aligned block
+  const int use_tiles = th.nseg == 1 && th.len[0] == lay.nth && th.stride[0] == lay.nth &&
+                        (reinterpret_cast<uintptr_t>(th.ptr[0]) & 15u) == 0 && Ninst >= 32;
+  if (use_tiles) smem += (size_t)KB_BLOCK * lay.nth * sizeof(double);
   BoxConst<N, NU> bc;
   for (int i = 0; i < N * N; ++i) bc.M[i] = hblk[lay.oM + i];
   for (int i = 0; i < N; ++i) { bc.du[i] = hblk[lay.odu + i]; bc.dl[i] = hblk[lay.odl + i]; }
@@ -419,7 +456,7 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   int64_t blocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   const int64_t cap = (int64_t)sm_count * per_sm;   // persistent: whole resident waves over the SMs
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out);
+  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out, use_tiles);
   return (int)cudaGetLastError();
 }
 

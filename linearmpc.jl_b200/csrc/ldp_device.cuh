@@ -53,6 +53,26 @@ LMPC_DEVINL void stage_constants_tma(double *dst_smem, const double *src_gmem, i
   }
 }
 
+// ---- per-warp TMA tiles (theta prefetch): one mbarrier per warp, one bulk copy per tile -------
+LMPC_DEVINL void tile_issue(uint64_t *bar, double *dst, const double *src, uint32_t bytes) {
+  const uint32_t b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+LMPC_DEVINL void tile_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t b = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(b), "r"(parity) : "memory");
+  }
+}
+
 // typed view of the constant block (pointers into shared memory)
 struct ConstView {
   const double *M, *MT, *G, *Dth, *du, *dl, *Rinv, *Uth, *uoff;
