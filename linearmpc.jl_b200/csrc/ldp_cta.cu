@@ -60,7 +60,13 @@ struct BigQp {
   bool sing;
 };
 
-struct BigCtx {
+// SQ_: the warp's L tile is a square cap x LS array indexed by position (rows hold exact zeros on
+// and above the diagonal, as in ldp_warp.cu) instead of the packed lower triangle; chosen by the
+// launcher when the square tile still leaves a full set of warps per CTA.
+template <bool SQ_>
+struct BigCtxT {
+  static constexpr bool SQ = SQ_;
+  int LS;                            // SQ: row stride of the tile (odd)
   const double *M, *MT, *G;          // global (L2) copies
   ConstView cv;                      // shared-memory copies of the small sections
   const LdpLayout *lay;
@@ -73,6 +79,7 @@ struct BigCtx {
   unsigned char *inwsb;   // CTA mode: m flags "row is in the working set" (else null)
   int lane;
 };
+using BigCtx = BigCtxT<false>;
 
 #define PIDX(i, c) ((size_t)(i) * ((i)-1) / 2 + (c))
 #define TFOR(t) _Pragma("unroll") for (int t = 0; t < T; ++t)
@@ -98,8 +105,24 @@ LMPC_DEVINL int bcast_pos_i(const int (&v)[T], int j) {
 }
 
 // z <- L^-1 z on positions [0, kk): column sweep, blocked by tile so register indices are static
-template <int T>
-LMPC_DEVINL void sweep_fwd(const BigCtx &c, double (&z)[T], int kk) {
+template <int T, class C>
+LMPC_DEVINL void sweep_fwd(const C &c, double (&z)[T], int kk) {
+  if constexpr (C::SQ) {
+    // unpredicated: rows at or above the diagonal multiply by stored zeros; idle positions re-read row 0
+    const double *rowp[T];
+    TFOR(t) { const int i = c.lane + 32 * t; rowp[t] = c.Lw + (size_t)(i < kk ? i : 0) * c.LS; }
+#pragma unroll
+    for (int tt = 0; tt < T; ++tt) {
+      const int jend = min(32, kk - 1 - 32 * tt);
+#pragma unroll 4
+      for (int jj = 0; jj < jend; ++jj) {
+        const double zj = shfl_d(z[tt], jj);
+#pragma unroll
+        for (int t = tt; t < T; ++t) z[t] = fma(-rowp[t][32 * tt + jj], zj, z[t]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int tt = 0; tt < T; ++tt) {
     const int jend = min(32, kk - 1 - 32 * tt);
@@ -115,8 +138,25 @@ LMPC_DEVINL void sweep_fwd(const BigCtx &c, double (&z)[T], int kk) {
   }
 }
 // x <- L^-T x on positions [0, kk), descending
-template <int T>
-LMPC_DEVINL void sweep_bwd(const BigCtx &c, double (&x)[T], int kk) {
+template <int T, class C>
+LMPC_DEVINL void sweep_bwd(const C &c, double (&x)[T], int kk) {
+  if constexpr (C::SQ) {
+    const double *colp[T];
+    TFOR(t) { const int i = c.lane + 32 * t; colp[t] = c.Lw + (i < c.LS ? i : c.LS - 1); }
+#pragma unroll
+    for (int tt = T - 1; tt >= 0; --tt) {
+      const int jhi = min(31, kk - 1 - 32 * tt);
+#pragma unroll 4
+      for (int jj = jhi; jj >= 0; --jj) {
+        const int j = 32 * tt + jj;
+        if (j == 0) break;
+        const double xj = shfl_d(x[tt], jj);
+#pragma unroll
+        for (int t = 0; t <= tt; ++t) x[t] = fma(-colp[t][(size_t)j * c.LS], xj, x[t]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int tt = T - 1; tt >= 0; --tt) {
     const int jhi = min(31, kk - 1 - 32 * tt);
@@ -134,8 +174,8 @@ LMPC_DEVINL void sweep_bwd(const BigCtx &c, double (&x)[T], int kk) {
 }
 
 // canonical lane sum of a[i] * b[i] over positions i < len (element i on lane i mod 32)
-template <int T>
-LMPC_DEVINL double lanesum_pos(const BigCtx &c, const double (&a)[T], const double (&b)[T], int len) {
+template <int T, class C>
+LMPC_DEVINL double lanesum_pos(const C &c, const double (&a)[T], const double (&b)[T], int len) {
   double s = (c.lane < len) ? __dmul_rn(a[0], b[0]) : 0.0;
 #pragma unroll
   for (int t = 1; t < T; ++t)
@@ -144,8 +184,8 @@ LMPC_DEVINL double lanesum_pos(const BigCtx &c, const double (&a)[T], const doub
 }
 
 // append row j (oracle: ldl_add)
-template <int T>
-LMPC_DEVINL void bq_add(const BigCtx &c, BigQp<T> &s, int j, bool lower, double dval) {
+template <int T, class C>
+LMPC_DEVINL void bq_add(const C &c, BigQp<T> &s, int j, bool lower, double dval) {
   const int m = c.lay->m, k = s.k, lane = c.lane;
   const double *g = c.G + (size_t)j * m;
   const int sj = c.cv.sense[j];
@@ -161,7 +201,8 @@ LMPC_DEVINL void bq_add(const BigCtx &c, BigQp<T> &s, int j, bool lower, double 
   const double dinv = sing ? 0.0 : 1.0 / dnew;
   TFOR(t) {
     const int i = lane + 32 * t;
-    if (i < k) c.Lw[PIDX(k, i)] = l[t];
+    if constexpr (C::SQ) { if (i < c.LS) c.Lw[(size_t)k * c.LS + i] = (i < k) ? l[t] : 0.0; }   // whole row, zeros from the diagonal on
+    else if (i < k) c.Lw[PIDX(k, i)] = l[t];
     if (i == k) {
       s.D[t] = dnew; s.Dinv[t] = dinv; s.lam[t] = 0.0; s.dW[t] = dval; s.row[t] = j;
       const unsigned bit = 1u << t;
@@ -179,8 +220,8 @@ LMPC_DEVINL void bq_add(const BigCtx &c, BigQp<T> &s, int j, bool lower, double 
 }
 
 // take back a trial add of row j (warm start from masks: the row would have been singular)
-template <int T>
-LMPC_DEVINL void bq_undo_add(const BigCtx &c, BigQp<T> &s, int j) {
+template <int T, class C>
+LMPC_DEVINL void bq_undo_add(const C &c, BigQp<T> &s, int j) {
   s.k -= 1;
   if ((j & 31) == c.lane) s.inws &= ~(1u << (j >> 5));
   if (c.inwsb && c.lane == 0) c.inwsb[j] = 0;
@@ -220,13 +261,74 @@ LMPC_DEVINL unsigned shift_down_bits(unsigned bits, int lane, int r, int k) {
 }
 
 // delete position r (oracle: ldl_remove): packed rows are physically shifted, as in the oracle
-template <int T>
-LMPC_DEVINL void bq_remove(const BigCtx &c, BigQp<T> &s, int r) {
+template <int T, class C>
+LMPC_DEVINL void bq_remove(const C &c, BigQp<T> &s, int r) {
   const int lane = c.lane;
   int k = s.k;
   double alpha = bcast_pos<T>(s.D, r);
   const int rrow = bcast_pos_i<T>(s.row, r);
   double wv[T];
+  if constexpr (C::SQ) {
+    // square tile (see ldp_warp.cu: wq_remove): positions above r move down one, L moves up a
+    // row and, right of r, a column while the rank-1 update rewrites it; zeros on and above the
+    // diagonal are never touched
+    const int LS = c.LS;
+    TFOR(t) { const int i = lane + 32 * t; wv[t] = (i > r && i < k) ? c.Lw[(size_t)i * LS + r] : 0.0; }
+    if ((rrow & 31) == lane) s.inws &= ~(1u << (rrow >> 5));
+    if (c.inwsb && lane == 0) c.inwsb[rrow] = 0;
+    shift_down<T>(s.D, lane, r, k); shift_down<T>(s.Dinv, lane, r, k); shift_down<T>(s.lam, lane, r, k);
+    shift_down<T>(s.dW, lane, r, k); shift_down<T>(wv, lane, r, k); shift_down_i<T>(s.row, lane, r, k);
+    s.low = shift_down_bits<T>(s.low, lane, r, k);
+    s.imm = shift_down_bits<T>(s.imm, lane, r, k);
+    s.soft = shift_down_bits<T>(s.soft, lane, r, k);
+    k -= 1;
+    TFOR(t) { const int i = lane + 32 * t; if (i >= r && i < k) c.roww[i] = s.row[t]; }
+#pragma unroll 1
+    for (int cc = 0; cc < r; ++cc) {           // columns left of r: same values, one row up
+      double v[T];
+      TFOR(t) { const int i = lane + 32 * t; v[t] = (i >= r && i < k) ? c.Lw[(size_t)(i + 1) * LS + cc] : 0.0; }
+      __syncwarp();
+      TFOR(t) { const int i = lane + 32 * t; if (i >= r && i < k) c.Lw[(size_t)i * LS + cc] = v[t]; }
+    }
+    bool sing = false;
+#pragma unroll
+    for (int tt = 0; tt < T; ++tt) {
+#pragma unroll 1
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = 32 * tt + jj;
+        if (j < r) continue;
+        if (j >= k) break;
+        const double pj = shfl_d(wv[tt], jj);
+        const double Dj = shfl_d(s.D[tt], jj);
+        const double tq = alpha * pj;
+        double dbar = fma(tq, pj, Dj);
+        double rinv = 1.0 / dbar;
+        const double beta = tq * rinv;
+        alpha = (Dj * alpha) * rinv;
+        if (j == k - 1 && !(dbar >= c.st->zero_tol)) { sing = true; dbar = 0.0; rinv = 0.0; }
+        if (lane == jj) { s.D[tt] = dbar; s.Dinv[tt] = rinv; }
+        double lij[T];
+#pragma unroll
+        for (int t = tt; t < T; ++t) {           // new L[i][j] from old L[i+1][j+1]
+          const int i = lane + 32 * t;
+          lij[t] = (i > j && i < k) ? c.Lw[(size_t)(i + 1) * LS + j + 1] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = tt; t < T; ++t) {
+          const int i = lane + 32 * t;
+          if (i > j && i < k) {
+            wv[t] = fma(-pj, lij[t], wv[t]);
+            c.Lw[(size_t)i * LS + j] = fma(beta, wv[t], lij[t]);
+          }
+        }
+      }
+    }
+    s.k = k;
+    s.sing = sing;
+    __syncwarp();
+    return;
+  }
   TFOR(t) { const int i = lane + 32 * t; wv[t] = (i > r && i < k) ? c.Lw[PIDX(i, r)] : 0.0; }
   if ((rrow & 31) == lane) s.inws &= ~(1u << (rrow >> 5));
   if (c.inwsb && lane == 0) c.inwsb[rrow] = 0;
@@ -279,8 +381,8 @@ LMPC_DEVINL void bq_remove(const BigCtx &c, BigQp<T> &s, int r) {
 }
 
 // lowest position holding the minimum of a[] (NaN-free), or -1 when all +inf
-template <int T>
-LMPC_DEVINL int argmin_first(const BigCtx &c, const double (&a)[T], double &amin) {
+template <int T, class C>
+LMPC_DEVINL int argmin_first(const C &c, const double (&a)[T], double &amin) {
   double mine = CUDART_INF;
   TFOR(t) mine = (a[t] < mine) ? a[t] : mine;
   amin = bfly_min(mine);
@@ -292,8 +394,8 @@ LMPC_DEVINL int argmin_first(const BigCtx &c, const double (&a)[T], double &amin
   return pos == (1 << 30) ? -1 : pos;
 }
 
-template <int T>
-LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T], double (&u)[T], int &iters) {
+template <int T, class C>
+LMPC_DEVINL int bq_loop(const C &c, BigQp<T> &s, const double (&sh)[2 * T], double (&u)[T], int &iters) {
   const LdpLayout &lay = *c.lay;
   const LdpSettings &st = *c.st;
   const int lane = c.lane, n = lay.n, m = lay.m, mp = lay.mp;
@@ -400,7 +502,7 @@ LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T],
         lastlow = bcast_pos_i<T>(lowv, kk) != 0;
       }
       double p[T];
-      TFOR(t) { const int i = lane + 32 * t; p[t] = (i < kk) ? -c.Lw[PIDX(kk, i)] : 0.0; }
+      TFOR(t) { const int i = lane + 32 * t; p[t] = (i < kk) ? -(C::SQ ? c.Lw[(size_t)kk * c.LS + i] : c.Lw[PIDX(kk, i)]) : 0.0; }
       sweep_bwd<T>(c, p, kk);
       TFOR(t) {
         const int i = lane + 32 * t;
@@ -422,8 +524,8 @@ LMPC_DEVINL int bq_loop(const BigCtx &c, BigQp<T> &s, const double (&sh)[2 * T],
   return flag;
 }
 
-template <int T>
-LMPC_DEVINL int bq_solve(const BigCtx &c, BigQp<T> &s, double (&u)[T], int &iters, bool cold = true,
+template <int T, class C>
+LMPC_DEVINL int bq_solve(const C &c, BigQp<T> &s, double (&u)[T], int &iters, bool cold = true,
                          const uint64_t *wsu = nullptr, const uint64_t *wsl = nullptr) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
@@ -488,7 +590,7 @@ struct K3Geom { int warps; size_t per_warp; size_t small_total; size_t smem; };
 // they are contiguous at the tail of the block starting at oDth
 LMPC_DEVINL int small_off(const LdpLayout &lay) { return lay.oDth; }
 
-template <int T>
+template <int T, bool SQ>
 __global__ void __launch_bounds__(256)
 ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out,
@@ -497,7 +599,7 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   __shared__ __align__(8) uint64_t mbar;
   const int soff = small_off(lay);
   stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
-  BigCtx c;
+  BigCtxT<SQ> c;
   c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
   const double *sb = smem - soff;    // so that section offsets stay valid
   c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
@@ -509,7 +611,8 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   c.lane = threadIdx.x & 31;
   double *w = smem + (lay.total - soff) + (size_t)warp * per_warp_doubles;
   const int cap = lay.cap;
-  c.Lw = w; w += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+  c.LS = cap | 1;
+  c.Lw = w; w += SQ ? (((size_t)cap * c.LS + 1) & ~(size_t)1) : (((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1);
   c.uw = w; w += (lay.n + 1) & ~1;
   c.thw = w; w += (lay.nth + 1) & ~1;
   c.lamw = w; w += (cap + 1) & ~1;
@@ -565,7 +668,7 @@ ldp_big_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
 }
 
 // closed loop in warp mode: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
-template <int T>
+template <int T, bool SQ>
 __global__ void __launch_bounds__(256)
 ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                    const double *__restrict__ cblk, int64_t Ninst, SimDesc sd, int32_t *flagout,
@@ -574,7 +677,7 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
   __shared__ __align__(8) uint64_t mbar;
   const int soff = small_off(lay);
   stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
-  BigCtx c;
+  BigCtxT<SQ> c;
   c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
   const double *sb = smem - soff;
   c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
@@ -586,7 +689,8 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
   c.lane = threadIdx.x & 31;
   double *w = smem + (lay.total - soff) + (size_t)warp * per_warp_doubles;
   const int cap = lay.cap;
-  c.Lw = w; w += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+  c.LS = cap | 1;
+  c.Lw = w; w += SQ ? (((size_t)cap * c.LS + 1) & ~(size_t)1) : (((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1);
   c.uw = w; w += (lay.n + 1) & ~1;
   c.thw = w; w += (lay.nth + 1) & ~1;
   c.lamw = w; w += (cap + 1) & ~1;
@@ -682,6 +786,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   const int soff = small_off(lay);
   stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
   BigCtx c;
+  c.LS = 0;
   c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
   const double *sb = smem - soff;
   c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
@@ -981,10 +1086,11 @@ int launch_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   return (int)cudaGetLastError();
 }
 
-K3Geom k3_geom(const LdpLayout &lay, int extra = 0) {
+K3Geom k3_geom(const LdpLayout &lay, int extra = 0, bool sq = false) {
   K3Geom g;
   const size_t cap = lay.cap;
-  size_t pw = ((cap * (cap - 1) / 2 + 1) & ~(size_t)1) + ((lay.n + 1) & ~1) + ((lay.nth + 1) & ~1) +
+  const size_t ltile = sq ? ((cap * (cap | 1) + 1) & ~(size_t)1) : ((cap * (cap - 1) / 2 + 1) & ~(size_t)1);
+  size_t pw = ltile + ((lay.n + 1) & ~1) + ((lay.nth + 1) & ~1) +
               ((cap + 1) & ~1) + ((cap + 1) / 2 + 1) + extra;
   pw = (pw + 1) & ~(size_t)1;
   g.per_warp = pw;
@@ -998,11 +1104,19 @@ K3Geom k3_geom(const LdpLayout &lay, int extra = 0) {
   return g;
 }
 
-template <int T>
+// the square (unpredicated-sweep) tile is used when it still leaves at least 6 warps per CTA
+inline bool k3_square(const LdpLayout &lay, int extra) {
+  return lay.cap <= 64 && k3_geom(lay, extra, true).warps >= 6;
+}
+
+template <int T, bool SQ = false>
 int launch_big(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
                int64_t N, const SolveOut &out, int sm_count, cudaStream_t s) {
-  const K3Geom g = k3_geom(lay);
-  auto kern = ldp_big_kernel<T>;
+  if constexpr (T == 2 && !SQ) {
+    if (k3_square(lay, 0)) return launch_big<T, true>(lay, st, cblk, th, N, out, sm_count, s);
+  }
+  const K3Geom g = k3_geom(lay, 0, SQ);
+  auto kern = ldp_big_kernel<T, SQ>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 0;
@@ -1014,12 +1128,16 @@ int launch_big(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   return (int)cudaGetLastError();
 }
 
-template <int T>
+template <int T, bool SQ = false>
 int launch_big_sim(const LdpLayout &lay, const LdpSettings &st, const double *cblk, int64_t N,
                    const SolveOut &out, const SimDesc &sim, int sm_count, cudaStream_t s) {
-  const K3Geom g = k3_geom(lay, ((sim.nx + 1) & ~1) + ((lay.nu + 1) & ~1));
+  const int extra = ((sim.nx + 1) & ~1) + ((lay.nu + 1) & ~1);
+  if constexpr (T == 2 && !SQ) {
+    if (k3_square(lay, extra)) return launch_big_sim<T, true>(lay, st, cblk, N, out, sim, sm_count, s);
+  }
+  const K3Geom g = k3_geom(lay, extra, SQ);
   if (g.warps < 1) return (int)cudaErrorNotSupported;
-  auto kern = ldp_big_sim_kernel<T>;
+  auto kern = ldp_big_sim_kernel<T, SQ>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 0;
