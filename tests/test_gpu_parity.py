@@ -388,3 +388,33 @@ def test_one_handle_many_host_threads(lmpc):
         sub = {k: (v[:, :20000] if k == "U" else v[:20000]) for k, v in outs[i].items()}
         assert_parity(sub, ref)
         assert np.all(outs[i]["exitflag"] >= 1)
+
+
+@pytest.mark.parametrize("name,kernel", [("invpend", 0), ("invpend", 2), ("dint_hard", 0), ("aircraft", 0),
+                                         ("aircraft_ksall", 0), ("chain_small", 0), ("chain", 0)])
+@pytest.mark.parametrize("over", [dict(iter_limit=4), dict(iter_limit=7, primal_tol=1e-4),
+                                  dict(primal_tol=1e-3, dual_tol=1e-9, cycle_tol=2, progress_tol=1e-3)])
+def test_non_default_settings_match_oracle(lmpc, name, kernel, over):
+    """lmpc_settings reach the kernels: a tight iteration limit (flag -4 where it bites, on every
+    kernel including the box kernel's specialised first iterations), looser tolerances and a short
+    cycle guard give the oracle's flags, iteration counts, active sets and controls bit for bit."""
+    mpc = util.controller(name)
+    qp = mpqp.mpc2mpqp(mpc)
+    st = lmpc.default_settings(kernel=kernel, **over)
+    g = lmpc.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight, settings=st)
+    cst = g.ldp_constants()
+    cst["senses"] = g.senses
+    P = util.oracle_from_constants(qp, mpc.nu, cst, soft_weight=mpc.soft_weight, **over)
+    lo, hi = util.theta_range(name, 1.0)
+    Th = mpqp.sample_theta(lo, hi, 100 if name == "chain" else 1500, seed=17)
+    ref = P.solve_batch(Th)
+    out = g.solve(Th)
+    assert np.array_equal(out["exitflag"], ref["flag"])
+    assert np.array_equal(out["iters"], ref["iters"])
+    done = ref["flag"] >= 1
+    assert np.array_equal(out["active_upper"][done], ref["act_u"][done])
+    assert np.array_equal(out["active_lower"][done], ref["act_l"][done])
+    assert np.array_equal(np.asarray(out["U"])[:, done], ref["U"][:, done])
+    if "iter_limit" in over and over["iter_limit"] == 4 and name != "dint_hard":
+        assert np.any(ref["flag"] == -4)
+    g.close()
