@@ -195,6 +195,34 @@ int lmpc_gpu_simulate_batch_traj(lmpc_handle *h, const double *F, const double *
                                  double *Xend, double *Ulast, double *Utraj,
                                  int32_t *exitflag, int32_t *iters);
 
+/* Extended closed loop: the scenario trajectories of simulate_batch_traj plus
+ *  - a TRUE PLANT x+ = Ft x + Gt u + Gdt d that may differ from the controller's prediction model
+ *    (scenario.dynamics, src/simulation.jl:39,110); NULL = the model's matrix;
+ *  - the steady-state Kalman observer of src/observer.jl:104-118 run inside the loop exactly as
+ *    src/simulation.jl:92-108 does: estimate = X0 at the start (set_state!), every step
+ *    y = C x + Dd d (+ v_t), correct! with gain K, compute_control on the ESTIMATE, predict! with the
+ *    model; C ny x nx, Dd ny x nd (NULL = 0), K nx x ny column-major; C == NULL: no observer, the
+ *    controller sees the true state;
+ *  - Vtraj ny x T: additive measurement noise shared by all closed loops (what a scenario's
+ *    get_measurement would add), NULL = none.
+ * All matrices are HOST arrays.  Xend returns the TRUE final states, Xhat_end (nullable) the final
+ * estimates.  ext == NULL or all-NULL fields: identical to lmpc_gpu_simulate_batch. */
+typedef struct {
+  const double *Rtraj, *Dtraj;
+  const double *Ft, *Gt, *Gdt;
+  const double *C, *Dd, *K;
+  const double *Vtraj;
+  int32_t ny;
+  double *Xhat_end;
+} lmpc_sim_ext;
+int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                               int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                               const double *X0, const double *R, const double *D, const double *U0,
+                               const lmpc_sim_ext *ext,
+                               int64_t N, int32_t T, int32_t warm_start,
+                               double *Xend, double *Ulast, double *Utraj,
+                               int32_t *exitflag, int32_t *iters);
+
 /* One process, several GPUs (BASELINE north_star: "the batch is sharded by contiguous theta ranges
  * across the 8 B200s of one box with no inter-GPU traffic beyond a final result gather").
  * create_multi builds one replica of the controller per listed device (devices NULL = 0..n-1);

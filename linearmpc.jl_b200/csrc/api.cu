@@ -511,40 +511,86 @@ int lmpc_gpu_simulate_batch_traj(lmpc_handle *h, const double *F, const double *
                                  int64_t N, int32_t T, int32_t warm_start,
                                  double *Xend, double *Ulast, double *Utraj,
                                  int32_t *exitflag, int32_t *iters) {
+  lmpc_sim_ext e;
+  memset(&e, 0, sizeof(e));
+  e.Rtraj = Rtraj; e.Dtraj = Dtraj;
+  return lmpc_gpu_simulate_batch_ex(h, F, G, Gd, nx, nr, nd, nuprev, X0, R, D, U0, &e, N, T, warm_start, Xend,
+                                    Ulast, Utraj, exitflag, iters);
+}
+
+// column-major (rows x cols) host matrix -> row-major, appended to v; returns the offset
+static size_t push_rowmajor(std::vector<double> &v, const double *A, int rows, int cols) {
+  const size_t off = v.size();
+  v.resize(off + (size_t)rows * cols);
+  for (int i = 0; i < rows; ++i)
+    for (int c = 0; c < cols; ++c) v[off + (size_t)i * cols + c] = A[(size_t)c * rows + i];
+  return off;
+}
+
+int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                               int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                               const double *X0, const double *R, const double *D, const double *U0,
+                               const lmpc_sim_ext *ext,
+                               int64_t N, int32_t T, int32_t warm_start,
+                               double *Xend, double *Ulast, double *Utraj,
+                               int32_t *exitflag, int32_t *iters) {
   if (!h || !F || !G || !X0 || !Xend || !Ulast || !exitflag || N < 0 || T < 0)
     return set_err(LMPC_E_INVALID, "lmpc_gpu_simulate_batch: bad argument%s");
   const LdpLayout &l = h->lay;
   if (nx + nr + nd + nuprev != l.nth || nuprev > l.nu || (nd > 0 && !Gd))
     return set_err(LMPC_E_INVALID, "simulate_batch: nx + nr + nd + nuprev must equal nth%s");
+  const double *Rtraj = ext ? ext->Rtraj : nullptr, *Dtraj = ext ? ext->Dtraj : nullptr;
+  const bool observer = ext && ext->C && ext->K;
+  const bool extended = ext && (ext->Ft || ext->Gt || ext->Gdt || observer || ext->Xhat_end);
+  if (ext && (ext->C != nullptr) != (ext->K != nullptr))
+    return set_err(LMPC_E_INVALID, "simulate_batch_ex: an observer needs both C and K%s");
+  if (observer && ext->ny <= 0) return set_err(LMPC_E_INVALID, "simulate_batch_ex: observer with ny <= 0%s");
   if (N == 0) return 0;
   std::lock_guard<std::mutex> lock(h->mu);
   CUDA_OK(cudaSetDevice(h->device));
-  const int nu = l.nu;
-  // dynamics to row-major on the device
-  const size_t ndyn = (size_t)nx * (nx + nu + nd);
-  const size_t nrt = (Rtraj && nr > 0) ? (size_t)nr * T : 0, ndt = (Dtraj && nd > 0) ? (size_t)nd * T : 0;
-  std::vector<double> dynh(ndyn + nrt + ndt);
-  double *Fr = dynh.data(), *Gr = Fr + (size_t)nx * nx, *Gdr = Gr + (size_t)nx * nu;
-  if (nrt) memcpy(dynh.data() + ndyn, Rtraj, nrt * sizeof(double));
-  if (ndt) memcpy(dynh.data() + ndyn + nrt, Dtraj, ndt * sizeof(double));
-  for (int i = 0; i < nx; ++i) {
-    for (int c = 0; c < nx; ++c) Fr[i * nx + c] = F[(size_t)c * nx + i];
-    for (int c = 0; c < nu; ++c) Gr[i * nu + c] = G[(size_t)c * nx + i];
-    for (int c = 0; c < nd; ++c) Gdr[i * nd + c] = Gd[(size_t)c * nx + i];
+  const int nu = l.nu, ny = observer ? ext->ny : 0;
+  // everything the kernels read besides the per-trajectory inputs, row-major, in one device buffer
+  std::vector<double> dynh;
+  const size_t oF = push_rowmajor(dynh, F, nx, nx), oG = push_rowmajor(dynh, G, nx, nu);
+  const size_t oGd = nd > 0 ? push_rowmajor(dynh, Gd, nx, nd) : dynh.size();
+  size_t oR = 0, oD = 0, oFt = oF, oGt = oG, oGdt = oGd, oC = 0, oDd = 0, oK = 0, oV = 0;
+  if (Rtraj && nr > 0) { oR = dynh.size(); dynh.insert(dynh.end(), Rtraj, Rtraj + (size_t)nr * T); }
+  if (Dtraj && nd > 0) { oD = dynh.size(); dynh.insert(dynh.end(), Dtraj, Dtraj + (size_t)nd * T); }
+  if (extended) {
+    if (ext->Ft) oFt = push_rowmajor(dynh, ext->Ft, nx, nx);
+    if (ext->Gt) oGt = push_rowmajor(dynh, ext->Gt, nx, nu);
+    if (ext->Gdt && nd > 0) oGdt = push_rowmajor(dynh, ext->Gdt, nx, nd);
+    if (observer) {
+      oC = push_rowmajor(dynh, ext->C, ny, nx);
+      if (ext->Dd && nd > 0) oDd = push_rowmajor(dynh, ext->Dd, ny, nd);
+      oK = push_rowmajor(dynh, ext->K, nx, ny);
+      if (ext->Vtraj) { oV = dynh.size(); dynh.insert(dynh.end(), ext->Vtraj, ext->Vtraj + (size_t)ny * T); }
+    }
   }
   if (h->dyn.reserve(dynh.size() * sizeof(double))) return LMPC_E_CUDA;
   CUDA_OK(cudaMemcpyAsync(h->dyn.p, dynh.data(), dynh.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  const double *db = (const double *)h->dyn.p;
   SimDesc sd;
   memset(&sd, 0, sizeof(sd));
-  sd.F = (double *)h->dyn.p; sd.G = sd.F + (size_t)nx * nx; sd.Gd = sd.G + (size_t)nx * nu;
+  sd.F = db + oF; sd.G = db + oG; sd.Gd = db + oGd;
   sd.nx = nx; sd.nr = nr; sd.nd = nd; sd.nuprev = nuprev; sd.T = T; sd.warm = warm_start;
-  sd.Rtraj = nrt ? sd.F + ndyn : nullptr;
-  sd.Dtraj = ndt ? sd.F + ndyn + nrt : nullptr;
+  sd.Rtraj = (Rtraj && nr > 0) ? db + oR : nullptr;
+  sd.Dtraj = (Dtraj && nd > 0) ? db + oD : nullptr;
+  if (extended) {
+    sd.ext = 1; sd.ny = ny;
+    sd.Ft = db + oFt; sd.Gt = db + oGt; sd.Gdt = db + oGdt;
+    if (observer) {
+      sd.Cm = db + oC; sd.Kobs = db + oK;
+      sd.Ddm = (ext->Dd && nd > 0) ? db + oDd : nullptr;
+      sd.Vtraj = ext->Vtraj ? db + oV : nullptr;
+    }
+  }
+  double *Xhat = extended ? ext->Xhat_end : nullptr;
   ThetaSegs th;
   memset(&th, 0, sizeof(th));
   if (is_device_ptr(X0)) {
-    sd.X0 = X0; sd.R = R; sd.D = D; sd.U0 = U0; sd.Xend = Xend; sd.Ulast = Ulast; sd.Utraj = Utraj;
+    sd.X0 = X0; sd.R = R; sd.D = D; sd.U0 = U0; sd.Xend = Xend; sd.Ulast = Ulast; sd.Utraj = Utraj; sd.Xhat = Xhat;
     SolveOut o{nullptr, exitflag, iters, nullptr, nullptr};
     int rc = run_kernel(h, th, N, o, &sd, h->stream);
     if (rc) return rc;
@@ -567,15 +613,18 @@ int lmpc_gpu_simulate_batch_traj(lmpc_handle *h, const double *F, const double *
     if (s.aux[0].reserve((size_t)cnt * nx * 8) || s.u.reserve((size_t)cnt * nu * 8) ||
         s.flag.reserve((size_t)cnt * 4) || s.iters.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
     if (Utraj && s.aux[1].reserve((size_t)cnt * nu * T * 8)) return LMPC_E_CUDA;
+    if (Xhat && s.aux[2].reserve((size_t)cnt * nx * 8)) return LMPC_E_CUDA;
     SimDesc d = sd;
     d.X0 = dv[0]; d.R = dv[1]; d.D = dv[2]; d.U0 = dv[3];
     d.Xend = (double *)s.aux[0].p; d.Ulast = (double *)s.u.p; d.Utraj = Utraj ? (double *)s.aux[1].p : nullptr;
+    d.Xhat = Xhat ? (double *)s.aux[2].p : nullptr;
     SolveOut o{nullptr, (int32_t *)s.flag.p, (int32_t *)s.iters.p, nullptr, nullptr};
     int rc = run_kernel(h, th, cnt, o, &d, s.stream);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(Xend + off * nx, d.Xend, (size_t)cnt * nx * 8, cudaMemcpyDeviceToHost, s.stream));
     CUDA_OK(cudaMemcpyAsync(Ulast + off * nu, d.Ulast, (size_t)cnt * nu * 8, cudaMemcpyDeviceToHost, s.stream));
     if (Utraj) CUDA_OK(cudaMemcpyAsync(Utraj + off * nu * T, d.Utraj, (size_t)cnt * nu * T * 8, cudaMemcpyDeviceToHost, s.stream));
+    if (Xhat) CUDA_OK(cudaMemcpyAsync(Xhat + off * nx, d.Xhat, (size_t)cnt * nx * 8, cudaMemcpyDeviceToHost, s.stream));
     CUDA_OK(cudaMemcpyAsync(exitflag + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
     if (iters) CUDA_OK(cudaMemcpyAsync(iters + off, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
   }

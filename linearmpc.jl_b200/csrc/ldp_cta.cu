@@ -698,14 +698,18 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
   c.inwsb = nullptr;
   const int nx = sd.nx, nr = sd.nr, nd = sd.nd, nup = sd.nuprev, nu = lay.nu;
   double *xnw = w; w += (nx + 1) & ~1;
-  double *ucw = w;
+  double *ucw = w; w += (nu + 1) & ~1;
+  const bool ext = sd.ext != 0;
+  const int ny = ext ? sd.ny : 0;
+  double *xsw = w; w += (nx + 1) & ~1;     // ext: true plant state
+  double *ew = w;                          // ext: innovation [ny]
   const int lane = c.lane;
   const int64_t wid = (int64_t)blockIdx.x * warps + warp;
   const int64_t wstride = (int64_t)gridDim.x * warps;
   BigQp<T> s;
   double u[T];
   for (int64_t q = wid; q < Ninst; q += wstride) {
-    for (int i = lane; i < nx; i += 32) c.thw[i] = ld_stream(sd.X0 + q * nx + i);
+    for (int i = lane; i < nx; i += 32) { c.thw[i] = ld_stream(sd.X0 + q * nx + i); if (ext) xsw[i] = c.thw[i]; }
     for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.R ? ld_stream(sd.R + q * nr + i) : 0.0;
     for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.D ? ld_stream(sd.D + q * nd + i) : 0.0;
     for (int i = lane; i < nu; i += 32) ucw[i] = (sd.U0 && i < nup) ? ld_stream(sd.U0 + q * nup + i) : 0.0;
@@ -717,6 +721,31 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
       if (sd.Rtraj) for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.Rtraj[(size_t)t * nr + i];
       if (sd.Dtraj) for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.Dtraj[(size_t)t * nd + i];
       __syncwarp();
+      if (ext) {
+        const double *dk = c.thw + nx + nr;
+        if (sd.Cm) {
+          // y = C x + Dd d + v, innovation against the estimate, correction (observer.jl:114-118)
+          for (int i = lane; i < ny; i += 32) {
+            double y = sd.Vtraj ? sd.Vtraj[(size_t)t * ny + i] : 0.0, yh = 0.0;
+            for (int cc = 0; cc < nx; ++cc) y = fma(sd.Cm[i * nx + cc], xsw[cc], y);
+            if (sd.Ddm) for (int cc = 0; cc < nd; ++cc) y = fma(sd.Ddm[i * nd + cc], dk[cc], y);
+            for (int cc = 0; cc < nx; ++cc) yh = fma(sd.Cm[i * nx + cc], c.thw[cc], yh);
+            if (sd.Ddm) for (int cc = 0; cc < nd; ++cc) yh = fma(sd.Ddm[i * nd + cc], dk[cc], yh);
+            ew[i] = __dsub_rn(y, yh);
+          }
+          __syncwarp();
+          for (int j = lane; j < nx; j += 32) {
+            double acc = c.thw[j];
+            for (int i = 0; i < ny; ++i) acc = fma(sd.Kobs[j * ny + i], ew[i], acc);
+            xnw[j] = acc;
+          }
+          __syncwarp();
+          for (int j = lane; j < nx; j += 32) c.thw[j] = xnw[j];
+        } else {
+          for (int j = lane; j < nx; j += 32) c.thw[j] = xsw[j];      // the controller measures the true state
+        }
+        __syncwarp();
+      }
       int iters;
       const int f = bq_solve<T>(c, s, u, iters, !(sd.warm && t > 0));
       tot += iters;
@@ -746,8 +775,21 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
       __syncwarp();
       for (int i = lane; i < nx; i += 32) c.thw[i] = xnw[i];
       __syncwarp();
+      if (ext) {   // true plant step
+        for (int i = lane; i < nx; i += 32) {
+          double acc = 0.0;
+          for (int cc = 0; cc < nx; ++cc) acc = fma(sd.Ft[i * nx + cc], xsw[cc], acc);
+          for (int cc = 0; cc < nu; ++cc) acc = fma(sd.Gt[i * nu + cc], ucw[cc], acc);
+          for (int cc = 0; cc < nd; ++cc) acc = fma(sd.Gdt[i * nd + cc], c.thw[nx + nr + cc], acc);
+          xnw[i] = acc;
+        }
+        __syncwarp();
+        for (int i = lane; i < nx; i += 32) xsw[i] = xnw[i];
+        __syncwarp();
+      }
     }
-    for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = c.thw[i];
+    if (ext && sd.Xhat) for (int i = lane; i < nx; i += 32) sd.Xhat[q * nx + i] = c.thw[i];
+    for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = ext ? xsw[i] : c.thw[i];
     for (int i = lane; i < nu; i += 32) sd.Ulast[q * nu + i] = ucw[i];
     if (lane == 0) {
       flagout[q] = worst;
@@ -1131,7 +1173,7 @@ int launch_big(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
 template <int T, bool SQ = false>
 int launch_big_sim(const LdpLayout &lay, const LdpSettings &st, const double *cblk, int64_t N,
                    const SolveOut &out, const SimDesc &sim, int sm_count, cudaStream_t s) {
-  const int extra = ((sim.nx + 1) & ~1) + ((lay.nu + 1) & ~1);
+  const int extra = ((sim.nx + 1) & ~1) + ((lay.nu + 1) & ~1) + (sim.ext ? ((sim.nx + 1) & ~1) + ((sim.ny + 1) & ~1) : 0);
   if constexpr (T == 2 && !SQ) {
     if (k3_square(lay, extra)) return launch_big_sim<T, true>(lay, st, cblk, N, out, sim, sm_count, s);
   }

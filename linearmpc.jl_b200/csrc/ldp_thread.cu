@@ -411,12 +411,16 @@ ldp_thread_sim_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ 
   double *shv = thv + (size_t)lay.nth * K1_BLOCK;           // [m][K1_BLOCK]
   double *xnv = shv + (size_t)lay.m * K1_BLOCK;             // [nx][K1_BLOCK]
   double *ucv = xnv + (size_t)sd.nx * K1_BLOCK;             // [nu][K1_BLOCK]
+  double *xsv = ucv + (size_t)lay.nu * K1_BLOCK;            // ext: [nx][K1_BLOCK] true plant state
+  double *ev = xsv + (size_t)sd.nx * K1_BLOCK;              // ext: [ny][K1_BLOCK] innovation
   const int nx = sd.nx, nr = sd.nr, nd = sd.nd, nup = sd.nuprev, nu = lay.nu;
+  const bool ext = sd.ext != 0;
+  const int ny = ext ? sd.ny : 0;
   QpState<N, CAP> s;
   double u[N];
   for (int64_t q = (int64_t)blockIdx.x * K1_BLOCK + threadIdx.x; q < Ninst;
        q += (int64_t)gridDim.x * K1_BLOCK) {
-    for (int i = 0; i < nx; ++i) thv[i * K1_BLOCK] = ld_stream(sd.X0 + q * nx + i);
+    for (int i = 0; i < nx; ++i) { thv[i * K1_BLOCK] = ld_stream(sd.X0 + q * nx + i); if (ext) xsv[i * K1_BLOCK] = thv[i * K1_BLOCK]; }
     for (int i = 0; i < nr; ++i) thv[(nx + i) * K1_BLOCK] = sd.R ? ld_stream(sd.R + q * nr + i) : 0.0;
     for (int i = 0; i < nd; ++i) thv[(nx + nr + i) * K1_BLOCK] = sd.D ? ld_stream(sd.D + q * nd + i) : 0.0;
     for (int i = 0; i < nu; ++i) ucv[i * K1_BLOCK] = (sd.U0 && i < nup) ? ld_stream(sd.U0 + q * nup + i) : 0.0;
@@ -426,6 +430,28 @@ ldp_thread_sim_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ 
       // reference / disturbance of step t (rs[:, k], ds[:, k] of src/simulation.jl:93-104)
       if (sd.Rtraj) for (int i = 0; i < nr; ++i) thv[(nx + i) * K1_BLOCK] = sd.Rtraj[(size_t)t * nr + i];
       if (sd.Dtraj) for (int i = 0; i < nd; ++i) thv[(nx + nr + i) * K1_BLOCK] = sd.Dtraj[(size_t)t * nd + i];
+      if (ext) {
+        const double *dk = thv + (size_t)(nx + nr) * K1_BLOCK;
+        if (sd.Cm) {
+          // y = C x + Dd d + v, innovation against the estimate, correction (observer.jl:114-118)
+          for (int i = 0; i < ny; ++i) {
+            double y = sd.Vtraj ? sd.Vtraj[(size_t)t * ny + i] : 0.0, yh = 0.0;
+            for (int c = 0; c < nx; ++c) y = fma(sd.Cm[i * nx + c], xsv[c * K1_BLOCK], y);
+            if (sd.Ddm) for (int c = 0; c < nd; ++c) y = fma(sd.Ddm[i * nd + c], dk[c * K1_BLOCK], y);
+            for (int c = 0; c < nx; ++c) yh = fma(sd.Cm[i * nx + c], thv[c * K1_BLOCK], yh);
+            if (sd.Ddm) for (int c = 0; c < nd; ++c) yh = fma(sd.Ddm[i * nd + c], dk[c * K1_BLOCK], yh);
+            ev[i * K1_BLOCK] = __dsub_rn(y, yh);
+          }
+          for (int j = 0; j < nx; ++j) {
+            double acc = thv[j * K1_BLOCK];
+            for (int i = 0; i < ny; ++i) acc = fma(sd.Kobs[j * ny + i], ev[i * K1_BLOCK], acc);
+            xnv[j * K1_BLOCK] = acc;
+          }
+          for (int j = 0; j < nx; ++j) thv[j * K1_BLOCK] = xnv[j * K1_BLOCK];
+        } else {
+          for (int j = 0; j < nx; ++j) thv[j * K1_BLOCK] = xsv[j * K1_BLOCK];   // the controller measures the true state
+        }
+      }
       int iters;
       const int f = qp_solve<N, CAP, GENERAL>(s, cv, lay, st, thv, shv, !(sd.warm && t > 0), u, iters);
       tot += iters;
@@ -444,8 +470,19 @@ ldp_thread_sim_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ 
         xnv[i * K1_BLOCK] = acc;
       }
       for (int i = 0; i < nx; ++i) thv[i * K1_BLOCK] = xnv[i * K1_BLOCK];
+      if (ext) {   // true plant step
+        for (int i = 0; i < nx; ++i) {
+          double acc = 0.0;
+          for (int c = 0; c < nx; ++c) acc = fma(sd.Ft[i * nx + c], xsv[c * K1_BLOCK], acc);
+          for (int c = 0; c < nu; ++c) acc = fma(sd.Gt[i * nu + c], ucv[c * K1_BLOCK], acc);
+          for (int c = 0; c < nd; ++c) acc = fma(sd.Gdt[i * nd + c], thv[(nx + nr + c) * K1_BLOCK], acc);
+          xnv[i * K1_BLOCK] = acc;
+        }
+        for (int i = 0; i < nx; ++i) xsv[i * K1_BLOCK] = xnv[i * K1_BLOCK];
+      }
     }
-    for (int i = 0; i < nx; ++i) sd.Xend[q * nx + i] = thv[i * K1_BLOCK];
+    if (ext && sd.Xhat) for (int i = 0; i < nx; ++i) sd.Xhat[q * nx + i] = thv[i * K1_BLOCK];
+    for (int i = 0; i < nx; ++i) sd.Xend[q * nx + i] = ext ? xsv[i * K1_BLOCK] : thv[i * K1_BLOCK];
     for (int i = 0; i < nu; ++i) sd.Ulast[q * nu + i] = ucv[i * K1_BLOCK];
     flagout[q] = worst;
     if (itersout) itersout[q] = tot;
@@ -457,7 +494,7 @@ int launch_inst(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
                 int64_t Ninst, const SolveOut &out, const SimDesc *sim, int sm_count,
                 cudaStream_t stream) {
   size_t smem = ((size_t)lay.total + (size_t)(lay.nth + lay.m) * K1_BLOCK) * sizeof(double);
-  if (sim) smem += (size_t)(sim->nx + lay.nu) * K1_BLOCK * sizeof(double);
+  if (sim) smem += (size_t)(sim->nx + lay.nu + (sim->ext ? sim->nx + sim->ny : 0)) * K1_BLOCK * sizeof(double);
   cudaError_t e;
   int64_t blocks = (Ninst + K1_BLOCK - 1) / K1_BLOCK;
   int per_sm = 0;

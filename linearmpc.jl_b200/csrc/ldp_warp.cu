@@ -457,7 +457,25 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
 }
 
 // closed loop: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
-template <bool EQ>
+// x+ = A x + B u + Bd d for the rows lane, lane + 32, ... (fma chains in index order)
+LMPC_DEVINL void step_rows(const double *A, const double *B, const double *Bd, const double *x, const double *uu,
+                           const double *d, double *out, int nx, int nu, int nd, int lane) {
+  _Pragma("unroll 1")
+  for (int i = lane; i < nx; i += 32) {
+    double acc = 0.0;
+    _Pragma("unroll 2")
+    for (int cc = 0; cc < nx; ++cc) acc = fma(A[i * nx + cc], x[cc], acc);
+    _Pragma("unroll 2")
+    for (int cc = 0; cc < nu; ++cc) acc = fma(B[i * nu + cc], uu[cc], acc);
+    _Pragma("unroll 2")
+    for (int cc = 0; cc < nd; ++cc) acc = fma(Bd[i * nd + cc], d[cc], acc);
+    out[i] = acc;
+  }
+}
+
+// EXT: separate true plant, steady-state observer and measurement noise (lmpc_gpu_simulate_batch_ex);
+// compiled as its own kernel so the plain closed loop keeps its instruction footprint
+template <bool EQ, bool EXT>
 __global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                     const double *__restrict__ cblk,
@@ -466,9 +484,12 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
   const int nx = sd.nx, nr = sd.nr, nd = sd.nd, nup = sd.nuprev, nu = lay.nu;
-  const WarpCtx c = make_ctx(smem, lay, st, nx + nu);
+  const int ny = EXT ? sd.ny : 0;
+  const WarpCtx c = make_ctx(smem, lay, st, nx + nu + (EXT ? nx + ny : 0));
   double *xnw = c.thw + lay.nth;      // [nx] next state
   double *ucw = xnw + nx;             // [nu] control
+  double *xsw = ucw + nu;             // EXT: [nx] true plant state (thw[0, nx) is then what the controller sees)
+  double *ew = xsw + nx;              // EXT: [ny] innovation
   const int lane = c.lane;
   const int64_t wid = (int64_t)blockIdx.x * K2_WARPS + (threadIdx.x >> 5);
   const int64_t wstride = (int64_t)gridDim.x * K2_WARPS;
@@ -476,7 +497,7 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
   double u = 0.0;
   for (int64_t q = wid; q < Ninst; q += wstride) {
     _Pragma("unroll 1")
-    for (int i = lane; i < nx; i += 32) c.thw[i] = ld_stream(sd.X0 + q * nx + i);
+    for (int i = lane; i < nx; i += 32) { c.thw[i] = ld_stream(sd.X0 + q * nx + i); if (EXT) xsw[i] = c.thw[i]; }
     _Pragma("unroll 1")
     for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.R ? ld_stream(sd.R + q * nr + i) : 0.0;
     _Pragma("unroll 1")
@@ -492,6 +513,35 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
       if (sd.Rtraj) { _Pragma("unroll 1") for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.Rtraj[(size_t)t * nr + i]; }
       if (sd.Dtraj) { _Pragma("unroll 1") for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.Dtraj[(size_t)t * nd + i]; }
       __syncwarp();
+      if constexpr (EXT) {
+        const double *dk = c.thw + nx + nr;
+        if (sd.Cm) {
+          // y = C x + Dd d + v, innovation against the estimate, correction (observer.jl:114-118)
+          _Pragma("unroll 1")
+          for (int i = lane; i < ny; i += 32) {
+            double y = sd.Vtraj ? sd.Vtraj[(size_t)t * ny + i] : 0.0, yh = 0.0;
+            for (int cc = 0; cc < nx; ++cc) y = fma(sd.Cm[i * nx + cc], xsw[cc], y);
+            if (sd.Ddm) for (int cc = 0; cc < nd; ++cc) y = fma(sd.Ddm[i * nd + cc], dk[cc], y);
+            for (int cc = 0; cc < nx; ++cc) yh = fma(sd.Cm[i * nx + cc], c.thw[cc], yh);
+            if (sd.Ddm) for (int cc = 0; cc < nd; ++cc) yh = fma(sd.Ddm[i * nd + cc], dk[cc], yh);
+            ew[i] = __dsub_rn(y, yh);
+          }
+          __syncwarp();
+          _Pragma("unroll 1")
+          for (int j = lane; j < nx; j += 32) {
+            double acc = c.thw[j];
+            for (int i = 0; i < ny; ++i) acc = fma(sd.Kobs[j * ny + i], ew[i], acc);
+            xnw[j] = acc;
+          }
+          __syncwarp();
+          _Pragma("unroll 1")
+          for (int j = lane; j < nx; j += 32) c.thw[j] = xnw[j];
+        } else {
+          _Pragma("unroll 1")
+          for (int j = lane; j < nx; j += 32) c.thw[j] = xsw[j];      // the controller measures the true state
+        }
+        __syncwarp();
+      }
       int iters;
       const int f = wq_solve<K2_UF_SIM, EQ>(c, s, !(sd.warm && t > 0), u, iters);
       tot += iters;
@@ -505,24 +555,25 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
         }
       }
       __syncwarp();
-      _Pragma("unroll 1")
-      for (int i = lane; i < nx; i += 32) {
-        double acc = 0.0;
-        _Pragma("unroll 2")
-        for (int cc = 0; cc < nx; ++cc) acc = fma(sd.F[i * nx + cc], c.thw[cc], acc);
-        _Pragma("unroll 2")
-        for (int cc = 0; cc < nu; ++cc) acc = fma(sd.G[i * nu + cc], ucw[cc], acc);
-        _Pragma("unroll 2")
-        for (int cc = 0; cc < nd; ++cc) acc = fma(sd.Gd[i * nd + cc], c.thw[nx + nr + cc], acc);
-        xnw[i] = acc;
-      }
+      step_rows(sd.F, sd.G, sd.Gd, c.thw, ucw, c.thw + nx + nr, xnw, nx, nu, nd, lane);   // model (predict!)
       __syncwarp();
       _Pragma("unroll 1")
       for (int i = lane; i < nx; i += 32) c.thw[i] = xnw[i];
       __syncwarp();
+      if constexpr (EXT) {
+        step_rows(sd.Ft, sd.Gt, sd.Gdt, xsw, ucw, c.thw + nx + nr, xnw, nx, nu, nd, lane);   // true plant
+        __syncwarp();
+        _Pragma("unroll 1")
+        for (int i = lane; i < nx; i += 32) xsw[i] = xnw[i];
+        __syncwarp();
+      }
+    }
+    if (EXT && sd.Xhat) {
+      _Pragma("unroll 1")
+      for (int i = lane; i < nx; i += 32) sd.Xhat[q * nx + i] = c.thw[i];
     }
     _Pragma("unroll 1")
-    for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = c.thw[i];
+    for (int i = lane; i < nx; i += 32) sd.Xend[q * nx + i] = EXT ? xsw[i] : c.thw[i];
     _Pragma("unroll 1")
     for (int i = lane; i < nu; i += 32) sd.Ulast[q * nu + i] = ucw[i];
     if (lane == 0) {
@@ -549,12 +600,12 @@ template <bool EQ>
 static int launch_warp_t(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
                          const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
                          int sm_count, cudaStream_t s) {
-  const size_t smem = k2_smem(lay, sim ? sim->nx + lay.nu : 0);
+  const size_t smem = k2_smem(lay, sim ? sim->nx + lay.nu + (sim->ext ? sim->nx + sim->ny : 0) : 0);
   int per_sm = 0;
   int64_t blocks = (N + K2_WARPS - 1) / K2_WARPS;
   cudaError_t e;
   if (sim) {
-    auto kern = ldp_warp_sim_kernel<EQ>;
+    auto kern = sim->ext ? ldp_warp_sim_kernel<EQ, true> : ldp_warp_sim_kernel<EQ, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_BLOCK, smem);

@@ -64,6 +64,12 @@ struct SimDesc {
   const double *Rtraj, *Dtraj;  // device, nr x T / nd x T (step t at + t * nr): shared by all trajectories, override R / D
   double *Xend, *Ulast, *Utraj;
   int nx, nr, nd, nuprev, T, warm;
+  // extended closed loop (lmpc_gpu_simulate_batch_ex): true plant, observer, measurement noise
+  int ext, ny;                            // ext != 0: the fields below are in use
+  const double *Ft, *Gt, *Gdt;            // device, row-major true plant (never null when ext)
+  const double *Cm, *Ddm, *Kobs;          // device, row-major ny x nx, ny x nd (nullable), nx x ny; Cm null = no observer
+  const double *Vtraj;                    // device, ny x T (nullable)
+  double *Xhat;                           // nx x N final estimates (nullable)
 };
 
 enum {

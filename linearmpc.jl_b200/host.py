@@ -84,6 +84,8 @@ def load_library():
     L.lmpc_gpu_compute_control_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.lmpc_gpu_simulate_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i64,
                                           i32, i32, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_simulate_batch_ex.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                             i64, i32, i32, vp, vp, vp, vp, vp]
     L.lmpc_gpu_simulate_batch_traj.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                                                i64, i32, i32, vp, vp, vp, vp, vp]
     L.lmpc_gpu_create_bst.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, C.c_int,
@@ -210,6 +212,12 @@ def host_ldp(H, f, f_theta, A, bu, bl, W, senses, nu, nx=0, K=None, soft_weight=
                                C.cast(C.byref(cap), C.c_void_p)))
     out["cap"] = cap.value
     return out
+
+
+class _SimExt(C.Structure):
+    """lmpc_sim_ext (include/lmpc_gpu.h)."""
+    _fields_ = [(k, C.c_void_p) for k in ("Rtraj", "Dtraj", "Ft", "Gt", "Gdt", "C", "Dd", "K", "Vtraj")] + \
+               [("ny", C.c_int32), ("Xhat_end", C.c_void_p)]
 
 
 class GpuMPC:
@@ -410,13 +418,18 @@ class GpuMPC:
 
     # -- Simulation, batched ----------------------------------------------------------------
     def simulate(self, F, G, x0, r=None, d=None, u0=None, N=None, T=None, Gd=None, warm_start=True,
-                 want_traj=False, r_traj=None, d_traj=None):
+                 want_traj=False, r_traj=None, d_traj=None, plant=None, observer=None, noise=None):
         """N independent closed loops of `steps` steps (simulation.jl:93-113) with the default
         linear dynamics (model.jl:70).  `N` = number of steps, as in the reference's keyword.
 
         r, d: constant per closed loop (vector = the same for all, matrix = one column each).
         r_traj (nr x Tr), d_traj (nd x Td): the scenario's trajectories, shared by all closed loops;
-        shorter than the horizon -> the last column is held (simulation.jl:70-80)."""
+        shorter than the horizon -> the last column is held (simulation.jl:70-80).
+        plant = dict(F=, G=, Gd=): the true plant when it differs from the prediction model
+        (scenario.dynamics); observer = dict(C=, K=, Dd=): steady-state Kalman observer run in the
+        loop (observer.jl:104-118), the controller then acts on the estimate; noise (ny x T):
+        additive measurement noise shared by all closed loops.  With any of them the result also
+        has Xhat_end (final estimates) and Xend is the TRUE final state."""
         nx, nr, nd, nup = self.dims
         steps = int(N if N is not None else T)
         X0 = _colmajor(x0, nx)
@@ -446,11 +459,35 @@ class GpuMPC:
         Utraj = np.zeros((n, steps, self.nu)) if want_traj else None
         flag = np.zeros(n, np.int32)
         iters = np.zeros(n, np.int32)
-        _check(lib().lmpc_gpu_simulate_batch_traj(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
-                                                  _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), _ptr(Rt), _ptr(Dt),
-                                                  n, steps, int(bool(warm_start)), _ptr(Xend), _ptr(Ulast),
-                                                  _ptr(Utraj), _ptr(flag), _ptr(iters)))
-        return dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj, exitflag=flag, iters=iters)
+        cm = lambda a, rows: None if a is None else np.asfortranarray(np.asarray(a, float).reshape(rows, -1))
+        ext = _SimExt()
+        keep = [Rt, Dt]
+        ext.Rtraj, ext.Dtraj = _ptr(Rt), _ptr(Dt)
+        extended = plant is not None or observer is not None
+        Xhat = np.zeros((nx, n), order="F") if extended else None
+        if plant is not None:
+            pm = [cm(plant.get("F"), nx), cm(plant.get("G"), nx), cm(plant.get("Gd"), nx) if nd > 0 else None]
+            keep += pm
+            ext.Ft, ext.Gt, ext.Gdt = _ptr(pm[0]), _ptr(pm[1]), _ptr(pm[2])
+        if observer is not None:
+            Cm = np.asfortranarray(np.atleast_2d(np.asarray(observer["C"], float)))
+            ny = Cm.shape[0]
+            Km = cm(observer["K"], nx)
+            Ddm = cm(observer.get("Dd"), ny) if (nd > 0 and observer.get("Dd") is not None) else None
+            Vm = None
+            if noise is not None:
+                Vm = hold(noise, ny)
+            keep += [Cm, Km, Ddm, Vm]
+            ext.C, ext.K, ext.Dd, ext.Vtraj, ext.ny = _ptr(Cm), _ptr(Km), _ptr(Ddm), _ptr(Vm), ny
+        ext.Xhat_end = _ptr(Xhat)
+        _check(lib().lmpc_gpu_simulate_batch_ex(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
+                                                _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), C.byref(ext),
+                                                n, steps, int(bool(warm_start)), _ptr(Xend), _ptr(Ulast),
+                                                _ptr(Utraj), _ptr(flag), _ptr(iters)))
+        out = dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj, exitflag=flag, iters=iters)
+        if extended:
+            out["Xhat_end"] = Xhat
+        return out
 
 
 def setup_gpu(mpqp, nu, dims=None, K=None, soft_weight=1e6, device=0, settings=None, devices=None,
@@ -732,6 +769,8 @@ class MPC:
     def solve(self, Theta, **kw):
         return self._g().solve(Theta, **kw)
 
-    def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None):
+    def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None,
+                 plant=None, observer=None, noise=None):
         return self._g().simulate(self.F, self.G, x0, r=r, d=d, N=N, Gd=self.Gd, warm_start=warm_start,
-                                  want_traj=want_traj, r_traj=r_traj, d_traj=d_traj)
+                                  want_traj=want_traj, r_traj=r_traj, d_traj=d_traj, plant=plant,
+                                  observer=observer, noise=noise)

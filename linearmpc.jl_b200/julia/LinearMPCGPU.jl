@@ -151,6 +151,52 @@ function simulate(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integ
     return Xend, Ulast, flag
 end
 
+# mirrors lmpc_sim_ext (include/lmpc_gpu.h)
+struct LmpcSimExt
+    Rtraj::Ptr{Float64}; Dtraj::Ptr{Float64}
+    Ft::Ptr{Float64}; Gt::Ptr{Float64}; Gdt::Ptr{Float64}
+    C::Ptr{Float64}; Dd::Ptr{Float64}; K::Ptr{Float64}
+    Vtraj::Ptr{Float64}
+    ny::Int32
+    Xhat_end::Ptr{Float64}
+end
+
+"""
+    simulate_observed(g, X0; N, r, d, plant=(F,G,Gd), noise) -> (Xend, Xhat_end, Ulast, exitflag)
+
+The closed loop of src/simulation.jl:92-110 with `mpc.state_observer` (a `KalmanFilter`,
+src/observer.jl:1-11) in the loop: estimate initialised at X0, `correct!` / `compute_control` on the
+estimate / `predict!` every step, true plant `plant` (default: the model), measurement noise `noise`
+(ny × T, shared by all closed loops).
+"""
+function simulate_observed(g::GpuMPC, X0::Matrix{Float64}; N::Integer=100, r=nothing, d=nothing,
+                           plant=nothing, noise=nothing, warm_start::Bool=true)
+    mdl = g.mpc.model; kf = g.mpc.state_observer
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
+    M = size(X0, 2)
+    hold(v, k) = (k == 0 || isnothing(v)) ? nothing :
+        (V = v isa AbstractMatrix ? Matrix{Float64}(v) : reshape(Vector{Float64}(v), k, 1);
+         hcat(V[:, 1:min(N, size(V, 2))], repeat(V[:, end], 1, max(0, N - size(V, 2)))))
+    Rt, Dt = hold(r, nr), hold(d, nd)
+    ny = size(kf.C, 1)
+    Vt = hold(noise, ny)
+    Ft, Gt, Gdt = isnothing(plant) ? (nothing, nothing, nothing) : Matrix{Float64}.(plant)
+    p(x) = isnothing(x) ? Ptr{Float64}(C_NULL) : pointer(x)
+    Xend = similar(X0); Xhat = similar(X0); Ulast = Matrix{Float64}(undef, g.nu, M); flag = Vector{Int32}(undef, M)
+    Cm, Ddm, Km = Matrix{Float64}(kf.C), Matrix{Float64}(kf.Dd), Matrix{Float64}(kf.K)
+    GC.@preserve Rt Dt Vt Ft Gt Gdt Cm Ddm Km Xhat begin
+        ext = Ref(LmpcSimExt(p(Rt), p(Dt), p(Ft), p(Gt), p(Gdt), pointer(Cm), nd == 0 ? C_NULL : pointer(Ddm),
+                             pointer(Km), p(Vt), ny, pointer(Xhat)))
+        check(ccall((:lmpc_gpu_simulate_batch_ex, liblmpcgpu), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{LmpcSimExt},
+                     Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                    g.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
+                    X0, C_NULL, C_NULL, C_NULL, ext, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
+    end
+    return Xend, Xhat, Ulast, flag
+end
+
 # ---- explicit controllers ---------------------------------------------------------------------
 mutable struct GpuExplicitMPC
     handle::Ptr{Cvoid}

@@ -138,8 +138,9 @@ class OracleProblem:
         return r["U"][:, 0], int(r["flag"][0]), r
 
     def simulate_batch(self, Fx, Gx, Gdx, X0, R, D, U0, T, nr, nd, nuprev, warm=False,
-                       nthreads=0, want_traj=False, Rtraj=None, Dtraj=None):
-        """Rtraj (nr x T) / Dtraj (nd x T): trajectories shared by all closed loops (override R / D)."""
+                       nthreads=0, want_traj=False, Rtraj=None, Dtraj=None, ext=None):
+        """Rtraj (nr x T) / Dtraj (nd x T): trajectories shared by all closed loops (override R / D).
+        ext: dict with any of Ft, Gt, Gdt (true plant), C, Dd, K (observer), Vtraj (ny x T noise)."""
         nx = Fx.shape[0]
         c = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, float).T)
         X0c, Rc, Dc, U0c = c(X0), c(R), c(D), c(U0)
@@ -152,12 +153,32 @@ class OracleProblem:
         flag = np.zeros(N, np.int32)
         iters = np.zeros(N, np.int32)
         Rt, Dt = c(Rtraj), c(Dtraj)      # T x nr, T x nd row-major == column-major nr x T
-        lib().orc_simulate_batch_traj(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
-                                      _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), _dp(Rt), _dp(Dt),
-                                      C.c_int64(N), T, int(warm),
-                                      _dp(Xend), _dp(Ulast), _dp(Utraj), _ip(flag), _ip(iters),
-                                      C.c_int(nthreads))
-        return dict(Xend=Xend.T, Ulast=Ulast.T, Utraj=Utraj, flag=flag, iters=iters)
+        ex, Xhat, keep = None, None, []
+        if ext is not None:
+            rm = lambda k: None if ext.get(k) is None else np.ascontiguousarray(np.asarray(ext[k], float))
+            m = {k: rm(k) for k in ("Ft", "Gt", "Gdt", "C", "Dd", "K")}
+            V = None if ext.get("Vtraj") is None else np.ascontiguousarray(np.asarray(ext["Vtraj"], float).T)
+            ny = 0 if m["C"] is None else m["C"].shape[0]
+            Xhat = np.zeros((N, nx))
+            keep = [m, V]
+            vp = lambda a: None if a is None else a.ctypes.data
+            ex = _SimExt(vp(m["Ft"]), vp(m["Gt"]), vp(m["Gdt"]), vp(m["C"]), vp(m["Dd"]), vp(m["K"]), vp(V),
+                         ny, vp(Xhat))
+        lib().orc_simulate_batch_ex(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
+                                    _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), _dp(Rt), _dp(Dt),
+                                    C.byref(ex) if ex is not None else None,
+                                    C.c_int64(N), T, int(warm),
+                                    _dp(Xend), _dp(Ulast), _dp(Utraj), _ip(flag), _ip(iters),
+                                    C.c_int(nthreads))
+        out = dict(Xend=Xend.T, Ulast=Ulast.T, Utraj=Utraj, flag=flag, iters=iters)
+        if Xhat is not None:
+            out["Xhat_end"] = Xhat.T
+        return out
+
+
+class _SimExt(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("Ft", "Gt", "Gdt", "C", "Dd", "K", "Vtraj")] + [("ny", C.c_int),
+                                                                                      ("Xhat_end", C.c_void_p)]
 
 
 class OracleBst:

@@ -405,6 +405,7 @@ typedef struct {
   const orc_problem *p; int nx, nr, nd, nuprev; const double *Fx, *Gx, *Gdx, *X0, *R, *D, *U0;
   const double *Rtraj, *Dtraj;   /* nr x T, nd x T shared trajectories (simulation.jl:70-80), or NULL */
   int T, warm; double *Xend, *Ulast, *Utraj; int32_t *flag, *iters;
+  const orc_sim_ext *ext;        /* true plant / observer / measurement noise, or NULL */
 } sim_ctx;
 static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
   sim_ctx *s = (sim_ctx *)vc;
@@ -415,39 +416,78 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
   double *x = (double *)calloc(nx, sizeof(double));
   double *xn = (double *)calloc(nx, sizeof(double));
   double *u = (double *)calloc(nu, sizeof(double));
+  const orc_sim_ext *e = s->ext;
+  const int ny = e ? e->ny : 0;
+  const int obs = e && e->C && e->K;
+  /* true plant (defaults to the prediction model) */
+  const double *Ft = (e && e->Ft) ? e->Ft : s->Fx, *Gt = (e && e->Gt) ? e->Gt : s->Gx;
+  const double *Gdt = (e && e->Gdt) ? e->Gdt : s->Gdx;
+  double *xs = (double *)calloc(nx, sizeof(double));           /* true state when ext != NULL */
+  double *inn = (double *)calloc(ny > 0 ? ny : 1, sizeof(double));
   for (int64_t q = lo; q < hi; ++q) {
     int worst = ORC_OPTIMAL, tot = 0;
-    for (int i = 0; i < nx; ++i) x[i] = s->X0[q * nx + i];
+    for (int i = 0; i < nx; ++i) x[i] = xs[i] = s->X0[q * nx + i];   /* set_state!(mpc, x0), simulation.jl:92 */
     for (int i = 0; i < nu; ++i) u[i] = (s->U0 && i < nuprev) ? s->U0[q * nuprev + i] : 0.0;
     for (int t = 0; t < s->T; ++t) {
-      /* theta = [x; r; d; uprev] (explicit.jl:54-63) */
-      int o = 0;
-      for (int i = 0; i < nx; ++i) th[o++] = x[i];
+      /* theta = [x; r; d; uprev] (explicit.jl:54-63); x is the estimate when an observer runs */
+      int o = nx;
       for (int i = 0; i < nr; ++i) th[o++] = s->Rtraj ? s->Rtraj[(size_t)t * nr + i] : (s->R ? s->R[q * nr + i] : 0.0);
       for (int i = 0; i < nd; ++i) th[o++] = s->Dtraj ? s->Dtraj[(size_t)t * nd + i] : (s->D ? s->D[q * nd + i] : 0.0);
       for (int i = 0; i < nuprev; ++i) th[o++] = u[i];
+      const double *dk = th + nx + nr;
+      if (obs) {
+        /* y = C x + Dd d + v (simulation.jl:94), innovation and correction (observer.jl:114-118) */
+        for (int i = 0; i < ny; ++i) {
+          double y = e->Vtraj ? e->Vtraj[(size_t)t * ny + i] : 0.0, yh = 0.0;
+          for (int c = 0; c < nx; ++c) y = fma(e->C[i * nx + c], xs[c], y);
+          for (int c = 0; c < nd; ++c) y = fma(e->Dd ? e->Dd[i * nd + c] : 0.0, dk[c], y);
+          for (int c = 0; c < nx; ++c) yh = fma(e->C[i * nx + c], x[c], yh);
+          for (int c = 0; c < nd; ++c) yh = fma(e->Dd ? e->Dd[i * nd + c] : 0.0, dk[c], yh);
+          inn[i] = y - yh;
+        }
+        for (int j = 0; j < nx; ++j) {
+          double acc = x[j];
+          for (int i = 0; i < ny; ++i) acc = fma(e->K[j * ny + i], inn[i], acc);
+          xn[j] = acc;
+        }
+        for (int j = 0; j < nx; ++j) x[j] = xn[j];
+      } else if (e) {
+        for (int j = 0; j < nx; ++j) x[j] = xs[j];           /* the controller measures the true state */
+      }
+      for (int i = 0; i < nx; ++i) th[i] = x[i];
       int32_t it = 0;
       int f = solve_with(p, w, th, u, &it, NULL, NULL, NULL, !(s->warm && t > 0));
       tot += it;
       if (f < 0) { if (worst > 0 || f < worst) worst = f; }
       else if (worst > 0 && f > worst) worst = f;
       if (s->Utraj) for (int i = 0; i < nu; ++i) s->Utraj[(q * s->T + t) * nu + i] = u[i];
-      /* x+ = F x + G u + Gd d (model.jl:70) */
+      /* model step x+ = F x + G u + Gd d (model.jl:70; predict!, observer.jl:104-108) */
       for (int i = 0; i < nx; ++i) {
         double acc = 0.0;
         for (int c = 0; c < nx; ++c) acc = fma(s->Fx[i * nx + c], x[c], acc);
         for (int c = 0; c < nu; ++c) acc = fma(s->Gx[i * nu + c], u[c], acc);
-        for (int c = 0; c < nd; ++c) acc = fma(s->Gdx[i * nd + c], th[nx + nr + c], acc);
+        for (int c = 0; c < nd; ++c) acc = fma(s->Gdx[i * nd + c], dk[c], acc);
         xn[i] = acc;
       }
       for (int i = 0; i < nx; ++i) x[i] = xn[i];
+      if (e) {   /* true plant step (scenario.dynamics, simulation.jl:110) */
+        for (int i = 0; i < nx; ++i) {
+          double acc = 0.0;
+          for (int c = 0; c < nx; ++c) acc = fma(Ft[i * nx + c], xs[c], acc);
+          for (int c = 0; c < nu; ++c) acc = fma(Gt[i * nu + c], u[c], acc);
+          for (int c = 0; c < nd; ++c) acc = fma(Gdt[i * nd + c], dk[c], acc);
+          xn[i] = acc;
+        }
+        for (int i = 0; i < nx; ++i) xs[i] = xn[i];
+      }
     }
-    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = x[i];
+    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = e ? xs[i] : x[i];
+    if (e && e->Xhat_end) for (int i = 0; i < nx; ++i) e->Xhat_end[q * nx + i] = x[i];
     for (int i = 0; i < nu; ++i) s->Ulast[q * nu + i] = u[i];
     if (s->flag) s->flag[q] = worst;
     if (s->iters) s->iters[q] = tot;
   }
-  free(th); free(x); free(xn); free(u);
+  free(th); free(x); free(xn); free(u); free(xs); free(inn);
   work_free(w);
 }
 void orc_simulate_batch(const orc_problem *p, int nx, int nr, int nd, int nuprev,
@@ -464,7 +504,17 @@ void orc_simulate_batch_traj(const orc_problem *p, int nx, int nr, int nd, int n
                              const double *Rtraj, const double *Dtraj,
                              int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
                              int32_t *flag, int32_t *iters, int nthreads) {
-  sim_ctx s = {p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, Rtraj, Dtraj, T, warm, Xend, Ulast, Utraj, flag, iters};
+  orc_simulate_batch_ex(p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, Rtraj, Dtraj, NULL, N, T, warm, Xend,
+                        Ulast, Utraj, flag, iters, nthreads);
+}
+void orc_simulate_batch_ex(const orc_problem *p, int nx, int nr, int nd, int nuprev,
+                           const double *Fx, const double *Gx, const double *Gdx,
+                           const double *X0, const double *R, const double *D, const double *U0,
+                           const double *Rtraj, const double *Dtraj, const orc_sim_ext *ext,
+                           int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
+                           int32_t *flag, int32_t *iters, int nthreads) {
+  sim_ctx s = {p, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, Rtraj, Dtraj, T, warm, Xend, Ulast, Utraj, flag,
+               iters, ext};
   parallel_for(N, nthreads, sim_chunk, &s);
 }
 

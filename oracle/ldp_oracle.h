@@ -71,6 +71,20 @@ void orc_simulate_batch(const orc_problem *p, int nx, int nr, int nd, int nuprev
                         const double *X0, const double *R, const double *D, const double *U0,
                         int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
                         int32_t *flag, int32_t *iters, int nthreads);
+/* true plant x+ = Ft x + Gt u + Gdt d (row-major; NULL = the model), steady-state observer
+ * (observer.jl:104-118: C ny x nx, Dd ny x nd or NULL, K nx x ny; C == NULL: the controller sees
+ * the true state) and additive measurement noise Vtraj (ny x T, shared) */
+typedef struct {
+  const double *Ft, *Gt, *Gdt, *C, *Dd, *K, *Vtraj;
+  int ny;
+  double *Xhat_end;   /* nx x N final estimates, nullable */
+} orc_sim_ext;
+void orc_simulate_batch_ex(const orc_problem *p, int nx, int nr, int nd, int nuprev,
+                           const double *Fx, const double *Gx, const double *Gdx,
+                           const double *X0, const double *R, const double *D, const double *U0,
+                           const double *Rtraj, const double *Dtraj, const orc_sim_ext *ext,
+                           int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
+                           int32_t *flag, int32_t *iters, int nthreads);
 /* same with reference / disturbance trajectories shared by all closed loops (nr x T, nd x T; NULL = use R / D) */
 void orc_simulate_batch_traj(const orc_problem *p, int nx, int nr, int nd, int nuprev,
                              const double *Fx, const double *Gx, const double *Gdx,

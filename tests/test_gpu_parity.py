@@ -418,3 +418,56 @@ def test_non_default_settings_match_oracle(lmpc, name, kernel, over):
     if "iter_limit" in over and over["iter_limit"] == 4 and name != "dint_hard":
         assert np.any(ref["flag"] == -4)
     g.close()
+
+
+@pytest.mark.parametrize("name,T", [("invpend", 50), ("aircraft", 30), ("aircraft_ksall", 20), ("chain_small", 10)])
+@pytest.mark.parametrize("mode", ["plant", "observer", "observer+noise+plant"])
+def test_closed_loop_with_true_plant_and_observer(lmpc, name, T, mode):
+    """lmpc_gpu_simulate_batch_ex: a true plant that differs from the prediction model, the
+    steady-state Kalman observer of observer.jl:104-118 in the loop (simulation.jl:92-110) and a
+    measurement-noise trajectory; bit-identical to the oracle's restatement on all three closed-loop
+    kernels, and the no-mismatch / no-noise observer reproduces the plain closed loop."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    rng = np.random.default_rng(9)
+    N = 257
+    lo, hi = util.theta_range(name, 0.1)
+    X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
+    r = np.zeros(nr)
+    d = 0.01 * np.ones(nd) if nd else None
+    Cm = mpc.C
+    ny = Cm.shape[0]
+    K = 0.4 * np.linalg.pinv(Cm)
+    Dd = mpc.Dd if nd else None
+    plant = dict(F=mpc.F * (1 + 1e-3), G=mpc.G * 0.98, Gd=mpc.Gd if nd else None)
+    V = 1e-3 * rng.standard_normal((ny, T - 3))
+    kw, ext = {}, {}
+    if "plant" in mode:
+        kw["plant"] = plant
+        ext.update(Ft=plant["F"], Gt=plant["G"], Gdt=plant["Gd"])
+    if "observer" in mode:
+        kw["observer"] = dict(C=Cm, K=K, Dd=Dd)
+        ext.update(C=Cm, K=K, Dd=Dd)
+    if "noise" in mode:
+        kw["noise"] = V
+        ext["Vtraj"] = np.hstack([V, np.repeat(V[:, -1:], 3, axis=1)])
+    Rm = np.repeat(r.reshape(-1, 1), N, axis=1) if nr else None
+    Dm = np.repeat(d.reshape(-1, 1), N, axis=1) if nd else None
+    for warm in (True, False):
+        out = g.simulate(mpc.F, mpc.G, X0, r=Rm, d=Dm, N=T, Gd=mpc.Gd if nd else None, warm_start=warm,
+                         want_traj=True, **kw)
+        ref = P.simulate_batch(mpc.F, mpc.G, mpc.Gd if nd else None, X0, Rm, Dm, None, T, nr, nd, nup, warm=warm,
+                               want_traj=True, ext=ext)
+        assert np.array_equal(out["exitflag"], ref["flag"])
+        assert np.array_equal(out["iters"], ref["iters"])
+        assert np.array_equal(out["Utraj"], ref["Utraj"])
+        assert np.array_equal(out["Xend"], ref["Xend"])
+        assert np.array_equal(out["Xhat_end"], ref["Xhat_end"])
+    if mode == "observer":
+        # exact model, no noise: the estimate is the state and the loop is the plain one
+        plain = g.simulate(mpc.F, mpc.G, X0, r=Rm, d=Dm, N=T, Gd=mpc.Gd if nd else None, warm_start=False,
+                           want_traj=True)
+        assert np.array_equal(plain["Utraj"], out["Utraj"]) and np.array_equal(plain["Xend"], out["Xend"])
+        assert np.array_equal(out["Xend"], out["Xhat_end"])
+    else:
+        assert not np.array_equal(out["Xend"], out["Xhat_end"])

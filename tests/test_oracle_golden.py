@@ -258,3 +258,34 @@ def test_warm_start_from_masks_reaches_the_cold_solution(name, tol):
     assert np.array_equal(z["U"], cold["U"]) and np.array_equal(z["iters"], cold["iters"])
     own = P.solve_batch_warm(Th, cold["act_u"], cold["act_l"])
     assert np.all(own["iters"][cold["flag"] == 1] == 1)
+
+
+def test_closed_loop_with_observer_equals_the_stepwise_loop():
+    """orc_simulate_batch_ex against simulation.jl:92-110 + observer.jl:104-118 written out in numpy:
+    set_state!(x0); per step y = C x + v, correct!, compute_control on the estimate, predict! with the
+    model, true plant step with a mismatched F, G."""
+    mpc, qp, L, P = make("invpend")
+    nx, nr, nd, nup = mpc.parameter_dims()
+    T, N = 40, 5
+    rng = np.random.default_rng(4)
+    lo, hi = util.theta_range("invpend", 0.1)
+    X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
+    Cm = mpc.C
+    ny = Cm.shape[0]
+    K = 0.4 * np.linalg.pinv(Cm)
+    Ft, Gt = mpc.F * (1 + 1e-3), mpc.G * 0.98
+    V = 1e-3 * rng.standard_normal((ny, T))
+    out = P.simulate_batch(mpc.F, mpc.G, None, X0, np.zeros((nr, N)), None, None, T, nr, nd, nup, warm=False,
+                           want_traj=True, ext=dict(Ft=Ft, Gt=Gt, C=Cm, K=K, Vtraj=V))
+    for q in range(N):
+        x, xh, u = X0[:, q].copy(), X0[:, q].copy(), np.zeros(mpc.nu)
+        for k in range(T):
+            y = Cm @ x + V[:, k]
+            xh = xh + K @ (y - Cm @ xh)
+            u, flag, _ = P.solve(np.concatenate([xh, np.zeros(nr), u[:nup]]))
+            assert flag >= 1
+            assert np.allclose(u, out["Utraj"][q, k], rtol=0, atol=1e-8)
+            xh = mpc.F @ xh + mpc.G @ u
+            x = Ft @ x + Gt @ u
+        assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=1e-8)
+        assert np.allclose(xh, out["Xhat_end"][:, q], rtol=0, atol=1e-8)
