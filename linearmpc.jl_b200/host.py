@@ -769,6 +769,17 @@ class MPC:
     def solve(self, Theta, **kw):
         return self._g().solve(Theta, **kw)
 
+    def explicit(self, lo, hi, n_samples=2_000_000, seed=0, device=0, clipping=None, **kw):
+        """ExplicitMPC(mpc; range, build_tree=true) (src/explicit.jl:25-52): explicit solution over the
+        parameter box [lo, hi], critical regions discovered by batched implicit solves on the GPU
+        (linearmpc.jl_b200/explicit.py).  Returns (GpuExplicitMPC, info)."""
+        from . import explicit as ex
+        q = self.condense()
+        sol = ex.build_explicit(q, self._g(), lo, hi, self.nu, n_samples=n_samples, seed=seed, **kw)
+        empc = GpuExplicitMPC(sol["halfplanes"], sol["feedbacks"], sol["hp_list"], sol["jump_list"],
+                              clipping=clipping, dims=q["dims"], device=device)
+        return empc, sol
+
     def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None,
                  plant=None, observer=None, noise=None):
         return self._g().simulate(self.F, self.G, x0, r=r, d=d, N=N, Gd=self.Gd, warm_start=warm_start,

@@ -106,3 +106,65 @@ def test_gpu_evaluate_device_buffers_and_large_batch(lmpc):
     assert np.array_equal(Uh, U[:, :300000].cpu().numpy())
     Uo, _ = B.evaluate_batch(sub[:, :50000])
     assert np.array_equal(Uo, Uh[:, :50000])
+
+
+def test_product_builder_logic_with_a_cpu_stand_in():
+    """The product's explicit builder (linearmpc.jl_b200/explicit.py) takes any object with a
+    GpuMPC-like solve(); here the CPU oracle stands in for the GPU so that region discovery, the
+    adjacency closure (two regions of this problem have a Chebyshev radius of 5e-3 and are never
+    sampled), the laws and the tree are covered without a device."""
+    import lmpc_b200
+    from lmpc_b200 import explicit as pex
+    mpc = mpqp.invpend(Np=30, Nc=3)
+    qp = mpqp.mpc2mpqp(mpc)
+    P = ldp.OracleProblem(mpqp.qp2ldp(qp, 1), 1)
+
+    class StandIn:
+        def solve(self, Th, want_iters=False):
+            o = P.solve_batch(Th)
+            return dict(exitflag=o["flag"], active_upper=o["act_u"], active_lower=o["act_l"])
+
+    q = dict(H=qp.H, f=qp.f, f_theta=qp.f_theta, A=qp.A, bu=qp.bu, bl=qp.bl, W=qp.W, senses=qp.senses)
+    lo, hi = mpqp.invpend_range(0.3)
+    sol = pex.build_explicit(q, StandIn(), lo, hi, 1, n_samples=30000, tree_samples=4000)
+    regs, laws = explicit.critical_regions(mpqp.make_singlesided(qp), lo, hi, 1)
+    assert len(sol["regions"]) == len(regs) == 15 and len(sol["laws"]) == len(laws)
+    B = ldp.OracleBst(sol["halfplanes"], sol["feedbacks"], sol["hp_list"], sol["jump_list"])
+    Th = mpqp.sample_theta(lo, hi, 30000, seed=9)
+    U, _ = B.evaluate_batch(Th)
+    assert np.max(np.abs(U - P.solve_batch(Th)["U"])) < 1e-10
+    with pytest.raises(NotImplementedError):
+        q2 = dict(q)
+        q2["senses"] = np.asarray(q["senses"]) | 8
+        pex.make_singlesided(q2)
+
+
+@pytest.mark.gpu
+def test_product_explicit_builder_matches_implicit_and_enumeration(lmpc):
+    """lmpc_b200.MPC.explicit: regions discovered by batched implicit solves, exact laws
+    and half-planes, LP-certified tree.  On a 3-move pendulum controller: the same full-dimensional
+    regions as the test-side combinatorial enumeration, and explicit == implicit to 1e-10 on fresh
+    parameters (runtests.jl:381,490)."""
+    from lmpc_b200 import explicit as pex
+    ref_mpc = mpqp.invpend(Np=30, Nc=3)
+    from scipy.linalg import expm
+    A = np.array([[0, 1, 0, 0], [0, -10, 9.81, 0], [0, 0, 0, 1], [0, -20, 39.24, 0.0]])
+    Bm = 100 * np.array([[0], [1.0], [0], [2.0]])
+    E = expm(np.block([[A * 0.01, Bm * 0.01], [np.zeros((1, 5))]]))
+    mpc = lmpc.MPC(E[:4, :4], E[:4, 4:], C=[[1.0, 0, 0, 0], [0, 0, 1.0, 0]], Np=30, Nc=3)
+    mpc.set_objective(Q=[1.2 ** 2, 1], R=[0.0], Rr=[1.0])
+    mpc.set_bounds(umin=[-2.0], umax=[2.0])
+    g = mpc.setup()
+    lo, hi = mpqp.invpend_range(0.3)
+    empc, sol = mpc.explicit(lo, hi, n_samples=100_000, seed=1)
+    # test-side enumeration of the same problem (3^3 candidate sets)
+    qp = mpqp.mpc2mpqp(ref_mpc)
+    regs, laws = explicit.critical_regions(mpqp.make_singlesided(qp), lo, hi, 1)
+    assert len(sol["regions"]) == len(regs) and len(sol["laws"]) == len(laws)
+    rep = pex.verify(empc, g, lo, hi, n=300_000)
+    assert rep["max_err"] < 1e-10 and rep["frac_within_tol"] == 1.0
+    # and against the CPU oracle's implicit solve
+    P = ldp.OracleProblem(mpqp.qp2ldp(qp, 1), 1)
+    Th = mpqp.sample_theta(lo, hi, 20000, seed=6)
+    U, _ = empc.evaluate(Th)
+    assert np.max(np.abs(U - P.solve_batch(Th)["U"])) < 1e-10
