@@ -214,6 +214,12 @@ typedef struct {
   const double *Vtraj;
   int32_t ny;
   double *Xhat_end;
+  /* Preview windows (reference_preview / disturbance_preview, src/simulation.jl:102-104,128-134):
+   * with rstride > 0, Rtraj is a flat HOST array and step t reads its nr = ny_ref * Np entries at
+   * offset t * rstride (rstride = ny_ref slides the window by one column per step; the caller
+   * appends the held last column Np times); likewise dstride for Dtraj.  0 = nr / nd (plain
+   * one-column-per-step trajectories, length nr * T). */
+  int32_t rstride, dstride;
 } lmpc_sim_ext;
 int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G, const double *Gd,
                                int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,

@@ -554,8 +554,11 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
   const size_t oF = push_rowmajor(dynh, F, nx, nx), oG = push_rowmajor(dynh, G, nx, nu);
   const size_t oGd = nd > 0 ? push_rowmajor(dynh, Gd, nx, nd) : dynh.size();
   size_t oR = 0, oD = 0, oFt = oF, oGt = oG, oGdt = oGd, oC = 0, oDd = 0, oK = 0, oV = 0;
-  if (Rtraj && nr > 0) { oR = dynh.size(); dynh.insert(dynh.end(), Rtraj, Rtraj + (size_t)nr * T); }
-  if (Dtraj && nd > 0) { oD = dynh.size(); dynh.insert(dynh.end(), Dtraj, Dtraj + (size_t)nd * T); }
+  const int rstride = (ext && ext->rstride > 0) ? ext->rstride : nr;
+  const int dstride = (ext && ext->dstride > 0) ? ext->dstride : nd;
+  // a windowed trajectory is read up to (T - 1) * stride + n entries
+  if (Rtraj && nr > 0) { oR = dynh.size(); dynh.insert(dynh.end(), Rtraj, Rtraj + ((size_t)(T > 0 ? T - 1 : 0) * rstride + nr)); }
+  if (Dtraj && nd > 0) { oD = dynh.size(); dynh.insert(dynh.end(), Dtraj, Dtraj + ((size_t)(T > 0 ? T - 1 : 0) * dstride + nd)); }
   if (extended) {
     if (ext->Ft) oFt = push_rowmajor(dynh, ext->Ft, nx, nx);
     if (ext->Gt) oGt = push_rowmajor(dynh, ext->Gt, nx, nu);
@@ -577,6 +580,7 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
   sd.nx = nx; sd.nr = nr; sd.nd = nd; sd.nuprev = nuprev; sd.T = T; sd.warm = warm_start;
   sd.Rtraj = (Rtraj && nr > 0) ? db + oR : nullptr;
   sd.Dtraj = (Dtraj && nd > 0) ? db + oD : nullptr;
+  sd.rstride = rstride; sd.dstride = dstride;
   if (extended) {
     sd.ext = 1; sd.ny = ny;
     sd.Ft = db + oFt; sd.Gt = db + oGt; sd.Gdt = db + oGdt;

@@ -428,8 +428,8 @@ ldp_thread_sim_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ 
     for (int t = 0; t < sd.T; ++t) {
       for (int i = 0; i < nup; ++i) thv[(nx + nr + nd + i) * K1_BLOCK] = ucv[i * K1_BLOCK];
       // reference / disturbance of step t (rs[:, k], ds[:, k] of src/simulation.jl:93-104)
-      if (sd.Rtraj) for (int i = 0; i < nr; ++i) thv[(nx + i) * K1_BLOCK] = sd.Rtraj[(size_t)t * nr + i];
-      if (sd.Dtraj) for (int i = 0; i < nd; ++i) thv[(nx + nr + i) * K1_BLOCK] = sd.Dtraj[(size_t)t * nd + i];
+      if (sd.Rtraj) for (int i = 0; i < nr; ++i) thv[(nx + i) * K1_BLOCK] = sd.Rtraj[(size_t)t * sd.rstride + i];
+      if (sd.Dtraj) for (int i = 0; i < nd; ++i) thv[(nx + nr + i) * K1_BLOCK] = sd.Dtraj[(size_t)t * sd.dstride + i];
       if (ext) {
         const double *dk = thv + (size_t)(nx + nr) * K1_BLOCK;
         if (sd.Cm) {

@@ -510,8 +510,8 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
       _Pragma("unroll 1")
       for (int i = lane; i < nup; i += 32) c.thw[nx + nr + nd + i] = ucw[i];
       // reference / disturbance of step t (rs[:, k], ds[:, k] of src/simulation.jl:93-104)
-      if (sd.Rtraj) { _Pragma("unroll 1") for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.Rtraj[(size_t)t * nr + i]; }
-      if (sd.Dtraj) { _Pragma("unroll 1") for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.Dtraj[(size_t)t * nd + i]; }
+      if (sd.Rtraj) { _Pragma("unroll 1") for (int i = lane; i < nr; i += 32) c.thw[nx + i] = sd.Rtraj[(size_t)t * sd.rstride + i]; }
+      if (sd.Dtraj) { _Pragma("unroll 1") for (int i = lane; i < nd; i += 32) c.thw[nx + nr + i] = sd.Dtraj[(size_t)t * sd.dstride + i]; }
       __syncwarp();
       if constexpr (EXT) {
         const double *dk = c.thw + nx + nr;

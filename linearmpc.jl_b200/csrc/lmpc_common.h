@@ -61,7 +61,8 @@ struct SolveOut {
 struct SimDesc {
   const double *F, *G, *Gd;     // device, row-major nx x nx, nx x nu, nx x nd
   const double *X0, *R, *D, *U0;
-  const double *Rtraj, *Dtraj;  // device, nr x T / nd x T (step t at + t * nr): shared by all trajectories, override R / D
+  const double *Rtraj, *Dtraj;  // device; step t reads nr / nd entries at + t * rstride / dstride: shared by all trajectories, override R / D
+  int rstride, dstride;         // nr / nd for plain trajectories, ny / nd_base for sliding preview windows
   double *Xend, *Ulast, *Utraj;
   int nx, nr, nd, nuprev, T, warm;
   // extended closed loop (lmpc_gpu_simulate_batch_ex): true plant, observer, measurement noise

@@ -217,7 +217,7 @@ def host_ldp(H, f, f_theta, A, bu, bl, W, senses, nu, nx=0, K=None, soft_weight=
 class _SimExt(C.Structure):
     """lmpc_sim_ext (include/lmpc_gpu.h)."""
     _fields_ = [(k, C.c_void_p) for k in ("Rtraj", "Dtraj", "Ft", "Gt", "Gdt", "C", "Dd", "K", "Vtraj")] + \
-               [("ny", C.c_int32), ("Xhat_end", C.c_void_p)]
+               [("ny", C.c_int32), ("Xhat_end", C.c_void_p), ("rstride", C.c_int32), ("dstride", C.c_int32)]
 
 
 class GpuMPC:
@@ -418,13 +418,17 @@ class GpuMPC:
 
     # -- Simulation, batched ----------------------------------------------------------------
     def simulate(self, F, G, x0, r=None, d=None, u0=None, N=None, T=None, Gd=None, warm_start=True,
-                 want_traj=False, r_traj=None, d_traj=None, plant=None, observer=None, noise=None):
+                 want_traj=False, r_traj=None, d_traj=None, plant=None, observer=None, noise=None,
+                 r_preview=0, d_preview=0):
         """N independent closed loops of `steps` steps (simulation.jl:93-113) with the default
         linear dynamics (model.jl:70).  `N` = number of steps, as in the reference's keyword.
 
         r, d: constant per closed loop (vector = the same for all, matrix = one column each).
         r_traj (nr x Tr), d_traj (nd x Td): the scenario's trajectories, shared by all closed loops;
         shorter than the horizon -> the last column is held (simulation.jl:70-80).
+        r_preview = Np > 0: the controller was condensed with reference_preview, nr = ny_ref * Np; r_traj
+        is then the ny_ref x Tr scenario reference and step k sees columns k+1 .. k+Np (last held), as
+        get_preview does (simulation.jl:102,128-134); d_preview likewise with columns k .. k+Np-1.
         plant = dict(F=, G=, Gd=): the true plant when it differs from the prediction model
         (scenario.dynamics); observer = dict(C=, K=, Dd=): steady-state Kalman observer run in the
         loop (observer.jl:104-118), the controller then acts on the estimate; noise (ny x T):
@@ -436,6 +440,8 @@ class GpuMPC:
         n = X0.shape[1]
         Fm, Gm = np.asfortranarray(np.asarray(F, float)), np.asfortranarray(np.asarray(G, float).reshape(nx, -1))
         Gdm = np.asfortranarray(np.asarray(Gd, float).reshape(nx, -1)) if (nd > 0 and Gd is not None) else None
+        if Gdm is not None and Gdm.shape[1] < nd:      # disturbance preview: only d_k itself drives the plant
+            Gdm = np.asfortranarray(np.hstack([Gdm, np.zeros((nx, nd - Gdm.shape[1]))]))
         def bc(v, rows):
             if rows == 0:
                 return None
@@ -453,7 +459,22 @@ class GpuMPC:
             if v.shape[1] < steps:
                 v = np.hstack([v, np.repeat(v[:, -1:], steps - v.shape[1], axis=1)])
             return np.asfortranarray(v[:, :steps])
-        Rt, Dt = hold(r_traj, nr), hold(d_traj, nd)
+        rstride = dstride = 0
+        def window(v, rows_total, Np, first):
+            """flat trajectory for a sliding window of Np columns starting at column k + first."""
+            base = rows_total // Np
+            v = np.asarray(v, float).reshape(base, -1)
+            need = first + steps - 1 + Np                      # last column index read + 1
+            if v.shape[1] < need:
+                v = np.hstack([v, np.repeat(v[:, -1:], need - v.shape[1], axis=1)])
+            return np.asfortranarray(v[:, first:need]), base
+        if r_preview and r_traj is not None and nr:
+            Rt, rstride = window(r_traj, nr, int(r_preview), 1)
+            Dt = hold(d_traj, nd)
+        else:
+            Rt, Dt = hold(r_traj, nr), hold(d_traj, nd)
+        if d_preview and d_traj is not None and nd:
+            Dt, dstride = window(d_traj, nd, int(d_preview), 0)
         Xend = np.zeros((nx, n), order="F")
         Ulast = np.zeros((self.nu, n), order="F")
         Utraj = np.zeros((n, steps, self.nu)) if want_traj else None
@@ -480,6 +501,7 @@ class GpuMPC:
             keep += [Cm, Km, Ddm, Vm]
             ext.C, ext.K, ext.Dd, ext.Vtraj, ext.ny = _ptr(Cm), _ptr(Km), _ptr(Ddm), _ptr(Vm), ny
         ext.Xhat_end = _ptr(Xhat)
+        ext.rstride, ext.dstride = rstride, dstride
         _check(lib().lmpc_gpu_simulate_batch_ex(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
                                                 _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), C.byref(ext),
                                                 n, steps, int(bool(warm_start)), _ptr(Xend), _ptr(Ulast),

@@ -163,7 +163,7 @@ class OracleProblem:
             keep = [m, V]
             vp = lambda a: None if a is None else a.ctypes.data
             ex = _SimExt(vp(m["Ft"]), vp(m["Gt"]), vp(m["Gdt"]), vp(m["C"]), vp(m["Dd"]), vp(m["K"]), vp(V),
-                         ny, vp(Xhat))
+                         ny, vp(Xhat), int(ext.get("rstride", 0)), int(ext.get("dstride", 0)))
         lib().orc_simulate_batch_ex(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
                                     _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), _dp(Rt), _dp(Dt),
                                     C.byref(ex) if ex is not None else None,
@@ -178,7 +178,9 @@ class OracleProblem:
 
 class _SimExt(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("Ft", "Gt", "Gdt", "C", "Dd", "K", "Vtraj")] + [("ny", C.c_int),
-                                                                                      ("Xhat_end", C.c_void_p)]
+                                                                                      ("Xhat_end", C.c_void_p),
+                                                                                      ("rstride", C.c_int),
+                                                                                      ("dstride", C.c_int)]
 
 
 class OracleBst:

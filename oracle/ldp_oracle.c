@@ -419,6 +419,8 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
   const orc_sim_ext *e = s->ext;
   const int ny = e ? e->ny : 0;
   const int obs = e && e->C && e->K;
+  /* sliding preview windows (simulation.jl:102-104, get_preview :128-134): step t reads nr entries at t * rstride */
+  const int rstride = (e && e->rstride > 0) ? e->rstride : nr, dstride = (e && e->dstride > 0) ? e->dstride : nd;
   /* true plant (defaults to the prediction model) */
   const double *Ft = (e && e->Ft) ? e->Ft : s->Fx, *Gt = (e && e->Gt) ? e->Gt : s->Gx;
   const double *Gdt = (e && e->Gdt) ? e->Gdt : s->Gdx;
@@ -431,8 +433,8 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
     for (int t = 0; t < s->T; ++t) {
       /* theta = [x; r; d; uprev] (explicit.jl:54-63); x is the estimate when an observer runs */
       int o = nx;
-      for (int i = 0; i < nr; ++i) th[o++] = s->Rtraj ? s->Rtraj[(size_t)t * nr + i] : (s->R ? s->R[q * nr + i] : 0.0);
-      for (int i = 0; i < nd; ++i) th[o++] = s->Dtraj ? s->Dtraj[(size_t)t * nd + i] : (s->D ? s->D[q * nd + i] : 0.0);
+      for (int i = 0; i < nr; ++i) th[o++] = s->Rtraj ? s->Rtraj[(size_t)t * rstride + i] : (s->R ? s->R[q * nr + i] : 0.0);
+      for (int i = 0; i < nd; ++i) th[o++] = s->Dtraj ? s->Dtraj[(size_t)t * dstride + i] : (s->D ? s->D[q * nd + i] : 0.0);
       for (int i = 0; i < nuprev; ++i) th[o++] = u[i];
       const double *dk = th + nx + nr;
       if (obs) {

@@ -78,6 +78,7 @@ typedef struct {
   const double *Ft, *Gt, *Gdt, *C, *Dd, *K, *Vtraj;
   int ny;
   double *Xhat_end;   /* nx x N final estimates, nullable */
+  int rstride, dstride;   /* > 0: step t reads its nr / nd entries at t * stride (preview windows) */
 } orc_sim_ext;
 void orc_simulate_batch_ex(const orc_problem *p, int nx, int nr, int nd, int nuprev,
                            const double *Fx, const double *Gx, const double *Gdx,

@@ -471,3 +471,42 @@ def test_closed_loop_with_true_plant_and_observer(lmpc, name, T, mode):
         assert np.array_equal(out["Xend"], out["Xhat_end"])
     else:
         assert not np.array_equal(out["Xend"], out["Xhat_end"])
+
+
+@pytest.mark.parametrize("name", ["aircraft", "aircraft_ksall"])
+def test_closed_loop_with_preview_windows(lmpc, name):
+    """Sliding preview windows (reference_preview / disturbance_preview slicing, simulation.jl:102-104,
+    128-134): the AFTI-16 parameter layout read as a one-output reference and a one-channel
+    disturbance previewed over Np = 2 steps.  Step k must see r columns k+1, k+2 and d columns k, k+1
+    of the scenario (last column held), and only d_k drives the plant."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    assert nr == 2 and nd == 2
+    T, N = 25, 200
+    rng = np.random.default_rng(12)
+    lo, hi = util.theta_range(name, 0.1)
+    X0 = rng.uniform(lo[:nx], hi[:nx], (N, nx)).T
+    rs = 0.05 * np.cumsum(rng.standard_normal((1, 18)), axis=1) * 0.2     # shorter than the horizon
+    ds = 0.02 * rng.standard_normal((1, 30))
+    Gd1 = mpc.Gd[:, :1]
+    out = g.simulate(mpc.F, mpc.G, X0, N=T, Gd=Gd1, warm_start=True, want_traj=True,
+                     r_traj=rs, d_traj=ds, r_preview=2, d_preview=2)
+    # the same loop spelled out for the oracle: explicit windows, zero-padded Gd
+    hold = lambda v, n: np.hstack([v, np.repeat(v[:, -1:], max(0, n - v.shape[1]), axis=1)])
+    rsx, dsx = hold(rs, T + 3), hold(ds, T + 3)
+    Gdp = np.hstack([Gd1, np.zeros((nx, 1))])
+    # stepwise restatement with the oracle's single solves (tolerance: BLAS vs fma-chain dynamics)
+    for q in range(0, N, 40):
+        x, u = X0[:, q].copy(), np.zeros(mpc.nu)
+        for k in range(T):
+            th = np.concatenate([x, rsx[0, k + 1:k + 3], dsx[0, k:k + 2], u[:nup]])
+            u, flag, _ = P.solve(th)
+            assert np.allclose(u, out["Utraj"][q, k], rtol=0, atol=2e-5)
+            x = mpc.F @ x + mpc.G @ u + Gd1[:, 0] * dsx[0, k]
+        assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=2e-5)
+    # bit-exact against the oracle's own windowed loop
+    Rflat = np.asfortranarray(rsx[:, 1:T + 2]); Dflat = np.asfortranarray(dsx[:, 0:T + 1])
+    ref = P.simulate_batch(mpc.F, mpc.G, Gdp, X0, None, None, None, T, nr, nd, nup, warm=True, want_traj=True,
+                           Rtraj=Rflat, Dtraj=Dflat, ext=dict(rstride=1, dstride=1))
+    assert np.array_equal(out["Utraj"], ref["Utraj"]) and np.array_equal(out["Xend"], ref["Xend"])
+    assert np.array_equal(out["exitflag"], ref["flag"])
