@@ -229,6 +229,16 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
                                double *Xend, double *Ulast, double *Utraj,
                                int32_t *exitflag, int32_t *iters);
 
+/* Closed loops with the EXPLICIT law: N copies of Simulation(empc, scenario)
+ * (src/simulation.jl:37-116 accepts an ExplicitMPC) with the linear dynamics of src/model.jl:70;
+ * every step walks the tree on chip.  Arguments as lmpc_gpu_simulate_batch_traj (Rtraj / Dtraj
+ * nullable HOST trajectories shared by all loops); nth <= 16, nu <= 4. */
+int lmpc_gpu_simulate_bst_batch(lmpc_bst *t, const double *F, const double *G, const double *Gd,
+                                int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                                const double *X0, const double *R, const double *D, const double *U0,
+                                const double *Rtraj, const double *Dtraj, int64_t N, int32_t T,
+                                double *Xend, double *Ulast, double *Utraj);
+
 /* One process, several GPUs (BASELINE north_star: "the batch is sharded by contiguous theta ranges
  * across the 8 B200s of one box with no inter-GPU traffic beyond a final result gather").
  * create_multi builds one replica of the controller per listed device (devices NULL = 0..n-1);

@@ -763,6 +763,73 @@ int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double 
   return 0;
 }
 
+int lmpc_gpu_simulate_bst_batch(lmpc_bst *t, const double *F, const double *G, const double *Gd,
+                                int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                                const double *X0, const double *R, const double *D, const double *U0,
+                                const double *Rtraj, const double *Dtraj, int64_t N, int32_t T,
+                                double *Xend, double *Ulast, double *Utraj) {
+  if (!t || !F || !G || !X0 || !Xend || !Ulast || N < 0 || T < 0 || (nd > 0 && !Gd))
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_simulate_bst_batch: bad argument%s");
+  const int nth = t->dev.nth, nu = t->dev.nu;
+  if (nx + nr + nd + nuprev != nth || nuprev > nu)
+    return set_err(LMPC_E_INVALID, "simulate_bst_batch: nx + nr + nd + nuprev must equal nth%s");
+  if (nth > 16 || nu > 4)
+    return set_err(LMPC_E_UNSUPPORTED, "simulate_bst_batch: supports nth <= 16 and nu <= 4%s");
+  if (N == 0) return 0;
+  std::lock_guard<std::mutex> lock(t->mu);
+  CUDA_OK(cudaSetDevice(t->device));
+  std::vector<double> dynh;
+  push_rowmajor(dynh, F, nx, nx);
+  push_rowmajor(dynh, G, nx, nu);
+  if (nd > 0) push_rowmajor(dynh, Gd, nx, nd);
+  size_t oR = 0, oD = 0;
+  if (Rtraj && nr > 0) { oR = dynh.size(); dynh.insert(dynh.end(), Rtraj, Rtraj + (size_t)nr * T); }
+  if (Dtraj && nd > 0) { oD = dynh.size(); dynh.insert(dynh.end(), Dtraj, Dtraj + (size_t)nd * T); }
+  Slot &s0 = t->slots[0];
+  if (s0.aux[2].reserve(dynh.size() * sizeof(double))) return LMPC_E_CUDA;
+  CUDA_OK(cudaMemcpyAsync(s0.aux[2].p, dynh.data(), dynh.size() * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+  CUDA_OK(cudaStreamSynchronize(t->stream));
+  const double *db = (const double *)s0.aux[2].p;
+  const double *dR = (Rtraj && nr > 0) ? db + oR : nullptr, *dD = (Dtraj && nd > 0) ? db + oD : nullptr;
+  auto launch = [&](const double *x0, const double *r, const double *d, const double *u0, int64_t cnt, double *xe,
+                    double *ul, double *ut, cudaStream_t st) -> int {
+    int e = launch_bst_sim(t->dev, db, nx, nr, nd, nuprev, x0, r, d, u0, dR, dD, cnt, T, xe, ul, ut, t->sm_count, st);
+    if (e) return set_err(LMPC_E_CUDA, "bst closed-loop kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    g_launches.fetch_add(1);
+    return 0;
+  };
+  if (is_device_ptr(X0)) {
+    int rc = launch(X0, R, D, U0, N, Xend, Ulast, Utraj, t->stream);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(t->stream));
+    return 0;
+  }
+  for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
+    const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;
+    Slot &s = t->slots[c % kSlots];
+    const double *src[4] = {X0, R, D, U0};
+    const int ln[4] = {nx, nr, nd, nuprev};
+    const double *dv[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int g = 0; g < 4; ++g) {
+      if (!src[g] || ln[g] == 0) continue;
+      const size_t bytes = (size_t)cnt * ln[g] * sizeof(double);
+      if (s.in[g].reserve(bytes)) return LMPC_E_CUDA;
+      CUDA_OK(cudaMemcpyAsync(s.in[g].p, src[g] + off * ln[g], bytes, cudaMemcpyHostToDevice, s.stream));
+      dv[g] = (const double *)s.in[g].p;
+    }
+    if (s.aux[0].reserve((size_t)cnt * nx * 8) || s.u.reserve((size_t)cnt * nu * 8)) return LMPC_E_CUDA;
+    if (Utraj && s.aux[1].reserve((size_t)cnt * nu * T * 8)) return LMPC_E_CUDA;
+    int rc = launch(dv[0], dv[1], dv[2], dv[3], cnt, (double *)s.aux[0].p, (double *)s.u.p,
+                    Utraj ? (double *)s.aux[1].p : nullptr, s.stream);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(Xend + off * nx, s.aux[0].p, (size_t)cnt * nx * 8, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaMemcpyAsync(Ulast + off * nu, s.u.p, (size_t)cnt * nu * 8, cudaMemcpyDeviceToHost, s.stream));
+    if (Utraj) CUDA_OK(cudaMemcpyAsync(Utraj + off * nu * T, s.aux[1].p, (size_t)cnt * nu * T * 8, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(t->slots[i].stream));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // one process, several GPUs: contiguous theta ranges, one worker thread per device
 // ---------------------------------------------------------------------------------------

@@ -175,6 +175,140 @@ int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t
   return launch_k4s<NTH, false, false>(t, bl, Theta, N, U, region, sm_count, s);
 }
 
+// ---- closed loop with the explicit law: Simulation(empc, scenario) (src/simulation.jl:37-116) ----
+// Thread per closed loop: theta = [x; r; d; u_prev] lives in registers, every step walks the tree
+// (same tables, same arithmetic as bst_eval_kernel), applies the leaf law (+ clipping) and the
+// linear dynamics x+ = F x + G u + Gd d (src/model.jl:70); F, G, Gd sit behind the tables in shared
+// memory.  Run-time sizes nx, nr, nd, nu <= NTH are handled by fully unrolled, predicated loops so
+// that theta never leaves the register file.
+constexpr int K4S_BLOCK = 256;
+constexpr int K4S_MAXU = 4;
+
+template <int NTH>
+__global__ void __launch_bounds__(K4S_BLOCK)
+bst_sim_kernel(const double *__restrict__ blk, BstLayout bl, int nu, int has_clip, const double *__restrict__ dyn,
+               int nx, int nr, int nd, int nup, const double *__restrict__ X0, const double *__restrict__ R,
+               const double *__restrict__ D, const double *__restrict__ U0, const double *__restrict__ Rtraj,
+               const double *__restrict__ Dtraj, int64_t N, int T, double *__restrict__ Xend,
+               double *__restrict__ Ulast, double *__restrict__ Utraj) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  stage_constants_tma(smem, blk, bl.total, &mbar);
+  const int ndyn = nx * (nx + nu + nd);
+  double *dsm = smem + ((bl.total + 1) & ~1);
+  for (int i = threadIdx.x; i < ndyn; i += K4S_BLOCK) dsm[i] = dyn[i];
+  __syncthreads();
+  const double *Fm = dsm, *Gm = dsm + nx * nx, *Gdm = Gm + nx * nu;
+  const int rep = bl.rep, pairs = bl.pairs;
+  const double2 *hp2 = reinterpret_cast<const double2 *>(smem + bl.ohp) + (threadIdx.x & (rep - 1));
+  const double2 *fb2 = reinterpret_cast<const double2 *>(smem + bl.ofb) + (threadIdx.x & (rep - 1));
+  const double *clip = smem + bl.oclip;
+  const int2 *nodes2 = reinterpret_cast<const int2 *>(smem + bl.onodes);
+  const uint32_t *nodes1 = reinterpret_cast<const uint32_t *>(smem + bl.onodes);
+  const bool packed = bl.packed != 0;
+  auto load_node = [&](int i) -> int2 {
+    if (packed) { const uint32_t w = nodes1[i]; return make_int2((int)(w >> 16), (int)(w & 0xffffu)); }
+    return nodes2[i];
+  };
+  constexpr int P2 = (NTH + 2) / 2;
+  for (int64_t q = (int64_t)blockIdx.x * K4S_BLOCK + threadIdx.x; q < N; q += (int64_t)gridDim.x * K4S_BLOCK) {
+    double th[NTH], u[K4S_MAXU];
+#pragma unroll
+    for (int c = 0; c < NTH; ++c) {
+      double v = 0.0;
+      if (c < nx) v = X0[q * nx + c];
+      else if (c < nx + nr) v = R ? R[q * nr + (c - nx)] : 0.0;
+      else if (c < nx + nr + nd) v = D ? D[q * nd + (c - nx - nr)] : 0.0;
+      th[c] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < K4S_MAXU; ++i) u[i] = (U0 && i < nup) ? U0[q * nup + i] : 0.0;
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int c = 0; c < NTH; ++c) {
+        if (Rtraj && c >= nx && c < nx + nr) th[c] = Rtraj[(size_t)t * nr + (c - nx)];
+        if (Dtraj && c >= nx + nr && c < nx + nr + nd) th[c] = Dtraj[(size_t)t * nd + (c - nx - nr)];
+#pragma unroll
+        for (int i = 0; i < K4S_MAXU; ++i) if (c == nx + nr + nd + i && i < nup) th[c] = u[i];
+      }
+      // tree walk (ParametricDAQP.evaluate, src/utils.jl:57)
+      int id = 0;
+      int2 nd2 = load_node(0);
+      while (nd2.x != 0) {
+        const double2 *h2 = hp2 + (size_t)nd2.y * pairs * rep;
+        double v[2 * P2];
+#pragma unroll
+        for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c * rep]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < NTH; ++c) acc = fma(v[c], th[c], acc);
+        id = id + nd2.x + (acc <= v[NTH] ? 0 : 1);
+        nd2 = load_node(id);
+      }
+      const int reg = nd2.y;
+#pragma unroll
+      for (int i = 0; i < K4S_MAXU; ++i) {
+        if (i < nu) {
+          const double2 *f2 = fb2 + ((size_t)reg * nu + i) * pairs * rep;
+          double v[2 * P2];
+#pragma unroll
+          for (int c = 0; c < P2; ++c) { const double2 t2 = f2[c * rep]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+          double acc = v[NTH];
+#pragma unroll
+          for (int c = 0; c < NTH; ++c) acc = fma(v[c], th[c], acc);
+          if (has_clip) {
+            if (acc < clip[2 * i]) acc = clip[2 * i];
+            if (acc > clip[2 * i + 1]) acc = clip[2 * i + 1];
+          }
+          u[i] = acc;
+          if (Utraj) Utraj[((size_t)q * T + t) * nu + i] = acc;
+        }
+      }
+      // x+ = F x + G u + Gd d, fma chains in index order (oracle: orc_bst_simulate_batch)
+      double xn[NTH];
+#pragma unroll
+      for (int i = 0; i < NTH; ++i) {
+        double acc = 0.0;
+        if (i < nx) {
+#pragma unroll
+          for (int c = 0; c < NTH; ++c) if (c < nx) acc = fma(Fm[i * nx + c], th[c], acc);
+#pragma unroll
+          for (int c = 0; c < K4S_MAXU; ++c) if (c < nu) acc = fma(Gm[i * nu + c], u[c], acc);
+#pragma unroll
+          for (int c = 0; c < NTH; ++c) if (c >= nx + nr && c < nx + nr + nd) acc = fma(Gdm[i * nd + (c - nx - nr)], th[c], acc);
+        }
+        xn[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < NTH; ++i) if (i < nx) th[i] = xn[i];
+    }
+#pragma unroll
+    for (int c = 0; c < NTH; ++c) if (c < nx) Xend[q * nx + c] = th[c];
+#pragma unroll
+    for (int i = 0; i < K4S_MAXU; ++i) if (i < nu) Ulast[q * nu + i] = u[i];
+  }
+}
+
+template <int NTH>
+int launch_k4_sim(const BstDev &t, const BstLayout &bl, const double *dyn, int nx, int nr, int nd, int nup,
+                  const double *X0, const double *R, const double *D, const double *U0, const double *Rtraj,
+                  const double *Dtraj, int64_t N, int T, double *Xend, double *Ulast, double *Utraj,
+                  int sm_count, cudaStream_t s) {
+  auto kern = bst_sim_kernel<NTH>;
+  const size_t smem = ((size_t)((bl.total + 1) & ~1) + (size_t)nx * (nx + t.nu + nd)) * sizeof(double);
+  if (smem > 220 * 1024) return (int)cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K4S_BLOCK, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (N + K4S_BLOCK - 1) / K4S_BLOCK;
+  if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+  kern<<<(unsigned)blocks, K4S_BLOCK, smem, s>>>(t.blk, bl, t.nu, t.has_clip, dyn, nx, nr, nd, nup, X0, R, D, U0,
+                                                 Rtraj, Dtraj, N, T, Xend, Ulast, Utraj);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
@@ -189,6 +323,23 @@ int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, 
     K4_CASE(1) K4_CASE(2) K4_CASE(3) K4_CASE(4) K4_CASE(5) K4_CASE(6) K4_CASE(7) K4_CASE(8)
     K4_CASE(9) K4_CASE(10) K4_CASE(11) K4_CASE(12) K4_CASE(13) K4_CASE(14) K4_CASE(15) K4_CASE(16)
     default: return launch_k4<0>(t, bl, Theta, N, U, region, sm_count, s);
+  }
+}
+
+int launch_bst_sim(const BstDev &t, const double *dyn, int nx, int nr, int nd, int nup, const double *X0,
+                   const double *R, const double *D, const double *U0, const double *Rtraj, const double *Dtraj,
+                   int64_t N, int T, double *Xend, double *Ulast, double *Utraj, int sm_count, void *stream) {
+  if (N <= 0) return 0;
+  if (t.nth < 1 || t.nth > 16 || t.nu > K4S_MAXU || nx + nr + nd + nup != t.nth) return (int)cudaErrorInvalidValue;
+  BstLayout bl;
+  bl.onodes = t.onodes; bl.ohp = t.ohp; bl.ofb = t.ofb; bl.oclip = t.oclip;
+  bl.pairs = t.pairs; bl.rep = t.rep; bl.packed = t.packed; bl.total = t.total;
+  cudaStream_t s = (cudaStream_t)stream;
+#define K4S_CASE(NN) case NN: return launch_k4_sim<NN>(t, bl, dyn, nx, nr, nd, nup, X0, R, D, U0, Rtraj, Dtraj, N, T, Xend, Ulast, Utraj, sm_count, s);
+  switch (t.nth) {
+    K4S_CASE(1) K4S_CASE(2) K4S_CASE(3) K4S_CASE(4) K4S_CASE(5) K4S_CASE(6) K4S_CASE(7) K4S_CASE(8)
+    K4S_CASE(9) K4S_CASE(10) K4S_CASE(11) K4S_CASE(12) K4S_CASE(13) K4S_CASE(14) K4S_CASE(15) K4S_CASE(16)
+    default: return (int)cudaErrorInvalidValue;
   }
 }
 

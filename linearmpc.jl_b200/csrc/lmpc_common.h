@@ -116,4 +116,8 @@ struct BstDev {
 };
 int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
                     int sm_count, void *stream);
+// closed loop with the explicit law; dyn = [F | G | Gd] row-major on the device; all pointers device
+int launch_bst_sim(const BstDev &t, const double *dyn, int nx, int nr, int nd, int nup, const double *X0,
+                   const double *R, const double *D, const double *U0, const double *Rtraj, const double *Dtraj,
+                   int64_t N, int T, double *Xend, double *Ulast, double *Utraj, int sm_count, void *stream);
 int launch_fp64_peak(int iters, double *d_out, int sm_count, void *stream);

@@ -91,6 +91,8 @@ def load_library():
     L.lmpc_gpu_create_bst.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, C.c_int,
                                       C.POINTER(vp)]
     L.lmpc_gpu_destroy_bst.argtypes = [vp]
+    L.lmpc_gpu_simulate_bst_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32,
+                                              vp, vp, vp]
     L.lmpc_gpu_evaluate_batch.argtypes = [vp, vp, i64, vp, vp]
     L.lmpc_gpu_evaluate_batch_async.argtypes = [vp, vp, i64, vp, vp, vp]
     L.lmpc_gpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -631,6 +633,44 @@ class GpuExplicitMPC:
         U, _ = self.evaluate(self.form_parameter(x, r, d, uprev), want_region=False)
         self.uprev = U[:, -1].copy()
         return U[:, 0].copy() if single else U
+
+    def simulate(self, F, G, x0, r=None, d=None, u0=None, N=100, Gd=None, want_traj=False,
+                 r_traj=None, d_traj=None):
+        """Simulation(empc, scenario) (simulation.jl:37-116) for every column of x0: N steps of the
+        explicit law + linear dynamics on the GPU.  Arguments as GpuMPC.simulate."""
+        if self.dims is None:
+            raise ValueError("GpuExplicitMPC was built without dims=(nx, nr, nd, nuprev)")
+        nx, nr, nd, nup = self.dims
+        steps = int(N)
+        X0 = _colmajor(x0, nx)
+        n = X0.shape[1]
+        Fm, Gm = np.asfortranarray(np.asarray(F, float)), np.asfortranarray(np.asarray(G, float).reshape(nx, -1))
+        Gdm = np.asfortranarray(np.asarray(Gd, float).reshape(nx, -1)) if (nd > 0 and Gd is not None) else None
+        def bc(v, rows):
+            if rows == 0:
+                return None
+            if v is None:
+                return np.zeros((rows, n), order="F")
+            v = np.asarray(v, float)
+            if v.ndim == 1:
+                v = np.repeat(v.reshape(rows, 1), n, axis=1)
+            return np.asfortranarray(v)
+        def hold(v, rows):
+            if v is None or rows == 0:
+                return None
+            v = np.asarray(v, float).reshape(rows, -1)
+            if v.shape[1] < steps:
+                v = np.hstack([v, np.repeat(v[:, -1:], steps - v.shape[1], axis=1)])
+            return np.asfortranarray(v[:, :steps])
+        Rm, Dm, Um = bc(r, nr), bc(d, nd), bc(u0, nup) if u0 is not None else None
+        Rt, Dt = hold(r_traj, nr), hold(d_traj, nd)
+        Xend = np.zeros((nx, n), order="F")
+        Ulast = np.zeros((self.nu, n), order="F")
+        Utraj = np.zeros((n, steps, self.nu)) if want_traj else None
+        _check(lib().lmpc_gpu_simulate_bst_batch(self._t, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
+                                                 _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), _ptr(Rt), _ptr(Dt),
+                                                 n, steps, _ptr(Xend), _ptr(Ulast), _ptr(Utraj)))
+        return dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj)
 
 
 # ---------------------------------------------------------------------------------------------

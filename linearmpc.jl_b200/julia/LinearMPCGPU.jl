@@ -243,4 +243,28 @@ function LinearMPC.compute_control(g::GpuExplicitMPC, X::AbstractMatrix; r=nothi
     return U
 end
 
+"""
+    simulate(ge, X0; N, r, d) -> (Xend, Ulast)
+
+`Simulation(empc, scenario)` (src/simulation.jl:37-116) for every column of X0, on the GPU: the tree
+walk and the model's linear dynamics run on chip for N steps.
+"""
+function simulate(ge::GpuExplicitMPC, X0::Matrix{Float64}; N::Integer=100, r=nothing, d=nothing)
+    mdl = ge.empc.model
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(ge.empc)
+    M = size(X0, 2)
+    traj(v, k) = (k == 0 || isnothing(v)) ? C_NULL :
+        (V = v isa AbstractMatrix ? Matrix{Float64}(v) : reshape(Vector{Float64}(v), k, 1);
+         hcat(V[:, 1:min(N, size(V, 2))], repeat(V[:, end], 1, max(0, N - size(V, 2)))))
+    Rt, Dt = traj(r, nr), traj(d, nd)
+    Xend = similar(X0); Ulast = Matrix{Float64}(undef, ge.nu, M)
+    check(ccall((:lmpc_gpu_simulate_bst_batch, liblmpcgpu), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ge.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
+                X0, C_NULL, C_NULL, C_NULL, Rt, Dt, M, N, Xend, Ulast, C_NULL))
+    return Xend, Ulast
+end
+
 end # module

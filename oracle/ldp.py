@@ -196,6 +196,22 @@ class OracleBst:
         self.c = _Bst(self.nth, self.nu, self.hp.shape[0], self.fb.shape[0], len(self.hl),
                       _dp(self.hp), _dp(self.fb), _dp(self.clip), _ip(self.hl), _ip(self.jl))
 
+    def simulate_batch(self, Fx, Gx, Gdx, X0, R, D, U0, T, nr, nd, nuprev, nthreads=0, want_traj=False,
+                       Rtraj=None, Dtraj=None):
+        """Closed loop with the explicit law; arguments as OracleProblem.simulate_batch."""
+        nx = np.asarray(Fx).shape[0]
+        c = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, float).T)
+        X0c, Rc, Dc, U0c, Rt, Dt = c(X0), c(R), c(D), c(U0), c(Rtraj), c(Dtraj)
+        N = X0c.shape[0]
+        Fx, Gx = np.ascontiguousarray(Fx, float), np.ascontiguousarray(np.asarray(Gx, float).reshape(nx, -1))
+        Gdx = np.ascontiguousarray(Gdx, float) if nd > 0 else np.zeros((nx, 0))
+        Xend, Ulast = np.zeros((N, nx)), np.zeros((N, self.nu))
+        Utraj = np.zeros((N, T, self.nu)) if want_traj else None
+        lib().orc_bst_simulate_batch(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
+                                     _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), _dp(Rt), _dp(Dt), C.c_int64(N), T,
+                                     _dp(Xend), _dp(Ulast), _dp(Utraj), C.c_int(nthreads))
+        return dict(Xend=Xend.T, Ulast=Ulast.T, Utraj=Utraj)
+
     def evaluate_batch(self, Theta, nthreads=0):
         Th = np.ascontiguousarray(np.asarray(Theta, float).T)
         N = Th.shape[0]

@@ -550,6 +550,67 @@ static void bst_chunk(void *vc, int64_t lo, int64_t hi) {
     if (b->region) b->region[q] = reg;
   }
 }
+/* closed loop with the explicit law: Simulation(empc, scenario), simulation.jl:37-116 */
+typedef struct {
+  const orc_bst *t; int nx, nr, nd, nuprev; const double *Fx, *Gx, *Gdx, *X0, *R, *D, *U0, *Rtraj, *Dtraj;
+  int T; double *Xend, *Ulast, *Utraj;
+} bsim_ctx;
+static void bsim_chunk(void *vc, int64_t lo, int64_t hi) {
+  bsim_ctx *s = (bsim_ctx *)vc;
+  const orc_bst *t = s->t;
+  const int nth = t->nth, nu = t->nu, ld = nth + 1, nx = s->nx, nr = s->nr, nd = s->nd, nup = s->nuprev;
+  double *th = (double *)calloc(nth, sizeof(double)), *xn = (double *)calloc(nx, sizeof(double));
+  double *u = (double *)calloc(nu, sizeof(double));
+  for (int64_t q = lo; q < hi; ++q) {
+    for (int i = 0; i < nx; ++i) th[i] = s->X0[q * nx + i];
+    for (int i = 0; i < nu; ++i) u[i] = (s->U0 && i < nup) ? s->U0[q * nup + i] : 0.0;
+    for (int k = 0; k < s->T; ++k) {
+      for (int i = 0; i < nr; ++i) th[nx + i] = s->Rtraj ? s->Rtraj[(size_t)k * nr + i] : (s->R ? s->R[q * nr + i] : 0.0);
+      for (int i = 0; i < nd; ++i) th[nx + nr + i] = s->Dtraj ? s->Dtraj[(size_t)k * nd + i] : (s->D ? s->D[q * nd + i] : 0.0);
+      for (int i = 0; i < nup; ++i) th[nx + nr + nd + i] = u[i];
+      int id = 0;
+      for (;;) {
+        int jmp = t->jump_list[id];
+        if (jmp == 0) break;
+        const double *hp = t->halfplanes + (size_t)t->hp_list[id] * ld;
+        double acc = 0.0;
+        for (int c = 0; c < nth; ++c) acc = fma(hp[c], th[c], acc);
+        id = id + jmp + (acc <= hp[nth] ? 0 : 1);
+      }
+      const double *fb = t->feedbacks + (size_t)t->hp_list[id] * nu * ld;
+      for (int i = 0; i < nu; ++i) {
+        double acc = fb[i * ld + nth];
+        for (int c = 0; c < nth; ++c) acc = fma(fb[i * ld + c], th[c], acc);
+        if (t->clip) {
+          if (acc < t->clip[2 * i]) acc = t->clip[2 * i];
+          if (acc > t->clip[2 * i + 1]) acc = t->clip[2 * i + 1];
+        }
+        u[i] = acc;
+        if (s->Utraj) s->Utraj[((size_t)q * s->T + k) * nu + i] = acc;
+      }
+      for (int i = 0; i < nx; ++i) {
+        double acc = 0.0;
+        for (int c = 0; c < nx; ++c) acc = fma(s->Fx[i * nx + c], th[c], acc);
+        for (int c = 0; c < nu; ++c) acc = fma(s->Gx[i * nu + c], u[c], acc);
+        for (int c = 0; c < nd; ++c) acc = fma(s->Gdx[i * nd + c], th[nx + nr + c], acc);
+        xn[i] = acc;
+      }
+      for (int i = 0; i < nx; ++i) th[i] = xn[i];
+    }
+    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = th[i];
+    for (int i = 0; i < nu; ++i) s->Ulast[q * nu + i] = u[i];
+  }
+  free(th); free(xn); free(u);
+}
+void orc_bst_simulate_batch(const orc_bst *t, int nx, int nr, int nd, int nuprev,
+                            const double *Fx, const double *Gx, const double *Gdx,
+                            const double *X0, const double *R, const double *D, const double *U0,
+                            const double *Rtraj, const double *Dtraj, int64_t N, int T,
+                            double *Xend, double *Ulast, double *Utraj, int nthreads) {
+  bsim_ctx s = {t, nx, nr, nd, nuprev, Fx, Gx, Gdx, X0, R, D, U0, Rtraj, Dtraj, T, Xend, Ulast, Utraj};
+  parallel_for(N, nthreads, bsim_chunk, &s);
+}
+
 void orc_bst_evaluate_batch(const orc_bst *t, const double *Theta, int64_t N, double *U,
                             int32_t *region, int nthreads) {
   bst_ctx b = {t, Theta, U, region};

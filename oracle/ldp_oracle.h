@@ -105,6 +105,13 @@ typedef struct {
 } orc_bst;
 void orc_bst_evaluate_batch(const orc_bst *t, const double *Theta, int64_t N, double *U,
                             int32_t *region, int nthreads);
+/* closed loop with the explicit law (row-major Fx nx x nx, Gx nx x nu, Gdx nx x nd; trajectories as in
+ * orc_simulate_batch_traj) */
+void orc_bst_simulate_batch(const orc_bst *t, int nx, int nr, int nd, int nuprev,
+                            const double *Fx, const double *Gx, const double *Gdx,
+                            const double *X0, const double *R, const double *D, const double *U0,
+                            const double *Rtraj, const double *Dtraj, int64_t N, int T,
+                            double *Xend, double *Ulast, double *Utraj, int nthreads);
 
 int orc_num_threads(void);
 

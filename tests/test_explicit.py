@@ -168,3 +168,50 @@ def test_product_explicit_builder_matches_implicit_and_enumeration(lmpc):
     Th = mpqp.sample_theta(lo, hi, 20000, seed=6)
     U, _ = empc.evaluate(Th)
     assert np.max(np.abs(U - P.solve_batch(Th)["U"])) < 1e-10
+
+
+def test_oracle_explicit_closed_loop_equals_implicit_closed_loop():
+    """Simulation(empc) vs Simulation(mpc): the reference asserts 1e-10 between explicit and implicit
+    (runtests.jl:381,490); here over 100 closed-loop steps from the README's initial state."""
+    z, B = load_tree()
+    mpc = mpqp.invpend()
+    qp = mpqp.mpc2mpqp(mpc)
+    P = ldp.OracleProblem(mpqp.qp2ldp(qp, 1), 1)
+    X0 = np.array([[5.0, 5, 0, 0], [1.0, -2, 0.1, 0], [0, 0, 0.15, 0], [10.0, -8, 0.2, 1]]).T
+    R = np.zeros((2, X0.shape[1]))
+    a = B.simulate_batch(mpc.F, mpc.G, None, X0, R, None, None, 100, 2, 0, 1, want_traj=True)
+    b = P.simulate_batch(mpc.F, mpc.G, None, X0, R, None, None, 100, 2, 0, 1, want_traj=True)
+    assert np.max(np.abs(a["Utraj"] - b["Utraj"])) < 1e-10
+    assert abs(a["Utraj"][0, 0, 0] - 1.7612519326) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_explicit_closed_loop_matches_oracle(lmpc):
+    """lmpc_gpu_simulate_bst_batch: tree walk + dynamics per step on chip, bit-identical to the
+    oracle's loop; with clipping, a reference trajectory, host and device buffers."""
+    import torch
+    z, _ = load_tree()
+    clip = np.array([[-2.0, 2.0]])
+    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=clip)
+    mpc = mpqp.invpend()
+    g = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=clip,
+                            dims=mpc.parameter_dims())
+    rng = np.random.default_rng(3)
+    N, T = 5000, 60
+    lo, hi = mpqp.invpend_range(0.2)
+    X0 = rng.uniform(lo[:4], hi[:4], (N, 4)).T
+    R = np.zeros((2, N))
+    out = g.simulate(mpc.F, mpc.G, X0, r=R, N=T, want_traj=True)
+    ref = B.simulate_batch(mpc.F, mpc.G, None, X0, R, None, None, T, 2, 0, 1, want_traj=True)
+    assert np.array_equal(out["Utraj"], ref["Utraj"]) and np.array_equal(out["Xend"], ref["Xend"])
+    assert np.array_equal(out["Ulast"], ref["Ulast"])
+    Rt = np.zeros((2, 40)); Rt[0, 20:] = 0.05
+    out2 = g.simulate(mpc.F, mpc.G, X0, N=T, want_traj=True, r_traj=Rt)
+    Rfull = np.hstack([Rt, np.repeat(Rt[:, -1:], T - 40, axis=1)])
+    ref2 = B.simulate_batch(mpc.F, mpc.G, None, X0, None, None, None, T, 2, 0, 1, want_traj=True, Rtraj=Rfull)
+    assert np.array_equal(out2["Utraj"], ref2["Utraj"]) and np.array_equal(out2["Xend"], ref2["Xend"])
+    assert not np.array_equal(out2["Utraj"], out["Utraj"])
+    # the implicit closed loop on the GPU gives the same controls to 1e-10
+    gi = lmpc.setup_gpu(mpqp.mpc2mpqp(mpc), nu=1, dims=mpc.parameter_dims())
+    imp = gi.simulate(mpc.F, mpc.G, X0, r=R, N=T, want_traj=True)
+    assert np.max(np.abs(imp["Utraj"] - out["Utraj"])) < 1e-10

@@ -144,6 +144,33 @@ if "aircraft_sim" in which:
 if "invpend_sim" in which:
     # the README's own closed loop (README.md:55-60) as a Monte-Carlo batch: 100 steps = 1 s
     sim_cfg("invpend", 0.25, 2_000_000, 100, [0.0, 0.0], "invpend_closed_loop")
+if "explicit_sim" in which:
+    # closed loop with the explicit law (Simulation(empc)): 2e6 x0, 100 steps, tree walk + dynamics on chip
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
+    mpc = util.controller("invpend")
+    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], dims=mpc.parameter_dims())
+    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    N, T = 2_000_000, 100
+    lo, hi = util.theta_range("invpend", 0.25)
+    X0 = rand_theta(lo[:4], hi[:4], N)
+    R = torch.zeros((N, 2), dtype=torch.float64, device=dev)
+    Xe = torch.empty((N, 4), dtype=torch.float64, device=dev); Ul = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    Fm, Gm = np.asfortranarray(mpc.F), np.asfortranarray(mpc.G)
+    L = lmpc_b200.lib()
+    def run():
+        rc = L.lmpc_gpu_simulate_bst_batch(ge._t, Fm.ctypes.data, Gm.ctypes.data, None, 4, 2, 0, 1, X0.data_ptr(),
+                                           R.data_ptr(), None, None, None, None, N, T, Xe.data_ptr(), Ul.data_ptr(), None)
+        assert rc == 0
+    run(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); run(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    ncpu = 50000
+    t1 = time.perf_counter()
+    ref = B.simulate_batch(mpc.F, mpc.G, None, X0[:ncpu].cpu().numpy().T, np.zeros((2, ncpu)), None, None, T, 2, 0, 1)
+    dc = time.perf_counter() - t1
+    same = bool(np.array_equal(Xe[:ncpu].cpu().numpy().T, ref["Xend"]))
+    print(json.dumps({"config": "explicit_invpend_closed_loop", "trajectories": N, "steps": T, "s": dt,
+                      "evaluations_per_s": N * T / dt, "cpu_port_evaluations_per_s": ncpu * T / dc,
+                      "cpu_cores": ldp.num_threads(), "bit_identical_to_oracle_on_sample": same}), flush=True)
 if "explicit" in which:
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
     ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
