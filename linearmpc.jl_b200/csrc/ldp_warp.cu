@@ -326,16 +326,23 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
 
 // one solve for theta in c.thw; returns the flag; u (lane c holds u_c) and iters by reference
 template <int UF, bool EQ>
-LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters,
+LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters, double &sho,
                          bool warm = false, unsigned long long wsu = 0ull, unsigned long long wsl = 0ull) {
   const LdpLayout &lay = *c.lay;
   const int lane = c.lane, m = lay.m, nth = lay.nth;
-  // mpc_update_qp: sh_j = Dth[j,:] theta for rows lane and lane + 32
+  // mpc_update_qp: sh_j = Dth[j,:] theta for rows lane and lane + 32.  When lanes are left over
+  // (m + nu <= 32) lanes m .. m+nu-1 ride along and accumulate the output shifts
+  // uoff_i + Uth[i,:] theta of mpc_get_solution in the same loop (sho on lane m + i).
   double sh0 = 0.0, sh1 = 0.0;
-  if (lane < m) {
-    const double *dr = c.cv.Dth + lane * nth;
+  const bool fold = m + lay.nu <= 32;
+  if (lane < m || (fold && lane < m + lay.nu)) {
+    const bool mine = lane < m;
+    const double *dr = mine ? c.cv.Dth + lane * nth : c.cv.Uth + (lane - m) * nth;
+    double acc = mine ? 0.0 : c.cv.uoff[lane - m];
 #pragma unroll 2
-    for (int t = 0; t < nth; ++t) sh0 = fma(dr[t], c.thw[t], sh0);
+    for (int t = 0; t < nth; ++t) acc = fma(dr[t], c.thw[t], acc);
+    sh0 = mine ? acc : 0.0;
+    sho = acc;
   }
   if (lane + 32 < m) {
     const double *dr = c.cv.Dth + (lane + 32) * nth;
@@ -381,9 +388,10 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
 }
 
 // mpc_get_solution: control_i = (R^-1 u)_i + uoff_i + Uth[i,:] theta, canonical lane sum over c
-LMPC_DEVINL double control_out_w(const WarpCtx &c, int i, double u) {
+LMPC_DEVINL double control_out_w(const WarpCtx &c, int i, double u, double sho) {
   const LdpLayout &lay = *c.lay;
   const double x = bfly_sum(c.lane < lay.n ? __dmul_rn(c.cv.Rinv[i * lay.n + c.lane], u) : 0.0);
+  if (lay.m + lay.nu <= 32) return __dadd_rn(x, shfl_d(sho, lay.m + i));   // accumulated by wq_solve
   double sh = c.cv.uoff[i];
   const double *ur = c.cv.Uth + i * lay.nth;
 #pragma unroll 2
@@ -433,10 +441,11 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
     __syncwarp();
     int iters;
     const bool warm = EQ && out.ws_u != nullptr;
-    const int flag = wq_solve<K2_UF_SOLVE, EQ>(c, s, true, u, iters, warm, warm ? out.ws_u[q * words] : 0ull,
+    double sho = 0.0;
+    const int flag = wq_solve<K2_UF_SOLVE, EQ>(c, s, true, u, iters, sho, warm, warm ? out.ws_u[q * words] : 0ull,
                                                warm ? out.ws_l[q * words] : 0ull);
     for (int i = 0; i < lay.nu; ++i) {
-      const double ctl = control_out_w(c, i, u);
+      const double ctl = control_out_w(c, i, u, sho);
       if (lane == 0) out.U[q * lay.nu + i] = ctl;
     }
     // active set as bit masks (m <= 64: one word each)
@@ -543,12 +552,13 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
         __syncwarp();
       }
       int iters;
-      const int f = wq_solve<K2_UF_SIM, EQ>(c, s, !(sd.warm && t > 0), u, iters);
+      double sho = 0.0;
+      const int f = wq_solve<K2_UF_SIM, EQ>(c, s, !(sd.warm && t > 0), u, iters, sho);
       tot += iters;
       if (f < 0) { if (worst > 0 || f < worst) worst = f; }
       else if (worst > 0 && f > worst) worst = f;
       for (int i = 0; i < nu; ++i) {
-        const double ctl = control_out_w(c, i, u);
+        const double ctl = control_out_w(c, i, u, sho);
         if (lane == 0) {
           ucw[i] = ctl;
           if (sd.Utraj) sd.Utraj[(q * sd.T + t) * nu + i] = ctl;

@@ -11,7 +11,24 @@ def rand_theta(lo, hi, N):
     gen = torch.Generator(device=dev); gen.manual_seed(1234)
     T = torch.rand((N, len(lo)), dtype=torch.float64, device=dev, generator=gen)
     return T * torch.tensor(hi - lo, device=dev) + torch.tensor(lo, device=dev)
-if which == "bst":
+if which == "sim":
+    mpc = util.controller("aircraft"); qp = mpqp.mpc2mpqp(mpc)
+    g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    N, T = 500_000, 40
+    lo, hi = util.theta_range("aircraft", 0.25)
+    X0 = rand_theta(lo[:nx], hi[:nx], N)
+    R = torch.tensor([0.1, 0.0], dtype=torch.float64, device=dev).repeat(N, 1).contiguous()
+    D = torch.zeros((N, nd), dtype=torch.float64, device=dev)
+    Xe = torch.empty((N, nx), dtype=torch.float64, device=dev); Ul = torch.empty((N, 2), dtype=torch.float64, device=dev)
+    fl = torch.empty(N, dtype=torch.int32, device=dev)
+    Fm, Gm, Gdm = [np.asfortranarray(a) for a in (mpc.F, mpc.G, mpc.Gd)]
+    for _ in range(3):
+        rc = lmpc_b200.lib().lmpc_gpu_simulate_batch(g._h, Fm.ctypes.data, Gm.ctypes.data, Gdm.ctypes.data, nx, nr, nd, nup,
+                                                     X0.data_ptr(), R.data_ptr(), D.data_ptr(), None, N, T, 1,
+                                                     Xe.data_ptr(), Ul.data_ptr(), None, fl.data_ptr(), None)
+        assert rc == 0
+elif which == "bst":
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
     ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
     N = 20_000_000
