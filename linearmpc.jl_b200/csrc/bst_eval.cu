@@ -43,7 +43,15 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   }
   const int nth = NTH > 0 ? NTH : nth_rt;
   const int rep = bl.rep, pairs = bl.pairs;
-  const double2 *hp2 = reinterpret_cast<const double2 *>(base + bl.ohp) + (threadIdx.x & (rep - 1));
+  // replica choice for the half-plane rows: near the root the lanes of a warp sit on a handful of
+  // nodes, so the replica is picked by NODE id there (lanes on the same node share one broadcast
+  // read; breadth-first ids make the <= rep nodes of a level hit distinct bank groups); deeper
+  // down the walks have scattered and the replica is picked by LANE (exactly 4 wavefronts per load)
+  const double2 *hp0 = reinterpret_cast<const double2 *>(base + bl.ohp);
+  const int lane_rep = threadIdx.x & (rep - 1);
+#ifndef K4_NODE_REP_IDS
+#define K4_NODE_REP_IDS 15          // node ids below this (levels 0..3 of a breadth-first tree)
+#endif
   const double2 *fb2 = reinterpret_cast<const double2 *>(base + bl.ofb) + (threadIdx.x & (rep - 1));
   const double *clip = base + bl.oclip;
   const int2 *nodes2 = reinterpret_cast<const int2 *>(base + bl.onodes);
@@ -93,7 +101,7 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
     int id = 0;
     int2 nd = load_node(0);
     while (nd.x != 0) {
-      const double2 *h2 = hp2 + (size_t)nd.y * pairs * rep;
+      const double2 *h2 = hp0 + (size_t)nd.y * pairs * rep + (id < K4_NODE_REP_IDS ? (id & (rep - 1)) : lane_rep);
       double acc = 0.0, rhs;
       if (NTH > 0) {
         double v[2 * P2];
