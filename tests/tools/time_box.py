@@ -17,4 +17,4 @@ with torch.cuda.stream(s):
     for _ in range(20): g.solve_async(Th, U, fl, N=N, stream=s.cuda_stream)
     b.record(s); s.synchronize()
 ms = a.elapsed_time(b) / 20
-print(os.environ.get("LMPC_BOX_MINB", "default"), f"{ms:.4f} ms  {N/ms*1e3:.4e} solves/s  checksum {U.sum().item():.10f}")
+print(os.environ.get("LMPC_GPU_LIB", "in-tree"), f"{ms:.4f} ms  {N/ms*1e3:.4e} solves/s  checksum {U.sum().item():.10f}")
