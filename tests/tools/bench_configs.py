@@ -60,6 +60,10 @@ def solve_cfg(name, scale, N, ncpu):
 if "invpend_scales" in which:
     for sc in (1.0, 0.25, 0.05):
         solve_cfg("invpend", sc, 10_000_000, 2_000_000)
+if "small_general" in which:
+    # small problems with hard general rows / equalities: the general thread-per-QP kernel K1
+    solve_cfg("dint_hard", 1.0, 10_000_000, 1_000_000)
+    solve_cfg("dint_eq_small", 1.0, 10_000_000, 1_000_000)
 if "aircraft" in which:
     solve_cfg("aircraft", 1.0, 1_000_000, 100_000)
     solve_cfg("aircraft", 0.25, 1_000_000, 100_000)
