@@ -20,6 +20,11 @@
 namespace {
 
 constexpr int K1_BLOCK = 128;
+// resident CTAs per SM the register allocation is capped for (measured r01: uncapped = 2 CTAs/SM,
+// 8 warps, latency-bound; 3 is a win for every size, 4 for n <= 5 but spills at n = 6:
+// dint_hard 2.7 / 3.5 / 3.9e9, dint_eq_small 2.19 / 2.23 / 1.63e9, invpend closed loop 5.4 / 6.4 / 6.6e9;
+// n = 7, 8 keep the uncapped allocation: at 168 registers their general variants spill 1-2 KB)
+constexpr int k1_minb(int n) { return n <= 5 ? 4 : (n == 6 ? 3 : 1); }
 
 template <int N, int CAP>
 struct QpState {
@@ -354,7 +359,7 @@ LMPC_DEVINL double control_out(const ConstView &cv, int nth, int i, const double
 }
 
 template <int N, int CAP, bool GENERAL>
-__global__ void __launch_bounds__(K1_BLOCK)
+__global__ void __launch_bounds__(K1_BLOCK, k1_minb(N))
 ldp_thread_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk, ThetaSegs th,
                   int64_t Ninst, SolveOut out) {
   extern __shared__ __align__(16) double smem[];
@@ -400,7 +405,7 @@ ldp_thread_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk
 
 // closed loop: T steps of (theta = [x; r; d; u_prev]) -> solve -> x+ = F x + G u + Gd d
 template <int N, int CAP, bool GENERAL>
-__global__ void __launch_bounds__(K1_BLOCK)
+__global__ void __launch_bounds__(K1_BLOCK, k1_minb(N))
 ldp_thread_sim_kernel(LdpLayout lay, LdpSettings st, const double *__restrict__ cblk,
                       int64_t Ninst, SimDesc sd, int32_t *flagout, int32_t *itersout) {
   extern __shared__ __align__(16) double smem[];
