@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -90,12 +91,70 @@ int copy_threads(int share) {
   return std::max(1, n / std::max(1, share));
 }
 
+// A few persistent copy workers per process (spawning threads per 2^18-instance stage cost a
+// visible fraction of the stage).  One job at a time: callers (the per-device pipelines of a
+// multi-device handle) take turns, which is fine because one job already saturates the workers.
+class CopyPool {
+ public:
+  static CopyPool &get() { static CopyPool p; return p; }
+  void run(int64_t rows, int nthreads, const std::function<void(int64_t, int64_t)> &f) {
+    if (nthreads <= 1 || rows < 4096) { f(0, rows); return; }
+    std::lock_guard<std::mutex> job(job_mu_);
+    grow(nthreads - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      f_ = &f; rows_ = rows; parts_ = nthreads; next_ = 1; pending_ = nthreads - 1; ++gen_;
+    }
+    cv_.notify_all();
+    f(0, rows / nthreads);                       // the caller is worker 0
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    f_ = nullptr;
+  }
+
+ private:
+  CopyPool() = default;
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  void grow(int n) {
+    while ((int)th_.size() < n) th_.emplace_back([this] { work(); });
+  }
+  void work() {
+    uint64_t seen = 0;
+    for (;;) {
+      int part;
+      const std::function<void(int64_t, int64_t)> *f;
+      int64_t rows; int parts;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || (gen_ != seen && next_ < parts_); });
+        if (stop_) return;
+        part = next_++;
+        if (next_ >= parts_) seen = gen_;
+        f = f_; rows = rows_; parts = parts_;
+      }
+      (*f)(rows * part / parts, rows * (part + 1) / parts);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::mutex job_mu_, mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> th_;
+  const std::function<void(int64_t, int64_t)> *f_ = nullptr;
+  int64_t rows_ = 0;
+  int parts_ = 0, next_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 void parallel_rows(int64_t rows, int nthreads, const std::function<void(int64_t, int64_t)> &f) {
-  if (nthreads <= 1 || rows < 4096) { f(0, rows); return; }
-  std::vector<std::thread> th;
-  for (int t = 1; t < nthreads; ++t) th.emplace_back(f, rows * t / nthreads, rows * (t + 1) / nthreads);
-  f(0, rows / nthreads);
-  for (auto &x : th) x.join();
+  CopyPool::get().run(rows, nthreads, f);
 }
 
 bool is_device_ptr(const void *p) {

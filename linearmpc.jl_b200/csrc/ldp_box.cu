@@ -20,7 +20,10 @@
 
 namespace {
 
-constexpr int KB_BLOCK = 128;
+#ifndef KB_BLOCK_SIZE
+#define KB_BLOCK_SIZE 128
+#endif
+constexpr int KB_BLOCK = KB_BLOCK_SIZE;
 #ifndef KB_TH_UNROLL
 #define KB_TH_UNROLL 4
 #endif
@@ -434,7 +437,10 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
   }
 }
 
-template <int N, int NU, int MINB = 3>
+#ifndef KB_MINB
+#define KB_MINB 3
+#endif
+template <int N, int NU, int MINB = KB_MINB>
 int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
                const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {

@@ -33,7 +33,7 @@ end
 
 Array in page-locked host memory (`lmpc_gpu_host_alloc`): batches allocated this way are DMA'd in
 place (9.5e8 invpend solves/s end to end per GPU); ordinary Julia arrays are staged through the
-library's pinned ring (about 3.8e8).  Freed by a finalizer.
+library's pinned ring (about 7e8 when the arrays are reused between calls).  Freed by a finalizer.
 """
 function pinned(::Type{T}, dims::Integer...) where {T}
     p = ccall((:lmpc_gpu_host_alloc, liblmpcgpu), Ptr{Cvoid}, (Csize_t,), max(prod(dims) * sizeof(T), 8))
