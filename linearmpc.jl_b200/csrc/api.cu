@@ -806,19 +806,51 @@ int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double 
   }
   std::lock_guard<std::mutex> lock(t->mu);
   const int nth = t->dev.nth, nu = t->dev.nu;
-  for (int64_t off = 0, c = 0; off < N; off += kChunk, ++c) {
-    const int64_t cnt = (N - off < kChunk) ? (N - off) : kChunk;
+  // pageable caller arrays go through the pinned ring, as in solve_segments_host
+  const bool stage = is_pageable(Theta) || is_pageable(U) || (region && is_pageable(region));
+  const int64_t chunk = stage ? kChunk / 4 : kChunk;
+  const int nthr = copy_threads(1);
+  auto drain = [&](Slot &s) -> int {
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    if (s.pend_cnt == 0) return 0;
+    const int64_t off = s.pend_off;
+    parallel_rows(s.pend_cnt, nthr, [&](int64_t a, int64_t b) {
+      memcpy(U + (off + a) * nu, (const double *)s.hu.p + a * nu, (size_t)(b - a) * nu * 8);
+      if (region) memcpy(region + off + a, (const int32_t *)s.hflag.p + a, (size_t)(b - a) * 4);
+    });
+    s.pend_cnt = 0;
+    return 0;
+  };
+  for (int i = 0; i < kSlots; ++i) t->slots[i].pend_cnt = 0;
+  for (int64_t off = 0, c = 0; off < N; off += chunk, ++c) {
+    const int64_t cnt = (N - off < chunk) ? (N - off) : chunk;
     Slot &s = t->slots[c % kSlots];
+    if (stage) { int rc = drain(s); if (rc) return rc; }
     if (s.in[0].reserve((size_t)cnt * nth * 8) || s.u.reserve((size_t)cnt * nu * 8)) return LMPC_E_CUDA;
     if (region && s.flag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
-    CUDA_OK(cudaMemcpyAsync(s.in[0].p, Theta + off * nth, (size_t)cnt * nth * 8, cudaMemcpyHostToDevice, s.stream));
+    const double *src = Theta + off * nth;
+    if (stage) {
+      if (s.hin[0].reserve((size_t)cnt * nth * 8) || s.hu.reserve((size_t)cnt * nu * 8)) return LMPC_E_CUDA;
+      if (region && s.hflag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
+      char *dst = (char *)s.hin[0].p;
+      const size_t row = (size_t)nth * 8;
+      parallel_rows(cnt, nthr, [&](int64_t a, int64_t b) { memcpy(dst + a * row, (const char *)src + a * row, (size_t)(b - a) * row); });
+      src = (const double *)s.hin[0].p;
+    }
+    CUDA_OK(cudaMemcpyAsync(s.in[0].p, src, (size_t)cnt * nth * 8, cudaMemcpyHostToDevice, s.stream));
     int rc = lmpc_gpu_evaluate_batch_async(t, (const double *)s.in[0].p, cnt, (double *)s.u.p,
                                            region ? (int32_t *)s.flag.p : nullptr, s.stream);
     if (rc) return rc;
+    if (stage) {
+      CUDA_OK(cudaMemcpyAsync(s.hu.p, s.u.p, (size_t)cnt * nu * 8, cudaMemcpyDeviceToHost, s.stream));
+      if (region) CUDA_OK(cudaMemcpyAsync(s.hflag.p, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+      s.pend_off = off; s.pend_cnt = cnt;
+      continue;
+    }
     CUDA_OK(cudaMemcpyAsync(U + off * nu, s.u.p, (size_t)cnt * nu * 8, cudaMemcpyDeviceToHost, s.stream));
     if (region) CUDA_OK(cudaMemcpyAsync(region + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
   }
-  for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(t->slots[i].stream));
+  for (int i = 0; i < kSlots; ++i) { int rc = drain(t->slots[i]); if (rc) return rc; }
   return 0;
 }
 
