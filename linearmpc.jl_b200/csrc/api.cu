@@ -183,7 +183,7 @@ int check_device(int device, int *sm_count) {
 
 struct lmpc_handle {
   int device = 0, sm_count = 148, kernel = 0;
-  int copy_share = 1;   // how many handles split the host's copy threads (multi-device handle)
+  int copy_share = 1;   // divisor of the copy-thread count (1: the shared pool runs one job at a time anyway)
   LdpLayout lay;
   LdpSettings st;
   double *h_blk = nullptr;
@@ -943,7 +943,6 @@ int lmpc_gpu_create_multi(const lmpc_problem *p, const lmpc_settings *s, const i
     }
     m->h.push_back(h);
   }
-  for (auto *x : m->h) x->copy_share = n_devices;
   *out = m;
   return 0;
 }
