@@ -184,16 +184,21 @@ LMPC_DEVINL double lanesum_pos(const C &c, const double (&a)[T], const double (&
 }
 
 // append row j (oracle: ldl_add)
+// swept: y = L^-1 g_W already computed by the whole CTA (coop_sweep_fwd), read it from there
 template <int T, class C>
-LMPC_DEVINL void bq_add(const C &c, BigQp<T> &s, int j, bool lower, double dval) {
+LMPC_DEVINL void bq_add(const C &c, BigQp<T> &s, int j, bool lower, double dval, const double *swept = nullptr) {
   const int m = c.lay->m, k = s.k, lane = c.lane;
   const double *g = c.G + (size_t)j * m;
   const int sj = c.cv.sense[j];
   double dnew = g[j];
   if (sj & S_SOFT) dnew += c.st->rho_soft;
   double y[T], l[T];
-  TFOR(t) y[t] = (lane + 32 * t < k) ? g[s.row[t]] : 0.0;
-  sweep_fwd<T>(c, y, k);
+  if (swept) {
+    TFOR(t) y[t] = (lane + 32 * t < k) ? swept[lane + 32 * t] : 0.0;
+  } else {
+    TFOR(t) y[t] = (lane + 32 * t < k) ? g[s.row[t]] : 0.0;
+    sweep_fwd<T>(c, y, k);
+  }
   TFOR(t) l[t] = (lane + 32 * t < k) ? y[t] * s.Dinv[t] : 0.0;
   dnew = __dsub_rn(dnew, lanesum_pos<T>(c, y, l, k));
   const bool sing = dnew < c.st->zero_tol;
@@ -819,6 +824,41 @@ struct CoopShared {
   int *ctl;           // [0] branch (0 add / 1 remove / 2 singular), [1] exit flag or 0, [2] k, [3] iters
 };
 
+// Forward substitution z <- L^-1 z with the whole CTA (CTA mode, packed L): columns are taken in
+// blocks of 32; warp 0 finishes the 32 x 32 diagonal block with shuffle broadcasts (the serial
+// part), then every thread owns one trailing row and runs its 32 fmas of that block on its own.
+// Every z_i still accumulates its terms in ascending column order, so the result is the same bits
+// as the single-warp sweep (and the oracle); what changes is that the O(k^2) trailing work no
+// longer sits on one warp (r01: the single-warp sweeps were ~85 % of the critical path at |W| ~ 130).
+// zs: kk values in shared memory, in/out.  Must be called by all CTA_THREADS threads.
+template <int T>
+LMPC_DEVINL void coop_sweep_fwd(const BigCtx &c, double *zs, int kk) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j0 = 0; j0 + 1 < kk; j0 += 32) {
+    const int nb = min(32, kk - 1 - j0);            // columns j0 .. j0 + nb - 1 have rows below them
+    if (warp == 0) {
+      const int i = j0 + lane;
+      const bool live = i < kk;
+      double zi = live ? zs[i] : 0.0;
+      const double *lrow = c.Lw + PIDX(i, j0);        // only dereferenced for i > j0
+      for (int jj = 0; jj < nb; ++jj) {
+        const double zj = shfl_d(zi, jj);
+        if (lane > jj && live) zi = fma(-lrow[jj], zj, zi);
+      }
+      if (live) zs[i] = zi;
+    }
+    __syncthreads();
+    for (int i = j0 + 32 + tid; i < kk; i += CTA_THREADS) {
+      double zi = zs[i];
+      const double *lrow = c.Lw + PIDX(i, j0);
+#pragma unroll 8
+      for (int jj = 0; jj < nb; ++jj) zi = fma(-lrow[jj], zs[j0 + jj], zi);
+      zs[i] = zi;
+    }
+    __syncthreads();
+  }
+}
+
 template <int T>
 __global__ void __launch_bounds__(CTA_THREADS)
 ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
@@ -911,18 +951,26 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     }
     __syncthreads();
     const bool dead = cs.ctl[1] != 0;
+    int pend_add = 0;
+    bool pend_low = false;
+    double pend_d = 0.0;
     for (iter = 1; !dead && iter < st.iter_limit; ++iter) {
-      // ---- phase A (warp 0): CSP, blocking test / singular step -------------------------------
+      // ---- phase A: CSP (forward sweep by the whole CTA, the rest on warp 0), blocking test ------
       double a[T];
       bool blk[T];
       if (warp == 0) {
-        const int k = s.k;
         TFOR(t) { a[t] = CUDART_INF; blk[t] = false; }
+        if (!s.sing) { TFOR(t) { const int i = lane + 32 * t; if (i < s.k) c.lamw[i] = -s.dW[t]; } }
+        if (lane == 0) { cs.ctl[0] = s.sing ? 2 : 0; cs.ctl[2] = s.k; }
+      }
+      __syncthreads();
+      if (cs.ctl[0] != 2) coop_sweep_fwd<T>(c, c.lamw, cs.ctl[2]);      // ends with a __syncthreads
+      if (warp == 0) {
+        const int k = s.k;
         int branch;
         if (!s.sing) {
           double z[T];
-          TFOR(t) z[t] = (lane + 32 * t < k) ? -s.dW[t] : 0.0;
-          sweep_fwd<T>(c, z, k);
+          TFOR(t) { const int i = lane + 32 * t; z[t] = (i < k) ? c.lamw[i] : 0.0; }
           TFOR(t) s.lams[t] = (lane + 32 * t < k) ? z[t] * s.Dinv[t] : 0.0;
           sweep_bwd<T>(c, s.lams, k);
           bool anyblk = false;
@@ -932,6 +980,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
             anyblk |= blk[t];
           }
           branch = __any_sync(FULL, anyblk) ? 1 : 0;
+          __syncwarp();
           if (branch == 0) { TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = s.lams[t]; } }
         } else {
           branch = 2;
@@ -1018,11 +1067,23 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
                 const bool addlow = __shfl_sync(FULL, (lane < 8) ? cs.red_low[lane] : 0, src) != 0;
                 const double addd = shfl_d((lane < 8) ? cs.red_d[lane] : 0.0, src);
                 TFOR(t) if (lane + 32 * t < k) s.lam[t] = s.lams[t];
-                bq_add<T>(c, s, add, addlow, addd);
+                // right-hand side of the add's forward sweep: the Gram column of the new row
+                const double *g = c.G + (size_t)add * m;
+                TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = g[s.row[t]]; }
+                pend_add = add; pend_low = addlow; pend_d = addd;
+                if (lane == 0) cs.ctl[3] = 1;
               }
             }
           }
           if (lane == 0) cs.ctl[1] = done;
+        }
+        __syncthreads();
+        if (cs.ctl[3] != 0) {          // the add: y = L^-1 g_W by the whole CTA, the rest on warp 0
+          coop_sweep_fwd<T>(c, c.lamw, k);
+          if (warp == 0) {
+            bq_add<T>(c, s, pend_add, pend_low, pend_d, c.lamw);
+            if (lane == 0) cs.ctl[3] = 0;
+          }
         }
       } else if (warp == 0) {
         // ---- removal branches (warp 0 only) -----------------------------------------------------
