@@ -834,6 +834,7 @@ struct CoopShared {
 template <int T>
 LMPC_DEVINL void coop_sweep_fwd(const BigCtx &c, double *zs, int kk) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (kk <= 1) { __syncthreads(); return; }          // always ends with a barrier (callers rely on it)
   for (int j0 = 0; j0 + 1 < kk; j0 += 32) {
     const int nb = min(32, kk - 1 - j0);            // columns j0 .. j0 + nb - 1 have rows below them
     if (warp == 0) {
@@ -964,7 +965,11 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
         if (lane == 0) { cs.ctl[0] = s.sing ? 2 : 0; cs.ctl[2] = s.k; }
       }
       __syncthreads();
-      if (cs.ctl[0] != 2) coop_sweep_fwd<T>(c, c.lamw, cs.ctl[2]);      // ends with a __syncthreads
+      {
+        const int not_sing = cs.ctl[0] != 2, kk = cs.ctl[2];              // read before warp 0 rewrites them
+        if (not_sing) coop_sweep_fwd<T>(c, c.lamw, kk);                   // ends with a __syncthreads
+        else __syncthreads();
+      }
       if (warp == 0) {
         const int k = s.k;
         int branch;
@@ -1078,7 +1083,8 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           if (lane == 0) cs.ctl[1] = done;
         }
         __syncthreads();
-        if (cs.ctl[3] != 0) {          // the add: y = L^-1 g_W by the whole CTA, the rest on warp 0
+        const int do_add = cs.ctl[3];
+        if (do_add != 0) {             // the add: y = L^-1 g_W by the whole CTA, the rest on warp 0
           coop_sweep_fwd<T>(c, c.lamw, k);
           if (warp == 0) {
             bq_add<T>(c, s, pend_add, pend_low, pend_d, c.lamw);
