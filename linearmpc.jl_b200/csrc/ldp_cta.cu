@@ -81,6 +81,10 @@ struct BigCtxT {
 };
 using BigCtx = BigCtxT<false>;
 
+#ifndef K3_BC_UNROLL
+#define K3_BC_UNROLL 8
+#endif
+constexpr int K3_BCU = K3_BC_UNROLL;   // unroll of the CTA-mode u / slack-scan loops (loads in flight per thread)
 #define PIDX(i, c) ((size_t)(i) * ((i)-1) / 2 + (c))
 #define TFOR(t) _Pragma("unroll") for (int t = 0; t < T; ++t)
 
@@ -999,7 +1003,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
         if (tid < n) {
           double uc = 0.0;
           const double *mcol = c.M + tid;
-#pragma unroll 8
+#pragma unroll K3_BCU
           for (int i = 0; i < k; ++i) uc = fma(-c.lamw[i], mcol[c.roww[i] * n], uc);
           c.uw[tid] = uc;
         }
@@ -1016,7 +1020,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
             // column j, so the sum may start there (fma(0, u, mu) == mu)
             const int c0 = (j < lay.ms) ? j : 0;
             const double *mt = c.MT + j + c0 * mp;
-#pragma unroll 8
+#pragma unroll K3_BCU
             for (int cc = c0; cc < n; ++cc) { mu = fma(*mt, c.uw[cc], mu); mt += mp; }
             if (!c.inwsb[j] && !(c.cv.sense[j] & S_IMMUTABLE)) {
               const double dU = c.cv.du[j] + shr[h], dLo = c.cv.dl[j] + shr[h];
