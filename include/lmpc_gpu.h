@@ -275,8 +275,8 @@ int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, d
 /* ---------------------------------------------------------------------------------------------
  * Host-side condensing: build the dense mpQP from a discrete-time model without
  * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
- * path supports: no prestabilising feedback, previews, move blocking, offsets, binaries or
- * generalized parameters.  Pure host code; needs no GPU.
+ * path supports: no prestabilising feedback, previews, offsets, binaries or generalized
+ * parameters.  Pure host code; needs no GPU.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
   int32_t rows;
@@ -303,6 +303,12 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
   int32_t n_constraints;
   int32_t reference_tracking;         /* MPCSettings.reference_tracking (default true) */
   int32_t preprocess;                 /* MPCSettings.preprocess_mpqp (default true) */
+  /* move blocking (move_block!, src/setup.jl:196-251; apply_move_block, src/mpc2mpqp.jl:830-857):
+   * the formatted blocks of all nu inputs back to back (each input's blocks sum to Np) and how many
+   * each input has; Nc must be max_i(sum of all but the last block of input i) + 1 as move_block!
+   * sets it.  NULL = no blocking. */
+  const int32_t *move_blocks;
+  const int32_t *n_move_blocks;
 } lmpc_model;
 
 typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */

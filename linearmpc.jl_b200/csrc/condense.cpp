@@ -2,12 +2,13 @@
 // bounds and constraints to the dense mpQP {H, f, f_theta, A, bu, bl, W, senses} that
 // lmpc_gpu_create consumes, so that non-Julia callers can build a controller.
 //
-// What it follows in the reference (subset: no prestabilising feedback, previews, move blocking,
-// offsets, binaries or generalized parameters -- those requests are refused):
+// What it follows in the reference (subset: no prestabilising feedback, previews, offsets,
+// binaries or generalized parameters -- those requests are refused):
 //   extended system / weights    /root/reference/src/mpc2mpqp.jl:649-731
 //   state predictor              /root/reference/src/mpc2mpqp.jl:20-46
 //   dense objective              /root/reference/src/mpc2mpqp.jl:407-533
 //   control bounds, general rows /root/reference/src/mpc2mpqp.jl:206-245, 249-354
+//   move blocking                /root/reference/src/mpc2mpqp.jl:830-857, src/setup.jl:196-251
 //   sort / preprocessing         /root/reference/src/mpc2mpqp.jl:733-866
 //   senses, clamping             /root/reference/src/mpc2mpqp.jl:868-899
 // Runs once per controller; plain dense loops.  Checked against the numpy restatement in
@@ -250,6 +251,57 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       }
     }
   }
+  // ---- move blocking (apply_move_block, mpc2mpqp.jl:830-857) -------------------------------------------
+  // U_old = T z: the blocks of all inputs are interleaved pass by pass; the last block of every
+  // input is clipped to one step (beyond Nc the control is held anyway); of the simple bounds only
+  // the first step of each block survives.
+  int nq = n;
+  if (md->move_blocks && md->n_move_blocks) {
+    std::vector<std::vector<int>> mb(nu);
+    size_t maxlen = 0;
+    const int32_t *pb = md->move_blocks;
+    for (int iu = 0; iu < nu; ++iu) {
+      for (int b = 0; b < md->n_move_blocks[iu]; ++b) mb[iu].push_back(*pb++);
+      if (mb[iu].empty()) return cfail(LMPC_E_INVALID, "move blocking: an input has no blocks");
+      maxlen = std::max(maxlen, mb[iu].size());
+    }
+    int nnew = 0;
+    for (auto &v : mb) nnew += (int)v.size();
+    Mat T(n, nnew);
+    std::vector<int> keep, counter(nu);
+    for (int iu = 0; iu < nu; ++iu) counter[iu] = iu;
+    int new_id = 0;
+    for (size_t pass = 0; pass < maxlen; ++pass)
+      for (int iu = 0; iu < nu; ++iu) {
+        if (mb[iu].size() <= pass) continue;
+        const int block = (mb[iu].size() != pass + 1) ? mb[iu][pass] : 1;
+        for (int b = 0; b < block; ++b) {
+          const int row = counter[iu] + nu * b;
+          if (row >= n) return cfail(LMPC_E_INVALID, "move blocking: blocks exceed the control horizon Nc");
+          T(row, new_id) = 1.0;
+        }
+        if (counter[iu] < ms) keep.push_back(counter[iu]);
+        counter[iu] += nu * block;
+        ++new_id;
+      }
+    const Mat Tt = tr(T);
+    H = mul(Tt, mul(H, T));
+    fth = mul(Tt, fth);
+    if (ms > 0) {
+      std::vector<double> bu2, bl2;
+      for (int r : keep) { bu2.push_back(bu[r]); bl2.push_back(bl[r]); }
+      bu.swap(bu2); bl.swap(bl2);
+      ms = (int)keep.size();
+      soft.assign(ms, 0); prio.assign(ms, 0);
+      W = Mat(ms, nth);
+    }
+    for (auto &ar : Arows) {
+      std::vector<double> r2(nnew, 0.0);
+      for (int j = 0; j < n; ++j) if (ar[j] != 0.0) for (int c2 = 0; c2 < nnew; ++c2) r2[c2] += ar[j] * T(j, c2);
+      ar.swap(r2);
+    }
+    nq = nnew;
+  }
   // stable sort of the general rows by priority (mpc2mpqp.jl:859-866)
   std::vector<int> order(Arows.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -266,7 +318,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       std::vector<double> &a = Arows[i];
       double nf = 0.0; for (double v : a) nf += v * v; nf = std::sqrt(nf);
       if (!(nf > 1e-10)) continue;
-      int nz = 0; while (nz < n && !(std::fabs(a[nz]) > 1e-12)) ++nz;
+      int nz = 0; while (nz < nq && !(std::fabs(a[nz]) > 1e-12)) ++nz;
       if (a[nz] < 0) {
         for (double &v : a) v = -v + 0.0;
         const double t = gbu[i]; gbu[i] = -gbl[i]; gbl[i] = -t;
@@ -315,13 +367,13 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   }
   lmpc_mpqp *q = new lmpc_mpqp();
   const int mg = (int)Arows.size(), m = ms + mg;
-  q->n = n; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nr; q->nd = nd; q->nuprev = nup; q->nu = nu;
-  q->H = H; q->f_theta = fth; q->f.assign(n, 0.0);
-  q->A = Mat(mg, n); q->W = Mat(m, nth);
+  q->n = nq; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nr; q->nd = nd; q->nuprev = nup; q->nu = nu;
+  q->H = H; q->f_theta = fth; q->f.assign(nq, 0.0);
+  q->A = Mat(mg, nq); q->W = Mat(m, nth);
   for (int i = 0; i < ms; ++i) for (int j = 0; j < nth; ++j) q->W(i, j) = W(i, j);
   q->bu = bu; q->bl = bl;
   for (int i = 0; i < mg; ++i) {
-    for (int j = 0; j < n; ++j) q->A(i, j) = Arows[i][j];
+    for (int j = 0; j < nq; ++j) q->A(i, j) = Arows[i][j];
     for (int j = 0; j < nth; ++j) q->W(ms + i, j) = Wrows[i][j];
     q->bu.push_back(gbu[i]); q->bl.push_back(gbl[i]);
     soft.push_back(gsoft[i]);

@@ -690,7 +690,8 @@ class _Model(C.Structure):
                 ("Q", C.c_void_p), ("R", C.c_void_p), ("Rr", C.c_void_p), ("Qf", C.c_void_p),
                 ("umin", C.c_void_p), ("umax", C.c_void_p),
                 ("constraints", C.c_void_p), ("n_constraints", C.c_int32),
-                ("reference_tracking", C.c_int32), ("preprocess", C.c_int32)]
+                ("reference_tracking", C.c_int32), ("preprocess", C.c_int32),
+                ("move_blocks", C.c_void_p), ("n_move_blocks", C.c_void_p)]
 
 
 def _diag(v, n):
@@ -721,8 +722,44 @@ class MPC:
         self.umin = self.umax = None
         self.constraints = []
         self.reference_tracking, self.preprocess_mpqp, self.soft_weight = True, True, 1e6
+        self.move_blocks = []
         self.gpu = None
         self.mpqp = None
+
+    # setup.jl:196-251
+    def move_block(self, block):
+        """move_block!(mpc, block): keep the control constant in blocks, e.g. [2, 1, 3].  An int gives
+        equal blocks, a list applies to every input, a list of lists is per input; blocks are padded /
+        clipped to the prediction horizon and Nc becomes max(sum(block[:-1])) + 1, as in the reference."""
+        self.gpu = None
+        scalar = isinstance(block, (int, float, np.integer, np.floating))
+        if block is None or (scalar and int(block) <= 0) or (not scalar and len(block) == 0):
+            self.move_blocks, self.Nc = [], self.Np
+            return
+        if scalar:
+            block = [int(block)] * (self.Np // int(block) + 1)
+        if isinstance(block[0], (int, float, np.integer, np.floating)):
+            block = [list(block) for _ in range(self.nu)]
+        if len(block) != self.nu:
+            raise ValueError("move_block: need blocks for every control input")
+
+        def fmt(b):                                  # format_move_block, setup.jl:235-251
+            b = [int(v) for v in b]
+            tot = sum(b)
+            if tot < self.Np:
+                b[-1] += self.Np - tot
+            elif tot > self.Np:
+                acc, i = 0, 0
+                while True:
+                    acc += b[i]
+                    if acc >= self.Np:
+                        break
+                    i += 1
+                b = b[:i + 1]
+                b[-1] += self.Np - acc
+            return b
+        self.move_blocks = [fmt(b) for b in block]
+        self.Nc = max(sum(b[:-1]) for b in self.move_blocks) + 1
 
     # setup.jl:118-132
     def set_objective(self, Q=None, R=None, Rr=None, Qf=None):
@@ -793,7 +830,12 @@ class MPC:
         md = _Model(self.nx, self.nu, self.ny, self.nd, self.Np, self.Nc, cm(self.F), cm(self.G), cm(self.C),
                     cm(self.Gd), cm(self.Dd), cm(self.Q), cm(self.R), cm(self.Rr), cm(self.Qf),
                     cm(self.umin), cm(self.umax), C.cast(cons, C.c_void_p), len(self.constraints),
-                    int(self.reference_tracking), int(self.preprocess_mpqp))
+                    int(self.reference_tracking), int(self.preprocess_mpqp), None, None)
+        if self.move_blocks:
+            mbf = np.ascontiguousarray([v for b in self.move_blocks for v in b], np.int32)
+            mbn = np.ascontiguousarray([len(b) for b in self.move_blocks], np.int32)
+            keep += [mbf, mbn]
+            md.move_blocks, md.n_move_blocks = mbf.ctypes.data, mbn.ctypes.data
         q = C.c_void_p()
         rc = L.lmpc_gpu_condense(C.byref(md), C.byref(q))
         if rc != 0:

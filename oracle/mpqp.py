@@ -466,6 +466,57 @@ def _remove_duplicate(A, bu, bl, W, soft, prio):
     return A2, bu2, bl2, W2, soft2, prio2
 
 
+def format_move_block(block, Np):
+    """setup.jl:235-251: pad / clip a block list to the prediction horizon."""
+    b = [int(v) for v in block]
+    tot = sum(b)
+    if tot < Np:
+        b[-1] += Np - tot
+    elif tot > Np:
+        acc, i = 0, 0
+        while True:
+            acc += b[i]
+            if acc >= Np:
+                break
+            i += 1
+        b = b[:i + 1]
+        b[-1] += Np - acc
+    return b
+
+
+def move_block(mpc: "MPC", blocks):
+    """move_block!(mpc, blocks) (setup.jl:196-233): blocks = one list per input."""
+    mpc.move_blocks = [format_move_block(b, mpc.Np) for b in blocks]
+    mpc.Nc = max(sum(b[:-1]) for b in mpc.move_blocks) + 1
+
+
+def apply_move_block(mpc, H, f, f_theta, A, bu, bl, W, soft, prio):
+    """apply_move_block (mpc2mpqp.jl:830-857): U_old = T z, blocks interleaved pass by pass, the
+    last block of every input clipped to one step, only the first bound of each block kept."""
+    nu, Nc = mpc.nu, mpc.Nc
+    nub = len(mpc.umax)
+    n_old = nu * Nc
+    n_new = sum(len(mb) for mb in mpc.move_blocks)
+    T = np.zeros((n_old, n_new))
+    counter = list(range(1, nu + 1))           # 1-based, as in the reference
+    keep, new_id = [], 1
+    for p in range(1, max(len(mb) for mb in mpc.move_blocks) + 1):
+        for iu, mb in enumerate(mpc.move_blocks):
+            if len(mb) < p:
+                continue
+            block = mb[p - 1] if len(mb) != p else 1
+            rows = np.arange(counter[iu], counter[iu] + nu * (block - 1) + 1, nu)
+            T[rows - 1, new_id - 1] = 1.0
+            if counter[iu] <= nub * Nc:
+                keep.append(counter[iu])
+            counter[iu] += nu * block
+            new_id += 1
+    ns = len(bu) - A.shape[0]
+    keep = np.array(keep, int) - 1
+    full = np.concatenate([keep, np.arange(ns, len(bu))]).astype(int)
+    return (T.T @ H @ T, T.T @ f, T.T @ f_theta, A @ T, bu[full], bl[full], W[full], soft[full], prio[full])
+
+
 def mpc2mpqp(mpc: MPC) -> MPQP:
     """The dense mpQP of `mpc` (mpc2mpqp.jl:612-647)."""
     F, G, C = extended_system(mpc)
@@ -486,6 +537,8 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
         A = Ag
         bu, bl, W = np.concatenate([bu, bug]), np.concatenate([bl, blg]), np.vstack([W, Wg])
         soft, prio = np.concatenate([soft, sg]), np.concatenate([prio, pg])
+    if getattr(mpc, "move_blocks", None):
+        H, f, f_theta, A, bu, bl, W, soft, prio = apply_move_block(mpc, H, f, f_theta, A, bu, bl, W, soft, prio)
     # sort general rows by priority, stable (mpc2mpqp.jl:859-866)
     ns = len(bu) - A.shape[0]
     order = np.argsort(prio[ns:], kind="stable")

@@ -71,3 +71,55 @@ def test_builder_end_to_end_known_answers(lmpc):
     assert abs(s.compute_control(np.array([0.0, 0.0]), r=[1.0, 0.0], uprev=[0.0])[0] - 1.0) < 1e-6
     sim = m.simulate(np.array([[0.0, 0, 0.15, 0]]).T, N=200)
     assert sim["exitflag"][0] >= 1 and abs(sim["Xend"][2, 0]) < 0.05
+
+
+@pytest.mark.parametrize("name,blocks", [("invpend", [[1, 1, 48]]), ("invpend", [[2, 3, 5, 40]]),
+                                         ("aircraft", [[1, 2, 7], [3, 7]]), ("dint_hard", [[1, 3]]),
+                                         ("aircraft_ksall", [[2, 2, 6], [2, 2, 6]])])
+def test_move_blocking_matches_numpy_restatement(lmpc, name, blocks):
+    """move_block! (setup.jl:196-251) + apply_move_block (mpc2mpqp.jl:830-857): the C++ condensing
+    against the numpy restatement, including per-input blocks of different lengths."""
+    o = util.controller(name)
+    o.Nc = o.Np
+    mpqp.move_block(o, blocks)
+    ref = mpqp.mpc2mpqp(o)
+    m = mirror_of(lmpc, util.controller(name))
+    m.Nc = m.Np
+    m.move_block(blocks)
+    assert m.Nc == o.Nc and m.move_blocks == o.move_blocks
+    q = m.condense()
+    assert q["H"].shape == ref.H.shape == (sum(len(b) for b in o.move_blocks),) * 2
+    assert q["A"].shape == ref.A.shape and q["bu"].shape == ref.bu.shape
+    assert np.max(np.abs(q["H"] - ref.H)) <= 1e-12 * max(1.0, np.abs(ref.H).max())
+    assert np.max(np.abs(q["f_theta"] - ref.f_theta)) <= 1e-12 * max(1.0, np.abs(ref.f_theta).max())
+    assert np.allclose(q["A"], ref.A, rtol=1e-12, atol=1e-13) and np.allclose(q["W"], ref.W, rtol=1e-12, atol=1e-13)
+    assert np.allclose(q["bu"], ref.bu, rtol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-13)
+    assert np.array_equal(q["senses"], ref.senses)
+
+
+def test_move_blocked_problem_is_the_full_problem_with_tied_moves():
+    """Independent check of the blocking algebra: the optimum of the blocked mpQP equals the
+    optimum of the UNBLOCKED one under the equality constraints 'moves of a block are equal' (and
+    held after the last block), solved by SLSQP."""
+    from scipy.optimize import minimize
+    from oracle import ldp
+    blocks = [[2, 3, 5]]
+    full = mpqp.invpend(Np=10, Nc=10)
+    blk = mpqp.invpend(Np=10, Nc=10)
+    mpqp.move_block(blk, blocks)
+    qf, qb = mpqp.mpc2mpqp(full), mpqp.mpc2mpqp(blk)
+    assert qb.n == 3 and blk.Nc == 6
+    P = ldp.OracleProblem(mpqp.qp2ldp(qb, 1), 1)
+    rng = np.random.default_rng(0)
+    lo, hi = mpqp.invpend_range(0.2)
+    # U (10 moves) tied: [z1 z1 z2 z2 z2 z3 z3 z3 z3 z3]
+    Tm = np.zeros((10, 3)); Tm[0:2, 0] = 1; Tm[2:5, 1] = 1; Tm[5:, 2] = 1
+    for _ in range(12):
+        th = lo + (hi - lo) * rng.random(len(lo))
+        u_blk, flag, _ = P.solve(th)
+        assert flag >= 1
+        fvec = qf.f + qf.f_theta @ th
+        obj = lambda z: 0.5 * (Tm @ z) @ qf.H @ (Tm @ z) + fvec @ (Tm @ z)
+        res = minimize(obj, np.zeros(3), jac=lambda z: Tm.T @ (qf.H @ (Tm @ z) + fvec), method="SLSQP",
+                       bounds=[(-2.0, 2.0)] * 3, options=dict(ftol=1e-14, maxiter=200))
+        assert res.success and abs(res.x[0] - u_blk[0]) < 1e-6

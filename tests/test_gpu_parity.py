@@ -510,3 +510,26 @@ def test_closed_loop_with_preview_windows(lmpc, name):
                            Rtraj=Rflat, Dtraj=Dflat, ext=dict(rstride=1, dstride=1))
     assert np.array_equal(out["Utraj"], ref["Utraj"]) and np.array_equal(out["Xend"], ref["Xend"])
     assert np.array_equal(out["exitflag"], ref["flag"])
+
+
+@pytest.mark.parametrize("name,blocks", [("aircraft", [[1, 2, 7], [3, 7]]), ("invpend", [[2, 3, 5, 40]]),
+                                         ("aircraft_ksall", [[1, 1, 1, 1, 6], [1, 1, 1, 1, 6]])])
+def test_move_blocked_controllers_on_gpu(lmpc, name, blocks):
+    """A controller condensed WITH move blocking by the product's builder (C++), solved on the GPU,
+    against the oracle on the numpy restatement of the same blocked problem."""
+    import test_condense_cpu as tc
+    o = util.controller(name)
+    o.Nc = o.Np
+    mpqp.move_block(o, blocks)
+    qp = mpqp.mpc2mpqp(o)
+    m = tc.mirror_of(lmpc, util.controller(name))
+    m.Nc = m.Np
+    m.move_block(blocks)
+    g = m.setup()
+    cst = g.ldp_constants()
+    cst["senses"] = g.senses
+    P = util.oracle_from_constants(qp, o.nu, cst, soft_weight=o.soft_weight)
+    lo, hi = util.theta_range(name, 0.25)
+    Th = mpqp.sample_theta(lo, hi, 3000, seed=31)
+    assert_parity(g.solve(Th), P.solve_batch(Th))
+    assert g.n == sum(len(b) for b in o.move_blocks)
