@@ -533,3 +533,30 @@ def test_move_blocked_controllers_on_gpu(lmpc, name, blocks):
     Th = mpqp.sample_theta(lo, hi, 3000, seed=31)
     assert_parity(g.solve(Th), P.solve_batch(Th))
     assert g.n == sum(len(b) for b in o.move_blocks)
+
+
+@pytest.mark.parametrize("name", ["invpend", "aircraft"])
+def test_prestabilising_feedback_in_the_output_map(lmpc, name):
+    """lmpc_problem.K: u = z[1:nu] - K x (src/utils.jl:46-50), folded into Uth_offset exactly as qp2ldp
+    does (src/codegen.jl:141,269-273).  The reference's condensing with K is out of scope, so K is applied to
+    an ordinary mpQP here: the GPU equals the oracle built with the same K bit for bit, and both equal the
+    K = 0 result minus K x."""
+    mpc = util.controller(name)
+    qp = mpqp.mpc2mpqp(mpc)
+    nx = mpc.parameter_dims()[0]
+    K = np.random.default_rng(4).standard_normal((mpc.nu, nx)) * 0.1
+    g = lmpc.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight, K=K)
+    g0 = lmpc.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
+    cst = g.ldp_constants()
+    cst["senses"] = g.senses
+    L = mpqp.qp2ldp(qp, mpc.nu, K=K, soft_weight=mpc.soft_weight)
+    # C++ setup vs numpy: equal to rounding amplified by cond(H) (3.5e8 for AFTI-16)
+    assert np.max(np.abs(cst["Uth"] - L.Uth_offset)) <= 1e-6 * max(1.0, np.abs(L.Uth_offset).max())
+    P = util.oracle_from_constants(qp, mpc.nu, cst, soft_weight=mpc.soft_weight)
+    lo, hi = util.theta_range(name, 0.25)
+    Th = mpqp.sample_theta(lo, hi, 3000, seed=8)
+    out = g.solve(Th)
+    assert_parity(out, P.solve_batch(Th))
+    base = g0.solve(Th)
+    ok = out["exitflag"] >= 1
+    assert np.max(np.abs(out["U"][:, ok] - (base["U"][:, ok] - K @ Th[:nx][:, ok]))) < 1e-10
