@@ -560,3 +560,44 @@ def test_prestabilising_feedback_in_the_output_map(lmpc, name):
     base = g0.solve(Th)
     ok = out["exitflag"] >= 1
     assert np.max(np.abs(out["U"][:, ok] - (base["U"][:, ok] - K @ Th[:nx][:, ok]))) < 1e-10
+
+
+def test_async_entry_points_on_caller_streams(lmpc):
+    """lmpc_gpu_solve_batch_async / lmpc_gpu_evaluate_batch_async: device pointers, the caller's
+    stream, no synchronisation inside; two streams in flight at once; the handle's own stream when
+    the stream argument is NULL.  Results equal the synchronous host-buffer path bit for bit."""
+    import torch
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    dev = torch.device("cuda", 0)
+    lo, hi = mpqp.invpend_range(1.0)
+    N = 200_000
+    Ths = [mpqp.sample_theta(lo, hi, N, seed=60 + i) for i in range(2)]
+    Td = [torch.tensor(np.ascontiguousarray(T.T), dtype=torch.float64, device=dev) for T in Ths]
+    U = [torch.empty((N, 1), dtype=torch.float64, device=dev) for _ in range(2)]
+    fl = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]
+    it = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    for i in range(2):
+        g.solve_async(Td[i], U[i], fl[i], it[i], N=N, stream=streams[i].cuda_stream)
+    for s in streams:
+        s.synchronize()
+    for i in range(2):
+        ref = g.solve(Ths[i], want_active=False)
+        assert np.array_equal(U[i].cpu().numpy().T, ref["U"]) and np.array_equal(fl[i].cpu().numpy(), ref["exitflag"])
+        assert np.array_equal(it[i].cpu().numpy(), ref["iters"])
+    # NULL stream = the handle's own stream
+    g.solve_async(Td[0], U[1], fl[1], N=N, stream=None)
+    torch.cuda.current_stream(dev).synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(U[0], U[1]) and g.stream() is not None
+    # explicit evaluate, async
+    z = np.load(os.path.join(GOLD, "invpend_explicit.npz"))
+    ge = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    Te = mpqp.sample_theta(z["lo"], z["hi"], N, seed=3)
+    Ted = torch.tensor(np.ascontiguousarray(Te.T), dtype=torch.float64, device=dev)
+    Ue = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    re = torch.empty(N, dtype=torch.int32, device=dev)
+    ge.evaluate_async(Ted, Ue, re, N=N, stream=streams[0].cuda_stream)
+    streams[0].synchronize()
+    Uh, rh = ge.evaluate(Te)
+    assert np.array_equal(Ue.cpu().numpy().T, Uh) and np.array_equal(re.cpu().numpy(), rh)
