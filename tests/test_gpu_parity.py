@@ -601,3 +601,42 @@ def test_async_entry_points_on_caller_streams(lmpc):
     streams[0].synchronize()
     Uh, rh = ge.evaluate(Te)
     assert np.array_equal(Ue.cpu().numpy().T, Uh) and np.array_equal(re.cpu().numpy(), rh)
+
+
+def test_api_errors_are_codes_not_crashes(lmpc):
+    """Error convention of the ABI: bad arguments come back as negative LMPC_E_* return
+    codes with a message, never as exceptions across the ABI or device faults."""
+    import ctypes as C
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    L = lmpc.lib()
+    Th = np.asfortranarray(mpqp.sample_theta(*mpqp.invpend_range(1.0), 16))
+    U = np.zeros((1, 16), order="F"); fl = np.zeros(16, np.int32)
+    assert L.lmpc_gpu_solve_batch(g._h, None, 16, U.ctypes.data, fl.ctypes.data, None, None, None) == -100
+    assert L.lmpc_gpu_solve_batch(g._h, Th.ctypes.data, -1, U.ctypes.data, fl.ctypes.data, None, None, None) == -100
+    assert b"bad argument" in L.lmpc_gpu_last_error()
+    au = np.zeros((16, 1), np.uint64)
+    # active-set words must come in pairs / be present for a warm start
+    assert L.lmpc_gpu_solve_batch(g._h, Th.ctypes.data, 16, U.ctypes.data, fl.ctypes.data, None, au.ctypes.data, None) == -100
+    assert L.lmpc_gpu_solve_batch_warm(g._h, Th.ctypes.data, 16, U.ctypes.data, fl.ctypes.data, None, None, None) == -100
+    # closed loop: the parameter split must add up to nth
+    with pytest.raises(lmpc.LmpcError) as e:
+        bad = lmpc.setup_gpu(qp, nu=1, dims=(4, 1, 0, 1))
+        bad.simulate(mpc.F, mpc.G, Th[:4], N=3)
+    assert e.value.code == -100
+    # explicit trees are validated on creation: a jump that leaves the node array, a leaf naming a missing law
+    hp = np.array([[1.0, 0.0, 0.5]]); fb = np.zeros((1, 1, 3))
+    for hl, jl in (([0, 0, 0], [5, 0, 0]), ([0, 0, 7], [1, 0, 0]), ([3, 0, 0], [1, 0, 0])):
+        with pytest.raises(lmpc.LmpcError) as e:
+            lmpc.GpuExplicitMPC(hp, fb, np.array(hl, np.int32), np.array(jl, np.int32))
+        assert e.value.code == -100
+    ok = lmpc.GpuExplicitMPC(hp, fb, np.array([0, 0, 0], np.int32), np.array([1, 0, 0], np.int32), dims=(2, 0, 0, 0))
+    u, reg = ok.evaluate(np.zeros((2, 5)))
+    assert u.shape == (1, 5) and np.all(reg == 0)
+    # explicit closed loop limits
+    with pytest.raises((lmpc.LmpcError, ValueError)):
+        ok.simulate(np.eye(3), np.ones((3, 1)), np.zeros((3, 2)), N=2)      # nx does not match nth
+    Fm, Gm, X0 = np.asfortranarray(np.eye(2)), np.asfortranarray(np.ones((2, 1))), np.zeros((2, 3), order="F")
+    Xe, Ul = np.zeros((2, 3), order="F"), np.zeros((1, 3), order="F")
+    rc = L.lmpc_gpu_simulate_bst_batch(ok._t, Fm.ctypes.data, Gm.ctypes.data, None, 1, 0, 0, 0, X0.ctypes.data, None, None,
+                                       None, None, None, 3, 2, Xe.ctypes.data, Ul.ctypes.data, None)
+    assert rc == -100 and b"must equal nth" in L.lmpc_gpu_last_error()
