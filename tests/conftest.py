@@ -15,5 +15,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def lmpc():
     import lmpc_b200
+    if not os.path.exists(lmpc_b200.lib_path()):
+        # fresh checkout (the .so is git-ignored): build it the way the driver does
+        import __graft_entry__
+        __graft_entry__.build()
     lmpc_b200.load_library()
     return lmpc_b200
