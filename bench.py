@@ -211,6 +211,27 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this rank (and first-touch its pinned staging buffers) on the CPUs
+    next to its GPU, as NVML reports them, so that the end-to-end leg's H2D / D2H traffic does not
+    cross the socket interconnect.  Returns the number of CPUs bound to, or None when unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -228,6 +249,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     import torch
     import torch.distributed as dist
@@ -381,7 +404,8 @@ def main():
             "e2e": {"value": float(n_per) * world * e2e_steps / e2e_s, "unit": "solves/s",
                     "h2d_bytes_per_step": 8 * nth * n_per, "d2h_bytes_per_step": (8 * nu + 4) * n_per,
                     "steps": e2e_steps, "timer": "wall clock around lmpc_gpu_solve_batch (host pointers)",
-                    "matches_device_path": e2e_ok},
+                    "matches_device_path": e2e_ok,
+                    "cpus_bound_per_rank": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity": parity,
