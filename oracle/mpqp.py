@@ -124,6 +124,9 @@ class MPC:
     umax: np.ndarray = field(default_factory=lambda: np.zeros(0))
     constraints: List[Constraint] = field(default_factory=list)
     reference_tracking: bool = True
+    # time-varying previews over the horizon (types.jl:56-57, 67-68): theta carries ny*Np / nd*Np values
+    reference_preview: bool = False
+    disturbance_preview: bool = False
     preprocess_mpqp: bool = True
     soft_weight: float = 1e6
     # generalized-parameter (affine) objective terms (Ex p + ex)'x + (Eu p + eu)'u, setup.jl:118-132
@@ -232,17 +235,26 @@ class MPC:
         return max(dims)
 
     def parameter_dims(self):
-        """(nx, nr, nd, nuprev) -- mpc2mpqp.jl:147-164 without previews; np via affine_parameter_dim."""
+        """(nx, nr, nd, nuprev) -- mpc2mpqp.jl:147-164 (previews: Np blocks each); np via affine_parameter_dim."""
         nr = self.ny if self.reference_tracking else 0
+        if self.reference_preview and nr > 0:
+            nr *= self.Np
         nd = self.nd_model
+        if self.disturbance_preview and nd > 0:
+            nd *= self.Np
         aup = any(c.Aup.size and np.any(c.Aup != 0) for c in self.constraints)
         nuprev = self.nu if (np.any(self.Rr != 0) or aup) else 0
         return self.nx, nr, nd, nuprev
 
     def form_parameter(self, x, r=None, d=None, uprev=None, p=None):
-        """theta = [x; r; d; uprev; p] (explicit.jl:54-63)."""
+        """theta = [x; r; d; uprev; p] (explicit.jl:54-63); previews flattened column by column with
+        the last column held when the trajectory is short (utils.jl:78-134, 155-205)."""
         nx, nr, nd, nup = self.parameter_dims()
         x = np.asarray(x, float).reshape(nx)
+        if self.reference_preview and nr > 0:
+            r = _flatten_preview(r, self.ny, self.Np)
+        if self.disturbance_preview and nd > 0:
+            d = _flatten_preview(d, self.nd_model, self.Np)
         r = np.zeros(nr) if r is None else np.asarray(r, float).reshape(-1)[:nr]
         d = np.zeros(nd) if d is None else np.asarray(d, float).reshape(-1)[:nd]
         up = np.zeros(nup) if uprev is None else np.asarray(uprev, float).reshape(-1)[:nup]
@@ -251,15 +263,36 @@ class MPC:
         return np.concatenate([x, r, d, up, pv])
 
 
+def _flatten_preview(v, rows, Np):
+    """vec of a rows x Np preview: a vector is repeated, a short matrix holds its last column."""
+    if v is None:
+        return np.zeros(rows * Np)
+    v = np.asarray(v, float)
+    if v.ndim == 1:
+        if v.size != rows:
+            raise ValueError(f"preview vector length ({v.size}) must match ({rows})")
+        return np.tile(v, Np)
+    if v.shape[0] != rows:
+        raise ValueError(f"preview matrix must have {rows} rows")
+    if v.shape[1] >= Np:
+        return v[:, :Np].reshape(-1, order="F")
+    ext = np.hstack([v, np.repeat(v[:, -1:], Np - v.shape[1], axis=1)])
+    return ext.reshape(-1, order="F")
+
+
 # ---------------------------------------------------------------------------
 # condensing
 # ---------------------------------------------------------------------------
 
 def extended_system(mpc: MPC):
-    """x~ = [x; r; d; u^-]  (mpc2mpqp.jl:649-690 with K = 0, no offset)."""
+    """x~ = [x; r; d; u^-]  (mpc2mpqp.jl:649-690 with K = 0, no offset); previewed r / d are not states."""
     nx, nr, nd, nup = mpc.parameter_dims()
     nu = mpc.nu
     F, G, C = mpc.F.copy(), mpc.G.copy(), mpc.C.copy()
+    if mpc.reference_preview:
+        nr = 0
+    if mpc.disturbance_preview:
+        nd = 0
     if nr > 0:
         F = block_diag(F, np.eye(mpc.ny))
         G = np.vstack([G, np.zeros((mpc.ny, nu))])
@@ -285,6 +318,10 @@ def extended_cost(mpc: MPC):
     Q, R, Rr = mpc.Q.copy(), mpc.R.copy(), mpc.Rr.copy()
     Qf = Q.copy() if not np.any(mpc.Qf != 0) else mpc.Qf.copy()
     S = np.zeros((nx, nu))
+    if mpc.reference_preview:
+        nr = 0
+    if mpc.disturbance_preview:
+        nd = 0
     if nr > 0:
         S = np.vstack([S, np.zeros((mpc.ny, nu))])
     if nd > 0:
@@ -313,6 +350,16 @@ def state_predictor(F, G, Np, Nc):
     return Phi, Gam
 
 
+def disturbance_predictor(F, E, Np):
+    """Psi with X = ... + Psi [d_0; ...; d_{Np-1}] (mpc2mpqp.jl:48-58)."""
+    nx, nd = E.shape
+    Psi = np.zeros(((Np + 1) * nx, Np * nd))
+    for k in range(1, Np + 1):
+        Psi[k * nx:(k + 1) * nx] = F @ Psi[(k - 1) * nx:k * nx]
+        Psi[k * nx:(k + 1) * nx, (k - 1) * nd:k * nd] += E
+    return Psi
+
+
 def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
     """H, f, f_theta (mpc2mpqp.jl:407-533, single objective, no previews/offsets)."""
     Q, R, S, Qf = extended_cost(mpc)
@@ -337,6 +384,27 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
         GS = Gam.T @ Stot
         H = H + GS + GS.T
         f_theta = f_theta + Stot.T @ Phi
+    ny = mpc.ny
+    nxp, nrp, ndp, _ = mpc.parameter_dims()
+    Cfull, Qfull, Qffull = C[:ny, :], Q[:ny, :ny], Qf[:ny, :ny]
+    if nrp > 0 and mpc.reference_preview:
+        # ref_preview_cost (mpc2mpqp.jl:535-577, no condensation): block k of the preview is the
+        # reference of x_{k+1}; the reference paired with x_0 does not touch U and is dropped
+        CQ = np.kron(np.eye(N + 1), Cfull.T @ Qfull)
+        CQ[-nxe:, -ny:] = Cfull.T @ Qffull
+        Fr = (-Gam.T @ CQ)[:, ny:]
+        f_theta = np.hstack([f_theta[:, :nxp], Fr, f_theta[:, nxp:]])
+    if ndp > 0 and mpc.disturbance_preview:
+        # disturbance_preview_cost (mpc2mpqp.jl:579-610): y_k = C x_k + Dd d_{k-1}, x through Psi
+        Psi = disturbance_predictor(F, np.vstack([mpc.Gd, np.zeros((nxe - mpc.nx, mpc.nd_model))]), N)
+        CY = np.kron(np.eye(N), Cfull)
+        Gy = CY @ Gam[nxe:, :]
+        Yd = CY @ Psi[nxe:, :] + np.kron(np.eye(N), mpc.Dd[:ny, :])
+        Qy = np.kron(np.eye(N), Qfull)
+        Qy[-ny:, -ny:] = Qffull
+        Fd = Gy.T @ Qy @ Yd
+        split = nxp + nrp
+        f_theta = np.hstack([f_theta[:, :split], Fd, f_theta[:, split:]])
     H = (H + H.T) / 2
     f = np.zeros(H.shape[0])
     # generalized-parameter terms (mpc2mpqp.jl:478-508), constant parameter across the horizon
@@ -370,7 +438,14 @@ def general_constraints(mpc: MPC, Phi, Gam):
     """Rows lb <= [Ax Ar Ad Aup] x~_{k-1} + Au u_{k-1} <= ub (mpc2mpqp.jl:249-354)."""
     Np, Nc, nu = mpc.Np, mpc.Nc, mpc.nu
     nx, nr, nd, nup = mpc.parameter_dims()
+    nrp, ndp = nr, nd
+    if mpc.reference_preview:
+        nr = 0
+    if mpc.disturbance_preview:
+        nd = 0
     nxe = nx + nr + nd + nup
+    ndm = mpc.nd_model
+    Wd_direct = []
     eyeX = np.eye(Np + 1)
     eyeU = np.vstack([np.eye(Nc), np.zeros((1 + Np - Nc, Nc))])
     Axt, Aut = np.zeros((0, nxe * (Np + 1))), np.zeros((0, nu * Nc))
@@ -391,8 +466,27 @@ def general_constraints(mpc: MPC, Phi, Gam):
         lb.append(np.tile(c.lb, Ni))
         soft += [c.soft] * (mi * Ni)
         prio += [c.prio] * (mi * Ni)
+        if mpc.reference_preview and nrp > 0 and c.Ar.size and np.any(c.Ar != 0):
+            raise ValueError("constraints on the reference are not supported with reference_preview")
+        if mpc.disturbance_preview and ndp > 0:
+            # disturbance_preview_direct (mpc2mpqp.jl:94-109): row block of x_{k-1} sees -Ad d_{k-2}
+            Wdd = np.zeros((mi * Ni, ndm * Np))
+            if c.Ad.size:
+                for i, k in enumerate(ks):
+                    if 2 <= k <= Np + 1:
+                        Wdd[i * mi:(i + 1) * mi, (k - 2) * ndm:(k - 1) * ndm] = -c.Ad
+            Wd_direct.append(Wdd)
     A = Axt @ Gam + Aut
     W = -Axt @ Phi
+    # insert_preview_parameter_blocks (mpc2mpqp.jl:70-92)
+    if mpc.reference_preview and nrp > 0:
+        W = np.hstack([W[:, :nx], np.zeros((W.shape[0], nrp)), W[:, nx:]])
+    if mpc.disturbance_preview and ndp > 0:
+        Fx = Phi[nxe:2 * nxe, :]   # one-step map of the extended state
+        Psi = disturbance_predictor(Fx, np.vstack([mpc.Gd, np.zeros((nxe - nx, ndm))]), Np)
+        Wd = -Axt @ Psi + np.vstack(Wd_direct)
+        split = nx + nrp + nd
+        W = np.hstack([W[:, :split], Wd, W[:, split:]])
     npar = mpc.affine_parameter_dim()
     if npar > 0:   # parameter_preview_direct without preview (mpc2mpqp.jl:125-143): W_p = -Ap per row
         Wp = []

@@ -1,0 +1,110 @@
+"""Reference / disturbance previews in the condensed mpQP (mpc2mpqp.jl:48-109, 535-610; types.jl:56-57).
+
+The checks are independent of the condensing algebra: the plant is rolled out step by step with
+time-varying r_k / d_k and the stage costs and constraint rows are evaluated directly, then compared
+with the dense {H, f_theta, A, W} the condenser produced."""
+import numpy as np
+import pytest
+
+from oracle import mpqp as om
+
+
+def _example(name, rp, dp, Np=8, Nc=3):
+    if name == "aircraft":
+        mpc = om.aircraft(Np=Np, Nc=Nc, ks=tuple(range(2, Np + 1)))
+        mpc.Gd = np.array([[0.1, 0.0], [0.0, 0.02], [0.03, 0.0], [0.0, 0.01]])   # make d act on x too
+    else:
+        mpc = om.invpend(Np=Np, Nc=Nc)
+    mpc.reference_preview, mpc.disturbance_preview = rp, dp
+    mpc.preprocess_mpqp = False
+    return mpc
+
+
+def _rollout(mpc, x0, Rp, Dp, up, U):
+    """Cost (up to terms constant in U) and the general constraint rows, from a plain simulation.
+    Rp: ny x Np (column k is the reference of x_{k+1}); Dp: nd x Np (d_k acts on x_k -> x_{k+1} and
+    appears in y_{k+1})."""
+    N, Nc, nu = mpc.Np, mpc.Nc, mpc.nu
+    Qf = mpc.Q if not np.any(mpc.Qf != 0) else mpc.Qf
+    xs, us = [x0], []
+    J, x, uprev = 0.0, x0, up
+    for k in range(N):
+        u = U[min(k, Nc - 1)]
+        J += u @ mpc.R @ u + (u - uprev) @ mpc.Rr @ (u - uprev)
+        x = mpc.F @ x + mpc.G @ u + (mpc.Gd @ Dp[:, k] if mpc.nd_model else 0)
+        y = mpc.C @ x + (mpc.Dd @ Dp[:, k] if mpc.nd_model else 0) - Rp[:, k]
+        J += y @ (mpc.Q if k < N - 1 else Qf) @ y
+        xs.append(x); us.append(u); uprev = u
+    rows = []
+    for c in mpc.constraints:
+        kmax = N + 1 if not np.any(c.Au != 0) else N
+        for k in [k for k in c.ks if k <= kmax]:
+            j = k - 1
+            v = c.Ax @ xs[j]
+            if j < N:
+                v = v + c.Au @ us[j]
+            if c.Ad.size and j >= 1:
+                v = v + c.Ad @ Dp[:, j - 1]
+            rows.append(v)
+    return J, (np.concatenate(rows) if rows else np.zeros(0))
+
+
+@pytest.mark.parametrize("name,rp,dp", [("invpend", True, False), ("aircraft", True, False),
+                                        ("aircraft", False, True), ("aircraft", True, True)])
+def test_preview_mpqp_matches_rollout(name, rp, dp):
+    mpc = _example(name, rp, dp)
+    qp = om.mpc2mpqp(mpc)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    N, Nc, nu, ny, ndm = mpc.Np, mpc.Nc, mpc.nu, mpc.ny, mpc.nd_model
+    assert nr == (ny * N if rp else ny) and nd == (ndm * N if dp else ndm)
+    assert qp.f_theta.shape == (Nc * nu, nx + nr + nd + nup) and qp.W.shape[1] == nx + nr + nd + nup
+    rng = np.random.default_rng(7)
+    for _ in range(5):
+        x0 = rng.normal(size=nx)
+        Rp = rng.normal(size=(ny, N)) if rp else np.repeat(rng.normal(size=(ny, 1)), N, axis=1)
+        Dp = (rng.normal(size=(ndm, N)) if dp else np.repeat(rng.normal(size=(ndm, 1)), N, axis=1))
+        up = rng.normal(size=nu) if nup else np.zeros(nu)
+        th = mpc.form_parameter(x0, Rp if rp else Rp[:, 0], (Dp if dp else Dp[:, 0]) if ndm else None, up)
+        assert th.size == qp.W.shape[1]
+        U1, U2 = rng.normal(size=(Nc, nu)), rng.normal(size=(Nc, nu))
+        J1, g1 = _rollout(mpc, x0, Rp, Dp, up, U1)
+        J2, _ = _rollout(mpc, x0, Rp, Dp, up, U2)
+        q = lambda U: 0.5 * U @ qp.H @ U + (qp.f + qp.f_theta @ th) @ U
+        d_dense = 2 * (q(U1.ravel()) - q(U2.ravel()))
+        assert abs((J1 - J2) - d_dense) <= 1e-9 * max(1.0, abs(J1), abs(J2))
+        ng = qp.A.shape[0]
+        if ng:
+            dense_rows = qp.A @ U1.ravel() - qp.W[-ng:] @ th
+            np.testing.assert_allclose(dense_rows, g1, rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["invpend", "aircraft"])
+def test_constant_preview_equals_no_preview(name):
+    """A preview that holds one value over the horizon is the plain controller (utils.jl:88-93)."""
+    base = _example(name, False, False)
+    prev = _example(name, True, name == "aircraft")
+    qb, qv = om.mpc2mpqp(base), om.mpc2mpqp(prev)
+    np.testing.assert_allclose(qv.H, qb.H, rtol=0, atol=1e-9 * np.abs(qb.H).max())
+    rng = np.random.default_rng(3)
+    for _ in range(4):
+        x0 = rng.normal(size=base.nx)
+        r = rng.normal(size=base.ny)
+        d = rng.normal(size=base.nd_model) if base.nd_model else None
+        up = rng.normal(size=base.nu)
+        tb, tv = base.form_parameter(x0, r, d, up), prev.form_parameter(x0, r, d, up)
+        # the reference paired with x_0 and y_0's disturbance feed-through are constants in U: the
+        # linear terms agree exactly; the constraint offsets agree except on rows of x_0 (ks >= 2 here)
+        np.testing.assert_allclose(qv.f_theta @ tv, qb.f_theta @ tb, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(qv.W @ tv, qb.W @ tb, rtol=1e-9, atol=1e-9)
+
+
+def test_preview_flattening_holds_last_column():
+    mpc = _example("invpend", True, False, Np=6)
+    ny = mpc.ny
+    r = np.arange(ny * 3, dtype=float).reshape(ny, 3, order="F")
+    th = mpc.form_parameter(np.zeros(mpc.nx), r, None, np.zeros(mpc.nu))
+    got = th[mpc.nx:mpc.nx + ny * 6].reshape(ny, 6, order="F")
+    np.testing.assert_array_equal(got[:, :3], r)
+    np.testing.assert_array_equal(got[:, 3:], np.repeat(r[:, -1:], 3, axis=1))
+    with pytest.raises(ValueError):
+        mpc.form_parameter(np.zeros(mpc.nx), np.zeros(ny + 1), None, None)
