@@ -275,8 +275,8 @@ int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, d
 /* ---------------------------------------------------------------------------------------------
  * Host-side condensing: build the dense mpQP from a discrete-time model without
  * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
- * path supports: no prestabilising feedback, previews, offsets, binaries or generalized
- * parameters.  Pure host code; needs no GPU.
+ * path supports: no prestabilising feedback, offsets, binaries or generalized parameters
+ * (previews of r and d are supported, reference condensation is not).  Pure host code; needs no GPU.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
   int32_t rows;
@@ -309,6 +309,12 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
    * sets it.  NULL = no blocking. */
   const int32_t *move_blocks;
   const int32_t *n_move_blocks;
+  /* MPCSettings.reference_preview / disturbance_preview (src/types.jl:56-57; reference condensation
+   * off): theta carries ny*Np reference values / nd*Np disturbance values, column k of the preview
+   * first (format_reference / format_disturbance, src/utils.jl:78-205).  Constraints with Ar != 0
+   * are refused under reference_preview. */
+  int32_t reference_preview;
+  int32_t disturbance_preview;
 } lmpc_model;
 
 typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */

@@ -2,10 +2,12 @@
 // bounds and constraints to the dense mpQP {H, f, f_theta, A, bu, bl, W, senses} that
 // lmpc_gpu_create consumes, so that non-Julia callers can build a controller.
 //
-// What it follows in the reference (subset: no prestabilising feedback, previews, offsets,
-// binaries or generalized parameters -- those requests are refused):
+// What it follows in the reference (subset: no prestabilising feedback, offsets, binaries or
+// generalized parameters; previews of r / d without reference condensation):
 //   extended system / weights    /root/reference/src/mpc2mpqp.jl:649-731
 //   state predictor              /root/reference/src/mpc2mpqp.jl:20-46
+//   disturbance predictor        /root/reference/src/mpc2mpqp.jl:48-68
+//   preview cost / constraints   /root/reference/src/mpc2mpqp.jl:70-109, 535-610
 //   dense objective              /root/reference/src/mpc2mpqp.jl:407-533
 //   control bounds, general rows /root/reference/src/mpc2mpqp.jl:206-245, 249-354
 //   move blocking                /root/reference/src/mpc2mpqp.jl:830-857, src/setup.jl:196-251
@@ -102,15 +104,21 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   Mat Rr = md->Rr ? from_colmajor(md->Rr, nu, nu) : Mat(nu, nu);
   Mat Qf = md->Qf ? from_colmajor(md->Qf, ny, ny) : Mat(ny, ny);
   // parameter layout (mpc2mpqp.jl:147-164)
-  const int nr = md->reference_tracking ? ny : 0;
-  const int nd = ndm;
+  // with a preview the Np future values of r / d are parameters, not extended states
+  const bool rp = md->reference_preview && md->reference_tracking;
+  const bool dp = md->disturbance_preview && ndm > 0;
+  const int nr = (md->reference_tracking && !rp) ? ny : 0;     // reference part of the extended state
+  const int nd = dp ? 0 : ndm;                                 // disturbance part of the extended state
+  const int nrp = rp ? ny * Np : nr, ndp = dp ? ndm * Np : nd; // widths of the r / d blocks of theta
   bool aup = false;
   for (int ci = 0; ci < md->n_constraints; ++ci) {
     const lmpc_constraint &c = md->constraints[ci];
     if (c.Aup) for (int i = 0; i < c.rows * nu; ++i) if (c.Aup[i] != 0.0) aup = true;
   }
   const int nup = (any_nonzero(Rr) || aup) ? nu : 0;
-  const int nxe = nx + nr + nd + nup, nth = nxe;
+  const int nxe = nx + nr + nd + nup, nth = nx + nrp + ndp + nup;
+  // column of theta that holds extended-state entry j (insert_preview_parameter_blocks, mpc2mpqp.jl:70-92)
+  auto th_col = [&](int j) { return j < nx + nr ? j : (j < nx + nr + nd ? j - nr + nrp : j - nr - nd + nrp + ndp); };
 
   // ---- extended system x~ = [x; r; d; u^-] (mpc2mpqp.jl:649-690, K = 0) -------------------------
   Mat F(nxe, nxe), G(nxe, nu);
@@ -139,6 +147,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   }
   // ---- extended weights (mpc2mpqp.jl:692-731, K = 0) ----------------------------------------------
   if (!any_nonzero(Qf)) Qf = Q;
+  const Mat Q0 = Q, Qf0 = Qf;   // output weights before the extension (Q_full, Qf_full)
   Mat S(nxe, nu);
   if (nup > 0) {
     Q = block_diag(Q, Rr);
@@ -157,6 +166,15 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       add_block(Gk, 0, j * nu, G);
       set_block(Phi, (k + 1) * nxe, 0, Pk);
       set_block(Gam, (k + 1) * nxe, 0, Gk);
+    }
+  }
+  // disturbance predictor X += Psi [d_0; ...; d_{Np-1}] (mpc2mpqp.jl:48-68), block row by block row
+  std::vector<Mat> Psi;
+  if (dp) {
+    Psi.assign(Np + 1, Mat(nxe, ndm * Np));
+    for (int k = 1; k <= Np; ++k) {
+      Psi[k] = mul(F, Psi[k - 1]);
+      add_block(Psi[k], 0, (k - 1) * ndm, Gd);   // E = [Gd; 0]
     }
   }
   // ---- objective (mpc2mpqp.jl:407-533) -------------------------------------------------------------
@@ -181,11 +199,25 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     }
     const Mat GtW = mul(tr(Gk), W);
     add_block(H, 0, 0, mul(GtW, Gk));
-    add_block(fth, 0, 0, mul(GtW, Pk));
+    const Mat fk = mul(GtW, Pk);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < nxe; ++j) fth(i, th_col(j)) += fk(i, j);
+    if (k >= 1 && (rp || dp)) {
+      // ref_preview_cost / disturbance_preview_cost (mpc2mpqp.jl:535-610): y_k = C x_k + Dd d_{k-1}
+      // is weighted against preview column k-1 with Q_full (Qf_full at k = Np)
+      Mat Cfull(ny, nxe);
+      for (int i = 0; i < ny; ++i) for (int j = 0; j < nxe; ++j) Cfull(i, j) = C(i, j);
+      const Mat GCQ = mul(tr(Gk), mul(tr(Cfull), (k == Np) ? Qf0 : Q0));   // n x ny
+      if (rp) add_block(fth, 0, nx + (k - 1) * ny, GCQ, -1.0);
+      if (dp) {
+        Mat Yd = mul(Cfull, Psi[k]);
+        add_block(Yd, 0, (k - 1) * ndm, Dd);
+        add_block(fth, 0, nx + nrp, mul(GCQ, Yd));
+      }
+    }
   }
   if (any_nonzero(S)) {
     // Stot: S on blocks k < Nc (column block k), and on Nc <= k < Np into the last column block
-    Mat GS(n, n), StP(n, nth);
+    Mat GS(n, n), StP(n, nxe);
     for (int k = 0; k < Np; ++k) {
       const int cb = std::min(k, Nc - 1);
       Mat Gk(nxe, n), Pk(nxe, nxe);
@@ -197,7 +229,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       add_block(StP, cb * nu, 0, mul(tr(S), Pk));
     }
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) H(i, j) += GS(i, j) + GS(j, i);
-    add_block(fth, 0, 0, StP);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < nxe; ++j) fth(i, th_col(j)) += StP(i, j);
   }
   { Mat Hs(n, n); for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Hs(i, j) = 0.5 * (H(i, j) + H(j, i)); H = Hs; }
 
@@ -226,6 +258,9 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     if (mi <= 0) continue;
     const Mat Au = from_colmajor(c.Au, mi, nu), Ax = from_colmajor(c.Ax, mi, nx);
     const Mat Ar = from_colmajor(c.Ar, mi, nr), Ad = from_colmajor(c.Ad, mi, nd), Aupm = from_colmajor(c.Aup, mi, nup);
+    if (rp && c.Ar) for (int i = 0; i < mi * ny; ++i) if (c.Ar[i] != 0.0)
+      return cfail(LMPC_E_UNSUPPORTED, "constraints on the reference are not supported with reference_preview");
+    const Mat Adp = dp ? from_colmajor(c.Ad, mi, ndm) : Mat(mi, 0);
     Mat row(mi, nxe);
     set_block(row, 0, 0, Ax); set_block(row, 0, nx, Ar); set_block(row, 0, nx + nr, Ad); set_block(row, 0, nx + nr + nd, Aupm);
     const int kmax = any_nonzero(Au) ? Np : Np + 1;
@@ -241,10 +276,16 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       Mat Ak = mul(row, Gk);
       if (k <= Nc) add_block(Ak, 0, (k - 1) * nu, Au);
       const Mat Wk = mul(row, Pk);
+      Mat Wdk(mi, dp ? ndm * Np : 0);
+      if (dp) {   // -Ax~ Psi_{k-1} and the direct term -Ad d_{k-2} (disturbance_preview_direct, mpc2mpqp.jl:94-109)
+        Wdk = mul(row, Psi[k - 1]);
+        if (c.Ad && k >= 2) add_block(Wdk, 0, (k - 2) * ndm, Adp);
+      }
       for (int i = 0; i < mi; ++i) {
-        std::vector<double> ar(n), wr(nth);
+        std::vector<double> ar(n), wr(nth, 0.0);
         for (int j = 0; j < n; ++j) ar[j] = Ak(i, j);
-        for (int j = 0; j < nth; ++j) wr[j] = -Wk(i, j);
+        for (int j = 0; j < nxe; ++j) wr[th_col(j)] = -Wk(i, j);
+        for (int j = 0; j < Wdk.c; ++j) wr[nx + nrp + j] = -Wdk(i, j);
         Arows.push_back(ar); Wrows.push_back(wr);
         gbu.push_back(c.ub ? c.ub[i] : 1e30); gbl.push_back(c.lb ? c.lb[i] : -1e30);
         gsoft.push_back(c.soft ? 1 : 0); gprio.push_back(c.prio);
@@ -367,7 +408,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   }
   lmpc_mpqp *q = new lmpc_mpqp();
   const int mg = (int)Arows.size(), m = ms + mg;
-  q->n = nq; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nr; q->nd = nd; q->nuprev = nup; q->nu = nu;
+  q->n = nq; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nrp; q->nd = ndp; q->nuprev = nup; q->nu = nu;
   q->H = H; q->f_theta = fth; q->f.assign(nq, 0.0);
   q->A = Mat(mg, nq); q->W = Mat(m, nth);
   for (int i = 0; i < ms; ++i) for (int j = 0; j < nth; ++j) q->W(i, j) = W(i, j);

@@ -691,7 +691,8 @@ class _Model(C.Structure):
                 ("umin", C.c_void_p), ("umax", C.c_void_p),
                 ("constraints", C.c_void_p), ("n_constraints", C.c_int32),
                 ("reference_tracking", C.c_int32), ("preprocess", C.c_int32),
-                ("move_blocks", C.c_void_p), ("n_move_blocks", C.c_void_p)]
+                ("move_blocks", C.c_void_p), ("n_move_blocks", C.c_void_p),
+                ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32)]
 
 
 def _diag(v, n):
@@ -722,6 +723,7 @@ class MPC:
         self.umin = self.umax = None
         self.constraints = []
         self.reference_tracking, self.preprocess_mpqp, self.soft_weight = True, True, 1e6
+        self.reference_preview = self.disturbance_preview = False   # types.jl:56-57
         self.move_blocks = []
         self.gpu = None
         self.mpqp = None
@@ -830,7 +832,8 @@ class MPC:
         md = _Model(self.nx, self.nu, self.ny, self.nd, self.Np, self.Nc, cm(self.F), cm(self.G), cm(self.C),
                     cm(self.Gd), cm(self.Dd), cm(self.Q), cm(self.R), cm(self.Rr), cm(self.Qf),
                     cm(self.umin), cm(self.umax), C.cast(cons, C.c_void_p), len(self.constraints),
-                    int(self.reference_tracking), int(self.preprocess_mpqp), None, None)
+                    int(self.reference_tracking), int(self.preprocess_mpqp), None, None,
+                    int(self.reference_preview), int(self.disturbance_preview))
         if self.move_blocks:
             mbf = np.ascontiguousarray([v for b in self.move_blocks for v in b], np.int32)
             mbn = np.ascontiguousarray([len(b) for b in self.move_blocks], np.int32)
@@ -868,7 +871,30 @@ class MPC:
         return self.gpu if self.gpu is not None else self.setup()
 
     def compute_control(self, x, r=None, d=None, uprev=None, check=True):
+        if self.reference_preview and self.reference_tracking:
+            r = self._flatten_preview(r, self.ny)
+        if self.disturbance_preview and self.nd > 0:
+            d = self._flatten_preview(d, self.nd)
         return self._g().compute_control(x, r=r, d=d, uprev=uprev, check=check)
+
+    def _flatten_preview(self, v, rows):
+        """format_reference / format_disturbance with a preview (utils.jl:78-134, 155-205): a vector is
+        held over the horizon, a rows x cols matrix is cut to Np columns or extended by holding its
+        last column, then flattened column by column; rows x cols x N gives one preview per instance."""
+        Np = self.Np
+        if v is None:
+            return np.zeros(rows * Np)
+        v = np.asarray(v, np.float64)
+        if v.ndim == 1:
+            if v.size != rows:
+                raise ValueError(f"Reference vector length ({v.size}) must match ({rows})")
+            return np.tile(v, Np)
+        if v.shape[0] != rows:
+            raise ValueError(f"preview matrix must have {rows} rows")
+        if v.shape[1] < Np:
+            v = np.concatenate([v, np.repeat(v[:, -1:], Np - v.shape[1], axis=1)], axis=1)
+        v = v[:, :Np]
+        return v.reshape(rows * Np, -1, order="F") if v.ndim == 3 else v.reshape(-1, order="F")
 
     def solve(self, Theta, **kw):
         return self._g().solve(Theta, **kw)
@@ -886,6 +912,12 @@ class MPC:
 
     def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None,
                  plant=None, observer=None, noise=None):
+        rp = self.Np if (self.reference_preview and self.reference_tracking and r_traj is not None) else 0
+        dp = self.Np if (self.disturbance_preview and self.nd > 0 and d_traj is not None) else 0
+        if self.reference_preview and self.reference_tracking and not rp:
+            r = self._flatten_preview(r, self.ny)
+        if self.disturbance_preview and self.nd > 0 and not dp:
+            d = self._flatten_preview(d, self.nd)
         return self._g().simulate(self.F, self.G, x0, r=r, d=d, N=N, Gd=self.Gd, warm_start=warm_start,
                                   want_traj=want_traj, r_traj=r_traj, d_traj=d_traj, plant=plant,
-                                  observer=observer, noise=noise)
+                                  observer=observer, noise=noise, r_preview=rp, d_preview=dp)

@@ -640,3 +640,71 @@ def test_api_errors_are_codes_not_crashes(lmpc):
     rc = L.lmpc_gpu_simulate_bst_batch(ok._t, Fm.ctypes.data, Gm.ctypes.data, None, 1, 0, 0, 0, X0.ctypes.data, None, None,
                                        None, None, None, 3, 2, Xe.ctypes.data, Ul.ctypes.data, None)
     assert rc == -100 and b"must equal nth" in L.lmpc_gpu_last_error()
+
+
+# ---- controllers condensed with reference / disturbance previews (types.jl:56-57) ---------------------
+
+def _preview_controller(lmpc, rp, dp, Np=10, Nc=4):
+    """AFTI-16 with Np-step previews, built with the product's builder (C++ condenser) and the
+    oracle handed the constants the product computed."""
+    from test_condense_cpu import mirror_of
+    o = mpqp.aircraft(Np=Np, Nc=Nc, ks=(2, 3))
+    o.Gd = np.array([[0.1, 0.0], [0.0, 0.02], [0.03, 0.0], [0.0, 0.01]])
+    o.reference_preview, o.disturbance_preview = rp, dp
+    m = mirror_of(lmpc, o)
+    m.reference_preview, m.disturbance_preview = rp, dp
+    g = m.setup()
+    qp = mpqp.mpc2mpqp(o)
+    cst = g.ldp_constants()
+    cst["senses"] = g.senses
+    P = util.oracle_from_constants(qp, o.nu, cst, soft_weight=o.soft_weight)
+    return o, m, g, P
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rp,dp", [(True, False), (False, True), (True, True)])
+def test_preview_controller_batch_parity(lmpc, rp, dp):
+    """theta = [x; vec(r_1..r_Np); vec(d_0..d_Np-1); uprev] with time-varying previews: the GPU solve
+    of the preview-condensed controller against the oracle, instance by instance."""
+    o, m, g, P = _preview_controller(lmpc, rp, dp)
+    nx, nr, nd, nup = o.parameter_dims()
+    assert g.dims == (nx, nr, nd, nup) and nr == (2 * o.Np if rp else 2) and nd == (2 * o.Np if dp else 2)
+    N = 3000
+    rng = np.random.default_rng(21)
+    X = rng.uniform(-1, 1, (nx, N)) * np.array([4, 0.3, 1, 0.3])[:, None]
+    Rm = 0.3 * rng.standard_normal((nr, N)) * np.tile([1.0, 0.05], nr // 2)[:, None]
+    Dm = 0.2 * rng.standard_normal((nd, N))
+    Um = rng.uniform(-0.5, 0.5, (nup, N))
+    Th = np.asfortranarray(np.vstack([X, Rm, Dm, Um]))
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    assert_parity(out, ref)
+    assert len(np.unique(ref["act_u"], axis=0)) > 3          # the batch does exercise the constraints
+    # the builder's compute_control flattens a per-instance preview the same way
+    if rp and dp:
+        U = m.compute_control(X[:, :50], r=Rm[:, :50].reshape(2, o.Np, 50, order="F"),
+                              d=Dm[:, :50].reshape(2, o.Np, 50, order="F"), uprev=Um[:, :50])
+        assert np.array_equal(U, np.asarray(out["U"])[:, :50])
+
+
+@pytest.mark.gpu
+def test_preview_controller_closed_loop_through_builder(lmpc):
+    """MPC.simulate on a preview-condensed controller slides the Np-column windows itself
+    (simulation.jl:102-104, 128-147): the same loop stepped with compute_control gives the same u."""
+    o, m, g, P = _preview_controller(lmpc, True, True)
+    T, N, Np = 15, 64, o.Np
+    rng = np.random.default_rng(5)
+    X0 = rng.uniform(-1, 1, (o.nx, N)) * np.array([4, 0.3, 1, 0.3])[:, None]
+    rs = np.vstack([0.2 * np.sin(0.3 * np.arange(12)), np.zeros(12)])     # shorter than T + Np: last held
+    ds = 0.2 * rng.standard_normal((2, 40))
+    out = m.simulate(X0, N=T, r_traj=rs, d_traj=ds, want_traj=True, warm_start=False)
+    hold = lambda v, n: np.hstack([v, np.repeat(v[:, -1:], max(0, n - v.shape[1]), axis=1)])
+    rsx, dsx = hold(rs, T + Np + 1), hold(ds, T + Np + 1)
+    for q in range(0, N, 16):
+        x, u = X0[:, q].copy(), np.zeros(o.nu)
+        for k in range(T):
+            th = o.form_parameter(x, rsx[:, k + 1:k + 1 + Np], dsx[:, k:k + Np], u)
+            u, flag, _ = P.solve(th)
+            assert flag >= 1
+            assert np.allclose(u, out["Utraj"][q, k], rtol=0, atol=2e-5)
+            x = o.F @ x + o.G @ u + o.Gd @ dsx[:, k]
+        assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=2e-5)

@@ -108,3 +108,44 @@ def test_preview_flattening_holds_last_column():
     np.testing.assert_array_equal(got[:, 3:], np.repeat(r[:, -1:], 3, axis=1))
     with pytest.raises(ValueError):
         mpc.form_parameter(np.zeros(mpc.nx), np.zeros(ny + 1), None, None)
+
+
+# ---- the C++ condenser behind the C ABI (lmpc_gpu_condense) against the restatement -----------------
+
+@pytest.mark.parametrize("name,rp,dp,pre", [("invpend", True, False, True), ("aircraft", True, False, True),
+                                            ("aircraft", False, True, False), ("aircraft", True, True, True),
+                                            ("aircraft", True, True, False)])
+def test_cpp_condenser_previews_match_restatement(lmpc, name, rp, dp, pre):
+    from test_condense_cpu import mirror_of
+    o = _example(name, rp, dp)
+    o.preprocess_mpqp = pre
+    ref = om.mpc2mpqp(o)
+    m = mirror_of(lmpc, o)
+    m.reference_preview, m.disturbance_preview, m.preprocess_mpqp = rp, dp, pre
+    q = m.condense()
+    assert q["dims"] == o.parameter_dims()
+    for k in ("H", "f_theta", "A", "W"):
+        want = getattr(ref, k)
+        assert q[k].shape == want.shape, k
+        assert np.max(np.abs(q[k] - want), initial=0.0) <= 1e-12 * max(1.0, np.abs(want).max(initial=0.0)), k
+    assert np.allclose(q["bu"], ref.bu, rtol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-13)
+    assert np.array_equal(q["senses"], ref.senses)
+
+
+def test_cpp_condenser_refuses_reference_rows_with_preview(lmpc):
+    m = lmpc.MPC(np.eye(2), np.ones((2, 1)), Np=4)
+    m.add_constraint(Ax=np.eye(2), Ar=np.eye(2), ub=[1, 1], lb=[-1, -1])
+    m.reference_preview = True
+    with pytest.raises(lmpc.LmpcError):
+        m.condense()
+
+
+def test_builder_flattens_previews(lmpc):
+    m = lmpc.MPC(np.eye(2), np.ones((2, 1)), Np=4)
+    r = np.array([[1.0, 2.0], [3.0, 4.0]])
+    np.testing.assert_array_equal(m._flatten_preview(r, 2), [1, 3, 2, 4, 2, 4, 2, 4])
+    np.testing.assert_array_equal(m._flatten_preview(np.array([5.0, 6.0]), 2), [5, 6] * 4)
+    r3 = np.stack([r, 10 * r], axis=2)
+    got = m._flatten_preview(r3, 2)
+    assert got.shape == (8, 2)
+    np.testing.assert_array_equal(got[:, 1], 10 * got[:, 0])
