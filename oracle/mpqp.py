@@ -224,6 +224,17 @@ class MPC:
         if len(np.atleast_1d(ymin)) or len(np.atleast_1d(ymax)):
             self.set_output_bounds(ymin, ymax)
 
+    def set_prestabilizing_feedback(self, K=None):
+        """setup.jl:186-199: u = v - K x, the QP is over v.  K = None: infinite-horizon LQR gain of
+        (F, G, R + Rr, C'QC) (the reference calls `ared`)."""
+        if K is None:
+            from scipy.linalg import solve_discrete_are
+            Rt = self.R + self.Rr
+            Qx = self.C.T @ self.Q @ self.C
+            P = solve_discrete_are(self.F, self.G, Qx, Rt)
+            K = np.linalg.solve(Rt + self.G.T @ P @ self.G, self.G.T @ P @ self.F)
+        self.K = np.asarray(K, float).reshape(self.nu, self.nx)
+
     # -- parameter layout ---------------------------------------------------
     def affine_parameter_dim(self):
         """np: widest generalized-parameter block in use (utils.jl:207-217)."""
@@ -288,7 +299,8 @@ def extended_system(mpc: MPC):
     """x~ = [x; r; d; u^-]  (mpc2mpqp.jl:649-690 with K = 0, no offset); previewed r / d are not states."""
     nx, nr, nd, nup = mpc.parameter_dims()
     nu = mpc.nu
-    F, G, C = mpc.F.copy(), mpc.G.copy(), mpc.C.copy()
+    K = mpc.K
+    F, G, C = mpc.F - mpc.G @ K, mpc.G.copy(), mpc.C.copy()
     if mpc.reference_preview:
         nr = 0
     if mpc.disturbance_preview:
@@ -304,10 +316,13 @@ def extended_system(mpc: MPC):
         C = np.hstack([C, mpc.Dd])
     if nup > 0:
         F = block_diag(F, np.zeros((nu, nu)))
+        F[-nu:, :nx] = -K                      # u^- of the next step is v - K x
         G = np.vstack([G, np.eye(nu)])
         nye, nxe = C.shape
         C = np.vstack([np.hstack([C, np.zeros((nye, nu))]),
-                       np.hstack([np.zeros((nu, nxe)), np.eye(nu)])])
+                       np.hstack([K, np.zeros((nu, nxe - nx)), np.eye(nu)])])
+    if np.any(mpc.R != 0) and np.any(K != 0):  # u'Ru with u = v - K x: output K x weighted by R
+        C = np.vstack([C, np.hstack([K, np.zeros((nu, C.shape[1] - nx))])])
     return F, G, C
 
 
@@ -330,7 +345,12 @@ def extended_cost(mpc: MPC):
         Q = block_diag(Q, Rr)
         Qf = block_diag(Qf, np.zeros((nu, nu)))
         S = np.vstack([S, -Rr])
+        S[:nx] -= mpc.K.T @ Rr
         R = R + Rr
+    if np.any(mpc.R != 0) and np.any(mpc.K != 0):
+        Q = block_diag(Q, mpc.R)
+        Qf = block_diag(Qf, np.zeros((nu, nu)))
+        S[:nx] -= mpc.K.T @ mpc.R
     return Q, R, S, Qf
 
 
@@ -425,13 +445,32 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
     return H, f, f_theta
 
 
-def control_bounds(mpc: MPC, nth):
-    """Leading simple rows (mpc2mpqp.jl:206-245 with K = 0)."""
-    Nc = mpc.Nc
+def control_bounds(mpc: MPC, nth, Phi=None, Gam=None):
+    """Leading simple rows, or with a prestabilising feedback the general rows
+    lb <= v_k - K x_k <= ub, i.e. A = I - K~ Gamma, W = K~ Phi (mpc2mpqp.jl:206-245)."""
+    Nc, nu, nx = mpc.Nc, mpc.nu, mpc.nx
     bu = np.tile(mpc.umax, Nc)
     bl = np.tile(mpc.umin, Nc)
-    W = np.zeros((Nc * mpc.nu, nth))
-    return bu, bl, W
+    W = np.zeros((Nc * nu, nth))
+    A = np.zeros((0, Nc * nu))
+    if np.any(mpc.K != 0):
+        nxe = Phi.shape[1]
+        Kfull = np.kron(np.eye(Nc), np.hstack([mpc.K, np.zeros((nu, nxe - nx))]))
+        A = np.eye(Nc * nu) - Kfull @ Gam[:Nc * nxe, :]
+        We = Kfull @ Phi[:Nc * nxe, :]
+        _, nrp, ndp, _ = mpc.parameter_dims()
+        nrx = 0 if mpc.reference_preview else nrp
+        ndx = 0 if mpc.disturbance_preview else ndp
+        parts = [We[:, :nx], np.zeros((Nc * nu, nrp)) if mpc.reference_preview else We[:, nx:nx + nrx]]
+        if mpc.disturbance_preview and ndp > 0:
+            Psi = disturbance_predictor(Phi[nxe:2 * nxe, :],
+                                        np.vstack([mpc.Gd, np.zeros((nxe - nx, mpc.nd_model))]), mpc.Np)
+            parts.append(Kfull @ Psi[:Nc * nxe, :])
+        else:
+            parts.append(We[:, nx + nrx:nx + nrx + ndx])
+        parts.append(We[:, nx + nrx + ndx:])
+        W = np.hstack(parts + [np.zeros((Nc * nu, nth - sum(p.shape[1] for p in parts)))])
+    return bu, bl, W, A
 
 
 def general_constraints(mpc: MPC, Phi, Gam):
@@ -458,7 +497,7 @@ def general_constraints(mpc: MPC, Phi, Gam):
         Ar = c.Ar if (c.Ar.size and nr > 0) else np.zeros((mi, nr))
         Ad = c.Ad if (c.Ad.size and nd > 0) else np.zeros((mi, nd))
         Aup = c.Aup if c.Aup.size else np.zeros((mi, nup))
-        row = np.hstack([c.Ax, Ar, Ad, Aup])
+        row = np.hstack([c.Ax - c.Au @ mpc.K, Ar, Ad, Aup])
         sel = [k - 1 for k in ks]
         Aut = np.vstack([Aut, np.kron(eyeU[sel, :], c.Au)])
         Axt = np.vstack([Axt, np.kron(eyeX[sel, :], row)])
@@ -618,17 +657,19 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
     H, f, f_theta = dense_objective(mpc, F, G, C, Phi, Gam)
     n = H.shape[0]
     nth = sum(mpc.parameter_dims()) + mpc.affine_parameter_dim()
+    A = np.zeros((0, n))
     if len(mpc.umax):
-        bu, bl, W = control_bounds(mpc, nth)
+        bu, bl, W, A = control_bounds(mpc, nth, Phi, Gam)
         soft = np.zeros(n, bool)
         prio = np.zeros(n, int)
     else:
         bu, bl, W = np.zeros(0), np.zeros(0), np.zeros((0, nth))
         soft, prio = np.zeros(0, bool), np.zeros(0, int)
-    A = np.zeros((0, n))
+    if np.any(mpc.K != 0) and getattr(mpc, "move_blocks", None):
+        raise ValueError("move blocking together with a prestabilising feedback is not supported")
     if mpc.constraints:
         Ag, bug, blg, Wg, sg, pg = general_constraints(mpc, Phi, Gam)
-        A = Ag
+        A = np.vstack([A, Ag])
         bu, bl, W = np.concatenate([bu, bug]), np.concatenate([bl, blg]), np.vstack([W, Wg])
         soft, prio = np.concatenate([soft, sg]), np.concatenate([prio, pg])
     if getattr(mpc, "move_blocks", None):
