@@ -275,8 +275,8 @@ int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, d
 /* ---------------------------------------------------------------------------------------------
  * Host-side condensing: build the dense mpQP from a discrete-time model without
  * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
- * path supports: no prestabilising feedback, offsets, binaries or generalized parameters
- * (previews of r and d are supported, reference condensation is not).  Pure host code; needs no GPU.
+ * path supports: no offsets, binaries or generalized parameters (previews of r and d and a
+ * prestabilising feedback are supported, reference condensation is not).  Pure host code; needs no GPU.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
   int32_t rows;
@@ -315,6 +315,11 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
    * are refused under reference_preview. */
   int32_t reference_preview;
   int32_t disturbance_preview;
+  /* prestabilising feedback u = v - K x (set_prestabilizing_feedback!, src/setup.jl:186-199): nu x nx,
+   * NULL = 0.  The QP is then over v, the control bounds become general rows (ms = 0), and the same K
+   * must be given to lmpc_gpu_create for the output map u = z[1:nu] - K x (src/utils.jl:46-50).
+   * Refused together with move blocking. */
+  const double *K;
 } lmpc_model;
 
 typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */

@@ -2,8 +2,8 @@
 // bounds and constraints to the dense mpQP {H, f, f_theta, A, bu, bl, W, senses} that
 // lmpc_gpu_create consumes, so that non-Julia callers can build a controller.
 //
-// What it follows in the reference (subset: no prestabilising feedback, offsets, binaries or
-// generalized parameters; previews of r / d without reference condensation):
+// What it follows in the reference (subset: no offsets, binaries or generalized parameters; previews
+// of r / d without reference condensation; prestabilising feedback not together with move blocking):
 //   extended system / weights    /root/reference/src/mpc2mpqp.jl:649-731
 //   state predictor              /root/reference/src/mpc2mpqp.jl:20-46
 //   disturbance predictor        /root/reference/src/mpc2mpqp.jl:48-68
@@ -103,6 +103,13 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   Mat R = md->R ? from_colmajor(md->R, nu, nu) : eye(nu);
   Mat Rr = md->Rr ? from_colmajor(md->Rr, nu, nu) : Mat(nu, nu);
   Mat Qf = md->Qf ? from_colmajor(md->Qf, ny, ny) : Mat(ny, ny);
+  // prestabilising feedback u = v - K x (src/setup.jl:186-199): the QP is over v
+  const Mat K = from_colmajor(md->K, nu, nx);
+  const bool hasK = any_nonzero(K);
+  const Mat Rorig = R;
+  const bool kr = hasK && any_nonzero(Rorig);   // u'Ru then needs the output K x (mpc2mpqp.jl:679-681, 718-724)
+  if (hasK && md->move_blocks && md->n_move_blocks)
+    return cfail(LMPC_E_UNSUPPORTED, "move blocking together with a prestabilising feedback is not supported");
   // parameter layout (mpc2mpqp.jl:147-164)
   // with a preview the Np future values of r / d are parameters, not extended states
   const bool rp = md->reference_preview && md->reference_tracking;
@@ -123,6 +130,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   // ---- extended system x~ = [x; r; d; u^-] (mpc2mpqp.jl:649-690, K = 0) -------------------------
   Mat F(nxe, nxe), G(nxe, nu);
   set_block(F, 0, 0, F0); set_block(G, 0, 0, G0);
+  if (hasK) add_block(F, 0, 0, mul(G0, K), -1.0);
   int off = nx;
   Mat C = C0;   // grows column-wise
   auto hcat = [](const Mat &A, const Mat &B) { Mat M(A.r, A.c + B.c); set_block(M, 0, 0, A); set_block(M, 0, A.c, B); return M; };
@@ -139,10 +147,18 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     off += nd;
   }
   if (nup > 0) {
-    for (int i = 0; i < nu; ++i) G(off + i, i) = 1.0;      // F block stays 0
+    for (int i = 0; i < nu; ++i) G(off + i, i) = 1.0;      // F block stays 0 ...
+    set_block(F, off, 0, K, -1.0);                         // ... except u^-+ = v - K x
     Mat C2(C.r + nu, C.c + nu);
     set_block(C2, 0, 0, C);
+    set_block(C2, C.r, 0, K);
     for (int i = 0; i < nu; ++i) C2(C.r + i, C.c + i) = 1.0;
+    C = C2;
+  }
+  if (kr) {
+    Mat C2(C.r + nu, C.c);
+    set_block(C2, 0, 0, C);
+    set_block(C2, C.r, 0, K);
     C = C2;
   }
   // ---- extended weights (mpc2mpqp.jl:692-731, K = 0) ----------------------------------------------
@@ -153,6 +169,12 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     Q = block_diag(Q, Rr);
     Qf = block_diag(Qf, Mat(nu, nu));
     for (int i = 0; i < nu; ++i) for (int j = 0; j < nu; ++j) { S(nx + nr + nd + i, j) = -Rr(i, j); R(i, j) += Rr(i, j); }
+    if (hasK) add_block(S, 0, 0, mul(tr(K), Rr), -1.0);
+  }
+  if (kr) {
+    Q = block_diag(Q, Rorig);
+    Qf = block_diag(Qf, Mat(nu, nu));
+    add_block(S, 0, 0, mul(tr(K), Rorig), -1.0);
   }
   // ---- predictor X = Phi x0 + Gamma U (mpc2mpqp.jl:20-46) -----------------------------------------
   Mat Phi((Np + 1) * nxe, nxe), Gam((Np + 1) * nxe, Nc * nu);
@@ -238,7 +260,33 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   std::vector<int> soft, prio;
   Mat W(0, nth);
   int ms = 0;
-  if (md->umax || md->umin) {
+  std::vector<std::vector<double>> Arows, Wrows;
+  std::vector<double> gbu, gbl;
+  std::vector<int> gsoft, gprio;
+  if ((md->umax || md->umin) && hasK) {
+    // lb <= v_k - K x_k <= ub: general rows A = I - K~ Gamma, W = K~ Phi (+ K~ Psi) (mpc2mpqp.jl:206-245)
+    Mat row(nu, nxe);
+    set_block(row, 0, 0, K);
+    for (int k = 0; k < Nc; ++k) {
+      Mat Gk(nxe, n), Pk(nxe, nxe);
+      for (int i = 0; i < nxe; ++i) {
+        for (int j = 0; j < n; ++j) Gk(i, j) = Gam(k * nxe + i, j);
+        for (int j = 0; j < nxe; ++j) Pk(i, j) = Phi(k * nxe + i, j);
+      }
+      const Mat KG = mul(row, Gk), KP = mul(row, Pk);
+      const Mat KPsi = dp ? mul(row, Psi[k]) : Mat(nu, 0);
+      for (int i = 0; i < nu; ++i) {
+        std::vector<double> ar(n), wr(nth, 0.0);
+        for (int j = 0; j < n; ++j) ar[j] = -KG(i, j);
+        ar[k * nu + i] += 1.0;
+        for (int j = 0; j < nxe; ++j) wr[th_col(j)] = KP(i, j);
+        for (int j = 0; j < KPsi.c; ++j) wr[nx + nrp + j] = KPsi(i, j);
+        Arows.push_back(ar); Wrows.push_back(wr);
+        gbu.push_back(md->umax ? md->umax[i] : 1e30); gbl.push_back(md->umin ? md->umin[i] : -1e30);
+        gsoft.push_back(0); gprio.push_back(0);
+      }
+    }
+  } else if (md->umax || md->umin) {
     ms = n;
     for (int b = 0; b < Nc; ++b)
       for (int i = 0; i < nu; ++i) {
@@ -249,14 +297,13 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     W = Mat(ms, nth);
   }
   // general rows (mpc2mpqp.jl:249-354): lb <= [Ax Ar Ad Aup] x~_{k-1} + Au u_{k-1} <= ub, k in ks
-  std::vector<std::vector<double>> Arows, Wrows;
-  std::vector<double> gbu, gbl;
-  std::vector<int> gsoft, gprio;
   for (int ci = 0; ci < md->n_constraints; ++ci) {
     const lmpc_constraint &c = md->constraints[ci];
     const int mi = c.rows;
     if (mi <= 0) continue;
-    const Mat Au = from_colmajor(c.Au, mi, nu), Ax = from_colmajor(c.Ax, mi, nx);
+    const Mat Au = from_colmajor(c.Au, mi, nu);
+    Mat Ax = from_colmajor(c.Ax, mi, nx);
+    if (hasK) add_block(Ax, 0, 0, mul(Au, K), -1.0);
     const Mat Ar = from_colmajor(c.Ar, mi, nr), Ad = from_colmajor(c.Ad, mi, nd), Aupm = from_colmajor(c.Aup, mi, nup);
     if (rp && c.Ar) for (int i = 0; i < mi * ny; ++i) if (c.Ar[i] != 0.0)
       return cfail(LMPC_E_UNSUPPORTED, "constraints on the reference are not supported with reference_preview");

@@ -692,7 +692,7 @@ class _Model(C.Structure):
                 ("constraints", C.c_void_p), ("n_constraints", C.c_int32),
                 ("reference_tracking", C.c_int32), ("preprocess", C.c_int32),
                 ("move_blocks", C.c_void_p), ("n_move_blocks", C.c_void_p),
-                ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32)]
+                ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32), ("K", C.c_void_p)]
 
 
 def _diag(v, n):
@@ -724,9 +724,23 @@ class MPC:
         self.constraints = []
         self.reference_tracking, self.preprocess_mpqp, self.soft_weight = True, True, 1e6
         self.reference_preview = self.disturbance_preview = False   # types.jl:56-57
+        self.K = None                                               # prestabilising feedback, setup.jl:186-199
         self.move_blocks = []
         self.gpu = None
         self.mpqp = None
+
+    def set_prestabilizing_feedback(self, K=None):
+        """set_prestabilizing_feedback!(mpc[, K]) (setup.jl:186-199): u = v - K x with the QP over v;
+        without K the infinite-horizon LQR gain of (F, G, R + Rr, C'QC), as the reference's `ared` call."""
+        if K is None:
+            from scipy.linalg import solve_discrete_are
+            Cm = np.eye(self.nx) if self.C is None else self.C
+            Q = np.eye(self.ny) if self.Q is None else self.Q
+            R = (np.eye(self.nu) if self.R is None else self.R) + (0 if self.Rr is None else self.Rr)
+            P = solve_discrete_are(self.F, self.G, Cm.T @ Q @ Cm, R)
+            K = np.linalg.solve(R + self.G.T @ P @ self.G, self.G.T @ P @ self.F)
+        self.K = np.asarray(K, np.float64).reshape(self.nu, self.nx)
+        self.gpu = self.mpqp = None
 
     # setup.jl:196-251
     def move_block(self, block):
@@ -833,7 +847,7 @@ class MPC:
                     cm(self.Gd), cm(self.Dd), cm(self.Q), cm(self.R), cm(self.Rr), cm(self.Qf),
                     cm(self.umin), cm(self.umax), C.cast(cons, C.c_void_p), len(self.constraints),
                     int(self.reference_tracking), int(self.preprocess_mpqp), None, None,
-                    int(self.reference_preview), int(self.disturbance_preview))
+                    int(self.reference_preview), int(self.disturbance_preview), cm(self.K))
         if self.move_blocks:
             mbf = np.ascontiguousarray([v for b in self.move_blocks for v in b], np.int32)
             mbn = np.ascontiguousarray([len(b) for b in self.move_blocks], np.int32)
@@ -862,7 +876,7 @@ class MPC:
         (`devices=[...]`: one replica per listed GPU, host batches split by contiguous ranges)."""
         q = self.condense()
         args = (q["H"], q["f"], q["f_theta"], q["A"], q["bu"], q["bl"], q["W"], q["senses"])
-        kw = dict(nu=self.nu, nx=self.nx, soft_weight=self.soft_weight, settings=settings, dims=q["dims"])
+        kw = dict(nu=self.nu, nx=self.nx, soft_weight=self.soft_weight, settings=settings, dims=q["dims"], K=self.K)
         self.gpu = (MultiGpuMPC(*args, devices=devices, **kw) if devices is not None
                     else GpuMPC(*args, device=device, **kw))
         return self.gpu

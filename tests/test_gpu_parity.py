@@ -708,3 +708,43 @@ def test_preview_controller_closed_loop_through_builder(lmpc):
             assert np.allclose(u, out["Utraj"][q, k], rtol=0, atol=2e-5)
             x = o.F @ x + o.G @ u + o.Gd @ dsx[:, k]
         assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=2e-5)
+
+
+# ---- prestabilising feedback condensed by the builder (setup.jl:186-199) ------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["invpend", "aircraft"])
+def test_prestabilised_controller_parity_and_equivalence(lmpc, name):
+    """u = v - K x with the QP over v.  (i) GPU == oracle on the prestabilised controller (bounds are
+    general rows there, ms = 0); (ii) with Nc = Np it is a change of variables of the plain controller,
+    so both give the same control (the reference asserts this kind of agreement at 1e-6 .. 1e-10)."""
+    from test_condense_cpu import mirror_of
+    if name == "invpend":
+        o = mpqp.invpend(Np=10, Nc=10)
+        lo, hi = util.theta_range("invpend", 0.25)
+    else:
+        o = mpqp.aircraft(Np=6, Nc=6, ks=(2, 3))
+        lo, hi = util.theta_range("aircraft", 0.1)
+    plain = mirror_of(lmpc, o)
+    gp = plain.setup()
+    o.set_prestabilizing_feedback()
+    m = mirror_of(lmpc, o)
+    m.set_prestabilizing_feedback()
+    g = m.setup()
+    qp = mpqp.mpc2mpqp(o)
+    assert qp.A.shape[0] == len(qp.bu) and g.dims == o.parameter_dims()
+    cst = g.ldp_constants()
+    cst["senses"] = g.senses
+    L = mpqp.qp2ldp(qp, o.nu, K=o.K, soft_weight=o.soft_weight)
+    P = util.oracle_from_constants(qp, o.nu, cst, soft_weight=o.soft_weight)
+    assert np.allclose(L.Uth_offset, cst["Uth"], rtol=1e-9, atol=1e-11)     # K is in the output map
+    N = 4000
+    Th = np.asfortranarray(mpqp.sample_theta(lo, hi, N, seed=33))
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    assert_parity(out, ref)
+    base = gp.solve(Th)
+    ok = (out["exitflag"] == 1) & (base["exitflag"] == 1)
+    assert ok.sum() > 500
+    Ua, Ub = np.asarray(out["U"])[:, ok], np.asarray(base["U"])[:, ok]
+    assert np.max(np.abs(Ua - Ub)) <= 1e-6 * max(1.0, np.abs(Ub).max())
+    assert len(np.unique(base["active_upper"][ok], axis=0)) > 3

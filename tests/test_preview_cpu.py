@@ -201,3 +201,38 @@ def test_lqr_gain_is_a_fixed_point_of_the_riccati_recursion():
         P = Qx + mpc.F.T @ P @ (mpc.F - mpc.G @ Kk)
     np.testing.assert_allclose(K, Kk, rtol=1e-6, atol=1e-8)
     assert np.max(np.abs(np.linalg.eigvals(mpc.F - mpc.G @ K))) < 1.0
+
+
+@pytest.mark.parametrize("name,rp,dp,pre", [("invpend", False, False, True), ("aircraft", False, False, True),
+                                            ("aircraft", True, True, False), ("aircraft", True, False, True)])
+def test_cpp_condenser_prestabilised_matches_restatement(lmpc, name, rp, dp, pre):
+    from test_condense_cpu import mirror_of
+    o = _example(name, rp, dp)
+    o.preprocess_mpqp = pre
+    if name == "aircraft":
+        o.R = np.diag([0.3, 0.2])
+        o.add_constraint(Ax=np.array([[1.0, 0, 0, 0.5]]), Au=np.array([[0.2, -0.1]]), ub=[3.0], lb=[-3.0],
+                         ks=[1, 2, 3])
+    o.set_prestabilizing_feedback()              # LQR gain
+    ref = om.mpc2mpqp(o)
+    m = mirror_of(lmpc, o)
+    m.reference_preview, m.disturbance_preview, m.preprocess_mpqp = rp, dp, pre
+    m.set_prestabilizing_feedback()
+    np.testing.assert_allclose(m.K, o.K, rtol=1e-12, atol=1e-14)
+    q = m.condense()
+    assert q["dims"] == o.parameter_dims() and q["A"].shape[0] == len(q["bu"])
+    for k in ("H", "f_theta", "A", "W"):
+        want = getattr(ref, k)
+        assert q[k].shape == want.shape, k
+        assert np.max(np.abs(q[k] - want), initial=0.0) <= 1e-11 * max(1.0, np.abs(want).max(initial=0.0)), k
+    assert np.allclose(q["bu"], ref.bu, rtol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-13)
+    assert np.array_equal(q["senses"], ref.senses)
+
+
+def test_cpp_condenser_refuses_feedback_with_move_blocking(lmpc):
+    m = lmpc.MPC(np.array([[1.0, 0.1], [0, 1.0]]), np.array([[0.0], [0.1]]), Np=6)
+    m.set_input_bounds([-1.0], [1.0])
+    m.move_block([2, 2, 2])
+    m.set_prestabilizing_feedback(np.array([[0.5, 0.5]]))
+    with pytest.raises(lmpc.LmpcError):
+        m.condense()
