@@ -748,3 +748,40 @@ def test_prestabilised_controller_parity_and_equivalence(lmpc, name):
     Ua, Ub = np.asarray(out["U"])[:, ok], np.asarray(base["U"])[:, ok]
     assert np.max(np.abs(Ua - Ub)) <= 1e-6 * max(1.0, np.abs(Ub).max())
     assert len(np.unique(base["active_upper"][ok], axis=0)) > 3
+
+
+@pytest.mark.gpu
+def test_reference_case_disturbance_preview_simulation(lmpc):
+    """test/runtests.jl:382-408 through the builder on the GPU: a 20-step closed loop with d stepping
+    0 -> 1 after 8 steps.  With the preview the controls differ (norm > 1e-2) and the output energy
+    drops below 0.9 of the no-preview loop; the GPU loop equals the oracle's stepwise loop."""
+    from test_condense_cpu import mirror_of
+    from test_preview_cpu import _dist_preview_case
+    o = _dist_preview_case()
+    d_traj = np.hstack([np.zeros((1, 8)), np.ones((1, 12))])
+    T = 20
+    def ys_of(U):
+        x, ys = np.zeros(2), []
+        for k in range(T):
+            ys.append(o.C @ x)
+            x = o.F @ x + o.G @ U[k] + o.Gd @ d_traj[:, k]
+        return np.array(ys)
+    m0 = mirror_of(lmpc, o)
+    U0 = m0.simulate(np.zeros((2, 1)), N=T, d_traj=d_traj, want_traj=True, warm_start=False)["Utraj"][0]
+    o.disturbance_preview = True
+    m1 = mirror_of(lmpc, o)
+    m1.disturbance_preview = True
+    out = m1.simulate(np.zeros((2, 1)), N=T, d_traj=d_traj, want_traj=True, warm_start=False)
+    U1 = out["Utraj"][0]
+    assert m1.gpu.dims == (2, 1, 5, 0) and np.all(out["exitflag"] >= 1)
+    assert np.linalg.norm(U1 - U0) > 1e-2
+    assert np.linalg.norm(ys_of(U1)) / np.linalg.norm(ys_of(U0)) < 0.9
+    # the oracle's loop, step by step, on the same controller
+    qp = mpqp.mpc2mpqp(o)
+    P = ldp.OracleProblem(mpqp.qp2ldp(qp, o.nu, soft_weight=o.soft_weight), o.nu)
+    dsx = np.hstack([d_traj, np.repeat(d_traj[:, -1:], o.Np + 1, axis=1)])
+    x = np.zeros(2)
+    for k in range(T):
+        u, flag, _ = P.solve(o.form_parameter(x, None, dsx[:, k:k + o.Np], None))
+        assert flag >= 1 and np.allclose(u, U1[k], rtol=0, atol=1e-9)
+        x = o.F @ x + o.G @ u + o.Gd @ dsx[:, k]

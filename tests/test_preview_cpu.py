@@ -236,3 +236,72 @@ def test_cpp_condenser_refuses_feedback_with_move_blocking(lmpc):
     m.set_prestabilizing_feedback(np.array([[0.5, 0.5]]))
     with pytest.raises(lmpc.LmpcError):
         m.condense()
+
+
+# ---- the reference's own tests of these features, restated on the oracle -----------------------------
+
+def _oracle_control(o, x, r=None, d=None, uprev=None):
+    from oracle import ldp
+    qp = om.mpc2mpqp(o)
+    P = ldp.OracleProblem(om.qp2ldp(qp, o.nu, K=o.K, soft_weight=o.soft_weight), o.nu)
+    u, flag, _ = P.solve(o.form_parameter(x, r, d, uprev))
+    assert flag >= 1
+    return u, qp
+
+
+def test_reference_case_prestabilising_feedback_keeps_the_control():
+    """test/runtests.jl:128-143: MPC([0 1; 10 0], [0; 1], 0.1; Np = 30), |u| <= 1, r = [1, 0]:
+    norm(unom - uprestab) < 1e-10 and cond(H) drops with the LQR feedback."""
+    F, G = om.zoh(np.array([[0.0, 1.0], [10.0, 0.0]]), np.array([[0.0], [1.0]]), 0.1)
+    o = om.MPC(F, G, Ts=0.1, Np=30)
+    o.set_input_bounds(umin=[-1.0], umax=[1.0])
+    unom, qp_nom = _oracle_control(o, np.zeros(2), r=[1.0, 0.0])
+    o.set_prestabilizing_feedback()
+    upre, qp_pre = _oracle_control(o, np.zeros(2), r=[1.0, 0.0])
+    assert np.linalg.norm(unom - upre) < 1e-10
+    assert np.linalg.cond(qp_pre.H) < np.linalg.cond(qp_nom.H)
+
+
+def test_reference_case_reference_preview_dimensions_and_effect():
+    """test/runtests.jl:225-274: Np = 5, Nc = 3, Q = [1, 1], R = 0.1, Rr = 0.1, |u| <= 20: parameter
+    dimensions (2, 10, 0, 1), a held single reference equals the plain controller, a changing
+    preview moves the control by more than 1e-1."""
+    F, G = om.zoh(np.array([[0.0, 1.0], [10.0, 0.0]]), np.array([[0.0], [1.0]]), 0.1)
+    o = om.MPC(F, G, C=np.eye(2), Ts=0.1, Np=5, Nc=3)
+    o.set_input_bounds(umin=[-20.0], umax=[20.0])
+    o.set_objective(Q=[1.0, 1.0], R=[0.1], Rr=[0.1])
+    x = np.array([1.0, 0.0])
+    u_std, _ = _oracle_control(o, x, r=[0.0, 0.0])
+    o.reference_preview = True
+    assert o.parameter_dims() == (2, 10, 0, 1)
+    u_single, _ = _oracle_control(o, x, r=[0.0, 0.0])
+    assert np.allclose(u_single, u_std, rtol=0, atol=1e-10)
+    r_dyn = np.array([[0.0, 1.0, 2.0, 1.0, 0.0], [0.0, 0.0, 0.5, 1.0, 0.5]])
+    u_prev, _ = _oracle_control(o, x, r=r_dyn)
+    assert np.linalg.norm(u_std - u_prev) > 1e-1
+
+
+def _dist_preview_case():
+    """test/runtests.jl:349-356: double integrator with an input disturbance."""
+    o = om.MPC(np.array([[1.0, 1.0], [0.0, 1.0]]), np.array([[0.0], [1.0]]), Gd=np.array([[0.0], [1.0]]),
+               C=np.array([[1.0, 0.0]]), Np=5, Nc=5)
+    o.set_input_bounds(umin=[-0.5], umax=[0.5])
+    o.set_objective(Q=[10.0], R=[0.1])
+    return o
+
+
+def test_reference_case_disturbance_preview_dimensions_and_effect():
+    """test/runtests.jl:357-376: dims (2, 1, 5, 0); knowing that d steps to 1 lowers the first control
+    by more than 1e-2; a vector d is held over the horizon."""
+    o = _dist_preview_case()
+    u_std, _ = _oracle_control(o, np.zeros(2), d=[0.0])
+    o.disturbance_preview = True
+    assert o.parameter_dims() == (2, 1, 5, 0)
+    u_single, _ = _oracle_control(o, np.zeros(2), d=[0.0])
+    assert np.allclose(u_single, u_std, atol=1e-12)
+    u_prev, _ = _oracle_control(o, np.zeros(2), d=np.array([[0.0, 1.0, 1.0, 1.0, 1.0]]))
+    assert u_prev[0] < u_single[0] - 1e-2
+    with pytest.raises(ValueError):            # runtests.jl:419-420: wrong lengths are errors
+        o.form_parameter(np.zeros(2), None, [0.0, 1.0], None)
+    with pytest.raises(ValueError):
+        o.form_parameter(np.zeros(2), None, np.ones((2, 2)), None)
