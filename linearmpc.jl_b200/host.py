@@ -920,6 +920,9 @@ class MPC:
         from . import explicit as ex
         q = self.condense()
         sol = ex.build_explicit(q, self._g(), lo, hi, self.nu, n_samples=n_samples, seed=seed, **kw)
+        if self.K is not None and np.any(self.K != 0):
+            # the laws give v; u = v - K x (build_tree! correction, src/explicit.jl:65-71)
+            sol["feedbacks"][:, :, :self.nx] -= self.K
         empc = GpuExplicitMPC(sol["halfplanes"], sol["feedbacks"], sol["hp_list"], sol["jump_list"],
                               clipping=clipping, dims=q["dims"], device=device)
         return empc, sol

@@ -215,3 +215,48 @@ def test_gpu_explicit_closed_loop_matches_oracle(lmpc):
     gi = lmpc.setup_gpu(mpqp.mpc2mpqp(mpc), nu=1, dims=mpc.parameter_dims())
     imp = gi.simulate(mpc.F, mpc.G, X0, r=R, N=T, want_traj=True)
     assert np.max(np.abs(imp["Utraj"] - out["Utraj"])) < 1e-10
+
+
+@pytest.mark.gpu
+def test_product_explicit_with_feedback_and_with_disturbance_preview(lmpc):
+    """(i) prestabilised controller: the explicit laws give v and are corrected by -K x
+    (build_tree!, src/explicit.jl:65-71); (ii) disturbance preview: theta carries d_0..d_{Np-1}
+    and `control_explicit ~ control_preview` (test/runtests.jl:378-380, atol 1e-10)."""
+    from lmpc_b200 import explicit as pex
+    # (i) double integrator, regulation, LQR prestabilisation
+    m = lmpc.MPC(np.array([[1.0, 1.0], [0.0, 1.0]]), np.array([[0.5], [1.0]]), Np=5, Nc=5)
+    m.reference_tracking = False
+    m.set_objective(Q=[1.0, 1.0], R=[0.5])
+    m.set_bounds(umin=[-1.0], umax=[1.0])
+    plain = m.setup()
+    m.set_prestabilizing_feedback()
+    g = m.setup()
+    lo, hi = np.array([-3.0, -1.5]), np.array([3.0, 1.5])
+    empc, sol = m.explicit(lo, hi, n_samples=100_000, seed=2)
+    assert len(sol["regions"]) > 3
+    Th = mpqp.sample_theta(lo, hi, 50_000, seed=9)
+    U, _ = empc.evaluate(Th)
+    imp = g.solve(Th)
+    ok = imp["exitflag"] == 1
+    assert ok.mean() > 0.5 and np.max(np.abs(U[:, ok] - np.asarray(imp["U"])[:, ok])) < 1e-9
+    base = plain.solve(Th)
+    both = ok & (base["exitflag"] == 1)
+    assert np.max(np.abs(U[:, both] - np.asarray(base["U"])[:, both])) < 1e-8   # same control as without K
+    # (ii) the reference's disturbance-preview case, horizon cut to 3 (the LP-certified tree over the
+    # 8-dimensional parameter of Np = 5 takes minutes of host time)
+    m = lmpc.MPC(np.array([[1.0, 1.0], [0.0, 1.0]]), np.array([[0.0], [1.0]]), Gd=np.array([[0.0], [1.0]]),
+                 C=np.array([[1.0, 0.0]]), Np=3, Nc=3)
+    m.set_bounds(umin=[-0.5], umax=[0.5])
+    m.set_objective(Q=[10.0], R=[0.1])
+    m.disturbance_preview = True
+    g = m.setup()
+    assert g.dims == (2, 1, 3, 0)
+    hi = np.concatenate([[0.5, 0.25], [0.2], np.ones(3)])
+    empc, sol = m.explicit(-hi, hi, n_samples=50_000, seed=3)
+    u_imp = m.compute_control(np.zeros(2), d=np.array([[0.0, 1.0, 1.0]]))
+    u_exp = empc.compute_control(np.zeros(2), d=np.array([0.0, 1.0, 1.0]))
+    assert abs(u_imp[0] - u_exp[0]) < 1e-10
+    rep = pex.verify(empc, g, -hi, hi, n=50_000)
+    # the implicit solve leaves rows violated by less than primal_tol = 1e-6 inactive, the explicit law is
+    # exact: next to region boundaries the two differ by that band, nowhere by more
+    assert rep["max_err"] < 2e-6 and rep["frac_within_tol"] > 0.999
