@@ -317,8 +317,7 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
   int32_t disturbance_preview;
   /* prestabilising feedback u = v - K x (set_prestabilizing_feedback!, src/setup.jl:186-199): nu x nx,
    * NULL = 0.  The QP is then over v, the control bounds become general rows (ms = 0), and the same K
-   * must be given to lmpc_gpu_create for the output map u = z[1:nu] - K x (src/utils.jl:46-50).
-   * Refused together with move blocking. */
+   * must be given to lmpc_gpu_create for the output map u = z[1:nu] - K x (src/utils.jl:46-50). */
   const double *K;
 } lmpc_model;
 

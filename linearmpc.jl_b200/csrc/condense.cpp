@@ -3,7 +3,7 @@
 // lmpc_gpu_create consumes, so that non-Julia callers can build a controller.
 //
 // What it follows in the reference (subset: no offsets, binaries or generalized parameters; previews
-// of r / d without reference condensation; prestabilising feedback not together with move blocking):
+// of r / d without reference condensation):
 //   extended system / weights    /root/reference/src/mpc2mpqp.jl:649-731
 //   state predictor              /root/reference/src/mpc2mpqp.jl:20-46
 //   disturbance predictor        /root/reference/src/mpc2mpqp.jl:48-68
@@ -108,8 +108,6 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   const bool hasK = any_nonzero(K);
   const Mat Rorig = R;
   const bool kr = hasK && any_nonzero(Rorig);   // u'Ru then needs the output K x (mpc2mpqp.jl:679-681, 718-724)
-  if (hasK && md->move_blocks && md->n_move_blocks)
-    return cfail(LMPC_E_UNSUPPORTED, "move blocking together with a prestabilising feedback is not supported");
   // parameter layout (mpc2mpqp.jl:147-164)
   // with a preview the Np future values of r / d are parameters, not extended states
   const bool rp = md->reference_preview && md->reference_tracking;
@@ -356,6 +354,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     int nnew = 0;
     for (auto &v : mb) nnew += (int)v.size();
     Mat T(n, nnew);
+    const int nbound = (md->umax || md->umin) ? n : 0;   // control-bound rows: simple, or the top of A with a feedback
     std::vector<int> keep, counter(nu);
     for (int iu = 0; iu < nu; ++iu) counter[iu] = iu;
     int new_id = 0;
@@ -368,7 +367,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
           if (row >= n) return cfail(LMPC_E_INVALID, "move blocking: blocks exceed the control horizon Nc");
           T(row, new_id) = 1.0;
         }
-        if (counter[iu] < ms) keep.push_back(counter[iu]);
+        if (counter[iu] < nbound) keep.push_back(counter[iu]);
         counter[iu] += nu * block;
         ++new_id;
       }
@@ -382,6 +381,13 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       ms = (int)keep.size();
       soft.assign(ms, 0); prio.assign(ms, 0);
       W = Mat(ms, nth);
+    }
+    if (hasK && nbound > 0) {   // mpc2mpqp.jl:854: with a feedback the bounds are rows of A; keep one per block
+      std::vector<int> rows = keep;
+      for (int i = nbound; i < (int)Arows.size(); ++i) rows.push_back(i);
+      std::vector<std::vector<double>> A2, W2; std::vector<double> u2, l2; std::vector<int> s2, p2;
+      for (int i : rows) { A2.push_back(Arows[i]); W2.push_back(Wrows[i]); u2.push_back(gbu[i]); l2.push_back(gbl[i]); s2.push_back(gsoft[i]); p2.push_back(gprio[i]); }
+      Arows.swap(A2); Wrows.swap(W2); gbu.swap(u2); gbl.swap(l2); gsoft.swap(s2); gprio.swap(p2);
     }
     for (auto &ar : Arows) {
       std::vector<double> r2(nnew, 0.0);

@@ -644,9 +644,11 @@ def apply_move_block(mpc, H, f, f_theta, A, bu, bl, W, soft, prio):
                 keep.append(counter[iu])
             counter[iu] += nu * block
             new_id += 1
-    ns = len(bu) - A.shape[0]
+    nb = nub * Nc                               # control-bound rows: simple, or the top of A with a feedback
     keep = np.array(keep, int) - 1
-    full = np.concatenate([keep, np.arange(ns, len(bu))]).astype(int)
+    full = np.concatenate([keep, np.arange(nb, len(bu))]).astype(int)
+    if np.any(mpc.K != 0) and nb:               # mpc2mpqp.jl:854: the bounds are rows of A then
+        A = A[np.concatenate([keep, np.arange(nb, A.shape[0])]).astype(int)]
     return (T.T @ H @ T, T.T @ f, T.T @ f_theta, A @ T, bu[full], bl[full], W[full], soft[full], prio[full])
 
 
@@ -665,8 +667,6 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
     else:
         bu, bl, W = np.zeros(0), np.zeros(0), np.zeros((0, nth))
         soft, prio = np.zeros(0, bool), np.zeros(0, int)
-    if np.any(mpc.K != 0) and getattr(mpc, "move_blocks", None):
-        raise ValueError("move blocking together with a prestabilising feedback is not supported")
     if mpc.constraints:
         Ag, bug, blg, Wg, sg, pg = general_constraints(mpc, Phi, Gam)
         A = np.vstack([A, Ag])

@@ -229,13 +229,42 @@ def test_cpp_condenser_prestabilised_matches_restatement(lmpc, name, rp, dp, pre
     assert np.array_equal(q["senses"], ref.senses)
 
 
-def test_cpp_condenser_refuses_feedback_with_move_blocking(lmpc):
-    m = lmpc.MPC(np.array([[1.0, 0.1], [0, 1.0]]), np.array([[0.0], [0.1]]), Np=6)
-    m.set_input_bounds([-1.0], [1.0])
-    m.move_block([2, 2, 2])
-    m.set_prestabilizing_feedback(np.array([[0.5, 0.5]]))
-    with pytest.raises(lmpc.LmpcError):
-        m.condense()
+def test_feedback_with_move_blocking_matches_rollout_and_cpp(lmpc):
+    """mpc2mpqp.jl:830-857 with K != 0 (line 854): the bound rows are rows of A and one per block is
+    kept.  Rollout of the unblocked plant with tied v against the blocked dense problem."""
+    from test_condense_cpu import mirror_of
+    K = np.array([[-0.8, -0.6, 2.0, 0.4]])
+    blk = om.invpend(Np=10, Nc=10)
+    blk.preprocess_mpqp = False
+    blk.set_prestabilizing_feedback(K)
+    om.move_block(blk, [[2, 3, 5]])
+    qb = om.mpc2mpqp(blk)
+    assert qb.n == 3 and blk.Nc == 6 and qb.A.shape[0] == 3 == len(qb.bu)
+    full = om.invpend(Np=10, Nc=10)
+    full.set_prestabilizing_feedback(K)
+    Tm = np.zeros((10, 3)); Tm[0:2, 0] = 1; Tm[2:5, 1] = 1; Tm[5:, 2] = 1
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        x0, r, up = rng.normal(size=4), rng.normal(size=2), rng.normal(size=1)
+        th = blk.form_parameter(x0, r, None, up)
+        Rp = np.repeat(r[:, None], 10, axis=1)
+        z1, z2 = rng.normal(size=3), rng.normal(size=3)
+        J1, g1 = _rollout(full, x0, Rp, np.zeros((0, 10)), up, (Tm @ z1)[:, None])
+        J2, _ = _rollout(full, x0, Rp, np.zeros((0, 10)), up, (Tm @ z2)[:, None])
+        q = lambda z: 0.5 * z @ qb.H @ z + (qb.f + qb.f_theta @ th) @ z
+        assert abs((J1 - J2) - 2 * (q(z1) - q(z2))) <= 1e-9 * max(1.0, abs(J1), abs(J2))
+        # kept bound rows: the applied control at the first step of every block (steps 0, 2, 5)
+        np.testing.assert_allclose(qb.A @ z1 - qb.W @ th, g1[[0, 2, 5]], rtol=1e-10, atol=1e-10)
+    m = mirror_of(lmpc, blk)
+    m.preprocess_mpqp = False
+    m.set_prestabilizing_feedback(K)
+    m.Nc = 10
+    m.move_block([2, 3, 5])
+    qc = m.condense()
+    for k in ("H", "f_theta", "A", "W"):
+        want = getattr(qb, k)
+        assert qc[k].shape == want.shape and np.max(np.abs(qc[k] - want)) <= 1e-11 * max(1.0, np.abs(want).max()), k
+    assert np.allclose(qc["bu"], qb.bu) and np.allclose(qc["bl"], qb.bl)
 
 
 # ---- the reference's own tests of these features, restated on the oracle -----------------------------
