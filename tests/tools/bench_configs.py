@@ -33,7 +33,7 @@ def timed(fn, reps=3, warm=1):
 
 def solve_cfg(name, scale, N, ncpu):
     mpc = util.controller(name); qp = mpqp.mpc2mpqp(mpc)
-    g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
+    g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight, K=mpc.K)
     lo, hi = util.theta_range(name, scale)
     Th = rand_theta(lo, hi, N)
     U = torch.empty((N, g.nu), dtype=torch.float64, device=dev); fl = torch.empty(N, dtype=torch.int32, device=dev)
@@ -60,6 +60,11 @@ def solve_cfg(name, scale, N, ncpu):
 if "invpend_scales" in which:
     for sc in (1.0, 0.25, 0.05):
         solve_cfg("invpend", sc, 10_000_000, 2_000_000)
+if "condensing_features" in which:
+    # controllers condensed with a prestabilising feedback (bounds become general rows) and with a
+    # 50-step reference preview (theta is 105 doubles: the solve streams 840 B per instance)
+    solve_cfg("invpend_prestab", 1.0, 10_000_000, 200_000)
+    solve_cfg("invpend_rpreview", 1.0, 4_000_000, 200_000)
 if "small_general" in which:
     # small problems with hard general rows / equalities: the general thread-per-QP kernel K1
     solve_cfg("dint_hard", 1.0, 10_000_000, 1_000_000)

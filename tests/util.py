@@ -33,6 +33,14 @@ def controller(name):
         return mpqp.double_integrator_terminal_eq(Np=6, Nc=6)
     if name == "genparam":
         return mpqp.generalized_parameter_example()
+    if name == "invpend_prestab":      # README pendulum with the LQR prestabilising feedback (setup.jl:196-199)
+        mpc = mpqp.invpend()
+        mpc.set_prestabilizing_feedback()
+        return mpc
+    if name == "invpend_rpreview":     # README pendulum with a 50-step reference preview (nth = 4 + 100 + 1)
+        mpc = mpqp.invpend()
+        mpc.reference_preview = True
+        return mpc
     if name == "simple":
         return mpqp.simple_md(1.0)
     if name == "simple_q1000":
@@ -41,8 +49,12 @@ def controller(name):
 
 
 def theta_range(name, scale=1.0):
-    if name == "invpend":
+    if name in ("invpend", "invpend_prestab"):
         return mpqp.invpend_range(scale)
+    if name == "invpend_rpreview":     # [x(4); r_1..r_50 (2 each); uprev]
+        lo, hi = mpqp.invpend_range(scale)
+        return (np.concatenate([lo[:4], np.tile(lo[4:6], 50), lo[6:]]),
+                np.concatenate([hi[:4], np.tile(hi[4:6], 50), hi[6:]]))
     if name.startswith("aircraft"):
         return mpqp.aircraft_range(scale)
     if name == "chain":
