@@ -35,7 +35,7 @@ elif which == "bst":
     Th = rand_theta(z["lo"], z["hi"], N); U = torch.empty((N, 1), dtype=torch.float64, device=dev)
     for _ in range(4): ge.evaluate_async(Th, U, N=N)
 else:
-    name, scale, N = {"box": ("invpend", 1.0, 10_000_000), "warp": ("aircraft", 0.25, 300_000), "cta": ("chain", 0.25, 3000), "big": ("aircraft_ksall", 0.25, 100_000), "thread": ("dint_eq_small", 1.0, 10_000_000), "cta1": ("chain", 1.0, 1500)}[which]
+    name, scale, N = {"box": ("invpend", 1.0, 10_000_000), "warp": ("aircraft", 0.25, 300_000), "cta": ("chain", 0.25, 3000), "big": ("aircraft_ksall", 0.25, 100_000), "thread": ("dint_eq_small", 1.0, 10_000_000), "cta1": ("chain", 1.0, 1500), "rpreview": ("invpend_rpreview", 1.0, 4_000_000), "prestab": ("invpend_prestab", 1.0, 10_000_000)}[which]
     mpc = util.controller(name); qp = mpqp.mpc2mpqp(mpc)
     g = lmpc_b200.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), soft_weight=mpc.soft_weight)
     Th = rand_theta(*util.theta_range(name, scale), N)
