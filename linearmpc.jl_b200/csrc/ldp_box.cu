@@ -227,11 +227,13 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const BC &
   cx.iter = K + 2;
 }
 
-template <int N, int NU, int MINB>
+template <int N, int NU, int MINB, bool CP = false>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
                const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-               SolveOut out, int use_tiles) {
+               SolveOut out, int flags) {
+  const bool use_tiles = flags & 1;
+  constexpr bool use_cp = CP;   // compile-time: with both loops in one kernel the gain on short theta is lost
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
@@ -240,12 +242,23 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
   constexpr int NP = BoxPad<N>::NP;
   double *Mp = smem + ((lay.total + 1) & ~1);
   for (int i = threadIdx.x; i < N * NP; i += KB_BLOCK) Mp[i] = (i % NP < N) ? cv.M[(i / NP) * N + i % NP] : 0.0;
+  // [Dth; Uth] transposed and padded to NQ doubles per theta entry: the constants of one entry of
+  // theta arrive in NQ / 2 128-bit broadcast loads instead of N + NU 64-bit ones (with a preview
+  // theta has ~100 entries and this mat-vec runs next to the theta stream: the LSU was the busiest unit).
+  // Only when the copy does not cost a resident CTA (the CP instantiation, chosen at launch).
+  constexpr int NQ = (N + NU + 1) & ~1;
+  double *Cp = Mp + N * NP;
+  const int ncp = use_cp ? lay.nth * NQ : 0;
+  for (int i = threadIdx.x; i < ncp; i += KB_BLOCK) {
+    const int tt = i / NQ, c = i % NQ;
+    Cp[i] = c < N ? cv.Dth[c * lay.nth + tt] : (c < N + NU ? cv.Uth[(c - N) * lay.nth + tt] : 0.0);
+  }
   // theta tiles: when Theta is one contiguous nth x N block, each warp streams its next 32
   // parameters into its own slot with one TMA bulk copy while it is still iterating on the
   // current ones (the direct loads at the top of a solve were 15 % of the stall samples)
   __shared__ __align__(8) uint64_t tbar[KB_BLOCK / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *tile = Mp + N * NP + (size_t)warp * 32 * lay.nth;
+  double *tile = Cp + ncp + (size_t)warp * 32 * lay.nth;
   const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
   uint32_t tphase = 0;
   if (use_tiles) {
@@ -271,11 +284,22 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
       tile_wait(&tbar[warp], tphase);
       tphase ^= 1u;
       const double *src = tile + lane * nth;     // stride nth doubles: conflict-free for odd and even nth alike
+      if constexpr (!use_cp) {
+#pragma unroll KB_THU
+        for (int tt = 0; tt < nth; ++tt) {
+          const double tv = src[tt];
+          SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
+          SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
+        }
+      } else
 #pragma unroll KB_THU
       for (int tt = 0; tt < nth; ++tt) {
         const double tv = src[tt];
-        SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
-        SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
+        const double2 *c2 = reinterpret_cast<const double2 *>(Cp + tt * NQ);
+        double cc[NQ];
+        SFOR(h, 0, NQ / 2) const double2 v = c2[h]; cc[2 * h] = v.x; cc[2 * h + 1] = v.y; SEND
+        SFOR(j, 0, N) sh[j] = fma(cc[j], tv, sh[j]); SEND
+        SFOR(i, 0, NU) sho[i] = fma(cc[N + i], tv, sho[i]); SEND
       }
       __syncwarp();                              // everybody has read the slot: refill it
       if (lane == 0 && qt + qstride + 32 <= Ninst)
@@ -444,12 +468,24 @@ template <int N, int NU, int MINB = KB_MINB>
 int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
                const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
-  auto kern = ldp_box_kernel<N, NU, MINB>;
+  auto kern = ldp_box_kernel<N, NU, MINB, false>;
+  auto kern_cp = ldp_box_kernel<N, NU, MINB, true>;
   size_t smem = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
   // one 32-theta slot per warp when Theta is a single contiguous, 16-byte aligned block
   const int use_tiles = th.nseg == 1 && th.len[0] == lay.nth && th.stride[0] == lay.nth &&
                         (reinterpret_cast<uintptr_t>(th.ptr[0]) & 15u) == 0 && Ninst >= 32;
   if (use_tiles) smem += (size_t)KB_BLOCK * lay.nth * sizeof(double);
+  // transposed constants for the theta mat-vec: taken only when they do not cost a resident CTA
+  const size_t smem_cp = smem + (size_t)lay.nth * ((N + NU + 1) & ~1) * sizeof(double);
+  int use_cp = 0;
+  if (use_tiles && smem_cp <= 227u * 1024u &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+      cudaFuncSetAttribute(kern_cp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cp) == cudaSuccess) {
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kern, KB_BLOCK, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern_cp, KB_BLOCK, smem_cp);
+    if (b >= a && b >= 1) { use_cp = 1; smem = smem_cp; kern = kern_cp; }
+  }
   BoxConst<N, NU> bc;
   for (int i = 0; i < N * N; ++i) bc.M[i] = hblk[lay.oM + i];
   for (int i = 0; i < N; ++i) { bc.du[i] = hblk[lay.odu + i]; bc.dl[i] = hblk[lay.odl + i]; }
