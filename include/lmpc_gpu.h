@@ -332,6 +332,20 @@ int lmpc_gpu_mpqp_get(const lmpc_mpqp *q, double *H, double *f, double *f_theta,
 int lmpc_gpu_mpqp_free(lmpc_mpqp *q);
 const char *lmpc_gpu_condense_error(void);
 
+/* Struct layouts as THIS build of the library sees them, so that a binding written in another
+ * language (the Julia structs in linearmpc.jl_b200/julia/LinearMPCGPU.jl, the ctypes mirrors in
+ * host.py) can be checked field by field instead of trusted: for each struct, in the order
+ * lmpc_problem, lmpc_settings, lmpc_sim_ext, lmpc_constraint, lmpc_model the record
+ *   { struct id (LMPC_ABI_*), sizeof, number of fields, offsetof(field 0), offsetof(field 1), ... }
+ * with the fields in declaration order.  Writes at most `cap` int32 values to `out` (nullable)
+ * and returns the number of values the full description has.  Host only, no GPU needed. */
+#define LMPC_ABI_PROBLEM 1
+#define LMPC_ABI_SETTINGS 2
+#define LMPC_ABI_SIM_EXT 3
+#define LMPC_ABI_CONSTRAINT 4
+#define LMPC_ABI_MODEL 5
+int lmpc_gpu_abi_layout(int32_t *out, int32_t cap);
+
 /* Measurement helpers used by bench.py (not part of the reference's interface):
  * sustained FP64 FMA throughput of the device in TFLOP/s, and the stream of a handle. */
 int lmpc_gpu_fp64_peak(int device, double *tflops);

@@ -174,7 +174,31 @@ struct LmpcSimExt
     Vtraj::Ptr{Float64}
     ny::Int32
     Xhat_end::Ptr{Float64}
+    rstride::Int32; dstride::Int32     # preview windows: step t reads its nr / nd entries at t * stride (0 = nr / nd)
 end
+
+# Layout self-check (lmpc_gpu_abi_layout, include/lmpc_gpu.h): the two structs above are hand-written
+# mirrors, so compare sizeof / fieldoffset with what the loaded library was compiled with and refuse
+# to run on a mismatch instead of letting C read past a Julia object.
+function check_abi()
+    n = ccall((:lmpc_gpu_abi_layout, liblmpcgpu), Cint, (Ptr{Int32}, Int32), C_NULL, 0)
+    v = Vector{Int32}(undef, n)
+    ccall((:lmpc_gpu_abi_layout, liblmpcgpu), Cint, (Ptr{Int32}, Int32), v, n)
+    mirrors = Dict(1 => LmpcProblem, 3 => LmpcSimExt)
+    i = 1
+    while i <= n
+        id, sz, nf = v[i], v[i+1], v[i+2]
+        offs = v[i+3:i+2+nf]
+        if haskey(mirrors, id)
+            T = mirrors[id]
+            (sizeof(T) == sz && fieldcount(T) == nf && all(fieldoffset(T, k) == offs[k] for k in 1:nf)) ||
+                error("LinearMPCGPU: struct $(T) does not match the loaded liblmpcgpu (size $(sizeof(T)) vs $sz)")
+        end
+        i += 3 + nf
+    end
+    return true
+end
+__init__() = check_abi()
 
 """
     simulate_observed(g, X0; N, r, d, plant=(F,G,Gd), noise) -> (Xend, Xhat_end, Ulast, exitflag)
@@ -192,7 +216,17 @@ function simulate_observed(g::GpuMPC, X0::Matrix{Float64}; N::Integer=100, r=not
     hold(v, k) = (k == 0 || isnothing(v)) ? nothing :
         (V = v isa AbstractMatrix ? Matrix{Float64}(v) : reshape(Vector{Float64}(v), k, 1);
          hcat(V[:, 1:min(N, size(V, 2))], repeat(V[:, end], 1, max(0, N - size(V, 2)))))
-    Rt, Dt = hold(r, nr), hold(d, nd)
+    # Controllers condensed with reference_preview / disturbance_preview read a WINDOW of Np columns per
+    # step (get_preview, src/simulation.jl:102-104,128-134): flat trajectory of N + Np - 1 columns with the
+    # column N held (rs[:, min(k+i, N)]), window start advancing by one column (= stride) per step.
+    Np = g.mpc.Np
+    rprev = g.mpc.settings.reference_preview && nr > 0
+    dprev = g.mpc.settings.disturbance_preview && nd > 0
+    nyr, ndb = rprev ? nr ÷ Np : nr, dprev ? nd ÷ Np : nd
+    window(V) = isnothing(V) ? nothing : hcat(V, repeat(V[:, end], 1, Np - 1))
+    Rt, Dt = hold(r, nyr), hold(d, ndb)
+    rprev && (Rt = window(Rt)); dprev && (Dt = window(Dt))
+    rstride, dstride = rprev ? nyr : 0, dprev ? ndb : 0
     ny = size(kf.C, 1)
     Vt = hold(noise, ny)
     Ft, Gt, Gdt = isnothing(plant) ? (nothing, nothing, nothing) : Matrix{Float64}.(plant)
@@ -201,7 +235,7 @@ function simulate_observed(g::GpuMPC, X0::Matrix{Float64}; N::Integer=100, r=not
     Cm, Ddm, Km = Matrix{Float64}(kf.C), Matrix{Float64}(kf.Dd), Matrix{Float64}(kf.K)
     GC.@preserve Rt Dt Vt Ft Gt Gdt Cm Ddm Km Xhat begin
         ext = Ref(LmpcSimExt(p(Rt), p(Dt), p(Ft), p(Gt), p(Gdt), pointer(Cm), nd == 0 ? C_NULL : pointer(Ddm),
-                             pointer(Km), p(Vt), ny, pointer(Xhat)))
+                             pointer(Km), p(Vt), ny, pointer(Xhat), rstride, dstride))
         check(ccall((:lmpc_gpu_simulate_batch_ex, liblmpcgpu), Cint,
                     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{LmpcSimExt},

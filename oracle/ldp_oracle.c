@@ -19,6 +19,7 @@ typedef struct {
   int8_t *side;   /* +1 upper, -1 lower */
   double *lam, *lams, *L, *D, *Dinv, *z, *y, *u, *dup, *dlo;
   uint8_t *inws;  /* m flags */
+  int32_t *tail_row; int8_t *tail_side; double *tail_lam;   /* rebuild scratch */
 } work_t;
 
 static work_t *work_new(const orc_problem *p) {
@@ -37,11 +38,15 @@ static work_t *work_new(const orc_problem *p) {
   w->dup = (double *)calloc(m, sizeof(double));
   w->dlo = (double *)calloc(m, sizeof(double));
   w->inws = (uint8_t *)calloc(m, 1);
+  w->tail_row = (int32_t *)calloc(cap, sizeof(int32_t));
+  w->tail_side = (int8_t *)calloc(cap, 1);
+  w->tail_lam = (double *)calloc(cap, sizeof(double));
   return w;
 }
 static void work_free(work_t *w) {
   free(w->ws); free(w->side); free(w->lam); free(w->lams); free(w->L); free(w->D); free(w->Dinv);
-  free(w->z); free(w->y); free(w->u); free(w->dup); free(w->dlo); free(w->inws); free(w);
+  free(w->z); free(w->y); free(w->u); free(w->dup); free(w->dlo); free(w->inws);
+  free(w->tail_row); free(w->tail_side); free(w->tail_lam); free(w);
 }
 static void work_reset(const orc_problem *p, work_t *w) {
   w->k = 0; w->sing = 0;
@@ -146,16 +151,66 @@ static void ldl_remove(const orc_problem *p, work_t *w, int r, double *fl) {
   if (fl) *fl += 3.0 * (k - r) * (k - r) + 2.0 * k;
 }
 
-static void remove_pos(const orc_problem *p, work_t *w, int r, double *fl) {
+/* Repair of the factorisation for problems with SOFT rows (DAQP's "reorder and refactorise"
+ * step, restated; libdaqp itself is not in /root/reference -- see ldp_oracle.h).
+ *
+ * A soft row contributes only rho (1e-6) to its own pivot, so a HARD row factorised after soft rows
+ * it depends on gets a pivot of order rho |c_soft|^2 (1e-10 and below on AFTI-16 with output bounds
+ * on every step).  Such a pivot drowns in the rounding of 1 - sum l^2 D: the zero_tol test fires at
+ * random and a problem that is feasible by construction ends as INFEASIBLE.  The repair rebuilds
+ * L, D from scratch with the hard rows first (their pivots are then Schur complements among hard
+ * rows only) and the soft rows last (pivots >= rho), multipliers kept.  A hard row that is dependent
+ * on the hard block itself is genuinely singular: it goes to the very end with a zero pivot, so
+ * that nothing is factorised after it.  Two such rows cannot both be handled: ORC_CYCLE. */
+static int rebuild(const orc_problem *p, work_t *w, double *fl) {
+  const int k = w->k;
+  int32_t *tr = w->tail_row; int8_t *ts = w->tail_side; double *tl = w->tail_lam;
+  for (int i = 0; i < k; ++i) { tr[i] = w->ws[i]; ts[i] = w->side[i]; tl[i] = w->lam[i]; }
+  w->k = 0; w->sing = 0;
+  int defer = -1;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < k; ++i) {
+      if (((p->sense[tr[i]] & ORC_SOFT) != 0) != pass) continue;
+      ldl_add(p, w, tr[i], ts[i], fl);
+      w->lam[w->k - 1] = tl[i];
+      if (w->sing) {
+        if (pass == 1 || defer >= 0) return ORC_CYCLE;
+        defer = i; w->k -= 1; w->sing = 0;
+      }
+    }
+  if (defer >= 0) {
+    ldl_add(p, w, tr[defer], ts[defer], fl);
+    w->lam[w->k - 1] = tl[defer];
+    w->sing = 1; w->D[w->k - 1] = 0.0; w->Dinv[w->k - 1] = 0.0;
+  }
+  return 0;
+}
+
+/* the working set holds a soft row: a pivot below zero_tol is then suspect (see rebuild) */
+static int has_soft(const orc_problem *p, const work_t *w) {
+  for (int i = 0; i < w->k; ++i) if (p->sense[w->ws[i]] & ORC_SOFT) return 1;
+  return 0;
+}
+
+/* append row j; returns 0 or an exit flag */
+static int add_row(const orc_problem *p, work_t *w, int j, int s, double *fl) {
+  ldl_add(p, w, j, s, fl);
+  if (w->sing && has_soft(p, w)) return rebuild(p, w, fl);
+  return 0;
+}
+
+static int remove_pos(const orc_problem *p, work_t *w, int r, double *fl) {
   w->inws[w->ws[r]] = 0;
   ldl_remove(p, w, r, fl);
+  if (w->sing && has_soft(p, w)) return rebuild(p, w, fl);
+  return 0;
 }
 
 /* the dual active-set loop */
 static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *soft_slack_out,
                     double *fl) {
   const int n = p->n, m = p->m;
-  int flag = ORC_ITERLIMIT, iter, cycle = 0;
+  int flag = ORC_ITERLIMIT, iter, cycle = 0, repaired = 0, rc;
   double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
   for (iter = 1; iter < p->iter_limit; ++iter) {
     int k = w->k, nblock = 0;
@@ -218,10 +273,16 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
         if (add < 0) { flag = soft_slack > p->primal_tol ? ORC_SOFT_OPTIMAL : ORC_OPTIMAL; break; }
         /* cycle guard, evaluated where the dual objective is fresh: a new dual-feasible iterate
          * that still violates a row must have raised fval by progress_tol, or the counter runs */
+        int rebuilt = 0;
         if (fval - p->progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-        else if (cycle++ > p->cycle_tol) { flag = ORC_CYCLE; break; }
+        else if (cycle++ > p->cycle_tol) {
+          /* second chance for problems with soft rows: refactorise once, restart the count */
+          if (repaired || !has_soft(p, w)) { flag = ORC_CYCLE; break; }
+          repaired = 1; rebuilt = 1; best_fval = -1.0; cycle = 0;
+        }
         for (int i = 0; i < k; ++i) w->lam[i] = w->lams[i];
-        ldl_add(p, w, add, addside, fl);
+        if (rebuilt && (rc = rebuild(p, w, fl)) != 0) { flag = rc; break; }
+        if ((rc = add_row(p, w, add, addside, fl)) != 0) { flag = rc; break; }
         continue;
       }
       /* 4. blocking: ratio test, step, remove */
@@ -235,7 +296,7 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
       if (!(alpha < INFINITY)) { flag = ORC_CYCLE; break; }  /* blocked but no finite ratio */
       for (int i = 0; i < k; ++i) w->lam[i] = fma(alpha, w->lams[i] - w->lam[i], w->lam[i]);
       if (fl) *fl += 3.0 * k;
-      remove_pos(p, w, rm, fl);
+      if ((rc = remove_pos(p, w, rm, fl)) != 0) { flag = rc; break; }
     } else {
       /* 5. singular: direction p = s [-L^-T l ; 1] on the first k-1 rows */
       int kk = k - 1;
@@ -259,7 +320,7 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
       if (rm < 0) { flag = ORC_INFEASIBLE; break; }
       for (int i = 0; i < k; ++i) w->lam[i] = fma(alpha, w->lams[i], w->lam[i]);
       if (fl) *fl += 3.0 * k;
-      remove_pos(p, w, rm, fl);
+      if ((rc = remove_pos(p, w, rm, fl)) != 0) { flag = rc; break; }
     }
   }
   *iters = iter;

@@ -115,3 +115,73 @@ def test_form_parameter_layout(lmpc):
     assert th.shape == (10, 3) and np.array_equal(th[4:6, 2], [1, 2]) and th.flags.f_contiguous
     with pytest.raises(ValueError):
         cls.form_parameter(np.zeros(3))
+
+
+# ---- struct layouts: the library's own sizeof / offsetof vs the Julia and ctypes mirrors ----------------
+_JL_TYPES = {"Int32": (4, 4), "Cint": (4, 4), "Int64": (8, 8), "Float64": (8, 8), "UInt64": (8, 8)}
+
+
+def _julia_struct_layout(name):
+    """Parse `struct name ... end` in LinearMPCGPU.jl and lay the fields out by the C rules Julia uses
+    for isbits structs (natural alignment, size rounded up to the largest alignment)."""
+    src = open(os.path.join(ROOT, "linearmpc.jl_b200", "julia", "LinearMPCGPU.jl")).read()
+    body = re.search(r"^struct\s+" + name + r"\b(.*?)^end", src, flags=re.S | re.M).group(1)
+    body = re.sub(r"#.*", "", body)
+    fields = re.findall(r"(\w+)::([\w{}]+)", body)
+    off, offs, amax = 0, [], 1
+    for _, ty in fields:
+        size, align = (8, 8) if ty.startswith("Ptr{") else _JL_TYPES[ty]
+        off = (off + align - 1) // align * align
+        offs.append(off)
+        off += size
+        amax = max(amax, align)
+    return [f for f, _ in fields], offs, (off + amax - 1) // amax * amax
+
+
+def _abi_layout(lmpc):
+    L = lmpc.lib()
+    L.lmpc_gpu_abi_layout.restype = C.c_int32
+    n = L.lmpc_gpu_abi_layout(None, 0)
+    buf = (C.c_int32 * n)()
+    assert L.lmpc_gpu_abi_layout(buf, n) == n
+    v, i, out = list(buf), 0, {}
+    while i < n:
+        sid, size, nf = v[i], v[i + 1], v[i + 2]
+        out[sid] = (size, v[i + 3:i + 3 + nf])
+        i += 3 + nf
+    return out
+
+
+def test_struct_layouts_match_the_julia_and_ctypes_mirrors(lmpc):
+    """include/lmpc_gpu.h structs as compiled (lmpc_gpu_abi_layout) == the hand-written Julia structs
+    (field count, offsets, size) == the ctypes mirrors of host.py.  Round 1 shipped a Julia LmpcSimExt
+    without the trailing rstride / dstride: C then read 8 bytes past the Julia object."""
+    lay = _abi_layout(lmpc)
+    assert sorted(lay) == [1, 2, 3, 4, 5]
+    for sid, jl in [(1, "LmpcProblem"), (3, "LmpcSimExt")]:
+        names, offs, size = _julia_struct_layout(jl)
+        assert (size, offs) == (lay[sid][0], lay[sid][1]), (jl, names, offs, size, lay[sid])
+    import sys
+    host = sys.modules[lmpc.__name__ + ".host"]
+    _Problem, _Settings, _SimExt, _Constraint, _Model = (host._Problem, host._Settings, host._SimExt,
+                                                          host._Constraint, host._Model)
+    for sid, T in [(1, _Problem), (2, _Settings), (3, _SimExt), (4, _Constraint), (5, _Model)]:
+        offs = [getattr(T, f[0]).offset for f in T._fields_]
+        assert (C.sizeof(T), offs) == (lay[sid][0], lay[sid][1]), T.__name__
+
+
+def test_julia_struct_field_names_follow_the_header():
+    """same field names, same order, as the C declarations (a renamed or reordered field is a bug even
+    when the sizes happen to agree)."""
+    hdr = open(os.path.join(ROOT, "include", "lmpc_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for cname, jl in [("lmpc_problem", "LmpcProblem"), ("lmpc_sim_ext", "LmpcSimExt")]:
+        body = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + r"\s*;", hdr).group(1)
+        cfields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(double|int32_t|int64_t|uint64_t)\s*", "", decl)
+            cfields += [x.strip().lstrip("*").strip() for x in decl.split(",")]
+        assert _julia_struct_layout(jl)[0] == cfields, (cname, cfields)
