@@ -73,6 +73,22 @@ struct Slot {
   int64_t pend_off = 0, pend_cnt = 0;   // results sitting in the pinned buffers, not yet handed out
 };
 
+// Error paths of the host pipelines return in the middle of the stage loop while other slots may still
+// have D2H copies into the CALLER's arrays in flight: wait for all of them before handing control back.
+struct SlotGuard {
+  Slot *slots;
+  bool armed = true;
+  explicit SlotGuard(Slot *s) : slots(s) {}
+  ~SlotGuard() {
+    if (!armed) return;
+    for (int i = 0; i < kSlots; ++i) {
+      if (slots[i].stream) cudaStreamSynchronize(slots[i].stream);
+      slots[i].pend_cnt = 0;
+    }
+    cudaGetLastError();
+  }
+};
+
 bool is_pageable(const void *p) {
   if (!p) return false;
   cudaPointerAttributes a;
@@ -405,6 +421,7 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
                                int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al,
                                bool warm = false) {
   std::lock_guard<std::mutex> lock(h->mu);
+  SlotGuard guard(h->slots);
   const LdpLayout &l = h->lay;
   const int words = (l.m + 63) / 64;
   bool stage = is_pageable(U) || is_pageable(flag);
@@ -477,6 +494,7 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
     int rc = drain_slot(h, h->slots[i], U, ustride, flag, iters, au, al);
     if (rc) return rc;
   }
+  guard.armed = false;
   return 0;
 }
 
@@ -607,6 +625,7 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
   if (N == 0) return 0;
   std::lock_guard<std::mutex> lock(h->mu);
   CUDA_OK(cudaSetDevice(h->device));
+  SlotGuard guard(h->slots);
   const int nu = l.nu, ny = observer ? ext->ny : 0;
   // everything the kernels read besides the per-trajectory inputs, row-major, in one device buffer
   std::vector<double> dynh;
@@ -692,6 +711,7 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
     if (iters) CUDA_OK(cudaMemcpyAsync(iters + off, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
   }
   for (int i = 0; i < kSlots; ++i) CUDA_OK(cudaStreamSynchronize(h->slots[i].stream));
+  guard.armed = false;
   return 0;
 }
 

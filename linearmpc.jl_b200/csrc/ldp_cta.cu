@@ -389,6 +389,66 @@ LMPC_DEVINL void bq_remove(const C &c, BigQp<T> &s, int r) {
   __syncwarp();
 }
 
+// Problems with SOFT rows only (oracle: rebuild; see ldp_warp.cu: wq_rebuild): refactorise from scratch
+// with the hard rows first, in their current order, and the soft rows last, multipliers kept.  A hard
+// row that is dependent on the hard block goes to the very end with a zero pivot; a second one:
+// returns EXIT_CYCLE.  Warp-local (in CTA mode warp 0 runs it alone, with its own forward sweeps).
+template <int T, class C>
+LMPC_DEVINL int bq_rebuild(const C &c, BigQp<T> &s) {
+  const int lane = c.lane, k = s.k;
+  int row0[T];
+  double lam0[T], dW0[T];
+  unsigned hm[T], sm[T];
+  TFOR(t) { row0[t] = s.row[t]; lam0[t] = s.lam[t]; dW0[t] = s.dW[t]; }
+  const unsigned low0 = s.low;
+  int nh = 0;
+  TFOR(t) {
+    const bool live = lane + 32 * t < k, sf = (s.soft >> t) & 1u;
+    hm[t] = __ballot_sync(FULL, live && !sf);
+    sm[t] = __ballot_sync(FULL, live && sf);
+    nh += __popc(hm[t]);
+  }
+  s.k = 0; s.sing = false;
+  int defer = -1;
+  for (int p = 0; p <= k; ++p) {
+    int src;
+    if (p < k) {
+      int rem = (p < nh) ? p : p - nh;
+      src = -1;
+      TFOR(t) {
+        const unsigned mk = (p < nh) ? hm[t] : sm[t];
+        const int cnt = __popc(mk);
+        if (src < 0) { if (rem < cnt) src = 32 * t + (int)__fns(mk, 0, rem + 1); else rem -= cnt; }
+      }
+    } else {
+      if (defer < 0) break;
+      src = defer;
+    }
+    const int j = bcast_pos_i<T>(row0, src);
+    int lowv[T];
+    TFOR(t) lowv[t] = (low0 >> t) & 1u;
+    const bool lo = bcast_pos_i<T>(lowv, src) != 0;
+    const double dv = bcast_pos<T>(dW0, src), lm = bcast_pos<T>(lam0, src);
+    bq_add<T>(c, s, j, lo, dv);
+    TFOR(t) if (lane + 32 * t == s.k - 1) s.lam[t] = lm;
+    if (p == k) {
+      TFOR(t) if (lane + 32 * t == s.k - 1) { s.D[t] = 0.0; s.Dinv[t] = 0.0; }
+      s.sing = true;
+    } else if (s.sing) {
+      if (p >= nh || defer >= 0) return EXIT_CYCLE;
+      defer = src; s.k -= 1; s.sing = false;
+    }
+  }
+  return 0;
+}
+template <int T, class C>
+LMPC_DEVINL bool bq_has_soft(const C &c, const BigQp<T> &s) {
+  if (c.lay->nsoft == 0) return false;
+  bool any = false;
+  TFOR(t) any |= (c.lane + 32 * t < s.k) && ((s.soft >> t) & 1u);
+  return __any_sync(FULL, any);
+}
+
 // lowest position holding the minimum of a[] (NaN-free), or -1 when all +inf
 template <int T, class C>
 LMPC_DEVINL int argmin_first(const C &c, const double (&a)[T], double &amin) {
@@ -408,7 +468,8 @@ LMPC_DEVINL int bq_loop(const C &c, BigQp<T> &s, const double (&sh)[2 * T], doub
   const LdpLayout &lay = *c.lay;
   const LdpSettings &st = *c.st;
   const int lane = c.lane, n = lay.n, m = lay.m, mp = lay.mp;
-  int flag = EXIT_ITERLIMIT, iter, cycle = 0;
+  int flag = EXIT_ITERLIMIT, iter, cycle = 0, rc;
+  bool repaired = false;
   double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
   for (iter = 1; iter < st.iter_limit; ++iter) {
     const int k = s.k;
@@ -484,14 +545,21 @@ LMPC_DEVINL int bq_loop(const C &c, BigQp<T> &s, const double (&sh)[2 * T], doub
         const int add = bfly_min_i((best == vmin && bestj < (1 << 30)) ? bestj : (1 << 30));
         if (add == (1 << 30)) { flag = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL; break; }
         // cycle guard where the dual objective is fresh (see oracle/ldp_oracle.c)
+        bool rebuilt = false;
         if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-        else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+        else if (cycle++ > st.cycle_tol) {
+          // second chance for problems with soft rows: refactorise once, restart the count
+          if (repaired || !bq_has_soft<T>(c, s)) { flag = EXIT_CYCLE; break; }
+          repaired = true; rebuilt = true; best_fval = -1.0; cycle = 0;
+        }
         if (k >= lay.cap || k >= 32 * T) { flag = EXIT_CAPACITY; break; }
         const int src = add & 31;
         const bool addlow = __shfl_sync(FULL, (int)(bestj == add && bestlow), src);
         const double addd = shfl_d(bestd, src);
         TFOR(t) if (lane + 32 * t < k) s.lam[t] = s.lams[t];
+        if (rebuilt && (rc = bq_rebuild<T>(c, s)) != 0) { flag = rc; break; }
         bq_add<T>(c, s, add, addlow, addd);
+        if (s.sing && bq_has_soft<T>(c, s) && (rc = bq_rebuild<T>(c, s)) != 0) { flag = rc; break; }
         continue;
       }
       // 4. blocking
@@ -501,6 +569,7 @@ LMPC_DEVINL int bq_loop(const C &c, BigQp<T> &s, const double (&sh)[2 * T], doub
       if (rm < 0) { flag = EXIT_CYCLE; break; }
       TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, s.lams[t] - s.lam[t], s.lam[t]);
       bq_remove<T>(c, s, rm);
+      if (s.sing && bq_has_soft<T>(c, s) && (rc = bq_rebuild<T>(c, s)) != 0) { flag = rc; break; }
     } else {
       // 5. singular direction
       const int kk = k - 1;
@@ -527,6 +596,7 @@ LMPC_DEVINL int bq_loop(const C &c, BigQp<T> &s, const double (&sh)[2 * T], doub
       if (rm < 0) { flag = EXIT_INFEASIBLE; break; }
       TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, p[t], s.lam[t]);
       bq_remove<T>(c, s, rm);
+      if (s.sing && bq_has_soft<T>(c, s) && (rc = bq_rebuild<T>(c, s)) != 0) { flag = rc; break; }
     }
   }
   iters = iter;
@@ -929,6 +999,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     if (tid == 0) { cs.ctl[1] = 0; cs.ctl[3] = 0; }
     __syncthreads();
     int flag = EXIT_ITERLIMIT, iter = 0, cycle = 0;
+    bool repaired = false;
     double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
     if (warp == 0) {
       bq_reset<T>(s);
@@ -1067,8 +1138,13 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
             const int add = bfly_min_i((v == vmin && jl < (1 << 30)) ? jl : (1 << 30));
             if (add == (1 << 30)) done = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL;
             else {
+              bool rebuilt = false;
               if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-              else if (cycle++ > st.cycle_tol) done = EXIT_CYCLE;
+              else if (cycle++ > st.cycle_tol) {
+                // second chance for problems with soft rows: refactorise once, restart the count
+                if (repaired || !bq_has_soft<T>(c, s)) done = EXIT_CYCLE;
+                else { repaired = true; rebuilt = true; best_fval = -1.0; cycle = 0; }
+              }
               if (!done && (k >= cap || k >= 32 * T)) done = EXIT_CAPACITY;
               if (!done) {
                 const unsigned own = __ballot_sync(FULL, lane < 8 && jl == add && v == vmin);
@@ -1076,11 +1152,14 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
                 const bool addlow = __shfl_sync(FULL, (lane < 8) ? cs.red_low[lane] : 0, src) != 0;
                 const double addd = shfl_d((lane < 8) ? cs.red_d[lane] : 0.0, src);
                 TFOR(t) if (lane + 32 * t < k) s.lam[t] = s.lams[t];
-                // right-hand side of the add's forward sweep: the Gram column of the new row
-                const double *g = c.G + (size_t)add * m;
-                TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = g[s.row[t]]; }
-                pend_add = add; pend_low = addlow; pend_d = addd;
-                if (lane == 0) cs.ctl[3] = 1;
+                if (rebuilt) done = bq_rebuild<T>(c, s);
+                if (!done) {
+                  // right-hand side of the add's forward sweep: the Gram column of the new row
+                  const double *g = c.G + (size_t)add * m;
+                  TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = g[s.row[t]]; }
+                  pend_add = add; pend_low = addlow; pend_d = addd;
+                  if (lane == 0) cs.ctl[3] = 1;
+                }
               }
             }
           }
@@ -1092,6 +1171,10 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           coop_sweep_fwd<T>(c, c.lamw, k);
           if (warp == 0) {
             bq_add<T>(c, s, pend_add, pend_low, pend_d, c.lamw);
+            if (s.sing && bq_has_soft<T>(c, s)) {
+              const int rc = bq_rebuild<T>(c, s);
+              if (rc != 0 && lane == 0) cs.ctl[1] = rc;
+            }
             if (lane == 0) cs.ctl[3] = 0;
           }
         }
@@ -1106,6 +1189,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           else {
             TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, s.lams[t] - s.lam[t], s.lam[t]);
             bq_remove<T>(c, s, rm);
+            if (s.sing && bq_has_soft<T>(c, s)) done = bq_rebuild<T>(c, s);
           }
         } else {
           const int kk = k - 1;
@@ -1133,6 +1217,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           else {
             TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, p[t], s.lam[t]);
             bq_remove<T>(c, s, rm);
+            if (s.sing && bq_has_soft<T>(c, s)) done = bq_rebuild<T>(c, s);
           }
         }
         if (lane == 0) cs.ctl[1] = done;

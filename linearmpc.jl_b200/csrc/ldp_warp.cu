@@ -78,6 +78,7 @@ struct WarpQp {
   // warp-uniform
   int k;
   bool sing;
+  int rc;                     // exit flag raised by wq_rebuild (0: none)
   unsigned long long inws;    // rows in the working set
 };
 
@@ -95,7 +96,7 @@ struct WarpCtx {
 LMPC_DEVINL void wq_reset(WarpQp &s) {
   s.D = 1.0; s.Dinv = 1.0; s.lam = 0.0; s.lams = 0.0; s.dW = 0.0; s.row = 0;
   s.low = false; s.imm = false; s.soft = false;
-  s.k = 0; s.sing = false; s.inws = 0ull;
+  s.k = 0; s.sing = false; s.rc = 0; s.inws = 0ull;
 }
 
 // Invariant of the tile: row i < k holds L[i][j] for j < i and exact ZEROS for i <= j < LS (the
@@ -211,6 +212,49 @@ LMPC_DEVINL int argmin_first(double a, double &amin) {
   return (amin < CUDART_INF) ? lane : -1;
 }
 
+// Problems with SOFT rows only (oracle: rebuild): refactorise from scratch with the hard rows first, in
+// their current order, and the soft rows last, multipliers kept.  Taken when a pivot fell below
+// zero_tol while a soft row (pivot contribution rho = 1e-6) is in the working set, and once per
+// solve when the cycle guard fires.  A hard row that is dependent on the hard block itself goes to
+// the very end with a zero pivot (the genuinely singular case); a second one: EXIT_CYCLE in s.rc.
+// Rare and long: kept out of line, state passed by value so the caller's copy stays in registers.
+template <int UF>
+__device__ __noinline__ WarpQp wq_rebuild(const WarpCtx c, WarpQp s) {
+  const int lane = c.lane, k = s.k;
+  const int row0 = s.row;
+  const bool low0 = s.low;
+  const double lam0 = s.lam, dW0 = s.dW;
+  const unsigned hard = __ballot_sync(FULL, lane < k && !s.soft), softm = __ballot_sync(FULL, lane < k && s.soft);
+  const int nh = __popc(hard);
+  s.k = 0; s.sing = false; s.rc = 0;
+  int defer = -1;
+  for (int t = 0; t < k; ++t) {
+    const int src = (t < nh) ? (int)__fns(hard, 0, t + 1) : (int)__fns(softm, 0, t - nh + 1);
+    const int j = __shfl_sync(FULL, row0, src);
+    const bool lo = __shfl_sync(FULL, (int)low0, src);
+    const double dv = shfl_d(dW0, src), lm = shfl_d(lam0, src);
+    wq_add<UF>(c, s, j, lo, dv);
+    if (lane == s.k - 1) s.lam = lm;
+    if (s.sing) {
+      if (t >= nh || defer >= 0) { s.rc = EXIT_CYCLE; return s; }
+      defer = src; s.k -= 1; s.sing = false;
+    }
+  }
+  if (defer >= 0) {
+    const int j = __shfl_sync(FULL, row0, defer);
+    const bool lo = __shfl_sync(FULL, (int)low0, defer);
+    const double dv = shfl_d(dW0, defer), lm = shfl_d(lam0, defer);
+    wq_add<UF>(c, s, j, lo, dv);
+    if (lane == s.k - 1) { s.lam = lm; s.D = 0.0; s.Dinv = 0.0; }
+    s.sing = true;
+  }
+  return s;
+}
+// a soft row is in the working set: a pivot below zero_tol is then suspect (see wq_rebuild)
+LMPC_DEVINL bool wq_has_soft(const WarpCtx &c, const WarpQp &s) {
+  return c.lay->nsoft > 0 && __any_sync(FULL, c.lane < s.k && s.soft);
+}
+
 // The dual active-set loop for one QP (oracle: ldp_loop).  sh0/sh1: shifts of rows lane, lane+32.
 template <int UF>
 LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, double &u, int &iters) {
@@ -218,6 +262,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
   const LdpSettings &st = *c.st;
   const int lane = c.lane, n = lay.n, m = lay.m, mp = lay.mp;
   int flag = EXIT_ITERLIMIT, iter, cycle = 0;
+  bool repaired = false;
   double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
   for (iter = 1; iter < st.iter_limit; ++iter) {
     const int k = s.k;
@@ -279,15 +324,22 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
           break;
         }
         // cycle guard where the dual objective is fresh (see oracle/ldp_oracle.c)
+        bool rebuilt = false;
         if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
-        else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; break; }
+        else if (cycle++ > st.cycle_tol) {
+          // second chance for problems with soft rows: refactorise once, restart the count
+          if (repaired || !wq_has_soft(c, s)) { flag = EXIT_CYCLE; break; }
+          repaired = true; rebuilt = true; best_fval = -1.0; cycle = 0;
+        }
         if (k >= lay.cap || k >= 32) { flag = EXIT_CAPACITY; break; }
         const int src = hit0 ? (__ffs(hit0) - 1) : (__ffs(hit1) - 1);
         const int add = __shfl_sync(FULL, bestj, src);
         const bool addlow = __shfl_sync(FULL, (int)bestlow, src);
         const double addd = shfl_d(bestd, src);
         if (lane < k) s.lam = s.lams;
+        if (rebuilt) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
         wq_add<UF>(c, s, add, addlow, addd);
+        if (s.sing && wq_has_soft(c, s)) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
         continue;
       }
       // 4. blocking: ratio test against lam* - lam
@@ -319,6 +371,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
     if (rm < 0) { flag = noblock; break; }   // regular: blocked but no finite ratio (NaN guard)
     if (lane < k) s.lam = fma(alpha, dir, s.lam);
     wq_remove(c, s, rm);
+    if (s.sing && wq_has_soft(c, s)) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
   }
   iters = iter;
   return flag;

@@ -222,6 +222,28 @@ class _SimExt(C.Structure):
                [("ny", C.c_int32), ("Xhat_end", C.c_void_p), ("rstride", C.c_int32), ("dstride", C.c_int32)]
 
 
+def hold_trajectory(v, rows, steps):
+    """Scenario trajectory -> rows x steps, last value held: the reference copies scenario.r / scenario.d
+    into an N-column array before the loop starts (simulation.jl:57-80)."""
+    if v is None or rows == 0:
+        return None
+    v = np.asarray(v, float).reshape(rows, -1)
+    if v.shape[1] < steps:
+        v = np.hstack([v, np.repeat(v[:, -1:], steps - v.shape[1], axis=1)])
+    return np.asfortranarray(v[:, :steps])
+
+
+def preview_window(v, rows_total, Np, first, steps):
+    """Flat trajectory for a sliding window of Np columns starting at column k + first of the held
+    `steps`-column trajectory (get_preview, simulation.jl:102-104,128-134: rs[:, min(k + i, end)] with
+    `end` = steps, so scenario columns beyond `steps` are never seen).  Returns (flat, stride)."""
+    base = rows_total // Np
+    v = hold_trajectory(v, base, steps)
+    need = first + steps - 1 + Np                      # last column index read + 1
+    v = np.hstack([v, np.repeat(v[:, -1:], need - v.shape[1], axis=1)])
+    return np.asfortranarray(v[:, first:need]), base
+
+
 class GpuMPC:
     """Device-resident implicit controller: the GPU backend `setup_gpu!` would attach to an MPC.
 
@@ -295,6 +317,7 @@ class GpuMPC:
                    Uth=np.zeros((nu, nth)), uoff=np.zeros(nu))
         _check(lib().lmpc_gpu_get_ldp(self._h, *[_ptr(out[k]) for k in
                                                  ("Mbar", "Gram", "Dth", "du", "dl", "Rinv", "Uth", "uoff")]))
+        out["senses"], out["cap"] = np.array(self.senses, np.int32), int(self.cap)   # lmpc_gpu_get_info
         return out
 
     # -- solve(mpc, theta), batched ---------------------------------------------------------
@@ -379,15 +402,18 @@ class GpuMPC:
                 base = np.zeros(rows) if default is None else np.asarray(default, float)[:rows]
                 return np.repeat(base.reshape(rows, 1), N, axis=1)
             v = np.asarray(v, float)
+            # any other size is an error, as in format_reference / format_disturbance (utils.jl:78-205)
             if v.ndim == 1:
-                if v.size != rows and v.size < rows:
+                if v.size != rows:
                     raise ValueError(f"vector length ({v.size}) must match ({rows})")
-                return np.repeat(v[:rows].reshape(rows, 1), N, axis=1)
-            if v.shape[0] < rows:
-                raise ValueError(f"matrix must have {rows} rows")
+                return np.repeat(v.reshape(rows, 1), N, axis=1)
+            if v.shape[0] != rows:
+                raise ValueError(f"matrix must have {rows} rows, got {v.shape[0]}")
             if v.shape[1] == 1 and N > 1:
-                return np.repeat(v[:rows], N, axis=1)
-            return v[:rows]
+                return np.repeat(v, N, axis=1)
+            if v.shape[1] != N:
+                raise ValueError(f"matrix must have {N} columns (one per instance), got {v.shape[1]}")
+            return v
         Rm, Dm, Um = blk(r, nr), blk(d, nd), blk(uprev, nup, self.uprev)
         if nd > 0 and Dm.shape[0] != nd:
             raise ValueError(f"Disturbance vector must have length {nd}")
@@ -454,22 +480,9 @@ class GpuMPC:
                 v = np.repeat(v.reshape(rows, 1), n, axis=1)
             return np.asfortranarray(v)
         Rm, Dm, Um = bc(r, nr), bc(d, nd), bc(u0, nup) if u0 is not None else None
-        def hold(v, rows):
-            if v is None or rows == 0:
-                return None
-            v = np.asarray(v, float).reshape(rows, -1)
-            if v.shape[1] < steps:
-                v = np.hstack([v, np.repeat(v[:, -1:], steps - v.shape[1], axis=1)])
-            return np.asfortranarray(v[:, :steps])
+        hold = lambda v, rows: hold_trajectory(v, rows, steps)
         rstride = dstride = 0
-        def window(v, rows_total, Np, first):
-            """flat trajectory for a sliding window of Np columns starting at column k + first."""
-            base = rows_total // Np
-            v = np.asarray(v, float).reshape(base, -1)
-            need = first + steps - 1 + Np                      # last column index read + 1
-            if v.shape[1] < need:
-                v = np.hstack([v, np.repeat(v[:, -1:], need - v.shape[1], axis=1)])
-            return np.asfortranarray(v[:, first:need]), base
+        window = lambda v, rows_total, Np, first: preview_window(v, rows_total, Np, first, steps)
         if r_preview and r_traj is not None and nr:
             Rt, rstride = window(r_traj, nr, int(r_preview), 1)
             Dt = hold(d_traj, nd)

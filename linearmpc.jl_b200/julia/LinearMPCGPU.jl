@@ -223,9 +223,10 @@ function simulate_observed(g::GpuMPC, X0::Matrix{Float64}; N::Integer=100, r=not
     rprev = g.mpc.settings.reference_preview && nr > 0
     dprev = g.mpc.settings.disturbance_preview && nd > 0
     nyr, ndb = rprev ? nr ÷ Np : nr, dprev ? nd ÷ Np : nd
-    window(V) = isnothing(V) ? nothing : hcat(V, repeat(V[:, end], 1, Np - 1))
+    # r: get_preview(rs, k, Np) reads columns k+1 .. k+Np; d: get_preview(ds, k-1, Np) reads k .. k+Np-1
+    window(V, first) = isnothing(V) ? nothing : hcat(V[:, 1+first:end], repeat(V[:, end], 1, Np - 1 + first))
     Rt, Dt = hold(r, nyr), hold(d, ndb)
-    rprev && (Rt = window(Rt)); dprev && (Dt = window(Dt))
+    rprev && (Rt = window(Rt, 1)); dprev && (Dt = window(Dt, 0))
     rstride, dstride = rprev ? nyr : 0, dprev ? ndb : 0
     ny = size(kf.C, 1)
     Vt = hold(noise, ny)

@@ -24,7 +24,7 @@ class _Problem(C.Structure):
                 ("Rinv", c_dp), ("Uth", c_dp), ("uoff", c_dp), ("sense", c_ip),
                 ("rho_soft", C.c_double), ("primal_tol", C.c_double), ("dual_tol", C.c_double),
                 ("zero_tol", C.c_double), ("progress_tol", C.c_double), ("fval_bound", C.c_double),
-                ("cycle_tol", C.c_int), ("iter_limit", C.c_int)]
+                ("cycle_tol", C.c_int), ("iter_limit", C.c_int), ("no_repair", C.c_int), ("cap", C.c_int)]
 
 
 class _Bst(C.Structure):
@@ -62,7 +62,7 @@ def _up(a):
 
 
 DEFAULT_SETTINGS = dict(primal_tol=1e-6, dual_tol=1e-12, zero_tol=1e-11, progress_tol=1e-6,
-                        fval_bound=1e30, cycle_tol=10, iter_limit=10000)
+                        fval_bound=1e30, cycle_tol=10, iter_limit=10000, no_repair=0, cap=0)
 
 
 def gram(Mbar):
@@ -100,7 +100,7 @@ class OracleProblem:
                           _dp(self.Dth), _dp(self.du), _dp(self.dl), _dp(self.Rinv), _dp(self.Uth),
                           _dp(self.uoff), _ip(self.sense), ldp.rho_soft, s["primal_tol"],
                           s["dual_tol"], s["zero_tol"], s["progress_tol"], s["fval_bound"],
-                          s["cycle_tol"], s["iter_limit"])
+                          s["cycle_tol"], s["iter_limit"], int(s["no_repair"]), int(s["cap"]))
 
     def solve_batch(self, Theta, nthreads=0, want_flops=False):
         """Theta: nth x N (any layout).  Returns dict(U nu x N, flag, iters, act_u, act_l[, flops])."""

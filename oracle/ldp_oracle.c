@@ -188,6 +188,7 @@ static int rebuild(const orc_problem *p, work_t *w, double *fl) {
 
 /* the working set holds a soft row: a pivot below zero_tol is then suspect (see rebuild) */
 static int has_soft(const orc_problem *p, const work_t *w) {
+  if (p->no_repair) return 0;
   for (int i = 0; i < w->k; ++i) if (p->sense[w->ws[i]] & ORC_SOFT) return 1;
   return 0;
 }
@@ -280,6 +281,7 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
           if (repaired || !has_soft(p, w)) { flag = ORC_CYCLE; break; }
           repaired = 1; rebuilt = 1; best_fval = -1.0; cycle = 0;
         }
+        if (p->cap > 0 && k >= p->cap) { flag = ORC_CAPACITY; break; }
         for (int i = 0; i < k; ++i) w->lam[i] = w->lams[i];
         if (rebuilt && (rc = rebuild(p, w, fl)) != 0) { flag = rc; break; }
         if ((rc = add_row(p, w, add, addside, fl)) != 0) { flag = rc; break; }
@@ -332,6 +334,7 @@ static int ldp_loop(const orc_problem *p, work_t *w, int32_t *iters, double *sof
 static int activate_equalities(const orc_problem *p, work_t *w) {
   for (int j = 0; j < p->m; ++j)
     if (p->sense[j] & ORC_ACTIVE) {
+      if (p->cap > 0 && w->k >= p->cap) return ORC_OVERDETERMINED;
       ldl_add(p, w, j, (p->sense[j] & ORC_LOWER) ? -1 : 1, NULL);
       if (w->sing) return ORC_OVERDETERMINED;
     }
@@ -364,6 +367,7 @@ static int activate_rows(const orc_problem *p, work_t *w, const uint64_t *wu, co
     if (p->sense[j] & (ORC_ACTIVE | ORC_IMMUTABLE)) continue;
     const int up = wu && ((wu[j >> 6] >> (j & 63)) & 1ull), lo = wl && ((wl[j >> 6] >> (j & 63)) & 1ull);
     if (!up && !lo) continue;
+    if (p->cap > 0 && w->k >= p->cap) continue;
     ldl_add(p, w, j, up ? 1 : -1, NULL);
     if (w->sing) { w->k -= 1; w->inws[j] = 0; w->sing = 0; }   /* undo the trial add */
   }

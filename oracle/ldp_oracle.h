@@ -30,7 +30,8 @@ extern "C" {
 
 enum {
   ORC_OPTIMAL = 1, ORC_SOFT_OPTIMAL = 2, ORC_INFEASIBLE = -1, ORC_CYCLE = -2,
-  ORC_UNBOUNDED = -3, ORC_ITERLIMIT = -4, ORC_NONCONVEX = -5, ORC_OVERDETERMINED = -6
+  ORC_UNBOUNDED = -3, ORC_ITERLIMIT = -4, ORC_NONCONVEX = -5, ORC_OVERDETERMINED = -6,
+  ORC_CAPACITY = -7   /* not a DAQP flag: see orc_problem.cap */
 };
 enum { ORC_ACTIVE = 1, ORC_LOWER = 2, ORC_IMMUTABLE = 4, ORC_SOFT = 8, ORC_BINARY = 16 };
 
@@ -46,6 +47,10 @@ typedef struct {
   const int32_t *sense; /* m */
   double rho_soft, primal_tol, dual_tol, zero_tol, progress_tol, fval_bound;
   int cycle_tol, iter_limit;
+  int no_repair;        /* != 0: switch the soft-row repair (rebuild) off -- tests only, to show what it fixes */
+  int cap;              /* > 0: working-set capacity; a row that would not fit ends the solve with
+                         * ORC_CAPACITY, as the kernels do with the capacity they provision on chip
+                         * (lmpc_gpu_get_info).  0: unbounded (max(m, n) + 1), DAQP's own behaviour */
 } orc_problem;
 
 /* one solve; returns exit flag.  act_u/act_l: ceil(m/64) words each (nullable).

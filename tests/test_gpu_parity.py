@@ -71,7 +71,15 @@ CASES = [("invpend", 1.0, 10000), ("invpend", 0.25, 10000), ("invpend", 0.05, 10
          ("aircraft", 1.0, 4000), ("aircraft", 0.25, 4000), ("aircraft_ksall", 0.25, 2000),
          ("simple", 1.0, 4000), ("simple_q1000", 0.5, 2000),
          ("chain_small", 1.0, 2000), ("chain", 1.0, 300), ("chain", 0.25, 300),
-         ("dint_eq", 1.0, 4000), ("dint_eq_small", 1.0, 4000)]   # terminal equality rows
+         ("dint_eq", 1.0, 4000), ("dint_eq_small", 1.0, 4000),   # terminal equality rows
+         # soft rows on the whole horizon (the reference's default ks): the refactorisation repair runs
+         ("aircraft_ksall", 1.0, 4000), ("aircraft_ksall", 0.5, 4000),
+         # every box-kernel instantiation <n, nu>: n = 1..8 with nu = 1, n = 2, 4, 6, 8 with nu = 2
+         ("invpend_nc1", 1.0, 4000), ("invpend_nc2", 1.0, 4000), ("invpend_nc3", 1.0, 4000),
+         ("invpend_nc4", 0.25, 4000), ("invpend_nc6", 1.0, 4000), ("invpend_nc7", 0.25, 4000),
+         ("invpend_nc8", 1.0, 4000), ("invpend_nc8", 0.25, 4000),
+         ("aircraft_box1", 1.0, 4000), ("aircraft_box2", 0.25, 4000), ("aircraft_box3", 1.0, 4000),
+         ("aircraft_box4", 0.25, 4000), ("aircraft_box4", 1.0, 2000)]
 
 
 @pytest.mark.parametrize("name,scale,N", CASES)
@@ -81,6 +89,33 @@ def test_batch_matches_oracle(lmpc, name, scale, N):
     lo, hi = util.theta_range(name, scale)
     Th = mpqp.sample_theta(lo, hi, N)
     assert_parity(g.solve(Th), P.solve_batch(Th))
+
+
+def test_box_kernel_is_what_runs_on_box_only_problems(lmpc):
+    """the cases above really exercise K1b: box-only problems with n <= 8 select the thread kernel and
+    the library takes its box fast path (lmpc_gpu_get_info reports the thread kernel, capacity n)."""
+    for name in ("invpend_nc1", "invpend_nc8", "aircraft_box1", "aircraft_box4"):
+        mpc, qp, g, P = gpu_controller(lmpc, name)
+        assert g.kernel == lmpc.KERNEL_THREAD and g.cap == qp.n and not np.any(g.senses)
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.5, 0.25])
+def test_default_output_bounds_never_end_infeasible_at_size(lmpc, scale):
+    """AFTI-16 with output bounds on the reference's default ks = 2:Np (18 soft rows) over 1e6 theta:
+    flags in {1, 2} only (a soft problem is feasible by construction; round 1 returned -1 on 22 % at
+    s = 1), and a 2e4 subsample equals the oracle bit for bit.  One numerically cycling instance per
+    3e6 is the known residue (tests/test_oracle_golden.py)."""
+    mpc, qp, g, P = gpu_controller(lmpc, "aircraft_ksall")
+    lo, hi = util.theta_range("aircraft_ksall", scale)
+    N = 1_000_000
+    Th = mpqp.sample_theta(lo, hi, N, seed=4321)
+    out = g.solve(Th, want_active=False)
+    bad = np.count_nonzero((out["exitflag"] != 1) & (out["exitflag"] != 2))
+    assert bad <= 1, np.unique(out["exitflag"], return_counts=True)
+    sub = np.random.default_rng(1).choice(N, 20000, replace=False)
+    ref = P.solve_batch(Th[:, sub])
+    assert np.array_equal(out["exitflag"][sub], ref["flag"]) and np.array_equal(out["iters"][sub], ref["iters"])
+    assert np.array_equal(np.asarray(out["U"])[:, sub], ref["U"])
 
 
 @pytest.mark.parametrize("fn", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz") and "_s" in f))
@@ -493,7 +528,9 @@ def test_closed_loop_with_preview_windows(lmpc, name):
                      r_traj=rs, d_traj=ds, r_preview=2, d_preview=2)
     # the same loop spelled out for the oracle: explicit windows, zero-padded Gd
     hold = lambda v, n: np.hstack([v, np.repeat(v[:, -1:], max(0, n - v.shape[1]), axis=1)])
-    rsx, dsx = hold(rs, T + 3), hold(ds, T + 3)
+    # the reference holds column N of its N-column copy (simulation.jl:57-80, 128-134): scenario columns
+    # beyond the simulated horizon are never previewed
+    rsx, dsx = hold(rs[:, :T], T + 3), hold(ds[:, :T], T + 3)
     Gdp = np.hstack([Gd1, np.zeros((nx, 1))])
     # stepwise restatement with the oracle's single solves (tolerance: BLAS vs fma-chain dynamics)
     for q in range(0, N, 40):
@@ -698,7 +735,7 @@ def test_preview_controller_closed_loop_through_builder(lmpc):
     ds = 0.2 * rng.standard_normal((2, 40))
     out = m.simulate(X0, N=T, r_traj=rs, d_traj=ds, want_traj=True, warm_start=False)
     hold = lambda v, n: np.hstack([v, np.repeat(v[:, -1:], max(0, n - v.shape[1]), axis=1)])
-    rsx, dsx = hold(rs, T + Np + 1), hold(ds, T + Np + 1)
+    rsx, dsx = hold(rs[:, :T], T + Np + 1), hold(ds[:, :T], T + Np + 1)    # clamp at column N, as get_preview does
     for q in range(0, N, 16):
         x, u = X0[:, q].copy(), np.zeros(o.nu)
         for k in range(T):

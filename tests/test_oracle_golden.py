@@ -289,3 +289,72 @@ def test_closed_loop_with_observer_equals_the_stepwise_loop():
             x = Ft @ x + Gt @ u
         assert np.allclose(x, out["Xend"][:, q], rtol=0, atol=1e-8)
         assert np.allclose(xh, out["Xhat_end"][:, q], rtol=0, atol=1e-8)
+
+
+def _exact_kkt(L, P, th, au, al, nu):
+    """Re-solve the equality-constrained problem on a given working set in 50-digit arithmetic
+    (Gram matrix included, so the conditioning of the soft regularisation does not touch the check).
+    Returns (lam, sides, worst primal violation over inactive rows, control)."""
+    import mpmath
+    mpmath.mp.dps = 50
+    soft = (L.senses & mpqp.SOFT) != 0
+    sh = L.Dth @ th
+    dup, dlo = L.du + sh, L.dl + sh
+    W = np.where(au | al)[0]
+    sd = np.where(au[W], 1.0, -1.0)
+    Mw = mpmath.matrix(L.Mbar[W].tolist())
+    G = Mw * Mw.T
+    for i in range(len(W)):
+        if soft[W[i]]:
+            G[i, i] += mpmath.mpf(L.rho_soft)
+    dw = np.where(sd > 0, dup[W], dlo[W])
+    lam = mpmath.lu_solve(G, mpmath.matrix((-dw).tolist()))
+    u = np.array([float(x) for x in -(Mw.T * lam)])
+    lam = np.array([float(x) for x in lam])
+    mu = L.Mbar @ u
+    pv = np.maximum(mu - dup, dlo - mu)
+    pv[W] = -1.0
+    pv[(L.senses & mpqp.IMMUTABLE) != 0] = -1.0
+    return lam, sd, pv.max(), L.Rinv[:nu] @ u + L.u_offset + L.Uth_offset @ th
+
+
+def test_default_output_bounds_never_end_infeasible():
+    """AFTI-16 with output bounds on ks = 2:Np, the reference's DEFAULT ks (setup.jl:64,94): 18 soft rows.
+    A soft-constrained problem is feasible by construction and the reference asserts exitflag >= 1
+    (utils.jl:46).  Round 1 returned INFEASIBLE on 22 % of the example's own parameter range because
+    pivots of hard rows factorised after soft rows (order rho |c|^2 ~ 1e-10) drowned in rounding; the
+    repair (oracle: rebuild) refactorises with the hard block first.  Anchors:
+      * flags in {1, 2} on 1e5 theta at each of s = 1, 0.5, 0.25 (3e6 checked offline: one CYCLE);
+      * with the repair switched off the old failure is back (so the test is red on round 1's code);
+      * on theta that failed before, the final working set is the exact optimum: re-solved in 50-digit
+        arithmetic its multipliers have the right signs and no inactive row is violated beyond the
+        noise of u = -M'lam with lam ~ 1e8 (bounds below; the same limit applies to any fp64 dual method)."""
+    mpc, qp, L, P = make("aircraft_ksall")
+    P0 = ldp.OracleProblem(L, mpc.nu, no_repair=1)
+    for s, nbad_min, utol in [(1.0, 15000, 5e-3), (0.5, 1000, 5e-4), (0.25, 0, 1e-4)]:
+        lo, hi = util.theta_range("aircraft_ksall", s)
+        Th = mpqp.sample_theta(lo, hi, 100000)
+        out = P.solve_batch(Th)
+        assert set(np.unique(out["flag"]).tolist()) <= {1, 2}, np.unique(out["flag"], return_counts=True)
+        old = P0.solve_batch(Th)
+        bad = np.where(old["flag"] < 0)[0]
+        assert len(bad) >= nbad_min
+        au, al = util.bits(out["act_u"], P.m), util.bits(out["act_l"], P.m)
+        pick = bad[:12] if len(bad) else np.arange(12)
+        for q in pick:
+            lam, sd, pviol, ctl = _exact_kkt(L, P, Th[:, q], au[q], al[q], mpc.nu)
+            assert np.all(lam * sd >= -1e-6 * max(1.0, np.abs(lam).max())), q   # dual feasible (upper: lam >= 0)
+            assert pviol <= 1e-3 * s, (q, pviol)
+            assert np.max(np.abs(ctl - out["U"][:, q])) <= utol, (q, ctl, out["U"][:, q])
+
+
+def test_repair_leaves_the_baseline_controllers_alone():
+    """BASELINE AFTI-16 (2 soft rows) never needed the repair: identical results with it switched off."""
+    mpc, qp, L, P = make("aircraft")
+    P0 = ldp.OracleProblem(L, mpc.nu, no_repair=1)
+    for s in (1.0, 0.25):
+        lo, hi = util.theta_range("aircraft", s)
+        Th = mpqp.sample_theta(lo, hi, 50000)
+        a, b = P.solve_batch(Th), P0.solve_batch(Th)
+        assert set(np.unique(a["flag"]).tolist()) <= {1, 2}
+        assert np.array_equal(a["U"], b["U"]) and np.array_equal(a["iters"], b["iters"])

@@ -334,3 +334,28 @@ def test_reference_case_disturbance_preview_dimensions_and_effect():
         o.form_parameter(np.zeros(2), None, [0.0, 1.0], None)
     with pytest.raises(ValueError):
         o.form_parameter(np.zeros(2), None, np.ones((2, 2)), None)
+
+
+def test_preview_windows_follow_the_reference_simulation_loop(lmpc):
+    """host.preview_window against simulation.jl:57-80,102-104,128-134 written out literally: the
+    scenario is first copied into an N-column array (shorter: last column held; longer: truncated),
+    then step k (1-based) previews rs[:, min(k + i, N)], i = 1..Np, and ds[:, min(k - 1 + i, N)]."""
+    import sys
+    host = sys.modules[lmpc.__name__ + ".host"]
+    rng = np.random.default_rng(3)
+    for ncols in (4, 9, 10, 17):                 # shorter than, equal to and LONGER than the horizon
+        N, Np, ny = 10, 4, 2
+        scen = rng.standard_normal((ny, ncols))
+        rs = np.zeros((ny, N))
+        Nr = min(N, ncols)
+        rs[:, :Nr] = scen[:, :Nr]
+        rs[:, ncols:] = scen[:, -1:]                 # rs[:, size(r,2)+1:end] .= r[:, end]
+        for first, kshift in ((1, 0), (0, -1)):      # reference preview, disturbance preview
+            flat, stride = host.preview_window(scen, ny * Np, Np, first, N)
+            assert stride == ny
+            flat = np.asarray(flat).reshape(-1, order="F")
+            for k in range(1, N + 1):
+                want = np.stack([rs[:, min(k + kshift + i, N) - 1] for i in range(1, Np + 1)], axis=1)
+                got = flat[(k - 1) * stride:(k - 1) * stride + ny * Np]
+                assert np.array_equal(got, want.reshape(-1, order="F")), (ncols, first, k)
+        assert np.array_equal(host.hold_trajectory(scen, ny, N), rs)

@@ -41,6 +41,11 @@ def controller(name):
         mpc = mpqp.invpend()
         mpc.reference_preview = True
         return mpc
+    if name.startswith("invpend_nc"):  # README pendulum with Nc = 1..8 moves: one box-kernel instantiation <n, 1> each
+        return mpqp.invpend(Nc=int(name[len("invpend_nc"):]))
+    if name.startswith("aircraft_box"):  # AFTI-16 with input bounds only, Nc = 1..4: box-only, nu = 2, n = 2 Nc
+        Nc = int(name[len("aircraft_box"):])
+        return mpqp.aircraft(Np=10, Nc=Nc, ks=())
     if name == "simple":
         return mpqp.simple_md(1.0)
     if name == "simple_q1000":
@@ -49,7 +54,7 @@ def controller(name):
 
 
 def theta_range(name, scale=1.0):
-    if name in ("invpend", "invpend_prestab"):
+    if name in ("invpend", "invpend_prestab") or name.startswith("invpend_nc"):
         return mpqp.invpend_range(scale)
     if name == "invpend_rpreview":     # [x(4); r_1..r_50 (2 each); uprev]
         lo, hi = mpqp.invpend_range(scale)
@@ -86,6 +91,8 @@ def oracle_from_constants(qp, nu, cst, soft_weight=1e6, **settings):
     L.Uth_offset, L.u_offset = cst["Uth"], cst["uoff"]
     if "senses" in cst:
         L.senses = np.asarray(cst["senses"], np.int32)
+    if "cap" in cst and "cap" not in settings:      # the working-set capacity the kernels provision
+        settings["cap"] = int(cst["cap"])
     P = ldp.OracleProblem(L, nu, **settings)
     P.Gram[:] = cst["Gram"]
     return P
