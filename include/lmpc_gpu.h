@@ -167,6 +167,22 @@ int lmpc_gpu_compute_control_batch(lmpc_handle *h, double *control, const double
                                    int32_t nr, int32_t nd, int32_t nuprev, int64_t N,
                                    int32_t *exitflag);
 
+/* Monte-Carlo form of the same call: any of reference / disturbance / uprev may be ONE vector shared by
+ * all N instances (bit set in `bcast`: the block is then nr x 1 / nd x 1 / nuprev x 1 and is uploaded
+ * once instead of N times -- compute_control(mpc, x; r, d, uprev) called in a loop over x with the other
+ * arguments fixed, src/utils.jl:43-51).  `control` (nu x N) is output only here; uprev is its own
+ * argument.  exitflag may be NULL when n_failed is given: the flags then stay on the device and only
+ * the number of instances with exitflag < 1 (what the reference's @assert would trip on) comes back.
+ * Host or device pointers.  End to end this moves 8 nx + 8 nu bytes per instance instead of
+ * 8 nth + 8 nu + 4. */
+#define LMPC_BCAST_REFERENCE 1
+#define LMPC_BCAST_DISTURBANCE 2
+#define LMPC_BCAST_UPREV 4
+int lmpc_gpu_compute_control_batch_bcast(lmpc_handle *h, double *control, const double *state,
+                                         const double *reference, const double *disturbance,
+                                         const double *uprev, int32_t nr, int32_t nd, int32_t nuprev,
+                                         int64_t N, int32_t bcast, int32_t *exitflag, int64_t *n_failed);
+
 /* Replaces N independent copies of the Simulation loop (src/simulation.jl:93-113) with the
  * default linear dynamics x+ = F x + G u + Gd d (src/model.jl:70): T steps of
  * compute_control + dynamics, entirely on the GPU.  F nx x nx, G nx x nu, Gd nx x nd
@@ -253,6 +269,28 @@ int lmpc_gpu_solve_batch_multi(lmpc_multi *m, const double *Theta, int64_t N, do
                                int32_t *exitflag, int32_t *iters,
                                uint64_t *active_upper, uint64_t *active_lower);
 
+/* Closed loops and explicit controllers on every GPU of the box from one process: the same contiguous
+ * split (device g owns [g N / G, (g+1) N / G)), HOST buffers, one worker thread per device; arguments
+ * otherwise as lmpc_gpu_simulate_batch_ex / lmpc_gpu_evaluate_batch. */
+int lmpc_gpu_simulate_batch_multi(lmpc_multi *m, const double *F, const double *G, const double *Gd,
+                                  int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                                  const double *X0, const double *R, const double *D, const double *U0,
+                                  const lmpc_sim_ext *ext, int64_t N, int32_t T, int32_t warm_start,
+                                  double *Xend, double *Ulast, double *Utraj,
+                                  int32_t *exitflag, int32_t *iters);
+
+/* The final result gather of BASELINE's north_star, fused into the solve: a "window" is a device buffer
+ * on ONE GPU (rank 0's) that every other process of the box maps through CUDA IPC; each rank then passes
+ * `window + its offset` as the U / exitflag output of lmpc_gpu_solve_batch_async, so the kernel's own
+ * stores travel over NVLink into the gathered array (8 nu + 4 bytes per solve, no second kernel, no
+ * NCCL call).  create: cudaMalloc on `device` + a 64-byte handle to send to the peers (any transport);
+ * open: map a peer's window into this process on `device`; close: unmap (owner = 0) or free (owner = 1). */
+int lmpc_gpu_window_create(int device, size_t bytes, void **devptr, unsigned char handle[64]);
+int lmpc_gpu_window_open(int device, const unsigned char handle[64], void **devptr);
+int lmpc_gpu_window_close(void *devptr, int owner);
+/* copy `bytes` of a window (at devptr, any offset into it) to host memory; synchronous */
+int lmpc_gpu_window_read(void *dst_host, const void *devptr, size_t bytes);
+
 /* Replaces ParametricDAQP.build_tree's result as used by compute_control(empc, ...)
  * (src/utils.jl:53-60, src/explicit.jl:65-71).  halfplanes (nth+1) x n_hp column-major
  * (column h = [a_h; b_h]); feedbacks n_fb blocks of (nth+1) x nu column-major (u = F'[theta;1]);
@@ -264,6 +302,17 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
                         int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
                         int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
                         int device, lmpc_bst **out);
+/* Same, for a tree whose producer uses the OTHER branch orientation.  le_child names the child taken
+ * when a'theta <= b: 0 = `next` (this library's convention, what lmpc_gpu_create_bst assumes and what the
+ * repo's own builder emits), 1 = `next + 1`.  ParametricDAQP is not vendored in the reference, so its
+ * convention cannot be read off here; from its generated C (`id = next_id + (val <= b)`) it is believed to
+ * be 1, which is what the Julia glue passes -- and then VERIFIES against ParametricDAQP.evaluate on sampled
+ * theta before trusting the upload (LinearMPCGPU.jl: setup_gpu!(empc)).  The children are exchanged once,
+ * on the host, at create time: the kernels always walk one convention. */
+int lmpc_gpu_create_bst_oriented(const double *halfplanes, int32_t n_hp, const double *feedbacks,
+                                 int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
+                                 int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
+                                 int32_t le_child, int device, lmpc_bst **out);
 int lmpc_gpu_destroy_bst(lmpc_bst *t);
 /* Replaces ParametricDAQP.evaluate(bst, theta) (src/utils.jl:57) / {fname}_evaluate
  * (src/codegen.jl:113-124) for N parameters.  region (nullable) receives the leaf's region id. */
@@ -271,6 +320,16 @@ int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double 
                             int32_t *region);
 int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, double *U,
                                   int32_t *region, void *stream);
+/* one process, several GPUs: a replica of the tree per listed device (devices NULL = 0..n-1), a HOST
+ * batch split into contiguous ranges */
+typedef struct lmpc_bst_multi lmpc_bst_multi;
+int lmpc_gpu_create_bst_multi(const double *halfplanes, int32_t n_hp, const double *feedbacks,
+                              int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
+                              int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
+                              const int32_t *devices, int32_t n_devices, lmpc_bst_multi **out);
+int lmpc_gpu_destroy_bst_multi(lmpc_bst_multi *t);
+int lmpc_gpu_evaluate_batch_multi(lmpc_bst_multi *t, const double *Theta, int64_t N, double *U,
+                                  int32_t *region);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-side condensing: build the dense mpQP from a discrete-time model without

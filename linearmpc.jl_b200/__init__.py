@@ -10,7 +10,8 @@ call raises.
 """
 from .host import (  # noqa: F401
     LmpcError, lib, lib_path, load_library, default_settings,
-    GpuMPC, MultiGpuMPC, GpuExplicitMPC, MPC, setup_gpu, host_ldp, fp64_peak_tflops, launch_count, device_count, pinned_empty,
+    GpuMPC, MultiGpuMPC, GpuExplicitMPC, ResultWindow, MPC, setup_gpu, host_ldp, fp64_peak_tflops, launch_count, device_count, pinned_empty,
     KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP, KERNEL_CTA,
 )
 from .sharding import shard_range, gather_columns, max_over_ranks  # noqa: F401,E402
+from .examples import mpc_examples, zoh  # noqa: F401,E402

@@ -207,6 +207,7 @@ struct lmpc_handle {
   cudaStream_t stream = nullptr;
   Slot slots[kSlots];
   DevBuf dyn;   // F, G, Gd for simulate
+  DevBuf counter;   // failed-instance count of the last *_bcast call
   std::mutex mu;   // host-buffer calls share the staging slots / dyn: one at a time per handle
 };
 
@@ -308,6 +309,7 @@ int lmpc_gpu_destroy(lmpc_handle *h) {
   cudaSetDevice(h->device);
   free_slots(h->slots);
   h->dyn.release();
+  h->counter.release();
   if (h->d_blk) cudaFree(h->d_blk);
   if (h->stream) cudaStreamDestroy(h->stream);
   free(h->h_blk);
@@ -402,7 +404,7 @@ static int drain_slot(lmpc_handle *h, Slot &s, double *U, int ustride, int32_t *
     const double *su = (const double *)s.hu.p;
     if (ustride == l.nu) memcpy(U + (off + a) * l.nu, su + a * l.nu, (size_t)(b - a) * l.nu * 8);
     else for (int64_t i = a; i < b; ++i) memcpy(U + (off + i) * ustride, su + i * l.nu, (size_t)l.nu * 8);
-    memcpy(flag + off + a, (const int32_t *)s.hflag.p + a, (size_t)(b - a) * 4);
+    if (flag) memcpy(flag + off + a, (const int32_t *)s.hflag.p + a, (size_t)(b - a) * 4);
     if (iters) memcpy(iters + off + a, (const int32_t *)s.hiters.p + a, (size_t)(b - a) * 4);
     if (au) {
       memcpy(au + (off + a) * words, (const uint64_t *)s.hau.p + a * words, (size_t)(b - a) * words * 8);
@@ -419,12 +421,17 @@ static int drain_slot(lmpc_handle *h, Slot &s, double *U, int ustride, int32_t *
 static int solve_segments_host(lmpc_handle *h, const double *const *seg, const int *len,
                                const int *stride, int nseg, int64_t N, double *U, int ustride,
                                int32_t *flag, int32_t *iters, uint64_t *au, uint64_t *al,
-                               bool warm = false) {
+                               bool warm = false, int64_t *n_failed = nullptr) {
   std::lock_guard<std::mutex> lock(h->mu);
   SlotGuard guard(h->slots);
   const LdpLayout &l = h->lay;
   const int words = (l.m + 63) / 64;
-  bool stage = is_pageable(U) || is_pageable(flag);
+  bool stage = is_pageable(U) || (flag && is_pageable(flag));
+  if (n_failed) {
+    if (h->counter.reserve(8)) return LMPC_E_CUDA;
+    CUDA_OK(cudaMemsetAsync(h->counter.p, 0, 8, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
   for (int g = 0; g < nseg; ++g) stage = stage || is_pageable(seg[g]);
   const int64_t chunk = stage ? kChunk / 4 : kChunk;   // smaller stages: the ring fills sooner
   for (int i = 0; i < kSlots; ++i) h->slots[i].pend_cnt = 0;
@@ -436,10 +443,15 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
     memset(&th, 0, sizeof(th));
     th.nseg = nseg;
     for (int g = 0; g < nseg; ++g) {
-      const size_t bytes = (size_t)cnt * stride[g] * sizeof(double);
+      // stride 0: one vector shared by every instance (broadcast segment), uploaded once per stage
+      const size_t bytes = (stride[g] == 0 ? (size_t)len[g] : (size_t)cnt * stride[g]) * sizeof(double);
       if (s.in[g].reserve(bytes)) return LMPC_E_CUDA;
       const double *src = seg[g] + off * stride[g];
-      if (stage) {
+      if (stage && stride[g] == 0) {
+        if (s.hin[g].reserve(bytes)) return LMPC_E_CUDA;
+        memcpy(s.hin[g].p, src, bytes);
+        src = (const double *)s.hin[g].p;
+      } else if (stage) {
         if (s.hin[g].reserve(bytes)) return LMPC_E_CUDA;
         char *dst = (char *)s.hin[g].p;
         const size_t row = (size_t)stride[g] * 8;
@@ -463,12 +475,17 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
     }
     int rc = run_kernel(h, th, cnt, o, nullptr, s.stream);
     if (rc) return rc;
+    if (n_failed) {   // exit flags < 1 are counted on the device: the caller may then skip the flag array altogether
+      int e = launch_count_failed((const int32_t *)s.flag.p, cnt, (unsigned long long *)h->counter.p, s.stream);
+      if (e) return set_err(LMPC_E_CUDA, "count kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+      g_launches.fetch_add(1);
+    }
     if (stage) {
       if (s.hu.reserve((size_t)cnt * l.nu * 8) || s.hflag.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
       if (iters && s.hiters.reserve((size_t)cnt * 4)) return LMPC_E_CUDA;
       if (au && (s.hau.reserve((size_t)cnt * words * 8) || s.hal.reserve((size_t)cnt * words * 8))) return LMPC_E_CUDA;
       CUDA_OK(cudaMemcpyAsync(s.hu.p, s.u.p, (size_t)cnt * l.nu * 8, cudaMemcpyDeviceToHost, s.stream));
-      CUDA_OK(cudaMemcpyAsync(s.hflag.p, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+      if (flag) CUDA_OK(cudaMemcpyAsync(s.hflag.p, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
       if (iters) CUDA_OK(cudaMemcpyAsync(s.hiters.p, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
       if (au) {
         CUDA_OK(cudaMemcpyAsync(s.hau.p, s.au.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -483,7 +500,7 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
       CUDA_OK(cudaMemcpy2DAsync(U + off * ustride, (size_t)ustride * 8, s.u.p, (size_t)l.nu * 8,
                                 (size_t)l.nu * 8, (size_t)cnt, cudaMemcpyDeviceToHost, s.stream));
     }
-    CUDA_OK(cudaMemcpyAsync(flag + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (flag) CUDA_OK(cudaMemcpyAsync(flag + off, s.flag.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
     if (iters) CUDA_OK(cudaMemcpyAsync(iters + off, s.iters.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
     if (au) {
       CUDA_OK(cudaMemcpyAsync(au + off * words, s.au.p, (size_t)cnt * words * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -493,6 +510,11 @@ static int solve_segments_host(lmpc_handle *h, const double *const *seg, const i
   for (int i = 0; i < kSlots; ++i) {
     int rc = drain_slot(h, h->slots[i], U, ustride, flag, iters, au, al);
     if (rc) return rc;
+  }
+  if (n_failed) {
+    unsigned long long cnt = 0;
+    CUDA_OK(cudaMemcpy(&cnt, h->counter.p, 8, cudaMemcpyDeviceToHost));
+    *n_failed = (int64_t)cnt;
   }
   guard.armed = false;
   return 0;
@@ -569,6 +591,57 @@ int lmpc_gpu_compute_control_batch(lmpc_handle *h, double *control, const double
     return 0;
   }
   return solve_segments_host(h, seg, len, stride, ns, N, control, l.nu, exitflag, nullptr, nullptr, nullptr);
+}
+
+int lmpc_gpu_compute_control_batch_bcast(lmpc_handle *h, double *control, const double *state,
+                                         const double *reference, const double *disturbance,
+                                         const double *uprev, int32_t nr, int32_t nd, int32_t nuprev,
+                                         int64_t N, int32_t bcast, int32_t *exitflag, int64_t *n_failed) {
+  if (!h || !control || !state || N < 0 || nr < 0 || nd < 0 || nuprev < 0 || (!exitflag && !n_failed))
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_compute_control_batch_bcast: bad argument%s");
+  const LdpLayout &l = h->lay;
+  const int nx = l.nth - nr - nd - nuprev;
+  if (nx <= 0 || nuprev > l.nu || (nr > 0 && !reference) || (nd > 0 && !disturbance) || (nuprev > 0 && !uprev))
+    return set_err(LMPC_E_INVALID, "compute_control_batch_bcast: nx + nr + nd + nuprev must equal nth, no NULL block%s");
+  if (n_failed) *n_failed = 0;
+  if (N == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  const double *seg[4]; int len[4], stride[4], ns = 0;
+  seg[ns] = state; len[ns] = nx; stride[ns] = nx; ns++;
+  if (nr > 0) { seg[ns] = reference; len[ns] = nr; stride[ns] = (bcast & LMPC_BCAST_REFERENCE) ? 0 : nr; ns++; }
+  if (nd > 0) { seg[ns] = disturbance; len[ns] = nd; stride[ns] = (bcast & LMPC_BCAST_DISTURBANCE) ? 0 : nd; ns++; }
+  if (nuprev > 0) { seg[ns] = uprev; len[ns] = nuprev; stride[ns] = (bcast & LMPC_BCAST_UPREV) ? 0 : nuprev; ns++; }
+  if (is_device_ptr(state)) {
+    ThetaSegs th;
+    memset(&th, 0, sizeof(th));
+    th.nseg = ns;
+    for (int g = 0; g < ns; ++g) { th.ptr[g] = seg[g]; th.len[g] = len[g]; th.stride[g] = stride[g]; }
+    std::lock_guard<std::mutex> lock(h->mu);
+    int32_t *fl = exitflag;
+    if (!fl) {        // flags stay on the device: scratch in slot 0
+      if (h->slots[0].flag.reserve((size_t)N * 4)) return LMPC_E_CUDA;
+      fl = (int32_t *)h->slots[0].flag.p;
+    }
+    SolveOut o{control, fl, nullptr, nullptr, nullptr};
+    int rc = run_kernel(h, th, N, o, nullptr, h->stream);
+    if (rc) return rc;
+    if (n_failed) {
+      if (h->counter.reserve(8)) return LMPC_E_CUDA;
+      CUDA_OK(cudaMemsetAsync(h->counter.p, 0, 8, h->stream));
+      int e = launch_count_failed(fl, N, (unsigned long long *)h->counter.p, h->stream);
+      if (e) return set_err(LMPC_E_CUDA, "count kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+      g_launches.fetch_add(1);
+      unsigned long long cnt = 0;
+      CUDA_OK(cudaMemcpyAsync(&cnt, h->counter.p, 8, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      *n_failed = (int64_t)cnt;
+      return 0;
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  return solve_segments_host(h, seg, len, stride, ns, N, control, l.nu, exitflag, nullptr, nullptr, nullptr, false,
+                             n_failed);
 }
 
 int lmpc_gpu_simulate_batch(lmpc_handle *h, const double *F, const double *G, const double *Gd,
@@ -718,6 +791,35 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
 // ---------------------------------------------------------------------------------------
 // explicit MPC
 // ---------------------------------------------------------------------------------------
+int lmpc_gpu_create_bst_oriented(const double *halfplanes, int32_t n_hp, const double *feedbacks,
+                                 int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
+                                 int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
+                                 int32_t le_child, int device, lmpc_bst **out) {
+  if (!hp_list || !jump_list || n_nodes <= 0 || (le_child != 0 && le_child != 1))
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_create_bst_oriented: bad argument%s");
+  if (le_child == 0)
+    return lmpc_gpu_create_bst(halfplanes, n_hp, feedbacks, n_fb, hp_list, jump_list, n_nodes, clipping, nth, nu,
+                               device, out);
+  // The producer walks to next + 1 when a'theta <= b.  Normalise to this library's convention (<= goes to
+  // `next`) by exchanging the two children of every internal node: they are adjacent entries, so the
+  // exchange is a swap of (hp, jump) with the relative jumps corrected by the one slot each entry moved.
+  std::vector<int32_t> hp(hp_list, hp_list + n_nodes), jp(jump_list, jump_list + n_nodes);
+  std::vector<char> seen(n_nodes, 0);
+  for (int i = 0; i < n_nodes; ++i) {
+    const int j = jump_list[i];
+    if (j == 0) continue;
+    const int c0 = i + j, c1 = c0 + 1;
+    if (j < 0 || c1 >= n_nodes || seen[c0] || seen[c1])
+      return set_err(LMPC_E_INVALID, "bst: not a tree (child out of range or shared by two parents)%s");
+    seen[c0] = seen[c1] = 1;
+    if (jump_list[c0] == 1) return set_err(LMPC_E_INVALID, "bst: a node's children overlap its sibling%s");
+    hp[c0] = hp_list[c1]; jp[c0] = jump_list[c1] ? jump_list[c1] + 1 : 0;
+    hp[c1] = hp_list[c0]; jp[c1] = jump_list[c0] ? jump_list[c0] - 1 : 0;
+  }
+  return lmpc_gpu_create_bst(halfplanes, n_hp, feedbacks, n_fb, hp.data(), jp.data(), n_nodes, clipping, nth, nu,
+                             device, out);
+}
+
 int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *feedbacks,
                         int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
                         int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
@@ -997,6 +1099,136 @@ int lmpc_gpu_solve_batch_multi(lmpc_multi *m, const double *Theta, int64_t N, do
   for (auto &t : th) t.join();
   for (int g = 0; g < G; ++g)
     if (rc[g]) return set_err(rc[g], "device worker: %s", msg[g].c_str());
+  return 0;
+}
+
+// run f(g, lo, hi) for the contiguous range of every device on its own thread; first error wins
+extern "C++" {
+template <class Fn>
+static int for_each_device(int G, int64_t N, Fn f) {
+  std::vector<int> rc(G, 0);
+  std::vector<std::string> msg(G);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g) {
+    const int64_t lo = N * g / G, hi = N * (g + 1) / G;
+    th.emplace_back([=, &rc, &msg]() {
+      if (hi <= lo) return;
+      rc[g] = f(g, lo, hi);
+      if (rc[g]) msg[g] = g_err;
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rc[g]) return set_err(rc[g], "device worker: %s", msg[g].c_str());
+  return 0;
+}
+}  // extern "C++"
+
+int lmpc_gpu_simulate_batch_multi(lmpc_multi *m, const double *F, const double *G, const double *Gd,
+                                  int32_t nx, int32_t nr, int32_t nd, int32_t nuprev,
+                                  const double *X0, const double *R, const double *D, const double *U0,
+                                  const lmpc_sim_ext *ext, int64_t N, int32_t T, int32_t warm_start,
+                                  double *Xend, double *Ulast, double *Utraj,
+                                  int32_t *exitflag, int32_t *iters) {
+  if (!m || m->h.empty() || !X0 || !Xend || !Ulast || !exitflag || N < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_simulate_batch_multi: bad argument%s");
+  const int nu = m->h[0]->lay.nu;
+  return for_each_device((int)m->h.size(), N, [=](int g, int64_t lo, int64_t hi) {
+    lmpc_sim_ext e;
+    memset(&e, 0, sizeof(e));
+    if (ext) e = *ext;
+    if (e.Xhat_end) e.Xhat_end += lo * nx;
+    return lmpc_gpu_simulate_batch_ex(m->h[g], F, G, Gd, nx, nr, nd, nuprev, X0 + lo * nx, R ? R + lo * nr : nullptr,
+                                      D ? D + lo * nd : nullptr, U0 ? U0 + lo * nuprev : nullptr, &e, hi - lo, T,
+                                      warm_start, Xend + lo * nx, Ulast + lo * nu,
+                                      Utraj ? Utraj + lo * nu * T : nullptr, exitflag + lo, iters ? iters + lo : nullptr);
+  });
+}
+
+struct lmpc_bst_multi {
+  std::vector<lmpc_bst *> t;
+  int nth = 0, nu = 0;
+};
+
+int lmpc_gpu_create_bst_multi(const double *halfplanes, int32_t n_hp, const double *feedbacks,
+                              int32_t n_fb, const int32_t *hp_list, const int32_t *jump_list,
+                              int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
+                              const int32_t *devices, int32_t n_devices, lmpc_bst_multi **out) {
+  if (!out || n_devices <= 0) return set_err(LMPC_E_INVALID, "lmpc_gpu_create_bst_multi: bad argument%s");
+  *out = nullptr;
+  lmpc_bst_multi *m = new lmpc_bst_multi();
+  m->nth = nth; m->nu = nu;
+  for (int i = 0; i < n_devices; ++i) {
+    lmpc_bst *t = nullptr;
+    const int rc = lmpc_gpu_create_bst(halfplanes, n_hp, feedbacks, n_fb, hp_list, jump_list, n_nodes, clipping, nth,
+                                       nu, devices ? devices[i] : i, &t);
+    if (rc != 0) { lmpc_gpu_destroy_bst_multi(m); return rc; }
+    m->t.push_back(t);
+  }
+  *out = m;
+  return 0;
+}
+
+int lmpc_gpu_destroy_bst_multi(lmpc_bst_multi *m) {
+  if (!m) return 0;
+  for (auto *x : m->t) lmpc_gpu_destroy_bst(x);
+  delete m;
+  return 0;
+}
+
+int lmpc_gpu_evaluate_batch_multi(lmpc_bst_multi *m, const double *Theta, int64_t N, double *U, int32_t *region) {
+  if (!m || m->t.empty() || !Theta || !U || N < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_evaluate_batch_multi: bad argument%s");
+  const int nth = m->nth, nu = m->nu;
+  return for_each_device((int)m->t.size(), N, [=](int g, int64_t lo, int64_t hi) {
+    return lmpc_gpu_evaluate_batch(m->t[g], Theta + lo * nth, hi - lo, U + lo * nu, region ? region + lo : nullptr);
+  });
+}
+
+// ---------------------------------------------------------------------------------------
+// result window: the final gather fused into the solve kernel's own stores (CUDA IPC + NVLink)
+// ---------------------------------------------------------------------------------------
+int lmpc_gpu_window_create(int device, size_t bytes, void **devptr, unsigned char handle[64]) {
+  if (!devptr || !handle || bytes == 0) return set_err(LMPC_E_INVALID, "lmpc_gpu_window_create: bad argument%s");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  int sm = 0;
+  int rc = check_device(device, &sm);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  void *p = nullptr;
+  CUDA_OK(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return set_err(LMPC_E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+  memcpy(handle, &hd, 64);
+  *devptr = p;
+  return 0;
+}
+
+int lmpc_gpu_window_open(int device, const unsigned char handle[64], void **devptr) {
+  if (!devptr || !handle) return set_err(LMPC_E_INVALID, "lmpc_gpu_window_open: bad argument%s");
+  int sm = 0;
+  int rc = check_device(device, &sm);
+  if (rc) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  void *p = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  *devptr = p;
+  return 0;
+}
+
+int lmpc_gpu_window_read(void *dst_host, const void *devptr, size_t bytes) {
+  if (!dst_host || !devptr) return set_err(LMPC_E_INVALID, "lmpc_gpu_window_read: bad argument%s");
+  CUDA_OK(cudaMemcpy(dst_host, devptr, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int lmpc_gpu_window_close(void *devptr, int owner) {
+  if (!devptr) return 0;
+  if (owner) CUDA_OK(cudaFree(devptr));
+  else CUDA_OK(cudaIpcCloseMemHandle(devptr));
   return 0;
 }
 

@@ -368,3 +368,20 @@ int launch_fp64_peak(int iters, double *d_out, int sm_count, void *stream) {
   fp64_peak_kernel<<<sm_count * 8, 256, 0, (cudaStream_t)stream>>>(iters, d_out);
   return (int)cudaGetLastError();
 }
+
+// ---- failed-instance count: how many exit flags are < 1 (what `@assert exitflag >= 1`, src/utils.jl:46,
+// would trip on).  Lets a Monte-Carlo caller leave the 4-byte-per-solve flag array on the device. ----
+__global__ void __launch_bounds__(256) count_failed_kernel(const int32_t *__restrict__ flag, int64_t n,
+                                                           unsigned long long *counter) {
+  unsigned cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) cnt += flag[i] < 1;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(counter, (unsigned long long)cnt);
+}
+int launch_count_failed(const int32_t *flag, int64_t n, unsigned long long *counter, void *stream) {
+  if (n <= 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_failed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(flag, n, counter);
+  return (int)cudaGetLastError();
+}

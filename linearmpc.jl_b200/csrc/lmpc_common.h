@@ -121,3 +121,5 @@ int launch_bst_sim(const BstDev &t, const double *dyn, int nx, int nr, int nd, i
                    const double *R, const double *D, const double *U0, const double *Rtraj, const double *Dtraj,
                    int64_t N, int T, double *Xend, double *Ulast, double *Utraj, int sm_count, void *stream);
 int launch_fp64_peak(int iters, double *d_out, int sm_count, void *stream);
+// counter += number of flags < 1 (exit flags that the reference's `@assert exitflag >= 1` would trip on)
+int launch_count_failed(const int32_t *flag, int64_t n, unsigned long long *counter, void *stream);

@@ -95,6 +95,19 @@ def load_library():
                                               vp, vp, vp]
     L.lmpc_gpu_evaluate_batch.argtypes = [vp, vp, i64, vp, vp]
     L.lmpc_gpu_evaluate_batch_async.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.lmpc_gpu_compute_control_batch_bcast.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, vp, vp]
+    L.lmpc_gpu_simulate_batch_multi.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                                i64, i32, i32, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_create_bst_oriented.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, i32, C.c_int,
+                                               C.POINTER(vp)]
+    L.lmpc_gpu_create_bst_multi.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, i32, C.POINTER(vp)]
+    L.lmpc_gpu_destroy_bst_multi.argtypes = [vp]
+    L.lmpc_gpu_evaluate_batch_multi.argtypes = [vp, vp, i64, vp, vp]
+    L.lmpc_gpu_window_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), vp]
+    L.lmpc_gpu_window_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.lmpc_gpu_window_close.argtypes = [vp, C.c_int]
+    L.lmpc_gpu_window_read.argtypes = [vp, vp, C.c_size_t]
+    L.lmpc_gpu_abi_layout.argtypes = [vp, i32]
     L.lmpc_gpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.lmpc_gpu_default_settings.argtypes = [C.POINTER(_Settings)]
     _LIB = L
@@ -430,6 +443,57 @@ class GpuMPC:
         self.uprev = U[:, -1].copy()
         return U[:, 0].copy() if single else U
 
+    def compute_control_bcast(self, x, r=None, d=None, uprev=None, want_flags=False):
+        """Monte-Carlo form (lmpc_gpu_compute_control_batch_bcast): x is nx x N, every one of r / d / uprev
+        that is a VECTOR is shared by all instances and uploaded once; matrices are per instance.
+        Returns (U nu x N, exitflag or None, number of instances with exitflag < 1)."""
+        nx, nr, nd, nup = self.dims
+        dev = hasattr(x, "data_ptr")
+        if dev:
+            import torch
+            N = x.numel() // nx
+            U = torch.empty((N, self.nu), dtype=torch.float64, device=x.device)
+            flag = torch.empty(N, dtype=torch.int32, device=x.device) if want_flags else None
+            X = x
+        else:
+            X = _colmajor(x, nx)
+            N = X.shape[1]
+            U = np.zeros((self.nu, N), order="F")
+            flag = np.zeros(N, np.int32) if want_flags else None
+        mask, blocks = 0, []
+        for bit, v, rows in ((1, r, nr), (2, d, nd), (4, uprev if uprev is not None else self.uprev, nup)):
+            if rows == 0:
+                blocks.append(None)
+                continue
+            if v is None:
+                v = np.zeros(rows)
+            if hasattr(v, "data_ptr"):
+                if v.numel() == rows:
+                    mask |= bit
+                blocks.append(v)
+                continue
+            v = np.asarray(v, float)
+            if v.ndim == 1 or v.shape[1] == 1:
+                if v.size != rows:
+                    raise ValueError(f"vector length ({v.size}) must match ({rows})")
+                mask |= bit
+                v = np.ascontiguousarray(v.reshape(rows))
+                if dev:
+                    import torch
+                    v = torch.as_tensor(v, device=x.device)
+                blocks.append(v)
+            else:
+                if v.shape != (rows, N):
+                    raise ValueError(f"matrix must be {rows} x {N}")
+                if dev:
+                    raise ValueError("per-instance blocks must be device tensors when x is one")
+                blocks.append(np.asfortranarray(v))
+        nfail = C.c_int64(0)
+        _check(lib().lmpc_gpu_compute_control_batch_bcast(self._h, _ptr(U), _ptr(X), _ptr(blocks[0]), _ptr(blocks[1]),
+                                                          _ptr(blocks[2]), nr, nd, nup, N, mask, _ptr(flag),
+                                                          C.addressof(nfail)))
+        return (U.T if dev else U), flag, int(nfail.value)
+
     def compute_control_c(self, control, state, reference=None, disturbance=None):
         """Batched twin of the generated mpc_compute_control(control, state, reference,
         disturbance) (codegen/mpc_update_qp.h:3-7): `control` (nu x N) is in/out."""
@@ -578,10 +642,67 @@ class MultiGpuMPC(GpuMPC):
                                                 _ptr(iters), _ptr(au), _ptr(al)))
         return dict(U=U, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
 
+    def simulate(self, F, G, x0, r=None, d=None, u0=None, N=100, Gd=None, warm_start=True):
+        """N_traj closed loops split over the devices (lmpc_gpu_simulate_batch_multi): constant r / d per loop."""
+        nx, nr, nd, nup = self.dims
+        X0 = _colmajor(x0, nx)
+        n = X0.shape[1]
+        def bc(v, rows):
+            if rows == 0:
+                return None
+            if v is None:
+                return np.zeros((rows, n), order="F")
+            v = np.asarray(v, float)
+            return np.asfortranarray(np.repeat(v.reshape(rows, 1), n, axis=1) if v.ndim == 1 else v)
+        Rm, Dm, Um = bc(r, nr), bc(d, nd), (bc(u0, nup) if u0 is not None else None)
+        Fm, Gm = np.asfortranarray(np.asarray(F, float)), np.asfortranarray(np.asarray(G, float).reshape(nx, -1))
+        Gdm = np.asfortranarray(np.asarray(Gd, float).reshape(nx, -1)) if (nd > 0 and Gd is not None) else None
+        Xend, Ulast = np.zeros((nx, n), order="F"), np.zeros((self.nu, n), order="F")
+        flag, iters = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        _check(lib().lmpc_gpu_simulate_batch_multi(self._mh, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nd, nup,
+                                                   _ptr(X0), _ptr(Rm), _ptr(Dm), _ptr(Um), None, n, int(N),
+                                                   int(bool(warm_start)), _ptr(Xend), _ptr(Ulast), None,
+                                                   _ptr(flag), _ptr(iters)))
+        return dict(Xend=Xend, Ulast=Ulast, exitflag=flag, iters=iters)
+
     def close(self):
         if getattr(self, "_mh", None):
             lib().lmpc_gpu_destroy_multi(self._mh)
             self._mh = None
+
+    __del__ = close
+
+
+class ResultWindow:
+    """The final result gather fused into the solve (lmpc_gpu_window_*): a device buffer on one GPU that the
+    other processes of the box map through CUDA IPC; a rank passes `ptr + its byte offset` as the U / flag
+    output of solve_async and its kernel's stores land in the gathered array over NVLink."""
+
+    def __init__(self, device, nbytes=None, handle=None):
+        self.owner = handle is None
+        self.device = device
+        p = C.c_void_p()
+        if self.owner:
+            self.handle = (C.c_ubyte * 64)()
+            _check(lib().lmpc_gpu_window_create(device, int(nbytes), C.byref(p), self.handle))
+        else:
+            self.handle = (C.c_ubyte * 64)(*bytes(handle))
+            _check(lib().lmpc_gpu_window_open(device, self.handle, C.byref(p)))
+        self.ptr = p.value
+
+    def handle_bytes(self):
+        return bytes(self.handle)
+
+    def read(self, offset, shape, dtype):
+        """host copy of part of the window"""
+        out = np.empty(shape, dtype)
+        _check(lib().lmpc_gpu_window_read(out.ctypes.data, self.ptr + int(offset), out.nbytes))
+        return out
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().lmpc_gpu_window_close(self.ptr, int(self.owner))
+            self.ptr = None
 
     __del__ = close
 
@@ -593,7 +714,11 @@ class GpuExplicitMPC:
     hp_list / jump_list: node arrays (0-based; jump 0 = leaf); clipping: nu x 2 or None.
     """
 
-    def __init__(self, halfplanes, feedbacks, hp_list, jump_list, clipping=None, dims=None, device=0):
+    def __init__(self, halfplanes, feedbacks, hp_list, jump_list, clipping=None, dims=None, device=0,
+                 le_child=0, devices=None):
+        """le_child: the child taken when a'theta <= b (0: `next`, this library's and its builder's
+        convention; 1: `next + 1`, see lmpc_gpu_create_bst_oriented).  devices: a list builds one replica
+        per GPU (lmpc_gpu_create_bst_multi; host batches only, le_child must be 0)."""
         hp = np.ascontiguousarray(halfplanes, np.float64)          # row-major n_hp x ld == col-major ld x n_hp
         fb = np.ascontiguousarray(feedbacks, np.float64)           # n_fb x nu x ld: block r col-major ld x nu
         self.nth = hp.shape[1] - 1 if hp.size else fb.shape[2] - 1
@@ -605,13 +730,28 @@ class GpuExplicitMPC:
         self.dims = dims
         self.uprev = np.zeros(self.nu)
         self._t = C.c_void_p()
-        _check(lib().lmpc_gpu_create_bst(_ptr(hp), hp.shape[0], _ptr(fb), fb.shape[0], _ptr(hl), _ptr(jl),
-                                         len(hl), _ptr(clip), self.nth, self.nu, device, C.byref(self._t)))
+        self._mt = None
+        if devices is not None:
+            if le_child != 0:
+                raise ValueError("multi-device trees take the library's own orientation (le_child = 0)")
+            dv = np.ascontiguousarray(list(devices), np.int32)
+            self._mt = C.c_void_p()
+            _check(lib().lmpc_gpu_create_bst_multi(_ptr(hp), hp.shape[0], _ptr(fb), fb.shape[0], _ptr(hl), _ptr(jl),
+                                                   len(hl), _ptr(clip), self.nth, self.nu, _ptr(dv), len(dv),
+                                                   C.byref(self._mt)))
+            self._t = None
+            return
+        _check(lib().lmpc_gpu_create_bst_oriented(_ptr(hp), hp.shape[0], _ptr(fb), fb.shape[0], _ptr(hl), _ptr(jl),
+                                                  len(hl), _ptr(clip), self.nth, self.nu, int(le_child), device,
+                                                  C.byref(self._t)))
 
     def close(self):
         if getattr(self, "_t", None) is not None and self._t:
             lib().lmpc_gpu_destroy_bst(self._t)
             self._t = None
+        if getattr(self, "_mt", None) is not None and self._mt:
+            lib().lmpc_gpu_destroy_bst_multi(self._mt)
+            self._mt = None
 
     def __del__(self):
         try:
@@ -631,7 +771,10 @@ class GpuExplicitMPC:
         N = Th.shape[1]
         U = np.zeros((self.nu, N), order="F")
         reg = np.zeros(N, np.int32) if want_region else None
-        _check(lib().lmpc_gpu_evaluate_batch(self._t, _ptr(Th), N, _ptr(U), _ptr(reg)))
+        if self._mt is not None:
+            _check(lib().lmpc_gpu_evaluate_batch_multi(self._mt, _ptr(Th), N, _ptr(U), _ptr(reg)))
+        else:
+            _check(lib().lmpc_gpu_evaluate_batch(self._t, _ptr(Th), N, _ptr(U), _ptr(reg)))
         return U, reg
 
     def evaluate_async(self, Theta_dev, U_dev, region_dev=None, N=None, stream=None):

@@ -138,7 +138,7 @@ class OracleProblem:
         return r["U"][:, 0], int(r["flag"][0]), r
 
     def simulate_batch(self, Fx, Gx, Gdx, X0, R, D, U0, T, nr, nd, nuprev, warm=False,
-                       nthreads=0, want_traj=False, Rtraj=None, Dtraj=None, ext=None):
+                       nthreads=0, want_traj=False, Rtraj=None, Dtraj=None, ext=None, want_flops=False):
         """Rtraj (nr x T) / Dtraj (nd x T): trajectories shared by all closed loops (override R / D).
         ext: dict with any of Ft, Gt, Gdt (true plant), C, Dd, K (observer), Vtraj (ny x T noise)."""
         nx = Fx.shape[0]
@@ -154,6 +154,9 @@ class OracleProblem:
         iters = np.zeros(N, np.int32)
         Rt, Dt = c(Rtraj), c(Dtraj)      # T x nr, T x nd row-major == column-major nr x T
         ex, Xhat, keep = None, None, []
+        fl = np.zeros(N) if want_flops else None
+        if ext is None and want_flops:
+            ex = _SimExt(None, None, None, None, None, None, None, 0, None, 0, 0, fl.ctypes.data)
         if ext is not None:
             rm = lambda k: None if ext.get(k) is None else np.ascontiguousarray(np.asarray(ext[k], float))
             m = {k: rm(k) for k in ("Ft", "Gt", "Gdt", "C", "Dd", "K")}
@@ -163,7 +166,8 @@ class OracleProblem:
             keep = [m, V]
             vp = lambda a: None if a is None else a.ctypes.data
             ex = _SimExt(vp(m["Ft"]), vp(m["Gt"]), vp(m["Gdt"]), vp(m["C"]), vp(m["Dd"]), vp(m["K"]), vp(V),
-                         ny, vp(Xhat), int(ext.get("rstride", 0)), int(ext.get("dstride", 0)))
+                         ny, vp(Xhat), int(ext.get("rstride", 0)), int(ext.get("dstride", 0)),
+                         fl.ctypes.data if fl is not None else None)
         lib().orc_simulate_batch_ex(C.byref(self.c), nx, nr, nd, nuprev, _dp(Fx), _dp(Gx), _dp(Gdx),
                                     _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c), _dp(Rt), _dp(Dt),
                                     C.byref(ex) if ex is not None else None,
@@ -171,6 +175,8 @@ class OracleProblem:
                                     _dp(Xend), _dp(Ulast), _dp(Utraj), _ip(flag), _ip(iters),
                                     C.c_int(nthreads))
         out = dict(Xend=Xend.T, Ulast=Ulast.T, Utraj=Utraj, flag=flag, iters=iters)
+        if fl is not None:
+            out["flops"] = fl
         if Xhat is not None:
             out["Xhat_end"] = Xhat.T
         return out
@@ -180,7 +186,8 @@ class _SimExt(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("Ft", "Gt", "Gdt", "C", "Dd", "K", "Vtraj")] + [("ny", C.c_int),
                                                                                       ("Xhat_end", C.c_void_p),
                                                                                       ("rstride", C.c_int),
-                                                                                      ("dstride", C.c_int)]
+                                                                                      ("dstride", C.c_int),
+                                                                                      ("flops", C.c_void_p)]
 
 
 class OracleBst:

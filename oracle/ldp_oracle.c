@@ -484,6 +484,8 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
   const orc_sim_ext *e = s->ext;
   const int ny = e ? e->ny : 0;
   const int obs = e && e->C && e->K;
+  /* the separate true-state bookkeeping runs only when a plant / observer field is set (flops alone does not count) */
+  const int ex = e && (e->Ft || e->Gt || e->Gdt || e->C || e->K || e->Vtraj || e->Xhat_end);
   /* sliding preview windows (simulation.jl:102-104, get_preview :128-134): step t reads nr entries at t * rstride */
   const int rstride = (e && e->rstride > 0) ? e->rstride : nr, dstride = (e && e->dstride > 0) ? e->dstride : nd;
   /* true plant (defaults to the prediction model) */
@@ -493,6 +495,7 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
   double *inn = (double *)calloc(ny > 0 ? ny : 1, sizeof(double));
   for (int64_t q = lo; q < hi; ++q) {
     int worst = ORC_OPTIMAL, tot = 0;
+    double flq = 0.0;
     for (int i = 0; i < nx; ++i) x[i] = xs[i] = s->X0[q * nx + i];   /* set_state!(mpc, x0), simulation.jl:92 */
     for (int i = 0; i < nu; ++i) u[i] = (s->U0 && i < nuprev) ? s->U0[q * nuprev + i] : 0.0;
     for (int t = 0; t < s->T; ++t) {
@@ -518,12 +521,12 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
           xn[j] = acc;
         }
         for (int j = 0; j < nx; ++j) x[j] = xn[j];
-      } else if (e) {
+      } else if (ex) {
         for (int j = 0; j < nx; ++j) x[j] = xs[j];           /* the controller measures the true state */
       }
       for (int i = 0; i < nx; ++i) th[i] = x[i];
       int32_t it = 0;
-      int f = solve_with(p, w, th, u, &it, NULL, NULL, NULL, !(s->warm && t > 0));
+      int f = solve_with(p, w, th, u, &it, NULL, NULL, (e && e->flops) ? &flq : NULL, !(s->warm && t > 0));
       tot += it;
       if (f < 0) { if (worst > 0 || f < worst) worst = f; }
       else if (worst > 0 && f > worst) worst = f;
@@ -537,7 +540,7 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
         xn[i] = acc;
       }
       for (int i = 0; i < nx; ++i) x[i] = xn[i];
-      if (e) {   /* true plant step (scenario.dynamics, simulation.jl:110) */
+      if (ex) {   /* true plant step (scenario.dynamics, simulation.jl:110) */
         for (int i = 0; i < nx; ++i) {
           double acc = 0.0;
           for (int c = 0; c < nx; ++c) acc = fma(Ft[i * nx + c], xs[c], acc);
@@ -548,11 +551,12 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
         for (int i = 0; i < nx; ++i) xs[i] = xn[i];
       }
     }
-    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = e ? xs[i] : x[i];
+    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = ex ? xs[i] : x[i];
     if (e && e->Xhat_end) for (int i = 0; i < nx; ++i) e->Xhat_end[q * nx + i] = x[i];
     for (int i = 0; i < nu; ++i) s->Ulast[q * nu + i] = u[i];
     if (s->flag) s->flag[q] = worst;
     if (s->iters) s->iters[q] = tot;
+    if (e && e->flops) e->flops[q] = flq;
   }
   free(th); free(x); free(xn); free(u); free(xs); free(inn);
   work_free(w);

@@ -84,6 +84,7 @@ typedef struct {
   int ny;
   double *Xhat_end;   /* nx x N final estimates, nullable */
   int rstride, dstride;   /* > 0: step t reads its nr / nd entries at t * stride (preview windows) */
+  double *flops;          /* N: algorithmic flops of each closed loop (all T solves), nullable */
 } orc_sim_ext;
 void orc_simulate_batch_ex(const orc_problem *p, int nx, int nr, int nd, int nuprev,
                            const double *Fx, const double *Gx, const double *Gdx,
