@@ -128,6 +128,13 @@ int lmpc_gpu_host_ldp(const lmpc_problem *p, double *Mbar, double *Gram, double 
  * and the effective sense bits (m; zero rows are marked IMMUTABLE).  Pointers may be NULL. */
 int lmpc_gpu_get_info(const lmpc_handle *h, int32_t *kernel, int32_t *cap, int32_t *senses);
 
+/* CTA-per-QP controllers whose factor nearly fills an SM's shared memory (chain of masses: 129 KB) run
+ * in two passes: a first pass with two CTAs per SM and a working-set capacity `fast_cap` < capacity, then
+ * a full-capacity pass over the instances that outgrew it (results are those of the full capacity).
+ * fast_cap = 0: single pass.  redone: instances the second pass has handled on this handle's device since
+ * the process started.  Either pointer may be NULL. */
+int lmpc_gpu_get_tiering(const lmpc_handle *h, int32_t *fast_cap, int64_t *redone);
+
 /* Replaces solve(mpc, theta) + the compute_control epilogue (src/utils.jl:43-51,268-283)
  * for N parameters at once.  Theta nth x N; U nu x N receives z[1:nu] - K theta[1:nx];
  * exitflag N; iters N (nullable); active_upper/active_lower ceil(m/64) words per

@@ -358,6 +358,16 @@ int lmpc_gpu_get_info(const lmpc_handle *h, int32_t *kernel, int32_t *cap, int32
   return 0;
 }
 
+int lmpc_gpu_get_tiering(const lmpc_handle *h, int32_t *fast_cap, int64_t *redone) {
+  if (!h) return set_err(LMPC_E_INVALID, "null handle%s");
+  if (fast_cap) *fast_cap = (h->kernel == LMPC_KERNEL_CTA) ? ldp_cta_fast_cap(h->lay) : 0;
+  if (redone) {
+    cudaSetDevice(h->device);
+    *redone = (h->kernel == LMPC_KERNEL_CTA) ? (int64_t)ldp_cta_redo_count(h->device) : 0;
+  }
+  return 0;
+}
+
 void *lmpc_gpu_stream(lmpc_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 static int run_kernel(lmpc_handle *h, const ThetaSegs &th, int64_t N, const SolveOut &o,

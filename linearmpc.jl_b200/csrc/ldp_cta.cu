@@ -84,7 +84,10 @@ using BigCtx = BigCtxT<false>;
 #ifndef K3_BC_UNROLL
 #define K3_BC_UNROLL 8
 #endif
-constexpr int K3_BCU = K3_BC_UNROLL;   // unroll of the CTA-mode u / slack-scan loops (loads in flight per thread)
+constexpr int K3_BCU = K3_BC_UNROLL;
+#ifndef K3_INTERLEAVE
+#define K3_INTERLEAVE 0
+#endif   // unroll of the CTA-mode u / slack-scan loops (loads in flight per thread)
 #define PIDX(i, c) ((size_t)(i) * ((i)-1) / 2 + (c))
 #define TFOR(t) _Pragma("unroll") for (int t = 0; t < T; ++t)
 
@@ -887,15 +890,14 @@ ldp_big_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant_
 // each thread keeping the oracle's sequential accumulation order, with the Mbar / Mbar' reads
 // coalesced and unrolled so eight loads are in flight per thread.
 // ---------------------------------------------------------------------------------------------
-constexpr int CTA_THREADS = 256;
-
 struct CoopShared {
   double *shw;        // m: shifts sh_j (for equality activation / warm rows)
+  double *zs;         // cap: z = L^-1 (-d_W), kept between iterations (see "z cache" below)
   double *red_v;      // 8: per-warp scan minima
   double *red_d;      // 8: bound value of the candidate
   int *red_j;         // 8: row of the candidate (1<<30: none)
   int *red_low;       // 8
-  int *ctl;           // [0] branch (0 add / 1 remove / 2 singular), [1] exit flag or 0, [2] k, [3] iters
+  int *ctl;           // [0] branch (0 add / 1 remove / 2 singular), [1] exit flag or 0, [2] k, [3] pending add, [4] z mode
 };
 
 // Forward substitution z <- L^-1 z with the whole CTA (CTA mode, packed L): columns are taken in
@@ -904,8 +906,8 @@ struct CoopShared {
 // Every z_i still accumulates its terms in ascending column order, so the result is the same bits
 // as the single-warp sweep (and the oracle); what changes is that the O(k^2) trailing work no
 // longer sits on one warp (r01: the single-warp sweeps were ~85 % of the critical path at |W| ~ 130).
-// zs: kk values in shared memory, in/out.  Must be called by all CTA_THREADS threads.
-template <int T>
+// zs: kk values in shared memory, in/out.  Must be called by all NT threads.
+template <int NT>
 LMPC_DEVINL void coop_sweep_fwd(const BigCtx &c, double *zs, int kk) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (kk <= 1) { __syncthreads(); return; }          // always ends with a barrier (callers rely on it)
@@ -923,7 +925,7 @@ LMPC_DEVINL void coop_sweep_fwd(const BigCtx &c, double *zs, int kk) {
       if (live) zs[i] = zi;
     }
     __syncthreads();
-    for (int i = j0 + 32 + tid; i < kk; i += CTA_THREADS) {
+    for (int i = j0 + 32 + tid; i < kk; i += NT) {
       double zi = zs[i];
       const double *lrow = c.Lw + PIDX(i, j0);
 #pragma unroll 8
@@ -934,60 +936,115 @@ LMPC_DEVINL void coop_sweep_fwd(const BigCtx &c, double *zs, int kk) {
   }
 }
 
-template <int T>
-__global__ void __launch_bounds__(CTA_THREADS)
+// Backward substitution x <- L^-T x with the whole CTA, the mirror image of coop_sweep_fwd: rows are
+// taken in blocks of 32 from the bottom; warp 0 finishes the diagonal block (x_i -= L[j][i] x_j for
+// i, j inside the block, j descending), then every thread owns trailing positions i < j0 and applies
+// the block's 32 rows to them, j descending.  Each x_i accumulates j = kk-1 .. i+1 in descending
+// order exactly as the oracle's axpy loop does, so the bits are the single-warp sweep's.
+// Row j of the packed L is contiguous in i: both parts read shared memory conflict free.
+template <int NT>
+LMPC_DEVINL void coop_sweep_bwd(const BigCtx &c, double *xs, int kk) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (kk <= 1) { __syncthreads(); return; }
+  for (int j0 = ((kk - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
+    const int j1 = min(kk, j0 + 32);
+    if (warp == 0) {
+      const int i = j0 + lane;
+      const bool live = i < j1;
+      double xi = live ? xs[i] : 0.0;
+      for (int j = j1 - 1; j > j0; --j) {
+        const double xj = shfl_d(xi, j - j0);
+        if (i < j && live) xi = fma(-c.Lw[PIDX(j, i)], xj, xi);
+      }
+      if (live) xs[i] = xi;
+    }
+    __syncthreads();
+    for (int i = tid; i < j0; i += NT) {
+      double xi = xs[i];
+#pragma unroll 8
+      for (int j = j1 - 1; j >= j0; --j) xi = fma(-c.Lw[PIDX(j, i)], xs[j], xi);
+      xs[i] = xi;
+    }
+    __syncthreads();
+  }
+}
+
+// CTA-per-QP kernel.  NT threads per CTA (256: one QP per SM at full capacity; 128: two CTAs per SM
+// with a reduced capacity `cap`, overflowing instances are redone by a full-capacity pass, `redo`).
+//
+// z cache.  The CSP's forward substitution z = L^-1 (-d_W) is kept in shared memory between
+// iterations (DAQP's reuse_ind): appending a row leaves the first k rows of
+// L and d_W untouched, so after an add only the new last entry is missing -- one sequential fma chain
+// of length k on one thread, the same operations in the same order as the sweep would do for that row
+// (bit-identical), instead of an O(k^2) sweep with k serial broadcast steps.  A removal at position r
+// invalidates the entries from r on; the chain of masses removes in < 1 % of its iterations.
+template <int T, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 128) ? 2 : 1)
 ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
-               const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out) {
+               const double *__restrict__ cblk, ThetaSegs th, int64_t Ninst, SolveOut out, int cap, int redo,
+               unsigned long long *redo_count) {
+  constexpr int RH = (512 + NT - 1) / NT;      // rows per thread (m <= 512)
+  constexpr int CH = (256 + NT - 1) / NT;      // columns per thread (n <= 256)
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t mbar;
-  const int soff = small_off(lay);
-  stage_constants_tma(smem, cblk + soff, lay.total - soff, &mbar);
+  __shared__ __align__(8) uint64_t mbar[2];
+  // shared-memory constants: du, dl (contiguous from odu) and Uth, uoff, sense (contiguous from oUth);
+  // Dth and R^-1 are read once per QP and stay in global memory / L2
+  const int nA = lay.oRinv - lay.odu, nB = lay.total - lay.oUth;
+  stage_constants_tma(smem, cblk + lay.odu, nA, &mbar[0]);
+  stage_constants_tma(smem + nA, cblk + lay.oUth, nB, &mbar[1]);
   BigCtx c;
   c.LS = 0;
   c.M = cblk + lay.oM; c.MT = cblk + lay.oMT; c.G = cblk + lay.oG;
-  const double *sb = smem - soff;
   c.cv.M = c.M; c.cv.MT = c.MT; c.cv.G = c.G;
-  c.cv.Dth = sb + lay.oDth; c.cv.du = sb + lay.odu; c.cv.dl = sb + lay.odl; c.cv.Rinv = sb + lay.oRinv;
-  c.cv.Uth = sb + lay.oUth; c.cv.uoff = sb + lay.ouoff;
-  c.cv.sense = reinterpret_cast<const int32_t *>(sb + lay.oSense);
+  c.cv.Dth = cblk + lay.oDth; c.cv.Rinv = cblk + lay.oRinv;
+  c.cv.du = smem; c.cv.dl = smem + (lay.odl - lay.odu);
+  c.cv.Uth = smem + nA; c.cv.uoff = smem + nA + (lay.ouoff - lay.oUth);
+  c.cv.sense = reinterpret_cast<const int32_t *>(smem + nA + (lay.oSense - lay.oUth));
   c.lay = &lay; c.st = &st;
   const int tid = threadIdx.x, warp = tid >> 5;
   c.lane = tid & 31;
-  const int cap = lay.cap, n = lay.n, m = lay.m, mp = lay.mp, nth = lay.nth;
-  double *w = smem + (lay.total - soff);
+  const int n = lay.n, m = lay.m, mp = lay.mp, nth = lay.nth;
+  double *w = smem + nA + nB;
   c.Lw = w; w += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
   c.uw = w; w += (n + 1) & ~1;
   c.thw = w; w += (nth + 1) & ~1;
   c.lamw = w; w += (cap + 1) & ~1;
   CoopShared cs;
   cs.shw = w; w += (m + 1) & ~1;
+  cs.zs = w; w += (cap + 1) & ~1;
   cs.red_v = w; w += 8;
   cs.red_d = w; w += 8;
   cs.red_j = reinterpret_cast<int *>(w); w += 4;
   cs.red_low = reinterpret_cast<int *>(w); w += 4;
-  cs.ctl = reinterpret_cast<int *>(w); w += 2;
+  cs.ctl = reinterpret_cast<int *>(w); w += 4;
   c.roww = reinterpret_cast<int *>(w); w += (cap + 1) / 2 + 1;
   c.inwsb = reinterpret_cast<unsigned char *>(w);
   const int lane = c.lane, words = (m + 63) >> 6;
   BigQp<T> s;          // meaningful in warp 0 only
   double u[T];
   for (int64_t q = blockIdx.x; q < Ninst; q += gridDim.x) {
-    // theta, shifts (thread j <-> rows j, j + 256), reset
+    if (redo) {         // second pass: only the instances the reduced-capacity pass could not hold
+      if (out.flag[q] != EXIT_CAPACITY) continue;
+      if (tid == 0 && redo_count) atomicAdd(redo_count, 1ull);
+    }
+    // theta, shifts (thread j <-> rows j, j + NT, ...), reset
     int o = 0;
 #pragma unroll
     for (int sg = 0; sg < 4; ++sg) {
       if (sg < th.nseg) {
         const int len = th.len[sg];
-        for (int t = tid; t < len; t += CTA_THREADS) c.thw[o + t] = ld_stream(th.ptr[sg] + q * th.stride[sg] + t);
+        for (int t = tid; t < len; t += NT) c.thw[o + t] = ld_stream(th.ptr[sg] + q * th.stride[sg] + t);
         o += len;
       }
     }
-    for (int j = tid; j < m; j += CTA_THREADS) c.inwsb[j] = 0;
+    for (int j = tid; j < m; j += NT) c.inwsb[j] = 0;
     __syncthreads();
-    double shr[2] = {0.0, 0.0};
+    double shr[RH];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = tid + CTA_THREADS * h;
+    for (int h = 0; h < RH; ++h) {
+      shr[h] = 0.0;
+      const int j = tid + NT * h;
       if (j < m) {
         const double *dr = c.cv.Dth + (size_t)j * nth;
         double acc = 0.0;
@@ -998,7 +1055,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     }
     if (tid == 0) { cs.ctl[1] = 0; cs.ctl[3] = 0; }
     __syncthreads();
-    int flag = EXIT_ITERLIMIT, iter = 0, cycle = 0;
+    int flag = EXIT_ITERLIMIT, iter = 0, cycle = 0, zvalid = 0;
     bool repaired = false;
     double best_fval = -1.0, fval = 0.0, soft_slack = 0.0;
     if (warp == 0) {
@@ -1031,28 +1088,46 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
     bool pend_low = false;
     double pend_d = 0.0;
     for (iter = 1; !dead && iter < st.iter_limit; ++iter) {
-      // ---- phase A: CSP (forward sweep by the whole CTA, the rest on warp 0), blocking test ------
+      // ---- phase A: CSP.  z from the cache (chain for one new row, cooperative sweep otherwise), then
+      //      lam* = L^-T (z / D) by the whole CTA, blocking test on warp 0 ------------------------------
       double a[T];
       bool blk[T];
       if (warp == 0) {
         TFOR(t) { a[t] = CUDART_INF; blk[t] = false; }
-        if (!s.sing) { TFOR(t) { const int i = lane + 32 * t; if (i < s.k) c.lamw[i] = -s.dW[t]; } }
-        if (lane == 0) { cs.ctl[0] = s.sing ? 2 : 0; cs.ctl[2] = s.k; }
+        int zmode = 0;                               // 0: cache complete, 1: last entry missing, 2: recompute
+        if (!s.sing && zvalid < s.k) {
+          zmode = (zvalid == s.k - 1) ? 1 : 2;
+          TFOR(t) { const int i = lane + 32 * t; if (i < s.k && (zmode == 2 || i == s.k - 1)) cs.zs[i] = -s.dW[t]; }
+        }
+        if (lane == 0) { cs.ctl[0] = s.sing ? 2 : 0; cs.ctl[2] = s.k; cs.ctl[4] = zmode; }
       }
       __syncthreads();
       {
-        const int not_sing = cs.ctl[0] != 2, kk = cs.ctl[2];              // read before warp 0 rewrites them
-        if (not_sing) coop_sweep_fwd<T>(c, c.lamw, kk);                   // ends with a __syncthreads
-        else __syncthreads();
+        const int not_sing = cs.ctl[0] != 2, kk = cs.ctl[2], zmode = cs.ctl[4];   // read before warp 0 rewrites them
+        if (not_sing && zmode == 2) coop_sweep_fwd<NT>(c, cs.zs, kk);             // ends with a __syncthreads
+        else {
+          if (not_sing && zmode == 1 && tid == 0) {
+            const int i = kk - 1;
+            double acc = cs.zs[i];
+            const double *lrow = c.Lw + PIDX(i, 0);
+#pragma unroll 8
+            for (int cc = 0; cc < i; ++cc) acc = fma(-lrow[cc], cs.zs[cc], acc);
+            cs.zs[i] = acc;
+          }
+          __syncthreads();
+        }
+        if (warp == 0 && not_sing) {
+          TFOR(t) { const int i = lane + 32 * t; if (i < kk) c.lamw[i] = cs.zs[i] * s.Dinv[t]; }
+          zvalid = kk;
+        }
+        __syncthreads();
+        if (not_sing) coop_sweep_bwd<NT>(c, c.lamw, kk);                          // ends with a __syncthreads
       }
       if (warp == 0) {
         const int k = s.k;
         int branch;
         if (!s.sing) {
-          double z[T];
-          TFOR(t) { const int i = lane + 32 * t; z[t] = (i < k) ? c.lamw[i] : 0.0; }
-          TFOR(t) s.lams[t] = (lane + 32 * t < k) ? z[t] * s.Dinv[t] : 0.0;
-          sweep_bwd<T>(c, s.lams, k);
+          TFOR(t) { const int i = lane + 32 * t; s.lams[t] = (i < k) ? c.lamw[i] : 0.0; }
           bool anyblk = false;
           TFOR(t) {
             const bool low = (s.low >> t) & 1u, imm = (s.imm >> t) & 1u;
@@ -1060,8 +1135,6 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
             anyblk |= blk[t];
           }
           branch = __any_sync(FULL, anyblk) ? 1 : 0;
-          __syncwarp();
-          if (branch == 0) { TFOR(t) { const int i = lane + 32 * t; if (i < k) c.lamw[i] = s.lams[t]; } }
         } else {
           branch = 2;
         }
@@ -1071,28 +1144,79 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
       const int branch = cs.ctl[0], k = cs.ctl[2];
       if (branch == 0) {
         // ---- phase B (all threads): u_c = -sum_i lam*_i Mbar[row_i][c], sequential in i ----------
-        if (tid < n) {
-          double uc = 0.0;
-          const double *mcol = c.M + tid;
+        // (a thread's CH columns run as independent chains inside one loop over i: their loads overlap)
+        {
+          double uc[CH];
+          const double *mcol[CH];
+#pragma unroll
+          for (int h = 0; h < CH; ++h) { uc[h] = 0.0; mcol[h] = c.M + min(tid + NT * h, n - 1); }
+          const int nmine = (n - tid + NT - 1) / NT;          // columns this thread owns (<= CH)
+          if (K3_INTERLEAVE && nmine >= 2) {
 #pragma unroll K3_BCU
-          for (int i = 0; i < k; ++i) uc = fma(-c.lamw[i], mcol[c.roww[i] * n], uc);
-          c.uw[tid] = uc;
+            for (int i = 0; i < k; ++i) {
+              const double li = -c.lamw[i];
+              const int ro = c.roww[i] * n;
+#pragma unroll
+              for (int h = 0; h < CH; ++h) uc[h] = fma(li, mcol[h][ro], uc[h]);
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+              if (h < nmine) {
+#pragma unroll K3_BCU
+                for (int i = 0; i < k; ++i) uc[h] = fma(-c.lamw[i], mcol[h][c.roww[i] * n], uc[h]);
+              }
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < CH; ++h) { const int cc = tid + NT * h; if (cc < n) c.uw[cc] = uc[h]; }
         }
         __syncthreads();
-        // ---- phase C (all threads): slack of rows tid, tid + 256, sequential in c ---------------
+        // ---- phase C (all threads): slack of rows tid, tid + NT, ..., sequential in c ------------
         double best = CUDART_INF, bestd = 0.0;
         int bestj = 1 << 30, bestlow = 0;
+        // a simple row j is a normalised row of the upper-triangular R^-1: exact zeros before column j,
+        // so its sum may start at any column <= j (fma(0, u, mu) == mu).  A thread's rows run as
+        // independent chains inside one loop over the columns, from the first row's start.
+        double mus[RH];
+        {
+          const int nmine = (m - tid + NT - 1) / NT;          // rows this thread owns (<= RH)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = tid + CTA_THREADS * h;
-          if (j < m) {
-            double mu = 0.0;
-            // a simple row j is a normalised row of the upper-triangular R^-1: exact zeros before
-            // column j, so the sum may start there (fma(0, u, mu) == mu)
-            const int c0 = (j < lay.ms) ? j : 0;
-            const double *mt = c.MT + j + c0 * mp;
+          for (int h = 0; h < RH; ++h) mus[h] = 0.0;
+          if (nmine >= 1) {
+            // start at the first row's own column only when every row of this thread is a simple row
+            const int c0 = (tid + NT * (nmine - 1) < lay.ms) ? tid : 0;
+            const double *mt = c.MT + tid + c0 * mp;
+            if (nmine == 1) {
 #pragma unroll K3_BCU
-            for (int cc = c0; cc < n; ++cc) { mu = fma(*mt, c.uw[cc], mu); mt += mp; }
+              for (int cc = c0; cc < n; ++cc) { mus[0] = fma(*mt, c.uw[cc], mus[0]); mt += mp; }
+            } else if (!K3_INTERLEAVE) {
+#pragma unroll
+              for (int h = 0; h < RH; ++h) {
+                if (h < nmine) {
+                  const int j = tid + NT * h;
+                  const int cj = (j < lay.ms) ? j : 0;
+                  const double *mj = c.MT + j + cj * mp;
+#pragma unroll K3_BCU
+                  for (int cc = cj; cc < n; ++cc) { mus[h] = fma(*mj, c.uw[cc], mus[h]); mj += mp; }
+                }
+              }
+            } else {
+#pragma unroll K3_BCU
+              for (int cc = c0; cc < n; ++cc) {
+                const double ucc = c.uw[cc];
+#pragma unroll
+                for (int h = 0; h < RH; ++h) { if (h < nmine) mus[h] = fma(mt[min(NT * h, mp - 1 - tid)], ucc, mus[h]); }
+                mt += mp;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < RH; ++h) {
+          const int j = tid + NT * h;
+          if (j < m) {
+            const double mu = mus[h];
             if (!c.inwsb[j] && !(c.cv.sense[j] & S_IMMUTABLE)) {
               const double dU = c.cv.du[j] + shr[h], dLo = c.cv.dl[j] + shr[h];
               const double su = dU - mu, sl = mu - dLo;
@@ -1132,8 +1256,8 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           int done = 0;
           if (fval > st.fval_bound) done = EXIT_INFEASIBLE;
           else {
-            const double v = (lane < 8) ? cs.red_v[lane] : CUDART_INF;
-            const int jl = (lane < 8) ? cs.red_j[lane] : (1 << 30);
+            const double v = (lane < NW) ? cs.red_v[lane] : CUDART_INF;
+            const int jl = (lane < NW) ? cs.red_j[lane] : (1 << 30);
             const double vmin = bfly_min(v);
             const int add = bfly_min_i((v == vmin && jl < (1 << 30)) ? jl : (1 << 30));
             if (add == (1 << 30)) done = soft_slack > st.primal_tol ? EXIT_SOFT_OPTIMAL : EXIT_OPTIMAL;
@@ -1147,12 +1271,12 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
               }
               if (!done && (k >= cap || k >= 32 * T)) done = EXIT_CAPACITY;
               if (!done) {
-                const unsigned own = __ballot_sync(FULL, lane < 8 && jl == add && v == vmin);
+                const unsigned own = __ballot_sync(FULL, lane < NW && jl == add && v == vmin);
                 const int src = __ffs(own) - 1;
-                const bool addlow = __shfl_sync(FULL, (lane < 8) ? cs.red_low[lane] : 0, src) != 0;
-                const double addd = shfl_d((lane < 8) ? cs.red_d[lane] : 0.0, src);
+                const bool addlow = __shfl_sync(FULL, (lane < NW) ? cs.red_low[lane] : 0, src) != 0;
+                const double addd = shfl_d((lane < NW) ? cs.red_d[lane] : 0.0, src);
                 TFOR(t) if (lane + 32 * t < k) s.lam[t] = s.lams[t];
-                if (rebuilt) done = bq_rebuild<T>(c, s);
+                if (rebuilt) { done = bq_rebuild<T>(c, s); zvalid = 0; }
                 if (!done) {
                   // right-hand side of the add's forward sweep: the Gram column of the new row
                   const double *g = c.G + (size_t)add * m;
@@ -1168,11 +1292,12 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
         __syncthreads();
         const int do_add = cs.ctl[3];
         if (do_add != 0) {             // the add: y = L^-1 g_W by the whole CTA, the rest on warp 0
-          coop_sweep_fwd<T>(c, c.lamw, k);
+          coop_sweep_fwd<NT>(c, c.lamw, k);
           if (warp == 0) {
             bq_add<T>(c, s, pend_add, pend_low, pend_d, c.lamw);
             if (s.sing && bq_has_soft<T>(c, s)) {
               const int rc = bq_rebuild<T>(c, s);
+              zvalid = 0;
               if (rc != 0 && lane == 0) cs.ctl[1] = rc;
             }
             if (lane == 0) cs.ctl[3] = 0;
@@ -1189,7 +1314,8 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           else {
             TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, s.lams[t] - s.lam[t], s.lam[t]);
             bq_remove<T>(c, s, rm);
-            if (s.sing && bq_has_soft<T>(c, s)) done = bq_rebuild<T>(c, s);
+            zvalid = min(zvalid, rm);
+            if (s.sing && bq_has_soft<T>(c, s)) { done = bq_rebuild<T>(c, s); zvalid = 0; }
           }
         } else {
           const int kk = k - 1;
@@ -1217,7 +1343,8 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           else {
             TFOR(t) if (lane + 32 * t < k) s.lam[t] = fma(alpha, p[t], s.lam[t]);
             bq_remove<T>(c, s, rm);
-            if (s.sing && bq_has_soft<T>(c, s)) done = bq_rebuild<T>(c, s);
+            zvalid = min(zvalid, rm);
+            if (s.sing && bq_has_soft<T>(c, s)) { done = bq_rebuild<T>(c, s); zvalid = 0; }
           }
         }
         if (lane == 0) cs.ctl[1] = done;
@@ -1258,30 +1385,82 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   }
 }
 
-size_t cta_smem(const LdpLayout &lay) {
-  const size_t cap = lay.cap;
-  size_t d = (size_t)(lay.total - lay.oDth);
-  d += (cap * (cap - 1) / 2 + 1) & ~(size_t)1;
+size_t cta_smem(const LdpLayout &lay, int cap) {
+  size_t d = (size_t)(lay.oRinv - lay.odu) + (size_t)(lay.total - lay.oUth);
+  d += ((size_t)cap * (cap - 1) / 2 + 1) & ~(size_t)1;
   d += (lay.n + 1) & ~1; d += (lay.nth + 1) & ~1; d += (cap + 1) & ~1; d += (lay.m + 1) & ~1;
-  d += 8 + 8 + 4 + 4 + 2 + (cap + 1) / 2 + 1;
+  d += (cap + 1) & ~1;
+  d += 8 + 8 + 4 + 4 + 4 + (cap + 1) / 2 + 1;
   d += (lay.m + 7) / 8 + 1;
   return d * sizeof(double);
+}
+size_t cta_smem(const LdpLayout &lay) { return cta_smem(lay, lay.cap); }
+
+// Two CTAs per SM: the largest working-set capacity whose CTA still fits twice into an SM's shared
+// memory.  Used as a first pass when it is at least 85 % of the full capacity (instances that outgrow it
+// end with EXIT_CAPACITY and are redone at full capacity by a second launch); 0 = not worth it.
+int cta_fast_cap(const LdpLayout &lay) {
+  if (lay.n > 256 || lay.m > 512) return 0;
+  const size_t budget = (227u * 1024u - 2048u) / 2;
+  int cap = lay.cap;
+  while (cap > 0 && cta_smem(lay, cap) > budget) --cap;
+  if (cap >= lay.cap) return lay.cap;            // the full problem fits twice: no second pass needed
+  return (cap * 100 >= lay.cap * 85) ? cap : 0;
+}
+
+unsigned long long *g_redo_counter(int device) {
+  static unsigned long long *ctr[64] = {nullptr};
+  if (device < 0 || device >= 64) return nullptr;
+  if (!ctr[device]) {
+    if (cudaMalloc((void **)&ctr[device], 8) != cudaSuccess) { cudaGetLastError(); ctr[device] = nullptr; return nullptr; }
+    cudaMemset(ctr[device], 0, 8);
+  }
+  return ctr[device];
+}
+
+template <int T>
+int launch_cta_full(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
+                    int64_t N, const SolveOut &out, int sm_count, cudaStream_t s, int redo) {
+  auto kern = ldp_cta_kernel<T, 256>;
+  const size_t smem = cta_smem(lay, lay.cap);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = N;
+  if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+  kern<<<(unsigned)blocks, 256, smem, s>>>(lay, st, cblk, th, N, out, lay.cap, redo, redo ? g_redo_counter(dev) : nullptr);
+  return (int)cudaGetLastError();
 }
 
 template <int T>
 int launch_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const ThetaSegs &th,
                int64_t N, const SolveOut &out, int sm_count, cudaStream_t s) {
-  auto kern = ldp_cta_kernel<T>;
-  const size_t smem = cta_smem(lay);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_THREADS, smem);
-  if (per_sm < 1) per_sm = 1;
-  int64_t blocks = N;
-  if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
-  kern<<<(unsigned)blocks, CTA_THREADS, smem, s>>>(lay, st, cblk, th, N, out);
-  return (int)cudaGetLastError();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int fast = cta_fast_cap(lay);
+  if (fast > 0) {
+    auto k2 = ldp_cta_kernel<T, 128>;
+    const size_t smem2 = cta_smem(lay, fast);
+    cudaError_t e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, 128, smem2);
+    if (per_sm >= 2) {
+      int64_t blocks = N;
+      if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
+      k2<<<(unsigned)blocks, 128, smem2, s>>>(lay, st, cblk, th, N, out, fast, 0, nullptr);
+      e = cudaGetLastError();
+      if (e != cudaSuccess || fast >= lay.cap) return (int)e;
+      // second pass at full capacity over the instances that ended with EXIT_CAPACITY
+    } else {
+      return launch_cta_full<T>(lay, st, cblk, th, N, out, sm_count, s, 0);
+    }
+    return launch_cta_full<T>(lay, st, cblk, th, N, out, sm_count, s, 1);
+  }
+  return launch_cta_full<T>(lay, st, cblk, th, N, out, sm_count, s, 0);
 }
 
 K3Geom k3_geom(const LdpLayout &lay, int extra = 0, bool sq = false) {
@@ -1349,6 +1528,19 @@ int launch_big_sim(const LdpLayout &lay, const LdpSettings &st, const double *cb
 }
 
 }  // namespace
+
+// instances redone at full capacity by the two-pass CTA path on `device` since the process started
+long long ldp_cta_redo_count(int device) {
+  unsigned long long *p = g_redo_counter(device);
+  unsigned long long v = 0;
+  if (!p || cudaMemcpy(&v, p, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return (long long)v;
+}
+// capacity of the first (two CTAs per SM) pass for this layout; 0: single pass
+int ldp_cta_fast_cap(const LdpLayout &lay) {
+  const bool coop = k3_geom(lay).warps <= 2 && cta_smem(lay) <= 220 * 1024;
+  return coop ? cta_fast_cap(lay) : 0;
+}
 
 bool ldp_cta_supports(const LdpLayout &lay) {
   if (lay.n < 1 || lay.n > 256 || lay.cap > 256 || lay.m > 512) return false;

@@ -107,6 +107,8 @@ int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cb
                    const ThetaSegs &th, int64_t N, const SolveOut &out, int sm_count, void *stream);
 bool ldp_warp_supports(const LdpLayout &lay);
 bool ldp_cta_supports(const LdpLayout &lay);
+long long ldp_cta_redo_count(int device);
+int ldp_cta_fast_cap(const LdpLayout &lay);
 
 struct BstDev {
   const double *blk;     // packed tree block on the device (layout: see bst_eval.cu)

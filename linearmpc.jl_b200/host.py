@@ -75,6 +75,7 @@ def load_library():
     L.lmpc_gpu_destroy.argtypes = [vp]
     L.lmpc_gpu_get_ldp.argtypes = [vp] * 9
     L.lmpc_gpu_get_info.argtypes = [vp, vp, vp, vp]
+    L.lmpc_gpu_get_tiering.argtypes = [vp, vp, vp]
     L.lmpc_gpu_solve_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     L.lmpc_gpu_create_multi.argtypes = [C.POINTER(_Problem), C.POINTER(_Settings), vp, i32, C.POINTER(vp)]
     L.lmpc_gpu_destroy_multi.argtypes = [vp]
@@ -332,6 +333,12 @@ class GpuMPC:
                                                  ("Mbar", "Gram", "Dth", "du", "dl", "Rinv", "Uth", "uoff")]))
         out["senses"], out["cap"] = np.array(self.senses, np.int32), int(self.cap)   # lmpc_gpu_get_info
         return out
+
+    def tiering(self):
+        """(fast_cap, redone): see lmpc_gpu_get_tiering"""
+        fc, rd = C.c_int32(0), C.c_int64(0)
+        _check(lib().lmpc_gpu_get_tiering(self._h, C.byref(fc), C.byref(rd)))
+        return int(fc.value), int(rd.value)
 
     # -- solve(mpc, theta), batched ---------------------------------------------------------
     def solve(self, Theta, want_iters=True, want_active=True):

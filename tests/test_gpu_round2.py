@@ -178,3 +178,28 @@ def test_result_window_gathers_across_processes(lmpc, tmp_path):
     assert np.array_equal(Uw[:N], ref0["U"][0]) and np.array_equal(Uw[N:], ref1["U"][0])
     assert np.array_equal(Fw[:N], ref0["flag"]) and np.array_equal(Fw[N:], ref1["flag"])
     win.close()
+
+
+def test_chain_two_pass_cta_path(lmpc):
+    """chain of masses (n = 180): first pass with two CTAs per SM at a reduced working-set capacity, second
+    pass at full capacity for the instances that outgrew it.  Results are those of the full capacity, bit
+    for bit the oracle's (z cache + cooperative backward sweep included), and the second pass really ran."""
+    mpc, qp, g, P = gpu_controller(lmpc, "chain")
+    fast_cap, before = g.tiering()
+    assert g.kernel == lmpc.KERNEL_CTA and 0.85 * g.cap <= fast_cap < g.cap
+    lo, hi = util.theta_range("chain", 1.4)            # beyond the nominal range: working sets up to ~175 rows
+    Th = mpqp.sample_theta(lo, hi, 800, seed=5)
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    for a, b in (("exitflag", "flag"), ("iters", "iters"), ("active_upper", "act_u"), ("active_lower", "act_l")):
+        assert np.array_equal(out[a], ref[b]), a
+    assert np.array_equal(out["U"], ref["U"]) and np.all(ref["flag"] == 1)
+    k = (util.bits(ref["act_u"], P.m) | util.bits(ref["act_l"], P.m)).sum(1)
+    over = int(np.count_nonzero(k > fast_cap))          # adds are never undone on this problem class
+    assert over >= 1 and g.tiering()[1] - before >= over
+    # small theta: tiny working sets, everything ends in the first pass
+    lo, hi = util.theta_range("chain", 0.25)
+    Th = mpqp.sample_theta(lo, hi, 1500, seed=6)
+    mid = g.tiering()[1]
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    assert np.array_equal(out["U"], ref["U"]) and np.array_equal(out["iters"], ref["iters"])
+    assert g.tiering()[1] == mid
