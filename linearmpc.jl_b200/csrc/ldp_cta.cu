@@ -88,6 +88,28 @@ constexpr int K3_BCU = K3_BC_UNROLL;
 #ifndef K3_INTERLEAVE
 #define K3_INTERLEAVE 0
 #endif   // unroll of the CTA-mode u / slack-scan loops (loads in flight per thread)
+// rows per TMA batch of the CTA kernel's Mbar / Mbar' stream (two batches in flight: 2 * K3_RB row slots)
+// Measured (r02, chain n = 180): a TMA bulk copy of one 1.4 KB row lands ~390 cycles after issue while the fma
+// chains consume a row every 8 cycles, so a ring that fits next to the factor (8 rows) starves: 3.3e4 solves/s
+// against 7.9e4 with direct loads.  Kept for problems whose constants leave room for a deep ring; off by default.
+#ifndef K3_TRIM_U
+#define K3_TRIM_U 0
+#endif
+#ifndef K3_USE_RING
+#define K3_USE_RING 0
+#endif
+#ifndef K3_RING_ROWS
+#define K3_RING_ROWS 4
+#endif
+constexpr int K3_RB = K3_RING_ROWS;
+LMPC_DEVINL void bulk_expect(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+LMPC_DEVINL void bulk_copy(uint64_t *bar, double *dst, const double *src, uint32_t bytes) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 #define PIDX(i, c) ((size_t)(i) * ((i)-1) / 2 + (c))
 #define TFOR(t) _Pragma("unroll") for (int t = 0; t < T; ++t)
 
@@ -988,6 +1010,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t rbar[2];     // "batch landed" barriers of the two halves of the row ring
   // shared-memory constants: du, dl (contiguous from odu) and Uth, uoff, sense (contiguous from oUth);
   // Dth and R^-1 are read once per QP and stay in global memory / L2
   const int nA = lay.oRinv - lay.odu, nB = lay.total - lay.oUth;
@@ -1018,8 +1041,22 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
   cs.red_j = reinterpret_cast<int *>(w); w += 4;
   cs.red_low = reinterpret_cast<int *>(w); w += 4;
   cs.ctl = reinterpret_cast<int *>(w); w += 4;
+  // Row ring: the two O(k n) / O(n m) phases stream rows of Mbar / Mbar' from L2 through 2 * K3_RB row slots
+  // with TMA bulk copies, one batch ahead of the fma chains that consume them (r02 ncu: those chains waited
+  // on L2 for ~55 cycles per step with 8 loads in flight; from shared memory a step costs the DFMA latency, 8).
+  // Needs 16-byte aligned rows: n even (Mbar rows) -- mp is a multiple of 4 by construction.
+  double *ring = w; w += K3_USE_RING ? 2 * K3_RB * mp : 0;
+  const bool use_ring = K3_USE_RING && (n & 1) == 0 && (mp & 1) == 0 && n <= mp;
   c.roww = reinterpret_cast<int *>(w); w += (cap + 1) / 2 + 1;
   c.inwsb = reinterpret_cast<unsigned char *>(w);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&rbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&rbar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t rph0 = 0, rph1 = 0;                  // phase parity of rbar[0] / rbar[1] (uniform over the CTA)
+  const bool boxonly = (m == lay.ms);           // every row is a (triangular) row of R^-1: copies can be trimmed
   const int lane = c.lane, words = (m + 63) >> 6;
   BigQp<T> s;          // meaningful in warp 0 only
   double u[T];
@@ -1151,7 +1188,43 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
 #pragma unroll
           for (int h = 0; h < CH; ++h) { uc[h] = 0.0; mcol[h] = c.M + min(tid + NT * h, n - 1); }
           const int nmine = (n - tid + NT - 1) / NT;          // columns this thread owns (<= CH)
-          if (K3_INTERLEAVE && nmine >= 2) {
+          if (use_ring) {
+            // batch b = working-set positions [b RB, (b+1) RB): row w_i of Mbar, trimmed to its non-zero tail
+            // [w_i & ~1, n) for a simple row (zeros before the diagonal); column c of the row sits at slot[c]
+            const int nb = (k + K3_RB - 1) / K3_RB;
+            auto issue = [&](int b) {
+              const int hf = b & 1, i0 = b * K3_RB, i1 = min(k, i0 + K3_RB);
+              uint32_t tot = 0;
+              for (int i = i0; i < i1; ++i) { const int wr = c.roww[i]; tot += (uint32_t)(n - (wr < lay.ms ? (wr & ~1) : 0)) * 8u; }
+              bulk_expect(&rbar[hf], tot);
+              for (int i = i0; i < i1; ++i) {
+                const int wr = c.roww[i], cs0 = wr < lay.ms ? (wr & ~1) : 0;
+                bulk_copy(&rbar[hf], ring + (size_t)(hf * K3_RB + (i - i0)) * mp + cs0, c.M + (size_t)wr * n + cs0,
+                          (uint32_t)(n - cs0) * 8u);
+              }
+            };
+            if (tid == 0 && nb > 0) issue(0);
+            for (int b = 0; b < nb; ++b) {
+              if (tid == 0 && b + 1 < nb) issue(b + 1);
+              if (b & 1) { tile_wait(&rbar[1], rph1); rph1 ^= 1u; } else { tile_wait(&rbar[0], rph0); rph0 ^= 1u; }
+              const double *slot = ring + (size_t)((b & 1) * K3_RB) * mp;
+              const int i0 = b * K3_RB;
+#pragma unroll
+              for (int r = 0; r < K3_RB; ++r) {
+                const int i = i0 + r;
+                if (i < k) {
+                  const double li = -c.lamw[i];
+                  const int wr = c.roww[i], cs0 = wr < lay.ms ? (wr & ~1) : 0;
+#pragma unroll
+                  for (int h = 0; h < CH; ++h) {
+                    const int cc = tid + NT * h;
+                    if (cc < n && cc >= cs0) uc[h] = fma(li, slot[r * mp + cc], uc[h]);
+                  }
+                }
+              }
+              __syncthreads();               // the half is free again (it is refilled two batches later)
+            }
+          } else if (K3_INTERLEAVE && nmine >= 2) {
 #pragma unroll K3_BCU
             for (int i = 0; i < k; ++i) {
               const double li = -c.lamw[i];
@@ -1163,8 +1236,14 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
 #pragma unroll
             for (int h = 0; h < CH; ++h) {
               if (h < nmine) {
+                const int cc = tid + NT * h;
+                // a simple row w is zero before column w: fma(-lam, 0, uc) == uc, so those steps are skipped
+                // (K3_TRIM_U; the loads they would have issued are half of this phase's L2 traffic)
 #pragma unroll K3_BCU
-                for (int i = 0; i < k; ++i) uc[h] = fma(-c.lamw[i], mcol[h][c.roww[i] * n], uc[h]);
+                for (int i = 0; i < k; ++i) {
+                  const int wr = c.roww[i];
+                  if (!K3_TRIM_U || wr <= cc || wr >= lay.ms) uc[h] = fma(-c.lamw[i], mcol[h][wr * n], uc[h]);
+                }
               }
             }
           }
@@ -1183,7 +1262,41 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
           const int nmine = (m - tid + NT - 1) / NT;          // rows this thread owns (<= RH)
 #pragma unroll
           for (int h = 0; h < RH; ++h) mus[h] = 0.0;
-          if (nmine >= 1) {
+          if (use_ring) {
+            // batch b = columns [b RB, (b+1) RB) of Mbar == rows of Mbar'; on a box-only problem row cc of Mbar'
+            // has its non-zeros in [0, cc] (row j of Mbar starts at column j), so only that head is copied
+            const int nb = (n + K3_RB - 1) / K3_RB;
+            auto issue = [&](int b) {
+              const int hf = b & 1, c0 = b * K3_RB, c1 = min(n, c0 + K3_RB);
+              uint32_t tot = 0;
+              for (int cc = c0; cc < c1; ++cc) tot += (uint32_t)(boxonly ? min(mp, (cc + 2) & ~1) : mp) * 8u;
+              bulk_expect(&rbar[hf], tot);
+              for (int cc = c0; cc < c1; ++cc)
+                bulk_copy(&rbar[hf], ring + (size_t)(hf * K3_RB + (cc - c0)) * mp, c.MT + (size_t)cc * mp,
+                          (uint32_t)(boxonly ? min(mp, (cc + 2) & ~1) : mp) * 8u);
+            };
+            int jc0[RH];                       // first column with a non-zero in row j (simple rows), else 0
+#pragma unroll
+            for (int h = 0; h < RH; ++h) { const int j = tid + NT * h; jc0[h] = (j < lay.ms) ? j : 0; }
+            if (tid == 0) issue(0);
+            for (int b = 0; b < nb; ++b) {
+              if (tid == 0 && b + 1 < nb) issue(b + 1);
+              if (b & 1) { tile_wait(&rbar[1], rph1); rph1 ^= 1u; } else { tile_wait(&rbar[0], rph0); rph0 ^= 1u; }
+              const double *slot = ring + (size_t)((b & 1) * K3_RB) * mp;
+              const int c0 = b * K3_RB;
+#pragma unroll
+              for (int r = 0; r < K3_RB; ++r) {
+                const int cc = c0 + r;
+                if (cc < n) {
+                  const double ucc = c.uw[cc];
+#pragma unroll
+                  for (int h = 0; h < RH; ++h)
+                    if (h < nmine && cc >= jc0[h]) mus[h] = fma(slot[r * mp + tid + NT * h], ucc, mus[h]);
+                }
+              }
+              __syncthreads();
+            }
+          } else if (nmine >= 1) {
             // start at the first row's own column only when every row of this thread is a simple row
             const int c0 = (tid + NT * (nmine - 1) < lay.ms) ? tid : 0;
             const double *mt = c.MT + tid + c0 * mp;
@@ -1391,13 +1504,14 @@ size_t cta_smem(const LdpLayout &lay, int cap) {
   d += (lay.n + 1) & ~1; d += (lay.nth + 1) & ~1; d += (cap + 1) & ~1; d += (lay.m + 1) & ~1;
   d += (cap + 1) & ~1;
   d += 8 + 8 + 4 + 4 + 4 + (cap + 1) / 2 + 1;
+  d += K3_USE_RING ? (size_t)2 * K3_RB * lay.mp : 0;
   d += (lay.m + 7) / 8 + 1;
   return d * sizeof(double);
 }
 size_t cta_smem(const LdpLayout &lay) { return cta_smem(lay, lay.cap); }
 
 // Two CTAs per SM: the largest working-set capacity whose CTA still fits twice into an SM's shared
-// memory.  Used as a first pass when it is at least 85 % of the full capacity (instances that outgrow it
+// memory.  Used as a first pass when it is at least 80 % of the full capacity (instances that outgrow it
 // end with EXIT_CAPACITY and are redone at full capacity by a second launch); 0 = not worth it.
 int cta_fast_cap(const LdpLayout &lay) {
   if (lay.n > 256 || lay.m > 512) return 0;
@@ -1405,7 +1519,7 @@ int cta_fast_cap(const LdpLayout &lay) {
   int cap = lay.cap;
   while (cap > 0 && cta_smem(lay, cap) > budget) --cap;
   if (cap >= lay.cap) return lay.cap;            // the full problem fits twice: no second pass needed
-  return (cap * 100 >= lay.cap * 85) ? cap : 0;
+  return (cap * 100 >= lay.cap * 80) ? cap : 0;
 }
 
 unsigned long long *g_redo_counter(int device) {
