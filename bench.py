@@ -232,7 +232,7 @@ def run_reference_one(name, steps, warmup):
     n = min(w["n"], REF_SAMPLE[name])
     if w["kind"] == "explicit":
         z = explicit_tree()
-        P, mpc, lo, hi = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"]), None, z["lo"], z["hi"]
+        P, mpc, lo, hi = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"]), None, z["lo"], z["hi"]
     else:
         mpc, qp = checker_controller(w["ctrl"])
         P = oracle_problem(mpc, qp)
@@ -317,7 +317,7 @@ class Bench:
         self.n = w["n"]
         if w["kind"] == "explicit":
             z = explicit_tree()
-            self.g = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"],
+            self.g = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"],
                                               dims=(4, 2, 0, 1), device=dev_index)
             self.tree = z
             lo, hi = z["lo"], z["hi"]
@@ -413,7 +413,7 @@ class Bench:
         w = self.w
         if w["kind"] == "explicit":
             z = self.tree
-            return ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"]), None
+            return ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"]), None
         mpc, qp = checker_controller(w["ctrl"])
         return oracle_problem(mpc, qp, self.g.ldp_constants()), mpc
 

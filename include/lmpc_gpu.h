@@ -39,9 +39,12 @@ extern "C" {
 /* API-level errors */
 #define LMPC_E_INVALID    (-100)  /* bad argument / dimension */
 #define LMPC_E_UNSUPPORTED (-101) /* binaries, non-symmetric H (AVI), hierarchical break points */
-#define LMPC_E_SETUP      (-102)  /* Cholesky failed (setup flag -5) or zero row */
+#define LMPC_E_SETUP      (-102)  /* Cholesky failed: H not positive definite (setup flag -5) */
 #define LMPC_E_CUDA       (-103)  /* CUDA runtime error; see lmpc_gpu_last_error() */
 #define LMPC_E_NOGPU      (-104)  /* no usable sm_100 device: there is NO CPU fallback */
+/* the two other flags DAQP.setup can return (src/setup.jl:14-23), found once at create instead of per instance */
+#define LMPC_E_SETUP_INFEASIBLE     (-105)  /* setup flag -1: a row's lower bound lies above its upper bound */
+#define LMPC_E_SETUP_OVERDETERMINED (-106)  /* setup flag -6: equality rows dependent or more than n */
 
 /* constraint sense bits (DAQPBase constants, set at src/mpc2mpqp.jl:868-885) */
 #define LMPC_ACTIVE 1
@@ -100,7 +103,11 @@ typedef struct {
   int32_t cycle_tol;    /* 10    */
   int32_t iter_limit;   /* 10000 */
   int32_t kernel;       /* LMPC_KERNEL_* */
-  int32_t reserved;
+  int32_t certified_iterations; /* > 0: a proven bound on DAQP's iteration count over the parameter range,
+                                 * CertificationResult.max_iterations of certify(mpc; range) (src/certify.jl:18-29).
+                                 * Becomes a hard iteration cap (iter_limit = min(iter_limit, bound + 1)) and shrinks
+                                 * the on-chip working-set capacity to n_eq + bound rows (every iteration adds at most
+                                 * one), i.e. smaller factor tiles and more QPs resident per SM.  0: no certificate */
 } lmpc_settings;
 
 void lmpc_gpu_default_settings(lmpc_settings *s);

@@ -26,7 +26,7 @@ extern "C" int lmpc_gpu_abi_layout(int32_t *out, int32_t cap) {
   emit(o, LMPC_ABI_SETTINGS, sizeof(lmpc_settings),
        {F(lmpc_settings, primal_tol), F(lmpc_settings, dual_tol), F(lmpc_settings, zero_tol),
         F(lmpc_settings, progress_tol), F(lmpc_settings, fval_bound), F(lmpc_settings, cycle_tol),
-        F(lmpc_settings, iter_limit), F(lmpc_settings, kernel), F(lmpc_settings, reserved)});
+        F(lmpc_settings, iter_limit), F(lmpc_settings, kernel), F(lmpc_settings, certified_iterations)});
   emit(o, LMPC_ABI_SIM_EXT, sizeof(lmpc_sim_ext),
        {F(lmpc_sim_ext, Rtraj), F(lmpc_sim_ext, Dtraj), F(lmpc_sim_ext, Ft), F(lmpc_sim_ext, Gt),
         F(lmpc_sim_ext, Gdt), F(lmpc_sim_ext, C), F(lmpc_sim_ext, Dd), F(lmpc_sim_ext, K), F(lmpc_sim_ext, Vtraj),

@@ -226,7 +226,7 @@ void lmpc_gpu_default_settings(lmpc_settings *s) {
   if (!s) return;
   s->primal_tol = 1e-6; s->dual_tol = 1e-12; s->zero_tol = 1e-11; s->progress_tol = 1e-6;
   s->fval_bound = 1e30; s->cycle_tol = 10; s->iter_limit = 10000; s->kernel = LMPC_KERNEL_AUTO;
-  s->reserved = 0;
+  s->certified_iterations = 0;
 }
 
 const char *lmpc_gpu_last_error(void) { return g_err; }
@@ -258,6 +258,12 @@ int lmpc_gpu_create(const lmpc_problem *p, const lmpc_settings *s, int device, l
   h->st.progress_tol = def.progress_tol; h->st.fval_bound = def.fval_bound;
   h->st.rho_soft = 1.0 / (p->soft_weight > 0 ? p->soft_weight : 1e6);
   h->st.cycle_tol = def.cycle_tol; h->st.iter_limit = def.iter_limit;
+  if (def.certified_iterations > 0) {
+    // certify(mpc; range).max_iterations (src/certify.jl:18-29): hard cap + static capacity sizing
+    if (h->st.iter_limit > def.certified_iterations + 1) h->st.iter_limit = def.certified_iterations + 1;
+    const int capc = h->lay.neq + def.certified_iterations;
+    if (capc >= 1 && capc < h->lay.cap) h->lay.cap = capc;
+  }
   int kern = def.kernel;
   if (kern == LMPC_KERNEL_AUTO) {
     if (ldp_thread_supports(h->lay)) kern = LMPC_KERNEL_THREAD;

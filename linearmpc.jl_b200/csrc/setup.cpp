@@ -157,6 +157,41 @@ int lmpc_host_setup(const lmpc_problem *p, LdpHost *out, char *err, int errlen) 
     for (int c = i; c < n; ++c) s += Rinv[(size_t)i * n + c] * v[c];
     uoff[i] = -s;
   }
+  // DAQP.setup's remaining flags (src/setup.jl:14-23), both independent of theta because bu and bl shift
+  // together: -1 a row whose bounds cross (d_u - d_l < -primal_tol on the normalised row), -6 equality rows
+  // that are linearly dependent or outnumber the variables (found by factorising their Gram block the way
+  // the cold start activates them: a pivot below zero_tol).
+  for (int i = 0; i < m; ++i) {
+    if (sense[i] & S_IMMUTABLE && !(sense[i] & S_ACTIVE)) continue;
+    if (du[i] < 1e29 && dl[i] > -1e29 && du[i] - dl[i] < -1e-6) {
+      free(blk);
+      snprintf(err, errlen, "row %d: lower bound above upper bound, the problem is infeasible (setup flag -1)", i);
+      return LMPC_E_SETUP_INFEASIBLE;
+    }
+  }
+  if (neq > 0) {
+    std::vector<int> eq;
+    for (int i = 0; i < m; ++i) if (sense[i] & S_ACTIVE) eq.push_back(i);
+    const int ne = (int)eq.size();
+    std::vector<double> Lq((size_t)ne * ne, 0.0), Dq(ne, 0.0);
+    bool over = ne > n;
+    for (int a = 0; a < ne && !over; ++a) {          // LDL' of the equality rows' Gram block, row by row
+      double d = G[(size_t)eq[a] * m + eq[a]];
+      for (int b = 0; b < a; ++b) {
+        double y = G[(size_t)eq[a] * m + eq[b]];
+        for (int c = 0; c < b; ++c) y -= Lq[(size_t)a * ne + c] * Dq[c] * Lq[(size_t)b * ne + c];
+        Lq[(size_t)a * ne + b] = y / Dq[b];
+        d -= y * Lq[(size_t)a * ne + b];
+      }
+      if (d < 1e-11) over = true;
+      Dq[a] = d;
+    }
+    if (over) {
+      free(blk);
+      snprintf(err, errlen, "equality constraints are overdetermined (setup flag -6)");
+      return LMPC_E_SETUP_OVERDETERMINED;
+    }
+  }
   out->lay = lay;
   out->blk = blk;
   return 0;

@@ -45,7 +45,7 @@ class _Settings(C.Structure):
     _fields_ = [("primal_tol", C.c_double), ("dual_tol", C.c_double), ("zero_tol", C.c_double),
                 ("progress_tol", C.c_double), ("fval_bound", C.c_double),
                 ("cycle_tol", C.c_int32), ("iter_limit", C.c_int32), ("kernel", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("certified_iterations", C.c_int32)]
 
 
 def lib_path():
@@ -752,6 +752,19 @@ class GpuExplicitMPC:
                                                   len(hl), _ptr(clip), self.nth, self.nu, int(le_child), device,
                                                   C.byref(self._t)))
 
+    @classmethod
+    def from_codegen(cls, path_c, path_h=None, clipping=None, dims=None, device=0, le_child=None):
+        """A tree computed by the real package, read from the C arrays ParametricDAQP.codegen emitted
+        (src/codegen.jl:62-66).  The branch orientation is taken from the generated evaluate function in the
+        file; le_child overrides it."""
+        from . import explicit as ex
+        t = ex.load_pdaqp_codegen(path_c, path_h)
+        lc = t["le_child"] if le_child is None else le_child
+        if lc is None:
+            raise ValueError("branch orientation not found in the file: pass le_child = 0 or 1")
+        return cls(t["halfplanes"], t["feedbacks"], t["hp_list"], t["jump_list"], clipping=clipping, dims=dims,
+                   device=device, le_child=lc)
+
     def close(self):
         if getattr(self, "_t", None) is not None and self._t:
             lib().lmpc_gpu_destroy_bst(self._t)
@@ -1076,18 +1089,36 @@ class MPC:
     def solve(self, Theta, **kw):
         return self._g().solve(Theta, **kw)
 
-    def explicit(self, lo, hi, n_samples=2_000_000, seed=0, device=0, clipping=None, **kw):
+    def clipping_bounds(self):
+        """[umin umax] (nu x 2) when every input has finite simple bounds and there is no prestabilising
+        feedback (then the first nu decision variables ARE the controls and clipping is exact); else None."""
+        if self.K is not None and np.any(self.K != 0):
+            return None
+        if self.umin is None or self.umax is None:
+            return None
+        lo, hi = np.asarray(self.umin, float).ravel(), np.asarray(self.umax, float).ravel()
+        if len(lo) != self.nu or len(hi) != self.nu or np.any(np.abs(lo) > 1e20) or np.any(np.abs(hi) > 1e20):
+            return None
+        return np.stack([lo, hi], axis=1)
+
+    def explicit(self, lo, hi, n_samples=2_000_000, seed=0, device=0, clipping=True, gpu=None, **kw):
         """ExplicitMPC(mpc; range, build_tree=true) (src/explicit.jl:25-52): explicit solution over the
         parameter box [lo, hi], critical regions discovered by batched implicit solves on the GPU
-        (linearmpc.jl_b200/explicit.py).  Returns (GpuExplicitMPC, info)."""
+        (linearmpc.jl_b200/explicit.py); soft constraints included (make_singlesided's slack columns).
+        clipping=True (the reference's default, src/explicit.jl:65): the tree only has to be right after the
+        control is clipped to the input bounds, which absorbs the saturated regions; an array gives the bounds
+        explicitly, None / False builds an exact tree.  Returns (GpuExplicitMPC, info)."""
         from . import explicit as ex
         q = self.condense()
-        sol = ex.build_explicit(q, self._g(), lo, hi, self.nu, n_samples=n_samples, seed=seed, **kw)
+        clip = self.clipping_bounds() if clipping is True else (None if clipping in (None, False) else
+                                                                np.asarray(clipping, float).reshape(self.nu, 2))
+        sol = ex.build_explicit(q, gpu if gpu is not None else self._g(), lo, hi, self.nu, n_samples=n_samples,
+                                seed=seed, clipping=clip, soft_weight=self.soft_weight, **kw)
         if self.K is not None and np.any(self.K != 0):
             # the laws give v; u = v - K x (build_tree! correction, src/explicit.jl:65-71)
             sol["feedbacks"][:, :, :self.nx] -= self.K
         empc = GpuExplicitMPC(sol["halfplanes"], sol["feedbacks"], sol["hp_list"], sol["jump_list"],
-                              clipping=clipping, dims=q["dims"], device=device)
+                              clipping=clip, dims=q["dims"], device=device)
         return empc, sol
 
     def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None,

@@ -10,6 +10,7 @@
 module LinearMPCGPU
 
 using LinearMPC, LinearAlgebra
+import ParametricDAQP
 
 const liblmpcgpu = get(ENV, "LMPC_GPU_LIB", "liblmpcgpu.so")
 
@@ -19,6 +20,12 @@ struct LmpcProblem            # mirrors lmpc_problem in include/lmpc_gpu.h
     bu::Ptr{Float64}; bl::Ptr{Float64}; W::Ptr{Float64}; senses::Ptr{Cint}
     K::Ptr{Float64}; soft_weight::Float64
     has_binaries::Int32; is_symmetric::Int32; n_break_points::Int32
+end
+
+mutable struct LmpcSettings    # mirrors lmpc_settings in include/lmpc_gpu.h (DAQP settings, docs/src/manual/solver.md:49-56)
+    primal_tol::Float64; dual_tol::Float64; zero_tol::Float64; progress_tol::Float64; fval_bound::Float64
+    cycle_tol::Int32; iter_limit::Int32; kernel::Int32; certified_iterations::Int32
+    LmpcSettings() = (s = new(); ccall((:lmpc_gpu_default_settings, liblmpcgpu), Cvoid, (Ref{LmpcSettings},), s); s)
 end
 
 mutable struct GpuMPC
@@ -52,8 +59,12 @@ check(rc) = rc == 0 || error("liblmpcgpu error $rc: $(lasterror())")
 Uploads the condensed problem once (what `DAQP.setup` + `qp2ldp` do on the host,
 src/setup.jl:11-13, src/codegen.jl:239-280).  Refuses hybrid / AVI / hierarchical problems.
 """
-function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0, devices=nothing)
+function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0, devices=nothing, certificate=nothing)
     mpc.mpqp_issetup || LinearMPC.setup!(mpc)
+    # certificate: a CertificationResult of certify(mpc; range) (src/certify.jl:18-29).  Its proven iteration
+    # bound becomes the hard iteration cap and sizes the on-chip working-set capacity (lmpc_settings).
+    st = LmpcSettings()
+    isnothing(certificate) || (st.certified_iterations = Int32(certificate.max_iterations))
     q = mpc.mpQP
     n, m = size(q.H, 1), length(q.bu)
     nth = size(q.f_theta, 2)
@@ -67,12 +78,12 @@ function setup_gpu!(mpc::LinearMPC.MPC; device::Integer=0, devices=nothing)
                         q.has_binaries, q.is_symmetric, length(q.break_points))
         if isnothing(devices)
             check(ccall((:lmpc_gpu_create, liblmpcgpu), Cint,
-                        (Ref{LmpcProblem}, Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), p, C_NULL, device, h))
+                        (Ref{LmpcProblem}, Ref{LmpcSettings}, Cint, Ref{Ptr{Cvoid}}), p, st, device, h))
         else    # one process, several GPUs: contiguous theta ranges, no inter-GPU traffic
             dv = Int32.(collect(devices))
             check(ccall((:lmpc_gpu_create_multi, liblmpcgpu), Cint,
-                        (Ref{LmpcProblem}, Ptr{Cvoid}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
-                        p, C_NULL, dv, length(dv), h))
+                        (Ref{LmpcProblem}, Ref{LmpcSettings}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                        p, st, dv, length(dv), h))
         end
     end
     g = GpuMPC(h[], mpc, nth, mpc.model.nu, m, !isnothing(devices))
@@ -137,6 +148,29 @@ function LinearMPC.compute_control(g::GpuMPC, X::AbstractMatrix; r=nothing, d=no
 end
 
 """
+    compute_control_shared(g, X; r, d, uprev) -> (U, n_failed)
+
+Monte-Carlo form of `compute_control` (lmpc_gpu_compute_control_batch_bcast): X is nx × N, `r`, `d`, `uprev`
+are single vectors shared by all columns and travel to the GPU once; the exit flags stay on the device and
+only the number of columns with exitflag < 1 comes back (what `@assert exitflag ≥ 1`, src/utils.jl:46, checks).
+"""
+function compute_control_shared(g::GpuMPC, X::Matrix{Float64}; r=nothing, d=nothing, uprev=nothing)
+    g.multi && error("compute_control_shared: single-device backends only")
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
+    N = size(X, 2)
+    vec_or(v, k) = k == 0 ? Float64[] : Vector{Float64}(isnothing(v) ? zeros(k) : v[1:k])
+    rv, dv, uv = vec_or(r, nr), vec_or(d, nd), vec_or(isnothing(uprev) ? g.mpc.uprev : uprev, nup)
+    U = Matrix{Float64}(undef, g.nu, N)
+    nfail = Ref{Int64}(0)
+    check(ccall((:lmpc_gpu_compute_control_batch_bcast, liblmpcgpu), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,
+                 Int64, Int32, Ptr{Int32}, Ref{Int64}),
+                g.handle, U, X, nr == 0 ? C_NULL : pointer(rv), nd == 0 ? C_NULL : pointer(dv),
+                nup == 0 ? C_NULL : pointer(uv), nr, nd, nup, N, 7, C_NULL, nfail))
+    return U, nfail[]
+end
+
+"""
     simulate(g, X0; r, d, N, warm_start=true) -> (Xend, Ulast, exitflag)
 
 N_traj independent copies of the `Simulation` loop (src/simulation.jl:93-113) with the model's
@@ -146,7 +180,7 @@ with one column per step, its last column held when it is shorter than the horiz
 scenario drives every closed loop.
 """
 function simulate(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integer=100, warm_start::Bool=true)
-    g.multi && error("simulate: build the backend with a single `device` (closed loops are per-GPU)")
+    g.multi && return simulate_multi(g, X0; r, d, N, warm_start)
     mdl = g.mpc.model
     nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
     M = size(X0, 2)
@@ -163,6 +197,29 @@ function simulate(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integ
                  Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
                 g.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
                 X0, C_NULL, C_NULL, C_NULL, Rt, Dt, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
+    return Xend, Ulast, flag
+end
+
+# every GPU of the box from one process (lmpc_gpu_simulate_batch_multi): contiguous ranges of X0's columns
+function simulate_multi(g::GpuMPC, X0::Matrix{Float64}; r=nothing, d=nothing, N::Integer=100, warm_start::Bool=true)
+    mdl = g.mpc.model
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
+    M = size(X0, 2)
+    hold(v, k) = (k == 0 || isnothing(v)) ? nothing :
+        (V = v isa AbstractMatrix ? Matrix{Float64}(v) : reshape(Vector{Float64}(v), k, 1);
+         hcat(V[:, 1:min(N, size(V, 2))], repeat(V[:, end], 1, max(0, N - size(V, 2)))))
+    Rt, Dt = hold(r, nr), hold(d, nd)
+    p(x) = isnothing(x) ? Ptr{Float64}(C_NULL) : pointer(x)
+    Xend = similar(X0); Ulast = Matrix{Float64}(undef, g.nu, M); flag = Vector{Int32}(undef, M)
+    GC.@preserve Rt Dt begin
+        ext = Ref(LmpcSimExt(p(Rt), p(Dt), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, 0, C_NULL, 0, 0))
+        check(ccall((:lmpc_gpu_simulate_batch_multi, liblmpcgpu), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{LmpcSimExt},
+                     Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                    g.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
+                    X0, C_NULL, C_NULL, C_NULL, ext, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
+    end
     return Xend, Ulast, flag
 end
 
@@ -184,7 +241,7 @@ function check_abi()
     n = ccall((:lmpc_gpu_abi_layout, liblmpcgpu), Cint, (Ptr{Int32}, Int32), C_NULL, 0)
     v = Vector{Int32}(undef, n)
     ccall((:lmpc_gpu_abi_layout, liblmpcgpu), Cint, (Ptr{Int32}, Int32), v, n)
-    mirrors = Dict(1 => LmpcProblem, 3 => LmpcSimExt)
+    mirrors = Dict(1 => LmpcProblem, 2 => LmpcSettings, 3 => LmpcSimExt)
     i = 1
     while i <= n
         id, sz, nf = v[i], v[i+1], v[i+2]
@@ -255,13 +312,19 @@ mutable struct GpuExplicitMPC
 end
 
 """
-    setup_gpu!(empc) -> GpuExplicitMPC     (needs `build_tree!(empc)` first, src/explicit.jl:65-71)
+    setup_gpu!(empc; device=0, le_child=1, verify=256) -> GpuExplicitMPC
 
-Uploads bst.halfplanes / feedbacks / hp_list / jump_list / clipping.  The library's node
-convention is 0-based with jump 0 marking a leaf; ParametricDAQP's arrays are 1-based with
-`next == id` marking a leaf, so the lists are shifted here.
+Uploads bst.halfplanes / feedbacks / hp_list / jump_list / clipping (needs `build_tree!(empc)` first,
+src/explicit.jl:65-71).  The library's node arrays are 0-based with jump 0 marking a leaf; ParametricDAQP's
+are 1-based with `next == id` marking a leaf, so hp_list is shifted here.
+
+Branch orientation.  The library walks to `next` when a'θ ≤ b; ParametricDAQP is believed to walk to
+`next + 1` (its generated C reads `id = next_id + (val <= b)`), which is `le_child = 1`.  ParametricDAQP
+is not vendored in LinearMPC.jl, so instead of trusting that, the upload is CHECKED: `verify` parameters
+sampled in the solution's box are evaluated by `ParametricDAQP.evaluate(bst, θ)` on the CPU and on the GPU;
+if they disagree the other orientation is tried, and if neither agrees the call errors.
 """
-function setup_gpu!(empc::LinearMPC.ExplicitMPC; device::Integer=0)
+function setup_gpu!(empc::LinearMPC.ExplicitMPC; device::Integer=0, le_child::Integer=1, verify::Integer=256)
     bst = empc.bst
     isnothing(bst) && error("Need to build a binary search tree to evaluate control law")  # src/utils.jl:54-55
     nth = size(bst.halfplanes, 1) - 1
@@ -270,15 +333,31 @@ function setup_gpu!(empc::LinearMPC.ExplicitMPC; device::Integer=0)
     jump = Int32.(bst.jump_list)                                   # 0 stays 0 (leaf)
     hp = Int32.(bst.hp_list) .- Int32(1)
     clip = isnothing(bst.clipping) ? C_NULL : Matrix{Float64}(bst.clipping[:, 1:2])
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:lmpc_gpu_create_bst, liblmpcgpu), Cint,
-                (Ptr{Float64}, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64},
-                 Int32, Int32, Cint, Ref{Ptr{Cvoid}}),
-                bst.halfplanes, size(bst.halfplanes, 2), fb, size(fb, 2), hp, jump, length(jump), clip,
-                nth, nu, device, h))
-    g = GpuExplicitMPC(h[], empc, nth, nu)
-    finalizer(x -> ccall((:lmpc_gpu_destroy_bst, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle), g)
-    return g
+    function upload(orient)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:lmpc_gpu_create_bst_oriented, liblmpcgpu), Cint,
+                    (Ptr{Float64}, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64},
+                     Int32, Int32, Int32, Cint, Ref{Ptr{Cvoid}}),
+                    bst.halfplanes, size(bst.halfplanes, 2), fb, size(fb, 2), hp, jump, length(jump), clip,
+                    nth, nu, orient, device, h))
+        g = GpuExplicitMPC(h[], empc, nth, nu)
+        finalizer(x -> ccall((:lmpc_gpu_destroy_bst, liblmpcgpu), Cint, (Ptr{Cvoid},), x.handle), g)
+        return g
+    end
+    verify <= 0 && return upload(le_child)
+    lb, ub = empc.TH.lb, empc.TH.ub                                # the box the solution was computed on
+    Θ = lb .+ (ub .- lb) .* rand(nth, verify)
+    clipu(u) = isnothing(bst.clipping) ? u : clamp.(u, bst.clipping[:, 1], bst.clipping[:, 2])
+    Uref = reduce(hcat, [clipu(ParametricDAQP.evaluate(bst, Θ[:, k])) for k in 1:verify])
+    for orient in (le_child, 1 - le_child)
+        g = upload(orient)
+        U = Matrix{Float64}(undef, nu, verify)
+        check(ccall((:lmpc_gpu_evaluate_batch, liblmpcgpu), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}), g.handle, Θ, verify, U, C_NULL))
+        maximum(abs.(U .- Uref)) <= 1e-9 * max(1.0, maximum(abs.(Uref))) && return g
+        orient == le_child && @warn "liblmpcgpu: tree orientation le_child=$le_child disagrees with ParametricDAQP.evaluate; trying the other one"
+    end
+    error("liblmpcgpu: the uploaded tree does not reproduce ParametricDAQP.evaluate in either branch orientation")
 end
 
 function LinearMPC.compute_control(g::GpuExplicitMPC, X::AbstractMatrix; r=nothing, d=nothing, uprev=nothing)

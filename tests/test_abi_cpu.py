@@ -125,7 +125,8 @@ def _julia_struct_layout(name):
     """Parse `struct name ... end` in LinearMPCGPU.jl and lay the fields out by the C rules Julia uses
     for isbits structs (natural alignment, size rounded up to the largest alignment)."""
     src = open(os.path.join(ROOT, "linearmpc.jl_b200", "julia", "LinearMPCGPU.jl")).read()
-    body = re.search(r"^struct\s+" + name + r"\b(.*?)^end", src, flags=re.S | re.M).group(1)
+    body = re.search(r"^(?:mutable )?struct\s+" + name + r"\b(.*?)^end", src, flags=re.S | re.M).group(1)
+    body = re.sub(r"^\s*\w+\(\)\s*=.*$", "", body, flags=re.M)           # inner constructors
     body = re.sub(r"#.*", "", body)
     fields = re.findall(r"(\w+)::([\w{}]+)", body)
     off, offs, amax = 0, [], 1
@@ -158,7 +159,7 @@ def test_struct_layouts_match_the_julia_and_ctypes_mirrors(lmpc):
     without the trailing rstride / dstride: C then read 8 bytes past the Julia object."""
     lay = _abi_layout(lmpc)
     assert sorted(lay) == [1, 2, 3, 4, 5]
-    for sid, jl in [(1, "LmpcProblem"), (3, "LmpcSimExt")]:
+    for sid, jl in [(1, "LmpcProblem"), (2, "LmpcSettings"), (3, "LmpcSimExt")]:
         names, offs, size = _julia_struct_layout(jl)
         assert (size, offs) == (lay[sid][0], lay[sid][1]), (jl, names, offs, size, lay[sid])
     import sys
@@ -175,7 +176,7 @@ def test_julia_struct_field_names_follow_the_header():
     when the sizes happen to agree)."""
     hdr = open(os.path.join(ROOT, "include", "lmpc_gpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    for cname, jl in [("lmpc_problem", "LmpcProblem"), ("lmpc_sim_ext", "LmpcSimExt")]:
+    for cname, jl in [("lmpc_problem", "LmpcProblem"), ("lmpc_settings", "LmpcSettings"), ("lmpc_sim_ext", "LmpcSimExt")]:
         body = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + r"\s*;", hdr).group(1)
         cfields = []
         for decl in body.split(";"):
@@ -185,3 +186,28 @@ def test_julia_struct_field_names_follow_the_header():
             decl = re.sub(r"^(const\s+)?(double|int32_t|int64_t|uint64_t)\s*", "", decl)
             cfields += [x.strip().lstrip("*").strip() for x in decl.split(",")]
         assert _julia_struct_layout(jl)[0] == cfields, (cname, cfields)
+
+
+def test_setup_flags_infeasible_and_overdetermined(lmpc):
+    """DAQP.setup's other two flags (src/setup.jl:14-23) are raised once, at create / host setup, instead of
+    showing up per instance at solve time: -1 (a row whose bounds cross) and -6 (equality rows that are
+    dependent or outnumber the variables)."""
+    mpc = util.controller("invpend")
+    qp = mpqp.mpc2mpqp(mpc)
+    bl = qp.bl.copy()
+    bl[2] = qp.bu[2] + 1.0                                   # lower bound above the upper bound
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.host_ldp(qp.H, qp.f, qp.f_theta, qp.A, qp.bu, bl, qp.W, qp.senses, 1)
+    assert e.value.code == -105 and "setup flag -1" in str(e.value)
+    # six equality rows on five variables: the same row twice makes the set dependent
+    n, nth = qp.n, qp.f_theta.shape[1]
+    A = np.vstack([np.ones((1, n)), np.ones((1, n))])
+    bu = np.concatenate([qp.bu, [0.3, 0.3]]); bl2 = np.concatenate([qp.bl, [0.3, 0.3]])
+    W = np.vstack([qp.W, np.zeros((2, nth))])
+    s = np.concatenate([qp.senses, [5, 5]]).astype(np.int32)  # EQUALITY = ACTIVE + IMMUTABLE (mpc2mpqp.jl:868-885)
+    with pytest.raises(lmpc.LmpcError) as e:
+        lmpc.host_ldp(qp.H, qp.f, qp.f_theta, A, bu, bl2, W, s, 1)
+    assert e.value.code == -106 and "setup flag -6" in str(e.value)
+    # one such row is fine
+    c = lmpc.host_ldp(qp.H, qp.f, qp.f_theta, A[:1], bu[:-1], bl2[:-1], W[:-1], s[:-1], 1)
+    assert c["cap"] >= 1

@@ -13,7 +13,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "invpe
 
 def load_tree():
     z = np.load(GOLD)
-    return z, ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    return z, ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"])
 
 
 def test_explicit_known_answer_and_matches_implicit():
@@ -60,7 +60,7 @@ def test_region_enumeration_small_problem():
 @pytest.mark.gpu
 def test_gpu_evaluate_matches_oracle_walk(lmpc):
     z, B = load_tree()
-    g = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"],
+    g = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"],
                             dims=(4, 2, 0, 1))
     for N in (0, 1, 255, 256, 257, 100000):
         Th = mpqp.sample_theta(z["lo"], z["hi"], max(N, 1), seed=3)[:, :N]
@@ -78,8 +78,8 @@ def test_gpu_explicit_equals_gpu_implicit(lmpc):
     mpc = mpqp.invpend()
     qp = mpqp.mpc2mpqp(mpc)
     gi = lmpc.setup_gpu(qp, nu=1, dims=mpc.parameter_dims())
-    ge = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"],
-                             clipping=np.array([[-2.0, 2.0]]), dims=mpc.parameter_dims())
+    ge = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"],
+                             dims=mpc.parameter_dims())
     Th = mpqp.sample_theta(z["lo"], z["hi"], 200000, seed=8)
     Ue, _ = ge.evaluate(Th)
     Ui = gi.solve(Th, want_active=False)["U"]
@@ -89,18 +89,23 @@ def test_gpu_explicit_equals_gpu_implicit(lmpc):
 
 @pytest.mark.gpu
 def test_gpu_evaluate_device_buffers_and_large_batch(lmpc):
-    """BASELINE config 5 shape at 1e7 (1e8 needs 6.4 GB; same code path): device-resident
-    evaluate equals the chunked host path; every result within the input bounds."""
+    """BASELINE config 5 at its stated size, 1e8 theta (5.6 GB of parameters resident in HBM): every result
+    within the input bounds, idempotent, device-resident evaluate equals the chunked host path and a
+    subsample equals the oracle's walk bit for bit."""
     import torch
     z, B = load_tree()
-    g = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
-    N = 10_000_000
+    g = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"])
+    N = 100_000_000
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234)
     lo, hi = torch.tensor(z["lo"], device="cuda"), torch.tensor(z["hi"], device="cuda")
-    Th = torch.rand((N, 7), dtype=torch.float64, device="cuda", generator=gen) * (hi - lo) + lo
+    Th = torch.rand((N, 7), dtype=torch.float64, device="cuda", generator=gen)
+    Th.mul_(hi - lo).add_(lo)
     U, reg = g.evaluate(Th)
     assert bool((U.abs() <= 2.0 + 1e-9).all())
+    U2, reg2 = g.evaluate(Th)
+    assert bool((U == U2).all()) and bool((reg == reg2).all())
+    del U2, reg2
     sub = Th[:300000].cpu().numpy().T
     Uh, regh = g.evaluate(np.asfortranarray(sub))
     assert np.array_equal(Uh, U[:, :300000].cpu().numpy())
@@ -133,10 +138,13 @@ def test_product_builder_logic_with_a_cpu_stand_in():
     Th = mpqp.sample_theta(lo, hi, 30000, seed=9)
     U, _ = B.evaluate_batch(Th)
     assert np.max(np.abs(U - P.solve_batch(Th)["U"])) < 1e-10
-    with pytest.raises(NotImplementedError):
-        q2 = dict(q)
-        q2["senses"] = np.asarray(q["senses"]) | 8
-        pex.make_singlesided(q2)
+    # soft rows are made explicit with one slack column each (utils.jl:345-380), no longer refused
+    q2 = dict(q)
+    q2["senses"] = np.asarray(q["senses"]) | 8
+    H2, f2, fth2, A2, b2, W2, src2 = pex.make_singlesided(q2, soft_weight=1e6)
+    n, m = qp.H.shape[0], len(qp.bu)
+    assert H2.shape == (n + m, n + m) and np.allclose(np.diag(H2)[n:], 1e6) and A2.shape[1] == n + m
+    assert np.all(A2[:, n:] <= 0) and np.count_nonzero(A2[:, n:]) == A2.shape[0]   # a slack relaxes both sides of its row
 
 
 @pytest.mark.gpu
@@ -260,3 +268,110 @@ def test_product_explicit_with_feedback_and_with_disturbance_preview(lmpc):
     # the implicit solve leaves rows violated by less than primal_tol = 1e-6 inactive, the explicit law is
     # exact: next to region boundaries the two differ by that band, nowhere by more
     assert rep["max_err"] < 2e-6 and rep["frac_within_tol"] > 0.999
+
+
+# ---- product-side explicit builder (linearmpc.jl_b200/explicit.py): soft rows, clipping, codegen arrays ------
+class _OracleSolver:
+    """stands in for a GpuMPC in the explicit builder on a box without a GPU: region DISCOVERY only (the
+    builder computes polyhedra and laws itself); on a GPU box the product's own batched solver does this"""
+
+    def __init__(self, mpc):
+        self.qp = mpqp.mpc2mpqp(mpc)
+        self.P = ldp.OracleProblem(mpqp.qp2ldp(self.qp, mpc.nu, soft_weight=mpc.soft_weight), mpc.nu)
+
+    def solve(self, Th, want_iters=False, want_active=True):
+        r = self.P.solve_batch(Th)
+        return dict(U=r["U"], exitflag=r["flag"], active_upper=r["act_u"], active_lower=r["act_l"])
+
+
+def _product_builder(lmpc):
+    import importlib
+    return importlib.import_module(lmpc.__name__ + ".explicit")
+
+
+def _walk(sol, Th, clip=None):
+    B = ldp.OracleBst(sol["halfplanes"], sol["feedbacks"], sol["hp_list"], sol["jump_list"], clip=clip)
+    return B.evaluate_batch(Th)[0]
+
+
+def test_explicit_builder_handles_soft_rows(lmpc):
+    """(f-2) ExplicitMPC on a controller WITH soft constraints (the reference makes them explicit through the
+    slack columns of make_singlesided, src/utils.jl:345-380): double integrator with a soft velocity bound.
+    explicit == implicit to 1e-8 on fresh parameters, including those where the soft row is active."""
+    from test_condense_cpu import mirror_of
+    ex = _product_builder(lmpc)
+    o = mpqp.double_integrator_hard(Np=3, Nc=3)
+    for c in o.constraints:
+        c.soft = True
+    m = mirror_of(lmpc, o)
+    q = m.condense()
+    assert np.count_nonzero(np.asarray(q["senses"]) & 8) >= 2
+    lo, hi = np.array([-3.0, -1.5, -2.0]), np.array([3.0, 1.5, 2.0])
+    S = _OracleSolver(o)
+    sol = ex.build_explicit(q, S, lo, hi, o.nu, n_samples=40000, soft_weight=o.soft_weight)
+    Th = mpqp.sample_theta(lo, hi, 20000, seed=17)
+    ref = S.P.solve_batch(Th)
+    assert np.count_nonzero(ref["flag"] == 2) > 500          # soft rows really are active in the sample
+    err = np.abs(_walk(sol, Th) - ref["U"])
+    # soft_weight = 1e6 puts cond ~1e6 into both computations: they agree to ~6e-9 where soft rows are active
+    assert np.max(err) < 1e-7 and np.mean(err < 1e-8) > 0.999
+
+
+def test_clipping_aware_tree_is_smaller_and_right_after_clipping(lmpc):
+    """build_tree!(...; clipping=true) is the reference default (src/explicit.jl:65): with the input bounds
+    as clipping values the leaves only have to be right AFTER clipping, so saturated regions are absorbed."""
+    ex = _product_builder(lmpc)
+    m, rng, _ = lmpc.mpc_examples("invpend", Np=20, Nc=3)
+    o = mpqp.invpend(Np=20, Nc=3)
+    q = m.condense()
+    lo, hi = np.array(rng[0]) * 0.5, np.array(rng[1]) * 0.5
+    lo[-1], hi[-1] = -2.0, 2.0
+    S = _OracleSolver(o)
+    clip = m.clipping_bounds()
+    assert np.array_equal(clip, [[-2.0, 2.0]])
+    exact = ex.build_explicit(q, S, lo, hi, 1, n_samples=60000)
+    clipped = ex.build_explicit(q, S, lo, hi, 1, n_samples=60000, clipping=clip)
+    Th = mpqp.sample_theta(lo, hi, 30000, seed=23)
+    ref = S.P.solve_batch(Th)["U"]
+    assert np.max(np.abs(_walk(exact, Th) - ref)) < 1e-9
+    assert np.max(np.abs(_walk(clipped, Th, clip=clip) - ref)) < 1e-9
+    assert len(clipped["hp_list"]) < len(exact["hp_list"]) and clipped["depth"][0] <= exact["depth"][0]
+
+
+def test_parametricdaqp_codegen_arrays_round_trip(lmpc, tmp_path):
+    """The reader of ParametricDAQP.codegen's emitted arrays (src/codegen.jl:62-66; same array style as
+    write_float_array, src/codegen.jl:220-236): a tree written in the package's layout and branch order is read
+    back bit for bit, its orientation is recognised from the evaluate function in the file, and the committed
+    sample (tests/golden/pdaqp_sample.c/.h) parses.  The format follows the package's public generator as
+    recollected; it is NOT pinned on a file produced by the real package (none is available here)."""
+    ex = _product_builder(lmpc)
+    z = np.load(GOLD)
+    path = str(tmp_path / "empc.c")
+    ex.write_pdaqp_codegen(path, z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], fname="empc")
+    t = ex.load_pdaqp_codegen(path)
+    assert t["le_child"] == 1 and t["nth"] == 7 and t["nu"] == 1 and t["fname"] == "empc"
+    # "%.20f" (the generator's format) keeps 20 decimals: exact to 5e-21 absolute, which is every bit of the
+    # entries that matter and a truncation only of numerically-zero ones (5e-19 and below)
+    assert np.max(np.abs(t["halfplanes"] - z["halfplanes"])) <= 5e-21 + 1e-16 * 0
+    assert np.max(np.abs(t["feedbacks"] - z["feedbacks"])) <= 5e-21
+    big = np.abs(z["halfplanes"]) > 1e-3
+    assert np.array_equal(t["halfplanes"][big], z["halfplanes"][big])
+    # the file holds the tree in the package's branch order: walking it with `id = next + (val <= b)` gives
+    # the leaves of the library-order walk
+    Th = mpqp.sample_theta(z["lo"], z["hi"], 2000, seed=31)
+    _, rego = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"]).evaluate_batch(Th)
+    for q in range(0, 2000, 41):
+        i = 0
+        while t["jump_list"][i] != 0:
+            hp = t["halfplanes"][t["hp_list"][i]]
+            i = i + t["jump_list"][i] + int(hp[:-1] @ Th[:, q] <= hp[-1])
+        assert t["hp_list"][i] == rego[q]
+    # library order written as such is recognised as such
+    ex.write_pdaqp_codegen(str(tmp_path / "lib.c"), z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"],
+                           fname="lib", le_child=0)
+    t0 = ex.load_pdaqp_codegen(str(tmp_path / "lib.c"))
+    assert t0["le_child"] == 0 and np.array_equal(t0["hp_list"], z["hp_list"]) and np.array_equal(t0["jump_list"], z["jump_list"])
+    # the committed sample
+    samp = os.path.join(os.path.dirname(GOLD), "pdaqp_sample.c")
+    ts = ex.load_pdaqp_codegen(samp)
+    assert ts["le_child"] == 1 and ts["halfplanes"].shape[1] == ts["nth"] + 1 and len(ts["hp_list"]) == len(ts["jump_list"])

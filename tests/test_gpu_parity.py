@@ -118,6 +118,29 @@ def test_default_output_bounds_never_end_infeasible_at_size(lmpc, scale):
     assert np.array_equal(np.asarray(out["U"])[:, sub], ref["U"])
 
 
+def test_closed_loop_at_config_3_size(lmpc):
+    """BASELINE config 3 at its stated size: AFTI-16, 10^6 initial states x 40 steps, warm start, the example's
+    scenario r = [0.1, 0] (mpc_examples.jl:206).  Size-independent properties on the whole batch (every step of
+    every loop ends with flag 1 or 2, finite states, running it twice gives the same bits) and a 1e5-loop
+    subsample equal to the oracle's loop bit for bit (states, last controls, flags, iteration totals)."""
+    import torch
+    mpc, qp, g, P = gpu_controller(lmpc, "aircraft")
+    nx, nr, nd, nup = mpc.parameter_dims()
+    N, T = 1_000_000, 40
+    lo, hi = util.theta_range("aircraft", 0.25)
+    X0 = mpqp.sample_theta(lo[:nx], hi[:nx], N, seed=2024)
+    a = g.simulate(mpc.F, mpc.G, X0, r=[0.1, 0.0], d=[0.0, 0.0], N=T, Gd=mpc.Gd, warm_start=True)
+    b = g.simulate(mpc.F, mpc.G, X0, r=[0.1, 0.0], d=[0.0, 0.0], N=T, Gd=mpc.Gd, warm_start=True)
+    assert np.all((a["exitflag"] == 1) | (a["exitflag"] == 2)) and np.all(np.isfinite(a["Xend"]))
+    assert np.all(np.abs(a["Ulast"]) <= 0.5 + 1e-9)                        # input bounds, mpc_examples.jl:188
+    assert np.array_equal(a["Xend"], b["Xend"]) and np.array_equal(a["iters"], b["iters"])
+    sub = np.random.default_rng(3).choice(N, 100_000, replace=False)
+    R = np.repeat(np.array([[0.1], [0.0]]), len(sub), axis=1)
+    ref = P.simulate_batch(mpc.F, mpc.G, mpc.Gd, X0[:, sub], R, np.zeros((nd, len(sub))), None, T, nr, nd, nup, warm=True)
+    assert np.array_equal(a["Xend"][:, sub], ref["Xend"]) and np.array_equal(a["Ulast"][:, sub], ref["Ulast"])
+    assert np.array_equal(a["exitflag"][sub], ref["flag"]) and np.array_equal(a["iters"][sub], ref["iters"])
+
+
 @pytest.mark.parametrize("fn", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz") and "_s" in f))
 def test_batch_matches_golden_fixture(lmpc, fn):
     z = np.load(os.path.join(GOLD, fn))
@@ -629,7 +652,7 @@ def test_async_entry_points_on_caller_streams(lmpc):
     assert torch.equal(U[0], U[1]) and g.stream() is not None
     # explicit evaluate, async
     z = np.load(os.path.join(GOLD, "invpend_explicit.npz"))
-    ge = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    ge = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"])
     Te = mpqp.sample_theta(z["lo"], z["hi"], N, seed=3)
     Ted = torch.tensor(np.ascontiguousarray(Te.T), dtype=torch.float64, device=dev)
     Ue = torch.empty((N, 1), dtype=torch.float64, device=dev)

@@ -81,7 +81,7 @@ def test_oriented_tree_import(lmpc):
     hl2, jl2 = _swap_children(z["hp_list"], z["jump_list"])
     # the swapped tree walked by a literal transcription of `id = next_id + (val <= b)` gives the same leaves
     Th = mpqp.sample_theta(z["lo"], z["hi"], 4000, seed=11)
-    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"])
     Uo, rego = B.evaluate_batch(Th)
     for q in range(0, 4000, 97):
         i = 0
@@ -89,9 +89,9 @@ def test_oriented_tree_import(lmpc):
             hp = z["halfplanes"][hl2[i]]
             i = i + jl2[i] + int(hp[:-1] @ Th[:, q] <= hp[-1])
         assert hl2[i] == rego[q]
-    a = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], dims=(4, 2, 0, 1))
-    b = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], hl2, jl2, dims=(4, 2, 0, 1), le_child=1)
-    c = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], hl2, jl2, dims=(4, 2, 0, 1), le_child=0)
+    a = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"], dims=(4, 2, 0, 1))
+    b = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], hl2, jl2, clipping=z["clipping"], dims=(4, 2, 0, 1), le_child=1)
+    c = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], hl2, jl2, clipping=z["clipping"], dims=(4, 2, 0, 1), le_child=0)
     Ua, ra = a.evaluate(Th)
     Ub, rb = b.evaluate(Th)
     Uc, rc = c.evaluate(Th)
@@ -114,8 +114,8 @@ def test_single_process_multi_device_closed_loop_and_explicit(lmpc):
     assert np.array_equal(one["Xend"], two["Xend"]) and np.array_equal(one["exitflag"], two["exitflag"])
     assert np.array_equal(one["Ulast"], two["Ulast"])
     z = np.load(GOLD)
-    e1 = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], dims=(4, 2, 0, 1))
-    e2 = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], dims=(4, 2, 0, 1),
+    e1 = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"], dims=(4, 2, 0, 1))
+    e2 = lmpc.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"], dims=(4, 2, 0, 1),
                              devices=devs)
     Th = mpqp.sample_theta(z["lo"], z["hi"], 70001, seed=3)
     U1, r1 = e1.evaluate(Th)
@@ -203,3 +203,29 @@ def test_chain_two_pass_cta_path(lmpc):
     out, ref = g.solve(Th), P.solve_batch(Th)
     assert np.array_equal(out["U"], ref["U"]) and np.array_equal(out["iters"], ref["iters"])
     assert g.tiering()[1] == mid
+
+
+def test_certified_iteration_bound_sizes_the_kernel(lmpc):
+    """(f-4) certify(mpc; range).max_iterations (src/certify.jl:18-29) as `certified_iterations`: a hard
+    iteration cap and a smaller on-chip capacity.  The chain of masses restricted to a quarter of its range
+    never needs more than ~56 iterations, so with a bound of 60 its factor shrinks from 180 to 60 rows: eight
+    QPs per CTA in warp mode instead of one per CTA.  Same bits as the oracle given the same cap / limit; an
+    instance outside the certified range ends with the iteration-limit flag instead of a wrong answer."""
+    mpc = util.controller("chain")
+    qp = mpqp.mpc2mpqp(mpc)
+    st = lmpc.default_settings(certified_iterations=60)
+    g = lmpc.setup_gpu(qp, nu=mpc.nu, dims=mpc.parameter_dims(), settings=st)
+    assert g.cap == 60 and g.tiering()[0] == 0
+    cst = g.ldp_constants()
+    P = util.oracle_from_constants(qp, mpc.nu, cst, iter_limit=61)
+    lo, hi = util.theta_range("chain", 0.25)
+    Th = mpqp.sample_theta(lo, hi, 3000, seed=8)
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    assert np.all(ref["flag"] == 1) and ref["iters"].max() <= 60
+    for a, b in (("exitflag", "flag"), ("iters", "iters"), ("active_upper", "act_u"), ("active_lower", "act_l")):
+        assert np.array_equal(out[a], ref[b]), a
+    assert np.array_equal(out["U"], ref["U"])
+    lo, hi = util.theta_range("chain", 1.0)                  # outside the certificate's range
+    Th = mpqp.sample_theta(lo, hi, 200, seed=8)
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    assert np.array_equal(out["exitflag"], ref["flag"]) and np.all(out["exitflag"] == -4)

@@ -157,8 +157,8 @@ if "explicit_sim" in which:
     # closed loop with the explicit law (Simulation(empc)): 2e6 x0, 100 steps, tree walk + dynamics on chip
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
     mpc = util.controller("invpend")
-    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], dims=mpc.parameter_dims())
-    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"], dims=mpc.parameter_dims())
+    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"])
     N, T = 2_000_000, 100
     lo, hi = util.theta_range("invpend", 0.25)
     X0 = rand_theta(lo[:4], hi[:4], N)
@@ -182,8 +182,8 @@ if "explicit_sim" in which:
                       "cpu_cores": ldp.num_threads(), "bit_identical_to_oracle_on_sample": same}), flush=True)
 if "explicit" in which:
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
-    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
-    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"])
+    B = ldp.OracleBst(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clip=z["clipping"])
     N = 100_000_000
     Th = rand_theta(z["lo"], z["hi"], N)
     U = torch.empty((N, 1), dtype=torch.float64, device=dev)

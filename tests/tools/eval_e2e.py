@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "t
 import numpy as np, lmpc_b200
 from oracle import mpqp
 z = np.load("tests/golden/invpend_explicit.npz")
-g = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+g = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"])
 N = 10_000_000
 Th = np.asfortranarray(mpqp.sample_theta(z["lo"], z["hi"], N, seed=1))
 L = lmpc_b200.lib()

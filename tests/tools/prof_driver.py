@@ -30,7 +30,7 @@ if which == "sim":
         assert rc == 0
 elif which == "bst":
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "invpend_explicit.npz"))
-    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"])
+    ge = lmpc_b200.GpuExplicitMPC(z["halfplanes"], z["feedbacks"], z["hp_list"], z["jump_list"], clipping=z["clipping"])
     N = 20_000_000
     Th = rand_theta(z["lo"], z["hi"], N); U = torch.empty((N, 1), dtype=torch.float64, device=dev)
     for _ in range(4): ge.evaluate_async(Th, U, N=N)
