@@ -39,6 +39,9 @@ constexpr int K2_BLOCK = K2_WARPS * 32;
 constexpr int K2_UF_SOLVE = 4;
 constexpr int K2_UF_SIM = 2;
 constexpr unsigned FULL = 0xffffffffu;
+// internal: this instance needs the factorisation repair (wq_rebuild); the fast kernel leaves it to the second,
+// repair-capable launch (never seen by the caller)
+constexpr int EXIT_REDO = -100;
 
 LMPC_DEVINL double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 LMPC_DEVINL double shfl_down_d(double v, int d) { return __shfl_down_sync(FULL, v, d); }
@@ -251,12 +254,19 @@ __device__ __noinline__ WarpQp wq_rebuild(const WarpCtx c, WarpQp s) {
   return s;
 }
 // a soft row is in the working set: a pivot below zero_tol is then suspect (see wq_rebuild)
+#ifndef K2_REPAIR
+#define K2_REPAIR 1
+#endif
 LMPC_DEVINL bool wq_has_soft(const WarpCtx &c, const WarpQp &s) {
-  return c.lay->nsoft > 0 && __any_sync(FULL, c.lane < s.k && s.soft);
+  return K2_REPAIR && c.lay->nsoft > 0 && __any_sync(FULL, c.lane < s.k && s.soft);
 }
 
 // The dual active-set loop for one QP (oracle: ldp_loop).  sh0/sh1: shifts of rows lane, lane+32.
-template <int UF>
+// REPAIR = false: the hot variant.  Where the repair would run (problems with soft rows only: a pivot below
+// zero_tol next to a soft row, or the cycle guard's second chance) it stops with EXIT_REDO instead, and the
+// instance is solved again from scratch by the REPAIR = true kernel launched right after (r02: keeping the
+// out-of-line rebuild call in the one kernel cost every solve 6-9 % in spills around the call site).
+template <int UF, bool REPAIR>
 LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, double &u, int &iters) {
   const LdpLayout &lay = *c.lay;
   const LdpSettings &st = *c.st;
@@ -329,6 +339,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         else if (cycle++ > st.cycle_tol) {
           // second chance for problems with soft rows: refactorise once, restart the count
           if (repaired || !wq_has_soft(c, s)) { flag = EXIT_CYCLE; break; }
+          if (!REPAIR) { flag = EXIT_REDO; break; }
           repaired = true; rebuilt = true; best_fval = -1.0; cycle = 0;
         }
         if (k >= lay.cap || k >= 32) { flag = EXIT_CAPACITY; break; }
@@ -337,9 +348,12 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         const bool addlow = __shfl_sync(FULL, (int)bestlow, src);
         const double addd = shfl_d(bestd, src);
         if (lane < k) s.lam = s.lams;
-        if (rebuilt) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
+        if constexpr (REPAIR) { if (rebuilt) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } } }
         wq_add<UF>(c, s, add, addlow, addd);
-        if (s.sing && wq_has_soft(c, s)) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
+        if (s.sing && wq_has_soft(c, s)) {
+          if constexpr (REPAIR) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
+          else { flag = EXIT_REDO; break; }
+        }
         continue;
       }
       // 4. blocking: ratio test against lam* - lam
@@ -371,14 +385,17 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
     if (rm < 0) { flag = noblock; break; }   // regular: blocked but no finite ratio (NaN guard)
     if (lane < k) s.lam = fma(alpha, dir, s.lam);
     wq_remove(c, s, rm);
-    if (s.sing && wq_has_soft(c, s)) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
+    if (s.sing && wq_has_soft(c, s)) {
+      if constexpr (REPAIR) { s = wq_rebuild<UF>(c, s); if (s.rc) { flag = s.rc; break; } }
+      else { flag = EXIT_REDO; break; }
+    }
   }
   iters = iter;
   return flag;
 }
 
 // one solve for theta in c.thw; returns the flag; u (lane c holds u_c) and iters by reference
-template <int UF, bool EQ>
+template <int UF, bool EQ, bool REPAIR>
 LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int &iters, double &sho,
                          bool warm = false, unsigned long long wsu = 0ull, unsigned long long wsl = 0ull) {
   const LdpLayout &lay = *c.lay;
@@ -436,7 +453,7 @@ LMPC_DEVINL int wq_solve(const WarpCtx &c, WarpQp &s, bool cold, double &u, int 
     if (lane < s.k) s.dW = (s.low ? c.cv.dl[j] : c.cv.du[j]) + (j < 32 ? shj_lo : shj_hi);
   }
   iters = 0;
-  if (flag == 0) flag = wq_loop<UF>(c, s, sh0, sh1, u, iters);
+  if (flag == 0) flag = wq_loop<UF, REPAIR>(c, s, sh0, sh1, u, iters);
   return flag;
 }
 
@@ -465,11 +482,11 @@ LMPC_DEVINL WarpCtx make_ctx(double *smem, const LdpLayout &lay, const LdpSettin
   return c;
 }
 
-template <bool EQ>
+template <bool EQ, bool REPAIR>
 __global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                 const double *__restrict__ cblk, ThetaSegs th,
-                int64_t Ninst, SolveOut out) {
+                int64_t Ninst, SolveOut out, int redo) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
@@ -480,6 +497,7 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
   WarpQp s;
   double u = 0.0;
   for (int64_t q = wid; q < Ninst; q += wstride) {
+    if (redo && out.flag[q] != EXIT_REDO) continue;      // second launch: only what the fast kernel handed over
     // batched mpc_update_parameter: gather theta from its row segments (coalesced per segment)
     int o = 0;
 #pragma unroll
@@ -495,7 +513,7 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
     int iters;
     const bool warm = EQ && out.ws_u != nullptr;
     double sho = 0.0;
-    const int flag = wq_solve<K2_UF_SOLVE, EQ>(c, s, true, u, iters, sho, warm, warm ? out.ws_u[q * words] : 0ull,
+    const int flag = wq_solve<K2_UF_SOLVE, EQ, REPAIR>(c, s, true, u, iters, sho, warm, warm ? out.ws_u[q * words] : 0ull,
                                                warm ? out.ws_l[q * words] : 0ull);
     for (int i = 0; i < lay.nu; ++i) {
       const double ctl = control_out_w(c, i, u, sho);
@@ -512,7 +530,9 @@ ldp_warp_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ L
     if (lane == 0) {
       out.flag[q] = flag;
       if (out.iters) out.iters[q] = iters;
-      if (out.act_u) { out.act_u[q * words] = au; out.act_l[q * words] = al; }
+      // (an instance handed over to the repair launch keeps its input working-set words: they may be the
+      // warm start it has to begin from again)
+      if (out.act_u && (REPAIR || flag != EXIT_REDO)) { out.act_u[q * words] = au; out.act_l[q * words] = al; }
     }
     __syncwarp();
   }
@@ -537,11 +557,11 @@ LMPC_DEVINL void step_rows(const double *A, const double *B, const double *Bd, c
 
 // EXT: separate true plant, steady-state observer and measurement noise (lmpc_gpu_simulate_batch_ex);
 // compiled as its own kernel so the plain closed loop keeps its instruction footprint
-template <bool EQ, bool EXT>
+template <bool EQ, bool EXT, bool REPAIR>
 __global__ void __launch_bounds__(K2_BLOCK, K2_MINB)
 ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ LdpSettings st,
                     const double *__restrict__ cblk,
-                    int64_t Ninst, SimDesc sd, int32_t *flagout, int32_t *itersout) {
+                    int64_t Ninst, SimDesc sd, int32_t *flagout, int32_t *itersout, int redo) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   stage_constants_tma(smem, cblk, lay.total, &mbar);
@@ -558,6 +578,7 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
   WarpQp s;
   double u = 0.0;
   for (int64_t q = wid; q < Ninst; q += wstride) {
+    if (redo && flagout[q] != EXIT_REDO) continue;       // second launch: whole closed loops handed over
     _Pragma("unroll 1")
     for (int i = lane; i < nx; i += 32) { c.thw[i] = ld_stream(sd.X0 + q * nx + i); if (EXT) xsw[i] = c.thw[i]; }
     _Pragma("unroll 1")
@@ -606,8 +627,9 @@ ldp_warp_sim_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant
       }
       int iters;
       double sho = 0.0;
-      const int f = wq_solve<K2_UF_SIM, EQ>(c, s, !(sd.warm && t > 0), u, iters, sho);
+      const int f = wq_solve<K2_UF_SIM, EQ, REPAIR>(c, s, !(sd.warm && t > 0), u, iters, sho);
       tot += iters;
+      if (!REPAIR && f == EXIT_REDO) { worst = EXIT_REDO; break; }   // the repair-capable launch redoes this loop
       if (f < 0) { if (worst > 0 || f < worst) worst = f; }
       else if (worst > 0 && f > worst) worst = f;
       for (int i = 0; i < nu; ++i) {
@@ -659,38 +681,50 @@ bool ldp_warp_supports(const LdpLayout &lay) {
   return lay.n >= 1 && lay.n <= 32 && lay.cap <= 32 && lay.m <= 64 && k2_smem(lay, 64) <= 200 * 1024;
 }
 
-template <bool EQ>
+template <bool EQ, bool REPAIR>
 static int launch_warp_t(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
                          const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
-                         int sm_count, cudaStream_t s) {
+                         int sm_count, cudaStream_t s, int redo) {
   const size_t smem = k2_smem(lay, sim ? sim->nx + lay.nu + (sim->ext ? sim->nx + sim->ny : 0) : 0);
   int per_sm = 0;
   int64_t blocks = (N + K2_WARPS - 1) / K2_WARPS;
   cudaError_t e;
   if (sim) {
-    auto kern = sim->ext ? ldp_warp_sim_kernel<EQ, true> : ldp_warp_sim_kernel<EQ, false>;
+    auto kern = sim->ext ? ldp_warp_sim_kernel<EQ, true, REPAIR> : ldp_warp_sim_kernel<EQ, false, REPAIR>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_BLOCK, smem);
     if (per_sm < 1) per_sm = 1;
     if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
-    kern<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, N, *sim, out.flag, out.iters);
+    kern<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, N, *sim, out.flag, out.iters, redo);
   } else {
-    auto kern = ldp_warp_kernel<EQ>;
+    auto kern = ldp_warp_kernel<EQ, REPAIR>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K2_BLOCK, smem);
     if (per_sm < 1) per_sm = 1;
     if (blocks > (int64_t)sm_count * per_sm) blocks = (int64_t)sm_count * per_sm;
-    kern<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, th, N, out);
+    kern<<<(unsigned)blocks, K2_BLOCK, smem, s>>>(lay, st, cblk, th, N, out, redo);
   }
   return (int)cudaGetLastError();
+}
+
+// Problems without soft rows never repair: one launch of the fast kernel.  With soft rows: the fast kernel,
+// then the repair-capable one over the instances (closed loops) it handed over -- none on the BASELINE
+// AFTI-16 controller, a few percent with output bounds on the whole horizon.
+template <bool EQ>
+static int launch_warp_2(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
+                         const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
+                         int sm_count, cudaStream_t s) {
+  int e = launch_warp_t<EQ, false>(lay, st, cblk, th, N, out, sim, sm_count, s, 0);
+  if (e != 0 || lay.nsoft == 0 || !K2_REPAIR) return e;
+  return launch_warp_t<EQ, true>(lay, st, cblk, th, N, out, sim, sm_count, s, 1);
 }
 
 int launch_ldp_warp(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
                     const ThetaSegs &th, int64_t N, const SolveOut &out, const SimDesc *sim,
                     int sm_count, void *stream) {
   if (N <= 0) return 0;
-  return (lay.neq > 0 || out.ws_u) ? launch_warp_t<true>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream)
-                     : launch_warp_t<false>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream);
+  return (lay.neq > 0 || out.ws_u) ? launch_warp_2<true>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream)
+                     : launch_warp_2<false>(lay, st, cblk, th, N, out, sim, sm_count, (cudaStream_t)stream);
 }
