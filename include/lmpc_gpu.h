@@ -348,8 +348,9 @@ int lmpc_gpu_evaluate_batch_multi(lmpc_bst_multi *t, const double *Theta, int64_
 /* ---------------------------------------------------------------------------------------------
  * Host-side condensing: build the dense mpQP from a discrete-time model without
  * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
- * path supports: no offsets, binaries or generalized parameters (previews of r and d and a
- * prestabilising feedback are supported, reference condensation is not).  Pure host code; needs no GPU.
+ * path supports: move blocking, previews of r and d, a prestabilising feedback, generalized (affine)
+ * parameters with or without a parameter preview; no model offsets, binaries or reference condensation.
+ * Pure host code; needs no GPU.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
   int32_t rows;
@@ -363,6 +364,8 @@ typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= 
   int32_t nks;
   int32_t soft;             /* src/setup.jl:94: output bounds are soft by default */
   int32_t prio;
+  const double *Ap;         /* rows x np: generalized (affine) parameter term Ap p on the constrained side
+                             * (add_constraint!(...; Ap), src/setup.jl:61-84; W gets -Ap, mpc2mpqp.jl:125-143), NULL = 0 */
 } lmpc_constraint;
 
 typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.jl:17-41) */
@@ -392,12 +395,23 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
    * NULL = 0.  The QP is then over v, the control bounds become general rows (ms = 0), and the same K
    * must be given to lmpc_gpu_create for the output map u = z[1:nu] - K x (src/utils.jl:46-50). */
   const double *K;
+  /* generalized (affine) parameters p, constant over the horizon (parameter_preview off): the linear cost
+   * (Ex p + ex)'x_k + (Eu p + eu)'u_k of set_objective!(...; Ex, ex, Eu, eu) (src/setup.jl:118-132,
+   * mpc2mpqp.jl:478-508) and the constraints' Ap.  theta = [x; r; d; uprev; p].  Ex nx x np, ex nx,
+   * Eu nu x np, eu nu (any NULL = 0; every block given must have exactly np columns, as the reference
+   * demands, mpc2mpqp.jl:486-490); np = 0: none. */
+  int32_t np;
+  const double *Ex, *ex, *Eu, *eu;
+  /* settings.parameter_preview (src/types.jl:58): theta ends with Np blocks p_0 .. p_{Np-1} of np values instead
+   * of one; stage k pairs u_k and x_{k+1} with p_k (stage_parameter_matrix, mpc2mpqp.jl:148), a constraint at
+   * ks = k sees block min(k, Np) (parameter_preview_direct, mpc2mpqp.jl:125-143) */
+  int32_t parameter_preview;
 } lmpc_model;
 
 typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */
 
 int lmpc_gpu_condense(const lmpc_model *model, lmpc_mpqp **out);
-/* dims9 = {n, m, ms, nth, nu, nx, nr, nd, nuprev}: theta = [x(nx); r(nr); d(nd); uprev(nuprev)] */
+/* dims9 = {n, m, ms, nth, nu, nx, nr, nd, nuprev}: theta = [x(nx); r(nr); d(nd); uprev(nuprev); p(nth - the rest)] */
 int lmpc_gpu_mpqp_dims(const lmpc_mpqp *q, int32_t *dims9);
 /* copy out, column-major: H n x n, f n, f_theta n x nth, A (m-ms) x n, bu m, bl m, W m x nth, senses m */
 int lmpc_gpu_mpqp_get(const lmpc_mpqp *q, double *H, double *f, double *f_theta, double *A,

@@ -34,7 +34,8 @@ extern "C" int lmpc_gpu_abi_layout(int32_t *out, int32_t cap) {
   emit(o, LMPC_ABI_CONSTRAINT, sizeof(lmpc_constraint),
        {F(lmpc_constraint, rows), F(lmpc_constraint, Au), F(lmpc_constraint, Ax), F(lmpc_constraint, Ar),
         F(lmpc_constraint, Ad), F(lmpc_constraint, Aup), F(lmpc_constraint, ub), F(lmpc_constraint, lb),
-        F(lmpc_constraint, ks), F(lmpc_constraint, nks), F(lmpc_constraint, soft), F(lmpc_constraint, prio)});
+        F(lmpc_constraint, ks), F(lmpc_constraint, nks), F(lmpc_constraint, soft), F(lmpc_constraint, prio),
+        F(lmpc_constraint, Ap)});
   emit(o, LMPC_ABI_MODEL, sizeof(lmpc_model),
        {F(lmpc_model, nx), F(lmpc_model, nu), F(lmpc_model, ny), F(lmpc_model, nd), F(lmpc_model, Np),
         F(lmpc_model, Nc), F(lmpc_model, F), F(lmpc_model, G), F(lmpc_model, C), F(lmpc_model, Gd),
@@ -42,7 +43,8 @@ extern "C" int lmpc_gpu_abi_layout(int32_t *out, int32_t cap) {
         F(lmpc_model, umin), F(lmpc_model, umax), F(lmpc_model, constraints), F(lmpc_model, n_constraints),
         F(lmpc_model, reference_tracking), F(lmpc_model, preprocess), F(lmpc_model, move_blocks),
         F(lmpc_model, n_move_blocks), F(lmpc_model, reference_preview), F(lmpc_model, disturbance_preview),
-        F(lmpc_model, K)});
+        F(lmpc_model, K), F(lmpc_model, np), F(lmpc_model, Ex), F(lmpc_model, ex), F(lmpc_model, Eu),
+        F(lmpc_model, eu), F(lmpc_model, parameter_preview)});
   if (out)
     for (int32_t i = 0; i < cap && i < (int32_t)o.size(); ++i) out[i] = o[i];
   return (int32_t)o.size();

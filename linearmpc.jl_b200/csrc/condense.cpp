@@ -121,7 +121,10 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     if (c.Aup) for (int i = 0; i < c.rows * nu; ++i) if (c.Aup[i] != 0.0) aup = true;
   }
   const int nup = (any_nonzero(Rr) || aup) ? nu : 0;
-  const int nxe = nx + nr + nd + nup, nth = nx + nrp + ndp + nup;
+  // generalized parameters: the last block of theta, np values, or Np blocks of np with parameter_preview
+  const int npb = md->np > 0 ? md->np : 0, pp = (md->parameter_preview && npb > 0) ? 1 : 0;
+  const int npar = pp ? npb * Np : npb;
+  const int nxe = nx + nr + nd + nup, nth = nx + nrp + ndp + nup + npar, opar = nth - npar;
   // column of theta that holds extended-state entry j (insert_preview_parameter_blocks, mpc2mpqp.jl:70-92)
   auto th_col = [&](int j) { return j < nx + nr ? j : (j < nx + nr + nd ? j - nr + nrp : j - nr - nd + nrp + ndp); };
 
@@ -252,6 +255,29 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     for (int i = 0; i < n; ++i) for (int j = 0; j < nxe; ++j) fth(i, th_col(j)) += StP(i, j);
   }
   { Mat Hs(n, n); for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Hs(i, j) = 0.5 * (H(i, j) + H(j, i)); H = Hs; }
+  // generalized-parameter cost (mpc2mpqp.jl:478-508): f += Umap' rep(eu) + Gx' rep(ex), and the p columns of
+  // f_theta = Umap' rep(Eu) + Gx' rep(Ex); Umap picks the Nc moves out of the first Nc of the Np stages, Gx is
+  // the plant-state part of the predictor rows x_1 .. x_Np
+  std::vector<double> fvec(n, 0.0);
+  // (stage_parameter_matrix, mpc2mpqp.jl:148: with parameter_preview stage k pairs u_k and x_{k+1} with p block k)
+  if (md->ex || md->eu || npar > 0) {
+    const Mat Exm = from_colmajor(md->Ex, nx, npb), Eum = from_colmajor(md->Eu, nu, npb);
+    for (int b = 0; b < Nc; ++b)
+      for (int i = 0; i < nu; ++i) {
+        if (md->eu) fvec[b * nu + i] += md->eu[i];
+        for (int j = 0; j < npb; ++j) fth(b * nu + i, opar + (pp ? b * npb : 0) + j) += Eum(i, j);
+      }
+    for (int k = 1; k <= Np; ++k)
+      for (int i = 0; i < nx; ++i) {
+        const double exi = md->ex ? md->ex[i] : 0.0;
+        for (int c2 = 0; c2 < n; ++c2) {
+          const double gx = Gam(k * nxe + i, c2);
+          if (gx == 0.0) continue;
+          fvec[c2] += gx * exi;
+          for (int j = 0; j < npb; ++j) fth(c2, opar + (pp ? (k - 1) * npb : 0) + j) += gx * Exm(i, j);
+        }
+      }
+  }
 
   // ---- constraints ------------------------------------------------------------------------------------
   std::vector<double> bu, bl;
@@ -331,6 +357,8 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
         for (int j = 0; j < n; ++j) ar[j] = Ak(i, j);
         for (int j = 0; j < nxe; ++j) wr[th_col(j)] = -Wk(i, j);
         for (int j = 0; j < Wdk.c; ++j) wr[nx + nrp + j] = -Wdk(i, j);
+        // parameter_preview_direct (mpc2mpqp.jl:125-143): constraint stage k sees p block min(k, Np)
+        if (c.Ap) for (int j = 0; j < npb; ++j) wr[opar + (pp ? (std::min(k, Np) - 1) * npb : 0) + j] = -c.Ap[(size_t)j * mi + i];
         Arows.push_back(ar); Wrows.push_back(wr);
         gbu.push_back(c.ub ? c.ub[i] : 1e30); gbl.push_back(c.lb ? c.lb[i] : -1e30);
         gsoft.push_back(c.soft ? 1 : 0); gprio.push_back(c.prio);
@@ -374,6 +402,11 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     const Mat Tt = tr(T);
     H = mul(Tt, mul(H, T));
     fth = mul(Tt, fth);
+    {
+      std::vector<double> f2(nnew, 0.0);
+      for (int j = 0; j < n; ++j) for (int c2 = 0; c2 < nnew; ++c2) f2[c2] += T(j, c2) * fvec[j];
+      fvec.swap(f2);
+    }
     if (ms > 0) {
       std::vector<double> bu2, bl2;
       for (int r : keep) { bu2.push_back(bu[r]); bl2.push_back(bl[r]); }
@@ -462,7 +495,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   lmpc_mpqp *q = new lmpc_mpqp();
   const int mg = (int)Arows.size(), m = ms + mg;
   q->n = nq; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nrp; q->nd = ndp; q->nuprev = nup; q->nu = nu;
-  q->H = H; q->f_theta = fth; q->f.assign(nq, 0.0);
+  q->H = H; q->f_theta = fth; q->f = fvec;
   q->A = Mat(mg, nq); q->W = Mat(m, nth);
   for (int i = 0; i < ms; ++i) for (int j = 0; j < nth; ++j) q->W(i, j) = W(i, j);
   q->bu = bu; q->bl = bl;

@@ -407,9 +407,10 @@ class GpuMPC:
         return lib().lmpc_gpu_stream(self._h)
 
     # -- form_parameter / compute_control -----------------------------------------------------
-    def form_parameter(self, x, r=None, d=None, uprev=None):
-        """theta = [x; r; d; uprev] per column (explicit.jl:54-63); missing r/d default to 0 and
-        missing uprev to the controller's stored previous control (utils.jl:48, explicit.jl:60)."""
+    def form_parameter(self, x, r=None, d=None, uprev=None, p=None):
+        """theta = [x; r; d; uprev; p] per column (explicit.jl:54-63); missing r/d/p default to 0 and
+        missing uprev to the controller's stored previous control (utils.jl:48, explicit.jl:60).
+        p: the generalized parameters (format_affine_parameters, utils.jl:225-240), nth - the rest rows."""
         if self.dims is None:
             raise ValueError("GpuMPC was built without dims=(nx, nr, nd, nuprev)")
         nx, nr, nd, nup = self.dims
@@ -437,12 +438,15 @@ class GpuMPC:
         Rm, Dm, Um = blk(r, nr), blk(d, nd), blk(uprev, nup, self.uprev)
         if nd > 0 and Dm.shape[0] != nd:
             raise ValueError(f"Disturbance vector must have length {nd}")
-        return np.asfortranarray(np.vstack([X, Rm, Dm, Um]))
+        npar = max(0, getattr(self, "nth", nx + nr + nd + nup) - (nx + nr + nd + nup))
+        if npar == 0 and p is not None and np.size(p):
+            raise ValueError("this controller has no generalized parameters")
+        return np.asfortranarray(np.vstack([X, Rm, Dm, Um, blk(p, npar)]))
 
-    def compute_control(self, x, r=None, d=None, uprev=None, check=True):
+    def compute_control(self, x, r=None, d=None, uprev=None, p=None, check=True):
         """Batched compute_control (utils.jl:43-51): returns nu x N (a vector for a single x)."""
         single = np.ndim(x) == 1
-        Th = self.form_parameter(x, r, d, uprev)
+        Th = self.form_parameter(x, r, d, uprev, p)
         out = self.solve(Th, want_iters=False, want_active=False)
         if check:
             assert np.all(out["exitflag"] >= 1), "exitflag < 1 (utils.jl:46)"
@@ -856,7 +860,8 @@ class GpuExplicitMPC:
 class _Constraint(C.Structure):
     _fields_ = [("rows", C.c_int32), ("Au", C.c_void_p), ("Ax", C.c_void_p), ("Ar", C.c_void_p),
                 ("Ad", C.c_void_p), ("Aup", C.c_void_p), ("ub", C.c_void_p), ("lb", C.c_void_p),
-                ("ks", C.c_void_p), ("nks", C.c_int32), ("soft", C.c_int32), ("prio", C.c_int32)]
+                ("ks", C.c_void_p), ("nks", C.c_int32), ("soft", C.c_int32), ("prio", C.c_int32),
+                ("Ap", C.c_void_p)]
 
 
 class _Model(C.Structure):
@@ -868,7 +873,9 @@ class _Model(C.Structure):
                 ("constraints", C.c_void_p), ("n_constraints", C.c_int32),
                 ("reference_tracking", C.c_int32), ("preprocess", C.c_int32),
                 ("move_blocks", C.c_void_p), ("n_move_blocks", C.c_void_p),
-                ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32), ("K", C.c_void_p)]
+                ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32), ("K", C.c_void_p),
+                ("np", C.c_int32), ("Ex", C.c_void_p), ("ex", C.c_void_p), ("Eu", C.c_void_p), ("eu", C.c_void_p),
+                ("parameter_preview", C.c_int32)]
 
 
 def _diag(v, n):
@@ -901,6 +908,8 @@ class MPC:
         self.reference_tracking, self.preprocess_mpqp, self.soft_weight = True, True, 1e6
         self.reference_preview = self.disturbance_preview = False   # types.jl:56-57
         self.K = None                                               # prestabilising feedback, setup.jl:186-199
+        self.Ex = self.ex = self.Eu = self.eu = None                # generalized-parameter cost, setup.jl:118-132
+        self.parameter_preview = False                              # types.jl:58,69
         self.move_blocks = []
         self.gpu = None
         self.mpqp = None
@@ -954,12 +963,23 @@ class MPC:
         self.Nc = max(sum(b[:-1]) for b in self.move_blocks) + 1
 
     # setup.jl:118-132
-    def set_objective(self, Q=None, R=None, Rr=None, Qf=None):
+    def set_objective(self, Q=None, R=None, Rr=None, Qf=None, Ex=None, ex=None, Eu=None, eu=None):
         if Q is not None: self.Q = _diag(Q, self.ny)
         if R is not None: self.R = _diag(R, self.nu)
         if Rr is not None: self.Rr = _diag(Rr, self.nu)
         if Qf is not None: self.Qf = _diag(Qf, self.ny)
+        # linear cost (Ex p + ex)'x_k + (Eu p + eu)'u_k in the generalized parameter p
+        if Ex is not None: self.Ex = np.asarray(Ex, np.float64).reshape(self.nx, -1)
+        if ex is not None: self.ex = np.asarray(ex, np.float64).reshape(self.nx)
+        if Eu is not None: self.Eu = np.asarray(Eu, np.float64).reshape(self.nu, -1)
+        if eu is not None: self.eu = np.asarray(eu, np.float64).reshape(self.nu)
         self.gpu = None
+
+    def affine_parameter_dim(self):
+        """np: the widest generalized-parameter block in use (get_affine_parameter_base_dim, utils.jl:207-217)."""
+        dims = [0] + [E.shape[1] for E in (self.Ex, self.Eu) if E is not None]
+        dims += [c["Ap"].shape[1] for c in self.constraints if c["Ap"] is not None]
+        return max(dims)
 
     # setup.jl:36-46
     def set_input_bounds(self, umin=None, umax=None):
@@ -973,7 +993,7 @@ class MPC:
         self.gpu = None
 
     # setup.jl:61-84
-    def add_constraint(self, Ax=None, Au=None, Ar=None, Ad=None, Aup=None, ub=(), lb=(), ks=None,
+    def add_constraint(self, Ax=None, Au=None, Ar=None, Ad=None, Aup=None, Ap=None, ub=(), lb=(), ks=None,
                        soft=False, prio=0):
         if Ax is None and Au is None:
             return
@@ -986,6 +1006,7 @@ class MPC:
         ks = np.ascontiguousarray(list(range(2, self.Np + 1)) if ks is None else list(ks), np.int32)
         self.constraints.append(dict(rows=m, Au=mat(Au, self.nu), Ax=mat(Ax, self.nx), Ar=mat(Ar, self.ny),
                                      Ad=mat(Ad, self.nd), Aup=mat(Aup, self.nu), ub=ub, lb=lb, ks=ks,
+                                     Ap=None if Ap is None else np.asfortranarray(np.asarray(Ap, np.float64).reshape(m, -1)),
                                      soft=int(bool(soft)), prio=int(prio)))
         self.gpu = None
 
@@ -1015,15 +1036,23 @@ class MPC:
                 return None
             a = np.asfortranarray(np.asarray(a, np.float64)); keep.append(a)
             return a.ctypes.data
+        npar = self.affine_parameter_dim()
+        def wide(a, rows):                       # every block in use must have np columns (mpc2mpqp.jl:486-490)
+            if a is not None and a.shape[1] != npar:
+                raise ValueError(f"generalized-parameter blocks (Ex, Eu, Ap) must all have {npar} columns")
+            return a
         cons = (_Constraint * max(len(self.constraints), 1))()
         for i, c in enumerate(self.constraints):
             cons[i] = _Constraint(c["rows"], cm(c["Au"]), cm(c["Ax"]), cm(c["Ar"]), cm(c["Ad"]), cm(c["Aup"]),
-                                  cm(c["ub"]), cm(c["lb"]), c["ks"].ctypes.data, len(c["ks"]), c["soft"], c["prio"])
+                                  cm(c["ub"]), cm(c["lb"]), c["ks"].ctypes.data, len(c["ks"]), c["soft"], c["prio"],
+                                  cm(wide(c["Ap"], c["rows"])))
         md = _Model(self.nx, self.nu, self.ny, self.nd, self.Np, self.Nc, cm(self.F), cm(self.G), cm(self.C),
                     cm(self.Gd), cm(self.Dd), cm(self.Q), cm(self.R), cm(self.Rr), cm(self.Qf),
                     cm(self.umin), cm(self.umax), C.cast(cons, C.c_void_p), len(self.constraints),
                     int(self.reference_tracking), int(self.preprocess_mpqp), None, None,
-                    int(self.reference_preview), int(self.disturbance_preview), cm(self.K))
+                    int(self.reference_preview), int(self.disturbance_preview), cm(self.K),
+                    npar, cm(wide(self.Ex, self.nx)), cm(self.ex), cm(wide(self.Eu, self.nu)), cm(self.eu),
+                    int(self.parameter_preview))
         if self.move_blocks:
             mbf = np.ascontiguousarray([v for b in self.move_blocks for v in b], np.int32)
             mbn = np.ascontiguousarray([len(b) for b in self.move_blocks], np.int32)
@@ -1060,12 +1089,19 @@ class MPC:
     def _g(self):
         return self.gpu if self.gpu is not None else self.setup()
 
-    def compute_control(self, x, r=None, d=None, uprev=None, check=True):
+    def compute_control(self, x, r=None, d=None, uprev=None, p=None, check=True):
         if self.reference_preview and self.reference_tracking:
             r = self._flatten_preview(r, self.ny)
         if self.disturbance_preview and self.nd > 0:
             d = self._flatten_preview(d, self.nd)
-        return self._g().compute_control(x, r=r, d=d, uprev=uprev, check=check)
+        nb = self.affine_parameter_dim()
+        if nb > 0 and p is not None:           # format_affine_parameters, utils.jl:225-259
+            p = np.asarray(p, np.float64)
+            if self.parameter_preview and not (p.ndim == 1 and p.size == nb * self.Np):
+                p = self._flatten_preview(p, nb)
+            elif not self.parameter_preview and p.ndim == 2 and np.ndim(x) == 1:
+                p = p[:, 0]
+        return self._g().compute_control(x, r=r, d=d, uprev=uprev, p=p, check=check)
 
     def _flatten_preview(self, v, rows):
         """format_reference / format_disturbance with a preview (utils.jl:78-134, 155-205): a vector is

@@ -130,17 +130,18 @@ function solve_warm!(g::GpuMPC, Θ::Matrix{Float64}, active_upper::Matrix{UInt64
 end
 
 """
-    compute_control(g, X; r, d, uprev, check=true) -> nu × N
+    compute_control(g, X; r, d, uprev, p, check=true) -> nu × N
 
-Batched `compute_control` (src/utils.jl:43-51): X is nx × N; r, d, uprev are vectors (broadcast)
-or matrices with N columns.  θ = [x; r; d; uprev] exactly as `form_parameter` (src/explicit.jl:54-63).
+Batched `compute_control` (src/utils.jl:43-51): X is nx × N; r, d, uprev, p are vectors (broadcast)
+or matrices with N columns.  θ = [x; r; d; uprev; p] exactly as `form_parameter` (src/explicit.jl:54-63);
+p holds the generalized parameters (np rows, constant over the horizon: `parameter_preview` off).
 """
-function LinearMPC.compute_control(g::GpuMPC, X::AbstractMatrix; r=nothing, d=nothing, uprev=nothing, check=true)
+function LinearMPC.compute_control(g::GpuMPC, X::AbstractMatrix; r=nothing, d=nothing, uprev=nothing, p=nothing, check=true)
     nx, nr, nd, nup, np = LinearMPC.get_parameter_dims(g.mpc)
-    np == 0 || error("generalized parameters are not supported by the GPU backend")
+    (np == 0 || !g.mpc.settings.parameter_preview) || error("parameter_preview is not supported by the GPU backend")
     N = size(X, 2)
     col(v, k) = v isa AbstractMatrix ? v[1:k, :] : repeat(isnothing(v) ? zeros(k) : v[1:k], 1, N)
-    Θ = Matrix{Float64}([X; col(r, nr); col(d, nd); col(isnothing(uprev) ? g.mpc.uprev : uprev, nup)])
+    Θ = Matrix{Float64}([X; col(r, nr); col(d, nd); col(isnothing(uprev) ? g.mpc.uprev : uprev, nup); col(p, np)])
     U, flag, _ = solve(g, Θ)
     check && @assert all(flag .>= 1)
     g.mpc.uprev .= U[:, end]

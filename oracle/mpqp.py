@@ -127,6 +127,7 @@ class MPC:
     # time-varying previews over the horizon (types.jl:56-57, 67-68): theta carries ny*Np / nd*Np values
     reference_preview: bool = False
     disturbance_preview: bool = False
+    parameter_preview: bool = False   # types.jl:58,69: Np blocks of generalized parameters in theta
     preprocess_mpqp: bool = True
     soft_weight: float = 1e6
     # generalized-parameter (affine) objective terms (Ex p + ex)'x + (Eu p + eu)'u, setup.jl:118-132
@@ -269,9 +270,27 @@ class MPC:
         r = np.zeros(nr) if r is None else np.asarray(r, float).reshape(-1)[:nr]
         d = np.zeros(nd) if d is None else np.asarray(d, float).reshape(-1)[:nd]
         up = np.zeros(nup) if uprev is None else np.asarray(uprev, float).reshape(-1)[:nup]
-        npar = self.affine_parameter_dim()
-        pv = np.zeros(npar) if p is None else np.asarray(p, float).reshape(-1)[:npar]
-        return np.concatenate([x, r, d, up, pv])
+        return np.concatenate([x, r, d, up, self.format_affine_parameters(p)])
+
+    def format_affine_parameters(self, p):
+        """utils.jl:225-259: a vector of np values is held over the horizon, an np x cols matrix is cut to Np
+        columns or extended by holding its last column (first column only without parameter_preview)."""
+        nb = self.affine_parameter_dim()
+        tot = nb * self.Np if self.parameter_preview else nb
+        if tot == 0:
+            return np.zeros(0)
+        if p is None:
+            return np.zeros(tot)
+        p = np.asarray(p, float)
+        if p.ndim == 1 and p.size == nb:
+            return np.tile(p, self.Np) if self.parameter_preview else p
+        if p.ndim == 1 and p.size == tot:
+            return p
+        if p.ndim == 2:
+            if p.shape[0] != nb:
+                raise ValueError(f"Generalized parameter matrix must have {nb} rows")
+            return _flatten_preview(p, nb, self.Np) if self.parameter_preview else p[:, 0].copy()
+        raise ValueError("Generalized parameters must be a vector or matrix")
 
 
 def _flatten_preview(v, rows, Np):
@@ -434,13 +453,17 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
     ex = np.zeros(nxm) if mpc.ex is None else mpc.ex
     Eu = np.zeros((nu, npar)) if mpc.Eu is None else mpc.Eu
     eu = np.zeros(nu) if mpc.eu is None else mpc.eu
+    if Ex.shape != (nxm, npar) or Eu.shape != (nu, npar):    # mpc2mpqp.jl:486-490
+        raise ValueError(f"Affine objective matrices Ex / Eu must have {npar} columns")
+    # stage_parameter_matrix (mpc2mpqp.jl:148): one shared p, or stage k <-> p block k with parameter_preview
+    stage = (lambda E: np.kron(np.eye(N), E)) if mpc.parameter_preview else (lambda E: np.tile(E, (N, 1)))
     Umap = np.kron(np.vstack([np.eye(Nc), np.zeros((N - Nc, Nc))]), np.eye(nu))
     f = f + Umap.T @ np.tile(eu, N)
     xsel = np.hstack([np.eye(nxm), np.zeros((nxm, nxe - nxm))])
     Gx = np.kron(np.eye(N), xsel) @ Gam[nxe:, :]
     f = f + Gx.T @ np.tile(ex, N)
     if npar > 0:
-        Fp = Umap.T @ np.tile(Eu, (N, 1)) + Gx.T @ np.tile(Ex, (N, 1))
+        Fp = Umap.T @ stage(Eu) + Gx.T @ stage(Ex)
         f_theta = np.hstack([f_theta, Fp])
     return H, f, f_theta
 
@@ -532,9 +555,18 @@ def general_constraints(mpc: MPC, Phi, Gam):
         for c in mpc.constraints:
             mi = c.Au.shape[0]
             kmax = Np + 1 if not np.any(c.Au != 0) else Np
-            Ni = len([k for k in c.ks if k <= kmax])
+            kk = [k for k in c.ks if 1 <= k <= kmax]
             Apm = c.Ap if c.Ap.size else np.zeros((mi, npar))
-            Wp.append(np.tile(-Apm, (Ni, 1)))
+            if Apm.shape[1] != npar:
+                raise ValueError(f"Ap must have {npar} columns")
+            if mpc.parameter_preview:      # stage k sees p block min(k, Np)
+                blk = np.zeros((mi * len(kk), npar * Np))
+                for i, k in enumerate(kk):
+                    cid = min(k, Np) - 1
+                    blk[i * mi:(i + 1) * mi, cid * npar:(cid + 1) * npar] = -Apm
+                Wp.append(blk)
+            else:
+                Wp.append(np.tile(-Apm, (len(kk), 1)))
         W = np.hstack([W, np.vstack(Wp)])
     return (A, np.concatenate(ub), np.concatenate(lb), W,
             np.array(soft, bool), np.array(prio, int))
@@ -658,7 +690,7 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
     Phi, Gam = state_predictor(F, G, mpc.Np, mpc.Nc)
     H, f, f_theta = dense_objective(mpc, F, G, C, Phi, Gam)
     n = H.shape[0]
-    nth = sum(mpc.parameter_dims()) + mpc.affine_parameter_dim()
+    nth = sum(mpc.parameter_dims()) + mpc.affine_parameter_dim() * (mpc.Np if mpc.parameter_preview else 1)
     A = np.zeros((0, n))
     if len(mpc.umax):
         bu, bl, W, A = control_bounds(mpc, nth, Phi, Gam)

@@ -11,12 +11,13 @@ def mirror_of(lmpc, o):
     """Rebuild an oracle-side controller description with the product's builder API."""
     m = lmpc.MPC(o.F, o.G, C=o.C, Gd=o.Gd if o.nd_model else None, Dd=o.Dd if o.nd_model else None,
                  Np=o.Np, Nc=o.Nc)
-    m.set_objective(Q=o.Q, R=o.R, Rr=o.Rr, Qf=o.Qf)
+    m.set_objective(Q=o.Q, R=o.R, Rr=o.Rr, Qf=o.Qf, Ex=o.Ex, ex=o.ex, Eu=o.Eu, eu=o.eu)
     if len(o.umax):
         m.set_input_bounds(o.umin, o.umax)
     for c in o.constraints:
         m.add_constraint(Ax=c.Ax, Au=c.Au, Ar=c.Ar if c.Ar.size else None, Ad=c.Ad if c.Ad.size else None,
-                         Aup=c.Aup if c.Aup.size else None, ub=c.ub, lb=c.lb, ks=c.ks, soft=c.soft, prio=c.prio)
+                         Aup=c.Aup if c.Aup.size else None, Ap=c.Ap if c.Ap.size else None,
+                         ub=c.ub, lb=c.lb, ks=c.ks, soft=c.soft, prio=c.prio)
     m.reference_tracking = o.reference_tracking
     m.soft_weight = o.soft_weight
     return m
@@ -36,6 +37,59 @@ def test_condense_matches_numpy_restatement(lmpc, name):
     assert np.allclose(q["A"], ref.A, rtol=1e-12, atol=1e-13) and np.allclose(q["W"], ref.W, rtol=1e-12, atol=1e-13)
     assert np.allclose(q["bu"], ref.bu, rtol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-13)
     assert np.array_equal(q["senses"], ref.senses) and np.all(q["f"] == 0)
+
+
+def _genparam_rich():
+    """README pendulum with every generalized-parameter term in use: Ex (np = 2), ex, Eu (np = 1, padded),
+    eu, a parametric state constraint (Ap, np = 2) and a parametric input constraint."""
+    o = mpqp.invpend(Np=12, Nc=4)
+    o.set_objective(Ex=np.array([[0.3, 0.0], [0.0, -0.2], [0.1, 0.1], [0.0, 0.0]]), ex=[0.05, 0.0, -0.02, 0.0],
+                    Eu=np.array([[-0.4, 0.25]]), eu=[0.07])
+    o.add_constraint(Ax=np.array([[0.0, 0.0, 1.0, 0.0]]), Ap=np.array([[0.5, -1.0]]), ub=[0.4], lb=[-0.4],
+                     ks=range(2, 8), soft=True)
+    o.add_constraint(Au=np.array([[1.0]]), Ap=np.array([[1.0, 0.0]]), ub=[1.5], ks=range(1, 4))
+    return o
+
+
+@pytest.mark.parametrize("preview", [False, True])
+@pytest.mark.parametrize("blocks", [None, [[1, 2, 9]]])
+def test_generalized_parameters_match_numpy_restatement(lmpc, blocks, preview):
+    """Ex / ex / Eu / eu (setup.jl:118-132, mpc2mpqp.jl:478-508) and the constraints' Ap (setup.jl:61-84):
+    theta = [x; r; d; uprev; p], f != 0, the p columns of f_theta and W; also under move blocking."""
+    for o in (mpqp.generalized_parameter_example(), _genparam_rich()):
+        m = mirror_of(lmpc, o)
+        o.parameter_preview = m.parameter_preview = preview
+        if blocks is not None:
+            if o.Np != 12:
+                continue
+            o.Nc = m.Nc = o.Np
+            mpqp.move_block(o, blocks)
+            m.move_block(blocks)
+        ref = mpqp.mpc2mpqp(o)
+        q = m.condense()
+        npar = o.affine_parameter_dim() * (o.Np if preview else 1)
+        assert m.affine_parameter_dim() * (o.Np if preview else 1) == npar
+        assert q["f_theta"].shape[1] == sum(o.parameter_dims()) + npar
+        assert q["H"].shape == ref.H.shape and q["A"].shape == ref.A.shape and q["W"].shape == ref.W.shape
+        assert np.any(ref.f != 0) and np.any(ref.f_theta[:, -npar:] != 0) and np.any(ref.W[:, -npar:] != 0)
+        assert np.max(np.abs(q["H"] - ref.H)) <= 1e-12 * max(1.0, np.abs(ref.H).max())
+        assert np.max(np.abs(q["f"] - ref.f)) <= 1e-12 * max(1.0, np.abs(ref.f).max())
+        assert np.max(np.abs(q["f_theta"] - ref.f_theta)) <= 1e-12 * max(1.0, np.abs(ref.f_theta).max())
+        assert np.allclose(q["A"], ref.A, rtol=1e-12, atol=1e-13) and np.allclose(q["W"], ref.W, rtol=1e-12, atol=1e-13)
+        assert np.allclose(q["bu"], ref.bu, rtol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-13)
+        assert np.array_equal(q["senses"], ref.senses)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,expect", [(0.0, 1.0), (0.75, 0.25)])
+def test_generalized_parameter_known_answer_through_the_builder(lmpc, p, expect):
+    """runtests.jl:1250-1268 with the product's own builder: model -> C++ condensing -> GPU."""
+    m = lmpc.MPC([[1.0]], [[1.0]], C=[[1.0]], Np=4, Nc=4)
+    m.set_bounds(umin=[0.0], umax=[2.0])
+    m.set_objective(Q=[0.0], R=[1e-6], Eu=[[-1.0]], eu=[-0.1])
+    m.add_constraint(Au=[[1.0]], Ap=[[1.0]], ub=[1.0], ks=range(1, 5))
+    u = m.compute_control(np.array([0.0]), r=[0.0], p=[p])
+    assert abs(u[0] - expect) < 1e-6
 
 
 def test_condense_preprocessing_known_answer(lmpc):

@@ -359,3 +359,52 @@ def test_preview_windows_follow_the_reference_simulation_loop(lmpc):
                 got = flat[(k - 1) * stride:(k - 1) * stride + ny * Np]
                 assert np.array_equal(got, want.reshape(-1, order="F")), (ncols, first, k)
         assert np.array_equal(host.hold_trajectory(scen, ny, N), rs)
+
+
+@pytest.mark.parametrize("pp", [False, True])
+def test_generalized_parameter_terms_match_rollout(pp):
+    """(Ex p_k + ex)'x_{k+1} + (Eu p_k + eu)'u_k and the constraints' Ap p (setup.jl:61-84,118-132;
+    mpc2mpqp.jl:125-148,478-508), with one p held over the horizon or a parameter preview: dense
+    {f, f_theta, W} against stage costs and constraint rows evaluated along a plain simulation."""
+    mpc = om.invpend(Np=8, Nc=3)
+    mpc.preprocess_mpqp, mpc.parameter_preview = False, pp
+    Ex = np.array([[0.3, 0.0], [0.0, -0.2], [0.1, 0.1], [0.0, 0.05]])
+    ex, Eu, eu = np.array([0.05, 0.0, -0.02, 0.01]), np.array([[-0.4, 0.25]]), np.array([0.07])
+    mpc.set_objective(Ex=Ex, ex=ex, Eu=Eu, eu=eu)
+    Apx, Apu = np.array([[0.5, -1.0]]), np.array([[1.0, 0.3]])
+    mpc.add_constraint(Ax=np.array([[0.0, 0.0, 1.0, 0.0]]), Ap=Apx, ub=[0.4], lb=[-0.4], ks=range(2, 10))
+    mpc.add_constraint(Au=np.array([[1.0]]), Ap=Apu, ub=[1.5], ks=range(1, 4))
+    qp = om.mpc2mpqp(mpc)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    N, Nc, nu = mpc.Np, mpc.Nc, mpc.nu
+    npar = 2 * N if pp else 2
+    assert qp.f_theta.shape[1] == nx + nr + nd + nup + npar == qp.W.shape[1]
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        x0, up, r = rng.normal(size=nx), rng.normal(size=nu), rng.normal(size=mpc.ny)
+        P = rng.normal(size=(2, N)) if pp else np.repeat(rng.normal(size=(2, 1)), N, axis=1)
+        th = mpc.form_parameter(x0, r, None, up, P if pp else P[:, 0])
+        assert th.size == qp.W.shape[1]
+
+        def lin(U):                        # linear stage costs and the parametric rows along a rollout
+            x, L, xs, us = x0, 0.0, [x0], []
+            for k in range(N):
+                u = U[min(k, Nc - 1)]
+                if k < Nc:                 # Umap (mpc2mpqp.jl:492) counts the Nc free moves only, not the held ones
+                    L += (Eu @ P[:, k] + eu) @ u
+                x = mpc.F @ x + mpc.G @ u
+                L += (Ex @ P[:, k] + ex) @ x
+                xs.append(x); us.append(u)
+            rows = [np.array([xs[k - 1][2]]) + Apx @ P[:, min(k, N) - 1] for k in range(2, 10)]
+            rows += [us[k - 1] + Apu @ P[:, k - 1] for k in range(1, 4)]
+            return L, np.concatenate(rows)
+        U1, U2 = rng.normal(size=(Nc, nu)), rng.normal(size=(Nc, nu))
+        Rp = np.repeat(r.reshape(-1, 1), N, axis=1)
+        J1, _ = _rollout(mpc, x0, Rp, np.zeros((0, N)), up, U1)
+        J2, _ = _rollout(mpc, x0, Rp, np.zeros((0, N)), up, U2)
+        (L1, g1), (L2, _) = lin(U1), lin(U2)
+        q = lambda U: 0.5 * U @ qp.H @ U + (qp.f + qp.f_theta @ th) @ U
+        assert abs(2 * (q(U1.ravel()) - q(U2.ravel())) - (J1 - J2 + 2 * (L1 - L2))) < 1e-9 * max(1.0, abs(J1), abs(J2))
+        # rows: A U - W theta is what the bounds apply to (the simple bounds come first in W)
+        m0 = qp.W.shape[0] - qp.A.shape[0]
+        assert np.allclose(qp.A @ U1.ravel() - qp.W[m0:] @ th, g1, atol=1e-10)
