@@ -349,7 +349,8 @@ int lmpc_gpu_evaluate_batch_multi(lmpc_bst_multi *t, const double *Theta, int64_
  * Host-side condensing: build the dense mpQP from a discrete-time model without
  * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
  * path supports: move blocking, previews of r and d, a prestabilising feedback, generalized (affine)
- * parameters with or without a parameter preview; no model offsets, binaries or reference condensation.
+ * parameters with or without a parameter preview, model offsets and operating points; no binaries or
+ * reference condensation.
  * Pure host code; needs no GPU.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
@@ -406,6 +407,13 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
    * of one; stage k pairs u_k and x_{k+1} with p_k (stage_parameter_matrix, mpc2mpqp.jl:148), a constraint at
    * ks = k sees block min(k, Np) (parameter_preview_direct, mpc2mpqp.jl:125-143) */
   int32_t parameter_preview;
+  /* affine model x+ = F x + G u + Gd d + f_offset, y = C x + Dd d + h_offset around the operating point (xo, uo)
+   * (Model(...; f_offset, h_offset, xo, uo), src/model.jl:45-72; a linearised model, src/model.jl:113-124):
+   * f_offset (nx) is a constant extra state collapsed into f / bu / bl (mpc2mpqp.jl:395-399, 518-522, 684-689),
+   * h_offset (ny) shifts the tracked reference (mpc2mpqp.jl:523-530), xo (nx) / uo (nu) shift the cost of a
+   * regulator (reference_tracking = 0, mpc2mpqp.jl:433-443, 457-459).  Any NULL = 0.  f_offset cannot be combined
+   * with generalized parameters (LMPC_E_UNSUPPORTED). */
+  const double *f_offset, *h_offset, *xo, *uo;
 } lmpc_model;
 
 typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */

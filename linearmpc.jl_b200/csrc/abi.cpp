@@ -44,7 +44,8 @@ extern "C" int lmpc_gpu_abi_layout(int32_t *out, int32_t cap) {
         F(lmpc_model, reference_tracking), F(lmpc_model, preprocess), F(lmpc_model, move_blocks),
         F(lmpc_model, n_move_blocks), F(lmpc_model, reference_preview), F(lmpc_model, disturbance_preview),
         F(lmpc_model, K), F(lmpc_model, np), F(lmpc_model, Ex), F(lmpc_model, ex), F(lmpc_model, Eu),
-        F(lmpc_model, eu), F(lmpc_model, parameter_preview)});
+        F(lmpc_model, eu), F(lmpc_model, parameter_preview),
+        F(lmpc_model, f_offset), F(lmpc_model, h_offset), F(lmpc_model, xo), F(lmpc_model, uo)});
   if (out)
     for (int32_t i = 0; i < cap && i < (int32_t)o.size(); ++i) out[i] = o[i];
   return (int32_t)o.size();

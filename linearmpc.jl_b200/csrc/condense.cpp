@@ -124,7 +124,16 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   // generalized parameters: the last block of theta, np values, or Np blocks of np with parameter_preview
   const int npb = md->np > 0 ? md->np : 0, pp = (md->parameter_preview && npb > 0) ? 1 : 0;
   const int npar = pp ? npb * Np : npb;
-  const int nxe = nx + nr + nd + nup, nth = nx + nrp + ndp + nup + npar, opar = nth - npar;
+  // a constant dynamics offset is one more extended state that stays at 1 (mpc2mpqp.jl:684-689); its column of
+  // f_theta / W lives in a scratch column behind theta and is collapsed into f / bu / bl before move blocking
+  bool has_off = false;
+  if (md->f_offset) for (int i = 0; i < nx; ++i) if (md->f_offset[i] != 0.0) has_off = true;
+  const int noff = has_off ? 1 : 0;
+  if (noff && npar > 0)   // the reference collapses the LAST column, which is a p column then (mpc2mpqp.jl:395-399)
+    return cfail(LMPC_E_UNSUPPORTED, "f_offset together with generalized parameters is not supported");
+  const int nth_out = nx + nrp + ndp + nup + npar;
+  const int nxe = nx + nr + nd + nup + noff, opar = nth_out - npar;
+  int nth = nth_out + noff;
   // column of theta that holds extended-state entry j (insert_preview_parameter_blocks, mpc2mpqp.jl:70-92)
   auto th_col = [&](int j) { return j < nx + nr ? j : (j < nx + nr + nd ? j - nr + nrp : j - nr - nd + nrp + ndp); };
 
@@ -161,6 +170,11 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     set_block(C2, 0, 0, C);
     set_block(C2, C.r, 0, K);
     C = C2;
+  }
+  if (noff) {
+    F(nxe - 1, nxe - 1) = 1.0;
+    for (int i = 0; i < nx; ++i) F(i, nxe - 1) = md->f_offset[i];
+    C = hcat(C, Mat(C.r, 1));
   }
   // ---- extended weights (mpc2mpqp.jl:692-731, K = 0) ----------------------------------------------
   if (!any_nonzero(Qf)) Qf = Q;
@@ -211,6 +225,29 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   Mat H(n, n);
   for (int b = 0; b < Nc; ++b) add_block(H, b * nu, b * nu, R);
   add_block(H, n - nu, n - nu, R, (double)(Np - Nc));
+  std::vector<double> fvec(n, 0.0);
+  // a regulator (reference_tracking off) penalises the distance to the operating point (xo, uo)
+  // (mpc2mpqp.jl:433-443, 457-459)
+  const bool regulator = !md->reference_tracking;
+  bool has_xo = false, has_uo = false;
+  if (regulator && md->xo) for (int i = 0; i < nx; ++i) if (md->xo[i] != 0.0) has_xo = true;
+  if (regulator && md->uo) for (int i = 0; i < nu; ++i) if (md->uo[i] != 0.0) has_uo = true;
+  if (has_uo) {
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) fvec[i] -= H(i, j) * md->uo[j % nu];
+    if (hasK && any_nonzero(R)) {
+      // f -= (GKR + GKR') Uo, GKR = Gamma' KRtot, KRtot: -K'R on stage k's plant-state rows, column block min(k, Nc-1)
+      const Mat KR = mul(tr(K), R);
+      Mat GKR(n, n);
+      for (int k = 0; k < Np; ++k) {
+        const int cb = std::min(k, Nc - 1);
+        for (int r = 0; r < n; ++r) for (int i = 0; i < nx; ++i) {
+          const double g = Gam(k * nxe + i, r);
+          if (g != 0.0) for (int j = 0; j < nu; ++j) GKR(r, cb * nu + j) -= g * KR(i, j);
+        }
+      }
+      for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) fvec[i] -= (GKR(i, j) + GKR(j, i)) * md->uo[j % nu];
+    }
+  }
   // Gamma' CQCtot Gamma and Gamma' CQCtot Phi, block row by block row (CQCtot is block diagonal)
   Mat fth(n, nth);
   for (int k = 0; k <= Np; ++k) {
@@ -222,6 +259,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     }
     const Mat GtW = mul(tr(Gk), W);
     add_block(H, 0, 0, mul(GtW, Gk));
+    if (has_xo) for (int i = 0; i < n; ++i) for (int j = 0; j < nx; ++j) fvec[i] -= GtW(i, j) * md->xo[j];
     const Mat fk = mul(GtW, Pk);
     for (int i = 0; i < n; ++i) for (int j = 0; j < nxe; ++j) fth(i, th_col(j)) += fk(i, j);
     if (k >= 1 && (rp || dp)) {
@@ -258,7 +296,6 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   // generalized-parameter cost (mpc2mpqp.jl:478-508): f += Umap' rep(eu) + Gx' rep(ex), and the p columns of
   // f_theta = Umap' rep(Eu) + Gx' rep(Ex); Umap picks the Nc moves out of the first Nc of the Np stages, Gx is
   // the plant-state part of the predictor rows x_1 .. x_Np
-  std::vector<double> fvec(n, 0.0);
   // (stage_parameter_matrix, mpc2mpqp.jl:148: with parameter_preview stage k pairs u_k and x_{k+1} with p block k)
   if (md->ex || md->eu || npar > 0) {
     const Mat Exm = from_colmajor(md->Ex, nx, npb), Eum = from_colmajor(md->Eu, nu, npb);
@@ -364,6 +401,21 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
         gsoft.push_back(c.soft ? 1 : 0); gprio.push_back(c.prio);
       }
     }
+  }
+  // ---- model offsets ------------------------------------------------------------------------------------
+  if (noff) {   // collapse the constant state (value 1): mpc2mpqp.jl:395-399, 518-522
+    const int sc = nth - 1;
+    for (int i = 0; i < n; ++i) fvec[i] += fth(i, sc);
+    for (size_t i = 0; i < Wrows.size(); ++i) { gbu[i] += Wrows[i][sc]; gbl[i] += Wrows[i][sc]; Wrows[i].pop_back(); }
+    Mat f2(n, nth - 1);
+    for (int i = 0; i < n; ++i) for (int j = 0; j < nth - 1; ++j) f2(i, j) = fth(i, j);
+    fth = f2;
+    W = Mat(ms, nth - 1);          // the simple bounds never depend on theta
+    nth = nth_out;
+  }
+  if (nrp > 0 && md->h_offset) {   // the outputs track r - h_offset (mpc2mpqp.jl:523-530)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < nrp; ++j) fvec[i] -= fth(i, nx + j) * md->h_offset[j % ny];
   }
   // ---- move blocking (apply_move_block, mpc2mpqp.jl:830-857) -------------------------------------------
   // U_old = T z: the blocks of all inputs are interleaved pass by pass; the last block of every

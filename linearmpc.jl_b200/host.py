@@ -875,7 +875,8 @@ class _Model(C.Structure):
                 ("move_blocks", C.c_void_p), ("n_move_blocks", C.c_void_p),
                 ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32), ("K", C.c_void_p),
                 ("np", C.c_int32), ("Ex", C.c_void_p), ("ex", C.c_void_p), ("Eu", C.c_void_p), ("eu", C.c_void_p),
-                ("parameter_preview", C.c_int32)]
+                ("parameter_preview", C.c_int32),
+                ("f_offset", C.c_void_p), ("h_offset", C.c_void_p), ("xo", C.c_void_p), ("uo", C.c_void_p)]
 
 
 def _diag(v, n):
@@ -890,7 +891,8 @@ class MPC:
     host (C++) and uploads to the GPU, after which `compute_control` / `solve` / `simulate` work as
     on GpuMPC.  Discrete-time models only (use your own zoh for continuous ones, utils.jl:291-295)."""
 
-    def __init__(self, F, G, C=None, Gd=None, Dd=None, Np=10, Nc=None, Ts=-1.0):
+    def __init__(self, F, G, C=None, Gd=None, Dd=None, Np=10, Nc=None, Ts=-1.0, f_offset=None, h_offset=None,
+                 xo=None, uo=None):
         f64 = lambda a: np.asarray(a, np.float64)
         self.F = np.atleast_2d(f64(F)); self.nx = self.F.shape[0]
         self.G = f64(G).reshape(self.nx, -1); self.nu = self.G.shape[1]
@@ -910,6 +912,10 @@ class MPC:
         self.K = None                                               # prestabilising feedback, setup.jl:186-199
         self.Ex = self.ex = self.Eu = self.eu = None                # generalized-parameter cost, setup.jl:118-132
         self.parameter_preview = False                              # types.jl:58,69
+        # affine model / operating point (Model(...; f_offset, h_offset, xo, uo), model.jl:45-72)
+        vec = lambda v, n: None if v is None or np.size(v) == 0 else f64(v).reshape(n)
+        self.f_offset, self.h_offset = vec(f_offset, self.nx), vec(h_offset, self.ny)
+        self.xo, self.uo = vec(xo, self.nx), vec(uo, self.nu)
         self.move_blocks = []
         self.gpu = None
         self.mpqp = None
@@ -1052,7 +1058,7 @@ class MPC:
                     int(self.reference_tracking), int(self.preprocess_mpqp), None, None,
                     int(self.reference_preview), int(self.disturbance_preview), cm(self.K),
                     npar, cm(wide(self.Ex, self.nx)), cm(self.ex), cm(wide(self.Eu, self.nu)), cm(self.eu),
-                    int(self.parameter_preview))
+                    int(self.parameter_preview), cm(self.f_offset), cm(self.h_offset), cm(self.xo), cm(self.uo))
         if self.move_blocks:
             mbf = np.ascontiguousarray([v for b in self.move_blocks for v in b], np.int32)
             mbn = np.ascontiguousarray([len(b) for b in self.move_blocks], np.int32)

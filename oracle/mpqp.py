@@ -135,6 +135,12 @@ class MPC:
     ex: Optional[np.ndarray] = None
     Eu: Optional[np.ndarray] = None
     eu: Optional[np.ndarray] = None
+    # affine model x+ = F x + G u + Gd d + f_offset, y = C x + Dd d + h_offset, operating point (xo, uo)
+    # (model.jl:17-41,61-64); xo / uo only enter the cost of a regulator (reference_tracking off)
+    f_offset: Optional[np.ndarray] = None
+    h_offset: Optional[np.ndarray] = None
+    xo: Optional[np.ndarray] = None
+    uo: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.F = np.atleast_2d(np.asarray(self.F, float))
@@ -159,6 +165,9 @@ class MPC:
         self.umin = np.atleast_1d(np.asarray(self.umin, float))
         self.umax = np.atleast_1d(np.asarray(self.umax, float))
         self.K = np.zeros((nu, nx))
+        vec = lambda v, n: np.zeros(n) if v is None or np.size(v) == 0 else np.asarray(v, float).reshape(n)
+        self.f_offset, self.h_offset = vec(self.f_offset, nx), vec(self.h_offset, ny)
+        self.xo, self.uo = vec(self.xo, nx), vec(self.uo, nu)
 
     # -- builder API mirroring setup.jl ------------------------------------
     def set_objective(self, Q=None, R=None, Rr=None, Qf=None, Ex=None, ex=None, Eu=None, eu=None):
@@ -411,11 +420,25 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
 
     H = np.kron(np.eye(Nc), R)
     H[-nu:, -nu:] += (N - Nc) * R
+    f0 = np.zeros(Nc * nu)
+    regulator = not mpc.reference_tracking
+    if regulator and np.any(mpc.uo != 0):          # nonzero operating point (mpc2mpqp.jl:433-443)
+        Uo = np.tile(mpc.uo, Nc)
+        f0 -= H @ Uo
+        if np.any(mpc.K != 0) and np.any(R != 0):
+            KR = np.vstack([-mpc.K.T @ R, np.zeros((nxe - mpc.nx, nu))])
+            KRtot = np.vstack([np.kron(np.eye(Nc), KR), np.zeros(((N - Nc + 1) * nxe, Nc * nu))])
+            if N > Nc:
+                KRtot[Nc * nxe:N * nxe, -nu:] = np.tile(KR, (N - Nc, 1))
+            GKR = Gam.T @ KRtot
+            f0 -= (GKR + GKR.T) @ Uo
     CQC = Cp.T @ Qp @ Cp
     CQCtot = np.kron(np.eye(N + 1), CQC)
     CQCtot[-nxe:, -nxe:] = Cf.T @ Qfp @ Cf
     H = H + Gam.T @ CQCtot @ Gam
     f_theta = Gam.T @ CQCtot @ Phi
+    if regulator and np.any(mpc.xo != 0):          # mpc2mpqp.jl:457-459
+        f0 -= Gam.T @ CQCtot @ np.tile(np.concatenate([mpc.xo, np.zeros(nxe - mpc.nx)]), N + 1)
     if np.any(S != 0):
         Stot = np.vstack([np.kron(np.eye(Nc), S), np.zeros(((N - Nc + 1) * nxe, Nc * nu))])
         if N > Nc:
@@ -445,7 +468,7 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
         split = nxp + nrp
         f_theta = np.hstack([f_theta[:, :split], Fd, f_theta[:, split:]])
     H = (H + H.T) / 2
-    f = np.zeros(H.shape[0])
+    f = f0
     # generalized-parameter terms (mpc2mpqp.jl:478-508), constant parameter across the horizon
     npar = mpc.affine_parameter_dim()
     nxm = mpc.nx
@@ -684,8 +707,41 @@ def apply_move_block(mpc, H, f, f_theta, A, bu, bl, W, soft, prio):
     return (T.T @ H @ T, T.T @ f, T.T @ f_theta, A @ T, bu[full], bl[full], W[full], soft[full], prio[full])
 
 
+def _with_offset_channel(mpc: MPC):
+    """A constant dynamics offset f_offset is one more state that stays at 1 (mpc2mpqp.jl:684-689): here it
+    rides as an extra measured-disturbance channel d_off = 1 with Gd column f_offset and Dd column 0, which
+    gives the same columns of f_theta and W (only their position in the extended state differs); the
+    caller collapses them into f, bu and bl (mpc2mpqp.jl:395-399, 518-522)."""
+    import copy
+    aug = copy.copy(mpc)
+    ndm = mpc.nd_model
+    aug.Gd = np.hstack([mpc.Gd, mpc.f_offset.reshape(-1, 1)])
+    aug.Dd = np.hstack([mpc.Dd, np.zeros((mpc.ny, 1))])
+    aug.nd_model = ndm + 1
+    aug.f_offset = np.zeros(mpc.nx)
+    aug.constraints = []
+    for c in mpc.constraints:
+        c2 = copy.copy(c)
+        if c.Ad.size:
+            c2.Ad = np.hstack([c.Ad, np.zeros((c.Ad.shape[0], 1))])
+        aug.constraints.append(c2)
+    nx, nr, _, _ = mpc.parameter_dims()
+    if mpc.disturbance_preview:
+        cols = [nx + nr + k * (ndm + 1) + ndm for k in range(mpc.Np)]
+    else:
+        cols = [nx + nr + ndm]
+    return aug, cols
+
+
 def mpc2mpqp(mpc: MPC) -> MPQP:
     """The dense mpQP of `mpc` (mpc2mpqp.jl:612-647)."""
+    offset_cols = None
+    if np.any(mpc.f_offset != 0):
+        if mpc.affine_parameter_dim() > 0:
+            # the reference collapses the LAST column of f_theta / W, which is a p column then
+            raise ValueError("f_offset together with generalized parameters is not supported")
+        orig = mpc
+        mpc, offset_cols = _with_offset_channel(mpc)
     F, G, C = extended_system(mpc)
     Phi, Gam = state_predictor(F, G, mpc.Np, mpc.Nc)
     H, f, f_theta = dense_objective(mpc, F, G, C, Phi, Gam)
@@ -704,6 +760,15 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
         A = np.vstack([A, Ag])
         bu, bl, W = np.concatenate([bu, bug]), np.concatenate([bl, blg]), np.vstack([W, Wg])
         soft, prio = np.concatenate([soft, sg]), np.concatenate([prio, pg])
+    if offset_cols is not None:                     # collapse the constant channel (value 1)
+        f = f + f_theta[:, offset_cols].sum(axis=1)
+        bu, bl = bu + W[:, offset_cols].sum(axis=1), bl + W[:, offset_cols].sum(axis=1)
+        f_theta, W = np.delete(f_theta, offset_cols, axis=1), np.delete(W, offset_cols, axis=1)
+        mpc = orig
+    nxp, nrp, _, _ = mpc.parameter_dims()
+    if nrp > 0 and np.any(mpc.h_offset != 0):       # r - h_offset is what the outputs track (mpc2mpqp.jl:523-530)
+        ho = np.tile(mpc.h_offset, mpc.Np) if mpc.reference_preview else mpc.h_offset
+        f = f - f_theta[:, nxp:nxp + nrp] @ ho
     if getattr(mpc, "move_blocks", None):
         H, f, f_theta, A, bu, bl, W, soft, prio = apply_move_block(mpc, H, f, f_theta, A, bu, bl, W, soft, prio)
     # sort general rows by priority, stable (mpc2mpqp.jl:859-866)

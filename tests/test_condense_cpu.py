@@ -10,7 +10,7 @@ from oracle import mpqp
 def mirror_of(lmpc, o):
     """Rebuild an oracle-side controller description with the product's builder API."""
     m = lmpc.MPC(o.F, o.G, C=o.C, Gd=o.Gd if o.nd_model else None, Dd=o.Dd if o.nd_model else None,
-                 Np=o.Np, Nc=o.Nc)
+                 Np=o.Np, Nc=o.Nc, f_offset=o.f_offset, h_offset=o.h_offset, xo=o.xo, uo=o.uo)
     m.set_objective(Q=o.Q, R=o.R, Rr=o.Rr, Qf=o.Qf, Ex=o.Ex, ex=o.ex, Eu=o.Eu, eu=o.eu)
     if len(o.umax):
         m.set_input_bounds(o.umin, o.umax)
@@ -90,6 +90,94 @@ def test_generalized_parameter_known_answer_through_the_builder(lmpc, p, expect)
     m.add_constraint(Au=[[1.0]], Ap=[[1.0]], ub=[1.0], ks=range(1, 5))
     u = m.compute_control(np.array([0.0]), r=[0.0], p=[p])
     assert abs(u[0] - expect) < 1e-6
+
+
+def _assert_same_mpqp(q, ref):
+    assert q["H"].shape == ref.H.shape and q["A"].shape == ref.A.shape and q["W"].shape == ref.W.shape
+    assert np.max(np.abs(q["H"] - ref.H)) <= 1e-12 * max(1.0, np.abs(ref.H).max())
+    assert np.max(np.abs(q["f"] - ref.f)) <= 1e-11 * max(1.0, np.abs(ref.f).max())
+    assert np.max(np.abs(q["f_theta"] - ref.f_theta)) <= 1e-12 * max(1.0, np.abs(ref.f_theta).max())
+    for k in ("A", "W"):       # relative to the largest entry (feedback rows go through powers of F - G K)
+        r = getattr(ref, k)
+        assert r.size == 0 or np.max(np.abs(q[k] - r)) <= 1e-11 * max(1.0, np.abs(r).max())
+    assert np.allclose(q["bu"], ref.bu, rtol=1e-12, atol=1e-13) and np.allclose(q["bl"], ref.bl, rtol=1e-12, atol=1e-13)
+    assert np.array_equal(q["senses"], ref.senses)
+
+
+@pytest.mark.parametrize("name,rp,dp,pre,blocks", [
+    ("invpend", False, False, False, None), ("invpend", True, False, False, None),
+    ("aircraft", False, False, False, None), ("aircraft_ksall", False, True, False, None),
+    ("aircraft_ksall", True, True, False, None), ("aircraft", False, False, True, None),
+    ("invpend", False, False, True, [[1, 2, 47]]), ("aircraft_ksall", False, False, False, [[2, 2, 6], [3, 7]])])
+def test_model_offsets_match_numpy_restatement(lmpc, name, rp, dp, pre, blocks):
+    """f_offset / h_offset (model.jl:45-72; mpc2mpqp.jl:395-399, 518-530, 684-689): the C++ condenser carries the
+    constant as a trailing extended state, the restatement as an extra disturbance channel (itself checked
+    against simulations of the affine model in test_preview_cpu.py); with previews, a feedback, move blocking."""
+    rng = np.random.default_rng(2)
+    o = util.controller(name)
+    if name.startswith("aircraft"):
+        o.Gd = np.array([[0.1, 0.0], [0.0, 0.02], [0.03, 0.0], [0.0, 0.01]])
+    o.f_offset, o.h_offset = 0.1 * rng.normal(size=o.nx), 0.2 * rng.normal(size=o.ny)
+    o.reference_preview, o.disturbance_preview = rp, dp
+    if pre:
+        o.set_prestabilizing_feedback()
+    m = mirror_of(lmpc, o)
+    m.reference_preview, m.disturbance_preview = rp, dp
+    if pre:
+        m.set_prestabilizing_feedback(o.K)
+    if blocks is not None:
+        o.Nc = m.Nc = o.Np
+        mpqp.move_block(o, blocks)
+        m.move_block(blocks)
+    ref = mpqp.mpc2mpqp(o)
+    assert np.any(ref.f != 0)
+    _assert_same_mpqp(m.condense(), ref)
+
+
+@pytest.mark.parametrize("pre", [False, True])
+def test_regulator_operating_point_matches_numpy_restatement(lmpc, pre):
+    """reference_tracking off with (xo, uo) (mpc2mpqp.jl:433-443, 457-459), also with the feedback terms."""
+    o = mpqp.invpend(Np=12, Nc=4)
+    o.reference_tracking = False
+    o.Rr = np.zeros((1, 1))
+    o.xo, o.uo = np.array([0.3, -0.1, 0.05, 0.2]), np.array([0.4])
+    o.f_offset = np.array([0.01, 0.0, -0.02, 0.03])
+    if pre:
+        o.set_prestabilizing_feedback()
+    m = mirror_of(lmpc, o)
+    if pre:
+        m.set_prestabilizing_feedback(o.K)
+    ref = mpqp.mpc2mpqp(o)
+    assert ref.f_theta.shape[1] == 4
+    _assert_same_mpqp(m.condense(), ref)
+
+
+@pytest.mark.gpu
+def test_affine_model_controller_on_gpu_matches_oracle(lmpc):
+    """A linearised (affine) pendulum model -> C++ condensing -> GPU, against the oracle's solve of the
+    restated mpQP on sampled theta (f != 0 through the collapsed offset)."""
+    from oracle import ldp
+    o = mpqp.invpend()
+    o.f_offset, o.h_offset = np.array([0.02, -0.01, 0.03, 0.0]), np.array([0.05, -0.02])
+    m = mirror_of(lmpc, o)
+    g = m.setup()
+    qp = mpqp.mpc2mpqp(o)
+    P = ldp.OracleProblem(mpqp.qp2ldp(qp, o.nu), o.nu)
+    lo, hi = mpqp.invpend_range(1.0)
+    Th = mpqp.sample_theta(lo, hi, 2000)
+    out, ref = g.solve(Th), P.solve_batch(Th)
+    assert np.array_equal(out["exitflag"], ref["flag"])
+    assert np.max(np.abs(out["U"] - ref["U"])) < 1e-9
+    # the offset matters: the plain model gives a different control on the same theta
+    plain = mirror_of(lmpc, mpqp.invpend()).setup().solve(Th)
+    assert np.max(np.abs(plain["U"] - out["U"])) > 1e-3
+
+
+def test_offsets_with_generalized_parameters_are_refused(lmpc):
+    m = lmpc.MPC([[1.0]], [[1.0]], Np=3, f_offset=[0.1])
+    m.set_objective(Eu=[[1.0]])
+    with pytest.raises(lmpc.LmpcError):
+        m.condense()
 
 
 def test_condense_preprocessing_known_answer(lmpc):

@@ -33,9 +33,11 @@ def _rollout(mpc, x0, Rp, Dp, up, U):
         u = U[min(k, Nc - 1)] - mpc.K @ x       # U holds v_k; K = 0 unless prestabilised
         if np.any(mpc.K != 0) and len(mpc.umax) and k < Nc:
             rows.append(u)                      # control bounds are general rows then
-        J += u @ mpc.R @ u + (u - uprev) @ mpc.Rr @ (u - uprev)
-        x = mpc.F @ x + mpc.G @ u + (mpc.Gd @ Dp[:, k] if mpc.nd_model else 0)
-        y = mpc.C @ x + (mpc.Dd @ Dp[:, k] if mpc.nd_model else 0) - Rp[:, k]
+        reg = not mpc.reference_tracking       # a regulator penalises the distance to (xo, uo)
+        J += (u - reg * mpc.uo) @ mpc.R @ (u - reg * mpc.uo) + (u - uprev) @ mpc.Rr @ (u - uprev)
+        x = mpc.F @ x + mpc.G @ u + (mpc.Gd @ Dp[:, k] if mpc.nd_model else 0) + mpc.f_offset
+        y = mpc.C @ (x - reg * mpc.xo) + (mpc.Dd @ Dp[:, k] if mpc.nd_model else 0) + mpc.h_offset * (not reg) \
+            - (Rp[:, k] if not reg else 0)
         J += y @ (mpc.Q if k < N - 1 else Qf) @ y
         xs.append(x); us.append(u); uprev = u
     for c in mpc.constraints:
@@ -408,3 +410,65 @@ def test_generalized_parameter_terms_match_rollout(pp):
         # rows: A U - W theta is what the bounds apply to (the simple bounds come first in W)
         m0 = qp.W.shape[0] - qp.A.shape[0]
         assert np.allclose(qp.A @ U1.ravel() - qp.W[m0:] @ th, g1, atol=1e-10)
+
+
+@pytest.mark.parametrize("name,rp,dp,pre", [("invpend", False, False, False), ("invpend", True, False, False),
+                                            ("aircraft", False, False, False), ("aircraft", False, True, False),
+                                            ("aircraft", True, True, False), ("aircraft", False, False, True),
+                                            ("invpend", False, False, True)])
+def test_model_offsets_match_rollout(name, rp, dp, pre):
+    """x+ = F x + G u + Gd d + f_offset, y = C x + Dd d + h_offset (model.jl:61-72): the offset state of
+    mpc2mpqp.jl:684-689 collapsed into f / bu / bl (:395-399, :518-522) and h_offset folded into the reference
+    (:523-530), against a plain simulation of the affine model; also with a prestabilising feedback."""
+    mpc = _example(name, rp, dp)
+    rng = np.random.default_rng(11)
+    mpc.f_offset = 0.1 * rng.normal(size=mpc.nx)
+    mpc.h_offset = 0.2 * rng.normal(size=mpc.ny)
+    if pre:
+        mpc.set_prestabilizing_feedback()
+    qp = om.mpc2mpqp(mpc)
+    nx, nr, nd, nup = mpc.parameter_dims()
+    N, Nc, nu, ny, ndm = mpc.Np, mpc.Nc, mpc.nu, mpc.ny, mpc.nd_model
+    assert qp.f_theta.shape[1] == nx + nr + nd + nup == qp.W.shape[1] and np.any(qp.f != 0)
+    for _ in range(4):
+        x0 = rng.normal(size=nx)
+        Rp = rng.normal(size=(ny, N)) if rp else np.repeat(rng.normal(size=(ny, 1)), N, axis=1)
+        Dp = (rng.normal(size=(ndm, N)) if dp else np.repeat(rng.normal(size=(ndm, 1)), N, axis=1))
+        up = rng.normal(size=nu) if nup else np.zeros(nu)
+        th = mpc.form_parameter(x0, Rp if rp else Rp[:, 0], (Dp if dp else Dp[:, 0]) if ndm else None, up)
+        U1, U2 = rng.normal(size=(Nc, nu)), rng.normal(size=(Nc, nu))
+        J1, g1 = _rollout(mpc, x0, Rp, Dp, up, U1)
+        J2, _ = _rollout(mpc, x0, Rp, Dp, up, U2)
+        q = lambda U: 0.5 * U @ qp.H @ U + (qp.f + qp.f_theta @ th) @ U
+        assert abs((J1 - J2) - 2 * (q(U1.ravel()) - q(U2.ravel()))) <= 1e-9 * max(1.0, abs(J1), abs(J2))
+        ng = qp.A.shape[0]
+        if ng:
+            # the collapsed offset sits in the bounds: bl <= A U - W theta <= bu  <=>  lb <= row <= ub
+            c_ub = np.concatenate([np.zeros(0)] + [np.tile(c.ub, len([k for k in c.ks if k <= (N + 1 if not np.any(c.Au != 0) else N)]))
+                                                   for c in mpc.constraints])
+            if pre and len(mpc.umax):
+                c_ub = np.concatenate([np.tile(mpc.umax, Nc), c_ub])
+            dense = qp.A @ U1.ravel() - qp.W[-ng:] @ th
+            fin = c_ub < 1e20
+            np.testing.assert_allclose((dense - qp.bu[-ng:])[fin], (g1 - c_ub)[fin], rtol=1e-9, atol=1e-9)
+
+
+def test_operating_point_of_a_regulator_matches_rollout():
+    """reference_tracking off: the cost is around (xo, uo) (mpc2mpqp.jl:433-443, 457-459)."""
+    mpc = _example("invpend", False, False)
+    mpc.reference_tracking = False
+    mpc.Rr = np.zeros((1, 1))
+    mpc.xo, mpc.uo = np.array([0.3, -0.1, 0.05, 0.2]), np.array([0.4])
+    mpc.f_offset = np.array([0.01, 0.0, -0.02, 0.03])
+    qp = om.mpc2mpqp(mpc)
+    assert mpc.parameter_dims() == (4, 0, 0, 0) and qp.f_theta.shape[1] == 4
+    rng = np.random.default_rng(5)
+    N, Nc, nu = mpc.Np, mpc.Nc, mpc.nu
+    for _ in range(4):
+        x0 = rng.normal(size=4)
+        U1, U2 = rng.normal(size=(Nc, nu)), rng.normal(size=(Nc, nu))
+        Z = np.zeros((mpc.ny, N))
+        J1, _ = _rollout(mpc, x0, Z, np.zeros((0, N)), np.zeros(nu), U1)
+        J2, _ = _rollout(mpc, x0, Z, np.zeros((0, N)), np.zeros(nu), U2)
+        q = lambda U: 0.5 * U @ qp.H @ U + (qp.f + qp.f_theta @ x0) @ U
+        assert abs((J1 - J2) - 2 * (q(U1.ravel()) - q(U2.ravel()))) <= 1e-9 * max(1.0, abs(J1), abs(J2))
