@@ -227,40 +227,189 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const BC &
   cx.iter = K + 2;
 }
 
-template <int N, int NU, int MINB, bool CP = false>
-__global__ void __launch_bounds__(KB_BLOCK, MINB)
-ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
-               const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-               SolveOut out, int flags) {
-  const bool use_tiles = flags & 1;
-  constexpr bool use_cp = CP;   // compile-time: with both loops in one kernel the gain on short theta is lost
-  extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t mbar;
-  stage_constants_tma(smem, cblk, lay.total, &mbar);
-  const ConstView cv = make_view(smem, lay);
-  // padded copy of M-bar for the 128-bit row gathers
-  constexpr int NP = BoxPad<N>::NP;
-  double *Mp = smem + ((lay.total + 1) & ~1);
-  for (int i = threadIdx.x; i < N * NP; i += KB_BLOCK) Mp[i] = (i % NP < N) ? cv.M[(i / NP) * N + i % NP] : 0.0;
-  // [Dth; Uth] transposed and padded to NQ doubles per theta entry: the constants of one entry of
-  // theta arrive in NQ / 2 128-bit broadcast loads instead of N + NU 64-bit ones (with a preview
-  // theta has ~100 entries and this mat-vec runs next to the theta stream: the LSU was the busiest unit).
-  // Only when the copy does not cost a resident CTA (the CP instantiation, chosen at launch).
+
+// ---------------------------------------------------------------------------------------------
+// K1c: the add-only fast path.  98 % of the headline batch (s = 1; 100 % at s <= 0.25) never remove a
+// row: iteration K + 1 then works on exactly the slots 0..K-1, so the whole solve is straight-line
+// code with compile-time loop bounds and slots -- no generic loop, no "which slot" selects, no lam /
+// lam* / D kept between iterations, and the forward sweep of the CSP solve collapses to the one new
+// entry of z (z_0..z_{K-2} are the same fma chains as in the previous iteration).  An instance whose
+// multipliers block is handed over (flag EXIT_REDO_BOX, nothing else written) to the second launch:
+// the generic kernel in REDO mode, which compacts the handed-over instances per CTA and solves them
+// from scratch.  Same operations in the same order as the generic iteration -> bit-identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int EXIT_REDO_BOX = -100;   // internal, never seen by the caller
+
+template <int N>
+struct FastState {
+  double L[N * (N - 1) / 2 > 0 ? N * (N - 1) / 2 : 1];
+  double Dinv[N], dW[N], z[N];
+  int row[N];
+  unsigned lowmask, inws;
+};
+
+// most violated free row: code = 2 * row + (1 if lower), -1 if none (first minimum wins)
+template <int N, class BC>
+LMPC_DEVINL int box_scan(const BC &bc, unsigned inws, double primal_tol, const double (&dU)[N],
+                         const double (&dLo)[N], const double (&u)[N]) {
+  double best = -primal_tol;
+  int code = -1;
+  SFOR(j, 0, N)
+    double mu = 0.0;
+    SFOR(c, j, N) mu = fma(bc.M[j * N + c], u[c], mu); SEND
+    const bool free_row = !((inws >> j) & 1u);
+    const double su = dU[j] - mu, sl = mu - dLo[j];
+    const bool tu = free_row && (su < best);
+    const bool tl = free_row && !tu && (sl < best);
+    best = tu ? su : (tl ? sl : best);
+    code = tu ? 2 * j : (tl ? 2 * j + 1 : code);
+  SEND
+  return code;
+}
+
+// iteration K + 1 on the working set {slots 0..K-1}; true = this instance is finished (flag, iter set)
+template <int N, int K, class BC>
+LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, const double *Mp, const LdpSettings &st,
+                           const double (&dU)[N], const double (&dLo)[N], double (&u)[N], double &best_fval,
+                           int &cycle, int &flag, int &iter) {
+  iter = K + 1;
+  {
+    double zi = -s.dW[K - 1];
+    SFOR(c, 0, K - 1) zi = fma(-s.L[LIDX(K - 1, c)], s.z[c], zi); SEND
+    s.z[K - 1] = zi;
+  }
+  double lams[K];
+  SFOR(i, 0, K) lams[i] = s.z[i] * s.Dinv[i]; SEND
+  SFOR_DOWN(j, K, 1)
+    const double xj = lams[j];
+    SFOR(i, 0, j) lams[i] = fma(-s.L[LIDX(j, i)], xj, lams[i]); SEND
+  SEND
+  bool blocked = false;
+  SFOR(i, 0, K)
+    const bool low = (s.lowmask >> i) & 1u;
+    blocked |= low ? (lams[i] > st.dual_tol) : (lams[i] < -st.dual_tol);
+  SEND
+  if (blocked) { flag = EXIT_REDO_BOX; return true; }
+  SFOR(c, 0, N) u[c] = 0.0; SEND
+  SFOR(i, 0, K) box_axpy_row<N>(Mp, s.row[i], lams[i], u); SEND
+  double pu[N];
+  SFOR(c, 0, N) pu[c] = __dmul_rn(u[c], u[c]); SEND
+  const double fval = tree_sum<N, 0, 1>(pu);
+  if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; return true; }
+  if constexpr (K == N) {          // every row is in the working set: nothing left to violate
+    flag = EXIT_OPTIMAL;
+    return true;
+  } else {
+    const int code = box_scan<N>(bc, s.inws, st.primal_tol, dU, dLo, u);
+    const int add = code >> 1;
+    const bool addlow = code & 1;
+    if (add < 0) { flag = EXIT_OPTIMAL; return true; }
+    if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
+    else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; return true; }
+    double addd = 0.0;
+    SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
+    const double *g = cv.G + add * N;
+    double y[K], l[K], pr[K];
+    SFOR(i, 0, K)
+      double yi = g[s.row[i]];
+      SFOR(c, 0, i) yi = fma(-s.L[LIDX(i, c)], y[c], yi); SEND
+      y[i] = yi;
+    SEND
+    SFOR(i, 0, K) l[i] = y[i] * s.Dinv[i]; pr[i] = __dmul_rn(y[i], l[i]); SEND
+    const double dnew = __dsub_rn(g[add], tree_sum<K, 0, 1>(pr));
+    SFOR(i, 0, K) s.L[LIDX(K, i)] = l[i]; SEND
+    s.Dinv[K] = 1.0 / dnew; s.dW[K] = addd; s.row[K] = add;
+    if (addlow) s.lowmask |= 1u << K;
+    s.inws |= 1u << add;
+    return false;
+  }
+}
+
+template <int N, int K, class BC>
+LMPC_DEVINL void fast_chain(FastState<N> &s, const ConstView &cv, const BC &bc, const double *Mp, const LdpSettings &st,
+                            const double (&dU)[N], const double (&dLo)[N], double (&u)[N], double &best_fval,
+                            int &cycle, int &flag, int &iter) {
+  if (fast_iter<N, K>(s, cv, bc, Mp, st, dU, dLo, u, best_fval, cycle, flag, iter)) return;
+  if constexpr (K < N) fast_chain<N, K + 1>(s, cv, bc, Mp, st, dU, dLo, u, best_fval, cycle, flag, iter);
+}
+
+// theta pass shared by the box kernels: sh = Dth theta, sho = uoff + Uth theta, from the warp's TMA tile
+// (refilled for the warp's next batch) or straight from the row segments
+template <int N, int NU, bool CP>
+LMPC_DEVINL void box_theta_pass(const ConstView &cv, const double *Cp, double *tile, uint64_t *tbar_w, uint32_t &tphase,
+                                const ThetaSegs &th, int nth, int64_t q, int lane, int64_t qstride, int64_t Ninst,
+                                bool use_tiles, double (&sh)[N], double (&sho)[NU]) {
   constexpr int NQ = (N + NU + 1) & ~1;
-  double *Cp = Mp + N * NP;
-  const int ncp = use_cp ? lay.nth * NQ : 0;
+  SFOR(j, 0, N) sh[j] = 0.0; SEND
+  SFOR(i, 0, NU) sho[i] = cv.uoff[i]; SEND
+  const int64_t qt = q - lane;                 // first instance of this warp's tile (warp-uniform)
+  if (use_tiles && qt + 32 <= Ninst) {
+    tile_wait(tbar_w, tphase);
+    tphase ^= 1u;
+    const double *src = tile + lane * nth;     // stride nth doubles: conflict-free for odd and even nth alike
+    if constexpr (!CP) {
+#pragma unroll KB_THU
+      for (int tt = 0; tt < nth; ++tt) {
+        const double tv = src[tt];
+        SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
+        SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
+      }
+    } else
+#pragma unroll KB_THU
+    for (int tt = 0; tt < nth; ++tt) {
+      const double tv = src[tt];
+      const double2 *c2 = reinterpret_cast<const double2 *>(Cp + tt * NQ);
+      double cc[NQ];
+      SFOR(h, 0, NQ / 2) const double2 v = c2[h]; cc[2 * h] = v.x; cc[2 * h + 1] = v.y; SEND
+      SFOR(j, 0, N) sh[j] = fma(cc[j], tv, sh[j]); SEND
+      SFOR(i, 0, NU) sho[i] = fma(cc[N + i], tv, sho[i]); SEND
+    }
+    __syncwarp();                              // everybody has read the slot: refill it
+    if (lane == 0 && qt + qstride + 32 <= Ninst)
+      tile_issue(tbar_w, tile, th.ptr[0] + (qt + qstride) * nth, 32u * nth * 8u);
+  } else {
+    int o = 0;
+#pragma unroll 1
+    for (int sg = 0; sg < th.nseg; ++sg) {      // one copy of the loop body for all segments
+      const int len = th.len[sg];
+      const double *src = th.ptr[sg] + q * th.stride[sg];
+#pragma unroll KB_THU
+      for (int t = 0; t < len; ++t) {
+        const double tv = ld_stream(src + t);
+        const int tt = o + t;
+        SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
+        SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
+      }
+      o += len;
+    }
+  }
+}
+
+// shared prologue of the box kernels: constants by TMA, padded M-bar, transposed [Dth; Uth], theta tiles
+template <int N, int NU, bool CP>
+struct BoxSmem {
+  ConstView cv;
+  double *Mp, *Cp, *tile, *end;
+};
+template <int N, int NU, bool CP>
+LMPC_DEVINL BoxSmem<N, NU, CP> box_prologue(double *smem, uint64_t *mbar, uint64_t *tbar, const LdpLayout &lay,
+                                            const double *cblk, const ThetaSegs &th, int64_t Ninst, bool use_tiles) {
+  BoxSmem<N, NU, CP> b;
+  stage_constants_tma(smem, cblk, lay.total, mbar);
+  b.cv = make_view(smem, lay);
+  constexpr int NP = BoxPad<N>::NP;
+  constexpr int NQ = (N + NU + 1) & ~1;
+  b.Mp = smem + ((lay.total + 1) & ~1);
+  for (int i = threadIdx.x; i < N * NP; i += KB_BLOCK) b.Mp[i] = (i % NP < N) ? b.cv.M[(i / NP) * N + i % NP] : 0.0;
+  b.Cp = b.Mp + N * NP;
+  const int ncp = CP ? lay.nth * NQ : 0;
   for (int i = threadIdx.x; i < ncp; i += KB_BLOCK) {
     const int tt = i / NQ, c = i % NQ;
-    Cp[i] = c < N ? cv.Dth[c * lay.nth + tt] : (c < N + NU ? cv.Uth[(c - N) * lay.nth + tt] : 0.0);
+    b.Cp[i] = c < N ? b.cv.Dth[c * lay.nth + tt] : (c < N + NU ? b.cv.Uth[(c - N) * lay.nth + tt] : 0.0);
   }
-  // theta tiles: when Theta is one contiguous nth x N block, each warp streams its next 32
-  // parameters into its own slot with one TMA bulk copy while it is still iterating on the
-  // current ones (the direct loads at the top of a solve were 15 % of the stall samples)
-  __shared__ __align__(8) uint64_t tbar[KB_BLOCK / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *tile = Cp + ncp + (size_t)warp * 32 * lay.nth;
-  const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
-  uint32_t tphase = 0;
+  b.tile = b.Cp + ncp + (size_t)warp * 32 * lay.nth;
+  b.end = b.Cp + ncp;
   if (use_tiles) {
     if (lane == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar[warp])));
@@ -268,58 +417,114 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
     }
     __syncwarp();
     const int64_t q0 = (int64_t)blockIdx.x * KB_BLOCK + warp * 32;
-    if (lane == 0 && q0 + 32 <= Ninst) tile_issue(&tbar[warp], tile, th.ptr[0] + q0 * lay.nth, 32u * lay.nth * 8u);
+    if (lane == 0 && q0 + 32 <= Ninst) tile_issue(&tbar[warp], b.tile, th.ptr[0] + q0 * lay.nth, 32u * lay.nth * 8u);
   }
   __syncthreads();
+  return b;
+}
+
+template <int N, int NU, int MINB, bool CP>
+__global__ void __launch_bounds__(KB_BLOCK, MINB)
+ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
+                    const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
+                    SolveOut out, int flags) {
+  const bool use_tiles = flags & 1;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t tbar[KB_BLOCK / 32];
+  const BoxSmem<N, NU, CP> b = box_prologue<N, NU, CP>(smem, &mbar, tbar, lay, cblk, th, Ninst, use_tiles);
+  const ConstView &cv = b.cv;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
+  uint32_t tphase = 0;
   const int nth = lay.nth;
-  BoxState<N> s;
-  for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst;
-       q += qstride) {
-    // ---- mpc_update_parameter + mpc_update_qp + output shift in one pass over theta ----------
+  for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst; q += qstride) {
     double sh[N], sho[NU];
-    SFOR(j, 0, N) sh[j] = 0.0; SEND
-    SFOR(i, 0, NU) sho[i] = cv.uoff[i]; SEND
-    const int64_t qt = q - lane;                 // first instance of this warp's tile (warp-uniform)
-    if (use_tiles && qt + 32 <= Ninst) {
-      tile_wait(&tbar[warp], tphase);
-      tphase ^= 1u;
-      const double *src = tile + lane * nth;     // stride nth doubles: conflict-free for odd and even nth alike
-      if constexpr (!use_cp) {
-#pragma unroll KB_THU
-        for (int tt = 0; tt < nth; ++tt) {
-          const double tv = src[tt];
-          SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
-          SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
-        }
-      } else
-#pragma unroll KB_THU
-      for (int tt = 0; tt < nth; ++tt) {
-        const double tv = src[tt];
-        const double2 *c2 = reinterpret_cast<const double2 *>(Cp + tt * NQ);
-        double cc[NQ];
-        SFOR(h, 0, NQ / 2) const double2 v = c2[h]; cc[2 * h] = v.x; cc[2 * h + 1] = v.y; SEND
-        SFOR(j, 0, N) sh[j] = fma(cc[j], tv, sh[j]); SEND
-        SFOR(i, 0, NU) sho[i] = fma(cc[N + i], tv, sho[i]); SEND
-      }
-      __syncwarp();                              // everybody has read the slot: refill it
-      if (lane == 0 && qt + qstride + 32 <= Ninst)
-        tile_issue(&tbar[warp], tile, th.ptr[0] + (qt + qstride) * nth, 32u * nth * 8u);
-    } else {
-      int o = 0;
-#pragma unroll 1
-      for (int sg = 0; sg < th.nseg; ++sg) {      // one copy of the loop body for all segments
-        const int len = th.len[sg];
-        const double *src = th.ptr[sg] + q * th.stride[sg];
-#pragma unroll KB_THU
-        for (int t = 0; t < len; ++t) {
-          const double tv = ld_stream(src + t);
-          const int tt = o + t;
-          SFOR(j, 0, N) sh[j] = fma(cv.Dth[j * nth + tt], tv, sh[j]); SEND
-          SFOR(i, 0, NU) sho[i] = fma(cv.Uth[i * nth + tt], tv, sho[i]); SEND
-        }
-        o += len;
+    box_theta_pass<N, NU, CP>(cv, b.Cp, b.tile, &tbar[warp], tphase, th, nth, q, lane, qstride, Ninst, use_tiles, sh, sho);
+    double dU[N], dLo[N];
+    SFOR(j, 0, N) dU[j] = bc.du[j] + sh[j]; dLo[j] = bc.dl[j] + sh[j]; SEND
+    FastState<N> s;
+    s.lowmask = 0u; s.inws = 0u;
+    double u[N];
+    SFOR(c, 0, N) u[c] = 0.0; SEND
+    int flag = EXIT_OPTIMAL, iter = 1, cycle = 0;
+    double best_fval = -1.0;
+    // iteration 1: empty working set, u = 0, every slack is a bound, the dual objective is 0
+    {
+      double best = -st.primal_tol;
+      int code = -1;
+      SFOR(j, 0, N)
+        const double su = dU[j] - 0.0, sl = 0.0 - dLo[j];
+        const bool tu = su < best;
+        const bool tl = !tu && (sl < best);
+        best = tu ? su : (tl ? sl : best);
+        code = tu ? 2 * j : (tl ? 2 * j + 1 : code);
+      SEND
+      const int add = code >> 1;
+      const bool addlow = code & 1;
+      if (add >= 0) {
+        if (0.0 - st.progress_tol > best_fval) { best_fval = 0.0; cycle = 0; }
+        else cycle++;
+        double addd = 0.0;
+        SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
+        const double g = cv.G[add * N + add];
+        s.Dinv[0] = 1.0 / g; s.dW[0] = addd; s.row[0] = add;
+        s.lowmask = addlow ? 1u : 0u;
+        s.inws = 1u << add;
+        fast_chain<N, 1>(s, cv, bc, b.Mp, st, dU, dLo, u, best_fval, cycle, flag, iter);
       }
     }
+    if (flag == EXIT_REDO_BOX) { out.flag[q] = flag; continue; }
+    SFOR(i, 0, NU)
+      double pr[N];
+      SFOR(c, 0, N) pr[c] = __dmul_rn(bc.Rinv[i * N + c], u[c]); SEND
+      out.U[q * NU + i] = __dadd_rn(tree_sum<N, 0, 1>(pr), sho[i]);
+    SEND
+    out.flag[q] = flag;
+    if (out.iters) out.iters[q] = iter;
+    if (out.act_u) {
+      // slots 0..k-1 hold the working set; k = popcount(inws)
+      unsigned long long au = 0ull, al = 0ull;
+      const int k = __popc(s.inws);
+      SFOR(i, 0, N)
+        if (i < k) {
+          if ((s.lowmask >> i) & 1u) al |= 1ull << s.row[i]; else au |= 1ull << s.row[i];
+        }
+      SEND
+      out.act_u[q] = au;
+      out.act_l[q] = al;
+    }
+  }
+}
+
+// REDO = true: the second launch behind the add-only fast kernel.  Every CTA owns a contiguous range of
+// instances, compacts the ones the fast kernel handed over (flag == EXIT_REDO_BOX) into a shared-memory
+// queue (coalesced flag reads, one ballot per warp and step) and solves them 128 at a time from scratch,
+// so the lanes stay full although only ~2 % of the batch comes back.
+constexpr int KB_QCAP = 1024;   // queue entries per CTA (int32 offsets into the CTA's range)
+template <int N, int NU, int MINB, bool CP = false, bool REDO = false>
+__global__ void __launch_bounds__(KB_BLOCK, MINB)
+ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
+               const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
+               SolveOut out, int flags) {
+  const bool use_tiles = !REDO && (flags & 1);
+  constexpr bool use_cp = CP;   // compile-time: with both loops in one kernel the gain on short theta is lost
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t tbar[KB_BLOCK / 32];
+  const BoxSmem<N, NU, CP> bsm = box_prologue<N, NU, CP>(smem, &mbar, tbar, lay, cblk, th, Ninst, use_tiles);
+  const ConstView &cv = bsm.cv;
+  const double *Mp = bsm.Mp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
+  uint32_t tphase = 0;
+  const int nth = lay.nth;
+  BoxState<N> s;
+  auto solve_one = [&](const int64_t q) {
+    // ---- mpc_update_parameter + mpc_update_qp + output shift in one pass over theta ----------
+    double sh[N], sho[NU];
+    box_theta_pass<N, NU, use_cp>(cv, bsm.Cp, bsm.tile, &tbar[warp], tphase, th, nth, q, lane, qstride, Ninst,
+                                  use_tiles, sh, sho);
     // theta-dependent bounds, once per solve (mpc_update_qp): d_u = du + sh, d_l = dl + sh
     double dU[N], dLo[N];
     SFOR(j, 0, N) dU[j] = bc.du[j] + sh[j]; dLo[j] = bc.dl[j] + sh[j]; SEND
@@ -458,19 +663,62 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
       out.act_u[q] = au;
       out.act_l[q] = al;
     }
+  };
+  if constexpr (!REDO) {
+    for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst; q += qstride) solve_one(q);
+  } else {
+    int *queue = reinterpret_cast<int *>(bsm.end);
+    __shared__ int qn;
+    // contiguous range per CTA, a multiple of the block size
+    const int64_t per = ((Ninst + gridDim.x - 1) / gridDim.x + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = (r0 + per < Ninst) ? r0 + per : Ninst;
+    int64_t pos = r0;
+    while (pos < r1) {
+      if (threadIdx.x == 0) qn = 0;
+      __syncthreads();
+      // fill: stop when another step might not fit
+      int filled = 0;
+      while (pos < r1 && filled <= KB_QCAP - KB_BLOCK) {
+        const int64_t q = pos + threadIdx.x;
+        const bool mine = q < r1 && out.flag[q] == EXIT_REDO_BOX;
+        const unsigned bal = __ballot_sync(0xffffffffu, mine);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (mine) queue[base + __popc(bal & ((1u << lane) - 1u))] = (int)(q - r0);
+        pos += KB_BLOCK;
+        __syncthreads();
+        filled = qn;
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < filled; i += KB_BLOCK) solve_one(r0 + queue[i]);
+      __syncthreads();
+    }
   }
 }
 
 #ifndef KB_MINB
 #define KB_MINB 3
 #endif
+#ifndef KB_FAST
+#define KB_FAST 1      // 0: the generic kernel alone, as before r02
+#endif
+#ifndef KB_FAST_MINB
+#define KB_FAST_MINB 4
+#endif
 template <int N, int NU, int MINB = KB_MINB>
 int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
                const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
-  auto kern = ldp_box_kernel<N, NU, MINB, false>;
-  auto kern_cp = ldp_box_kernel<N, NU, MINB, true>;
-  size_t smem = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
+  // the add-only fast kernel + the REDO launch of the generic one, or the generic kernel alone when the
+  // settings could stop a solve inside the fast kernel's N + 1 iterations
+  const bool fast = KB_FAST && st.iter_limit > N + 2;
+  using kern_t = void (*)(LdpLayout, LdpSettings, const BoxConst<N, NU>, const double *, const ThetaSegs, int64_t,
+                          SolveOut, int);
+  kern_t kern = fast ? (kern_t)ldp_box_fast_kernel<N, NU, KB_FAST_MINB, false> : (kern_t)ldp_box_kernel<N, NU, MINB, false>;
+  kern_t kern_cp = fast ? (kern_t)ldp_box_fast_kernel<N, NU, KB_FAST_MINB, true> : (kern_t)ldp_box_kernel<N, NU, MINB, true>;
+  const size_t smem_base = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
+  size_t smem = smem_base;
   // one 32-theta slot per warp when Theta is a single contiguous, 16-byte aligned block
   const int use_tiles = th.nseg == 1 && th.len[0] == lay.nth && th.stride[0] == lay.nth &&
                         (reinterpret_cast<uintptr_t>(th.ptr[0]) & 15u) == 0 && Ninst >= 32;
@@ -486,6 +734,7 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern_cp, KB_BLOCK, smem_cp);
     if (b >= a && b >= 1) { use_cp = 1; smem = smem_cp; kern = kern_cp; }
   }
+  (void)use_cp;
   BoxConst<N, NU> bc;
   for (int i = 0; i < N * N; ++i) bc.M[i] = hblk[lay.oM + i];
   for (int i = 0; i < N; ++i) { bc.du[i] = hblk[lay.odu + i]; bc.dl[i] = hblk[lay.odl + i]; }
@@ -499,6 +748,19 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   const int64_t cap = (int64_t)sm_count * per_sm;   // persistent: whole resident waves over the SMs
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out, use_tiles);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || !fast) return (int)e;
+  // second launch: whatever the fast kernel handed over, compacted per CTA
+  kern_t redo = (kern_t)ldp_box_kernel<N, NU, MINB, false, true>;
+  const size_t smem_redo = smem_base + (size_t)KB_QCAP * sizeof(int);
+  e = cudaFuncSetAttribute(redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_redo);
+  if (e != cudaSuccess) return (int)e;
+  per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, redo, KB_BLOCK, smem_redo);
+  if (per_sm < 1) per_sm = 1;
+  int64_t rblocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
+  if (rblocks > (int64_t)sm_count * per_sm) rblocks = (int64_t)sm_count * per_sm;
+  redo<<<(unsigned)rblocks, KB_BLOCK, smem_redo, stream>>>(lay, st, bc, cblk, th, Ninst, out, 0);
   return (int)cudaGetLastError();
 }
 
@@ -520,7 +782,11 @@ int launch_ldp_box(const LdpLayout &lay, const LdpSettings &st, const double *cb
   cudaStream_t s = (cudaStream_t)stream;
   if (N <= 0) return 0;
   switch (lay.n) {
+#ifdef KB_ONLY5          // A/B builds: the headline instantiation only (compiles in seconds)
+    KB_CASE(5)
+#else
     KB_CASE(1) KB_CASE(2) KB_CASE(3) KB_CASE(4) KB_CASE(5) KB_CASE(6) KB_CASE(7) KB_CASE(8)
+#endif
     default: return (int)cudaErrorInvalidValue;
   }
 }
