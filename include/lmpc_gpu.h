@@ -11,6 +11,9 @@
  * Pointers passed to the *_batch calls may be host or device pointers (detected with
  * cudaPointerGetAttributes).  Host buffers are staged through the handle's pinned/device
  * scratch inside the call; device buffers are used in place on the handle's stream.
+ * The handle's stream is non-blocking: work that PRODUCES a device buffer on another stream must have
+ * completed (or be ordered by an event) before a synchronous entry point is handed that buffer; the
+ * call itself returns only after its own kernels and copies have finished.
  *
  * Return value of every function: 0 on success, negative LMPC_E_* on API failure
  * (never an exception).  Per-instance solver status uses DAQP's exit-flag integers

@@ -270,8 +270,8 @@ LMPC_DEVINL int box_scan(const BC &bc, unsigned inws, double primal_tol, const d
 // iteration K + 1 on the working set {slots 0..K-1}; true = this instance is finished (flag, iter set)
 template <int N, int K, class BC>
 LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, const double *Mp, const LdpSettings &st,
-                           const double (&dU)[N], const double (&dLo)[N], double (&u)[N], double &best_fval,
-                           int &cycle, int &flag, int &iter) {
+                           const double (&dU)[N], const double (&dLo)[N], const double *bnd, double (&u)[N],
+                           double &best_fval, int &cycle, int &flag, int &iter) {
   iter = K + 1;
   {
     double zi = -s.dW[K - 1];
@@ -306,8 +306,7 @@ LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, c
     if (add < 0) { flag = EXIT_OPTIMAL; return true; }
     if (fval - st.progress_tol > best_fval) { best_fval = fval; cycle = 0; }
     else if (cycle++ > st.cycle_tol) { flag = EXIT_CYCLE; return true; }
-    double addd = 0.0;
-    SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
+    const double addd = bnd[code * KB_BLOCK];   // the thread's own copy of dU / dLo: one load instead of 2 N selects
     const double *g = cv.G + add * N;
     double y[K], l[K], pr[K];
     SFOR(i, 0, K)
@@ -327,10 +326,10 @@ LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, c
 
 template <int N, int K, class BC>
 LMPC_DEVINL void fast_chain(FastState<N> &s, const ConstView &cv, const BC &bc, const double *Mp, const LdpSettings &st,
-                            const double (&dU)[N], const double (&dLo)[N], double (&u)[N], double &best_fval,
-                            int &cycle, int &flag, int &iter) {
-  if (fast_iter<N, K>(s, cv, bc, Mp, st, dU, dLo, u, best_fval, cycle, flag, iter)) return;
-  if constexpr (K < N) fast_chain<N, K + 1>(s, cv, bc, Mp, st, dU, dLo, u, best_fval, cycle, flag, iter);
+                            const double (&dU)[N], const double (&dLo)[N], const double *bnd, double (&u)[N],
+                            double &best_fval, int &cycle, int &flag, int &iter) {
+  if (fast_iter<N, K>(s, cv, bc, Mp, st, dU, dLo, bnd, u, best_fval, cycle, flag, iter)) return;
+  if constexpr (K < N) fast_chain<N, K + 1>(s, cv, bc, Mp, st, dU, dLo, bnd, u, best_fval, cycle, flag, iter);
 }
 
 // theta pass shared by the box kernels: sh = Dth theta, sho = uoff + Uth theta, from the warp's TMA tile
@@ -438,11 +437,14 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
   const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
   uint32_t tphase = 0;
   const int nth = lay.nth;
+  double *bnd = b.end + (use_tiles ? (size_t)KB_BLOCK * nth : 0) + threadIdx.x;
   for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst; q += qstride) {
     double sh[N], sho[NU];
     box_theta_pass<N, NU, CP>(cv, b.Cp, b.tile, &tbar[warp], tphase, th, nth, q, lane, qstride, Ninst, use_tiles, sh, sho);
     double dU[N], dLo[N];
     SFOR(j, 0, N) dU[j] = bc.du[j] + sh[j]; dLo[j] = bc.dl[j] + sh[j]; SEND
+    // bnd[(2 j + lower) * KB_BLOCK]: the bound a scan result `code` refers to (column of this thread)
+    SFOR(j, 0, N) bnd[(2 * j) * KB_BLOCK] = dU[j]; bnd[(2 * j + 1) * KB_BLOCK] = dLo[j]; SEND
     FastState<N> s;
     s.lowmask = 0u; s.inws = 0u;
     double u[N];
@@ -465,13 +467,12 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
       if (add >= 0) {
         if (0.0 - st.progress_tol > best_fval) { best_fval = 0.0; cycle = 0; }
         else cycle++;
-        double addd = 0.0;
-        SFOR(j, 0, N) addd = (add == j) ? (addlow ? dLo[j] : dU[j]) : addd; SEND
+        const double addd = bnd[code * KB_BLOCK];
         const double g = cv.G[add * N + add];
         s.Dinv[0] = 1.0 / g; s.dW[0] = addd; s.row[0] = add;
         s.lowmask = addlow ? 1u : 0u;
         s.inws = 1u << add;
-        fast_chain<N, 1>(s, cv, bc, b.Mp, st, dU, dLo, u, best_fval, cycle, flag, iter);
+        fast_chain<N, 1>(s, cv, bc, b.Mp, st, dU, dLo, bnd, u, best_fval, cycle, flag, iter);
       }
     }
     if (flag == EXIT_REDO_BOX) { out.flag[q] = flag; continue; }
@@ -501,7 +502,9 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
 // instances, compacts the ones the fast kernel handed over (flag == EXIT_REDO_BOX) into a shared-memory
 // queue (coalesced flag reads, one ballot per warp and step) and solves them 128 at a time from scratch,
 // so the lanes stay full although only ~2 % of the batch comes back.
-constexpr int KB_QCAP = 1024;   // queue entries per CTA (int32 offsets into the CTA's range)
+constexpr int KB_SCAN = 16 * KB_BLOCK;   // flags examined per fill step
+constexpr int KB_QCAP = 2 * KB_SCAN;     // queue entries per CTA (int32 offsets into the CTA's range)
+static_assert(KB_QCAP >= KB_SCAN, "a fill step must fit into an empty queue");
 template <int N, int NU, int MINB, bool CP = false, bool REDO = false>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
@@ -670,23 +673,32 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
     int *queue = reinterpret_cast<int *>(bsm.end);
     __shared__ int qn;
     // contiguous range per CTA, a multiple of the block size
-    const int64_t per = ((Ninst + gridDim.x - 1) / gridDim.x + KB_BLOCK - 1) / KB_BLOCK * KB_BLOCK;
+    const int64_t per = ((Ninst + gridDim.x - 1) / gridDim.x + KB_SCAN - 1) / KB_SCAN * KB_SCAN;
     const int64_t r0 = (int64_t)blockIdx.x * per, r1 = (r0 + per < Ninst) ? r0 + per : Ninst;
     int64_t pos = r0;
     while (pos < r1) {
       if (threadIdx.x == 0) qn = 0;
       __syncthreads();
-      // fill: stop when another step might not fit
+      // fill: KB_SCAN flags per step (the loads of a step are all in flight together: a 128-flag step was
+      // one exposed DRAM latency each, 144 us per launch), stop when another step might not fit
       int filled = 0;
-      while (pos < r1 && filled <= KB_QCAP - KB_BLOCK) {
-        const int64_t q = pos + threadIdx.x;
-        const bool mine = q < r1 && out.flag[q] == EXIT_REDO_BOX;
-        const unsigned bal = __ballot_sync(0xffffffffu, mine);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (mine) queue[base + __popc(bal & ((1u << lane) - 1u))] = (int)(q - r0);
-        pos += KB_BLOCK;
+      while (pos < r1 && filled <= KB_QCAP - KB_SCAN) {
+        int fl[KB_SCAN / KB_BLOCK];
+#pragma unroll
+        for (int j = 0; j < KB_SCAN / KB_BLOCK; ++j) {
+          const int64_t q = pos + j * KB_BLOCK + threadIdx.x;
+          fl[j] = q < r1 ? out.flag[q] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < KB_SCAN / KB_BLOCK; ++j) {
+          const bool mine = fl[j] == EXIT_REDO_BOX;
+          const unsigned bal = __ballot_sync(0xffffffffu, mine);
+          int base = 0;
+          if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (mine) queue[base + __popc(bal & ((1u << lane) - 1u))] = (int)(pos + j * KB_BLOCK + threadIdx.x - r0);
+        }
+        pos += KB_SCAN;
         __syncthreads();
         filled = qn;
         __syncthreads();
@@ -704,25 +716,29 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
 #define KB_FAST 1      // 0: the generic kernel alone, as before r02
 #endif
 #ifndef KB_FAST_MINB
-#define KB_FAST_MINB 4
+#define KB_FAST_MINB 3
 #endif
-template <int N, int NU, int MINB = KB_MINB>
+// resident CTAs per SM: 3 up to n = 5 (145-159 registers, no spills); from n = 6 on the state no longer fits
+// 168 registers (80 - 1700 B of spills per thread), so two CTAs with up to 255 registers each
+template <int N, int NU, int MINB = (N <= 5 ? KB_MINB : 2)>
 int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, const double *hblk,
                const ThetaSegs &th,
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
   // the add-only fast kernel + the REDO launch of the generic one, or the generic kernel alone when the
   // settings could stop a solve inside the fast kernel's N + 1 iterations
   const bool fast = KB_FAST && st.iter_limit > N + 2;
+  constexpr int FMINB = N <= 5 ? KB_FAST_MINB : 2;
   using kern_t = void (*)(LdpLayout, LdpSettings, const BoxConst<N, NU>, const double *, const ThetaSegs, int64_t,
                           SolveOut, int);
-  kern_t kern = fast ? (kern_t)ldp_box_fast_kernel<N, NU, KB_FAST_MINB, false> : (kern_t)ldp_box_kernel<N, NU, MINB, false>;
-  kern_t kern_cp = fast ? (kern_t)ldp_box_fast_kernel<N, NU, KB_FAST_MINB, true> : (kern_t)ldp_box_kernel<N, NU, MINB, true>;
+  kern_t kern = fast ? (kern_t)ldp_box_fast_kernel<N, NU, FMINB, false> : (kern_t)ldp_box_kernel<N, NU, MINB, false>;
+  kern_t kern_cp = fast ? (kern_t)ldp_box_fast_kernel<N, NU, FMINB, true> : (kern_t)ldp_box_kernel<N, NU, MINB, true>;
   const size_t smem_base = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
   size_t smem = smem_base;
   // one 32-theta slot per warp when Theta is a single contiguous, 16-byte aligned block
   const int use_tiles = th.nseg == 1 && th.len[0] == lay.nth && th.stride[0] == lay.nth &&
                         (reinterpret_cast<uintptr_t>(th.ptr[0]) & 15u) == 0 && Ninst >= 32;
   if (use_tiles) smem += (size_t)KB_BLOCK * lay.nth * sizeof(double);
+  if (fast) smem += (size_t)KB_BLOCK * 2 * N * sizeof(double);   // per-thread columns of dU / dLo
   // transposed constants for the theta mat-vec: taken only when they do not cost a resident CTA
   const size_t smem_cp = smem + (size_t)lay.nth * ((N + NU + 1) & ~1) * sizeof(double);
   int use_cp = 0;

@@ -192,6 +192,16 @@ def _is_device(a):
     return a is not None and not isinstance(a, np.ndarray)
 
 
+def _wait_producer(*tensors):
+    """The library's streams are non-blocking (include/lmpc_gpu.h, top): whatever torch queued on its
+    current stream to produce a device argument must have finished before a synchronous entry point reads it."""
+    for t in tensors:
+        if t is not None and getattr(t, "is_cuda", False):
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
+            return
+
+
 def _colmajor(a, rows):
     """Batch argument -> (rows x N) column-major float64 host array (instance per column).
     A vector of length `rows` is one instance; with rows == 1 a vector is 1 x N."""
@@ -355,6 +365,7 @@ class GpuMPC:
             iters = torch.empty(N, dtype=torch.int32, device=dev) if want_iters else None
             au = torch.empty((N, words), dtype=torch.int64, device=dev) if want_active else None
             al = torch.empty((N, words), dtype=torch.int64, device=dev) if want_active else None
+            _wait_producer(Theta)
             _check(lib().lmpc_gpu_solve_batch(self._h, _ptr(Theta), N, _ptr(U), _ptr(flag),
                                               _ptr(iters), _ptr(au), _ptr(al)))
             return dict(U=U.T, exitflag=flag, iters=iters, active_upper=au, active_lower=al)
@@ -381,6 +392,7 @@ class GpuMPC:
             U = torch.empty((N, self.nu), dtype=torch.float64, device=dev)
             flag = torch.empty(N, dtype=torch.int32, device=dev)
             iters = torch.empty(N, dtype=torch.int32, device=dev) if want_iters else None
+            _wait_producer(Theta)
             _check(lib().lmpc_gpu_solve_batch_warm(self._h, _ptr(Theta), N, _ptr(U), _ptr(flag), _ptr(iters),
                                                    _ptr(active_upper), _ptr(active_lower)))
             return dict(U=U.T, exitflag=flag, iters=iters, active_upper=active_upper, active_lower=active_lower)
@@ -500,6 +512,7 @@ class GpuMPC:
                     raise ValueError("per-instance blocks must be device tensors when x is one")
                 blocks.append(np.asfortranarray(v))
         nfail = C.c_int64(0)
+        _wait_producer(X)
         _check(lib().lmpc_gpu_compute_control_batch_bcast(self._h, _ptr(U), _ptr(X), _ptr(blocks[0]), _ptr(blocks[1]),
                                                           _ptr(blocks[2]), nr, nd, nup, N, mask, _ptr(flag),
                                                           C.addressof(nfail)))
@@ -789,6 +802,7 @@ class GpuExplicitMPC:
             N = Theta.numel() // self.nth
             U = torch.empty((N, self.nu), dtype=torch.float64, device=Theta.device)
             reg = torch.empty(N, dtype=torch.int32, device=Theta.device) if want_region else None
+            _wait_producer(Theta)
             _check(lib().lmpc_gpu_evaluate_batch(self._t, _ptr(Theta), N, _ptr(U), _ptr(reg)))
             return U.T, reg
         Th = _colmajor(Theta, self.nth)

@@ -3,6 +3,7 @@ import csv, subprocess, sys, io
 from collections import Counter
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+which = int(sys.argv[3]) if len(sys.argv) > 3 else None   # index of the kernel's source section (default: the longest)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h, units, data = rows[0], rows[1], rows[2:]
@@ -17,7 +18,7 @@ best = None
 for hi, hd in enumerate(hdrs):
     end = hdrs[hi + 1] - 3 if hi + 1 < len(hdrs) else len(rows)
     sec = rows[hd + 1:end]
-    if best is None or len(sec) > len(best[1]): best = (rows[hd], sec, rows[hd - 2][:2] if hd >= 2 else None)
+    if (which is None and (best is None or len(sec) > len(best[1]))) or which == hi: best = (rows[hd], sec, rows[hd - 2][:2] if hd >= 2 else None)
 hh, sec, fn = best
 print("source file:", fn)
 iS, iI = hh.index("# Samples"), hh.index("Instructions Executed")
