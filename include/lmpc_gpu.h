@@ -262,6 +262,44 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
                                double *Xend, double *Ulast, double *Utraj,
                                int32_t *exitflag, int32_t *iters);
 
+/* Stepped closed loop: the same Simulation loop, one short kernel sequence per time step with the
+ * loop state in HBM, for what the fused on-chip loop above cannot express:
+ *  - a NONLINEAR (or otherwise user-defined) TRUE PLANT, `scenario.dynamics` of src/simulation.jl:39,110 and
+ *    Model(f, h, ...)'s true_dynamics (src/model.jl:113-124): `dynamics` is called once per step and must enqueue,
+ *    on `stream`, work that writes Xnext (nx x N) from X (nx x N), U (nu x N) and D (ndm x N, NULL when ndm = 0),
+ *    all DEVICE arrays, instance per column; returns 0 on success.  dynamics == NULL: the affine plant
+ *    x+ = Ft x + Gt u + Gdt d + ft (NULL matrices = the controller's model F, G, Gd; ft NULL = 0);
+ *  - an observer with ITS OWN STATE of dimension nxo >= nx: the KalmanFilter of src/observer.jl:1-124 (nxo = nx)
+ *    or the OffsetFreeObserver's augmented estimator (src/observer.jl:12-47, 203-222), whose last nxo - nx
+ *    entries are estimated disturbances that are appended to the ndm measured ones in theta
+ *    (get_control_disturbance, src/observer.jl:203-222).  Every step: y = Cm x + Ddm d + hm (+ v_t),
+ *    correct! xhat += Ko (y - Co xhat - Ddo d - ho), compute_control on xhat[1:nx], predict!
+ *    xhat = Fo xhat + Go u + Gdo d + fo.  Ko == NULL: no observer (nxo is taken as nx).
+ * theta = [xhat[1:nx]; r; d_measured; xhat[nx+1:nxo]; uprev], so nx + nr + ndm + (nxo - nx) + nuprev = nth.
+ * Matrices are column-major HOST arrays: Ft nx x nx, Gt nx x nu, Gdt nx x ndm, Cm ny x nx, Ddm ny x ndm,
+ * Fo nxo x nxo, Go nxo x nu, Gdo nxo x ndm, Co ny x nxo, Ddo ny x ndm, Ko nxo x ny; Rtraj nr x T, Dtraj ndm x T,
+ * Vtraj ny x T shared by all closed loops (NULL: R / D per closed loop, no noise).  X0, R (nr x N), D (ndm x N),
+ * U0 and the outputs are HOST arrays.  warm_start carries the working set between steps through
+ * the warm-start entry of the solve kernels.  Xhat_end (nullable) nxo x N. */
+typedef int (*lmpc_plant_fn)(void *user, void *stream, int64_t N, int32_t k, const double *X, const double *U,
+                             const double *D, double *Xnext);
+typedef struct {
+  lmpc_plant_fn dynamics;
+  void *user;
+  const double *Ft, *Gt, *Gdt, *ft;
+  int32_t ny;
+  const double *Cm, *Ddm, *hm, *Vtraj;
+  int32_t nxo, ndm;
+  const double *Fo, *Go, *Gdo, *fo, *Co, *Ddo, *ho, *Ko;
+  const double *Rtraj, *Dtraj;
+  double *Xhat_end;
+} lmpc_sim_stepped;
+int lmpc_gpu_simulate_batch_stepped(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                                    int32_t nx, int32_t nr, int32_t nuprev,
+                                    const double *X0, const double *R, const double *D, const double *U0,
+                                    const lmpc_sim_stepped *cfg, int64_t N, int32_t T, int32_t warm_start,
+                                    double *Xend, double *Ulast, double *Utraj, int32_t *exitflag, int32_t *iters);
+
 /* Closed loops with the EXPLICIT law: N copies of Simulation(empc, scenario)
  * (src/simulation.jl:37-116 accepts an ExplicitMPC) with the linear dynamics of src/model.jl:70;
  * every step walks the tree on chip.  Arguments as lmpc_gpu_simulate_batch_traj (Rtraj / Dtraj
@@ -442,6 +480,7 @@ const char *lmpc_gpu_condense_error(void);
 #define LMPC_ABI_SIM_EXT 3
 #define LMPC_ABI_CONSTRAINT 4
 #define LMPC_ABI_MODEL 5
+#define LMPC_ABI_SIM_STEPPED 6
 int lmpc_gpu_abi_layout(int32_t *out, int32_t cap);
 
 /* Measurement helpers used by bench.py (not part of the reference's interface):

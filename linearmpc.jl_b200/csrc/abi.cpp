@@ -46,6 +46,14 @@ extern "C" int lmpc_gpu_abi_layout(int32_t *out, int32_t cap) {
         F(lmpc_model, K), F(lmpc_model, np), F(lmpc_model, Ex), F(lmpc_model, ex), F(lmpc_model, Eu),
         F(lmpc_model, eu), F(lmpc_model, parameter_preview),
         F(lmpc_model, f_offset), F(lmpc_model, h_offset), F(lmpc_model, xo), F(lmpc_model, uo)});
+  emit(o, LMPC_ABI_SIM_STEPPED, sizeof(lmpc_sim_stepped),
+       {F(lmpc_sim_stepped, dynamics), F(lmpc_sim_stepped, user), F(lmpc_sim_stepped, Ft), F(lmpc_sim_stepped, Gt),
+        F(lmpc_sim_stepped, Gdt), F(lmpc_sim_stepped, ft), F(lmpc_sim_stepped, ny), F(lmpc_sim_stepped, Cm),
+        F(lmpc_sim_stepped, Ddm), F(lmpc_sim_stepped, hm), F(lmpc_sim_stepped, Vtraj), F(lmpc_sim_stepped, nxo),
+        F(lmpc_sim_stepped, ndm), F(lmpc_sim_stepped, Fo), F(lmpc_sim_stepped, Go), F(lmpc_sim_stepped, Gdo),
+        F(lmpc_sim_stepped, fo), F(lmpc_sim_stepped, Co), F(lmpc_sim_stepped, Ddo), F(lmpc_sim_stepped, ho),
+        F(lmpc_sim_stepped, Ko), F(lmpc_sim_stepped, Rtraj), F(lmpc_sim_stepped, Dtraj),
+        F(lmpc_sim_stepped, Xhat_end)});
   if (out)
     for (int32_t i = 0; i < cap && i < (int32_t)o.size(); ++i) out[i] = o[i];
   return (int32_t)o.size();

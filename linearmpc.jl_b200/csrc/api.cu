@@ -804,6 +804,108 @@ int lmpc_gpu_simulate_batch_ex(lmpc_handle *h, const double *F, const double *G,
   return 0;
 }
 
+int lmpc_gpu_simulate_batch_stepped(lmpc_handle *h, const double *F, const double *G, const double *Gd,
+                                    int32_t nx, int32_t nr, int32_t nuprev,
+                                    const double *X0, const double *R, const double *D, const double *U0,
+                                    const lmpc_sim_stepped *cfg, int64_t N, int32_t T, int32_t warm_start,
+                                    double *Xend, double *Ulast, double *Utraj, int32_t *exitflag, int32_t *iters) {
+  if (!h || !F || !G || !X0 || !Xend || !Ulast || !exitflag || !cfg || N < 0 || T < 0)
+    return set_err(LMPC_E_INVALID, "lmpc_gpu_simulate_batch_stepped: bad argument%s");
+  const LdpLayout &l = h->lay;
+  const bool obs = cfg->Ko != nullptr;
+  const int nu = l.nu, ndm = cfg->ndm, nxo = obs ? cfg->nxo : nx, ny = obs ? cfg->ny : 0, ndo = nxo - nx;
+  if (nxo < nx || nx + nr + ndm + ndo + nuprev != l.nth || nuprev > nu || (ndm > 0 && !Gd && !cfg->Gdt && !cfg->dynamics))
+    return set_err(LMPC_E_INVALID, "simulate_batch_stepped: nx + nr + ndm + (nxo - nx) + nuprev must equal nth%s");
+  if (obs && (!cfg->Co || !cfg->Cm || !cfg->Fo || !cfg->Go || ny <= 0))
+    return set_err(LMPC_E_INVALID, "simulate_batch_stepped: an observer needs Cm, Co, Fo, Go, Ko and ny > 0%s");
+  if (is_device_ptr(X0)) return set_err(LMPC_E_UNSUPPORTED, "simulate_batch_stepped takes host arrays%s");
+  if (N == 0 || T == 0) return 0;
+  std::lock_guard<std::mutex> lock(h->mu);
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // constants, row-major, one upload
+  std::vector<double> ch;
+  auto mat = [&](const double *A, int r, int c) -> long { return (A && r > 0 && c > 0) ? (long)push_rowmajor(ch, A, r, c) : -1; };
+  auto vec = [&](const double *v, size_t n) -> long { if (!v || n == 0) return -1; const long o = (long)ch.size(); ch.insert(ch.end(), v, v + n); return o; };
+  const long oFt = mat(cfg->Ft ? cfg->Ft : F, nx, nx), oGt = mat(cfg->Gt ? cfg->Gt : G, nx, nu);
+  const long oGdt = mat(cfg->Gdt ? cfg->Gdt : Gd, nx, ndm), oft = vec(cfg->ft, nx);
+  const long oCm = mat(cfg->Cm, ny, nx), oDdm = mat(cfg->Ddm, ny, ndm), ohm = vec(cfg->hm, ny), oV = vec(cfg->Vtraj, (size_t)ny * T);
+  const long oFo = obs ? mat(cfg->Fo, nxo, nxo) : -1, oGo = obs ? mat(cfg->Go, nxo, nu) : -1, oGdo = obs ? mat(cfg->Gdo, nxo, ndm) : -1;
+  const long ofo = obs ? vec(cfg->fo, nxo) : -1, oCo = obs ? mat(cfg->Co, ny, nxo) : -1, oDdo = obs ? mat(cfg->Ddo, ny, ndm) : -1;
+  const long oho = obs ? vec(cfg->ho, ny) : -1, oKo = obs ? mat(cfg->Ko, nxo, ny) : -1;
+  const long oRt = vec(cfg->Rtraj, (size_t)nr * T), oDt = vec(cfg->Dtraj, (size_t)ndm * T);
+  if (ch.empty()) ch.push_back(0.0);
+  if (h->dyn.reserve(ch.size() * sizeof(double))) return LMPC_E_CUDA;
+  CUDA_OK(cudaMemcpyAsync(h->dyn.p, ch.data(), ch.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double *cb = (const double *)h->dyn.p;
+  auto P = [&](long o) -> const double * { return o < 0 ? nullptr : cb + o; };
+  // loop state, one slot's buffers (a closed loop is sequential in time: no chunk pipeline here)
+  Slot &s = h->slots[0];
+  const int words = (l.m + 63) / 64;
+  DevBuf xs, xn, xh, up, dm, theta, wsu, wsl, fstep, istep;
+  struct Rel { DevBuf *b[10]; ~Rel() { for (DevBuf *x : b) x->release(); } } rel{{&xs, &xn, &xh, &up, &dm, &theta, &wsu, &wsl, &fstep, &istep}};
+  if (xs.reserve((size_t)N * nx * 8) || xn.reserve((size_t)N * nx * 8) || xh.reserve((size_t)N * nxo * 8) ||
+      up.reserve((size_t)N * nu * 8) || dm.reserve((size_t)N * (ndm > 0 ? ndm : 1) * 8) || theta.reserve((size_t)N * l.nth * 8) ||
+      wsu.reserve((size_t)N * words * 8) || wsl.reserve((size_t)N * words * 8) || fstep.reserve((size_t)N * 4) ||
+      istep.reserve((size_t)N * 4) || s.u.reserve((size_t)N * nu * 8) || s.flag.reserve((size_t)N * 4) ||
+      s.iters.reserve((size_t)N * 4))
+    return LMPC_E_CUDA;
+  if (nr > 0 && R && s.in[1].reserve((size_t)N * nr * 8)) return LMPC_E_CUDA;
+  if (ndm > 0 && D && s.in[2].reserve((size_t)N * ndm * 8)) return LMPC_E_CUDA;
+  if (Utraj && s.aux[1].reserve((size_t)N * nu * T * 8)) return LMPC_E_CUDA;
+  CUDA_OK(cudaMemcpyAsync(xs.p, X0, (size_t)N * nx * 8, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(xh.p, 0, (size_t)N * nxo * 8, st));
+  CUDA_OK(cudaMemcpy2DAsync(xh.p, (size_t)nxo * 8, X0, (size_t)nx * 8, (size_t)nx * 8, (size_t)N, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(up.p, 0, (size_t)N * nu * 8, st));
+  if (U0 && nuprev > 0)
+    CUDA_OK(cudaMemcpy2DAsync(up.p, (size_t)nu * 8, U0, (size_t)nuprev * 8, (size_t)nuprev * 8, (size_t)N, cudaMemcpyHostToDevice, st));
+  if (nr > 0 && R) CUDA_OK(cudaMemcpyAsync(s.in[1].p, R, (size_t)N * nr * 8, cudaMemcpyHostToDevice, st));
+  if (ndm > 0 && D) CUDA_OK(cudaMemcpyAsync(s.in[2].p, D, (size_t)N * ndm * 8, cudaMemcpyHostToDevice, st));
+  StepDesc d;
+  memset(&d, 0, sizeof(d));
+  d.Ft = P(oFt); d.Gt = P(oGt); d.Gdt = P(oGdt); d.ft = P(oft);
+  d.Cm = P(oCm); d.Ddm = P(oDdm); d.hm = P(ohm); d.Vtraj = P(oV);
+  d.Fo = P(oFo); d.Go = P(oGo); d.Gdo = P(oGdo); d.fo = P(ofo); d.Co = P(oCo); d.Ddo = P(oDdo); d.ho = P(oho); d.Ko = P(oKo);
+  d.Rtraj = P(oRt); d.Dtraj = P(oDt);
+  d.R = (nr > 0 && R) ? (const double *)s.in[1].p : nullptr;
+  d.D = (ndm > 0 && D) ? (const double *)s.in[2].p : nullptr;
+  d.nx = nx; d.nu = nu; d.nr = nr; d.ndm = ndm; d.nxo = nxo; d.ny = ny; d.nuprev = nuprev; d.nth = l.nth; d.T = T;
+  d.has_obs = obs; d.user_plant = cfg->dynamics != nullptr;
+  d.Xs = (double *)xs.p; d.Xn = (double *)xn.p; d.Xh = (double *)xh.p; d.Uprev = (double *)up.p;
+  d.Theta = (double *)theta.p; d.U = (double *)s.u.p; d.Dm = (double *)dm.p;
+  d.Utraj = Utraj ? (double *)s.aux[1].p : nullptr;
+  d.flag_step = (int32_t *)fstep.p; d.iters_step = (int32_t *)istep.p;
+  d.flag_worst = (int32_t *)s.flag.p; d.iters_tot = (int32_t *)s.iters.p;
+  if (!step_dims_ok(d)) return set_err(LMPC_E_UNSUPPORTED, "simulate_batch_stepped: dimension beyond the step kernels' limits%s");
+  ThetaSegs th;
+  memset(&th, 0, sizeof(th));
+  th.nseg = 1; th.ptr[0] = d.Theta; th.len[0] = l.nth; th.stride[0] = l.nth;
+  for (int t = 0; t < T; ++t) {
+    int e = launch_step_pre(d, t, N, st);
+    if (e) return set_err(LMPC_E_CUDA, "step kernel: %s", cudaGetErrorString((cudaError_t)e));
+    const bool warm = warm_start && t > 0;
+    SolveOut o{d.U, d.flag_step, d.iters_step, (uint64_t *)wsu.p, (uint64_t *)wsl.p,
+               warm ? (const uint64_t *)wsu.p : nullptr, warm ? (const uint64_t *)wsl.p : nullptr};
+    int rc = run_kernel(h, th, N, o, nullptr, st);
+    if (rc) return rc;
+    e = launch_step_post(d, t, N, st);
+    if (e) return set_err(LMPC_E_CUDA, "step kernel: %s", cudaGetErrorString((cudaError_t)e));
+    if (cfg->dynamics) {
+      rc = cfg->dynamics(cfg->user, (void *)st, N, t, d.Xs, d.U, ndm > 0 ? d.Dm : nullptr, d.Xn);
+      if (rc) { cudaStreamSynchronize(st); return set_err(LMPC_E_INVALID, "simulate_batch_stepped: the plant callback failed%s"); }
+    }
+    std::swap(d.Xs, d.Xn);
+  }
+  CUDA_OK(cudaMemcpyAsync(Xend, d.Xs, (size_t)N * nx * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(Ulast, d.Uprev, (size_t)N * nu * 8, cudaMemcpyDeviceToHost, st));
+  if (Utraj) CUDA_OK(cudaMemcpyAsync(Utraj, d.Utraj, (size_t)N * nu * T * 8, cudaMemcpyDeviceToHost, st));
+  if (cfg->Xhat_end) CUDA_OK(cudaMemcpyAsync(cfg->Xhat_end, d.Xh, (size_t)N * nxo * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(exitflag, d.flag_worst, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  if (iters) CUDA_OK(cudaMemcpyAsync(iters, d.iters_tot, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // explicit MPC
 // ---------------------------------------------------------------------------------------

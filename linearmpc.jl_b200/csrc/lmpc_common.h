@@ -122,6 +122,19 @@ int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, 
 int launch_bst_sim(const BstDev &t, const double *dyn, int nx, int nr, int nd, int nup, const double *X0,
                    const double *R, const double *D, const double *U0, const double *Rtraj, const double *Dtraj,
                    int64_t N, int T, double *Xend, double *Ulast, double *Utraj, int sm_count, void *stream);
+// stepped closed loop (sim_step.cu): everything on the device, matrices row-major, batches instance-contiguous
+struct StepDesc {
+  const double *Ft, *Gt, *Gdt, *ft;                       // affine plant (unused when the caller steps the plant)
+  const double *Cm, *Ddm, *hm, *Vtraj;                    // measurement
+  const double *Fo, *Go, *Gdo, *fo, *Co, *Ddo, *ho, *Ko;  // observer
+  const double *Rtraj, *Dtraj, *R, *D;
+  int nx, nu, nr, ndm, nxo, ny, nuprev, nth, T, has_obs, user_plant;
+  double *Xs, *Xn, *Xh, *Uprev, *Theta, *U, *Dm, *Utraj;
+  int32_t *flag_step, *iters_step, *flag_worst, *iters_tot;
+};
+bool step_dims_ok(const StepDesc &d);
+int launch_step_pre(const StepDesc &d, int t, int64_t N, void *stream);
+int launch_step_post(const StepDesc &d, int t, int64_t N, void *stream);
 int launch_fp64_peak(int iters, double *d_out, int sm_count, void *stream);
 // counter += number of flags < 1 (exit flags that the reference's `@assert exitflag >= 1` would trip on)
 int launch_count_failed(const int32_t *flag, int64_t n, unsigned long long *counter, void *stream);

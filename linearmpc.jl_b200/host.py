@@ -87,6 +87,8 @@ def load_library():
                                           i32, i32, vp, vp, vp, vp, vp]
     L.lmpc_gpu_simulate_batch_ex.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
                                              i64, i32, i32, vp, vp, vp, vp, vp]
+    L.lmpc_gpu_simulate_batch_stepped.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i64, i32, i32,
+                                                  vp, vp, vp, vp, vp]
     L.lmpc_gpu_simulate_batch_traj.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
                                                i64, i32, i32, vp, vp, vp, vp, vp]
     L.lmpc_gpu_create_bst.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, C.c_int,
@@ -615,6 +617,123 @@ class GpuMPC:
         return out
 
 
+    def simulate_stepped(self, F, G, x0, r=None, d=None, u0=None, N=100, Gd=None, warm_start=True, want_traj=False,
+                         r_traj=None, d_traj=None, dynamics=None, plant=None, measurement=None, observer=None,
+                         noise=None):
+        """lmpc_gpu_simulate_batch_stepped: the Simulation loop stepped from the host (one kernel sequence per
+        step, loop state in HBM) for a user-defined true plant and / or an observer with its own state.
+
+        dynamics(k, X, U, D, Xnext, stream): the true plant (scenario.dynamics, simulation.jl:39,110); X, U, D,
+          Xnext are torch views (N x nx, N x nu, N x ndm or None, N x nx) of the library's device buffers and
+          the function must queue its work on `stream` (a torch.cuda.ExternalStream) writing Xnext in place.
+        plant = dict(F=, G=, Gd=, f_offset=): an affine true plant instead (default: the model F, G, Gd).
+        observer = dict(F=, G=, Gd=, f_offset=, C=, Dd=, h_offset=, K=): KalmanFilter (observer.jl:1-124) with
+          nxo = F.shape[0] >= nx states; the extra nxo - nx states are the OffsetFreeObserver's disturbance
+          estimates and take the LAST nxo - nx disturbance slots of theta.
+        measurement = dict(C=, Dd=, h_offset=): the true measurement map (default: the observer's C / Dd / h_offset
+          restricted to the plant state)."""
+        nx, nr, nd, nup = self.dims
+        steps = int(N)
+        X0 = _colmajor(x0, nx)
+        n = X0.shape[1]
+        nxo = nx if observer is None else np.atleast_2d(np.asarray(observer["F"], float)).shape[0]
+        ndo = nxo - nx
+        ndm = nd - ndo
+        if ndm < 0:
+            raise ValueError("the observer estimates more disturbances than the controller has")
+        cm = lambda a, rows: None if a is None else np.asfortranarray(np.asarray(a, float).reshape(rows, -1))
+        vec = lambda a, rows: None if a is None else np.ascontiguousarray(np.asarray(a, float).reshape(rows))
+        Fm, Gm = cm(F, nx), cm(G, nx)
+        Gdm = cm(np.asarray(Gd, float).reshape(nx, -1)[:, :ndm], nx) if (ndm > 0 and Gd is not None) else None
+        def bc(v, rows):
+            if rows == 0:
+                return None
+            if v is None:
+                return np.zeros((rows, n), order="F")
+            v = np.asarray(v, float)
+            if v.ndim == 1:
+                v = np.repeat(v.reshape(rows, 1), n, axis=1)
+            return np.asfortranarray(v)
+        Rm, Dm, Um = bc(r, nr), bc(d, ndm), (bc(u0, nup) if u0 is not None else None)
+        Rt, Dt = hold_trajectory(r_traj, nr, steps), hold_trajectory(d_traj, ndm, steps)
+        cfg = _SimStepped()
+        keep = [Rt, Dt]
+        cfg.Rtraj, cfg.Dtraj, cfg.ndm, cfg.nxo = _ptr(Rt), _ptr(Dt), ndm, nxo
+        if plant is not None:
+            pm = [cm(plant.get("F"), nx), cm(plant.get("G"), nx), cm(plant.get("Gd"), nx) if ndm > 0 else None,
+                  vec(plant.get("f_offset"), nx)]
+            keep += pm
+            cfg.Ft, cfg.Gt, cfg.Gdt, cfg.ft = [_ptr(a) for a in pm]
+        cb = None
+        if dynamics is not None:
+            import torch
+            def tramp(user, stream, Nn, k, X, U, D, Xn):
+                try:
+                    es = torch.cuda.ExternalStream(stream, device=self.device)
+                    with torch.cuda.stream(es):
+                        dynamics(int(k), device_view(X, nx, Nn, self.device), device_view(U, self.nu, Nn, self.device),
+                                 device_view(D, ndm, Nn, self.device) if D else None,
+                                 device_view(Xn, nx, Nn, self.device), es)
+                    return 0
+                except Exception:            # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = PLANT_FN(tramp)
+            cfg.dynamics = cb
+        Xhat = np.zeros((nxo, n), order="F")
+        cfg.Xhat_end = _ptr(Xhat)
+        if observer is not None:
+            Co = cm(observer["C"], -1) if np.ndim(observer["C"]) == 1 else np.asfortranarray(np.atleast_2d(np.asarray(observer["C"], float)))
+            ny = Co.shape[0]
+            om = dict(Fo=cm(observer["F"], nxo), Go=cm(observer["G"], nxo),
+                      Gdo=cm(observer.get("Gd"), nxo) if ndm > 0 and observer.get("Gd") is not None else None,
+                      fo=vec(observer.get("f_offset"), nxo), Co=Co,
+                      Ddo=cm(observer.get("Dd"), ny) if ndm > 0 and observer.get("Dd") is not None else None,
+                      ho=vec(observer.get("h_offset"), ny), Ko=cm(observer["K"], nxo))
+            meas = measurement or {}
+            mm = dict(Cm=cm(meas.get("C", Co[:, :nx]), ny),
+                      Ddm=cm(meas.get("Dd", observer.get("Dd")), ny) if ndm > 0 and meas.get("Dd", observer.get("Dd")) is not None else None,
+                      hm=vec(meas.get("h_offset", observer.get("h_offset")), ny),
+                      Vtraj=hold_trajectory(noise, ny, steps) if noise is not None else None)
+            keep += list(om.values()) + list(mm.values())
+            cfg.ny = ny
+            for k, v in {**om, **mm}.items():
+                setattr(cfg, k, _ptr(v))
+        Xend = np.zeros((nx, n), order="F")
+        Ulast = np.zeros((self.nu, n), order="F")
+        Utraj = np.zeros((n, steps, self.nu)) if want_traj else None
+        flag, iters = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        _check(lib().lmpc_gpu_simulate_batch_stepped(self._h, _ptr(Fm), _ptr(Gm), _ptr(Gdm), nx, nr, nup, _ptr(X0),
+                                                     _ptr(Rm), _ptr(Dm), _ptr(Um), C.byref(cfg), C.c_int64(n), steps,
+                                                     int(bool(warm_start)), _ptr(Xend), _ptr(Ulast), _ptr(Utraj),
+                                                     _ptr(flag), _ptr(iters)))
+        return dict(Xend=Xend, Ulast=Ulast, Utraj=Utraj, exitflag=flag, iters=iters, Xhat_end=Xhat)
+
+
+PLANT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                       C.c_void_p)
+
+
+class _SimStepped(C.Structure):
+    """ctypes mirror of lmpc_sim_stepped (include/lmpc_gpu.h)"""
+    _fields_ = [("dynamics", PLANT_FN), ("user", C.c_void_p)] + \
+               [(k, C.c_void_p) for k in ("Ft", "Gt", "Gdt", "ft")] + [("ny", C.c_int32)] + \
+               [(k, C.c_void_p) for k in ("Cm", "Ddm", "hm", "Vtraj")] + [("nxo", C.c_int32), ("ndm", C.c_int32)] + \
+               [(k, C.c_void_p) for k in ("Fo", "Go", "Gdo", "fo", "Co", "Ddo", "ho", "Ko", "Rtraj", "Dtraj", "Xhat_end")]
+
+
+class _DevArray:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = dict(shape=shape, typestr="<f8", data=(int(ptr), False), version=2, strides=None)
+
+
+def device_view(ptr, rows, n, device=0):
+    """(n x rows) torch view of a column-major rows x n device array owned by the library (no copy)."""
+    import torch
+    return torch.as_tensor(_DevArray(ptr, (int(n), int(rows))), device=torch.device("cuda", device))
+
+
 def setup_gpu(mpqp, nu, dims=None, K=None, soft_weight=1e6, device=0, settings=None, devices=None,
               **kw):
     """`setup_gpu!(mpc)`: build the device-resident backend from an MPQP-like object with
@@ -933,6 +1052,7 @@ class MPC:
         self.move_blocks = []
         self.gpu = None
         self.mpqp = None
+        self.observer, self.nd_measured, self._ndo = None, None, 0   # set_state_observer / set_offset_free_observer
 
     def set_prestabilizing_feedback(self, K=None):
         """set_prestabilizing_feedback!(mpc[, K]) (setup.jl:186-199): u = v - K x with the QP over v;
@@ -946,6 +1066,71 @@ class MPC:
             K = np.linalg.solve(R + self.G.T @ P @ self.G, self.G.T @ P @ self.F)
         self.K = np.asarray(K, np.float64).reshape(self.nu, self.nx)
         self.gpu = self.mpqp = None
+
+    # setup.jl:328-340 (KalmanFilter, observer.jl:50-68)
+    @staticmethod
+    def kalman_gain(F, Cm, Q=None, R=None):
+        """Steady-state gain of KalmanFilter(F, G, C; Q, R): P = ared(F', C', R, Q), K = P C' (C P C' + R)^-1."""
+        from scipy.linalg import solve_discrete_are
+        F, Cm = np.atleast_2d(np.asarray(F, float)), np.atleast_2d(np.asarray(Cm, float))
+        nx, ny = F.shape[0], Cm.shape[0]
+        Q = np.eye(nx) if Q is None else _diag(Q, nx)
+        R = np.eye(ny) if R is None else _diag(R, ny)
+        P = solve_discrete_are(F.T, Cm.T, Q, R)
+        return P @ Cm.T @ np.linalg.inv(Cm @ P @ Cm.T + R)
+
+    def set_state_observer(self, Q=None, R=None, K=None):
+        """set_state_observer!(mpc; Q, R): steady-state Kalman filter on the prediction model, run inside
+        `simulate` (correct! -> compute_control on the estimate -> predict!, simulation.jl:92-108)."""
+        Cm = np.eye(self.nx) if self.C is None else self.C
+        self.observer = dict(F=self.F, G=self.G, Gd=self.Gd, f_offset=self.f_offset, C=Cm, Dd=self.Dd,
+                             h_offset=self.h_offset, K=self.kalman_gain(self.F, Cm, Q, R) if K is None else np.asarray(K, float))
+        self.nd_measured = self.nd
+        return self.observer
+
+    def set_offset_free_observer(self, method="state_disturbance", Q=None, R=None, K=None, Bd=None, Cd=None,
+                                 Kx=None, Kd=None):
+        """set_offset_free_observer!(mpc; method, Q, R, K, Bd, Cd, Kx, Kd) (setup.jl:393-487): the controller model
+        gets ndo constant disturbance channels [Gd Bd], [Dd Cd] and the observer estimates [x; d]; in the closed loop
+        the estimated disturbances are appended to the measured ones (observer.jl:203-222).  Methods as in the
+        reference: state_disturbance / velocity (Bd = K, Cd = I - C K, Kx = K, Kd = I), output_disturbance
+        (Bd = 0, Cd = I), general (Bd, Cd given)."""
+        nx, ny = self.nx, self.ny
+        Cm = np.eye(nx) if self.C is None else self.C
+        ndm = getattr(self, "nd_measured", None)
+        ndm = self.nd if ndm is None or getattr(self, "_ndo", 0) == 0 else ndm
+        Gd = np.zeros((nx, 0)) if self.Gd is None else self.Gd[:, :ndm]          # strip_offset_free_model
+        Dd = np.zeros((ny, 0)) if self.Dd is None else self.Dd[:, :ndm]
+        if method in ("state_disturbance", "velocity"):
+            K = self.kalman_gain(self.F, Cm, Q, R) if K is None else np.asarray(K, float).reshape(nx, ny)
+            Bd, Cd, Kx, Kd = K, np.eye(ny) - Cm @ K, K, np.eye(ny)
+        elif method == "output_disturbance":
+            Bd, Cd = np.zeros((nx, ny)), np.eye(ny)
+        elif method == "general":
+            if Bd is None or Cd is None:
+                raise ValueError("method 'general' requires Bd and Cd")
+            Bd, Cd = np.asarray(Bd, float).reshape(nx, -1), np.asarray(Cd, float).reshape(ny, -1)
+        else:
+            raise ValueError(f"unknown offset-free method {method}")
+        ndo = Bd.shape[1]
+        if np.linalg.matrix_rank(np.block([[self.F - np.eye(nx), Bd], [Cm, Cd]])) != nx + ndo:
+            raise ValueError("Offset-free disturbance model violates rank([F-I Bd; C Cd]) = nx + nd")
+        Fa = np.block([[self.F, Bd], [np.zeros((ndo, nx)), np.eye(ndo)]])
+        Ga = np.vstack([self.G, np.zeros((ndo, self.nu))])
+        Gda = np.vstack([Gd, np.zeros((ndo, ndm))])
+        Ca = np.hstack([Cm, Cd])
+        fa = None if self.f_offset is None else np.concatenate([self.f_offset, np.zeros(ndo)])
+        if Kx is not None or Kd is not None:
+            Ka = np.vstack([np.zeros((nx, ny)) if Kx is None else np.asarray(Kx, float).reshape(nx, ny),
+                            np.zeros((ndo, ny)) if Kd is None else np.asarray(Kd, float).reshape(ndo, ny)])
+        else:
+            Ka = self.kalman_gain(Fa, Ca, Q, R)
+        self.observer = dict(F=Fa, G=Ga, Gd=Gda if ndm else None, f_offset=fa, C=Ca, Dd=Dd if ndm else None,
+                             h_offset=self.h_offset, K=Ka)
+        self.Gd, self.Dd = np.hstack([Gd, Bd]), np.hstack([Dd, Cd])                # append_offset_free_model
+        self.nd, self.nd_measured, self._ndo = ndm + ndo, ndm, ndo
+        self.gpu = self.mpqp = None
+        return self.observer
 
     # setup.jl:196-251
     def move_block(self, block):
@@ -1178,7 +1363,18 @@ class MPC:
         return empc, sol
 
     def simulate(self, x0, r=None, d=None, N=100, warm_start=True, want_traj=False, r_traj=None, d_traj=None,
-                 plant=None, observer=None, noise=None):
+                 plant=None, observer=None, noise=None, dynamics=None, measurement=None):
+        """Simulation(mpc; x0, N, r, d) (simulation.jl:37-126).  With `dynamics` (a user-defined true plant, see
+        GpuMPC.simulate_stepped) or an observer set by set_state_observer / set_offset_free_observer the loop is
+        stepped from the host; otherwise it runs fused on chip."""
+        obs = observer if observer is not None else self.observer
+        affine_plant = plant is not None and plant.get("f_offset") is not None
+        if dynamics is not None or affine_plant or (obs is not None and "F" in obs):
+            if self.reference_preview or self.disturbance_preview:
+                raise ValueError("the stepped closed loop does not slide preview windows")
+            return self._g().simulate_stepped(self.F, self.G, x0, r=r, d=d, N=N, Gd=self.Gd, warm_start=warm_start,
+                                              want_traj=want_traj, r_traj=r_traj, d_traj=d_traj, dynamics=dynamics,
+                                              plant=plant, measurement=measurement, observer=obs, noise=noise)
         rp = self.Np if (self.reference_preview and self.reference_tracking and r_traj is not None) else 0
         dp = self.Np if (self.disturbance_preview and self.nd > 0 and d_traj is not None) else 0
         if self.reference_preview and self.reference_tracking and not rp:

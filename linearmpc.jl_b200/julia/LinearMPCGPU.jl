@@ -235,6 +235,19 @@ struct LmpcSimExt
     rstride::Int32; dstride::Int32     # preview windows: step t reads its nr / nd entries at t * stride (0 = nr / nd)
 end
 
+# mirrors lmpc_sim_stepped (include/lmpc_gpu.h)
+struct LmpcSimStepped
+    dynamics::Ptr{Cvoid}; user::Ptr{Cvoid}
+    Ft::Ptr{Float64}; Gt::Ptr{Float64}; Gdt::Ptr{Float64}; ft::Ptr{Float64}
+    ny::Int32
+    Cm::Ptr{Float64}; Ddm::Ptr{Float64}; hm::Ptr{Float64}; Vtraj::Ptr{Float64}
+    nxo::Int32; ndm::Int32
+    Fo::Ptr{Float64}; Go::Ptr{Float64}; Gdo::Ptr{Float64}; fo::Ptr{Float64}
+    Co::Ptr{Float64}; Ddo::Ptr{Float64}; ho::Ptr{Float64}; Ko::Ptr{Float64}
+    Rtraj::Ptr{Float64}; Dtraj::Ptr{Float64}
+    Xhat_end::Ptr{Float64}
+end
+
 # Layout self-check (lmpc_gpu_abi_layout, include/lmpc_gpu.h): the two structs above are hand-written
 # mirrors, so compare sizeof / fieldoffset with what the loaded library was compiled with and refuse
 # to run on a mismatch instead of letting C read past a Julia object.
@@ -242,7 +255,7 @@ function check_abi()
     n = ccall((:lmpc_gpu_abi_layout, liblmpcgpu), Cint, (Ptr{Int32}, Int32), C_NULL, 0)
     v = Vector{Int32}(undef, n)
     ccall((:lmpc_gpu_abi_layout, liblmpcgpu), Cint, (Ptr{Int32}, Int32), v, n)
-    mirrors = Dict(1 => LmpcProblem, 2 => LmpcSettings, 3 => LmpcSimExt)
+    mirrors = Dict(1 => LmpcProblem, 2 => LmpcSettings, 3 => LmpcSimExt, 6 => LmpcSimStepped)
     i = 1
     while i <= n
         id, sz, nf = v[i], v[i+1], v[i+2]
@@ -301,6 +314,58 @@ function simulate_observed(g::GpuMPC, X0::Matrix{Float64}; N::Integer=100, r=not
                      Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
                     g.handle, mdl.F, mdl.G, nd == 0 ? C_NULL : mdl.Gd, nx, nr, nd, nup,
                     X0, C_NULL, C_NULL, C_NULL, ext, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
+    end
+    return Xend, Xhat, Ulast, flag
+end
+
+"""
+    simulate_stepped(g, X0; N, r, d, dynamics=nothing, plant=nothing, noise=nothing, warm_start=true)
+        -> (Xend, Xhat, Ulast, exitflag)
+
+The Simulation loop (src/simulation.jl:93-113) stepped from the host for what the fused loops cannot express:
+a user-defined true plant and the controller's own `state_observer` with its full state, i.e. a `KalmanFilter`
+or the augmented estimator of an `OffsetFreeObserver` (src/observer.jl:12-47, 203-222; the estimated disturbances
+are appended to the measured ones in θ).  `dynamics` is a C-callable
+`(user, stream, N, k, X, U, D, Xnext) -> Cint` (e.g. `@cfunction` around a CUDA.jl kernel launch on `stream`)
+that steps all N plants on the device; without it the affine plant `plant = (Ft, Gt, Gdt, ft)` or the model runs.
+"""
+function simulate_stepped(g::GpuMPC, X0::Matrix{Float64}; N::Integer=100, r=nothing, d=nothing,
+                          dynamics::Ptr{Cvoid}=C_NULL, user::Ptr{Cvoid}=C_NULL, plant=nothing, noise=nothing,
+                          warm_start::Bool=true)
+    mdl = g.mpc.model; obs = g.mpc.state_observer
+    nx, nr, nd, nup, _ = LinearMPC.get_parameter_dims(g.mpc)
+    kf = obs isa LinearMPC.OffsetFreeObserver ? obs.estimator : obs
+    nxo = isnothing(kf) ? nx : size(kf.F, 1)
+    ndm = nd - (nxo - nx)
+    M = size(X0, 2)
+    hold(v, k) = (k == 0 || isnothing(v)) ? nothing :
+        (V = v isa AbstractMatrix ? Matrix{Float64}(v) : reshape(Vector{Float64}(v), k, 1);
+         hcat(V[:, 1:min(N, size(V, 2))], repeat(V[:, end], 1, max(0, N - size(V, 2)))))
+    Rt, Dt = hold(r, nr), hold(d, ndm)
+    ny = isnothing(kf) ? 0 : size(kf.C, 1)
+    Vt = hold(noise, ny)
+    mats = isnothing(plant) ? (nothing, nothing, nothing, nothing) : plant
+    Ft, Gt, Gdt, ft = (isnothing(m) ? nothing : Array{Float64}(m) for m in mats)
+    p(x) = (isnothing(x) || isempty(x)) ? Ptr{Float64}(C_NULL) : pointer(x)
+    Fo, Go, Gdo, fo, Co, Ddo, ho, Ko = isnothing(kf) ? ntuple(_ -> nothing, 8) :
+        (Matrix{Float64}(kf.F), Matrix{Float64}(kf.G), Matrix{Float64}(kf.Gd), Vector{Float64}(kf.f_offset),
+         Matrix{Float64}(kf.C), Matrix{Float64}(kf.Dd), Vector{Float64}(kf.h_offset), Matrix{Float64}(kf.K))
+    Cm = isnothing(kf) ? nothing : Matrix{Float64}(mdl.C)
+    Ddm = (isnothing(kf) || ndm == 0) ? nothing : Matrix{Float64}(mdl.Dd[:, 1:ndm])
+    hm = isnothing(kf) ? nothing : Vector{Float64}(mdl.h_offset)
+    Gdm = ndm == 0 ? nothing : Matrix{Float64}(mdl.Gd[:, 1:ndm])
+    Xend = similar(X0); Xhat = Matrix{Float64}(undef, nxo, M)
+    Ulast = Matrix{Float64}(undef, g.nu, M); flag = Vector{Int32}(undef, M)
+    GC.@preserve Rt Dt Vt Ft Gt Gdt ft Fo Go Gdo fo Co Ddo ho Ko Cm Ddm hm Gdm Xhat begin
+        cfg = Ref(LmpcSimStepped(dynamics, user, p(Ft), p(Gt), p(Gdt), p(ft), ny, p(Cm), p(Ddm), p(hm), p(Vt),
+                                 nxo, ndm, p(Fo), p(Go), p(Gdo), p(fo), p(Co), p(Ddo), p(ho), p(Ko),
+                                 p(Rt), p(Dt), pointer(Xhat)))
+        check(ccall((:lmpc_gpu_simulate_batch_stepped, liblmpcgpu), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{LmpcSimStepped},
+                     Int64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                    g.handle, mdl.F, mdl.G, p(Gdm), nx, nr, nup,
+                    X0, C_NULL, C_NULL, C_NULL, cfg, M, N, warm_start, Xend, Ulast, C_NULL, flag, C_NULL))
     end
     return Xend, Xhat, Ulast, flag
 end

@@ -182,6 +182,56 @@ class OracleProblem:
         return out
 
 
+DYN_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp)
+
+
+class _SimStepped(C.Structure):
+    _fields_ = [("dyn", DYN_FN), ("user", C.c_void_p)] + \
+               [(k, C.c_void_p) for k in ("Ft", "Gt", "Gdt", "ft")] + [("ny", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("Cm", "Ddm", "hm", "Vtraj")] + [("nxo", C.c_int), ("ndm", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("Fo", "Go", "Gdo", "fo", "Co", "Ddo", "ho", "Ko", "Rtraj", "Dtraj", "Xhat_end")]
+
+
+def simulate_batch_stepped(P, nx, nr, nuprev, X0, R, D, U0, T, cfg, warm=True, nthreads=0, want_traj=False):
+    """orc_simulate_batch_stepped: cfg is a dict of row-major matrices / vectors (ldp_oracle.h: orc_sim_stepped),
+    'dyn' a Python function (k, x, u, d) -> xnext for a nonlinear plant; X0 nx x N, R nr x N, D ndm x N."""
+    c = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, float).T)
+    X0c, Rc, Dc, U0c = c(X0), c(R), c(D), c(U0)
+    N = X0c.shape[0]
+    nu = P.nu
+    keep = {}
+    def vp(k, transpose=False):
+        a = cfg.get(k)
+        if a is None:
+            return None
+        a = np.ascontiguousarray(np.asarray(a, float).T if transpose else np.asarray(a, float))
+        keep[k] = a
+        return a.ctypes.data
+    ndm = int(cfg.get("ndm", 0))
+    nxo = int(cfg.get("nxo", nx))
+    ny = int(cfg.get("ny", 0))
+    Xhat = np.zeros((N, nxo))
+    dyn = cfg.get("dyn")
+    if dyn is not None:
+        def tramp(user, k, x, u, d, xn):
+            xv = np.ctypeslib.as_array(x, (nx,)); uv = np.ctypeslib.as_array(u, (nu,))
+            dv = np.ctypeslib.as_array(d, (max(ndm, 1),))[:ndm]
+            np.ctypeslib.as_array(xn, (nx,))[:] = dyn(k, xv, uv, dv)
+        cb = DYN_FN(tramp)
+    else:
+        cb = DYN_FN(0)
+    st = _SimStepped(cb, None, vp("Ft"), vp("Gt"), vp("Gdt"), vp("ft"), ny, vp("Cm"), vp("Ddm"), vp("hm"),
+                     vp("Vtraj", True), nxo, ndm, vp("Fo"), vp("Go"), vp("Gdo"), vp("fo"), vp("Co"), vp("Ddo"),
+                     vp("ho"), vp("Ko"), vp("Rtraj", True), vp("Dtraj", True), Xhat.ctypes.data)
+    Xend, Ulast = np.zeros((N, nx)), np.zeros((N, nu))
+    Utraj = np.zeros((N, T, nu)) if want_traj else None
+    flag, iters = np.zeros(N, np.int32), np.zeros(N, np.int32)
+    lib().orc_simulate_batch_stepped(C.byref(P.c), nx, nr, nuprev, _dp(X0c), _dp(Rc), _dp(Dc), _dp(U0c),
+                                     C.byref(st), C.c_int64(N), T, int(warm), _dp(Xend), _dp(Ulast), _dp(Utraj),
+                                     _ip(flag), _ip(iters), C.c_int(nthreads))
+    return dict(Xend=Xend.T, Ulast=Ulast.T, Utraj=Utraj, flag=flag, iters=iters, Xhat_end=Xhat.T)
+
+
 class _SimExt(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("Ft", "Gt", "Gdt", "C", "Dd", "K", "Vtraj")] + [("ny", C.c_int),
                                                                                       ("Xhat_end", C.c_void_p),

@@ -561,6 +561,98 @@ static void sim_chunk(void *vc, int64_t lo, int64_t hi) {
   free(th); free(x); free(xn); free(u); free(xs); free(inn);
   work_free(w);
 }
+typedef struct {
+  const orc_problem *p; int nx, nr, nuprev; const double *X0, *R, *D, *U0; const orc_sim_stepped *c;
+  int T, warm; double *Xend, *Ulast, *Utraj; int32_t *flag, *iters;
+} step_ctx;
+/* acc = A[i, :] v (row-major, fma chain in index order) added onto acc */
+static double row_fma(const double *A, int i, int n, const double *v, double acc) {
+  if (A) for (int c = 0; c < n; ++c) acc = fma(A[i * n + c], v[c], acc);
+  return acc;
+}
+static void step_chunk(void *vc, int64_t lo, int64_t hi) {
+  step_ctx *s = (step_ctx *)vc;
+  const orc_problem *p = s->p;
+  const orc_sim_stepped *c = s->c;
+  const int nu = p->nu, nth = p->nth, nx = s->nx, nr = s->nr, nuprev = s->nuprev;
+  const int nxo = c->Ko ? c->nxo : nx, ndm = c->ndm, ndo = nxo - nx, ny = c->ny;
+  work_t *w = work_new(p);
+  double *th = (double *)calloc(nth, sizeof(double));
+  double *xs = (double *)calloc(nx, sizeof(double)), *xn = (double *)calloc(nxo > nx ? nxo : nx, sizeof(double));
+  double *xh = (double *)calloc(nxo, sizeof(double));
+  double *u = (double *)calloc(nu, sizeof(double)), *dm = (double *)calloc(ndm > 0 ? ndm : 1, sizeof(double));
+  double *inn = (double *)calloc(ny > 0 ? ny : 1, sizeof(double));
+  const int words = (p->m + 63) / 64;
+  uint64_t *au = (uint64_t *)calloc(words, sizeof(uint64_t)), *al = (uint64_t *)calloc(words, sizeof(uint64_t));
+  for (int64_t q = lo; q < hi; ++q) {
+    int worst = ORC_OPTIMAL, tot = 0;
+    for (int i = 0; i < nx; ++i) xs[i] = s->X0[q * nx + i];
+    for (int i = 0; i < nxo; ++i) xh[i] = i < nx ? xs[i] : 0.0;     /* set_state!(observer, x0): d-hat = 0 */
+    for (int i = 0; i < nu; ++i) u[i] = (s->U0 && i < nuprev) ? s->U0[q * nuprev + i] : 0.0;
+    for (int t = 0; t < s->T; ++t) {
+      for (int i = 0; i < ndm; ++i) dm[i] = c->Dtraj ? c->Dtraj[(size_t)t * ndm + i] : (s->D ? s->D[q * ndm + i] : 0.0);
+      if (c->Ko) {
+        for (int i = 0; i < ny; ++i) {
+          double y = c->Vtraj ? c->Vtraj[(size_t)t * ny + i] : 0.0;
+          y = row_fma(c->Cm, i, nx, xs, y); y = row_fma(c->Ddm, i, ndm, dm, y);
+          if (c->hm) y += c->hm[i];
+          double yh = row_fma(c->Co, i, nxo, xh, 0.0); yh = row_fma(c->Ddo, i, ndm, dm, yh);
+          if (c->ho) yh += c->ho[i];
+          inn[i] = y - yh;
+        }
+        for (int j = 0; j < nxo; ++j) xn[j] = row_fma(c->Ko, j, ny, inn, xh[j]);
+        for (int j = 0; j < nxo; ++j) xh[j] = xn[j];
+      } else {
+        for (int j = 0; j < nx; ++j) xh[j] = xs[j];
+      }
+      int o = 0;
+      for (int i = 0; i < nx; ++i) th[o++] = xh[i];
+      for (int i = 0; i < nr; ++i) th[o++] = c->Rtraj ? c->Rtraj[(size_t)t * nr + i] : (s->R ? s->R[q * nr + i] : 0.0);
+      for (int i = 0; i < ndm; ++i) th[o++] = dm[i];
+      for (int i = 0; i < ndo; ++i) th[o++] = xh[nx + i];
+      for (int i = 0; i < nuprev; ++i) th[o++] = u[i];
+      int32_t it = 0;
+      /* warm: the working set travels between the steps as bit masks and the factorisation is rebuilt from
+       * them (the batch warm start, orc_solve_batch_warm), which is what a loop stepped from the host does */
+      int f = solve_with(p, w, th, u, &it, au, al, NULL, (s->warm && t > 0) ? 2 : 1);
+      tot += it;
+      if (f < 0) { if (worst > 0 || f < worst) worst = f; }
+      else if (worst > 0 && f > worst) worst = f;
+      if (s->Utraj) for (int i = 0; i < nu; ++i) s->Utraj[(q * s->T + t) * nu + i] = u[i];
+      if (c->Ko) {   /* predict!(observer, u, d_measured) */
+        for (int i = 0; i < nxo; ++i) {
+          double acc = row_fma(c->Fo, i, nxo, xh, 0.0);
+          acc = row_fma(c->Go, i, nu, u, acc); acc = row_fma(c->Gdo, i, ndm, dm, acc);
+          xn[i] = c->fo ? acc + c->fo[i] : acc;
+        }
+        for (int i = 0; i < nxo; ++i) xh[i] = xn[i];
+      }
+      if (c->dyn) c->dyn(c->user, t, xs, u, dm, xn);
+      else
+        for (int i = 0; i < nx; ++i) {
+          double acc = row_fma(c->Ft, i, nx, xs, 0.0);
+          acc = row_fma(c->Gt, i, nu, u, acc); acc = row_fma(c->Gdt, i, ndm, dm, acc);
+          xn[i] = c->ft ? acc + c->ft[i] : acc;
+        }
+      for (int i = 0; i < nx; ++i) xs[i] = xn[i];
+    }
+    for (int i = 0; i < nx; ++i) s->Xend[q * nx + i] = xs[i];
+    if (c->Xhat_end) for (int i = 0; i < nxo; ++i) c->Xhat_end[q * nxo + i] = xh[i];
+    for (int i = 0; i < nu; ++i) s->Ulast[q * nu + i] = u[i];
+    if (s->flag) s->flag[q] = worst;
+    if (s->iters) s->iters[q] = tot;
+  }
+  free(th); free(xs); free(xn); free(xh); free(u); free(dm); free(inn); free(au); free(al);
+  work_free(w);
+}
+void orc_simulate_batch_stepped(const orc_problem *p, int nx, int nr, int nuprev,
+                                const double *X0, const double *R, const double *D, const double *U0,
+                                const orc_sim_stepped *c, int64_t N, int T, int warm,
+                                double *Xend, double *Ulast, double *Utraj, int32_t *flag, int32_t *iters,
+                                int nthreads) {
+  step_ctx s = {p, nx, nr, nuprev, X0, R, D, U0, c, T, warm, Xend, Ulast, Utraj, flag, iters};
+  parallel_for(N, c->dyn ? 1 : nthreads, step_chunk, &s);   /* a Python callback is not thread-safe */
+}
 void orc_simulate_batch(const orc_problem *p, int nx, int nr, int nd, int nuprev,
                         const double *Fx, const double *Gx, const double *Gdx,
                         const double *X0, const double *R, const double *D, const double *U0,

@@ -100,6 +100,30 @@ void orc_simulate_batch_traj(const orc_problem *p, int nx, int nr, int nd, int n
                              int64_t N, int T, int warm, double *Xend, double *Ulast, double *Utraj,
                              int32_t *flag, int32_t *iters, int nthreads);
 
+/* General closed loop (simulation.jl:37-116 with scenario.dynamics, observer.jl:1-148,203-222):
+ *  - true plant: `dyn` (any function, e.g. a nonlinear model) or the affine x+ = Ft x + Gt u + Gdt d + ft;
+ *  - measurement y = Cm x + Ddm d + hm + v_t;
+ *  - observer state of dimension nxo >= nx (KalmanFilter on the model, or the OffsetFreeObserver's augmented
+ *    estimator: the last nxo - nx entries are estimated disturbances, appended to the ndm measured ones in theta);
+ *    correct! with (Co, Ddo, ho, Ko), compute_control on the estimate, predict! with (Fo, Go, Gdo, fo).
+ *    Ko == NULL: no observer, the controller sees the true state (nxo == nx).
+ * theta = [xhat[0:nx]; r; d_measured; xhat[nx:nxo]; uprev].  All matrices row-major. */
+typedef void (*orc_dyn_fn)(void *user, int k, const double *x, const double *u, const double *d, double *xnext);
+typedef struct {
+  orc_dyn_fn dyn; void *user;
+  const double *Ft, *Gt, *Gdt, *ft;
+  int ny; const double *Cm, *Ddm, *hm, *Vtraj;
+  int nxo, ndm;
+  const double *Fo, *Go, *Gdo, *fo, *Co, *Ddo, *ho, *Ko;
+  const double *Rtraj, *Dtraj;   /* nr x T, ndm x T shared, or NULL */
+  double *Xhat_end;              /* nxo x N, nullable */
+} orc_sim_stepped;
+void orc_simulate_batch_stepped(const orc_problem *p, int nx, int nr, int nuprev,
+                                const double *X0, const double *R, const double *D, const double *U0,
+                                const orc_sim_stepped *c, int64_t N, int T, int warm,
+                                double *Xend, double *Ulast, double *Utraj, int32_t *flag, int32_t *iters,
+                                int nthreads);
+
 /* explicit MPC: binary search tree walk + affine law.
  * halfplanes: n_hp x (nth+1) row-major [a; b]; feedbacks: n_fb x nu x (nth+1)
  * row-major [F | g]; node i: next = i + jump[i]; leaf iff jump[i]==0, region

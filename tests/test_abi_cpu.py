@@ -158,15 +158,15 @@ def test_struct_layouts_match_the_julia_and_ctypes_mirrors(lmpc):
     (field count, offsets, size) == the ctypes mirrors of host.py.  Round 1 shipped a Julia LmpcSimExt
     without the trailing rstride / dstride: C then read 8 bytes past the Julia object."""
     lay = _abi_layout(lmpc)
-    assert sorted(lay) == [1, 2, 3, 4, 5]
-    for sid, jl in [(1, "LmpcProblem"), (2, "LmpcSettings"), (3, "LmpcSimExt")]:
+    assert sorted(lay) == [1, 2, 3, 4, 5, 6]
+    for sid, jl in [(1, "LmpcProblem"), (2, "LmpcSettings"), (3, "LmpcSimExt"), (6, "LmpcSimStepped")]:
         names, offs, size = _julia_struct_layout(jl)
         assert (size, offs) == (lay[sid][0], lay[sid][1]), (jl, names, offs, size, lay[sid])
     import sys
     host = sys.modules[lmpc.__name__ + ".host"]
     _Problem, _Settings, _SimExt, _Constraint, _Model = (host._Problem, host._Settings, host._SimExt,
                                                           host._Constraint, host._Model)
-    for sid, T in [(1, _Problem), (2, _Settings), (3, _SimExt), (4, _Constraint), (5, _Model)]:
+    for sid, T in [(1, _Problem), (2, _Settings), (3, _SimExt), (4, _Constraint), (5, _Model), (6, host._SimStepped)]:
         offs = [getattr(T, f[0]).offset for f in T._fields_]
         assert (C.sizeof(T), offs) == (lay[sid][0], lay[sid][1]), T.__name__
 
@@ -176,14 +176,15 @@ def test_julia_struct_field_names_follow_the_header():
     when the sizes happen to agree)."""
     hdr = open(os.path.join(ROOT, "include", "lmpc_gpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    for cname, jl in [("lmpc_problem", "LmpcProblem"), ("lmpc_settings", "LmpcSettings"), ("lmpc_sim_ext", "LmpcSimExt")]:
+    for cname, jl in [("lmpc_problem", "LmpcProblem"), ("lmpc_settings", "LmpcSettings"), ("lmpc_sim_ext", "LmpcSimExt"),
+                      ("lmpc_sim_stepped", "LmpcSimStepped")]:
         body = re.search(r"typedef struct \{([^{}]*)\}\s*" + cname + r"\s*;", hdr).group(1)
         cfields = []
         for decl in body.split(";"):
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(double|int32_t|int64_t|uint64_t)\s*", "", decl)
+            decl = re.sub(r"^(const\s+)?(double|int32_t|int64_t|uint64_t|void|lmpc_plant_fn)\s*", "", decl)
             cfields += [x.strip().lstrip("*").strip() for x in decl.split(",")]
         assert _julia_struct_layout(jl)[0] == cfields, (cname, cfields)
 
