@@ -390,8 +390,8 @@ int lmpc_gpu_evaluate_batch_multi(lmpc_bst_multi *t, const double *Theta, int64_
  * Host-side condensing: build the dense mpQP from a discrete-time model without
  * Julia.  Replaces mpc2mpqp(mpc) (src/mpc2mpqp.jl:612-647) for the feature subset the batched
  * path supports: move blocking, previews of r and d, a prestabilising feedback, generalized (affine)
- * parameters with or without a parameter preview, model offsets and operating points; no binaries or
- * reference condensation.
+ * parameters with or without a parameter preview, model offsets and operating points, reference condensation;
+ * no binaries.
  * Pure host code; needs no GPU.
  * --------------------------------------------------------------------------------------------- */
 typedef struct {            /* lb <= Ax x_k + Au u_k + Ar r + Ad d + Aup u^- <= ub for k in ks (src/types.jl:4-18) */
@@ -455,6 +455,12 @@ typedef struct {            /* x+ = F x + G u + Gd d, y = C x + Dd d (src/model.
    * regulator (reference_tracking = 0, mpc2mpqp.jl:433-443, 457-459).  Any NULL = 0.  f_offset cannot be combined
    * with generalized parameters (LMPC_E_UNSUPPORTED). */
   const double *f_offset, *h_offset, *xo, *uo;
+  /* settings.reference_condensation (src/types.jl:54,65) together with reference_preview: the previewed reference
+   * trajectory is collapsed to ONE setpoint, theta carries ny reference values again, and the library computes the
+   * ny x (ny Np) map traj2setpoint = (W H^-1 Fr Is) \ (W H^-1 Fr) (src/mpc2mpqp.jl:550-568; W = I with 1e6 on the first
+   * move) that the caller applies to a flattened trajectory before compute_control (condense_reference,
+   * src/utils.jl:140-147; read it with lmpc_gpu_mpqp_traj2setpoint) */
+  int32_t reference_condensation;
 } lmpc_model;
 
 typedef struct lmpc_mpqp lmpc_mpqp;   /* the dense mpQP (src/types.jl:75-98) owned by the library */
@@ -463,6 +469,8 @@ int lmpc_gpu_condense(const lmpc_model *model, lmpc_mpqp **out);
 /* dims9 = {n, m, ms, nth, nu, nx, nr, nd, nuprev}: theta = [x(nx); r(nr); d(nd); uprev(nuprev); p(nth - the rest)] */
 int lmpc_gpu_mpqp_dims(const lmpc_mpqp *q, int32_t *dims9);
 /* copy out, column-major: H n x n, f n, f_theta n x nth, A (m-ms) x n, bu m, bl m, W m x nth, senses m */
+/* traj2setpoint (column-major rows x cols = ny x ny*Np; 0 x 0 without reference_condensation); T may be NULL */
+int lmpc_gpu_mpqp_traj2setpoint(const lmpc_mpqp *q, double *T, int32_t *rows, int32_t *cols);
 int lmpc_gpu_mpqp_get(const lmpc_mpqp *q, double *H, double *f, double *f_theta, double *A,
                       double *bu, double *bl, double *W, int32_t *senses);
 int lmpc_gpu_mpqp_free(lmpc_mpqp *q);

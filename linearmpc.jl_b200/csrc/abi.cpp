@@ -45,7 +45,8 @@ extern "C" int lmpc_gpu_abi_layout(int32_t *out, int32_t cap) {
         F(lmpc_model, n_move_blocks), F(lmpc_model, reference_preview), F(lmpc_model, disturbance_preview),
         F(lmpc_model, K), F(lmpc_model, np), F(lmpc_model, Ex), F(lmpc_model, ex), F(lmpc_model, Eu),
         F(lmpc_model, eu), F(lmpc_model, parameter_preview),
-        F(lmpc_model, f_offset), F(lmpc_model, h_offset), F(lmpc_model, xo), F(lmpc_model, uo)});
+        F(lmpc_model, f_offset), F(lmpc_model, h_offset), F(lmpc_model, xo), F(lmpc_model, uo),
+        F(lmpc_model, reference_condensation)});
   emit(o, LMPC_ABI_SIM_STEPPED, sizeof(lmpc_sim_stepped),
        {F(lmpc_sim_stepped, dynamics), F(lmpc_sim_stepped, user), F(lmpc_sim_stepped, Ft), F(lmpc_sim_stepped, Gt),
         F(lmpc_sim_stepped, Gdt), F(lmpc_sim_stepped, ft), F(lmpc_sim_stepped, ny), F(lmpc_sim_stepped, Cm),

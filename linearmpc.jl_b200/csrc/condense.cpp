@@ -74,11 +74,75 @@ Mat sub(const Mat &A, const std::vector<int> &ri, const std::vector<int> &ci) {
   return S;
 }
 
+// X with A X = B (LU, partial pivoting); false when A is singular to working precision
+bool solve_lu(Mat A, Mat B, Mat &X) {
+  const int n = A.r;
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < n; ++i) if (std::fabs(A(i, k)) > std::fabs(A(piv, k))) piv = i;
+    if (A(piv, k) == 0.0) return false;
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) std::swap(A(k, j), A(piv, j));
+      for (int j = 0; j < B.c; ++j) std::swap(B(k, j), B(piv, j));
+    }
+    for (int i = k + 1; i < n; ++i) {
+      const double l = A(i, k) / A(k, k);
+      if (l == 0.0) continue;
+      for (int j = k; j < n; ++j) A(i, j) -= l * A(k, j);
+      for (int j = 0; j < B.c; ++j) B(i, j) -= l * B(k, j);
+    }
+  }
+  X = Mat(n, B.c);
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = 0; j < B.c; ++j) {
+      double v = B(i, j);
+      for (int k = i + 1; k < n; ++k) v -= A(i, k) * X(k, j);
+      X(i, j) = v / A(i, i);
+    }
+  return true;
+}
+// least squares X = argmin |A X - B| for a tall full-column-rank A (Householder QR), what Julia's A \ B does
+bool lstsq_qr(Mat A, Mat B, Mat &X) {
+  const int m = A.r, n = A.c;
+  if (m < n) return false;
+  for (int k = 0; k < n; ++k) {
+    double nrm = 0.0;
+    for (int i = k; i < m; ++i) nrm += A(i, k) * A(i, k);
+    nrm = std::sqrt(nrm);
+    if (nrm == 0.0) return false;
+    const double alpha = A(k, k) > 0 ? -nrm : nrm;
+    std::vector<double> v(m - k);
+    for (int i = k; i < m; ++i) v[i - k] = A(i, k);
+    v[0] -= alpha;
+    double vn = 0.0;
+    for (double t : v) vn += t * t;
+    if (vn == 0.0) continue;
+    auto reflect = [&](Mat &M) {
+      for (int j = 0; j < M.c; ++j) {
+        double d = 0.0;
+        for (int i = k; i < m; ++i) d += v[i - k] * M(i, j);
+        d = 2.0 * d / vn;
+        for (int i = k; i < m; ++i) M(i, j) -= d * v[i - k];
+      }
+    };
+    reflect(A); reflect(B);
+  }
+  X = Mat(n, B.c);
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = 0; j < B.c; ++j) {
+      double v = B(i, j);
+      for (int k = i + 1; k < n; ++k) v -= A(i, k) * X(k, j);
+      X(i, j) = v / A(i, i);
+    }
+  return true;
+}
+
 }  // namespace
 
 struct lmpc_mpqp {
   int n = 0, m = 0, ms = 0, nth = 0, nx = 0, nr = 0, nd = 0, nuprev = 0, nu = 0;
   Mat H, f_theta, A, W;
+  Mat traj2setpoint;   // ny x ny*Np with reference_condensation, else empty
   std::vector<double> f, bu, bl;
   std::vector<int32_t> senses;
 };
@@ -114,7 +178,10 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   const bool dp = md->disturbance_preview && ndm > 0;
   const int nr = (md->reference_tracking && !rp) ? ny : 0;     // reference part of the extended state
   const int nd = dp ? 0 : ndm;                                 // disturbance part of the extended state
-  const int nrp = rp ? ny * Np : nr, ndp = dp ? ndm * Np : nd; // widths of the r / d blocks of theta
+  // reference_condensation (types.jl:54,65): the previewed trajectory is collapsed to one setpoint, theta carries
+  // ny values again and traj2setpoint maps a trajectory to them (mpc2mpqp.jl:550-568, utils.jl:140-147)
+  const bool rcond = rp && md->reference_condensation;
+  const int nrp = rp ? (rcond ? ny : ny * Np) : nr, ndp = dp ? ndm * Np : nd; // widths of the r / d blocks of theta
   bool aup = false;
   for (int ci = 0; ci < md->n_constraints; ++ci) {
     const lmpc_constraint &c = md->constraints[ci];
@@ -250,6 +317,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   }
   // Gamma' CQCtot Gamma and Gamma' CQCtot Phi, block row by block row (CQCtot is block diagonal)
   Mat fth(n, nth);
+  Mat Frp(n, rp ? ny * Np : 0);     // Fr of ref_preview_cost: column block k-1 pairs y_k with preview column k-1
   for (int k = 0; k <= Np; ++k) {
     const Mat &W = (k == Np) ? CQCf : CQC;
     Mat Gk(nxe, n), Pk(nxe, nxe);
@@ -268,7 +336,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
       Mat Cfull(ny, nxe);
       for (int i = 0; i < ny; ++i) for (int j = 0; j < nxe; ++j) Cfull(i, j) = C(i, j);
       const Mat GCQ = mul(tr(Gk), mul(tr(Cfull), (k == Np) ? Qf0 : Q0));   // n x ny
-      if (rp) add_block(fth, 0, nx + (k - 1) * ny, GCQ, -1.0);
+      if (rp) add_block(Frp, 0, (k - 1) * ny, GCQ, -1.0);
       if (dp) {
         Mat Yd = mul(Cfull, Psi[k]);
         add_block(Yd, 0, (k - 1) * ndm, Dd);
@@ -291,6 +359,22 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
     }
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) H(i, j) += GS(i, j) + GS(j, i);
     for (int i = 0; i < n; ++i) for (int j = 0; j < nxe; ++j) fth(i, th_col(j)) += StP(i, j);
+  }
+  Mat T2S;
+  if (rp && !rcond) add_block(fth, 0, nx, Frp);
+  if (rcond) {
+    // traj2setpoint = (W H^-1 Fr Is) \ (W H^-1 Fr), W = I with 1e6 on the first move (mpc2mpqp.jl:552-563);
+    // the cost then sees the setpoint on every stage: Fr <- Fr Is
+    Mat X;
+    if (!solve_lu(H, Frp, X)) return cfail(LMPC_E_SETUP, "reference condensation: singular Hessian");
+    for (int i = 0; i < nu && i < n; ++i) for (int j = 0; j < X.c; ++j) X(i, j) *= 1e6;
+    Mat XI(n, ny), FI(n, ny);
+    for (int i = 0; i < n; ++i) for (int k = 0; k < Np; ++k) for (int j = 0; j < ny; ++j) {
+      XI(i, j) += X(i, k * ny + j);
+      FI(i, j) += Frp(i, k * ny + j);
+    }
+    if (!lstsq_qr(XI, X, T2S)) return cfail(LMPC_E_SETUP, "reference condensation: rank-deficient least squares");
+    add_block(fth, 0, nx, FI);
   }
   { Mat Hs(n, n); for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Hs(i, j) = 0.5 * (H(i, j) + H(j, i)); H = Hs; }
   // generalized-parameter cost (mpc2mpqp.jl:478-508): f += Umap' rep(eu) + Gx' rep(ex), and the p columns of
@@ -547,7 +631,7 @@ extern "C" int lmpc_gpu_condense(const lmpc_model *md, lmpc_mpqp **out) {
   lmpc_mpqp *q = new lmpc_mpqp();
   const int mg = (int)Arows.size(), m = ms + mg;
   q->n = nq; q->m = m; q->ms = ms; q->nth = nth; q->nx = nx; q->nr = nrp; q->nd = ndp; q->nuprev = nup; q->nu = nu;
-  q->H = H; q->f_theta = fth; q->f = fvec;
+  q->H = H; q->f_theta = fth; q->f = fvec; q->traj2setpoint = T2S;
   q->A = Mat(mg, nq); q->W = Mat(m, nth);
   for (int i = 0; i < ms; ++i) for (int j = 0; j < nth; ++j) q->W(i, j) = W(i, j);
   q->bu = bu; q->bl = bl;
@@ -574,6 +658,15 @@ extern "C" int lmpc_gpu_mpqp_dims(const lmpc_mpqp *q, int32_t *dims9) {
   if (!q || !dims9) return cfail(LMPC_E_INVALID, "null argument");
   const int32_t d[9] = {q->n, q->m, q->ms, q->nth, q->nu, q->nx, q->nr, q->nd, q->nuprev};
   memcpy(dims9, d, sizeof(d));
+  return 0;
+}
+
+extern "C" int lmpc_gpu_mpqp_traj2setpoint(const lmpc_mpqp *q, double *T, int32_t *rows, int32_t *cols) {
+  if (!q) return cfail(LMPC_E_INVALID, "null argument");
+  if (rows) *rows = q->traj2setpoint.r;
+  if (cols) *cols = q->traj2setpoint.c;
+  if (T) for (int j = 0; j < q->traj2setpoint.c; ++j) for (int i = 0; i < q->traj2setpoint.r; ++i)
+    T[(size_t)j * q->traj2setpoint.r + i] = q->traj2setpoint(i, j);
   return 0;
 }
 

@@ -1009,7 +1009,8 @@ class _Model(C.Structure):
                 ("reference_preview", C.c_int32), ("disturbance_preview", C.c_int32), ("K", C.c_void_p),
                 ("np", C.c_int32), ("Ex", C.c_void_p), ("ex", C.c_void_p), ("Eu", C.c_void_p), ("eu", C.c_void_p),
                 ("parameter_preview", C.c_int32),
-                ("f_offset", C.c_void_p), ("h_offset", C.c_void_p), ("xo", C.c_void_p), ("uo", C.c_void_p)]
+                ("f_offset", C.c_void_p), ("h_offset", C.c_void_p), ("xo", C.c_void_p), ("uo", C.c_void_p),
+                ("reference_condensation", C.c_int32)]
 
 
 def _diag(v, n):
@@ -1042,6 +1043,7 @@ class MPC:
         self.constraints = []
         self.reference_tracking, self.preprocess_mpqp, self.soft_weight = True, True, 1e6
         self.reference_preview = self.disturbance_preview = False   # types.jl:56-57
+        self.reference_condensation, self.traj2setpoint = False, None   # types.jl:54,65; set by condense()
         self.K = None                                               # prestabilising feedback, setup.jl:186-199
         self.Ex = self.ex = self.Eu = self.eu = None                # generalized-parameter cost, setup.jl:118-132
         self.parameter_preview = False                              # types.jl:58,69
@@ -1257,7 +1259,8 @@ class MPC:
                     int(self.reference_tracking), int(self.preprocess_mpqp), None, None,
                     int(self.reference_preview), int(self.disturbance_preview), cm(self.K),
                     npar, cm(wide(self.Ex, self.nx)), cm(self.ex), cm(wide(self.Eu, self.nu)), cm(self.eu),
-                    int(self.parameter_preview), cm(self.f_offset), cm(self.h_offset), cm(self.xo), cm(self.uo))
+                    int(self.parameter_preview), cm(self.f_offset), cm(self.h_offset), cm(self.xo), cm(self.uo),
+                    int(self.reference_condensation))
         if self.move_blocks:
             mbf = np.ascontiguousarray([v for b in self.move_blocks for v in b], np.int32)
             mbn = np.ascontiguousarray([len(b) for b in self.move_blocks], np.int32)
@@ -1276,6 +1279,13 @@ class MPC:
                        W=np.zeros((m, nth), order="F"), senses=np.zeros(m, np.int32))
             L.lmpc_gpu_mpqp_get(q, *[out[k].ctypes.data for k in ("H", "f", "f_theta", "A", "bu", "bl", "W", "senses")])
             out["dims"] = (nx, nr, nd, nup)
+            L.lmpc_gpu_mpqp_traj2setpoint.argtypes = [C.c_void_p] * 4
+            tr, tc = C.c_int32(0), C.c_int32(0)
+            L.lmpc_gpu_mpqp_traj2setpoint(q, None, C.byref(tr), C.byref(tc))
+            self.traj2setpoint = None
+            if tr.value > 0:
+                self.traj2setpoint = np.zeros((tr.value, tc.value), order="F")
+                L.lmpc_gpu_mpqp_traj2setpoint(q, self.traj2setpoint.ctypes.data, None, None)
         finally:
             L.lmpc_gpu_mpqp_free(q)
         self.mpqp = out
@@ -1297,6 +1307,9 @@ class MPC:
     def compute_control(self, x, r=None, d=None, uprev=None, p=None, check=True):
         if self.reference_preview and self.reference_tracking:
             r = self._flatten_preview(r, self.ny)
+            if self.reference_condensation:      # condense_reference (utils.jl:140-147)
+                self._g()
+                r = self.traj2setpoint @ r
         if self.disturbance_preview and self.nd > 0:
             d = self._flatten_preview(d, self.nd)
         nb = self.affine_parameter_dim()

@@ -128,6 +128,10 @@ class MPC:
     reference_preview: bool = False
     disturbance_preview: bool = False
     parameter_preview: bool = False   # types.jl:58,69: Np blocks of generalized parameters in theta
+    # types.jl:54,65: with reference_preview, collapse the previewed trajectory to ONE setpoint (theta carries ny
+    # values again); traj2setpoint (ny x ny*Np) maps a trajectory to it, set by mpc2mpqp (mpc2mpqp.jl:550-568)
+    reference_condensation: bool = False
+    traj2setpoint: Optional[np.ndarray] = None
     preprocess_mpqp: bool = True
     soft_weight: float = 1e6
     # generalized-parameter (affine) objective terms (Ex p + ex)'x + (Eu p + eu)'u, setup.jl:118-132
@@ -258,7 +262,7 @@ class MPC:
     def parameter_dims(self):
         """(nx, nr, nd, nuprev) -- mpc2mpqp.jl:147-164 (previews: Np blocks each); np via affine_parameter_dim."""
         nr = self.ny if self.reference_tracking else 0
-        if self.reference_preview and nr > 0:
+        if self.reference_preview and not self.reference_condensation and nr > 0:
             nr *= self.Np
         nd = self.nd_model
         if self.disturbance_preview and nd > 0:
@@ -274,6 +278,8 @@ class MPC:
         x = np.asarray(x, float).reshape(nx)
         if self.reference_preview and nr > 0:
             r = _flatten_preview(r, self.ny, self.Np)
+            if self.reference_condensation:          # condense_reference, utils.jl:140-147
+                r = self.traj2setpoint @ r
         if self.disturbance_preview and nd > 0:
             d = _flatten_preview(d, self.nd_model, self.Np)
         r = np.zeros(nr) if r is None else np.asarray(r, float).reshape(-1)[:nr]
@@ -455,6 +461,15 @@ def dense_objective(mpc: MPC, F, G, C, Phi, Gam):
         CQ = np.kron(np.eye(N + 1), Cfull.T @ Qfull)
         CQ[-nxe:, -ny:] = Cfull.T @ Qffull
         Fr = (-Gam.T @ CQ)[:, ny:]
+        if mpc.reference_condensation:
+            # mpc2mpqp.jl:550-568: the setpoint whose (weighted) effect on the unconstrained optimum -H^-1 Fr r is
+            # closest to the trajectory's; the first control move is weighted 1e6
+            Is = np.tile(np.eye(ny), (N, 1))
+            Wc = np.eye(nu * Nc)
+            Wc[np.arange(nu), np.arange(nu)] = 1e6
+            WinvHFr = (Wc @ np.linalg.inv(H)) @ Fr
+            mpc.traj2setpoint = np.linalg.lstsq(WinvHFr @ Is, WinvHFr, rcond=None)[0]
+            Fr = Fr @ Is
         f_theta = np.hstack([f_theta[:, :nxp], Fr, f_theta[:, nxp:]])
     if ndp > 0 and mpc.disturbance_preview:
         # disturbance_preview_cost (mpc2mpqp.jl:579-610): y_k = C x_k + Dd d_{k-1}, x through Psi
@@ -767,7 +782,7 @@ def mpc2mpqp(mpc: MPC) -> MPQP:
         mpc = orig
     nxp, nrp, _, _ = mpc.parameter_dims()
     if nrp > 0 and np.any(mpc.h_offset != 0):       # r - h_offset is what the outputs track (mpc2mpqp.jl:523-530)
-        ho = np.tile(mpc.h_offset, mpc.Np) if mpc.reference_preview else mpc.h_offset
+        ho = np.tile(mpc.h_offset, mpc.Np) if (mpc.reference_preview and not mpc.reference_condensation) else mpc.h_offset
         f = f - f_theta[:, nxp:nxp + nrp] @ ho
     if getattr(mpc, "move_blocks", None):
         H, f, f_theta, A, bu, bl, W, soft, prio = apply_move_block(mpc, H, f, f_theta, A, bu, bl, W, soft, prio)

@@ -472,3 +472,41 @@ def test_operating_point_of_a_regulator_matches_rollout():
         J2, _ = _rollout(mpc, x0, Z, np.zeros((0, N)), np.zeros(nu), U2)
         q = lambda U: 0.5 * U @ qp.H @ U + (qp.f + qp.f_theta @ x0) @ U
         assert abs((J1 - J2) - 2 * (q(U1.ravel()) - q(U2.ravel()))) <= 1e-9 * max(1.0, abs(J1), abs(J2))
+
+
+@pytest.mark.parametrize("name", ["invpend", "aircraft"])
+def test_reference_condensation(lmpc, name):
+    """reference_preview + reference_condensation (types.jl:54,65; mpc2mpqp.jl:550-568; utils.jl:140-147): theta
+    carries ny reference values again, the mpQP is the setpoint-tracking one, traj2setpoint (ny x ny Np) maps a
+    trajectory to the setpoint: a constant trajectory maps to its value, and for any trajectory the condensed
+    controller's unconstrained first move is the weighted-least-squares fit of the previewing controller's."""
+    plain = _example(name, False, False)
+    prev = _example(name, True, False)
+    cond = _example(name, True, False)
+    cond.reference_condensation = True
+    qn, qp, qc = om.mpc2mpqp(plain), om.mpc2mpqp(prev), om.mpc2mpqp(cond)
+    ny, N, nu = cond.ny, cond.Np, cond.nu
+    assert cond.parameter_dims() == plain.parameter_dims() and qc.f_theta.shape == qn.f_theta.shape
+    assert np.allclose(qc.f_theta, qn.f_theta, rtol=1e-12, atol=1e-12) and np.allclose(qc.H, qn.H, rtol=1e-12, atol=1e-12)
+    T = cond.traj2setpoint
+    assert T.shape == (ny, ny * N)
+    assert np.allclose(T @ np.tile(np.eye(ny), (N, 1)), np.eye(ny), atol=1e-9)
+    rng = np.random.default_rng(4)
+    Rp = rng.normal(size=(ny, N))
+    nx = cond.nx
+    x0, up = rng.normal(size=nx), rng.normal(size=nu)
+    thp, thc = prev.form_parameter(x0, Rp, None, up), cond.form_parameter(x0, Rp, None, up)
+    assert thc.size == qc.f_theta.shape[1] and np.allclose(thc[nx:nx + ny], T @ Rp.reshape(-1, order="F"))
+    # unconstrained optima: the reference parts of -H^-1 f_theta theta agree in the 1e6-weighted first move
+    zp = -np.linalg.solve(qp.H, qp.f_theta[:, nx:nx + ny * N] @ thp[nx:nx + ny * N])
+    zc = -np.linalg.solve(qc.H, qc.f_theta[:, nx:nx + ny] @ thc[nx:nx + ny])
+    assert np.max(np.abs(zp[:nu] - zc[:nu])) < 1e-3 * max(1.0, np.max(np.abs(zp)))
+    # the C++ condenser: same mpQP, same map
+    from test_condense_cpu import mirror_of
+    m = mirror_of(lmpc, cond)
+    m.reference_preview = m.reference_condensation = True
+    q = m.condense()
+    assert q["dims"] == cond.parameter_dims()
+    assert np.max(np.abs(q["f_theta"] - qc.f_theta)) <= 1e-12 * max(1.0, np.abs(qc.f_theta).max())
+    assert np.max(np.abs(q["H"] - qc.H)) <= 1e-12 * max(1.0, np.abs(qc.H).max())
+    assert m.traj2setpoint.shape == T.shape and np.max(np.abs(m.traj2setpoint - T)) < 1e-8 * max(1.0, np.abs(T).max())
