@@ -584,7 +584,9 @@ def measure(name, dev_index, rank, world, dist, torch, steps, warmup, cpu_baseli
 def kernel_name(g, w):
     """from what the handle selected (lmpc_gpu_get_info), not a literal"""
     box = g.kernel == 1 and w["kind"] == "solve" and not np.any(g.senses) and g.m == g.n and g.n <= 8
-    base = {1: "ldp_box_kernel<%d,%d>" % (g.n, g.nu) if box else "ldp_thread_kernel<%d>" % g.n,
+    # box problems: the add-only fast kernel, then the generic box kernel over the instances it handed over
+    base = {1: "ldp_box_fast_kernel<%d,%d> + ldp_box_kernel<%d,%d> REDO pass" % (g.n, g.nu, g.n, g.nu) if box
+            else "ldp_thread_kernel<%d>" % g.n,
             2: "ldp_warp_kernel", 3: "ldp_cta_kernel / ldp_big_kernel"}[g.kernel]
     if w["kind"] == "sim":
         base = base.replace("_kernel", "_sim_kernel")

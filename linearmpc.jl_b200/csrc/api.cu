@@ -21,6 +21,9 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+}
+void lmpc_count_kernel(int n) { g_launches.fetch_add(n); }
+namespace {
 
 int set_err(int code, const char *fmt, const char *detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);

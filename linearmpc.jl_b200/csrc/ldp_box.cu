@@ -267,10 +267,30 @@ LMPC_DEVINL int box_scan(const BC &bc, unsigned inws, double primal_tol, const d
   return code;
 }
 
+// the same scan with the bounds read back from the thread's shared-memory column (bnd[(2 j + lower) * KB_BLOCK]),
+// where the add needs them anyway.  (Measured and dropped: a tournament form -- independent per-row candidates
+// min(su, sl) + a comparison tree instead of the serial compare-select chain -- was 2 % slower.)
+template <int N, class BC>
+LMPC_DEVINL int box_scan_smem(const BC &bc, unsigned inws, double primal_tol, const double *bnd, const double (&u)[N]) {
+  double best = -primal_tol;
+  int code = -1;
+  SFOR(j, 0, N)
+    double mu = 0.0;
+    SFOR(c, j, N) mu = fma(bc.M[j * N + c], u[c], mu); SEND
+    const bool free_row = !((inws >> j) & 1u);
+    const double su = bnd[(2 * j) * KB_BLOCK] - mu, sl = mu - bnd[(2 * j + 1) * KB_BLOCK];
+    const bool tu = free_row && (su < best);
+    const bool tl = free_row && !tu && (sl < best);
+    best = tu ? su : (tl ? sl : best);
+    code = tu ? 2 * j : (tl ? 2 * j + 1 : code);
+  SEND
+  return code;
+}
+
 // iteration K + 1 on the working set {slots 0..K-1}; true = this instance is finished (flag, iter set)
 template <int N, int K, class BC>
 LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, const double *Mp, const LdpSettings &st,
-                           const double (&dU)[N], const double (&dLo)[N], const double *bnd, double (&u)[N],
+                           const double *bnd, double (&u)[N],
                            double &best_fval, int &cycle, int &flag, int &iter) {
   iter = K + 1;
   {
@@ -300,7 +320,7 @@ LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, c
     flag = EXIT_OPTIMAL;
     return true;
   } else {
-    const int code = box_scan<N>(bc, s.inws, st.primal_tol, dU, dLo, u);
+    const int code = box_scan_smem<N>(bc, s.inws, st.primal_tol, bnd, u);
     const int add = code >> 1;
     const bool addlow = code & 1;
     if (add < 0) { flag = EXIT_OPTIMAL; return true; }
@@ -326,10 +346,10 @@ LMPC_DEVINL bool fast_iter(FastState<N> &s, const ConstView &cv, const BC &bc, c
 
 template <int N, int K, class BC>
 LMPC_DEVINL void fast_chain(FastState<N> &s, const ConstView &cv, const BC &bc, const double *Mp, const LdpSettings &st,
-                            const double (&dU)[N], const double (&dLo)[N], const double *bnd, double (&u)[N],
+                            const double *bnd, double (&u)[N],
                             double &best_fval, int &cycle, int &flag, int &iter) {
-  if (fast_iter<N, K>(s, cv, bc, Mp, st, dU, dLo, bnd, u, best_fval, cycle, flag, iter)) return;
-  if constexpr (K < N) fast_chain<N, K + 1>(s, cv, bc, Mp, st, dU, dLo, bnd, u, best_fval, cycle, flag, iter);
+  if (fast_iter<N, K>(s, cv, bc, Mp, st, bnd, u, best_fval, cycle, flag, iter)) return;
+  if constexpr (K < N) fast_chain<N, K + 1>(s, cv, bc, Mp, st, bnd, u, best_fval, cycle, flag, iter);
 }
 
 // theta pass shared by the box kernels: sh = Dth theta, sho = uoff + Uth theta, from the warp's TMA tile
@@ -472,7 +492,7 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
         s.Dinv[0] = 1.0 / g; s.dW[0] = addd; s.row[0] = add;
         s.lowmask = addlow ? 1u : 0u;
         s.inws = 1u << add;
-        fast_chain<N, 1>(s, cv, bc, b.Mp, st, dU, dLo, bnd, u, best_fval, cycle, flag, iter);
+        fast_chain<N, 1>(s, cv, bc, b.Mp, st, bnd, u, best_fval, cycle, flag, iter);
       }
     }
     if (flag == EXIT_REDO_BOX) { out.flag[q] = flag; continue; }
@@ -715,6 +735,9 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
 #ifndef KB_FAST
 #define KB_FAST 1      // 0: the generic kernel alone, as before r02
 #endif
+#ifndef KB_FAST_MIN_BATCH
+#define KB_FAST_MIN_BATCH 200000
+#endif
 #ifndef KB_FAST_MINB
 #define KB_FAST_MINB 3
 #endif
@@ -726,7 +749,8 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
                int64_t Ninst, const SolveOut &out, int sm_count, cudaStream_t stream) {
   // the add-only fast kernel + the REDO launch of the generic one, or the generic kernel alone when the
   // settings could stop a solve inside the fast kernel's N + 1 iterations
-  const bool fast = KB_FAST && st.iter_limit > N + 2;
+  // (small batches: the second launch costs ~8 us, more than the fast kernel saves below ~2e5 instances)
+  const bool fast = KB_FAST && st.iter_limit > N + 2 && Ninst >= KB_FAST_MIN_BATCH;
   constexpr int FMINB = N <= 5 ? KB_FAST_MINB : 2;
   using kern_t = void (*)(LdpLayout, LdpSettings, const BoxConst<N, NU>, const double *, const ThetaSegs, int64_t,
                           SolveOut, int);
@@ -777,6 +801,7 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   int64_t rblocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   if (rblocks > (int64_t)sm_count * per_sm) rblocks = (int64_t)sm_count * per_sm;
   redo<<<(unsigned)rblocks, KB_BLOCK, smem_redo, stream>>>(lay, st, bc, cblk, th, Ninst, out, 0);
+  lmpc_count_kernel(1);
   return (int)cudaGetLastError();
 }
 

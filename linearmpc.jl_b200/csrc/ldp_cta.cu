@@ -1572,6 +1572,7 @@ int launch_cta(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
     } else {
       return launch_cta_full<T>(lay, st, cblk, th, N, out, sm_count, s, 0);
     }
+    lmpc_count_kernel(1);
     return launch_cta_full<T>(lay, st, cblk, th, N, out, sm_count, s, 1);
   }
   return launch_cta_full<T>(lay, st, cblk, th, N, out, sm_count, s, 0);

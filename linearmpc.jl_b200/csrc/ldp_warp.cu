@@ -718,6 +718,7 @@ static int launch_warp_2(const LdpLayout &lay, const LdpSettings &st, const doub
                          int sm_count, cudaStream_t s) {
   int e = launch_warp_t<EQ, false>(lay, st, cblk, th, N, out, sim, sm_count, s, 0);
   if (e != 0 || lay.nsoft == 0 || !K2_REPAIR) return e;
+  lmpc_count_kernel(1);
   return launch_warp_t<EQ, true>(lay, st, cblk, th, N, out, sim, sm_count, s, 1);
 }
 

@@ -89,6 +89,8 @@ struct LdpHost {
 // setup.cpp
 int lmpc_host_setup(const lmpc_problem *p, LdpHost *out, char *err, int errlen);
 
+// a launcher that issues more than one kernel per call reports the extra ones here (lmpc_gpu_launch_count)
+void lmpc_count_kernel(int n);
 // kernel launchers (each .cu exports one); all return cudaError_t as int
 struct cudaDeviceProp;
 int launch_ldp_thread(const LdpLayout &lay, const LdpSettings &st, const double *cblk,
