@@ -296,7 +296,7 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
         u = uc;
         if (lane < n) c.uw[lane] = uc;
         __syncwarp();
-        fval = bfly_sum(lane < n ? __dmul_rn(uc, uc) : 0.0);
+        fval = k > 0 ? bfly_sum(lane < n ? __dmul_rn(uc, uc) : 0.0) : 0.0;   // k == 0: a sum of +0 products
         const bool sf = lay.nsoft > 0 && lane < k && s.soft;
         if (lay.nsoft > 0) fval = fma(st.rho_soft, bfly_sum(sf ? __dmul_rn(s.lams, s.lams) : 0.0), fval);
         if (fval > st.fval_bound) { flag = EXIT_INFEASIBLE; break; }
@@ -309,8 +309,12 @@ LMPC_DEVINL int wq_loop(const WarpCtx &c, WarpQp &s, double sh0, double sh1, dou
           const int j = lane + 32 * half;
           if (j < m) {
             double mu = 0.0;
+            // empty working set (three steps out of four of a settled closed loop): u is exactly +0, and so is
+            // every fma(M, +0, +0) of this chain
+            if (k > 0) {
 #pragma unroll UF
-            for (int cc = 0; cc < n; ++cc) mu = fma(c.cv.MT[cc * mp + j], c.uw[cc], mu);
+              for (int cc = 0; cc < n; ++cc) mu = fma(c.cv.MT[cc * mp + j], c.uw[cc], mu);
+            }
             const bool skip = ((s.inws >> j) & 1ull) || (c.cv.sense[j] & S_IMMUTABLE);
             const double shj = half ? sh1 : sh0;
             const double dU = c.cv.du[j] + shj, dLo = c.cv.dl[j] + shj;
