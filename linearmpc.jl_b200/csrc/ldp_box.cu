@@ -446,7 +446,7 @@ template <int N, int NU, int MINB, bool CP>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
                     const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-                    SolveOut out, int flags) {
+                    SolveOut out, int flags, int32_t *rflag) {
   const bool use_tiles = flags & 1;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
@@ -495,7 +495,10 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
         fast_chain<N, 1>(s, cv, bc, b.Mp, st, bnd, u, best_fval, cycle, flag, iter);
       }
     }
-    if (flag == EXIT_REDO_BOX) { out.flag[q] = flag; continue; }
+    // hand-over marks go to rflag when the caller's flag array is remote (a peer GPU's result window): the REDO
+    // launch then scans local memory instead of reading N flags back over NVLink
+    if (rflag) rflag[q] = flag;
+    if (flag == EXIT_REDO_BOX) { if (!rflag) out.flag[q] = flag; continue; }
     SFOR(i, 0, NU)
       double pr[N];
       SFOR(c, 0, N) pr[c] = __dmul_rn(bc.Rinv[i * N + c], u[c]); SEND
@@ -529,7 +532,7 @@ template <int N, int NU, int MINB, bool CP = false, bool REDO = false>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
                const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-               SolveOut out, int flags) {
+               SolveOut out, int flags, int32_t *rflag) {
   const bool use_tiles = !REDO && (flags & 1);
   constexpr bool use_cp = CP;   // compile-time: with both loops in one kernel the gain on short theta is lost
   extern __shared__ __align__(16) double smem[];
@@ -707,7 +710,7 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
 #pragma unroll
         for (int j = 0; j < KB_SCAN / KB_BLOCK; ++j) {
           const int64_t q = pos + j * KB_BLOCK + threadIdx.x;
-          fl[j] = q < r1 ? out.flag[q] : 0;
+          fl[j] = q < r1 ? (rflag ? rflag[q] : out.flag[q]) : 0;
         }
 #pragma unroll
         for (int j = 0; j < KB_SCAN / KB_BLOCK; ++j) {
@@ -753,7 +756,7 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   const bool fast = KB_FAST && st.iter_limit > N + 2 && Ninst >= KB_FAST_MIN_BATCH;
   constexpr int FMINB = N <= 5 ? KB_FAST_MINB : 2;
   using kern_t = void (*)(LdpLayout, LdpSettings, const BoxConst<N, NU>, const double *, const ThetaSegs, int64_t,
-                          SolveOut, int);
+                          SolveOut, int, int32_t *);
   kern_t kern = fast ? (kern_t)ldp_box_fast_kernel<N, NU, FMINB, false> : (kern_t)ldp_box_kernel<N, NU, MINB, false>;
   kern_t kern_cp = fast ? (kern_t)ldp_box_fast_kernel<N, NU, FMINB, true> : (kern_t)ldp_box_kernel<N, NU, MINB, true>;
   const size_t smem_base = ((size_t)((lay.total + 1) & ~1) + N * BoxPad<N>::NP) * sizeof(double);
@@ -787,9 +790,27 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   int64_t blocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   const int64_t cap = (int64_t)sm_count * per_sm;   // persistent: whole resident waves over the SMs
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out, use_tiles);
+  // caller's flag array on another device (peer window)?  keep the hand-over marks in a stream-ordered local scratch
+  int32_t *rflag = nullptr;
+  if (fast) {
+    cudaPointerAttributes pa;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaPointerGetAttributes(&pa, out.flag) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != dev) {
+      static bool pool_kept[64] = {false};
+      if (dev < 64 && !pool_kept[dev]) {   // keep freed scratch in the pool instead of returning it to the OS every call
+        cudaMemPool_t mp;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_kept[dev] = true;
+      }
+      if (cudaMallocAsync((void **)&rflag, (size_t)Ninst * sizeof(int32_t), stream) != cudaSuccess) rflag = nullptr;
+    }
+    cudaGetLastError();
+  }
+  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out, use_tiles, rflag);
   e = cudaGetLastError();
-  if (e != cudaSuccess || !fast) return (int)e;
+  if (e != cudaSuccess || !fast) { if (rflag) cudaFreeAsync(rflag, stream); return (int)e; }
   // second launch: whatever the fast kernel handed over, compacted per CTA
   kern_t redo = (kern_t)ldp_box_kernel<N, NU, MINB, false, true>;
   const size_t smem_redo = smem_base + (size_t)KB_QCAP * sizeof(int);
@@ -800,8 +821,9 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   if (per_sm < 1) per_sm = 1;
   int64_t rblocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   if (rblocks > (int64_t)sm_count * per_sm) rblocks = (int64_t)sm_count * per_sm;
-  redo<<<(unsigned)rblocks, KB_BLOCK, smem_redo, stream>>>(lay, st, bc, cblk, th, Ninst, out, 0);
+  redo<<<(unsigned)rblocks, KB_BLOCK, smem_redo, stream>>>(lay, st, bc, cblk, th, Ninst, out, 0, rflag);
   lmpc_count_kernel(1);
+  if (rflag) cudaFreeAsync(rflag, stream);
   return (int)cudaGetLastError();
 }
 
