@@ -441,7 +441,10 @@ class Bench:
             out["bit_identical_xend"] = bool(np.array_equal(self.Xend[:n_gate].cpu().numpy().T, ref["Xend"]))
             out["identical_iteration_totals"] = bool(np.array_equal(self.iters[:n_gate].cpu().numpy(), ref["iters"]))
         else:
+            # the same launches as the timed step (box problems: fast kernel + REDO launch at any batch size)
+            os.environ["LMPC_BOX_FAST_MIN_BATCH"] = "0" if self.n >= 200000 else str(1 << 62)
             got = self.g.solve(np.asfortranarray(sub.T))
+            del os.environ["LMPC_BOX_FAST_MIN_BATCH"]
             same = (got["exitflag"] == ref["flag"]) & np.all(got["active_upper"] == ref["act_u"], axis=1) & \
                 np.all(got["active_lower"] == ref["act_l"], axis=1) & (got["iters"] == ref["iters"])
             out["identical_flag_iters_and_active_set"] = int(same.sum())

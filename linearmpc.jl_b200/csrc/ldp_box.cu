@@ -17,6 +17,7 @@
 //   * no immutable / soft / singular handling at all (cannot occur for this class).
 #include "ldp_device.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace {
 
@@ -753,7 +754,10 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   // the add-only fast kernel + the REDO launch of the generic one, or the generic kernel alone when the
   // settings could stop a solve inside the fast kernel's N + 1 iterations
   // (small batches: the second launch costs ~8 us, more than the fast kernel saves below ~2e5 instances)
-  const bool fast = KB_FAST && st.iter_limit > N + 2 && Ninst >= KB_FAST_MIN_BATCH;
+  // LMPC_BOX_FAST_MIN_BATCH overrides the threshold (tests and sanitizer runs push small batches through both launches)
+  const char *env_min = getenv("LMPC_BOX_FAST_MIN_BATCH");
+  const int64_t min_batch = env_min ? atoll(env_min) : (int64_t)KB_FAST_MIN_BATCH;
+  const bool fast = KB_FAST && st.iter_limit > N + 2 && Ninst >= min_batch;
   constexpr int FMINB = N <= 5 ? KB_FAST_MINB : 2;
   using kern_t = void (*)(LdpLayout, LdpSettings, const BoxConst<N, NU>, const double *, const ThetaSegs, int64_t,
                           SolveOut, int, int32_t *);

@@ -91,6 +91,32 @@ def test_batch_matches_oracle(lmpc, name, scale, N):
     assert_parity(g.solve(Th), P.solve_batch(Th))
 
 
+BOX_CASES = [c for c in CASES if c[0] == "invpend" or c[0].startswith("invpend_nc") or c[0].startswith("aircraft_box")]
+
+
+@pytest.mark.parametrize("name,scale,N", BOX_CASES)
+def test_box_fast_path_matches_oracle(lmpc, monkeypatch, name, scale, N):
+    """K1c: the add-only fast kernel + the REDO launch of the generic box kernel, which the library takes from
+    2e5 instances on; LMPC_BOX_FAST_MIN_BATCH = 0 pushes these oracle-sized batches through both launches
+    (every <n, nu> instantiation): flags, iteration counts, active sets and u identical to the oracle, and to
+    the single-launch path the default threshold selects at this size."""
+    mpc, qp, g, P = gpu_controller(lmpc, name)
+    lo, hi = util.theta_range(name, scale)
+    Th = mpqp.sample_theta(lo, hi, N, seed=11)
+    single = g.solve(Th)
+    launches = lmpc.launch_count()
+    monkeypatch.setenv("LMPC_BOX_FAST_MIN_BATCH", "0")
+    fast = g.solve(Th)
+    assert lmpc.launch_count() - launches == 2          # fast kernel + REDO launch
+    assert_parity(fast, P.solve_batch(Th))
+    for k in ("U", "exitflag", "iters", "active_upper", "active_lower"):
+        assert np.array_equal(fast[k], single[k]), k
+    # ragged sizes around the warp / CTA / scan-step boundaries
+    for n in (1, 31, 33, 127, 129, 2047, 2049):
+        out = g.solve(Th[:, :n])
+        assert np.array_equal(out["U"], single["U"][:, :n]) and np.array_equal(out["exitflag"], single["exitflag"][:n])
+
+
 def test_box_kernel_is_what_runs_on_box_only_problems(lmpc):
     """the cases above really exercise K1b: box-only problems with n <= 8 select the thread kernel and
     the library takes its box fast path (lmpc_gpu_get_info reports the thread kernel, capacity n)."""
