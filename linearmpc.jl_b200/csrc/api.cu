@@ -15,6 +15,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <cmath>
+#include <algorithm>
 #include "lmpc_common.h"
 
 namespace {
@@ -970,10 +972,20 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
   // replicate the half-plane and leaf-law tables so that lane l reads replica l mod rep
   // (conflict-free at 8); as many replicas (power of two <= 8) as fit in ~200 KB of shared memory
   const size_t rows = (size_t)n_hp + (size_t)n_fb * nu;
+  // fp32 screening rows [a | b] (bst_eval.cu): 16-byte quads of four floats, nth <= 16 only
+  const int quads = (nth <= 16) ? (ld + 3) / 4 : 0;
   int rep = 8;
-  while (rep > 1 && (node_d + rows * pairs * 2 * rep + 2 * nu) * sizeof(double) > 200 * 1024) rep >>= 1;
-  const size_t onodes = 0, ohp = node_d, ofb = ohp + (size_t)n_hp * pairs * 2 * rep;
-  const size_t oclip = ofb + (size_t)n_fb * nu * pairs * 2 * rep, total = oclip + al2((size_t)2 * nu);
+  // what has to sit in shared memory: with the screen, the fp32 rows + the laws; without it, the fp64 rows + the laws
+  auto smem_doubles = [&](int r) {
+    return quads ? node_d + ((size_t)n_fb * nu * pairs * 2 + (size_t)n_hp * quads * 2) * r + 2 * nu + 2
+                 : node_d + rows * pairs * 2 * r + 2 * nu;
+  };
+  // (the closed-loop kernel stages the whole block, fp64 rows included: keep that within reach too when possible)
+  auto all_doubles = [&](int r) { return smem_doubles(r) + (quads ? (size_t)n_hp * pairs * 2 * r : 0); };
+  while (rep > 1 && (smem_doubles(rep) * sizeof(double) > 160 * 1024 || all_doubles(rep) * sizeof(double) > 210 * 1024)) rep >>= 1;
+  const size_t onodes = 0, ofb = node_d, oclip = ofb + (size_t)n_fb * nu * pairs * 2 * rep;
+  const size_t ohp32 = oclip + al2((size_t)2 * nu), oscr = ohp32 + (size_t)n_hp * quads * 2 * rep;
+  const size_t ohp = oscr + (quads ? 2 : 0), total = ohp + (size_t)n_hp * pairs * 2 * rep;
   std::vector<double> blk(total, 0.0);
   if (packed) {
     uint32_t *nodes = reinterpret_cast<uint32_t *>(blk.data() + onodes);
@@ -994,6 +1006,21 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
               feedbacks[(size_t)r * ld * nu + (size_t)i * ld + c];
   if (clipping)
     for (int i = 0; i < nu; ++i) { blk[oclip + 2 * i] = clipping[i]; blk[oclip + 2 * i + 1] = clipping[nu + i]; }
+  if (quads) {
+    float *h32 = reinterpret_cast<float *>(blk.data() + ohp32);
+    double a1max = 0.0, bmax = 0.0;
+    for (int hI = 0; hI < n_hp; ++hI) {
+      double a1 = 0.0;
+      for (int c = 0; c < ld; ++c) {
+        const double v = halfplanes[(size_t)hI * ld + c];
+        if (c < nth) a1 += std::fabs(v); else bmax = std::max(bmax, std::fabs(v));
+        for (int p2 = 0; p2 < rep; ++p2) h32[(((size_t)hI * quads + c / 4) * rep + p2) * 4 + (c & 3)] = (float)v;
+      }
+      a1max = std::max(a1max, a1);
+    }
+    // bound constants of the screen: |d32 - (a'theta - b)| <= 2^-18 (a1max * max|theta_i| + bmax), see bst_eval.cu
+    blk[oscr] = a1max * (1.0 + 1e-6); blk[oscr + 1] = bmax * (1.0 + 1e-6);
+  }
   lmpc_bst *t = new lmpc_bst();
   t->device = device; t->sm_count = sm;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1012,6 +1039,7 @@ int lmpc_gpu_create_bst(const double *halfplanes, int32_t n_hp, const double *fe
   t->dev.onodes = (int)onodes; t->dev.ohp = (int)ohp; t->dev.ofb = (int)ofb; t->dev.oclip = (int)oclip;
   t->dev.pairs = pairs; t->dev.rep = rep; t->dev.packed = packed ? 1 : 0;
   t->dev.total = (int)total; t->dev.has_clip = clipping ? 1 : 0;
+  t->dev.ohp32 = (int)ohp32; t->dev.quads = quads; t->dev.oscr = (int)oscr; t->dev.staged = (int)(quads ? ohp : total);
   t->dev.nth = nth; t->dev.nu = nu; t->dev.n_hp = n_hp; t->dev.n_fb = n_fb; t->dev.n_nodes = n_nodes;
   *out = t;
   return 0;

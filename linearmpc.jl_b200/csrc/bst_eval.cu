@@ -10,6 +10,9 @@
 namespace {
 
 constexpr int K4_BLOCK = 1024;
+#ifndef K4_SCREEN
+#define K4_SCREEN 1        // fp32 screening of the branch decisions (0: fp64 rows from shared memory, as in r01)
+#endif
 
 // Tree block as packed by lmpc_gpu_create_bst (api.cu), all offsets in doubles:
 //   nodes  n_nodes x {jump, index}: packed into ONE 32-bit word (16 + 16 bits) when every jump and
@@ -22,13 +25,23 @@ constexpr int K4_BLOCK = 1024;
 //   clip   nu x 2
 struct BstLayout {
   int onodes, ohp, ofb, oclip, pairs, rep, packed, total;
+  int ohp32, quads, oscr, staged;   // fp32 screening rows (lmpc_common.h: BstDev)
 };
 
 // theta tiles: each warp streams its 32 parameters (one contiguous 32*nth*8-byte block of the
 // column-major Theta) into its own shared-memory slot with ONE TMA bulk copy, issued a whole tree
 // walk ahead; lanes then read their rows conflict-free.  This takes the theta traffic off the
 // L1TEX path that the table gathers saturate.
-template <int NTH, bool SMEM, bool PACKED>
+// SCREEN (r02): the kernel is bound by the shared-memory bytes a visited node costs (64 B of fp64 half-plane per lane).
+// The branch decision only needs the SIGN of a'theta - b, so it is first evaluated on an fp32 copy of the row (32 B per
+// lane for nth = 7, FFMA on the idle FP32 pipe) together with a rigorous bound on how far the fp32 value can be from
+// the exact one:  |d32 - (a'theta - b)| <= (n + 4) 2^-24 (sum |a_i theta_i| + |b|) <= 2^-18 (A1 max|theta_i| + B),
+// A1 = max_rows sum|a_i|, B = max_rows |b| (n <= 16; rounding of a, theta, b to fp32, the fp32 fma chain and the
+// final subtraction; the fp64 evaluation's own error is 2^-29 of that).  Outside the band the fp32 sign IS the fp64
+// sign; inside it (a few theta per million, NaN / overflow included) the lane re-evaluates the row in fp64 from
+// global memory, exactly as the unscreened kernel does.  Decisions, hence results, are bit-identical; the fp64 rows
+// leave shared memory altogether (invpend: 158 KB -> 70 KB staged).  The leaf law stays fp64.
+template <int NTH, bool SMEM, bool PACKED, bool SCREEN = false>
 __global__ void __launch_bounds__(K4_BLOCK, 1)
 bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu, int has_clip,
                 const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
@@ -37,8 +50,9 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t tbar[K4_BLOCK / 32];
   const double *base = blk;
+  const int staged = SCREEN ? bl.staged : bl.total;
   if (SMEM) {
-    stage_constants_tma(smem, blk, bl.total, &mbar);
+    stage_constants_tma(smem, blk, staged, &mbar);
     base = smem;
   }
   const int nth = NTH > 0 ? NTH : nth_rt;
@@ -47,7 +61,10 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   // nodes, so the replica is picked by NODE id there (lanes on the same node share one broadcast
   // read; breadth-first ids make the <= rep nodes of a level hit distinct bank groups); deeper
   // down the walks have scattered and the replica is picked by LANE (exactly 4 wavefronts per load)
-  const double2 *hp0 = reinterpret_cast<const double2 *>(base + bl.ohp);
+  const double2 *hp0 = reinterpret_cast<const double2 *>((SCREEN ? blk : base) + bl.ohp);   // SCREEN: fallback rows in global memory
+  const float4 *hq0 = reinterpret_cast<const float4 *>(base + bl.ohp32);
+  const int quads = bl.quads;
+  const float scrA = SCREEN ? (float)base[bl.oscr] * 1.0000002f : 0.f, scrB = SCREEN ? (float)base[bl.oscr + 1] * 1.0000002f : 0.f;
   const int lane_rep = threadIdx.x & (rep - 1);
 #ifndef K4_NODE_REP_IDS
 #define K4_NODE_REP_IDS 15          // node ids below this (levels 0..3 of a breadth-first tree)
@@ -64,7 +81,7 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   constexpr int P2 = (TH + 2) / 2;     // 16-byte pairs covering [a(nth) | b]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool tiles = SMEM && NTH > 0 && use_tiles;
-  double *tile = smem + bl.total + (size_t)warp * 32 * TH;      // this warp's theta slot
+  double *tile = smem + staged + (size_t)warp * 32 * TH;      // this warp's theta slot
   uint32_t tphase = 0;
   const int64_t stride = (int64_t)gridDim.x * K4_BLOCK;
   const int64_t q0 = (int64_t)blockIdx.x * K4_BLOCK + warp * 32;   // first theta of the warp's tile
@@ -100,25 +117,51 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
     if (!live) continue;
     int id = 0;
     int2 nd = load_node(0);
+    float thf[TH];
+    float scrE = 0.f;
+    if (SCREEN) {
+      float mx = 0.f;
+#pragma unroll
+      for (int c = 0; c < TH; ++c) { thf[c] = (float)th[c]; mx = fmaxf(mx, fabsf(thf[c])); }
+      scrE = 3.8146973e-6f * fmaf(scrA, mx * 1.0000002f, scrB);      // 2^-18 (A1 max|theta| + B); NaN / inf -> fallback
+      if (!(scrA * mx < 1e37f && scrB < 1e37f)) scrE = __int_as_float(0x7f800000);   // partial sums could overflow fp32: always fp64
+    }
     while (nd.x != 0) {
-      const double2 *h2 = hp0 + (size_t)nd.y * pairs * rep + (id < K4_NODE_REP_IDS ? (id & (rep - 1)) : lane_rep);
-      double acc = 0.0, rhs;
-      if (NTH > 0) {
-        double v[2 * P2];
+      const int repsel = (id < K4_NODE_REP_IDS ? (id & (rep - 1)) : lane_rep);
+      int go = -1;
+      if (SCREEN) {
+        constexpr int Q4 = (TH + 4) / 4;     // float4 quads covering [a(nth) | b]
+        const float4 *h4 = hq0 + (size_t)nd.y * quads * rep + repsel;
+        float v[4 * Q4];
 #pragma unroll
-        for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c * rep]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+        for (int c = 0; c < Q4; ++c) { const float4 t4 = h4[c * rep]; v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w; }
+        float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
-        rhs = v[TH];
-      } else {
-        rhs = 0.0;
-        for (int c = 0; c <= nth; ++c) {
-          const double2 t2 = h2[(c >> 1) * rep];
-          const double hv = (c & 1) ? t2.y : t2.x;
-          if (c < nth) acc = fma(hv, src[c], acc); else rhs = hv;
-        }
+        for (int c = 0; c < TH; ++c) acc = fmaf(v[c], thf[c], acc);
+        const float d = acc - v[TH];
+        if (fabsf(d) > scrE) go = d > 0.f ? 1 : 0;
       }
-      id = id + nd.x + (acc <= rhs ? 0 : 1);
+      if (go < 0) {
+        const double2 *h2 = hp0 + (size_t)nd.y * pairs * rep + repsel;
+        double acc = 0.0, rhs;
+        if (NTH > 0) {
+          double v[2 * P2];
+#pragma unroll
+          for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c * rep]; v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+#pragma unroll
+          for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
+          rhs = v[TH];
+        } else {
+          rhs = 0.0;
+          for (int c = 0; c <= nth; ++c) {
+            const double2 t2 = h2[(c >> 1) * rep];
+            const double hv = (c & 1) ? t2.y : t2.x;
+            if (c < nth) acc = fma(hv, src[c], acc); else rhs = hv;
+          }
+        }
+        go = acc <= rhs ? 0 : 1;
+      }
+      id = id + nd.x + go;
       nd = load_node(id);
     }
     const int reg = nd.y;
@@ -150,11 +193,11 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   }
 }
 
-template <int NTH, bool SMEM, bool PACKED>
+template <int NTH, bool SMEM, bool PACKED, bool SCREEN = false>
 int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
                int32_t *region, int sm_count, cudaStream_t s) {
-  auto kern = bst_eval_kernel<NTH, SMEM, PACKED>;
-  size_t smem = SMEM ? (size_t)bl.total * sizeof(double) : 0;
+  auto kern = bst_eval_kernel<NTH, SMEM, PACKED, SCREEN>;
+  size_t smem = SMEM ? (size_t)(SCREEN ? bl.staged : bl.total) * sizeof(double) : 0;
   // room for one 32-theta tile per warp next to the tables?
   const size_t tile_bytes = (size_t)K4_BLOCK * (NTH > 0 ? NTH : 0) * sizeof(double);
   const int use_tiles = SMEM && NTH > 0 && smem + tile_bytes <= 225 * 1024 &&
@@ -176,6 +219,11 @@ int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_
 template <int NTH>
 int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
               int32_t *region, int sm_count, cudaStream_t s) {
+  // the fp32 screen needs compile-time nth, 32-bit node words and its staged prefix in shared memory
+  if constexpr (NTH > 0) {
+    if (K4_SCREEN && bl.quads > 0 && bl.packed && (size_t)bl.staged * sizeof(double) <= 165 * 1024)
+      return launch_k4s<NTH, true, true, true>(t, bl, Theta, N, U, region, sm_count, s);
+  }
   const bool in_smem = (size_t)bl.total * sizeof(double) <= 220 * 1024;
   if (in_smem && bl.packed) return launch_k4s<NTH, true, true>(t, bl, Theta, N, U, region, sm_count, s);
   if (in_smem) return launch_k4s<NTH, true, false>(t, bl, Theta, N, U, region, sm_count, s);
@@ -325,6 +373,7 @@ int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, 
   BstLayout bl;
   bl.onodes = t.onodes; bl.ohp = t.ohp; bl.ofb = t.ofb; bl.oclip = t.oclip;
   bl.pairs = t.pairs; bl.rep = t.rep; bl.packed = t.packed; bl.total = t.total;
+  bl.ohp32 = t.ohp32; bl.quads = t.quads; bl.oscr = t.oscr; bl.staged = t.staged;
   cudaStream_t s = (cudaStream_t)stream;
 #define K4_CASE(NN) case NN: return launch_k4<NN>(t, bl, Theta, N, U, region, sm_count, s);
   switch (t.nth) {
@@ -342,6 +391,7 @@ int launch_bst_sim(const BstDev &t, const double *dyn, int nx, int nr, int nd, i
   BstLayout bl;
   bl.onodes = t.onodes; bl.ohp = t.ohp; bl.ofb = t.ofb; bl.oclip = t.oclip;
   bl.pairs = t.pairs; bl.rep = t.rep; bl.packed = t.packed; bl.total = t.total;
+  bl.ohp32 = t.ohp32; bl.quads = t.quads; bl.oscr = t.oscr; bl.staged = t.staged;
   cudaStream_t s = (cudaStream_t)stream;
 #define K4S_CASE(NN) case NN: return launch_k4_sim<NN>(t, bl, dyn, nx, nr, nd, nup, X0, R, D, U0, Rtraj, Dtraj, N, T, Xend, Ulast, Utraj, sm_count, s);
   switch (t.nth) {

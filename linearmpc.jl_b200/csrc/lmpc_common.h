@@ -115,6 +115,10 @@ int ldp_cta_fast_cap(const LdpLayout &lay);
 struct BstDev {
   const double *blk;     // packed tree block on the device (layout: see bst_eval.cu)
   int onodes, ohp, ofb, oclip, total;        // offsets / sizes in doubles
+  // fp32 screening copy of the half-planes (bst_eval.cu): [a | b] rows as 16-byte quads, replicated like hp; 0 = none.
+  // The block is ordered [nodes | fb | clip | hp32 | bound constants | hp]: with the screen, only the prefix before
+  // hp (`staged` doubles) is staged into shared memory, the fp64 rows stay in global memory for the rare fallback
+  int ohp32, quads, oscr, staged;
   int pairs, rep, packed;                    // 16-byte pairs per row, table replicas, 32-bit node records
   int nth, nu, n_hp, n_fb, n_nodes, has_clip;
 };
