@@ -5,6 +5,7 @@
 // One thread per theta; theta lives in registers (NTH is a template parameter), the tree
 // (half-planes, leaf laws, node lists) is staged once per CTA into shared memory with a TMA
 // bulk copy.  The kernel is HBM-bound by design: 8(nth+nu) bytes per theta, everything else on chip.
+#include <cstdlib>
 #include "ldp_device.cuh"
 
 namespace {
@@ -193,6 +194,272 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
   }
 }
 
+// ---- K4r (r02): the screened walk as a lane-refill ring ------------------------------------------------------------
+// Two findings of the ncu capture of the kernel above drive this variant (profiles/r02_k4_bst_ncu_full.md):
+//  (1) it is issue-bound (84 % of the slots) and a visited node costs 34 instructions, half of them address
+//      arithmetic on run-time layout fields.  Here the replication factor (8), quads / pairs per row and NU are
+//      compile-time, the tables are addressed with 32-bit shared-memory addresses, and a node costs ~22;
+//  (2) 92 % of the invpend walks end after 4-5 nodes, 8 % take up to 20, so a warp that walks 32 theta together
+//      waits 10.2 steps on average for 4.85 steps of work per lane (SIMT 19 / 32).  Here a lane that reaches its leaf
+//      writes its result and takes the NEXT theta of the warp's stream while the stragglers keep walking:
+//      each warp owns a two-tile shared-memory ring fed by TMA bulk copies (one 32-theta tile = one contiguous block of
+//      Theta); a round = refill the free lanes from the ring (rank among the free lanes -> stream position), walk
+//      until at most `park` lanes are still inside the tree, apply the leaf law for the lanes that arrived.
+// Per theta the arithmetic is the kernel's above (same fp32 screen and error band, same fp64 fallback, same fp64
+// law in the same fma order): results are bit-identical, only the order in which theta are visited changes.
+#ifndef K4_RING
+#define K4_RING 1
+#endif
+#ifndef K4_STEPS_PER_VOTE
+#define K4_STEPS_PER_VOTE 1  // walk steps between two "how many lanes are still walking" votes
+#endif
+#ifndef K4R_REP_IDS
+#define K4R_REP_IDS 0         // > 0: node ids below this pick the half-plane replica by node id (broadcast reads near the root)
+#endif
+#ifndef K4R_BLOCK
+#define K4R_BLOCK 1024
+#endif
+#ifndef K4_PARK
+#define K4_PARK 8            // a round's walk ends once this many lanes or fewer are still walking
+#endif
+LMPC_DEVINL float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+LMPC_DEVINL double2 lds_d2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+LMPC_DEVINL uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+template <int NTH, int NU>   // NU: outputs (0 = run-time count)
+__global__ void __launch_bounds__(K4R_BLOCK, 1)
+bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, int has_clip,
+                     const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
+                     int32_t *__restrict__ region, int park) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t tbar[K4R_BLOCK / 32][2];
+  stage_constants_tma(smem, blk, bl.staged, &mbar);
+  constexpr int TH = NTH, Q4 = (TH + 4) / 4, P2 = (TH + 2) / 2, REP = 8;
+  constexpr uint32_t HROW = Q4 * REP * 16, FROW = P2 * REP * 16;      // bytes per replicated row
+  const int nu = NU > 0 ? NU : nu_rt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_nodes = s_base + (uint32_t)bl.onodes * 8u;
+  const uint32_t s_hq = s_base + (uint32_t)bl.ohp32 * 8u;
+  const uint32_t s_hq_lane = s_hq + (uint32_t)(lane & (REP - 1)) * 16u;
+  const uint32_t s_fb_lane = s_base + (uint32_t)bl.ofb * 8u + (uint32_t)(lane & (REP - 1)) * 16u;
+  const double2 *hp0 = reinterpret_cast<const double2 *>(blk + bl.ohp) + (lane & (REP - 1));   // fp64 rows: global memory
+  const float scrA = (float)smem[bl.oscr] * 1.0000002f, scrB = (float)smem[bl.oscr + 1] * 1.0000002f;
+  const bool scr_ovf = !(scrB < 1e37f);
+  double clo[NU > 0 ? NU : 1], chi[NU > 0 ? NU : 1];
+  if (NU > 0) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      clo[i] = has_clip ? smem[bl.oclip + 2 * i] : -__longlong_as_double(0x7ff0000000000000ll);
+      chi[i] = has_clip ? smem[bl.oclip + 2 * i + 1] : __longlong_as_double(0x7ff0000000000000ll);
+    }
+  }
+  const uint32_t root = lds_u32(s_nodes);
+
+  // per-lane walk state
+  double th[TH];
+  float thf[TH];
+  float scrE = 0.f;
+  uint32_t w = 0;            // node word of the current node: jump << 16 | index; < 0x10000 = leaf (or no theta)
+  int id = 0;
+  int64_t q = -1;            // theta index, -1 = the lane holds none
+
+  auto screen = [&]() {
+    float mx = 0.f;
+#pragma unroll
+    for (int c = 0; c < TH; ++c) { thf[c] = (float)th[c]; mx = fmaxf(mx, fabsf(thf[c])); }
+    scrE = 3.8146973e-6f * fmaf(scrA, mx * 1.0000002f, scrB);      // 2^-18 (A1 max|theta| + B); NaN / inf -> fallback
+    if (!(scrA * mx < 1e37f) || scr_ovf) scrE = __int_as_float(0x7f800000);   // partial sums could overflow fp32: always fp64
+  };
+  // one node on the fp32 screen.  A lane whose |d| falls inside the error band keeps walking on the fp32 sign but
+  // is marked: at its leaf it repeats the whole walk in fp64 (walk64; a few theta per million), so the hot loop holds
+  // no fp64 code at all.  Any root-to-leaf path is valid, so the provisional walk always ends at a leaf.
+  float margin = 0.f;        // min over the visited nodes of |d| (NaN-propagating): the walk is exact iff margin > scrE
+  auto step = [&]() {
+#if K4R_REP_IDS > 0
+    const uint32_t rb = id < K4R_REP_IDS ? s_hq + ((uint32_t)(id & (REP - 1)) << 4) : s_hq_lane;
+#else
+    const uint32_t rb = s_hq_lane;
+#endif
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(w & 0xffffu), "r"(HROW), "r"(rb));
+    float v[4 * Q4];
+#pragma unroll
+    for (int c = 0; c < Q4; ++c) { const float4 t4 = lds_f4(a + c * (REP * 16)); v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w; }
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < TH; ++c) acc = fmaf(v[c], thf[c], acc);
+    const float d = acc - v[TH];
+    asm("min.NaN.f32 %0, %0, %1;" : "+f"(margin) : "f"(fabsf(d)));
+    int gm;                                    // -1 when a'theta > b
+    asm("set.gt.s32.f32 %0, %1, %2;" : "=r"(gm) : "f"(acc), "f"(v[TH]));
+    id = id + (int)(w >> 16) - gm;
+    w = lds_u32(s_nodes + ((uint32_t)id << 2));
+  };
+  auto walk64 = [&]() {
+    id = 0;
+    w = root;
+    while (w >= 0x10000u) {
+      const double2 *h2 = hp0 + (size_t)(w & 0xffffu) * (P2 * REP);
+      double vv[2 * P2];
+#pragma unroll
+      for (int c = 0; c < P2; ++c) { const double2 t2 = h2[c * REP]; vv[2 * c] = t2.x; vv[2 * c + 1] = t2.y; }
+      double ad = 0.0;
+#pragma unroll
+      for (int c = 0; c < TH; ++c) ad = fma(vv[c], th[c], ad);
+      id += (int)(w >> 16) + (ad <= vv[TH] ? 0 : 1);
+      w = lds_u32(s_nodes + ((uint32_t)id << 2));
+    }
+  };
+  auto leaf_out = [&]() {
+    if (!(margin > scrE)) walk64();
+    const uint32_t reg = w & 0xffffu;
+    auto law = [&](int i) {
+      const uint32_t a = s_fb_lane + (reg * (uint32_t)nu + (uint32_t)i) * FROW;
+      double v[2 * P2];
+#pragma unroll
+      for (int c = 0; c < P2; ++c) { const double2 t2 = lds_d2(a + c * (REP * 16)); v[2 * c] = t2.x; v[2 * c + 1] = t2.y; }
+      double acc = v[TH];
+#pragma unroll
+      for (int c = 0; c < TH; ++c) acc = fma(v[c], th[c], acc);
+      return acc;
+    };
+    if (NU > 0) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        double acc = law(i);
+        if (acc < clo[i]) acc = clo[i];
+        if (acc > chi[i]) acc = chi[i];
+        U[q * NU + i] = acc;
+      }
+    } else {
+      for (int i = 0; i < nu; ++i) {
+        double acc = law(i);
+        if (has_clip) {
+          const double lo = smem[bl.oclip + 2 * i], hi = smem[bl.oclip + 2 * i + 1];
+          if (acc < lo) acc = lo;
+          if (acc > hi) acc = hi;
+        }
+        U[q * nu + i] = acc;
+      }
+    }
+    if (region) region[q] = (int32_t)reg;
+  };
+
+  // this warp's stream: the full tiles t0, t0 + ts, ... of Theta (tile = 32 theta = 32 * TH * 8 contiguous bytes)
+  const int64_t nt_full = N >> 5;
+  const int64_t t0 = (int64_t)blockIdx.x * (K4R_BLOCK / 32) + warp, ts = (int64_t)gridDim.x * (K4R_BLOCK / 32);
+  const uint32_t ntw = t0 < nt_full ? (uint32_t)((nt_full - t0 + ts - 1) / ts) : 0u;
+  const uint32_t total = ntw * 32u;
+  double *ring = smem + bl.staged + (size_t)warp * 64 * TH;
+  const uint32_t s_ring = smem_u32(ring);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar[warp][0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbar[warp][1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (ntw > 0) tile_issue(&tbar[warp][0], ring, Theta + t0 * 32 * TH, 32u * TH * 8u);
+    if (ntw > 1) tile_issue(&tbar[warp][1], ring + 32 * TH, Theta + (t0 + ts) * 32 * TH, 32u * TH * 8u);
+  }
+  uint32_t head = 0;          // theta of the stream handed to lanes so far (warp-uniform)
+  uint32_t landed = 0;        // tiles of the stream waited for so far (warp-uniform)
+  const unsigned lt = (1u << lane) - 1u;
+  while (true) {
+    // refill: the lanes outside the tree take the next theta of the stream, in lane order
+    const bool need = w < 0x10000u;
+    const unsigned fm = __ballot_sync(0xffffffffu, need);
+    const uint32_t want = head + (uint32_t)__popc(fm);
+    const uint32_t nhead = want < total ? want : total;
+    if (nhead > head) {
+      const uint32_t jl = (nhead - 1u) >> 5;
+      while (landed <= jl) { tile_wait(&tbar[warp][landed & 1u], (landed >> 1) & 1u); ++landed; }
+      const uint32_t p = head + (uint32_t)__popc(fm & lt);
+      if (need && p < total) {
+        const uint32_t sa = s_ring + (p & 63u) * (TH * 8u);
+#pragma unroll
+        for (int c = 0; c < TH; ++c) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(th[c]) : "r"(sa + c * 8u));
+        q = ((t0 + (int64_t)(p >> 5) * ts) << 5) + (int64_t)(p & 31u);
+        screen();
+        id = 0;
+        w = root;
+        margin = __int_as_float(0x7f800000);
+      }
+      __syncwarp();
+      // a tile whose 32 theta are all in registers frees its half of the ring for the tile two ahead
+      if (lane == 0) {
+        for (uint32_t j = head >> 5; j < (nhead >> 5); ++j)
+          if (j + 2u < ntw)
+            tile_issue(&tbar[warp][j & 1u], ring + (size_t)(j & 1u) * 32 * TH, Theta + (t0 + (int64_t)(j + 2u) * ts) * 32 * TH, 32u * TH * 8u);
+      }
+      head = nhead;
+    }
+    if (__ballot_sync(0xffffffffu, q >= 0) == 0u) break;
+    // walk until at most `lim` lanes are still inside the tree (to the end once the stream is exhausted)
+    const int lim = head < total ? park : 0;
+    while (true) {
+      const bool in = w >= 0x10000u;
+      if (__popc(__ballot_sync(0xffffffffu, in)) <= lim) break;
+      if (in) step();
+#if K4_STEPS_PER_VOTE > 1
+      if (w >= 0x10000u) step();
+#endif
+    }
+    if (q >= 0 && w < 0x10000u) { leaf_out(); q = -1; }
+  }
+  // ragged tail (N mod 32 theta): first warp of the grid, straight from global memory
+  if (blockIdx.x == 0 && warp == 0) {
+    const int64_t qq = (nt_full << 5) + lane;
+    if (qq < N) {
+#pragma unroll
+      for (int c = 0; c < TH; ++c) th[c] = ld_stream(Theta + qq * TH + c);
+      q = qq;
+      screen();
+      id = 0;
+      w = root;
+      margin = __int_as_float(0x7f800000);
+      while (w >= 0x10000u) step();
+      leaf_out();
+    }
+  }
+}
+
+template <int NTH>
+int launch_k4_ring(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
+                   int32_t *region, int sm_count, cudaStream_t s) {
+  const size_t smem = (size_t)bl.staged * sizeof(double) + (size_t)K4R_BLOCK * 2 * NTH * sizeof(double);
+  int64_t blocks = (N + K4R_BLOCK - 1) / K4R_BLOCK;
+  if (blocks > sm_count) blocks = sm_count;
+  int park = K4_PARK;
+  if (const char *e = getenv("LMPC_K4_PARK")) park = atoi(e);
+#define K4R_GO(NUU)                                                                                             \
+  {                                                                                                             \
+    auto kern = bst_eval_ring_kernel<NTH, NUU>;                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    if (e != cudaSuccess) return (int)e;                                                                        \
+    kern<<<(unsigned)blocks, K4R_BLOCK, smem, s>>>(t.blk, bl, t.nu, t.has_clip, Theta, N, U, region, park);      \
+    return (int)cudaGetLastError();                                                                             \
+  }
+  if (t.nu == 1) K4R_GO(1)
+  if (t.nu == 2) K4R_GO(2)
+  K4R_GO(0)
+#undef K4R_GO
+}
+
 template <int NTH, bool SMEM, bool PACKED, bool SCREEN = false>
 int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
                int32_t *region, int sm_count, cudaStream_t s) {
@@ -221,8 +488,14 @@ int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t
               int32_t *region, int sm_count, cudaStream_t s) {
   // the fp32 screen needs compile-time nth, 32-bit node words and its staged prefix in shared memory
   if constexpr (NTH > 0) {
-    if (K4_SCREEN && bl.quads > 0 && bl.packed && (size_t)bl.staged * sizeof(double) <= 165 * 1024)
+    if (K4_SCREEN && bl.quads > 0 && bl.packed && (size_t)bl.staged * sizeof(double) <= 165 * 1024) {
+      // lane-refill ring: 8 replicas, room for two theta tiles per warp, TMA-aligned Theta
+      if (K4_RING && bl.rep == 8 && (reinterpret_cast<uintptr_t>(Theta) & 15u) == 0 &&
+          (size_t)bl.staged * sizeof(double) + (size_t)K4R_BLOCK * 2 * NTH * sizeof(double) <= 225 * 1024 &&
+          !getenv("LMPC_K4_NO_RING"))
+        return launch_k4_ring<NTH>(t, bl, Theta, N, U, region, sm_count, s);
       return launch_k4s<NTH, true, true, true>(t, bl, Theta, N, U, region, sm_count, s);
+    }
   }
   const bool in_smem = (size_t)bl.total * sizeof(double) <= 220 * 1024;
   if (in_smem && bl.packed) return launch_k4s<NTH, true, true>(t, bl, Theta, N, U, region, sm_count, s);
