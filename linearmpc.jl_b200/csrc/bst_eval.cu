@@ -210,9 +210,6 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
 #ifndef K4_RING
 #define K4_RING 1
 #endif
-#ifndef K4_STEPS_PER_VOTE
-#define K4_STEPS_PER_VOTE 1  // walk steps between two "how many lanes are still walking" votes
-#endif
 #ifndef K4R_REP_IDS
 #define K4R_REP_IDS 0         // > 0: node ids below this pick the half-plane replica by node id (broadcast reads near the root)
 #endif
@@ -238,7 +235,7 @@ LMPC_DEVINL uint32_t lds_u32(uint32_t a) {
   return v;
 }
 
-template <int NTH, int NU>   // NU: outputs (0 = run-time count)
+template <int NTH, int NU, typename QI>   // NU: outputs (0 = run-time count); QI: theta index type (int32_t while N < 2^31)
 __global__ void __launch_bounds__(K4R_BLOCK, 1)
 bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, int has_clip,
                      const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
@@ -275,7 +272,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
   float scrE = 0.f;
   uint32_t w = 0;            // node word of the current node: jump << 16 | index; < 0x10000 = leaf (or no theta)
   int id = 0;
-  int64_t q = -1;            // theta index, -1 = the lane holds none
+  QI q = -1;                 // theta index, -1 = the lane holds none
 
   auto screen = [&]() {
     float mx = 0.f;
@@ -343,7 +340,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
         double acc = law(i);
         if (acc < clo[i]) acc = clo[i];
         if (acc > chi[i]) acc = chi[i];
-        U[q * NU + i] = acc;
+        U[(int64_t)q * NU + i] = acc;
       }
     } else {
       for (int i = 0; i < nu; ++i) {
@@ -353,7 +350,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
           if (acc < lo) acc = lo;
           if (acc > hi) acc = hi;
         }
-        U[q * nu + i] = acc;
+        U[(int64_t)q * nu + i] = acc;
       }
     }
     if (region) region[q] = (int32_t)reg;
@@ -379,6 +376,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
   uint32_t head = 0;          // theta of the stream handed to lanes so far (warp-uniform)
   uint32_t landed = 0;        // tiles of the stream waited for so far (warp-uniform)
   const unsigned lt = (1u << lane) - 1u;
+  int pre = 0;
   while (true) {
     // refill: the lanes outside the tree take the next theta of the stream, in lane order
     const bool need = w < 0x10000u;
@@ -393,7 +391,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
         const uint32_t sa = s_ring + (p & 63u) * (TH * 8u);
 #pragma unroll
         for (int c = 0; c < TH; ++c) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(th[c]) : "r"(sa + c * 8u));
-        q = ((t0 + (int64_t)(p >> 5) * ts) << 5) + (int64_t)(p & 31u);
+        q = (QI)(((QI)t0 + (QI)(p >> 5) * (QI)ts) << 5) + (QI)(p & 31u);
         screen();
         id = 0;
         w = root;
@@ -401,24 +399,28 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
       }
       __syncwarp();
       // a tile whose 32 theta are all in registers frees its half of the ring for the tile two ahead
-      if (lane == 0) {
-        for (uint32_t j = head >> 5; j < (nhead >> 5); ++j)
-          if (j + 2u < ntw)
-            tile_issue(&tbar[warp][j & 1u], ring + (size_t)(j & 1u) * 32 * TH, Theta + (t0 + (int64_t)(j + 2u) * ts) * 32 * TH, 32u * TH * 8u);
-      }
+      // (a refill hands out at most 32 theta, so at most one tile boundary is crossed)
+      const uint32_t j = head >> 5;
+      if ((nhead >> 5) != j && j + 2u < ntw && lane == 0)
+        tile_issue(&tbar[warp][j & 1u], ring + (size_t)(j & 1u) * 32 * TH, Theta + (t0 + (int64_t)(j + 2u) * ts) * 32 * TH, 32u * TH * 8u);
       head = nhead;
     }
     if (__ballot_sync(0xffffffffu, q >= 0) == 0u) break;
     // walk until at most `lim` lanes are still inside the tree (to the end once the stream is exhausted)
+    // The "how many lanes are still walking" vote costs half a node step: the first `pre` steps of a round run
+    // without it, pre = one less than what the previous round needed (adapts to the tree and to the theta).
     const int lim = head < total ? park : 0;
+    int ns = 0;
+#pragma unroll 1
+    for (; ns < pre; ++ns)
+      if (w >= 0x10000u) step();
     while (true) {
       const bool in = w >= 0x10000u;
       if (__popc(__ballot_sync(0xffffffffu, in)) <= lim) break;
       if (in) step();
-#if K4_STEPS_PER_VOTE > 1
-      if (w >= 0x10000u) step();
-#endif
+      ++ns;
     }
+    pre = ns > 0 ? ns - 1 : 0;
     if (q >= 0 && w < 0x10000u) { leaf_out(); q = -1; }
   }
   // ragged tail (N mod 32 theta): first warp of the grid, straight from global memory
@@ -427,7 +429,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
     if (qq < N) {
 #pragma unroll
       for (int c = 0; c < TH; ++c) th[c] = ld_stream(Theta + qq * TH + c);
-      q = qq;
+      q = (QI)qq;
       screen();
       id = 0;
       w = root;
@@ -448,7 +450,7 @@ int launch_k4_ring(const BstDev &t, const BstLayout &bl, const double *Theta, in
   if (const char *e = getenv("LMPC_K4_PARK")) park = atoi(e);
 #define K4R_GO(NUU)                                                                                             \
   {                                                                                                             \
-    auto kern = bst_eval_ring_kernel<NTH, NUU>;                                                                 \
+    auto kern = (N < (1ll << 31) - 64 && !getenv("LMPC_K4_INDEX64")) ? bst_eval_ring_kernel<NTH, NUU, int32_t> : bst_eval_ring_kernel<NTH, NUU, int64_t>; \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     if (e != cudaSuccess) return (int)e;                                                                        \
     kern<<<(unsigned)blocks, K4R_BLOCK, smem, s>>>(t.blk, bl, t.nu, t.has_clip, Theta, N, U, region, park);      \
