@@ -369,6 +369,9 @@ int lmpc_gpu_create_bst_oriented(const double *halfplanes, int32_t n_hp, const d
                                  int32_t n_nodes, const double *clipping, int32_t nth, int32_t nu,
                                  int32_t le_child, int device, lmpc_bst **out);
 int lmpc_gpu_destroy_bst(lmpc_bst *t);
+/* Diagnostics: which evaluate kernel this tree gets (0 = generic fp64 rows, 1 = fp32-screened walk, 2 = fp32-screened
+ * lane-refill ring); no reference counterpart (ParametricDAQP.evaluate is one scalar loop, src/utils.jl:57). */
+int lmpc_gpu_bst_kernel(const lmpc_bst *t);
 /* Replaces ParametricDAQP.evaluate(bst, theta) (src/utils.jl:57) / {fname}_evaluate
  * (src/codegen.jl:113-124) for N parameters.  region (nullable) receives the leaf's region id. */
 int lmpc_gpu_evaluate_batch(lmpc_bst *t, const double *Theta, int64_t N, double *U,

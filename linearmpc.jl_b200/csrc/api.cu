@@ -1055,6 +1055,8 @@ int lmpc_gpu_destroy_bst(lmpc_bst *t) {
   return 0;
 }
 
+int lmpc_gpu_bst_kernel(const lmpc_bst *t) { return t ? bst_eval_kind(t->dev) : -1; }
+
 int lmpc_gpu_evaluate_batch_async(lmpc_bst *t, const double *Theta, int64_t N, double *U,
                                   int32_t *region, void *stream) {
   if (!t || !Theta || !U || N < 0) return set_err(LMPC_E_INVALID, "lmpc_gpu_evaluate_batch_async: bad argument%s");

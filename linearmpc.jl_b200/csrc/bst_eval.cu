@@ -485,16 +485,28 @@ int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_
   return (int)cudaGetLastError();
 }
 
+}  // namespace
+// which evaluate kernel a tree gets (16-byte aligned Theta): 0 = fp64 rows (generic), 1 = fp32-screened walk, 32 theta per
+// warp in lockstep, 2 = fp32-screened lane-refill ring (K4r)
+int bst_eval_kind(const BstDev &t) {
+  if (!(K4_SCREEN && t.nth >= 1 && t.nth <= 16 && t.quads > 0 && t.packed && (size_t)t.staged * sizeof(double) <= 165 * 1024))
+    return 0;
+  if (K4_RING && t.rep == 8 &&
+      (size_t)t.staged * sizeof(double) + (size_t)K4R_BLOCK * 2 * t.nth * sizeof(double) <= 225 * 1024)
+    return 2;
+  return 1;
+}
+namespace {
+
 template <int NTH>
 int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
               int32_t *region, int sm_count, cudaStream_t s) {
   // the fp32 screen needs compile-time nth, 32-bit node words and its staged prefix in shared memory
   if constexpr (NTH > 0) {
-    if (K4_SCREEN && bl.quads > 0 && bl.packed && (size_t)bl.staged * sizeof(double) <= 165 * 1024) {
+    const int kind = bst_eval_kind(t);
+    if (kind >= 1) {
       // lane-refill ring: 8 replicas, room for two theta tiles per warp, TMA-aligned Theta
-      if (K4_RING && bl.rep == 8 && (reinterpret_cast<uintptr_t>(Theta) & 15u) == 0 &&
-          (size_t)bl.staged * sizeof(double) + (size_t)K4R_BLOCK * 2 * NTH * sizeof(double) <= 225 * 1024 &&
-          !getenv("LMPC_K4_NO_RING"))
+      if (kind == 2 && (reinterpret_cast<uintptr_t>(Theta) & 15u) == 0 && !getenv("LMPC_K4_NO_RING"))
         return launch_k4_ring<NTH>(t, bl, Theta, N, U, region, sm_count, s);
       return launch_k4s<NTH, true, true, true>(t, bl, Theta, N, U, region, sm_count, s);
     }

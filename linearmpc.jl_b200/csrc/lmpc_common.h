@@ -122,6 +122,7 @@ struct BstDev {
   int pairs, rep, packed;                    // 16-byte pairs per row, table replicas, 32-bit node records
   int nth, nu, n_hp, n_fb, n_nodes, has_clip;
 };
+int bst_eval_kind(const BstDev &t);
 int launch_bst_eval(const BstDev &t, const double *Theta, int64_t N, double *U, int32_t *region,
                     int sm_count, void *stream);
 // closed loop with the explicit law; dyn = [F | G | Gd] row-major on the device; all pointers device

@@ -94,6 +94,7 @@ def load_library():
     L.lmpc_gpu_create_bst.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, C.c_int,
                                       C.POINTER(vp)]
     L.lmpc_gpu_destroy_bst.argtypes = [vp]
+    L.lmpc_gpu_bst_kernel.argtypes = [vp]
     L.lmpc_gpu_simulate_bst_batch.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, i32,
                                               vp, vp, vp]
     L.lmpc_gpu_evaluate_batch.argtypes = [vp, vp, i64, vp, vp]
@@ -900,6 +901,11 @@ class GpuExplicitMPC:
             raise ValueError("branch orientation not found in the file: pass le_child = 0 or 1")
         return cls(t["halfplanes"], t["feedbacks"], t["hp_list"], t["jump_list"], clipping=clipping, dims=dims,
                    device=device, le_child=lc)
+
+    @property
+    def kernel(self):
+        """Evaluate kernel of this tree: 0 generic fp64 rows, 1 fp32-screened walk, 2 fp32-screened lane-refill ring."""
+        return int(lib().lmpc_gpu_bst_kernel(self._t)) if getattr(self, "_t", None) else -1
 
     def close(self):
         if getattr(self, "_t", None) is not None and self._t:

@@ -375,3 +375,62 @@ def test_parametricdaqp_codegen_arrays_round_trip(lmpc, tmp_path):
     samp = os.path.join(os.path.dirname(GOLD), "pdaqp_sample.c")
     ts = ex.load_pdaqp_codegen(samp)
     assert ts["le_child"] == 1 and ts["halfplanes"].shape[1] == ts["nth"] + 1 and len(ts["hp_list"]) == len(ts["jump_list"])
+
+
+def _random_tree(rng, nth, nu, n_hp, depth, p_leaf=0.25):
+    """Random binary search tree in the ParametricDAQP layout (children of node i at i + jump, i + jump + 1;
+    jump == 0 marks a leaf, whose index names the affine law)."""
+    hp = rng.normal(size=(n_hp, nth + 1))
+    hp[:, -1] *= 0.3
+    nodes = []                                  # [jump, index] in breadth-first order
+
+    def grow():
+        queue = [(0, 0)]
+        nodes.append([0, 0])
+        n_fb = 0
+        while queue:
+            i, d = queue.pop(0)
+            if d >= depth or (d > 0 and rng.random() < p_leaf):
+                nodes[i] = [0, n_fb]
+                n_fb += 1
+                continue
+            nodes[i] = [len(nodes) - i, int(rng.integers(n_hp))]
+            nodes.append([0, 0]); nodes.append([0, 0])
+            queue.append((len(nodes) - 2, d + 1)); queue.append((len(nodes) - 1, d + 1))
+        return n_fb
+    n_fb = grow()
+    fb = rng.normal(size=(n_fb, nu, nth + 1))
+    nd = np.array(nodes, np.int32)
+    return hp, fb, nd[:, 1].copy(), nd[:, 0].copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nth,nu,depth", [(1, 1, 3), (3, 2, 9), (7, 1, 14), (8, 3, 6), (10, 2, 5), (12, 2, 10), (16, 1, 7), (5, 1, 0)])
+def test_gpu_evaluate_random_trees_ragged_batches_and_band_hits(lmpc, nth, nu, depth):
+    """The lane-refill ring kernel (bst_eval.cu, K4r) on trees it was not tuned on: every nth up to 16, one / two /
+    run-time output counts, a leaf root, unbalanced depths, batch sizes around the 32-theta tile, theta that sit ON
+    half-planes (inside the fp32 screen's error band: decided by the fp64 re-walk) and non-finite theta (NaN
+    compares false everywhere: the walk must still end and agree with the oracle's).  Bit-exact against the oracle."""
+    rng = np.random.default_rng(100 * nth + nu)
+    hp, fb, hl, jl = _random_tree(rng, nth, nu, n_hp=37, depth=depth, p_leaf=0.3 if depth > 10 else 0.25)
+    clip = np.vstack([-0.7 * np.ones(nu), 0.9 * np.ones(nu)]).T.copy() if nu < 3 else None
+    B = ldp.OracleBst(hp, fb, hl, jl, clip=clip)
+    g = lmpc.GpuExplicitMPC(hp, fb, hl, jl, clipping=clip)
+    # the ring needs 8 table replicas and two theta tiles per warp next to the tables: big nth / many laws fall back
+    if nth <= 10:
+        assert g.kernel == 2, g.kernel
+    for N in (1, 31, 32, 33, 1000, 65 * 1024 + 17, 1_000_003):
+        Th = rng.normal(size=(nth, N))
+        if N >= 1000:
+            # project some theta onto a half-plane of the tree: a'theta - b == 0 up to rounding
+            for q in range(0, N, 7):
+                a, b = hp[q % len(hp), :-1], hp[q % len(hp), -1]
+                Th[:, q] -= a * ((a @ Th[:, q] - b) / (a @ a))
+            Th[0, 5] = np.nan
+            Th[nth - 1, 6] = np.inf
+            Th[0, 8] = -np.inf
+            Th[:, 9] = 1e300
+        U, reg = g.evaluate(np.asfortranarray(Th))
+        Uo, rego = B.evaluate_batch(Th)
+        assert np.array_equal(reg, rego), (N, int((reg != rego).sum()))
+        assert np.array_equal(U, Uo, equal_nan=True), N
