@@ -553,7 +553,9 @@ def measure(name, dev_index, rank, world, dist, torch, steps, warmup, cpu_baseli
         ach = bytes_per * b.n / (kernel_ms * 1e-3) / 1e9
         cfg.update({"nth": b.nin, "tree_nodes": nodes})
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic_of(name), "kernel": "bst_eval_kernel<%d>" % b.nin, "kernel_ms": kernel_ms,
+                "traffic": traffic_of(name), "kernel": {2: "bst_eval_ring_kernel<%d,%d> (fp32-screened lane-refill ring)", 1: "bst_eval_kernel<%d> (fp32-screened, nu %d)",
+                           0: "bst_eval_kernel<%d> (fp64 rows, nu %d)"}.get(b.g.kernel, "bst_eval_kernel<%d,%d>") % (b.nin, b.nu),
+                "kernel_ms": kernel_ms,
                 "bytes_per_theta": bytes_per, "peak_source": peak_src}
     else:
         fp64_peak = lmpc_b200.fp64_peak_tflops(dev_index)

@@ -1,7 +1,11 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_explicit.py -m gpu -x -q 2>&1 | tail -3
-LMPC_K4_INDEX64=1 timeout 300 python -m pytest tests/test_explicit.py -m gpu -x -q 2>&1 | tail -3
-run() { timeout 200 python bench.py --workload explicit_invpend_1e8 --no-cpu-baseline --no-secondary 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('$1', d['value'], d['ms_per_step'], d['roofline']['frac'], d.get('parity'))"; }
-run main; run main
-LMPC_K4_INDEX64=1 run idx64
-for p in 4 6 10 12; do LMPC_K4_PARK=$p run park$p; done
+for v in "" bcu16 bcu32 il1 il1bcu16; do
+  if [ -n "$v" ]; then export LMPC_GPU_LIB=$PWD/build_variants/lib$v.so; fi
+  echo "== $v"; timeout 300 python tests/tools/bench_configs.py chain 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d = json.loads(l)
+    except Exception: continue
+    print({k: d[k] for k in d if k in ('config','theta_scale','N','solves_per_s','gpu_solves_per_s','cold_solves_per_s','mean_iters','bit_identical','flags','ms')} or d)
+"
+done
