@@ -213,9 +213,6 @@ bst_eval_kernel(const double *__restrict__ blk, BstLayout bl, int nth_rt, int nu
 #ifndef K4R_REP_IDS
 #define K4R_REP_IDS 0         // > 0: node ids below this pick the half-plane replica by node id (broadcast reads near the root)
 #endif
-#ifndef K4R_BLOCK
-#define K4R_BLOCK 1024
-#endif
 #ifndef K4_PARK
 #define K4_PARK 8            // a round's walk ends once this many lanes or fewer are still walking
 #endif
@@ -235,14 +232,15 @@ LMPC_DEVINL uint32_t lds_u32(uint32_t a) {
   return v;
 }
 
-template <int NTH, int NU, typename QI>   // NU: outputs (0 = run-time count); QI: theta index type (int32_t while N < 2^31)
-__global__ void __launch_bounds__(K4R_BLOCK, 1)
+template <int NTH, int NU, typename QI, int BLK>   // NU: outputs (0 = run-time count); QI: theta index type (int32_t while
+                                                    // N < 2^31); BLK: threads per CTA (1024, or 512 when the ring of a wide theta needs room)
+__global__ void __launch_bounds__(BLK, 1)
 bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, int has_clip,
                      const double *__restrict__ Theta, int64_t N, double *__restrict__ U,
                      int32_t *__restrict__ region, int park) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ __align__(8) uint64_t tbar[K4R_BLOCK / 32][2];
+  __shared__ __align__(8) uint64_t tbar[BLK / 32][2];
   stage_constants_tma(smem, blk, bl.staged, &mbar);
   constexpr int TH = NTH, Q4 = (TH + 4) / 4, P2 = (TH + 2) / 2, REP = 8;
   constexpr uint32_t HROW = Q4 * REP * 16, FROW = P2 * REP * 16;      // bytes per replicated row
@@ -358,7 +356,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
 
   // this warp's stream: the full tiles t0, t0 + ts, ... of Theta (tile = 32 theta = 32 * TH * 8 contiguous bytes)
   const int64_t nt_full = N >> 5;
-  const int64_t t0 = (int64_t)blockIdx.x * (K4R_BLOCK / 32) + warp, ts = (int64_t)gridDim.x * (K4R_BLOCK / 32);
+  const int64_t t0 = (int64_t)blockIdx.x * (BLK / 32) + warp, ts = (int64_t)gridDim.x * (BLK / 32);
   const uint32_t ntw = t0 < nt_full ? (uint32_t)((nt_full - t0 + ts - 1) / ts) : 0u;
   const uint32_t total = ntw * 32u;
   double *ring = smem + bl.staged + (size_t)warp * 64 * TH;
@@ -440,20 +438,29 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
   }
 }
 
-template <int NTH>
+// threads per CTA of the ring kernel for this tree: 1024 when the tables and two theta tiles per warp fit, else 512, else 0
+static int k4_ring_block(const BstDev &t) {
+  if (!(K4_RING && t.rep == 8 && t.nth >= 1 && t.nth <= 16)) return 0;
+  for (int blk = 1024; blk >= 512; blk >>= 1)
+    if ((size_t)t.staged * sizeof(double) + (size_t)blk * 2 * t.nth * sizeof(double) <= 225 * 1024) return blk;
+  return 0;
+}
+
+template <int NTH, int BLK>
 int launch_k4_ring(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t N, double *U,
                    int32_t *region, int sm_count, cudaStream_t s) {
-  const size_t smem = (size_t)bl.staged * sizeof(double) + (size_t)K4R_BLOCK * 2 * NTH * sizeof(double);
-  int64_t blocks = (N + K4R_BLOCK - 1) / K4R_BLOCK;
+  const size_t smem = (size_t)bl.staged * sizeof(double) + (size_t)BLK * 2 * NTH * sizeof(double);
+  int64_t blocks = (N + BLK - 1) / BLK;
   if (blocks > sm_count) blocks = sm_count;
   int park = K4_PARK;
   if (const char *e = getenv("LMPC_K4_PARK")) park = atoi(e);
+  const bool small = N < (1ll << 31) - 64 && !getenv("LMPC_K4_INDEX64");
 #define K4R_GO(NUU)                                                                                             \
   {                                                                                                             \
-    auto kern = (N < (1ll << 31) - 64 && !getenv("LMPC_K4_INDEX64")) ? bst_eval_ring_kernel<NTH, NUU, int32_t> : bst_eval_ring_kernel<NTH, NUU, int64_t>; \
+    auto kern = small ? bst_eval_ring_kernel<NTH, NUU, int32_t, BLK> : bst_eval_ring_kernel<NTH, NUU, int64_t, BLK>; \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     if (e != cudaSuccess) return (int)e;                                                                        \
-    kern<<<(unsigned)blocks, K4R_BLOCK, smem, s>>>(t.blk, bl, t.nu, t.has_clip, Theta, N, U, region, park);      \
+    kern<<<(unsigned)blocks, BLK, smem, s>>>(t.blk, bl, t.nu, t.has_clip, Theta, N, U, region, park);           \
     return (int)cudaGetLastError();                                                                             \
   }
   if (t.nu == 1) K4R_GO(1)
@@ -491,8 +498,7 @@ int launch_k4s(const BstDev &t, const BstLayout &bl, const double *Theta, int64_
 int bst_eval_kind(const BstDev &t) {
   if (!(K4_SCREEN && t.nth >= 1 && t.nth <= 16 && t.quads > 0 && t.packed && (size_t)t.staged * sizeof(double) <= 165 * 1024))
     return 0;
-  if (K4_RING && t.rep == 8 &&
-      (size_t)t.staged * sizeof(double) + (size_t)K4R_BLOCK * 2 * t.nth * sizeof(double) <= 225 * 1024)
+  if (k4_ring_block(t) > 0)
     return 2;
   return 1;
 }
@@ -507,7 +513,8 @@ int launch_k4(const BstDev &t, const BstLayout &bl, const double *Theta, int64_t
     if (kind >= 1) {
       // lane-refill ring: 8 replicas, room for two theta tiles per warp, TMA-aligned Theta
       if (kind == 2 && (reinterpret_cast<uintptr_t>(Theta) & 15u) == 0 && !getenv("LMPC_K4_NO_RING"))
-        return launch_k4_ring<NTH>(t, bl, Theta, N, U, region, sm_count, s);
+        return k4_ring_block(t) == 1024 ? launch_k4_ring<NTH, 1024>(t, bl, Theta, N, U, region, sm_count, s)
+                                        : launch_k4_ring<NTH, 512>(t, bl, Theta, N, U, region, sm_count, s);
       return launch_k4s<NTH, true, true, true>(t, bl, Theta, N, U, region, sm_count, s);
     }
   }

@@ -417,8 +417,8 @@ def test_gpu_evaluate_random_trees_ragged_batches_and_band_hits(lmpc, nth, nu, d
     B = ldp.OracleBst(hp, fb, hl, jl, clip=clip)
     g = lmpc.GpuExplicitMPC(hp, fb, hl, jl, clipping=clip)
     # the ring needs 8 table replicas and two theta tiles per warp next to the tables: big nth / many laws fall back
-    if nth <= 10:
-        assert g.kernel == 2, g.kernel
+    if (nth, nu, depth) != (12, 2, 10):
+        assert g.kernel == 2, g.kernel                  # nth = 16 runs the ring with 512-thread CTAs
     for N in (1, 31, 32, 33, 1000, 65 * 1024 + 17, 1_000_003):
         Th = rng.normal(size=(nth, N))
         if N >= 1000:
