@@ -229,3 +229,37 @@ def test_certified_iteration_bound_sizes_the_kernel(lmpc):
     Th = mpqp.sample_theta(lo, hi, 200, seed=8)
     out, ref = g.solve(Th), P.solve_batch(Th)
     assert np.array_equal(out["exitflag"], ref["flag"]) and np.all(out["exitflag"] == -4)
+
+
+def test_chain_full_step_size_properties(lmpc):
+    """BASELINE config 4 at the size of one bench step (1e5 chain-of-masses QPs, n = 180, s = 1; the config's 1e6 are ten
+    such steps): every instance optimal, the applied control within its bounds, both passes of the two-pass CTA scheme
+    used, idempotent, device path == chunked host path, and a 1000-instance subsample equal to the oracle bit for bit
+    (exit flag, iteration count, active set, u)."""
+    import torch
+    mpc, qp, g, P = gpu_controller(lmpc, "chain")
+    lo, hi = util.theta_range("chain", 1.0)
+    N = 100_000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4321)
+    Th = torch.rand((N, len(lo)), dtype=torch.float64, device="cuda", generator=gen)
+    Th = Th * torch.tensor(hi - lo, device="cuda") + torch.tensor(lo, device="cuda")
+    before = g.tiering()[1]
+    a = g.solve(Th)
+    assert bool((a["exitflag"] == 1).all())
+    assert g.tiering()[1] > before                              # some working sets outgrow the reduced capacity
+    umin, umax = np.asarray(mpc.umin, float), np.asarray(mpc.umax, float)
+    U = a["U"].cpu().numpy()
+    assert np.all(U >= umin[:, None] - 1e-6) and np.all(U <= umax[:, None] + 1e-6)
+    b = g.solve(Th)
+    assert bool((a["U"] == b["U"]).all()) and bool((a["iters"] == b["iters"]).all())
+    sub = Th[:20_000].cpu().numpy().T
+    host = g.solve(np.asfortranarray(sub), want_active=False)
+    assert np.array_equal(host["U"], U[:, :20_000])
+    idx = torch.randperm(N, device="cuda")[:1000]
+    ref = P.solve_batch(Th[idx].cpu().numpy().T)
+    assert np.array_equal(U[:, idx.cpu().numpy()], ref["U"])
+    for k, r in (("exitflag", "flag"), ("iters", "iters")):
+        assert np.array_equal(a[k][idx].cpu().numpy(), ref[r]), k
+    assert np.array_equal(a["active_upper"][idx].cpu().numpy(), ref["act_u"])
+    assert np.array_equal(a["active_lower"][idx].cpu().numpy(), ref["act_l"])
