@@ -371,6 +371,7 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
     if (ntw > 0) tile_issue(&tbar[warp][0], ring, Theta + t0 * 32 * TH, 32u * TH * 8u);
     if (ntw > 1) tile_issue(&tbar[warp][1], ring + 32 * TH, Theta + (t0 + ts) * 32 * TH, 32u * TH * 8u);
   }
+  const double *next_src = Theta + (t0 + 2 * ts) * 32 * TH;     // source of the next tile to request (third of the stream)
   uint32_t head = 0;          // theta of the stream handed to lanes so far (warp-uniform)
   uint32_t landed = 0;        // tiles of the stream waited for so far (warp-uniform)
   const unsigned lt = (1u << lane) - 1u;
@@ -399,8 +400,10 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
       // a tile whose 32 theta are all in registers frees its half of the ring for the tile two ahead
       // (a refill hands out at most 32 theta, so at most one tile boundary is crossed)
       const uint32_t j = head >> 5;
-      if ((nhead >> 5) != j && j + 2u < ntw && lane == 0)
-        tile_issue(&tbar[warp][j & 1u], ring + (size_t)(j & 1u) * 32 * TH, Theta + (t0 + (int64_t)(j + 2u) * ts) * 32 * TH, 32u * TH * 8u);
+      if ((nhead >> 5) != j && j + 2u < ntw) {
+        if (lane == 0) tile_issue(&tbar[warp][j & 1u], ring + (size_t)(j & 1u) * 32 * TH, next_src, 32u * TH * 8u);
+        next_src += ts * (32 * TH);
+      }
       head = nhead;
     }
     if (__ballot_sync(0xffffffffu, q >= 0) == 0u) break;
@@ -410,8 +413,14 @@ bst_eval_ring_kernel(const double *__restrict__ blk, BstLayout bl, int nu_rt, in
     const int lim = head < total ? park : 0;
     int ns = 0;
 #pragma unroll 1
-    for (; ns < pre; ++ns)
+    for (; ns + 2 <= pre; ns += 2) {
       if (w >= 0x10000u) step();
+      if (w >= 0x10000u) step();
+    }
+    if (ns < pre) {
+      if (w >= 0x10000u) step();
+      ++ns;
+    }
     while (true) {
       const bool in = w >= 0x10000u;
       if (__popc(__ballot_sync(0xffffffffu, in)) <= lim) break;
