@@ -261,5 +261,5 @@ def test_chain_full_step_size_properties(lmpc):
     assert np.array_equal(U[:, idx.cpu().numpy()], ref["U"])
     for k, r in (("exitflag", "flag"), ("iters", "iters")):
         assert np.array_equal(a[k][idx].cpu().numpy(), ref[r]), k
-    assert np.array_equal(a["active_upper"][idx].cpu().numpy(), ref["act_u"])
-    assert np.array_equal(a["active_lower"][idx].cpu().numpy(), ref["act_l"])
+    assert np.array_equal(a["active_upper"][idx].cpu().numpy().view(np.uint64), ref["act_u"])   # int64 tensor: same bits
+    assert np.array_equal(a["active_lower"][idx].cpu().numpy().view(np.uint64), ref["act_l"])
