@@ -235,9 +235,10 @@ LMPC_DEVINL void box_iter_static(BoxState<N> &s, const ConstView &cv, const BC &
 // code with compile-time loop bounds and slots -- no generic loop, no "which slot" selects, no lam /
 // lam* / D kept between iterations, and the forward sweep of the CSP solve collapses to the one new
 // entry of z (z_0..z_{K-2} are the same fma chains as in the previous iteration).  An instance whose
-// multipliers block is handed over (flag EXIT_REDO_BOX, nothing else written) to the second launch:
-// the generic kernel in REDO mode, which compacts the handed-over instances per CTA and solves them
-// from scratch.  Same operations in the same order as the generic iteration -> bit-identical.
+// multipliers block is handed over to the second launch through its CTA's queue (a shared-memory counter and
+// a stream-ordered global scratch; nothing is written to the caller's arrays): the generic kernel in REDO
+// mode solves the queued instances from scratch.  Same operations in the same order as the generic
+// iteration -> bit-identical.
 // ---------------------------------------------------------------------------------------------
 constexpr int EXIT_REDO_BOX = -100;   // internal, never seen by the caller
 
@@ -443,23 +444,47 @@ LMPC_DEVINL BoxSmem<N, NU, CP> box_prologue(double *smem, uint64_t *mbar, uint64
   return b;
 }
 
+// instances a CTA of a persistent grid of `nblocks` CTAs can own: passes of KB_BLOCK instances, rounded up
+__host__ __device__ inline int64_t box_percta(int64_t Ninst, int nblocks) {
+  const int64_t passes = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
+  return (passes + nblocks - 1) / nblocks * KB_BLOCK;
+}
+
 template <int N, int NU, int MINB, bool CP>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
                     const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-                    SolveOut out, int flags, int32_t *rflag) {
+                    SolveOut out, int flags, int32_t *hq) {
   const bool use_tiles = flags & 1;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t tbar[KB_BLOCK / 32];
+  __shared__ int hcnt;                    // instances this CTA has handed over so far
+  if (threadIdx.x == 0) hcnt = 0;         // (the prologue ends with a __syncthreads)
   const BoxSmem<N, NU, CP> b = box_prologue<N, NU, CP>(smem, &mbar, tbar, lay, cblk, th, Ninst, use_tiles);
+  // hand-over queues: hq = [count per fast CTA (gridDim.x) | gridDim.x queues of (flags >> 1) * KB_BLOCK instance ids]
+  // (nothing about them is kept in registers across a solve: the queue address is rebuilt on the rare path)
   const ConstView &cv = b.cv;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t qstride = (int64_t)gridDim.x * KB_BLOCK;
   uint32_t tphase = 0;
   const int nth = lay.nth;
   double *bnd = b.end + (use_tiles ? (size_t)KB_BLOCK * nth : 0) + threadIdx.x;
+  int pend = -1;                          // instance handed over in the previous pass, not yet queued
+  auto push = [&](unsigned act) {         // one shared-memory atomic per warp and pass that has hand-overs (2 % of the threads)
+    const unsigned bal = __ballot_sync(act, pend >= 0);
+    if (bal) {
+      const int leader = __ffs(bal) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&hcnt, __popc(bal));
+      base = __shfl_sync(act, base, leader);
+      if (pend >= 0)
+        hq[gridDim.x + (size_t)blockIdx.x * ((size_t)(flags >> 1) * KB_BLOCK) + base + __popc(bal & ((1u << lane) - 1u))] = pend;
+      pend = -1;
+    }
+  };
   for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst; q += qstride) {
+    push(__activemask());
     double sh[N], sho[NU];
     box_theta_pass<N, NU, CP>(cv, b.Cp, b.tile, &tbar[warp], tphase, th, nth, q, lane, qstride, Ninst, use_tiles, sh, sho);
     double dU[N], dLo[N];
@@ -496,10 +521,10 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
         fast_chain<N, 1>(s, cv, bc, b.Mp, st, bnd, u, best_fval, cycle, flag, iter);
       }
     }
-    // hand-over marks go to rflag when the caller's flag array is remote (a peer GPU's result window): the REDO
-    // launch then scans local memory instead of reading N flags back over NVLink
-    if (rflag) rflag[q] = flag;
-    if (flag == EXIT_REDO_BOX) { if (!rflag) out.flag[q] = flag; continue; }
+    // hand-over: nothing is written to the caller's arrays, the REDO launch solves the instance from scratch.  The id is
+    // parked in a register and pushed at the top of the next pass, where the warp is converged again (pushing here, inside
+    // the divergent exit, made the early lanes run the next pass's prologue on their own: +8 % instructions).
+    if (flag == EXIT_REDO_BOX) { pend = (int)q; continue; }
     SFOR(i, 0, NU)
       double pr[N];
       SFOR(c, 0, N) pr[c] = __dmul_rn(bc.Rinv[i * N + c], u[c]); SEND
@@ -520,20 +545,22 @@ ldp_box_fast_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxCo
       out.act_l[q] = al;
     }
   }
+  push(__activemask());
+  __syncthreads();
+  if (threadIdx.x == 0) hq[blockIdx.x] = hcnt;
 }
 
-// REDO = true: the second launch behind the add-only fast kernel.  Every CTA owns a contiguous range of
-// instances, compacts the ones the fast kernel handed over (flag == EXIT_REDO_BOX) into a shared-memory
-// queue (coalesced flag reads, one ballot per warp and step) and solves them 128 at a time from scratch,
-// so the lanes stay full although only ~2 % of the batch comes back.
-constexpr int KB_SCAN = 16 * KB_BLOCK;   // flags examined per fill step
-constexpr int KB_QCAP = 2 * KB_SCAN;     // queue entries per CTA (int32 offsets into the CTA's range)
-static_assert(KB_QCAP >= KB_SCAN, "a fill step must fit into an empty queue");
+// REDO = true: the second launch behind the add-only fast kernel.  The fast kernel's CTAs leave the instances they
+// handed over in per-CTA queues (hq: counts, then one queue of local indices per fast CTA; `flags` = number of fast
+// CTAs); every CTA here takes the queues c = blockIdx.x, blockIdx.x + gridDim.x, ... and solves their entries from
+// scratch 128 at a time, so the lanes stay full although only ~2 % of the batch comes back.  (First r02 version: the
+// fast kernel marked the flag array and this launch re-read all N flags and compacted them per CTA -- 40 MB of DRAM
+// reads and 62 us per 1e7-instance step; with the queues the launch only touches what it solves.)
 template <int N, int NU, int MINB, bool CP = false, bool REDO = false>
 __global__ void __launch_bounds__(KB_BLOCK, MINB)
 ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N, NU> bc,
                const double *__restrict__ cblk, const __grid_constant__ ThetaSegs th, int64_t Ninst,
-               SolveOut out, int flags, int32_t *rflag) {
+               SolveOut out, int flags, int32_t *hq) {
   const bool use_tiles = !REDO && (flags & 1);
   constexpr bool use_cp = CP;   // compile-time: with both loops in one kernel the gain on short theta is lost
   extern __shared__ __align__(16) double smem[];
@@ -694,41 +721,12 @@ ldp_box_kernel(LdpLayout lay, LdpSettings st, const __grid_constant__ BoxConst<N
   if constexpr (!REDO) {
     for (int64_t q = (int64_t)blockIdx.x * KB_BLOCK + threadIdx.x; q < Ninst; q += qstride) solve_one(q);
   } else {
-    int *queue = reinterpret_cast<int *>(bsm.end);
-    __shared__ int qn;
-    // contiguous range per CTA, a multiple of the block size
-    const int64_t per = ((Ninst + gridDim.x - 1) / gridDim.x + KB_SCAN - 1) / KB_SCAN * KB_SCAN;
-    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = (r0 + per < Ninst) ? r0 + per : Ninst;
-    int64_t pos = r0;
-    while (pos < r1) {
-      if (threadIdx.x == 0) qn = 0;
-      __syncthreads();
-      // fill: KB_SCAN flags per step (the loads of a step are all in flight together: a 128-flag step was
-      // one exposed DRAM latency each, 144 us per launch), stop when another step might not fit
-      int filled = 0;
-      while (pos < r1 && filled <= KB_QCAP - KB_SCAN) {
-        int fl[KB_SCAN / KB_BLOCK];
-#pragma unroll
-        for (int j = 0; j < KB_SCAN / KB_BLOCK; ++j) {
-          const int64_t q = pos + j * KB_BLOCK + threadIdx.x;
-          fl[j] = q < r1 ? (rflag ? rflag[q] : out.flag[q]) : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < KB_SCAN / KB_BLOCK; ++j) {
-          const bool mine = fl[j] == EXIT_REDO_BOX;
-          const unsigned bal = __ballot_sync(0xffffffffu, mine);
-          int base = 0;
-          if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (mine) queue[base + __popc(bal & ((1u << lane) - 1u))] = (int)(pos + j * KB_BLOCK + threadIdx.x - r0);
-        }
-        pos += KB_SCAN;
-        __syncthreads();
-        filled = qn;
-        __syncthreads();
-      }
-      for (int i = threadIdx.x; i < filled; i += KB_BLOCK) solve_one(r0 + queue[i]);
-      __syncthreads();
+    const int nfast = flags;                                  // CTAs of the fast launch
+    const int64_t percta = box_percta(Ninst, nfast);
+    for (int cq = blockIdx.x; cq < nfast; cq += gridDim.x) {
+      const int cnt = hq[cq];
+      const int32_t *qv = hq + nfast + (size_t)cq * percta;
+      for (int i = threadIdx.x; i < cnt; i += KB_BLOCK) solve_one((int64_t)qv[i]);
     }
   }
 }
@@ -757,7 +755,8 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   // LMPC_BOX_FAST_MIN_BATCH overrides the threshold (tests and sanitizer runs push small batches through both launches)
   const char *env_min = getenv("LMPC_BOX_FAST_MIN_BATCH");
   const int64_t min_batch = env_min ? atoll(env_min) : (int64_t)KB_FAST_MIN_BATCH;
-  const bool fast = KB_FAST && st.iter_limit > N + 2 && Ninst >= min_batch;
+  // (instance ids travel through the hand-over queues as 32-bit integers)
+  const bool fast = KB_FAST && st.iter_limit > N + 2 && Ninst >= min_batch && Ninst < (1ll << 31) - 1;
   constexpr int FMINB = N <= 5 ? KB_FAST_MINB : 2;
   using kern_t = void (*)(LdpLayout, LdpSettings, const BoxConst<N, NU>, const double *, const ThetaSegs, int64_t,
                           SolveOut, int, int32_t *);
@@ -794,30 +793,42 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   int64_t blocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   const int64_t cap = (int64_t)sm_count * per_sm;   // persistent: whole resident waves over the SMs
   if (blocks > cap) blocks = cap;
-  // caller's flag array on another device (peer window)?  keep the hand-over marks in a stream-ordered local scratch
-  int32_t *rflag = nullptr;
+  // hand-over queues of the fast kernel's CTAs (stream-ordered scratch, kept in the pool between calls)
+  int32_t *hq = nullptr;
   if (fast) {
-    cudaPointerAttributes pa;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (cudaPointerGetAttributes(&pa, out.flag) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != dev) {
-      static bool pool_kept[64] = {false};
-      if (dev < 64 && !pool_kept[dev]) {   // keep freed scratch in the pool instead of returning it to the OS every call
-        cudaMemPool_t mp;
-        unsigned long long keep = ~0ull;
-        if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
-        pool_kept[dev] = true;
-      }
-      if (cudaMallocAsync((void **)&rflag, (size_t)Ninst * sizeof(int32_t), stream) != cudaSuccess) rflag = nullptr;
+    static bool pool_kept[64] = {false};
+    if (dev < 64 && !pool_kept[dev]) {   // keep freed scratch in the pool instead of returning it to the OS every call
+      cudaMemPool_t mp;
+      unsigned long long keep = ~0ull;
+      if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+      pool_kept[dev] = true;
     }
-    cudaGetLastError();
+    const size_t words = (size_t)blocks * (1 + (size_t)box_percta(Ninst, (int)blocks));
+    if (cudaMallocAsync((void **)&hq, words * sizeof(int32_t), stream) != cudaSuccess) {
+      // no scratch: the generic kernel alone
+      cudaGetLastError();
+      hq = nullptr;
+      kern_t gk = (kern_t)ldp_box_kernel<N, NU, MINB, false>;
+      cudaError_t e2 = cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base);
+      if (e2 != cudaSuccess) return (int)e2;
+      int ps = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, gk, KB_BLOCK, smem_base);
+      if (ps < 1) ps = 1;
+      int64_t gb = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
+      if (gb > (int64_t)sm_count * ps) gb = (int64_t)sm_count * ps;
+      gk<<<(unsigned)gb, KB_BLOCK, smem_base, stream>>>(lay, st, bc, cblk, th, Ninst, out, 0, nullptr);
+      return (int)cudaGetLastError();
+    }
   }
-  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out, use_tiles, rflag);
+  const int kflags = use_tiles | (fast ? (int)(box_percta(Ninst, (int)blocks) / KB_BLOCK) << 1 : 0);
+  kern<<<(unsigned)blocks, KB_BLOCK, smem, stream>>>(lay, st, bc, cblk, th, Ninst, out, kflags, hq);
   e = cudaGetLastError();
-  if (e != cudaSuccess || !fast) { if (rflag) cudaFreeAsync(rflag, stream); return (int)e; }
-  // second launch: whatever the fast kernel handed over, compacted per CTA
+  if (e != cudaSuccess || !fast) { if (hq) cudaFreeAsync(hq, stream); return (int)e; }
+  // second launch: whatever the fast kernel's CTAs left in their queues
   kern_t redo = (kern_t)ldp_box_kernel<N, NU, MINB, false, true>;
-  const size_t smem_redo = smem_base + (size_t)KB_QCAP * sizeof(int);
+  const size_t smem_redo = smem_base;
   e = cudaFuncSetAttribute(redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_redo);
   if (e != cudaSuccess) return (int)e;
   per_sm = 0;
@@ -825,9 +836,10 @@ int launch_box(const LdpLayout &lay, const LdpSettings &st, const double *cblk, 
   if (per_sm < 1) per_sm = 1;
   int64_t rblocks = (Ninst + KB_BLOCK - 1) / KB_BLOCK;
   if (rblocks > (int64_t)sm_count * per_sm) rblocks = (int64_t)sm_count * per_sm;
-  redo<<<(unsigned)rblocks, KB_BLOCK, smem_redo, stream>>>(lay, st, bc, cblk, th, Ninst, out, 0, rflag);
+  if (rblocks > blocks) rblocks = blocks;
+  redo<<<(unsigned)rblocks, KB_BLOCK, smem_redo, stream>>>(lay, st, bc, cblk, th, Ninst, out, (int)blocks, hq);
   lmpc_count_kernel(1);
-  if (rflag) cudaFreeAsync(rflag, stream);
+  cudaFreeAsync(hq, stream);
   return (int)cudaGetLastError();
 }
 
