@@ -117,6 +117,40 @@ def test_box_fast_path_matches_oracle(lmpc, monkeypatch, name, scale, N):
         assert np.array_equal(out["U"], single["U"][:, :n]) and np.array_equal(out["exitflag"], single["exitflag"][:n])
 
 
+def test_box_fast_path_with_many_handovers(lmpc, monkeypatch):
+    """K1c's hand-over queues under load: invpend far outside its nominal range (s = 3), 1e6 instances, so that every
+    CTA of the persistent grid runs several passes and a large share of the instances block a multiplier and travel
+    through the queues to the REDO launch.  The two-launch path (default from 2e5 instances on) must equal the
+    single-launch generic kernel bit for bit, and a subsample the oracle."""
+    import torch
+    mpc, qp, g, P = gpu_controller(lmpc, "invpend")
+    lo, hi = util.theta_range("invpend", 3.0)
+    N = 1_000_003
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(99)
+    Th = torch.rand((N, len(lo)), dtype=torch.float64, device="cuda", generator=gen)
+    Th = Th * torch.tensor(hi - lo, device="cuda") + torch.tensor(lo, device="cuda")
+    launches = lmpc.launch_count()
+    fast = g.solve(Th)
+    assert lmpc.launch_count() - launches == 2
+    monkeypatch.setenv("LMPC_BOX_FAST_MIN_BATCH", str(10 ** 12))
+    launches = lmpc.launch_count()
+    single = g.solve(Th)
+    assert lmpc.launch_count() - launches == 1
+    for k in ("U", "exitflag", "iters", "active_upper", "active_lower"):
+        assert bool((fast[k] == single[k]).all()), k
+    # instances that removed a row needed more iterations than rows they ended with + 1: those were handed over
+    k_final = util.bits(single["active_upper"].cpu().numpy().view(np.uint64).reshape(N, -1), 5).sum(1) + \
+        util.bits(single["active_lower"].cpu().numpy().view(np.uint64).reshape(N, -1), 5).sum(1)
+    handed = (single["iters"].cpu().numpy() > k_final + 1) & (single["exitflag"].cpu().numpy() == 1)
+    assert handed.mean() > 0.03, handed.mean()
+    idx = torch.randperm(N, device="cuda")[:20_000]
+    ref = P.solve_batch(Th[idx].cpu().numpy().T)
+    assert np.array_equal(fast["U"][:, idx].cpu().numpy(), ref["U"])
+    assert np.array_equal(fast["exitflag"][idx].cpu().numpy(), ref["flag"])
+    assert np.array_equal(fast["iters"][idx].cpu().numpy(), ref["iters"])
+
+
 def test_box_kernel_is_what_runs_on_box_only_problems(lmpc):
     """the cases above really exercise K1b: box-only problems with n <= 8 select the thread kernel and
     the library takes its box fast path (lmpc_gpu_get_info reports the thread kernel, capacity n)."""
