@@ -991,6 +991,51 @@ LMPC_DEVINL void coop_sweep_bwd(const BigCtx &c, double *xs, int kk) {
   }
 }
 
+// The two L2-bound fma chains of the CTA kernel, blocked by B with the TAIL blocked as well.  `#pragma unroll B` alone
+// leaves up to B - 1 remainder iterations that run one load at a time: each exposes a full L2 latency (~600 cycles under
+// load), 3.5 of them on average per chain and iteration.  Here the remainder's loads are issued together (indices
+// clamped into range, the surplus fmas predicated off): same operations on the same operands in the same order.
+template <int B>
+LMPC_DEVINL double chain_scan(const double *__restrict__ mt, const double *uw, int cc, int n, int mp, double mu) {
+  for (; cc + B <= n; cc += B) {
+    double v[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) v[t] = mt[(size_t)t * mp];
+#pragma unroll
+    for (int t = 0; t < B; ++t) mu = fma(v[t], uw[cc + t], mu);
+    mt += (size_t)B * mp;
+  }
+  if (cc < n) {
+    const int r = n - cc;
+    double v[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) v[t] = mt[(size_t)(t < r ? t : r - 1) * mp];
+#pragma unroll
+    for (int t = 0; t < B; ++t) if (t < r) mu = fma(v[t], uw[cc + t], mu);
+  }
+  return mu;
+}
+template <int B>
+LMPC_DEVINL double chain_u(const double *__restrict__ mcol, const int *roww, const double *lamw, int k, int n, double uc) {
+  int i = 0;
+  for (; i + B <= k; i += B) {
+    double v[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) v[t] = mcol[(size_t)roww[i + t] * n];
+#pragma unroll
+    for (int t = 0; t < B; ++t) uc = fma(-lamw[i + t], v[t], uc);
+  }
+  if (i < k) {
+    const int r = k - i;
+    double v[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) v[t] = mcol[(size_t)roww[i + (t < r ? t : r - 1)] * n];
+#pragma unroll
+    for (int t = 0; t < B; ++t) if (t < r) uc = fma(-lamw[i + t], v[t], uc);
+  }
+  return uc;
+}
+
 // CTA-per-QP kernel.  NT threads per CTA (256: one QP per SM at full capacity; 128: two CTAs per SM
 // with a reduced capacity `cap`, overflowing instances are redone by a full-capacity pass, `redo`).
 //
@@ -1239,11 +1284,16 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
                 const int cc = tid + NT * h;
                 // a simple row w is zero before column w: fma(-lam, 0, uc) == uc, so those steps are skipped
                 // (K3_TRIM_U; the loads they would have issued are half of this phase's L2 traffic)
+#if K3_TRIM_U
 #pragma unroll K3_BCU
                 for (int i = 0; i < k; ++i) {
                   const int wr = c.roww[i];
-                  if (!K3_TRIM_U || wr <= cc || wr >= lay.ms) uc[h] = fma(-c.lamw[i], mcol[h][wr * n], uc[h]);
+                  if (wr <= cc || wr >= lay.ms) uc[h] = fma(-c.lamw[i], mcol[h][wr * n], uc[h]);
                 }
+#else
+                (void)cc;
+                uc[h] = chain_u<K3_BCU>(mcol[h], c.roww, c.lamw, k, n, uc[h]);
+#endif
               }
             }
           }
@@ -1301,8 +1351,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
             const int c0 = (tid + NT * (nmine - 1) < lay.ms) ? tid : 0;
             const double *mt = c.MT + tid + c0 * mp;
             if (nmine == 1) {
-#pragma unroll K3_BCU
-              for (int cc = c0; cc < n; ++cc) { mus[0] = fma(*mt, c.uw[cc], mus[0]); mt += mp; }
+              mus[0] = chain_scan<K3_BCU>(mt, c.uw, c0, n, mp, mus[0]);
             } else if (!K3_INTERLEAVE) {
 #pragma unroll
               for (int h = 0; h < RH; ++h) {
@@ -1310,8 +1359,7 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
                   const int j = tid + NT * h;
                   const int cj = (j < lay.ms) ? j : 0;
                   const double *mj = c.MT + j + cj * mp;
-#pragma unroll K3_BCU
-                  for (int cc = cj; cc < n; ++cc) { mus[h] = fma(*mj, c.uw[cc], mus[h]); mj += mp; }
+                  mus[h] = chain_scan<K3_BCU>(mj, c.uw, cj, n, mp, mus[h]);
                 }
               }
             } else {
