@@ -95,6 +95,12 @@ constexpr int K3_BCU = K3_BC_UNROLL;
 #ifndef K3_TRIM_U
 #define K3_TRIM_U 0
 #endif
+#ifndef K3_PAIR
+#define K3_PAIR 1            // a thread's two columns / rows run as interleaved chains
+#endif
+#ifndef K3_PAIR_B
+#define K3_PAIR_B 8          // block of the paired chains (2 * K3_PAIR_B loads in flight per thread)
+#endif
 #ifndef K3_USE_RING
 #define K3_USE_RING 0
 #endif
@@ -1036,6 +1042,49 @@ LMPC_DEVINL double chain_u(const double *__restrict__ mcol, const int *roww, con
   return uc;
 }
 
+// Two chains of one thread run together (a thread of a 128-thread CTA owns columns / rows tid and tid + 128 when n, m > 128):
+// the same two sequences of fmas, interleaved, so the thread's critical path is one chain instead of two.
+template <int B>
+LMPC_DEVINL void chain_scan2(const double *__restrict__ ma, const double *__restrict__ mb, const double *uw, int cc, int n,
+                             int mp, double &mua, double &mub) {
+  for (; cc + B <= n; cc += B) {
+    double va[B], vb[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) { va[t] = ma[(size_t)t * mp]; vb[t] = mb[(size_t)t * mp]; }
+#pragma unroll
+    for (int t = 0; t < B; ++t) { const double ucc = uw[cc + t]; mua = fma(va[t], ucc, mua); mub = fma(vb[t], ucc, mub); }
+    ma += (size_t)B * mp; mb += (size_t)B * mp;
+  }
+  if (cc < n) {
+    const int r = n - cc;
+    double va[B], vb[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) { const size_t o = (size_t)(t < r ? t : r - 1) * mp; va[t] = ma[o]; vb[t] = mb[o]; }
+#pragma unroll
+    for (int t = 0; t < B; ++t) if (t < r) { const double ucc = uw[cc + t]; mua = fma(va[t], ucc, mua); mub = fma(vb[t], ucc, mub); }
+  }
+}
+template <int B>
+LMPC_DEVINL void chain_u2(const double *__restrict__ ca, const double *__restrict__ cb, const int *roww, const double *lamw,
+                          int k, int n, double &ua, double &ub) {
+  int i = 0;
+  for (; i + B <= k; i += B) {
+    double va[B], vb[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) { const size_t o = (size_t)roww[i + t] * n; va[t] = ca[o]; vb[t] = cb[o]; }
+#pragma unroll
+    for (int t = 0; t < B; ++t) { const double li = -lamw[i + t]; ua = fma(li, va[t], ua); ub = fma(li, vb[t], ub); }
+  }
+  if (i < k) {
+    const int r = k - i;
+    double va[B], vb[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) { const size_t o = (size_t)roww[i + (t < r ? t : r - 1)] * n; va[t] = ca[o]; vb[t] = cb[o]; }
+#pragma unroll
+    for (int t = 0; t < B; ++t) if (t < r) { const double li = -lamw[i + t]; ua = fma(li, va[t], ua); ub = fma(li, vb[t], ub); }
+  }
+}
+
 // CTA-per-QP kernel.  NT threads per CTA (256: one QP per SM at full capacity; 128: two CTAs per SM
 // with a reduced capacity `cap`, overflowing instances are redone by a full-capacity pass, `redo`).
 //
@@ -1277,6 +1326,8 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
 #pragma unroll
               for (int h = 0; h < CH; ++h) uc[h] = fma(li, mcol[h][ro], uc[h]);
             }
+          } else if (!K3_TRIM_U && K3_PAIR && CH == 2 && nmine == 2) {
+            chain_u2<K3_PAIR_B>(mcol[0], mcol[CH - 1], c.roww, c.lamw, k, n, uc[0], uc[CH - 1]);
           } else {
 #pragma unroll
             for (int h = 0; h < CH; ++h) {
@@ -1352,6 +1403,13 @@ ldp_cta_kernel(const __grid_constant__ LdpLayout lay, const __grid_constant__ Ld
             const double *mt = c.MT + tid + c0 * mp;
             if (nmine == 1) {
               mus[0] = chain_scan<K3_BCU>(mt, c.uw, c0, n, mp, mus[0]);
+            } else if (K3_PAIR && nmine == 2 && RH >= 2 && tid + NT < lay.ms && tid + NT <= n && NT % K3_BCU == 0 && NT % K3_PAIR_B == 0) {
+              // rows j = tid and j + NT, both simple: row j alone on columns [j, j + NT), then both (row j + NT is zero before
+              // its own column, so starting it at any column <= j + NT adds exact zeros)
+              const double *ma = c.MT + tid + (size_t)tid * mp;
+              mus[0] = chain_scan<K3_BCU>(ma, c.uw, tid, tid + NT, mp, mus[0]);
+              chain_scan2<K3_PAIR_B>(ma + (size_t)NT * mp, c.MT + (tid + NT) + (size_t)(tid + NT) * mp, c.uw, tid + NT, n, mp,
+                                     mus[0], mus[1]);
             } else if (!K3_INTERLEAVE) {
 #pragma unroll
               for (int h = 0; h < RH; ++h) {
