@@ -1001,12 +1001,26 @@ LMPC_DEVINL void coop_sweep_bwd(const BigCtx &c, double *xs, int kk) {
 // leaves up to B - 1 remainder iterations that run one load at a time: each exposes a full L2 latency (~600 cycles under
 // load), 3.5 of them on average per chain and iteration.  Here the remainder's loads are issued together (indices
 // clamped into range, the surplus fmas predicated off): same operations on the same operands in the same order.
+#ifndef K3_PREFETCH
+#define K3_PREFETCH 0       // 1: L1 prefetch of the next block's operands behind the current block's loads (measured, r02:
+                            // chain s = 1 8.5e4 -> 5.9e4 solves/s, s = 0.25 8.8e5 -> 4.1e5: the ~30 KB of L1 left next to 2 x 110 KB
+                            // of shared memory thrash; kept off)
+#endif
+LMPC_DEVINL void pf_l1(const double *p) {
+#if K3_PREFETCH
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 template <int B>
 LMPC_DEVINL double chain_scan(const double *__restrict__ mt, const double *uw, int cc, int n, int mp, double mu) {
   for (; cc + B <= n; cc += B) {
     double v[B];
 #pragma unroll
     for (int t = 0; t < B; ++t) v[t] = mt[(size_t)t * mp];
+    if (K3_PREFETCH && cc + 2 * B <= n) {
+#pragma unroll
+      for (int t = 0; t < B; ++t) pf_l1(mt + (size_t)(B + t) * mp);
+    }
 #pragma unroll
     for (int t = 0; t < B; ++t) mu = fma(v[t], uw[cc + t], mu);
     mt += (size_t)B * mp;
@@ -1028,6 +1042,10 @@ LMPC_DEVINL double chain_u(const double *__restrict__ mcol, const int *roww, con
     double v[B];
 #pragma unroll
     for (int t = 0; t < B; ++t) v[t] = mcol[(size_t)roww[i + t] * n];
+    if (K3_PREFETCH && i + 2 * B <= k) {
+#pragma unroll
+      for (int t = 0; t < B; ++t) pf_l1(mcol + (size_t)roww[i + B + t] * n);
+    }
 #pragma unroll
     for (int t = 0; t < B; ++t) uc = fma(-lamw[i + t], v[t], uc);
   }
